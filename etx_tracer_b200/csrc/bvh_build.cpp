@@ -1,0 +1,232 @@
+// bvh_build.cpp — host-side binned-SAH BVH2 builder (replaces rtcCommitScene, sources/etx/rt/rt.cxx:66-88).
+// Deterministic: same input -> same nodes, so the oracle and the CUDA module traverse identical trees.
+#include "bvh_build.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace etxb {
+
+namespace {
+
+struct Box {
+  float lo[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
+  float hi[3] = {-std::numeric_limits<float>::max(), -std::numeric_limits<float>::max(), -std::numeric_limits<float>::max()};
+  void grow(const float* p) {
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = std::min(lo[k], p[k]);
+      hi[k] = std::max(hi[k], p[k]);
+    }
+  }
+  void grow(const Box& b) {
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = std::min(lo[k], b.lo[k]);
+      hi[k] = std::max(hi[k], b.hi[k]);
+    }
+  }
+  float half_area() const {
+    float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    if (dx < 0.0f) return 0.0f;
+    return dx * dy + dy * dz + dz * dx;
+  }
+};
+
+struct Builder {
+  const float* positions;
+  uint32_t position_stride;  // in floats
+  const uint32_t* indices;
+  uint32_t index_stride;  // in uint32
+  uint32_t tri_count;
+
+  std::vector<Box> tri_box;
+  std::vector<float> centroid;  // 3 * tri_count
+  std::vector<uint32_t> order;
+
+  std::vector<BvhNode> nodes;
+  std::vector<uint32_t> leaf_tris;  // slot -> original triangle index
+
+  static constexpr int kBins = 16;
+
+  const float* vertex(uint32_t tri, int k) const {
+    return positions + size_t(indices[size_t(tri) * index_stride + k]) * position_stride;
+  }
+
+  int32_t make_leaf(uint32_t begin, uint32_t end) {
+    uint32_t first = uint32_t(leaf_tris.size());
+    uint32_t count = end - begin;
+    for (uint32_t i = begin; i < end; ++i) leaf_tris.push_back(order[i]);
+    uint32_t ref = (first << 2) | (count - 1u);
+    return int32_t(~ref);
+  }
+
+  // returns child reference; writes bounds of the subtree into `bounds`
+  int32_t build(uint32_t begin, uint32_t end, Box& bounds, bool force_inner) {
+    bounds = Box();
+    Box cbox;
+    for (uint32_t i = begin; i < end; ++i) {
+      bounds.grow(tri_box[order[i]]);
+      cbox.grow(&centroid[size_t(order[i]) * 3]);
+    }
+    uint32_t count = end - begin;
+    if ((count <= uint32_t(kBvhMaxLeafTris)) && !force_inner) {
+      if (count <= 2u) return make_leaf(begin, end);
+    }
+
+    uint32_t mid = begin;
+    bool split_found = false;
+    if (count > 1u) {
+      float best_cost = std::numeric_limits<float>::max();
+      int best_axis = -1, best_bin = -1;
+      for (int axis = 0; axis < 3; ++axis) {
+        float cmin = cbox.lo[axis], cmax = cbox.hi[axis];
+        if (!(cmax > cmin)) continue;
+        Box bin_box[kBins];
+        uint32_t bin_count[kBins] = {};
+        float scale = float(kBins) / (cmax - cmin);
+        for (uint32_t i = begin; i < end; ++i) {
+          uint32_t t = order[i];
+          int b = std::min(kBins - 1, std::max(0, int((centroid[size_t(t) * 3 + axis] - cmin) * scale)));
+          bin_box[b].grow(tri_box[t]);
+          bin_count[b]++;
+        }
+        float right_area[kBins];
+        uint32_t right_count[kBins];
+        Box acc;
+        uint32_t cnt = 0;
+        for (int b = kBins - 1; b > 0; --b) {
+          acc.grow(bin_box[b]);
+          cnt += bin_count[b];
+          right_area[b] = acc.half_area();
+          right_count[b] = cnt;
+        }
+        acc = Box();
+        cnt = 0;
+        for (int b = 0; b < kBins - 1; ++b) {
+          acc.grow(bin_box[b]);
+          cnt += bin_count[b];
+          if (cnt == 0 || right_count[b + 1] == 0) continue;
+          float cost = acc.half_area() * float(cnt) + right_area[b + 1] * float(right_count[b + 1]);
+          if (cost < best_cost) {
+            best_cost = cost;
+            best_axis = axis;
+            best_bin = b;
+          }
+        }
+      }
+      if (best_axis >= 0) {
+        float leaf_cost = bounds.half_area() * float(count);
+        bool must_split = (count > uint32_t(kBvhMaxLeafTris)) || force_inner;
+        if (must_split || (best_cost + bounds.half_area() * 1.0f < leaf_cost)) {
+          float cmin = cbox.lo[best_axis], cmax = cbox.hi[best_axis];
+          float scale = float(kBins) / (cmax - cmin);
+          auto it = std::stable_partition(order.begin() + begin, order.begin() + end, [&](uint32_t t) {
+            int b = std::min(kBins - 1, std::max(0, int((centroid[size_t(t) * 3 + best_axis] - cmin) * scale)));
+            return b <= best_bin;
+          });
+          mid = uint32_t(it - order.begin());
+          split_found = (mid > begin) && (mid < end);
+        }
+      }
+      if (!split_found && ((count > uint32_t(kBvhMaxLeafTris)) || force_inner)) {
+        // degenerate centroids: median split in current order
+        mid = begin + count / 2u;
+        split_found = (mid > begin) && (mid < end);
+      }
+    }
+
+    if (!split_found) {
+      if (force_inner) {
+        // single triangle at the root: inner node with the leaf in child0 and an empty box in child1
+        uint32_t node_index = uint32_t(nodes.size());
+        nodes.emplace_back();
+        BvhNode n = {};
+        std::memcpy(n.lo0, bounds.lo, 12);
+        std::memcpy(n.hi0, bounds.hi, 12);
+        for (int k = 0; k < 3; ++k) {
+          n.lo1[k] = std::numeric_limits<float>::max();
+          n.hi1[k] = -std::numeric_limits<float>::max();
+        }
+        n.child0 = make_leaf(begin, end);
+        n.child1 = n.child0;
+        nodes[node_index] = n;
+        return int32_t(node_index);
+      }
+      return make_leaf(begin, end);
+    }
+
+    uint32_t node_index = uint32_t(nodes.size());
+    nodes.emplace_back();
+    Box b0, b1;
+    int32_t c0 = build(begin, mid, b0, false);
+    int32_t c1 = build(mid, end, b1, false);
+    BvhNode n = {};
+    std::memcpy(n.lo0, b0.lo, 12);
+    std::memcpy(n.hi0, b0.hi, 12);
+    std::memcpy(n.lo1, b1.lo, 12);
+    std::memcpy(n.hi1, b1.hi, 12);
+    n.child0 = c0;
+    n.child1 = c1;
+    nodes[node_index] = n;
+    return int32_t(node_index);
+  }
+};
+
+}  // namespace
+
+void build_bvh(const float* positions, uint32_t position_stride_bytes, const uint32_t* indices, uint32_t index_stride_bytes, uint32_t tri_count, Bvh& out) {
+  out.nodes.clear();
+  out.tri_pos.clear();
+  out.tri_index.clear();
+
+  Builder b;
+  b.positions = positions;
+  b.position_stride = position_stride_bytes / 4u;
+  b.indices = indices;
+  b.index_stride = index_stride_bytes / 4u;
+  b.tri_count = tri_count;
+
+  if (tri_count == 0) {
+    BvhNode n = {};
+    for (int k = 0; k < 3; ++k) {
+      n.lo0[k] = n.lo1[k] = std::numeric_limits<float>::max();
+      n.hi0[k] = n.hi1[k] = -std::numeric_limits<float>::max();
+    }
+    // both children point at an (empty-box) leaf that is never reached
+    n.child0 = n.child1 = int32_t(~0u);
+    out.nodes.push_back(n);
+    out.tri_pos.resize(3, F4{0, 0, 0, 0});
+    out.tri_index.push_back(0xffffffffu);
+    return;
+  }
+
+  b.tri_box.resize(tri_count);
+  b.centroid.resize(size_t(tri_count) * 3);
+  b.order.resize(tri_count);
+  for (uint32_t t = 0; t < tri_count; ++t) {
+    Box bx;
+    for (int k = 0; k < 3; ++k) bx.grow(b.vertex(t, k));
+    b.tri_box[t] = bx;
+    for (int k = 0; k < 3; ++k) b.centroid[size_t(t) * 3 + k] = 0.5f * (bx.lo[k] + bx.hi[k]);
+    b.order[t] = t;
+  }
+  b.nodes.reserve(tri_count);
+  b.leaf_tris.reserve(tri_count);
+
+  Box root_box;
+  b.build(0, tri_count, root_box, true);
+
+  out.nodes = std::move(b.nodes);
+  out.tri_index = std::move(b.leaf_tris);
+  out.tri_pos.resize(out.tri_index.size() * 3);
+  for (size_t s = 0; s < out.tri_index.size(); ++s) {
+    uint32_t t = out.tri_index[s];
+    for (int k = 0; k < 3; ++k) {
+      const float* p = b.vertex(t, k);
+      out.tri_pos[s * 3 + k] = F4{p[0], p[1], p[2], (k == 0) ? u2f(t) : 0.0f};
+    }
+  }
+}
+
+}  // namespace etxb

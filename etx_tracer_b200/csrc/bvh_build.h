@@ -1,0 +1,19 @@
+// bvh_build.h — host BVH container + builder entry point.
+#pragma once
+#include <vector>
+
+#include "bvh.h"
+
+namespace etxb {
+
+struct Bvh {
+  std::vector<BvhNode> nodes;       // nodes[0] is the root and always an inner node
+  std::vector<F4> tri_pos;          // 3 entries per leaf slot
+  std::vector<uint32_t> tri_index;  // leaf slot -> original triangle index
+};
+
+// positions: first 3 floats of each vertex record; indices: first 3 uint32 of each triangle record
+// (strides in bytes — the reference's Vertex is 56 B, Triangle 32 B: sources/etx/render/shared/math.hxx:599,607)
+void build_bvh(const float* positions, uint32_t position_stride_bytes, const uint32_t* indices, uint32_t index_stride_bytes, uint32_t tri_count, Bvh& out);
+
+}  // namespace etxb

@@ -1,0 +1,513 @@
+"""Deterministic synthetic scene generators for the BASELINE.json configs.
+
+They fill the reference's Scene/Camera PODs (etx_tracer_b200/structs.py) the way the reference's loader would
+(sources/etx/render/host/scene_representation.cxx: commit():420, add_area_emitters_for_triangle:840,
+build_emitters_distribution:2460, validate_materials:262, build_camera:579) so that the same arrays can be handed
+to the CUDA module (etxb_upload_scene) and to the CPU oracle.  No file IO besides the committed data tables.
+"""
+import math
+import os
+
+import numpy as np
+
+from . import structs as S
+
+f32 = np.float32
+DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+_tables = {}
+
+
+def tables(name):
+    if name not in _tables:
+        _tables[name] = dict(np.load(os.path.join(DATA_DIR, name + ".npz")))
+    return _tables[name]
+
+
+K_RGB_LUMINANCE_SCALE = np.array([0.817660332, 1.05418909, 1.09945524], dtype=f32)  # spectrum.hxx:450
+WAVELENGTHS = np.arange(390, 831, dtype=f32)
+
+
+def luminance(rgb):
+    rgb = np.asarray(rgb, dtype=f32)
+    return f32(f32(f32(rgb[0] * f32(0.212671)) + f32(rgb[1] * f32(0.715160))) + f32(rgb[2] * f32(0.072169)))  # math.hxx:729
+
+
+def _spd(power441, integrated):
+    s = np.zeros(1, dtype=S.SPECTRUM)
+    s["entries"]["wavelength"][0] = WAVELENGTHS
+    s["entries"]["power"][0] = np.asarray(power441, dtype=f32)
+    s["entry_count"] = 441
+    s["integrated"][0] = np.asarray(integrated, dtype=f32)
+    return s
+
+
+def spd_constant(value):
+    """SpectralDistribution::constant (render/host/spectrum.cxx:108-116)."""
+    return _spd(np.full(441, value, dtype=f32), [value, value, value])
+
+
+def spd_rgb_reflectance(rgb):
+    """SpectralDistribution::rgb_reflectance (spectrum.cxx:135-148) via rgb_response (spectrum.cxx:399-)."""
+    rgb = np.asarray(rgb, dtype=f32)
+    if luminance(rgb) == 0.0:
+        return spd_constant(0.0)
+    w = tables("color_tables")["rgb_response_391x3"].astype(f32)
+    p = (rgb[0] * w[:, 0]).astype(f32)
+    p = (p + (rgb[1] * w[:, 1]).astype(f32)).astype(f32)
+    p = (p + (rgb[2] * w[:, 2]).astype(f32)).astype(f32)
+    power = np.concatenate([p, np.full(441 - 391, p[-1], dtype=f32)])  # from_samples clamps beyond the last sample
+    return _spd(power, rgb)
+
+
+def spd_rgb_luminance(rgb):
+    """SpectralDistribution::rgb_luminance (spectrum.cxx:150-154)."""
+    rgb = np.asarray(rgb, dtype=f32)
+    s = spd_rgb_reflectance((rgb * K_RGB_LUMINANCE_SCALE).astype(f32))
+    s["integrated"][0] = rgb
+    return s
+
+
+def spd_named_ior(name):
+    t = tables("spectra")
+    eta = _spd(t[f"{name}.eta_power"], t[f"{name}.eta_rgb"])
+    k = _spd(t[f"{name}.k_power"], t[f"{name}.k_rgb"])
+    return eta, k, int(t[f"{name}.cls"][0])
+
+
+def spd_named_emission(name):
+    t = tables("spectra")
+    return _spd(t[f"{name}.power"], t[f"{name}.rgb"])
+
+
+class SceneData:
+    """Owns every array a Scene POD points to."""
+
+    def __init__(self):
+        self.vertices = []
+        self.triangles = []
+        self.materials = []
+        self.spectra = []
+        self.material_names = {}
+        self.scene = np.zeros(1, dtype=S.SCENE)
+        self.camera = np.zeros(1, dtype=S.CAMERA)
+        self.name = ""
+        self._keep = []
+
+    # -- spectra / materials ---------------------------------------------------------------------
+    def add_spectrum(self, spd):
+        self.spectra.append(spd)
+        return len(self.spectra) - 1
+
+    def add_material(self, name, cls=S.MAT_DIFFUSE, kd=None, ks=None, roughness=0.0, emission=None, two_sided=0, int_ior=None,
+                     thinfilm=None, collimation=0.0, int_medium=S.INVALID, ext_medium=S.INVALID, diffuse_variation=0):
+        m = np.zeros(1, dtype=S.MATERIAL)
+        for fld in ("reflectance", "scattering", "emission"):
+            m[fld]["spectrum_index"] = S.INVALID
+            m[fld]["image_index"] = S.INVALID
+        for fld in ("roughness", "metalness", "transmission"):
+            m[fld]["image_index"] = S.INVALID
+            m[fld]["channel"] = S.INVALID
+        m["subsurface"]["spectrum_index"] = S.INVALID
+        m["subsurface"]["image_index"] = S.INVALID
+        m["thinfilm"]["ior"]["eta_index"] = S.INVALID
+        m["thinfilm"]["ior"]["k_index"] = S.INVALID
+        m["thinfilm"]["thickness_image"] = S.INVALID
+        for fld in ("ext_ior", "int_ior"):
+            m[fld]["eta_index"] = S.INVALID
+            m[fld]["k_index"] = S.INVALID
+        m["cls"] = cls
+        m["int_medium"] = int_medium
+        m["ext_medium"] = ext_medium
+        m["normal_image_index"] = S.INVALID
+        m["diffuse_variation"] = diffuse_variation
+        m["two_sided"] = two_sided
+        m["normal_scale"] = 1.0
+        m["opacity"] = 1.0
+        m["emission_collimation"] = collimation
+        if kd is not None:
+            m["scattering"]["spectrum_index"] = self.add_spectrum(spd_rgb_reflectance(kd))
+        if ks is not None:
+            m["reflectance"]["spectrum_index"] = self.add_spectrum(spd_rgb_reflectance(ks))
+        r2 = f32(roughness) * f32(roughness)  # "Pr" is squared by the loader (scene_representation.cxx:1731-1738)
+        m["roughness"]["value"][0][:2] = r2
+        if emission is not None:
+            m["emission"]["spectrum_index"] = self.add_spectrum(emission)
+        if int_ior is not None:
+            eta, k, cls_ior = spd_named_ior(int_ior)
+            m["int_ior"]["cls"] = cls_ior
+            m["int_ior"]["eta_index"] = self.add_spectrum(eta)
+            m["int_ior"]["k_index"] = self.add_spectrum(k)
+        if thinfilm is not None:
+            name_ior, tmin, tmax = thinfilm
+            eta, k, cls_ior = spd_named_ior(name_ior)
+            m["thinfilm"]["ior"]["cls"] = cls_ior
+            m["thinfilm"]["ior"]["eta_index"] = self.add_spectrum(eta)
+            m["thinfilm"]["ior"]["k_index"] = self.add_spectrum(k)
+            m["thinfilm"]["min_thickness"] = tmin
+            m["thinfilm"]["max_thickness"] = tmax
+        self.materials.append(m)
+        self.material_names[name] = len(self.materials) - 1
+        return len(self.materials) - 1
+
+    # -- geometry --------------------------------------------------------------------------------
+    def add_mesh(self, positions, normals, indices, material_index, uvs=None):
+        positions = np.asarray(positions, dtype=f32).reshape(-1, 3)
+        normals = np.asarray(normals, dtype=f32).reshape(-1, 3)
+        indices = np.asarray(indices, dtype=np.uint32).reshape(-1, 3)
+        n = positions.shape[0]
+        v = np.zeros(n, dtype=S.VERTEX)
+        v["pos"] = positions
+        nl = np.linalg.norm(normals, axis=1, keepdims=True).astype(f32)
+        nrm = (normals / np.maximum(nl, f32(1e-20))).astype(f32)
+        v["nrm"] = nrm
+        # tangent frame: any vector orthogonal to the normal (the loader runs MikkTSpace; a fixed rule is enough here)
+        helper = np.where(np.abs(nrm[:, 1:2]) < 0.9, np.array([[0, 1, 0]], dtype=f32), np.array([[1, 0, 0]], dtype=f32))
+        tan = np.cross(helper, nrm).astype(f32)
+        tan = (tan / np.linalg.norm(tan, axis=1, keepdims=True)).astype(f32)
+        btn = np.cross(nrm, tan).astype(f32)
+        btn = (btn / np.linalg.norm(btn, axis=1, keepdims=True)).astype(f32)
+        v["tan"] = tan
+        v["btn"] = btn
+        if uvs is not None:
+            v["tex"] = np.asarray(uvs, dtype=f32).reshape(-1, 2)
+        base = sum(a.shape[0] for a in self.vertices)
+        t = np.zeros(indices.shape[0], dtype=S.TRIANGLE)
+        t["i"] = indices + np.uint32(base)
+        t["material_index"] = material_index
+        p0, p1, p2 = positions[indices[:, 0]], positions[indices[:, 1]], positions[indices[:, 2]]
+        gn = np.cross(p1 - p0, p2 - p0).astype(f32)
+        gl = np.linalg.norm(gn, axis=1, keepdims=True).astype(f32)
+        t["geo_n"] = (gn / np.maximum(gl, f32(1e-30))).astype(f32)
+        self.vertices.append(v)
+        self.triangles.append(t)
+
+    def add_quad(self, p0, p1, p2, p3, material_index, subdiv=1):
+        """Quad p0,p1,p2,p3 (counter-clockwise seen from the side the normal points to), optionally tessellated."""
+        p0, p1, p2, p3 = [np.asarray(p, dtype=np.float64) for p in (p0, p1, p2, p3)]
+        n = np.cross(p1 - p0, p3 - p0)
+        n = n / np.linalg.norm(n)
+        s = subdiv
+        us, vs = np.meshgrid(np.linspace(0, 1, s + 1), np.linspace(0, 1, s + 1), indexing="xy")
+        us, vs = us.reshape(-1, 1), vs.reshape(-1, 1)
+        pos = (1 - us) * (1 - vs) * p0 + us * (1 - vs) * p1 + us * vs * p2 + (1 - us) * vs * p3
+        idx = []
+        for j in range(s):
+            for i in range(s):
+                a = j * (s + 1) + i
+                b, c, d = a + 1, a + s + 2, a + s + 1
+                idx.append((a, b, c))
+                idx.append((a, c, d))
+        self.add_mesh(pos, np.tile(n, (pos.shape[0], 1)), np.array(idx), material_index, uvs=np.hstack([us, vs]))
+
+    def add_box(self, center, half, yaw_deg, material_index, subdiv=1):
+        c = np.asarray(center, dtype=np.float64)
+        hx, hy, hz = half
+        a = math.radians(yaw_deg)
+        rot = np.array([[math.cos(a), 0, math.sin(a)], [0, 1, 0], [-math.sin(a), 0, math.cos(a)]])
+
+        def P(x, y, z):
+            return c + rot @ np.array([x * hx, y * hy, z * hz])
+
+        self.add_quad(P(-1, 1, 1), P(1, 1, 1), P(1, 1, -1), P(-1, 1, -1), material_index, subdiv)      # top
+        self.add_quad(P(-1, -1, -1), P(1, -1, -1), P(1, -1, 1), P(-1, -1, 1), material_index, subdiv)  # bottom
+        self.add_quad(P(-1, -1, 1), P(1, -1, 1), P(1, 1, 1), P(-1, 1, 1), material_index, subdiv)      # +z
+        self.add_quad(P(1, -1, -1), P(-1, -1, -1), P(-1, 1, -1), P(1, 1, -1), material_index, subdiv)  # -z
+        self.add_quad(P(1, -1, 1), P(1, -1, -1), P(1, 1, -1), P(1, 1, 1), material_index, subdiv)      # +x
+        self.add_quad(P(-1, -1, -1), P(-1, -1, 1), P(-1, 1, 1), P(-1, 1, -1), material_index, subdiv)  # -x
+
+    def add_uv_sphere(self, center, radius, segments, rings, material_index, displace=None):
+        """UV sphere with 2*segments*(rings-1) triangles, smooth normals."""
+        c = np.asarray(center, dtype=np.float64)
+        pos, nrm, uv = [], [], []
+        for r in range(rings + 1):
+            theta = math.pi * r / rings
+            for s in range(segments + 1):
+                phi = 2.0 * math.pi * s / segments
+                d = np.array([math.sin(theta) * math.cos(phi), math.cos(theta), math.sin(theta) * math.sin(phi)])
+                rr = radius if displace is None else radius * displace(d)
+                pos.append(c + rr * d)
+                nrm.append(d)
+                uv.append((s / segments, r / rings))
+        idx = []
+        for r in range(rings):
+            for s in range(segments):
+                a = r * (segments + 1) + s
+                b = a + 1
+                d = a + segments + 1
+                e = d + 1
+                if r != 0:
+                    idx.append((a, b, d))  # outward-facing winding (counter-clockwise from outside)
+                if r != rings - 1:
+                    idx.append((b, e, d))
+        self.add_mesh(np.array(pos), np.array(nrm), np.array(idx), material_index, uvs=np.array(uv))
+
+    # -- finalisation ----------------------------------------------------------------------------
+    def set_camera(self, origin, target, up, width, height, fov_deg, clip_near=1.0 / 256.0, clip_far=1024.0, lens_radius=0.0, focal_distance=0.0):
+        """build_camera (scene_representation.cxx:579-598) with float32 arithmetic."""
+        cam = self.camera
+        cam[:] = 0
+        cam["clip_near"] = clip_near
+        cam["clip_far"] = clip_far
+        cam["lens_image"] = S.INVALID
+        cam["medium_index"] = S.INVALID
+        cam["lens_radius"] = lens_radius
+        cam["focal_distance"] = focal_distance
+        o, t, u = [np.asarray(x, dtype=f32) for x in (origin, target, up)]
+
+        def nz(v):
+            return (v / f32(math.sqrt(float(np.dot(v, v))))).astype(f32)
+
+        f = nz(t - o)
+        s = nz(np.cross(f, u).astype(f32))
+        uu = np.cross(s, f).astype(f32)
+        view = np.zeros((4, 4), dtype=f32)  # view[col][row]
+        view[0][0], view[1][0], view[2][0] = s
+        view[0][1], view[1][1], view[2][1] = uu
+        view[0][2], view[1][2], view[2][2] = -f
+        view[3][0] = -np.dot(s, o)
+        view[3][1] = -np.dot(uu, o)
+        view[3][2] = np.dot(f, o)
+        view[3][3] = 1.0
+        fov = f32(fov_deg) * f32(math.pi) / f32(180.0)
+        w = f32(math.cos(0.5 * float(fov)) / math.sin(0.5 * float(fov)))
+        aspect = f32(width) / f32(height)
+        zn, zf = f32(clip_near), f32(clip_far)
+        proj = np.zeros((4, 4), dtype=f32)
+        proj[0][0] = w
+        proj[1][1] = w * aspect
+        proj[2][2] = zf / (zn - zf)
+        proj[2][3] = -1.0
+        proj[3][2] = -(zf * zn) / (zf - zn)
+        # column-major product proj * view: result.col[j] = sum_k proj.col[k] * view.col[j][k]
+        vp = np.zeros((4, 4), dtype=f32)
+        for j in range(4):
+            acc = np.zeros(4, dtype=f32)
+            for k in range(4):
+                acc = (acc + proj[k] * view[j][k]).astype(f32)
+            vp[j] = acc
+        cam["view_proj"][0] = vp.reshape(-1)
+        cam["target"][0] = t
+        cam["position"][0] = o  # inverse(view).col[3] == origin
+        cam["side"][0] = s
+        cam["up"][0] = uu
+        cam["direction"][0] = f
+        cam["tan_half_fov"] = f32(1.0) / abs(w)
+        cam["aspect"] = proj[1][1] / proj[0][0]
+        thf = cam["tan_half_fov"][0]
+        cam["area"] = (f32(2.0) * thf) * (f32(2.0) * thf / cam["aspect"][0])
+        cam["film_size"][0] = (width, height)
+        cam["image_plane"] = f32(width) / (f32(2.0) * thf)
+
+    def finalize(self, samples, spectral, max_path_length=1023, min_path_length=0, random_path_termination=6):
+        """validate_materials + commit + rebuild_area_emitters + build_emitters_distribution."""
+        sc = self.scene
+        sc[:] = 0
+        white = self.add_spectrum(spd_rgb_reflectance([1.0, 1.0, 1.0]))
+        black = self.add_spectrum(spd_constant(0.0))
+        one = self.add_spectrum(spd_constant(1.0))
+        sss = self.add_spectrum(spd_rgb_reflectance([1.0, 0.2, 0.04]))
+        glass_eta, glass_k, _ = spd_named_ior("glass")
+        def_diel = self.add_spectrum(glass_eta)
+        gold_eta, gold_k, _ = spd_named_ior("gold")
+        def_cond_eta, def_cond_k = self.add_spectrum(gold_eta), self.add_spectrum(gold_k)
+        for m in self.materials:
+            if m["reflectance"]["spectrum_index"][0] == S.INVALID:
+                m["reflectance"]["spectrum_index"] = white
+            if m["scattering"]["spectrum_index"][0] == S.INVALID:
+                m["scattering"]["spectrum_index"] = white
+            if m["subsurface"]["spectrum_index"][0] == S.INVALID:
+                m["subsurface"]["spectrum_index"] = sss
+            if m["emission"]["spectrum_index"][0] == S.INVALID:
+                m["emission"]["spectrum_index"] = black
+            r = m["roughness"]["value"][0]
+            if r[0] > 0 or r[1] > 0:
+                r[0] = max(f32(1e-6), r[0])
+                r[1] = max(f32(1e-6), r[1])
+            if m["int_ior"]["eta_index"][0] == S.INVALID:
+                m["int_ior"]["eta_index"] = def_cond_eta if m["cls"][0] == S.MAT_CONDUCTOR else def_diel
+            if m["int_ior"]["k_index"][0] == S.INVALID:
+                m["int_ior"]["k_index"] = def_cond_k if m["cls"][0] == S.MAT_CONDUCTOR else black
+            if m["thinfilm"]["ior"]["k_index"][0] == S.INVALID:
+                m["thinfilm"]["ior"]["k_index"] = black
+            if m["thinfilm"]["ior"]["eta_index"][0] == S.INVALID:
+                m["thinfilm"]["ior"]["eta_index"] = one
+
+        self.a_vertices = np.concatenate(self.vertices) if self.vertices else np.zeros(0, S.VERTEX)
+        self.a_triangles = np.concatenate(self.triangles) if self.triangles else np.zeros(0, S.TRIANGLE)
+        self.a_materials = np.concatenate(self.materials)
+        self.a_spectra = np.concatenate(self.spectra)
+        nt = self.a_triangles.shape[0]
+
+        # bounding sphere (commit():431-444)
+        tri_pos = self.a_vertices["pos"][self.a_triangles["i"].reshape(-1)]
+        bmin, bmax = tri_pos.min(axis=0).astype(f32), tri_pos.max(axis=0).astype(f32)
+        center = (f32(0.5) * (bmin + bmax)).astype(f32)
+        d = (bmax - center).astype(f32)
+        radius = f32(math.sqrt(float(f32(f32(f32(d[0] * d[0]) + f32(d[1] * d[1])) + f32(d[2] * d[2])))))
+
+        # area emitters (add_area_emitters_for_triangle:840-903)
+        tri_to_emitter = np.full(nt, S.INVALID, dtype=np.uint32)
+        profiles, instances, mat_to_profile = [], [], {}
+        lum = {}
+        for ti in range(nt):
+            mi = int(self.a_triangles["material_index"][ti])
+            m = self.a_materials[mi]
+            si = int(m["emission"]["spectrum_index"])
+            if si not in lum:
+                lum[si] = luminance(self.a_spectra["integrated"][si])
+            if lum[si] <= 0.0:
+                continue
+            i0, i1, i2 = self.a_triangles["i"][ti]
+            p0, p1, p2 = self.a_vertices["pos"][i0], self.a_vertices["pos"][i1], self.a_vertices["pos"][i2]
+            cr = np.cross((p1 - p0).astype(f32), (p2 - p0).astype(f32)).astype(f32)
+            area = f32(0.5) * f32(math.sqrt(float(np.dot(cr, cr))))
+            add_w = f32((2.0 if m["two_sided"] else 1.0)) * f32(area * f32(math.pi)) * f32(1.0)
+            if mi not in mat_to_profile:
+                p = np.zeros(1, dtype=S.EMITTER_PROFILE)
+                p["emission"] = m["emission"]
+                p["cls"] = S.EMITTER_AREA
+                p["angular_size_cosine"] = 1.0
+                mat_to_profile[mi] = len(profiles)
+                profiles.append(p)
+            e = np.zeros(1, dtype=S.EMITTER)
+            e["cls"] = S.EMITTER_AREA
+            e["profile"] = mat_to_profile[mi]
+            e["triangle_index"] = ti
+            e["triangle_area"] = area
+            e["additional_weight"] = add_w
+            e["spectrum_weight"] = lum[si]
+            tri_to_emitter[ti] = len(instances)
+            instances.append(e)
+        for (p, e) in getattr(self, "_distant_emitters", []):
+            e = e.copy()
+            e["profile"] = len(profiles)
+            e["additional_weight"] = f32(math.pi) * radius * radius
+            e["spectrum_weight"] = luminance(self.a_spectra["integrated"][int(p["emission"]["spectrum_index"][0])])
+            profiles.append(p)
+            instances.append(e)
+        assert instances, "scene needs at least one emitter (the loader would synthesise an atmosphere otherwise)"
+        self.a_profiles = np.concatenate(profiles)
+        self.a_emitters = np.concatenate(instances)
+        self.a_tri_to_emitter = tri_to_emitter
+
+        # emitter distribution (DistributionBuilder::finalize, distribution_builder.hxx:30-58)
+        ne = self.a_emitters.shape[0]
+        dist = np.zeros(ne + 1, dtype=S.DIST_ENTRY)
+        total = f32(0.0)
+        env = []
+        for i in range(ne):
+            w = f32(self.a_emitters["spectrum_weight"][i] * self.a_emitters["additional_weight"][i])
+            dist["value"][i] = w
+            dist["cdf"][i] = total
+            total = f32(total + w)
+            if self.a_emitters["cls"][i] != S.EMITTER_AREA and w > 0:
+                env.append(i)
+        dist["pdf"][:ne] = (dist["value"][:ne] / total).astype(f32)
+        dist["cdf"][:ne] = (dist["cdf"][:ne] / total).astype(f32)
+        dist["cdf"][ne] = 1.0
+        self.a_dist = dist
+
+        def view(field, arr):
+            sc[field]["a"] = arr.ctypes.data if arr.size else 0
+            sc[field]["count"] = arr.shape[0]
+
+        view("vertices", self.a_vertices)
+        view("triangles", self.a_triangles)
+        view("triangle_to_emitter", self.a_tri_to_emitter)
+        view("materials", self.a_materials)
+        view("emitter_profiles", self.a_profiles)
+        view("emitter_instances", self.a_emitters)
+        self.a_images = getattr(self, "a_images", np.zeros(0, dtype=S.IMAGE))
+        self.a_mediums = getattr(self, "a_mediums", np.zeros(0, dtype=S.MEDIUM))
+        view("images", self.a_images)
+        view("mediums", self.a_mediums)
+        view("spectrums", self.a_spectra)
+        sc["emitters_distribution"]["values"]["a"] = dist.ctypes.data
+        sc["emitters_distribution"]["values"]["count"] = ne + 1
+        sc["emitters_distribution"]["total_weight"] = total
+        sc["environment_emitter_count"] = len(env)
+        for k, i in enumerate(env):
+            sc["environment_emitters"][0][k] = i
+        sc["bounding_sphere_center"][0] = center
+        sc["bounding_sphere_radius"] = radius
+        sc["pixel_sampler_image"] = S.INVALID
+        sc["pixel_sampler_radius"] = 1.5
+        sc["min_path_length"] = min_path_length
+        sc["max_path_length"] = max_path_length
+        sc["samples"] = samples
+        sc["random_path_termination"] = random_path_termination
+        sc["noise_threshold"] = 0.1
+        sc["radiance_clamp"] = 0.0
+        sc["black_spectrum"] = black
+        sc["white_spectrum"] = white
+        for fld in ("rayleigh_spectrum", "mie_spectrum", "ozone_spectrum", "subsurface_scatter_material", "subsurface_exit_material"):
+            sc[fld] = S.INVALID
+        sc["default_dielectric_eta"] = def_diel
+        sc["default_conductor_eta"] = def_cond_eta
+        sc["default_conductor_k"] = def_cond_k
+        sc["flags"] = S.SCENE_COMMITTED | (S.SCENE_SPECTRAL if spectral else 0)
+        return self
+
+    @property
+    def width(self):
+        return int(self.camera["film_size"][0][0])
+
+    @property
+    def height(self):
+        return int(self.camera["film_size"][0][1])
+
+    @property
+    def triangle_count(self):
+        return int(self.a_triangles.shape[0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configs
+# ---------------------------------------------------------------------------------------------------
+def cornell_box(width=512, height=512, samples=16, spectral=False, sphere=False, sphere_segments=128, sphere_rings=81, wall_subdiv=1,
+                sphere_roughness=0.0, max_path_length=1023, tall_box_material="diffuse"):
+    """C1 (sphere=False, spectral=False) / C2 (sphere=True, spectral=True): SURVEY.md §8(d).
+
+    Closed box x,z in [-1,1], y in [0,2] (the reference asset's dimensions, bin/assets/cornellbox/cornellbox.json:9-34 camera),
+    all-diffuse walls and two boxes, one `light` quad emitter (color 10.018 3.918 0.932, two-sided).
+    """
+    sd = SceneData()
+    sd.name = "cornell" + ("+sphere" if sphere else "") + ("/spectral" if spectral else "/rgb")
+    white = sd.add_material("white", kd=[1.0, 1.0, 1.0], two_sided=1)
+    grey = sd.add_material("grey", kd=[0.906, 0.906, 0.906], two_sided=1)
+    red = sd.add_material("leftWall", kd=[1.0, 0.0, 0.0], two_sided=1)
+    green = sd.add_material("rightWall", kd=[0.0, 1.0, 0.0], two_sided=1)
+    light = sd.add_material("light", kd=[0.0, 0.0, 0.0], emission=spd_rgb_luminance([10.018, 3.918, 0.932]), two_sided=1)
+    s = wall_subdiv
+    zf = 4.0  # the box is closed behind the camera (camera sits at z = 3.82)
+    sd.add_quad([-1, 0, zf], [1, 0, zf], [1, 0, -1], [-1, 0, -1], white, s)    # floor (normal +y)
+    sd.add_quad([-1, 2, -1], [1, 2, -1], [1, 2, zf], [-1, 2, zf], white, s)    # ceiling (normal -y)
+    sd.add_quad([-1, 0, -1], [1, 0, -1], [1, 2, -1], [-1, 2, -1], grey, s)     # back wall (normal +z)
+    sd.add_quad([-1, 0, zf], [-1, 0, -1], [-1, 2, -1], [-1, 2, zf], red, s)    # left wall (normal +x)
+    sd.add_quad([1, 0, -1], [1, 0, zf], [1, 2, zf], [1, 2, -1], green, s)      # right wall (normal -x)
+    sd.add_quad([-1, 0, zf], [-1, 2, zf], [1, 2, zf], [1, 0, zf], grey, s)     # wall behind the camera (normal -z)
+    sd.add_quad([-0.24, 1.98, -0.22], [0.23, 1.98, -0.22], [0.23, 1.98, 0.16], [-0.24, 1.98, 0.16], light, 1)  # light (normal -y)
+    if tall_box_material == "diffuse":
+        tall = grey
+    else:
+        tall = sd.add_material("tallBox", cls=S.MAT_CONDUCTOR, ks=[1, 1, 1], int_ior="silver", two_sided=1)
+    sd.add_box([-0.33, 0.6, -0.29], (0.3, 0.6, 0.3), 17.0, tall, s)
+    if sphere:
+        glass = sd.add_material("glass", cls=S.MAT_DIELECTRIC, roughness=sphere_roughness, int_ior="glass")
+        sd.add_uv_sphere([0.33, 0.301, 0.35], 0.3, sphere_segments, sphere_rings, glass)
+    else:
+        sd.add_box([0.33, 0.3, 0.35], (0.3, 0.3, 0.3), -17.0, grey, s)
+    sd.set_camera([0.0, 1.0, 3.82], [0.0, 1.0, -6.18], [0.0, 1.0, 0.0], width, height, 39.597755335771296, clip_near=0.1, clip_far=100.0)
+    return sd.finalize(samples=samples, spectral=spectral, max_path_length=max_path_length)
+
+
+def config(name, scale=1.0):
+    """Named BASELINE.json configs. `scale` < 1 shrinks resolution for CPU-sized tests (geometry unchanged)."""
+    def dim(v):
+        return max(16, int(round(v * scale)))
+    if name == "C1":
+        return cornell_box(dim(512), dim(512), samples=16, spectral=False, sphere=False)
+    if name == "C2":
+        return cornell_box(dim(1024), dim(1024), samples=256, spectral=True, sphere=True)
+    raise KeyError(name)

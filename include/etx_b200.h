@@ -1,0 +1,363 @@
+/* etx_b200.h — C ABI of the B200-native wavefront VCM module (libetx_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of serhii-rieznik/etx-tracer: everything the reference's
+ * CPU VCM integrator does between `CPUVCM::run()` and the film (sources/etx/rt/integrators/vcm_cpu.cxx:81-241,
+ * vcm_shared.cxx:49-152, sources/etx/rt/shared/vcm_shared.hxx, sources/etx/rt/rt.cxx:327-579).
+ * A host adapter `GPUVCM : Integrator` (etx_tracer_b200/host/gpu_vcm.hpp) forwards the reference's
+ * Integrator vtable (sources/etx/rt/integrators/integrator.hxx:12-98) to these calls; INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions: plain C, no C++/torch types; all functions return 0 on success or a negative etxb_error;
+ * the caller owns every host buffer it passes, the module owns all device memory; one context drives one
+ * CUDA device (one process per GPU; multi-GPU sharding is expressed with etxb_set_partition + the
+ * exchange buffers below, the collective itself is issued by the host with NCCL).
+ *
+ * The scene is passed in the reference's OWN in-memory layout (struct etx::Scene, 528 B, and
+ * struct etx::Camera, 176 B — sources/etx/render/shared/scene.hxx:22-65, camera.hxx:8-39), so the
+ * reference-side call is `etxb_upload_scene(ctx, &rt.scene(), sizeof(Scene), &rt.camera(), sizeof(Camera))`.
+ * The etxb_* structs below are byte-compatible C mirrors of those PODs for callers that are not the
+ * reference (tests, bench); oracle/layout_check.cxx static_asserts every offset against the real headers.
+ */
+#ifndef ETX_B200_H
+#define ETX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ETXB_INVALID_INDEX 0xffffffffu
+
+typedef enum etxb_error {
+  ETXB_OK = 0,
+  ETXB_ERR_INVALID_ARGUMENT = -1,
+  ETXB_ERR_NO_DEVICE = -2,
+  ETXB_ERR_CUDA = -3,
+  ETXB_ERR_UNSUPPORTED = -4,
+  ETXB_ERR_NOT_READY = -5,
+  ETXB_ERR_OUT_OF_MEMORY = -6,
+  ETXB_ERR_OVERFLOW = -7
+} etxb_error;
+
+/* ---- byte-compatible mirrors of the reference PODs ------------------------------------------------ */
+
+/* etx::ArrayView<T> (base.hxx:52-56) */
+typedef struct etxb_array_view {
+  const void* a;
+  uint64_t count;
+} etxb_array_view;
+
+/* etx::Vertex (math.hxx:599), 56 B */
+typedef struct etxb_vertex {
+  float pos[3], nrm[3], tan[3], btn[3], tex[2];
+} etxb_vertex;
+
+/* etx::Triangle (math.hxx:607), 32 B */
+typedef struct etxb_triangle {
+  uint32_t i[3];
+  uint32_t material_index;
+  float geo_n[3];
+  float pad;
+} etxb_triangle;
+
+/* etx::SpectralImage / SampledImage / RefractiveIndex / Thinfilm / SubsurfaceMaterial (material.hxx:8-50) */
+typedef struct etxb_spectral_image {
+  uint32_t spectrum_index, image_index;
+} etxb_spectral_image;
+typedef struct etxb_sampled_image {
+  float value[4];
+  uint32_t image_index, channel;
+} etxb_sampled_image;
+typedef struct etxb_refractive_index {
+  uint32_t cls, eta_index, k_index;
+} etxb_refractive_index;
+typedef struct etxb_thinfilm {
+  etxb_refractive_index ior;
+  uint32_t thickness_image;
+  float min_thickness, max_thickness, pad;
+} etxb_thinfilm;
+typedef struct etxb_subsurface {
+  uint32_t spectrum_index, image_index, cls, path;
+} etxb_subsurface;
+
+/* etx::Material::Class (material.hxx:53-68) */
+enum {
+  ETXB_MAT_DIFFUSE = 0,
+  ETXB_MAT_TRANSLUCENT = 1,
+  ETXB_MAT_PLASTIC = 2,
+  ETXB_MAT_CONDUCTOR = 3,
+  ETXB_MAT_DIELECTRIC = 4,
+  ETXB_MAT_THINFILM = 5,
+  ETXB_MAT_MIRROR = 6,
+  ETXB_MAT_BOUNDARY = 7,
+  ETXB_MAT_VELVET = 8,
+  ETXB_MAT_PRINCIPLED = 9,
+  ETXB_MAT_VOID = 10
+};
+
+/* etx::Material (material.hxx:52-97), 200 B */
+typedef struct etxb_material {
+  etxb_spectral_image reflectance, scattering, emission;
+  etxb_sampled_image roughness, metalness, transmission;
+  etxb_subsurface subsurface;
+  etxb_thinfilm thinfilm;
+  etxb_refractive_index ext_ior, int_ior;
+  uint32_t cls, int_medium, ext_medium, normal_image_index, diffuse_variation, two_sided;
+  float normal_scale, opacity, emission_collimation;
+} etxb_material;
+
+/* etx::EmitterProfile (emitter.hxx:7-42), 48 B; Class: 0 Area, 1 Environment, 2 Directional */
+typedef struct etxb_emitter_profile {
+  etxb_spectral_image emission;
+  float direction[3];
+  uint32_t cls;
+  float angular_size, equivalent_disk_size, angular_size_cosine, pad0, pad1, pad2;
+} etxb_emitter_profile;
+
+/* etx::Emitter (emitter.hxx:44-71), 32 B */
+typedef struct etxb_emitter {
+  uint32_t cls, profile, triangle_index;
+  float spectrum_weight, additional_weight, triangle_area, pad0, pad1;
+} etxb_emitter;
+
+/* etx::SpectralDistribution (spectrum.hxx:449-), 3552 B */
+typedef struct etxb_spectrum {
+  struct {
+    float wavelength, power;
+  } entries[441];
+  uint32_t entry_count;
+  float integrated[3];
+  uint32_t pad[2];
+} etxb_spectrum;
+
+/* etx::Distribution::Entry / Distribution (distribution.hxx:7-15) */
+typedef struct etxb_distribution_entry {
+  float value, pdf, cdf;
+} etxb_distribution_entry;
+typedef struct etxb_distribution {
+  etxb_array_view values; /* etxb_distribution_entry[count] */
+  float total_weight;
+  uint32_t pad[3];
+} etxb_distribution;
+
+/* etx::Image (image.hxx:8-50), 112 B; format 1 = RGBA32F, 2 = RGBA8 */
+typedef struct etxb_image {
+  etxb_array_view pixels;
+  etxb_array_view x_distributions; /* etxb_distribution[isize.y] */
+  etxb_distribution y_distribution;
+  float fsize[2], offset[2], scale[2];
+  uint32_t isize[2];
+  float normalization;
+  uint32_t options, format, data_size;
+} etxb_image;
+
+/* etx::Medium (medium.hxx:8-47), 80 B */
+typedef struct etxb_medium {
+  etxb_array_view density; /* float[dx*dy*dz], normalised to max 1 */
+  float bounds_min[3], bounds_pad0, bounds_max[3], bounds_pad1;
+  uint16_t cls, enable_explicit_connections;
+  uint32_t absorption_index, scattering_index;
+  float phase_function_g, max_sigma;
+  uint32_t dimensions[3];
+} etxb_medium;
+
+/* etx::Camera (camera.hxx:8-39), 176 B; cls 0 = Perspective, 1 = Equirectangular */
+typedef struct etxb_camera {
+  float view_proj[16]; /* column-major float4 col[4] */
+  float position[3];
+  uint32_t cls;
+  float target[3], tan_half_fov;
+  float side[3], aspect;
+  float up[3], area;
+  float direction[3], image_plane;
+  uint32_t film_size[2];
+  float lens_radius, focal_distance;
+  float clip_near, clip_far;
+  uint32_t lens_image, medium_index;
+} etxb_camera;
+
+/* etx::Scene (scene.hxx:22-65), 528 B */
+#define ETXB_SCENE_COMMITTED 1u
+#define ETXB_SCENE_SPECTRAL 2u
+typedef struct etxb_scene {
+  etxb_array_view vertices, triangles, triangle_to_emitter, materials, emitter_profiles, emitter_instances, images, mediums, spectrums;
+  etxb_distribution emitters_distribution;
+  uint32_t environment_emitters[63];
+  uint32_t environment_emitter_count;
+  float bounding_sphere_center[3], bounding_sphere_radius;
+  uint32_t pixel_sampler_image;
+  float pixel_sampler_radius;
+  uint32_t min_path_length, max_path_length, samples, random_path_termination;
+  float noise_threshold, radiance_clamp;
+  uint32_t black_spectrum, white_spectrum, rayleigh_spectrum, mie_spectrum, ozone_spectrum;
+  uint32_t subsurface_scatter_material, subsurface_exit_material;
+  uint32_t default_dielectric_eta, default_conductor_eta, default_conductor_k;
+  uint32_t flags;
+  uint32_t pad;
+} etxb_scene;
+
+/* ---- options / status -------------------------------------------------------------------------- */
+
+/* VCMOptions bit flags (vcm_shared.hxx:24-37) */
+#define ETXB_VCM_CONNECT_TO_CAMERA (1u << 0)
+#define ETXB_VCM_DIRECT_HIT (1u << 1)
+#define ETXB_VCM_CONNECT_TO_LIGHT (1u << 2)
+#define ETXB_VCM_CONNECT_VERTICES (1u << 3)
+#define ETXB_VCM_MERGE_VERTICES (1u << 4)
+#define ETXB_VCM_ENABLE_MIS (1u << 5)
+#define ETXB_VCM_ENABLE_MERGING (1u << 6)
+#define ETXB_VCM_CONNECT_ONLY (ETXB_VCM_DIRECT_HIT | ETXB_VCM_CONNECT_TO_LIGHT | ETXB_VCM_CONNECT_TO_CAMERA | ETXB_VCM_CONNECT_VERTICES | ETXB_VCM_ENABLE_MIS)
+#define ETXB_VCM_FULL (ETXB_VCM_CONNECT_ONLY | ETXB_VCM_ENABLE_MERGING | ETXB_VCM_MERGE_VERTICES)
+
+/* Mirrors VCMOptions (vcm_shared.hxx:12-72); defaults = VCMOptions::default_values (vcm_shared.cxx:6-13).
+ * The option keys the reference UI uses ("vcm-initial_radius", "vcm-radius_decay", "vcm-blue_noise", "vcm-kernel",
+ * "vcm-direct_hit", ... vcm_shared.cxx:15-28) map 1:1 onto these fields; see etxb_options_set_key. */
+typedef struct etxb_vcm_options {
+  uint32_t options;      /* ETXB_VCM_* bits, default ETXB_VCM_FULL */
+  uint32_t radius_decay; /* default 256 */
+  uint32_t kernel;       /* 0 Tophat, 1 Epanechnikov (default) */
+  float initial_radius;  /* 0 => 5 * R_scene / max(W,H) (vcm_cpu.cxx:102-106) */
+  uint32_t blue_noise;   /* default 1 */
+} etxb_vcm_options;
+
+/* Mirrors Integrator::Status (integrator.hxx:24-37) + device counters. */
+typedef struct etxb_status {
+  double last_iteration_time; /* seconds, device time of the last finished iteration */
+  double total_time;          /* seconds, sum over finished iterations */
+  uint32_t completed_iterations;
+  uint32_t current_iteration;
+  uint32_t iteration_in_flight; /* 1 while an enqueued iteration has not finished */
+  uint32_t light_vertices;      /* vertices stored by the last light pass */
+  uint32_t overflow;            /* non-zero if a fixed-capacity pool overflowed (results invalid) */
+  uint32_t pad;
+} etxb_status;
+
+/* Per-iteration event counters (feed the algorithmic-bytes formula). */
+typedef struct etxb_counters {
+  uint64_t rays_closest;    /* closest-hit queries */
+  uint64_t rays_shadow;     /* transmittance (any-hit) queries */
+  uint64_t nodes_visited;   /* only counted when built with ETXB_COUNT_TRAVERSAL */
+  uint64_t tris_tested;     /* idem */
+  uint64_t bounces_light;   /* light-subpath surface events */
+  uint64_t bounces_camera;  /* camera-subpath surface events */
+  uint64_t light_vertices;  /* stored light vertices */
+  uint64_t connections;     /* camera-vertex x light-vertex connection attempts */
+  uint64_t merge_queries;   /* hash-grid gathers */
+  uint64_t merge_candidates;
+  uint64_t merge_accepts;
+  uint64_t splats;
+  uint64_t kernel_launches; /* kernels of this module launched */
+} etxb_counters;
+
+typedef struct etxb_device_config {
+  int32_t device_index;        /* CUDA device ordinal */
+  uint32_t max_light_vertices; /* pool capacity; 0 => 8 per pixel */
+  uint32_t flags;              /* reserved */
+  uint32_t pad;
+} etxb_device_config;
+
+/* Film layers readable with etxb_read_film: values follow Film::layer (film.cxx:381-418). */
+enum {
+  ETXB_FILM_RESULT = 0,      /* max(0, camera + light) as float4 */
+  ETXB_FILM_CAMERA = 1,      /* camera image (running mean over iterations) */
+  ETXB_FILM_LIGHT = 2,       /* light image (running mean over iterations) */
+  ETXB_FILM_LIGHT_ITERATION = 3
+};
+
+/* Named device buffers for etxb_read_buffer / etxb_device_pointer (parity tests + multi-GPU exchange). */
+enum {
+  ETXB_BUF_LIGHT_PATH_COUNT = 0,   /* uint32[N]  vertices stored per light path (VCMLightPath::count) */
+  ETXB_BUF_LIGHT_PATH_OFFSET = 1,  /* uint32[N]  first vertex of the path in the pool (VCMLightPath::index) */
+  ETXB_BUF_LIGHT_PATH_WAVELENGTH = 2, /* float[N] */
+  ETXB_BUF_LIGHT_SAMPLER = 3,      /* uint32[N]  sampler seed at the end of the light subpath */
+  ETXB_BUF_CAMERA_SAMPLER = 4,     /* uint32[N]  sampler seed at the end of the camera subpath */
+  ETXB_BUF_LV_POS = 5,             /* float[3*P] light vertex positions, path-major order */
+  ETXB_BUF_LV_THROUGHPUT = 6,      /* float[3*P] */
+  ETXB_BUF_LV_MIS = 7,             /* float[3*P] d_vcm, d_vc, d_vm */
+  ETXB_BUF_FILM_LIGHT_ITERATION = 8, /* float4[N] per-iteration light splats (all-reduced across ranks) */
+  ETXB_BUF_FILM_CAMERA = 9,        /* float4[N] */
+  ETXB_BUF_FILM_LIGHT = 10,        /* float4[N] */
+  ETXB_BUF_PHOTON_RECORDS = 11,    /* packed photon records of this rank (all-gathered across ranks) */
+  ETXB_BUF_CAMERA_GATHERED = 12,   /* float[3*N] last iteration's camera contribution per path */
+  ETXB_BUF_COUNT
+};
+
+typedef struct etxb_ctx etxb_ctx;
+
+/* ---- entry points -------------------------------------------------------------------------------- */
+
+/* Library identity: "fast" (product build) or "parity" (strict-IEEE build used by the bit-exact tests). */
+const char* etxb_build_flavor(void);
+/* Number of CUDA devices visible, or a negative etxb_error. */
+int etxb_device_count(void);
+
+/* Replaces Raytracing/Integrator construction (rt.cxx:27-36, vcm_cpu.cxx:62-66). */
+int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg);
+void etxb_destroy(etxb_ctx* ctx);
+const char* etxb_last_error(const etxb_ctx* ctx);
+
+/* Replaces Raytracing::commit_changes (rt.cxx:58-64,323): copies the scene to HBM, builds the BVH,
+ * allocates film + queues for camera->film_size.  `scene`/`camera` use the reference layouts. */
+int etxb_upload_scene(etxb_ctx* ctx, const void* scene, uint64_t scene_bytes, const void* camera, uint64_t camera_bytes);
+
+/* Blue-noise tables (thirdparty/bluenoise): sobol[256*256], and for the variant selected by
+ * next_power(min(scene.samples,256)) (bluenoise.cxx:73-95) scrambling[128*128*8], ranking[128*128*8], as uint8. */
+int etxb_upload_blue_noise(etxb_ctx* ctx, const uint8_t* sobol_256x256, const uint8_t* scrambling, const uint8_t* ranking);
+/* CIE 2006 XYZ table, 441 x float3, 390..830 nm (spectrum.hxx:28 spectral_xyz) and the RGB response table
+ * 391 x float3 (spectrum.cxx:399 rgb_response). */
+int etxb_upload_color_tables(etxb_ctx* ctx, const float* xyz_441x3, const float* rgb_response_391x3);
+
+/* VCMOptions::default_values / load (vcm_shared.cxx:6-28). */
+void etxb_options_default(etxb_vcm_options* opt);
+int etxb_options_set_key(etxb_vcm_options* opt, const char* key, double value);
+int etxb_set_options(etxb_ctx* ctx, const etxb_vcm_options* opt);
+
+/* Pixel-tile sharding across ranks (one process per GPU): rank r owns 32x32 tiles with (tile % world) == r.
+ * world == 1 (default) renders the full frame. */
+int etxb_set_partition(etxb_ctx* ctx, uint32_t rank, uint32_t world);
+
+/* CPUVCMImpl::start (vcm_cpu.cxx:81-93): clears film, sets iteration = first_iteration. */
+int etxb_begin(etxb_ctx* ctx, uint32_t first_iteration);
+
+/* One VCM iteration = start_next_iteration + gather_light_vertices + complete_light_vertices +
+ * gather_camera_vertices + complete_camera_vertices (vcm_cpu.cxx:95-241).  Asynchronous: returns after
+ * the work is queued on the context's stream. */
+int etxb_enqueue_iteration(etxb_ctx* ctx);
+/* The same iteration in three phases for multi-GPU runs (exchange photons / light image in between). */
+int etxb_enqueue_light_pass(etxb_ctx* ctx);
+int etxb_enqueue_grid_build(etxb_ctx* ctx, const void* device_photon_records, uint64_t photon_count);
+int etxb_enqueue_camera_pass(etxb_ctx* ctx);
+
+/* CPUVCM::update (vcm_cpu.cxx:264-276): non-blocking; fills status. */
+int etxb_poll(etxb_ctx* ctx, etxb_status* status);
+/* Blocks until all queued work is done. */
+int etxb_wait(etxb_ctx* ctx);
+/* CPUVCM::stop (vcm_cpu.cxx:278-288). */
+int etxb_stop(etxb_ctx* ctx, int wait_for_iteration);
+
+/* Film::layer (film.cxx:381-418): row-major float4, y already flipped in storage like the reference. */
+int etxb_read_film(etxb_ctx* ctx, uint32_t layer, float* dst_rgba, uint64_t dst_bytes);
+int etxb_film_size(const etxb_ctx* ctx, uint32_t* width, uint32_t* height);
+
+int etxb_get_counters(etxb_ctx* ctx, etxb_counters* out);
+/* Per-kernel device time of the last iteration (CUDA events): names[i] -> ms[i]; returns count. */
+int etxb_get_kernel_times(etxb_ctx* ctx, const char** names, float* ms, uint32_t* launches, uint32_t capacity);
+
+/* Introspection for parity tests and NCCL exchange. */
+int etxb_read_buffer(etxb_ctx* ctx, uint32_t buffer_id, void* dst, uint64_t dst_bytes, uint64_t* out_bytes);
+int etxb_device_pointer(etxb_ctx* ctx, uint32_t buffer_id, void** out_ptr, uint64_t* out_bytes);
+void* etxb_stream(etxb_ctx* ctx); /* cudaStream_t the module launches on */
+
+/* Unit entry points used by the parity tests (same kernels the iteration uses). */
+/* Closest-hit query for `count` rays (rt.cxx:428 Raytracing::trace): rays = float[8]*count {o,min_t,d,max_t},
+ * seeds in/out = sampler state per ray; hits out = {u, v, tri, t} (IntersectionBase, math.hxx:666). */
+int etxb_debug_trace(etxb_ctx* ctx, const float* rays, uint32_t* seeds, uint32_t count, float* hits_uv_t, uint32_t* hits_tri);
+/* Sampler / spectral KATs evaluated on the device (sampler.hxx:54,66; spectrum.hxx:219,234). */
+int etxb_debug_sampler(etxb_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t count, uint32_t draws, uint32_t* out_seed, float* out_values);
+int etxb_debug_math(etxb_ctx* ctx, uint32_t fn, const float* x, const float* y, uint32_t count, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ETX_B200_H */
