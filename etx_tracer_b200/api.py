@@ -1,0 +1,254 @@
+"""ctypes binding of the C ABI (include/etx_b200.h) + `GPUVCM`, the Python mirror of the reference's
+Integrator interface for this path (sources/etx/rt/integrators/integrator.hxx:12-98, vcm_cpu.cxx:247-310).
+
+There is no CPU fallback: loading fails loudly if the CUDA library is missing, and every call raises
+EtxbError with the module's message when the device path cannot do what was asked.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from . import scenes as _scenes
+from . import structs as S
+
+_libs = {}
+
+
+class EtxbError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"etxb error {code}: {message}")
+        self.code = code
+
+
+def load_library(flavor="fast"):
+    if flavor in _libs:
+        return _libs[flavor]
+    path = _build.lib_path(flavor)
+    if not os.path.exists(path):
+        raise EtxbError(-100, f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+    lib = C.CDLL(path)
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    lib.etxb_build_flavor.restype = C.c_char_p
+    lib.etxb_last_error.restype = C.c_char_p
+    lib.etxb_last_error.argtypes = [vp]
+    lib.etxb_create.argtypes = [C.POINTER(vp), vp]
+    lib.etxb_destroy.argtypes = [vp]
+    lib.etxb_destroy.restype = None
+    lib.etxb_upload_scene.argtypes = [vp, vp, u64, vp, u64]
+    lib.etxb_upload_blue_noise.argtypes = [vp, vp, vp, vp]
+    lib.etxb_upload_color_tables.argtypes = [vp, vp, vp]
+    lib.etxb_options_default.argtypes = [vp]
+    lib.etxb_options_default.restype = None
+    lib.etxb_options_set_key.argtypes = [vp, C.c_char_p, C.c_double]
+    lib.etxb_set_options.argtypes = [vp, vp]
+    lib.etxb_set_partition.argtypes = [vp, u32, u32]
+    lib.etxb_begin.argtypes = [vp, u32]
+    lib.etxb_enqueue_iteration.argtypes = [vp]
+    lib.etxb_enqueue_light_pass.argtypes = [vp]
+    lib.etxb_enqueue_grid_build.argtypes = [vp, vp, u64]
+    lib.etxb_enqueue_camera_pass.argtypes = [vp]
+    lib.etxb_poll.argtypes = [vp, vp]
+    lib.etxb_wait.argtypes = [vp]
+    lib.etxb_stop.argtypes = [vp, C.c_int]
+    lib.etxb_read_film.argtypes = [vp, u32, vp, u64]
+    lib.etxb_film_size.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+    lib.etxb_get_counters.argtypes = [vp, vp]
+    lib.etxb_get_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(u32), u32]
+    lib.etxb_read_buffer.argtypes = [vp, u32, vp, u64, C.POINTER(u64)]
+    lib.etxb_device_pointer.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64)]
+    lib.etxb_stream.restype = vp
+    lib.etxb_stream.argtypes = [vp]
+    lib.etxb_debug_trace.argtypes = [vp, vp, vp, u32, vp, vp]
+    lib.etxb_debug_sampler.argtypes = [vp, vp, vp, u32, u32, vp, vp]
+    lib.etxb_debug_math.argtypes = [vp, u32, vp, vp, u32, vp]
+    _libs[flavor] = lib
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class GPUVCM:
+    """`name()/run()/update()/stop()/status()/options` like the reference's CPUVCM, driving the CUDA module."""
+
+    def __init__(self, scene_data=None, flavor="fast", device=0, max_light_vertices=0, profile=False):
+        self.lib = load_library(flavor)
+        self.flavor = flavor
+        self.h = C.c_void_p()
+        cfg = np.zeros(1, dtype=S.DEVICE_CONFIG)
+        cfg["device_index"] = device
+        cfg["max_light_vertices"] = max_light_vertices
+        cfg["flags"] = 1 if profile else 0
+        rc = self.lib.etxb_create(C.byref(self.h), _p(cfg))
+        if rc != 0:
+            raise EtxbError(rc, "etxb_create failed (no CUDA device? the module has no CPU fallback)")
+        self.options = S.default_vcm_options()
+        self.scene_data = None
+        self._running = False
+        self._target_iterations = 0
+        ct = _scenes.tables("color_tables")
+        self._xyz = np.ascontiguousarray(ct["xyz_441x3"], dtype=np.float32)
+        self._rgbr = np.ascontiguousarray(ct["rgb_response_391x3"], dtype=np.float32)
+        self._check(self.lib.etxb_upload_color_tables(self.h, _p(self._xyz), _p(self._rgbr)))
+        if scene_data is not None:
+            self.set_scene(scene_data)
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc < 0:
+            raise EtxbError(rc, self.lib.etxb_last_error(self.h).decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.etxb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- Integrator surface -------------------------------------------------------------------------
+    @staticmethod
+    def name():
+        return "VCM (B200)"
+
+    def set_scene(self, scene_data):
+        """Raytracing::link_scene/link_camera + commit_changes."""
+        self.scene_data = scene_data
+        samples = int(scene_data.scene["samples"][0])
+        # BNSampler variant = next_power(min(samples, 256)) (thirdparty/bluenoise/bluenoise.cxx:73-95)
+        spp = 1
+        while spp < min(max(samples, 1), 256):
+            spp *= 2
+        bn = _scenes.tables("bluenoise")
+        self._bn = [np.ascontiguousarray(bn[k], dtype=np.uint8) for k in ("sobol", f"scrambling_{spp}", f"ranking_{spp}")]
+        self._check(self.lib.etxb_upload_blue_noise(self.h, _p(self._bn[0]), _p(self._bn[1]), _p(self._bn[2])))
+        self._check(self.lib.etxb_upload_scene(self.h, _p(scene_data.scene), scene_data.scene.nbytes, _p(scene_data.camera), scene_data.camera.nbytes))
+        w, h = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.lib.etxb_film_size(self.h, C.byref(w), C.byref(h)))
+        self.width, self.height = w.value, h.value
+
+    def set_option(self, key, value):
+        """Integrator::options() keys: vcm-initial_radius, vcm-radius_decay, vcm-blue_noise, vcm-kernel, vcm-direct_hit, ..."""
+        rc = self.lib.etxb_options_set_key(_p(self.options), key.encode(), float(value))
+        if rc != 0:
+            raise EtxbError(rc, f"unknown option key {key}")
+
+    def set_partition(self, rank, world):
+        self._check(self.lib.etxb_set_partition(self.h, rank, world))
+
+    def run(self, first_iteration=0):
+        """CPUVCM::run -> CPUVCMImpl::start: clears the film and arms iteration 0."""
+        self._check(self.lib.etxb_set_options(self.h, _p(self.options)))
+        self._check(self.lib.etxb_begin(self.h, first_iteration))
+        self._running = True
+        self._target_iterations = int(self.scene_data.scene["samples"][0])
+
+    def update(self):
+        """One pump of the integrator: renders the next iteration; stops at scene.samples like the reference."""
+        if not self._running:
+            return False
+        self._check(self.lib.etxb_enqueue_iteration(self.h))
+        st = self.status()
+        if st["completed_iterations"] >= self._target_iterations:
+            self._running = False
+        return self._running
+
+    def render(self, iterations, first_iteration=0):
+        self.run(first_iteration)
+        for _ in range(iterations):
+            self._check(self.lib.etxb_enqueue_iteration(self.h))
+        self._check(self.lib.etxb_wait(self.h))
+        return self.status()
+
+    def iterate(self):
+        self._check(self.lib.etxb_enqueue_iteration(self.h))
+
+    def light_pass(self):
+        self._check(self.lib.etxb_enqueue_light_pass(self.h))
+
+    def grid_build(self):
+        self._check(self.lib.etxb_enqueue_grid_build(self.h, None, 0))
+
+    def camera_pass(self):
+        self._check(self.lib.etxb_enqueue_camera_pass(self.h))
+
+    def stop(self, wait_for_iteration=True):
+        self._running = False
+        self._check(self.lib.etxb_stop(self.h, 1 if wait_for_iteration else 0))
+
+    def wait(self):
+        self._check(self.lib.etxb_wait(self.h))
+
+    def status(self):
+        st = np.zeros(1, dtype=S.STATUS)
+        self._check(self.lib.etxb_poll(self.h, _p(st)))
+        return {k: st[k][0].item() for k in st.dtype.names}
+
+    # -- results --------------------------------------------------------------------------------------
+    def film(self, layer=S.FILM_RESULT, out=None):
+        if out is None:
+            out = np.zeros((self.height, self.width, 4), dtype=np.float32)
+        self._check(self.lib.etxb_read_film(self.h, layer, _p(out), out.nbytes))
+        return out
+
+    def counters(self):
+        c = np.zeros(1, dtype=S.COUNTERS)
+        self._check(self.lib.etxb_get_counters(self.h, _p(c)))
+        return {k: int(c[k][0]) for k in c.dtype.names}
+
+    def kernel_times(self):
+        cap = 32
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        launches = (C.c_uint32 * cap)()
+        n = self._check(self.lib.etxb_get_kernel_times(self.h, names, ms, launches, cap))
+        return {names[i].decode(): (float(ms[i]), int(launches[i])) for i in range(n)}
+
+    def buffer(self, buf_id, dtype):
+        n = C.c_uint64(0)
+        self._check(self.lib.etxb_read_buffer(self.h, buf_id, None, 0, C.byref(n)))
+        out = np.zeros(n.value // np.dtype(dtype).itemsize, dtype=dtype)
+        if n.value:
+            self._check(self.lib.etxb_read_buffer(self.h, buf_id, _p(out), out.nbytes, C.byref(n)))
+        return out
+
+    def device_pointer(self, buf_id):
+        ptr, n = C.c_void_p(), C.c_uint64(0)
+        self._check(self.lib.etxb_device_pointer(self.h, buf_id, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def stream(self):
+        return self.lib.etxb_stream(self.h)
+
+    # -- unit entry points (parity tests) -----------------------------------------------------------------
+    def debug_trace(self, rays, seeds):
+        rays = np.ascontiguousarray(rays, dtype=np.float32)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32).copy()
+        n = rays.shape[0]
+        uvt = np.zeros((n, 3), dtype=np.float32)
+        tri = np.zeros(n, dtype=np.uint32)
+        self._check(self.lib.etxb_debug_trace(self.h, _p(rays), _p(seeds), n, _p(uvt), _p(tri)))
+        return uvt, tri, seeds
+
+    def debug_sampler(self, a, b, draws):
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        b = np.ascontiguousarray(b, dtype=np.uint32)
+        n = a.shape[0]
+        seeds = np.zeros((n, draws + 1), dtype=np.uint32)
+        vals = np.zeros((n, max(draws, 1)), dtype=np.float32)
+        self._check(self.lib.etxb_debug_sampler(self.h, _p(a), _p(b), n, draws, _p(seeds), _p(vals)))
+        return seeds, vals[:, :draws]
+
+    def debug_math(self, fn, x, y=None):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.zeros_like(x)
+        yy = np.ascontiguousarray(y, dtype=np.float32) if y is not None else None
+        self._check(self.lib.etxb_debug_math(self.h, fn, _p(x), _p(yy) if yy is not None else None, x.shape[0], _p(out)))
+        return out

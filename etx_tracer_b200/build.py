@@ -1,0 +1,57 @@
+"""Builds the CUDA module in-tree for sm_100a (nvcc cross-compiles without a GPU).
+
+  libetx_b200.so         product build ("fast": FMA contraction, CUDA math library)
+  libetx_b200_parity.so  strict-IEEE build (-fmad=false, portable transcendentals) used by the bit-exact parity tests
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["module.cu", "bvh_build.cpp"]
+HEADERS = ["bvh.h", "bvh_build.h", "dcore.cuh", "dscene.cuh", "dbsdf.cuh", "dtrace.cuh", "dvcm.cuh", "kernels.cuh", "portable_math.h",
+           os.path.join("..", "..", "include", "etx_b200.h")]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets"]
+FLAVORS = {
+    "fast": (os.path.join(HERE, "libetx_b200.so"), []),
+    "parity": (os.path.join(HERE, "libetx_b200_parity.so"), ["-fmad=false", "-DETXB_PARITY=1"]),
+}
+
+
+def lib_path(flavor="fast"):
+    return FLAVORS[flavor][0]
+
+
+def _stale(out):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(flavors=("fast", "parity"), force=False, verbose=False, extra=()):
+    procs = []
+    for fl in flavors:
+        out, flags = FLAVORS[fl]
+        if not force and not _stale(out):
+            continue
+        cmd = ["nvcc"] + ARCH + COMMON + flags + list(extra) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), flush=True)
+        procs.append((fl, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for fl, cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed for flavor {fl}:\n{' '.join(cmd)}\n{out}")
+        if verbose:
+            print(out)
+    return [FLAVORS[f][0] for f in flavors]
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built", [lib_path(f) for f in FLAVORS])

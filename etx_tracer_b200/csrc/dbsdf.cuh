@@ -1,0 +1,686 @@
+// dbsdf.cuh — BSDF sample / evaluate / pdf for the material classes on the hot path.
+//
+// Follows sources/etx/render/shared/{bsdf.hxx, scene_bsdf.hxx, bsdf_various.hxx, bsdf_dielectric.hxx,
+// bsdf_conductor.hxx, bsdf_external.hxx}.  The microfacet classes use the Heitz et al. multiple-scattering
+// random walk on the microsurface; its evaluate() is stochastic and consumes the path's sampler, so the order
+// of sampler draws below is part of the contract.
+#pragma once
+#include "dscene.cuh"
+
+namespace etxb {
+
+enum : uint32_t { kPathCamera = 1u, kPathLight = 2u };  // PathSource (bsdf.hxx:14-18)
+
+enum : uint32_t {  // BSDFSample::Properties (bsdf.hxx:63-69)
+  kBsdfDiffuse = 1u << 0u,
+  kBsdfReflection = 1u << 1u,
+  kBsdfTransmission = 1u << 2u,
+  kBsdfMediumChanged = 1u << 3u,
+  kBsdfDelta = 1u << 4u,
+};
+
+// BSDFData (bsdf.hxx:20-45): the surface point + incoming direction + query
+struct BData {
+  V3 pos, nrm, tan, btn;
+  V2 tex;
+  V3 w_i;
+  float wavelength;
+  uint32_t path_source;
+  uint32_t current_medium;
+};
+DEV BData make_bdata(const Isect& i, V3 w_i, float wavelength, uint32_t medium, uint32_t source) {
+  return {i.pos, i.nrm, i.tan, i.btn, i.tex, w_i, wavelength, source, medium};
+}
+
+template <bool SP>
+struct BEval {
+  Spec<SP> func, bsdf;
+  float pdf;
+  float eta;
+  DEV bool valid() const { return pdf > 0.0f; }
+};
+template <bool SP>
+DEV BEval<SP> beval_zero() {
+  return {Spec<SP>::make(0.0f), Spec<SP>::make(0.0f), 0.0f, 1.0f};
+}
+
+template <bool SP>
+struct BSample {
+  Spec<SP> weight;
+  V3 w_o;
+  float pdf;
+  float eta;
+  uint32_t properties;
+  uint32_t medium_index;
+  DEV bool valid() const { return pdf > 0.0f; }
+  DEV bool is_delta() const { return (properties & kBsdfDelta) == kBsdfDelta; }
+};
+template <bool SP>
+DEV BSample<SP> bsample_zero() {
+  return {Spec<SP>::make(0.0f), {0.0f, 0.0f, 0.0f}, 0.0f, 1.0f, 0u, kInvalidIndex};
+}
+
+// LocalFrame (math.hxx:614-643)
+struct Frame {
+  V3 tan, btn, nrm;
+  bool entering;
+  DEV V3 to_local(V3 v) const {
+    return {tan.x * v.x + tan.y * v.y + tan.z * v.z, btn.x * v.x + btn.y * v.y + btn.z * v.z, nrm.x * v.x + nrm.y * v.y + nrm.z * v.z};
+  }
+  DEV V3 from_local(V3 v) const {
+    return {tan.x * v.x + btn.x * v.y + nrm.x * v.z, tan.y * v.x + btn.y * v.y + nrm.y * v.z, tan.z * v.x + btn.z * v.y + nrm.z * v.z};
+  }
+};
+// BSDFData::get_normal_frame (bsdf.hxx:34-37)
+DEV Frame normal_frame(const BData& d) {
+  bool entering = dot(d.nrm, d.w_i) < 0.0f;
+  return entering ? Frame{d.tan, d.btn, d.nrm, true} : Frame{-d.tan, -d.btn, -d.nrm, false};
+}
+DEV V3 front_facing_normal(const BData& d) { return dot(d.nrm, d.w_i) < 0.0f ? d.nrm : -d.nrm; }
+
+// bsdf.hxx:232-239
+DEV float fix_shading_normal(V3 n_g, V3 n_s, V3 w_i, V3 w_o) {
+  float w_i_g = dot(w_i, n_g);
+  float w_i_s = dot(w_i, n_s);
+  float w_o_g = dot(w_o, n_g);
+  float w_o_s = dot(w_o, n_s);
+  float den = fmaxf(kInvMaxHalf, fabsf(w_o_s * w_i_g));
+  return fabsf(w_o_g * w_i_s) / den;
+}
+
+// ---- Fresnel (bsdf.hxx:241-377) ---------------------------------------------------------------------------
+template <bool SP>
+struct ThinfilmEval {
+  IorSample<SP> ior;
+  V3 rgb_wavelengths;
+  float thickness;
+};
+
+struct RsRp {
+  Cx a, b;
+};
+DEV Cx cx_div_conj(Cx a, Cx b) {
+  Cx num = a * cx_conj(b);
+  float denom = cx_norm(b);
+  return {num.re / denom, num.im / denom};
+}
+DEV RsRp fresnel_reflectance(Cx ni, Cx ci, Cx nj, Cx cj) {
+  if ((ci.re == 0.0f) && (cj.re == 0.0f) && (ci.im == 0.0f) && (cj.im == 0.0f)) return {cx(1.0f), cx(1.0f)};
+  if (ni == nj) return {cx(0.0f), cx(0.0f)};
+  Cx rs = cx_div_conj(ni * ci - nj * cj, ni * ci + nj * cj);
+  Cx rp = cx_div_conj(nj * ci - ni * cj, nj * ci + ni * cj);
+  return {rs, rp};
+}
+DEV RsRp fresnel_transmittance(Cx ni, Cx ci, Cx nj, Cx cj) {
+  if ((ci.re == 0.0f) && (cj.re == 0.0f) && (ci.im == 0.0f) && (cj.im == 0.0f)) return {cx(0.0f), cx(0.0f)};
+  if (ni == nj) return {cx(1.0f), cx(1.0f)};
+  Cx ts = cx_div_conj((2.0f * ni) * ci, ni * ci + nj * cj);
+  Cx tp = cx_div_conj((2.0f * ni) * ci, ni * cj + nj * ci);
+  return {ts, tp};
+}
+DEV float fresnel_generic(float cos_theta_i, Cx ext_ior, Cx int_ior) {
+  Cx q = ext_ior / int_ior;
+  Cx sin_theta_o_squared = (q * q) * (1.0f - cos_theta_i * cos_theta_i);
+  Cx cos_theta_o = cx_sqrt(1.0f - sin_theta_o_squared);
+  RsRp r = fresnel_reflectance(ext_ior, cx(cos_theta_i), int_ior, cos_theta_o);
+  return 0.5f * (cx_norm(r.a) + cx_norm(r.b));
+}
+DEV float fresnel_thinfilm(float wavelength, float cos_theta_0, Cx ext_ior, Cx film_ior, Cx int_ior, float thickness) {
+  const Cx i = {0.0f, 1.0f};
+  if (cos_theta_0 == 0.0f) return 0.0f;
+  Cx q1 = ext_ior / film_ior;
+  Cx sin_theta_1_squared = (q1 * q1) * (1.0f - cos_theta_0 * cos_theta_0);
+  if (sin_theta_1_squared.re >= 1.0f) return 1.0f;
+  Cx cos_theta_1 = cx_sqrt(1.0f - sin_theta_1_squared);
+  Cx q2 = film_ior / int_ior;
+  Cx sin_theta_2_squared = (q2 * q2) * (1.0f - cos_theta_1 * cos_theta_1);
+  if (sin_theta_2_squared.re >= 1.0f) return 1.0f;
+  Cx cos_theta_2 = cx_sqrt(1.0f - sin_theta_2_squared);
+  Cx ratio = (int_ior * cos_theta_2) / (ext_ior * cos_theta_0);
+  float delta_10 = ext_ior.re < film_ior.re ? kPi : 0.0f;
+  float delta_21 = film_ior.re < int_ior.re ? kPi : 0.0f;
+  float phase_shift = delta_10 + delta_21;
+  RsRp r01 = fresnel_reflectance(ext_ior, cx(cos_theta_0), film_ior, cos_theta_1);
+  RsRp t01 = fresnel_transmittance(ext_ior, cx(cos_theta_0), film_ior, cos_theta_1);
+  RsRp r12 = fresnel_reflectance(film_ior, cos_theta_1, int_ior, cos_theta_2);
+  RsRp t12 = fresnel_transmittance(film_ior, cos_theta_1, int_ior, cos_theta_2);
+  Cx phi = ((kDoublePi * 2.0f * thickness) * cos_theta_1 + phase_shift * film_ior) / wavelength;
+  Cx exp_i_phi = cx_exp(i * phi);
+  Cx tpq = t01.b * t12.b / (1.0f - r01.b * r12.b * exp_i_phi);
+  Cx tp = tpq * tpq;
+  Cx tsq = t01.a * t12.a / (1.0f - r01.a * r12.a * exp_i_phi);
+  Cx ts = tsq * tsq;
+  return cx_abs(1.0f - ratio * 0.5f * (tp + ts));
+}
+
+constexpr uint32_t kSpdClassConductor = 2u;  // SpectralDistribution::Class::Conductor (spectrum.hxx:455)
+
+template <bool SP>
+DEV Spec<SP> fresnel_calculate(float wavelength, float cos_theta, const IorSample<SP>& ext_ior, const IorSample<SP>& int_ior, const ThinfilmEval<SP>& thinfilm) {
+  cos_theta = fabsf(cos_theta);
+  bool plain = (thinfilm.thickness == 0.0f) || thinfilm.ior.eta.is_zero();
+  if constexpr (SP) {
+    float value;
+    if (plain) {
+      value = fresnel_generic(cos_theta, cx(ext_ior.eta.v, ext_ior.k.v), cx(int_ior.eta.v, int_ior.k.v));
+    } else {
+      value = fresnel_thinfilm(wavelength, cos_theta, cx(ext_ior.eta.v, ext_ior.k.v), cx(thinfilm.ior.eta.v, thinfilm.ior.k.v), cx(int_ior.eta.v, int_ior.k.v),
+        thinfilm.thickness);
+    }
+    return {saturatef(value)};
+  } else {
+    V3 values;
+    if (plain) {
+      values.x = fresnel_generic(cos_theta, cx(ext_ior.eta.x, ext_ior.k.x), cx(int_ior.eta.x, int_ior.k.x));
+      values.y = fresnel_generic(cos_theta, cx(ext_ior.eta.y, ext_ior.k.y), cx(int_ior.eta.y, int_ior.k.y));
+      values.z = fresnel_generic(cos_theta, cx(ext_ior.eta.z, ext_ior.k.z), cx(int_ior.eta.z, int_ior.k.z));
+      if (int_ior.cls == kSpdClassConductor) {
+        values = xyz_to_rgb(values) * V3{0.817660332f, 1.05418909f, 1.09945524f};
+      }
+    } else {
+      values.x = fresnel_thinfilm(thinfilm.rgb_wavelengths.x, cos_theta, cx(ext_ior.eta.x, ext_ior.k.x), cx(thinfilm.ior.eta.x, thinfilm.ior.k.x),
+        cx(int_ior.eta.x, int_ior.k.x), thinfilm.thickness);
+      values.y = fresnel_thinfilm(thinfilm.rgb_wavelengths.y, cos_theta, cx(ext_ior.eta.y, ext_ior.k.y), cx(thinfilm.ior.eta.y, thinfilm.ior.k.y),
+        cx(int_ior.eta.y, int_ior.k.y), thinfilm.thickness);
+      values.z = fresnel_thinfilm(thinfilm.rgb_wavelengths.z, cos_theta, cx(ext_ior.eta.z, ext_ior.k.z), cx(thinfilm.ior.eta.z, thinfilm.ior.k.z),
+        cx(int_ior.eta.z, int_ior.k.z), thinfilm.thickness);
+    }
+    return {saturatef(values.x), saturatef(values.y), saturatef(values.z)};
+  }
+}
+
+// scene_bsdf.hxx:110-126 evaluate_thinfilm (thickness image unsupported -> t = 1)
+template <bool SP>
+DEV ThinfilmEval<SP> evaluate_thinfilm(const DeviceScene& sc, float wavelength, const etxb_thinfilm& film, Smp& smp) {
+  ThinfilmEval<SP> r;
+  r.rgb_wavelengths = {610.0f, 537.0f, 450.0f};
+  if (film.max_thickness * film.min_thickness <= 0.0f) {
+    r.ior.cls = 0u;
+    r.ior.eta = Spec<SP>::make(0.0f);
+    r.ior.k = Spec<SP>::make(0.0f);
+    r.thickness = 0.0f;
+    return r;
+  }
+  float t = 1.0f;
+  r.thickness = lerpf(film.min_thickness, film.max_thickness, t);
+  if constexpr (SP) {
+    r.rgb_wavelengths = {wavelength, wavelength, wavelength};
+  } else {
+    r.rgb_wavelengths.x = 610.0f + 45.0f * (2.0f * smp.next() - 1.0f);
+    r.rgb_wavelengths.y = 537.0f + 47.0f * (2.0f * smp.next() - 1.0f);
+    r.rgb_wavelengths.z = 450.0f + 23.5f * (2.0f * smp.next() - 1.0f);
+  }
+  r.ior = evaluate_ior<SP>(sc, film.ior, wavelength);
+  return r;
+}
+
+// ---- microsurface random walk (bsdf_external.hxx:12-230) ---------------------------------------------------
+constexpr uint32_t kScatteringOrderMax = 16u;
+
+struct MicroRay {
+  V3 w;
+  float Lambda, h, C1, G1;
+
+  DEV void update_direction(V3 in_w, V2 alpha) {
+    w = in_w;
+    if (w.z > 0.9999f) {
+      Lambda = 0.0f;
+      return;
+    }
+    if (w.z < -0.9999f) {
+      Lambda = -1.0f;
+      return;
+    }
+    const float theta = m_acos(w.z);
+    const float cosTheta = w.z;
+    const float sinTheta = m_sin(theta);
+    const float tanTheta = sinTheta / cosTheta;
+    const float invSinTheta2 = 1.0f / (1.0f - w.z * w.z);
+    const float cosPhi2 = w.x * w.x * invSinTheta2;
+    const float sinPhi2 = w.y * w.y * invSinTheta2;
+    const float alpha_value = sqrtf(cosPhi2 * alpha.x * alpha.x + sinPhi2 * alpha.y * alpha.y);
+    const float a = 1.0f / tanTheta / alpha_value;
+    Lambda = 0.5f * (-1.0f + ((a > 0) ? 1.0f : -1.0f) * sqrtf(1.0f + 1.0f / (a * a)));
+  }
+  DEV void update_height(float in_h) {
+    h = in_h;
+    C1 = tmin(1.0f, tmax(0.0f, 0.5f * (h + 1.0f)));
+    if (w.z > 0.9999f)
+      G1 = 1.0f;
+    else if (w.z <= 0.0f)
+      G1 = 0.0f;
+    else
+      G1 = m_pow(C1, Lambda);
+  }
+};
+DEV MicroRay micro_ray(V3 w, V2 alpha) {
+  MicroRay r;
+  r.Lambda = 0.0f;
+  r.h = 0.0f;
+  r.C1 = 0.0f;
+  r.G1 = 0.0f;
+  r.update_direction(w, alpha);
+  return r;
+}
+DEV float inv_c1(float U) { return tmax(-1.0f, tmin(1.0f, 2.0f * U - 1.0f)); }
+DEV float sample_height(const MicroRay& ray, float U) {
+  if (ray.w.z > 0.9999f) return kMaxFloat;
+  if (ray.w.z < -0.9999f) return inv_c1(U * ray.C1);
+  if (fabsf(ray.w.z) < 0.0001f) return ray.h;
+  if (U > 1.0f - ray.G1) return kMaxFloat;
+  float P1 = m_pow((1.0f - U), 1.0f / ray.Lambda);
+  if (P1 <= 0.0f) return kMaxFloat;
+  float U1 = ray.C1 / P1;
+  return inv_c1(U1);
+}
+DEV float d_ggx(V3 wm, V2 alpha) {
+  if (wm.z <= kEpsilon) return 0.0f;
+  const float slope_x = -wm.x / wm.z;
+  const float slope_y = -wm.y / wm.z;
+  const float ax = fmaxf(kEpsilon, alpha.x * alpha.x);
+  const float ay = fmaxf(kEpsilon, alpha.y * alpha.y);
+  const float axy = fmaxf(kEpsilon, alpha.x * alpha.y);
+  const float tmp = 1.0f + slope_x * slope_x / ax + slope_y * slope_y / ay;
+  const float P22 = 1.0f / (kPi * axy * tmp * tmp);
+  return P22 / (wm.z * wm.z * wm.z * wm.z);
+}
+DEV V2 sample_p22_11(float theta_i, V2 rnd, V2 alpha) {
+  V2 slope = {0.0f, 0.0f};
+  if (theta_i < 0.0001f) {
+    const float r = sqrtf(rnd.x / (1.0f - rnd.x));
+    const float phi = kDoublePi * rnd.y;
+    slope.x = r * m_cos(phi);
+    slope.y = r * m_sin(phi);
+    return slope;
+  }
+  const float sin_theta_i = m_sin(theta_i);
+  const float cos_theta_i = m_cos(theta_i);
+  const float tan_theta_i = sin_theta_i / cos_theta_i;
+  const float projectedarea = 0.5f * (cos_theta_i + 1.0f);
+  if (projectedarea < 0.0001f) return {0.0f, 0.0f};
+  const float c = 1.0f / projectedarea;
+  const float A = 2.0f * rnd.x / cos_theta_i / c - 1.0f;
+  const float B = tan_theta_i;
+  const float tmp = 1.0f / (A * A - 1.0f);
+  const float D = sqrtf(tmax(0.0f, B * B * tmp * tmp - (A * A - B * B) * tmp));
+  const float slope_x_1 = B * tmp - D;
+  const float slope_x_2 = B * tmp + D;
+  slope.x = (A < 0.0f || slope_x_2 > 1.0f / tan_theta_i) ? slope_x_1 : slope_x_2;
+  float U2, S;
+  if (rnd.y > 0.5f) {
+    S = 1.0f;
+    U2 = 2.0f * (rnd.y - 0.5f);
+  } else {
+    S = -1.0f;
+    U2 = 2.0f * (0.5f - rnd.y);
+  }
+  const float z = (U2 * (U2 * (U2 * 0.27385f - 0.73369f) + 0.46341f)) / (U2 * (U2 * (U2 * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
+  slope.y = S * z * sqrtf(1.0f + slope.x * slope.x);
+  return slope;
+}
+// shared head of samplePhaseFunction_{conductor,dielectric} (bsdf_external.hxx:239-266, 413-441): visible micro-normal
+DEV V3 sample_visible_micronormal(V2 slope_rnd, V3 wi, V2 alpha) {
+  const V3 wi_11 = normalize(V3{alpha.x * wi.x, alpha.y * wi.y, wi.z});
+  V2 slope_11 = sample_p22_11(m_acos(wi_11.z), slope_rnd, alpha);
+  const float phi = m_atan2(wi_11.y, wi_11.x);
+  V2 slope = {m_cos(phi) * slope_11.x - m_sin(phi) * slope_11.y, m_sin(phi) * slope_11.x + m_cos(phi) * slope_11.y};
+  slope.x *= alpha.x;
+  slope.y *= alpha.y;
+  if ((slope.x != slope.x) || !finitef(slope.x)) {
+    return (wi.z > 0) ? V3{0.0f, 0.0f, 1.0f} : normalize(V3{wi.x, wi.y, 0.0f});
+  }
+  return normalize(V3{-slope.x, -slope.y, 1.0f});
+}
+
+template <bool SP>
+DEV Spec<SP> phase_function_reflection(float wavelength, const MicroRay& ray, V3 wo, V2 alpha, const IorSample<SP>& ext_ior, const IorSample<SP>& int_ior,
+  const ThinfilmEval<SP>& thinfilm) {
+  if (ray.w.z > 0.9999f) return Spec<SP>::make(0.0f);
+  float projectedArea = (ray.w.z < -0.9999f) ? 1.0f : ray.Lambda * ray.w.z;
+  if (projectedArea < kEpsilon) return Spec<SP>::make(0.0f);
+  const V3 wh = normalize(-ray.w + wo);
+  if (wh.z < 0.0f) return Spec<SP>::make(0.0f);
+  float w_dot_h = dot(-ray.w, wh);
+  if (w_dot_h < kEpsilon) return Spec<SP>::make(0.0f);
+  const Spec<SP> f = fresnel_calculate<SP>(wavelength, w_dot_h, ext_ior, int_ior, thinfilm);
+  const float dg = d_ggx(wh, alpha);
+  const float d = dg / (4.0f * projectedArea);
+  return f * d;
+}
+
+DEV float abgam(float x) {
+  const float g0 = 1.0f / 12.0f, g1 = 1.0f / 30.0f, g2 = 53.0f / 210.0f, g3 = 195.0f / 371.0f, g4 = 22999.0f / 22737.0f, g5 = 29944523.0f / 19733142.0f,
+              g6 = 109535241009.0f / 48264275462.0f;
+  constexpr float kHalfLogDoublePi = 0.918938518f;
+  return kHalfLogDoublePi - x + (x - 0.5f) * m_log(x) + g0 / (x + g1 / (x + g2 / (x + g3 / (x + g4 / (x + g5 / (x + g6 / x))))));
+}
+DEV float gamma_fn(float x) { return m_exp(abgam(x + 5.0f)) / (x * (x + 1.0f) * (x + 2.0f) * (x + 3.0f) * (x + 4.0f)); }
+DEV float beta_fn(float m, float n) { return gamma_fn(m) * gamma_fn(n) / gamma_fn(m + n); }
+
+DEV V3 refract_dir(V3 wi, V3 wm, float eta) {
+  const float cos_theta_i = dot(wi, wm);
+  const float cos_theta_t2 = 1.0f - (1.0f - cos_theta_i * cos_theta_i) / (eta * eta);
+  const float cos_theta_t = -sqrtf(tmax(0.0f, cos_theta_t2));
+  return wm * (dot(wi, wm) / eta + cos_theta_t) - wi / eta;
+}
+
+template <bool SP>
+DEV Spec<SP> eval_phase_function_dielectric(float wavelength, const MicroRay& ray, V3 wo, bool reflection, const IorSample<SP>& ext_ior, const IorSample<SP>& int_ior,
+  const ThinfilmEval<SP>& thinfilm, V2 alpha) {
+  if (ray.w.z > 0.9999f) return Spec<SP>::make(0.0f);
+  if (reflection) return phase_function_reflection<SP>(wavelength, ray, wo, alpha, ext_ior, int_ior, thinfilm);
+  float projectedArea = (ray.w.z < -0.9999f) ? 1.0f : ray.Lambda * ray.w.z;
+  if (projectedArea < kEpsilon) return Spec<SP>::make(0.0f);
+  float eta = (int_ior.eta / ext_ior.eta).monochromatic();
+  V3 wh = normalize(-ray.w + wo * eta);
+  wh *= (wh.z > 0) ? 1.0f : -1.0f;
+  float i_dot_m = -dot(wh, ray.w);
+  if (i_dot_m < 0) return Spec<SP>::make(0.0f);
+  float o_dot_m = dot(wo, wh);
+  float scalar = eta * eta * i_dot_m * tmax(0.0f, -o_dot_m) * d_ggx(wh, alpha) / (projectedArea * sqr(i_dot_m + eta * o_dot_m));
+  Spec<SP> f = fresnel_calculate<SP>(wavelength, i_dot_m, ext_ior, int_ior, thinfilm);
+  return (1.0f - f) * scalar;
+}
+
+template <bool SP>
+struct DielectricPhaseSample {
+  V3 w_o;
+  Spec<SP> weight;
+  bool reflection;
+};
+template <bool SP>
+DEV DielectricPhaseSample<SP> sample_phase_function_dielectric(float wavelength, V2 rnd_slope, float rnd_reflection, V3 wi, V2 alpha, const IorSample<SP>& ext_ior,
+  const IorSample<SP>& int_ior, const ThinfilmEval<SP>& thinfilm) {
+  V3 wm = sample_visible_micronormal(rnd_slope, wi, alpha);
+  float i_dot_m = dot(wi, wm);
+  Spec<SP> f = fresnel_calculate<SP>(wavelength, i_dot_m, ext_ior, int_ior, thinfilm);
+  float eta = (int_ior.eta / ext_ior.eta).monochromatic();
+  DielectricPhaseSample<SP> r;
+  r.reflection = rnd_reflection < f.monochromatic();
+  r.weight = r.reflection ? f : 1.0f - f;
+  r.w_o = r.reflection ? (-wi + 2.0f * wm * i_dot_m) : normalize(refract_dir(wi, wm, eta));
+  return r;
+}
+DEV float mis_weight_dielectric(V3 wi, V3 wo, bool reflection, float eta, V2 alpha) {
+  if (reflection) {
+    if (wi.x == -wo.x && wi.y == -wo.y && wi.z == -wo.z) return 1.0f;
+    const V3 wh = normalize(wi + wo);
+    return d_ggx((wh.z > 0) ? wh : -wh, alpha);
+  } else {
+    const V3 wh = normalize(wi + wo * eta);
+    return d_ggx((wh.z > 0) ? wh : -wh, alpha);
+  }
+}
+
+// bsdf_external.hxx:466-558
+template <bool SP>
+DEVN Spec<SP> eval_dielectric(float wavelength, Smp& smp, V3 wi, V3 wo, bool wo_outside, V2 alpha, const IorSample<SP>& ext_ior, const IorSample<SP>& int_ior,
+  const ThinfilmEval<SP>& thinfilm) {
+  if ((wi.z <= 0) || (wo.z <= 0 && wo_outside) || (wo.z >= 0 && !wo_outside)) return Spec<SP>::make(0.0f);
+  MicroRay ray = micro_ray(-wi, alpha);
+  ray.update_height(1.0f);
+  bool outside = true;
+  MicroRay ray_shadowing = micro_ray(wo_outside ? wo : -wo, alpha);
+  Spec<SP> singleScattering = Spec<SP>::make(0.0f);
+  Spec<SP> multipleScattering = Spec<SP>::make(0.0f);
+  float wi_MISweight = 0.0f;
+  float eta = (int_ior.eta / ext_ior.eta).monochromatic();
+  int current_scatteringOrder = 0;
+  while (current_scatteringOrder < int(kScatteringOrderMax)) {
+    ray.update_height(sample_height(ray, smp.next()));
+    if (ray.h == kMaxFloat) break;
+    current_scatteringOrder++;
+    if (current_scatteringOrder == 1) {
+      Spec<SP> phasefunction = eval_phase_function_dielectric<SP>(wavelength, ray, wo, wo_outside, ext_ior, int_ior, thinfilm, alpha);
+      float G2_G1;
+      if (wo_outside)
+        G2_G1 = (1.0f + (-ray.Lambda - 1.0f)) / (1.0f + (-ray.Lambda - 1.0f) + ray_shadowing.Lambda);
+      else
+        G2_G1 = (1.0f + (-ray.Lambda - 1.0f)) * beta_fn(1.0f + (-ray.Lambda - 1.0f), 1.0f + ray_shadowing.Lambda);
+      if (finitef(G2_G1)) {
+        singleScattering = phasefunction * G2_G1;
+      }
+    }
+    if (current_scatteringOrder > 1) {
+      Spec<SP> phasefunction;
+      float MIS;
+      if (outside) {
+        phasefunction = eval_phase_function_dielectric<SP>(wavelength, ray, wo, wo_outside, ext_ior, int_ior, thinfilm, alpha);
+        MIS = wi_MISweight / (wi_MISweight + mis_weight_dielectric(-ray.w, wo, wo_outside, eta, alpha));
+      } else {
+        phasefunction = eval_phase_function_dielectric<SP>(wavelength, ray, -wo, !wo_outside, int_ior, ext_ior, thinfilm, alpha);
+        MIS = wi_MISweight / (wi_MISweight + mis_weight_dielectric(-ray.w, -wo, !wo_outside, 1.0f / eta, alpha));
+      }
+      ray_shadowing.update_height((outside == wo_outside) ? ray.h : -ray.h);
+      multipleScattering += phasefunction * ray_shadowing.G1 * MIS;
+    }
+    V2 rnd_slope = (current_scatteringOrder == 1) && smp.has_fixed() ? V2{smp.fixed_u, smp.fixed_v} : smp.next_2d();
+    float rnd_reflection = (current_scatteringOrder == 1) && smp.has_fixed() ? smp.fixed_w : smp.next();
+    auto next_sample = sample_phase_function_dielectric<SP>(wavelength, rnd_slope, rnd_reflection, -ray.w, alpha, (outside ? ext_ior : int_ior),
+      (outside ? int_ior : ext_ior), thinfilm);
+    if (next_sample.reflection) {
+      ray.update_direction(next_sample.w_o, alpha);
+      ray.update_height(ray.h);
+    } else {
+      outside = !outside;
+      ray.update_direction(-next_sample.w_o, alpha);
+      ray.update_height(-ray.h);
+    }
+    if (current_scatteringOrder == 1) wi_MISweight = mis_weight_dielectric(wi, ray.w, outside, eta, alpha);
+    if ((ray.h != ray.h) || (ray.w.x != ray.w.x) || (ray.w.z <= kEpsilon)) return Spec<SP>::make(0.0f);
+  }
+  return 0.5f * singleScattering + multipleScattering;
+}
+
+// ---- Diffuse (bsdf_various.hxx:36-133), diffuse_variation 0 (Lambert) -------------------------------------
+template <bool SP>
+DEV BEval<SP> diffuse_layer(const DeviceScene& sc, const BData& d, V3 local_w_o, const etxb_material& m) {
+  if (local_w_o.z <= 0.0f) return beval_zero<SP>();
+  Spec<SP> diffuse = apply_image<SP>(sc, m.scattering, d.wavelength);
+  BEval<SP> e;
+  e.eta = 1.0f;
+  e.func = diffuse / kPi;
+  e.bsdf = e.func * local_w_o.z;
+  e.pdf = kInvPi * local_w_o.z;
+  return e;
+}
+template <bool SP>
+DEV BSample<SP> diffuse_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
+  Frame frame = normal_frame(d);
+  BSample<SP> r = bsample_zero<SP>();
+  r.eta = 1.0f;
+  r.properties = kBsdfReflection | kBsdfDiffuse;
+  V2 cos_rnd = smp.has_fixed() ? V2{smp.fixed_u, smp.fixed_v} : smp.next_2d();
+  V3 local_w_o = sample_cosine_local(cos_rnd, 1.0f);
+  BEval<SP> dl = diffuse_layer<SP>(sc, d, local_w_o, m);
+  r.weight = dl.pdf == 0.0f ? Spec<SP>::make(0.0f) : dl.bsdf / dl.pdf;
+  r.pdf = dl.pdf;
+  r.w_o = frame.from_local(local_w_o);
+  return r;
+}
+template <bool SP>
+DEV BEval<SP> diffuse_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m) {
+  Frame frame = normal_frame(d);
+  V3 local_w_o = frame.to_local(w_o);
+  if (local_w_o.z <= kEpsilon) return beval_zero<SP>();
+  return diffuse_layer<SP>(sc, d, local_w_o, m);
+}
+DEV float diffuse_pdf(const BData& d, V3 w_o) {
+  float n_dot_o = dot(front_facing_normal(d), w_o);
+  if (n_dot_o <= kEpsilon) return 0.0f;
+  return kInvPi * n_dot_o;
+}
+
+// ---- Dielectric (bsdf_dielectric.hxx:60-259) ---------------------------------------------------------------
+DEV bool dielectric_is_delta(const etxb_material& m) {
+  V2 r = evaluate_roughness(m);
+  return tmax(r.x, r.y) <= kDeltaAlphaTreshold;
+}
+template <bool SP>
+DEVN float dielectric_pdf(const DeviceScene& sc, const BData& d, V3 in_w_o, const etxb_material& m, Smp& smp) {
+  Frame lf = {d.tan, d.btn, d.nrm, false};
+  V3 w_i = lf.to_local(-d.w_i);
+  if (fabsf(w_i.z) <= kEpsilon) return 0.0f;
+  V3 w_o = lf.to_local(in_w_o);
+  if (fabsf(w_o.z) <= kEpsilon) return 0.0f;
+  V2 roughness = evaluate_roughness(m);
+  IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
+  IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  const bool outside = w_i.z > 0;
+  const bool reflection = w_i.z * w_o.z > 0.0f;
+  V3 wh;
+  float dwh_dwo;
+  if (reflection) {
+    wh = normalize(w_o + w_i);
+    dwh_dwo = 1.0f / (4.0f * dot(w_o, wh));
+  } else {
+    float eta = outside ? (int_ior.eta / ext_ior.eta).monochromatic() : (ext_ior.eta / int_ior.eta).monochromatic();
+    wh = normalize(w_i + w_o * eta);
+    float sqrt_denom = dot(w_i, wh) + eta * dot(w_o, wh);
+    dwh_dwo = sqr(eta) * dot(w_o, wh) / sqr(sqrt_denom);
+  }
+  wh *= (wh.z >= 0.0f) ? 1.0f : -1.0f;
+  MicroRay ray = micro_ray(w_i * (outside ? 1.0f : -1.0f), roughness);
+  float dg = d_ggx(wh, roughness);
+  float prob = tmax(0.0f, dot(wh, ray.w) * dg / ((1.0f + ray.Lambda) * ray.w.z));
+  float f = fresnel_calculate<SP>(d.wavelength, dot(w_i, wh), outside ? ext_ior : int_ior, outside ? int_ior : ext_ior, thinfilm).monochromatic();
+  prob *= reflection ? f : (1.0f - f);
+  return fabsf(prob * dwh_dwo) + fabsf(w_o.z);
+}
+template <bool SP>
+DEVN BSample<SP> dielectric_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
+  Frame lf = {d.tan, d.btn, d.nrm, false};
+  V3 w_i = lf.to_local(-d.w_i);
+  bool in_outside = w_i.z > 0;
+  float direction_scale = in_outside ? 1.0f : -1.0f;
+  IorSample<SP> ext_ior = in_outside ? evaluate_ior<SP>(sc, m.ext_ior, d.wavelength) : evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
+  IorSample<SP> int_ior = in_outside ? evaluate_ior<SP>(sc, m.int_ior, d.wavelength) : evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  BSample<SP> result = bsample_zero<SP>();
+  result.weight = Spec<SP>::make(1.0f);
+  V2 roughness = evaluate_roughness(m);
+  MicroRay ray = micro_ray(-direction_scale * w_i, roughness);
+  ray.update_height(1.0f);
+  bool ray_outside = true;
+  uint32_t scattering_order = 0;
+  while (true) {
+    float sampled_height = sample_height(ray, smp.next());
+    if (sampled_height == kMaxFloat) break;
+    ray.update_height(sampled_height);
+    V2 rnd_slope = (scattering_order == 0) && smp.has_fixed() ? V2{smp.fixed_u, smp.fixed_v} : smp.next_2d();
+    float rnd_reflection = (scattering_order == 0) && smp.has_fixed() ? smp.fixed_w : smp.next();
+    auto s = sample_phase_function_dielectric<SP>(d.wavelength, rnd_slope, rnd_reflection, -ray.w, roughness, (ray_outside ? ext_ior : int_ior),
+      (ray_outside ? int_ior : ext_ior), thinfilm);
+    result.weight *= s.weight;
+    if (s.reflection) {
+      ray.update_direction(s.w_o, roughness);
+      ray.update_height(ray.h);
+    } else {
+      ray_outside = !ray_outside;
+      ray.update_direction(-s.w_o, roughness);
+      ray.update_height(-ray.h);
+    }
+    if (scattering_order++ > kScatteringOrderMax) {
+      return bsample_zero<SP>();
+    }
+  }
+  V3 lw_o = direction_scale * (ray_outside ? ray.w : -ray.w);
+  uint32_t delta_sample = dielectric_is_delta(m) ? kBsdfDelta : 0u;
+  if (w_i.z * lw_o.z > 0.0f) {
+    result.eta = 1.0f;
+    result.weight = (result.weight / result.weight.monochromatic()) * apply_image<SP>(sc, m.reflectance, d.wavelength);
+    result.properties = kBsdfReflection | delta_sample;
+    result.medium_index = d.current_medium;
+  } else {
+    float eta = (int_ior.eta / ext_ior.eta).monochromatic();
+    float factor = sqr(1.0f / eta);
+    result.eta = eta;
+    result.weight = (result.weight / result.weight.monochromatic()) * apply_image<SP>(sc, m.scattering, d.wavelength) * factor;
+    result.properties = kBsdfTransmission | kBsdfMediumChanged | delta_sample;
+    result.medium_index = in_outside ? m.int_medium : m.ext_medium;
+  }
+  result.w_o = normalize(lf.from_local(lw_o));
+  result.pdf = dielectric_pdf<SP>(sc, d, result.w_o, m, smp);
+  return result;
+}
+template <bool SP>
+DEVN BEval<SP> dielectric_evaluate(const DeviceScene& sc, const BData& d, V3 in_w_o, const etxb_material& m, Smp& smp) {
+  Frame lf = {d.tan, d.btn, d.nrm, false};
+  V3 w_i = lf.to_local(-d.w_i);
+  if (fabsf(w_i.z) <= kEpsilon) return beval_zero<SP>();
+  V3 w_o = lf.to_local(in_w_o);
+  if (fabsf(w_o.z) <= kEpsilon) return beval_zero<SP>();
+  V2 roughness = evaluate_roughness(m);
+  IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
+  IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  bool forward_path = d.path_source == kPathCamera;
+  float backward_scale = fabsf(1.0f / w_i.z);
+  Spec<SP> value;
+  float wl = d.wavelength;
+  if (w_i.z > 0) {
+    if (w_o.z >= 0) {
+      value = forward_path ? eval_dielectric<SP>(wl, smp, w_i, w_o, true, roughness, ext_ior, int_ior, thinfilm)
+                           : eval_dielectric<SP>(wl, smp, w_o, w_i, true, roughness, ext_ior, int_ior, thinfilm) * backward_scale;
+    } else {
+      value = forward_path ? eval_dielectric<SP>(wl, smp, w_i, w_o, false, roughness, ext_ior, int_ior, thinfilm)
+                           : eval_dielectric<SP>(wl, smp, -w_o, -w_i, false, roughness, int_ior, ext_ior, thinfilm) * backward_scale;
+    }
+  } else if (w_o.z <= 0) {
+    value = forward_path ? eval_dielectric<SP>(wl, smp, -w_i, -w_o, true, roughness, int_ior, ext_ior, thinfilm)
+                         : eval_dielectric<SP>(wl, smp, -w_o, -w_i, true, roughness, int_ior, ext_ior, thinfilm) * backward_scale;
+  } else {
+    value = forward_path ? eval_dielectric<SP>(wl, smp, -w_i, -w_o, false, roughness, int_ior, ext_ior, thinfilm)
+                         : eval_dielectric<SP>(wl, smp, w_o, w_i, false, roughness, ext_ior, int_ior, thinfilm) * backward_scale;
+  }
+  if (value.is_zero()) return beval_zero<SP>();
+  bool reflection = w_i.z * w_o.z > 0.0f;
+  BEval<SP> e;
+  e.eta = 1.0f;
+  e.func = (2.0f * value) * apply_image<SP>(sc, reflection ? m.reflectance : m.scattering, d.wavelength);
+  e.bsdf = e.func * fabsf(w_o.z);
+  e.pdf = dielectric_pdf<SP>(sc, d, in_w_o, m, smp);
+  return e;
+}
+
+// ---- dispatch (scene_bsdf.hxx:56-90) -----------------------------------------------------------------------
+// Material classes not implemented on the device yet are rejected by etxb_upload_scene (ETXB_ERR_UNSUPPORTED).
+DEV bool material_class_supported(uint32_t cls) { return (cls == ETXB_MAT_DIFFUSE) || (cls == ETXB_MAT_DIELECTRIC); }
+
+template <bool SP>
+DEV BSample<SP> bsdf_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
+  switch (m.cls) {
+    case ETXB_MAT_DIELECTRIC:
+      return dielectric_sample<SP>(sc, d, m, smp);
+    default:
+      return diffuse_sample<SP>(sc, d, m, smp);
+  }
+}
+template <bool SP>
+DEV BEval<SP> bsdf_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
+  switch (m.cls) {
+    case ETXB_MAT_DIELECTRIC:
+      return dielectric_evaluate<SP>(sc, d, w_o, m, smp);
+    default:
+      return diffuse_evaluate<SP>(sc, d, w_o, m);
+  }
+}
+template <bool SP>
+DEV float bsdf_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
+  switch (m.cls) {
+    case ETXB_MAT_DIELECTRIC:
+      return dielectric_pdf<SP>(sc, d, w_o, m, smp);
+    default:
+      return diffuse_pdf(d, w_o);
+  }
+}
+template <bool SP>
+DEV float bsdf_reverse_pdf(const DeviceScene& sc, const BData& in_d, V3 in_w_o, const etxb_material& m, Smp& smp) {
+  V3 w_o = -in_d.w_i;
+  BData d = in_d;
+  d.w_i = -in_w_o;
+  return bsdf_pdf<SP>(sc, d, w_o, m, smp);
+}
+
+}  // namespace etxb

@@ -1,0 +1,596 @@
+// dvcm.cuh — per-path VCM logic: emitter / camera sampling, MIS recurrences, connections, merging.
+// Restates sources/etx/rt/shared/vcm_shared.hxx (line refs inline), render/shared/scene_emitters.hxx and
+// scene_camera.hxx for the device.  One sampler per path; every consumer draws in the oracle's order.
+#pragma once
+#include "dbsdf.cuh"
+#include "dtrace.cuh"
+
+namespace etxb {
+
+// VCMOptions bits (vcm_shared.hxx:24-37)
+struct VcmParams {
+  uint32_t options;
+  uint32_t kernel;  // 1 = Epanechnikov
+  uint32_t blue_noise;
+  uint32_t iteration;
+  float current_radius, vm_weight, vc_weight, vm_normalization;
+  DEV bool connect_to_camera() const { return options & ETXB_VCM_CONNECT_TO_CAMERA; }
+  DEV bool direct_hit() const { return options & ETXB_VCM_DIRECT_HIT; }
+  DEV bool connect_to_light() const { return options & ETXB_VCM_CONNECT_TO_LIGHT; }
+  DEV bool connect_vertices() const { return options & ETXB_VCM_CONNECT_VERTICES; }
+  DEV bool enable_mis() const { return options & ETXB_VCM_ENABLE_MIS; }
+  DEV bool enable_merging() const { return options & ETXB_VCM_ENABLE_MERGING; }
+  DEV bool merge_vertices() const { return enable_merging() && (options & ETXB_VCM_MERGE_VERTICES); }
+};
+
+enum : uint32_t {  // VCMPathState flags (vcm_shared.hxx:92-98)
+  kPathDeltaEmitter = 1u << 0u,
+  kPathLocalEmitter = 1u << 3u,
+  kPathValid = 1u << 4u,
+};
+
+// VCMPathState (vcm_shared.hxx:91-150) held in registers between the SoA load and store of a kernel
+template <bool SP>
+struct PathState {
+  Spec<SP> throughput;
+  Spec<SP> gathered;
+  V3 merged;
+  V3 ray_o, ray_d;
+  float ray_min_t, ray_max_t;
+  Smp sampler;
+  float wavelength;
+  float path_distance;
+  float d_vcm, d_vc, d_vm, eta;
+  uint32_t total_path_depth;
+  uint32_t medium_index;
+  uint32_t flags;
+  uint32_t lv_count;  // light vertices stored so far by this path
+};
+
+// ---- emitters (scene_emitters.hxx) ---------------------------------------------------------------------------
+DEV float collimation_to_exponent(float normalized) {  // scene.hxx:67-71
+  float t = saturatef(normalized);
+  float denom = sqr(sqr(1.0f - t));
+  return 1.0f / fmaxf(kEpsilon, denom);
+}
+// Distribution::sample (distribution.hxx:16-35)
+DEV uint32_t distribution_sample(const etxb_distribution_entry* values, uint32_t count, float rnd) {
+  uint32_t b = 0, e = count;
+  do {
+    uint32_t m = b + (e - b) / 2;
+    if (__ldg(&values[m].cdf) >= rnd) {
+      e = m;
+    } else {
+      b = m;
+    }
+  } while ((e - b) > 1);
+  return b;
+}
+DEV float emitter_discrete_pdf(const DeviceScene& sc, const etxb_emitter& e) { return (e.spectrum_weight * e.additional_weight) / sc.emitter_total_weight; }
+
+template <bool SP>
+struct EmitterSample {
+  Spec<SP> value;
+  V3 barycentric, origin, normal, direction;
+  float pdf_sample, pdf_area, pdf_dir, pdf_dir_out;
+  uint32_t emitter_index, triangle_index, medium_index;
+  bool is_delta, is_distant;
+};
+
+// emitter_get_radiance, Area case (scene_emitters.hxx:81-104)
+template <bool SP>
+DEV Spec<SP> emitter_get_radiance_area(const DeviceScene& sc, const etxb_emitter& em_inst, float wavelength, V3 source_position, V3 target_position, bool directly_visible,
+  float& pdf_area, float& pdf_dir, float& pdf_dir_out) {
+  pdf_dir = 0.0f;
+  pdf_area = 0.0f;
+  pdf_dir_out = 0.0f;
+  const etxb_emitter_profile& em = sc.emitter_profiles[em_inst.profile];
+  TriRec tri = load_triangle(sc, em_inst.triangle_index);
+  const etxb_material& material = sc.materials[tri.material_index];
+  if (dot(tri.geo_n, target_position - source_position) >= 0.0f) return Spec<SP>::make(0.0f);
+  pdf_area = 1.0f / em_inst.triangle_area;
+  V3 dp = source_position - target_position;
+  float distance_squared = dot(dp, dp);
+  if (distance_squared > 0.0f) {
+    float cos_t = fabsf(dot(dp, tri.geo_n)) / sqrtf(distance_squared);
+    float exponent = collimation_to_exponent(material.emission_collimation);
+    float cos_tx = directly_visible ? cos_t : m_pow(cos_t, exponent);
+    if (cos_tx > kEpsilon) {
+      pdf_dir = pdf_area * distance_squared / cos_tx;
+      pdf_dir_out = pdf_area * cos_tx * kInvPi;
+    }
+  }
+  return apply_image<SP>(sc, em.emission, wavelength);
+}
+
+// sample_emission (scene_emitters.hxx:226-305), Area emitters
+template <bool SP>
+DEV EmitterSample<SP> sample_emission(const DeviceScene& sc, float wavelength, Smp& smp) {
+  EmitterSample<SP> r;
+  r.value = Spec<SP>::make(0.0f);
+  r.pdf_area = r.pdf_dir = r.pdf_dir_out = 0.0f;
+  r.emitter_index = distribution_sample(sc.emitter_dist, sc.emitter_count + 1u, smp.next());
+  r.pdf_sample = __ldg(&sc.emitter_dist[r.emitter_index].pdf);
+  const etxb_emitter& em_inst = sc.emitters[r.emitter_index];
+  const etxb_emitter_profile& em = sc.emitter_profiles[em_inst.profile];
+  TriRec tri = load_triangle(sc, em_inst.triangle_index);
+  const etxb_material& material = sc.materials[tri.material_index];
+  r.triangle_index = em_inst.triangle_index;
+  r.barycentric = random_barycentric(smp.next_2d());
+  V3 pos, nrm, tan, btn;
+  V2 tex;
+  lerp_vertex(sc, tri, r.barycentric, pos, nrm, tan, btn, tex);
+  r.origin = pos;
+  r.normal = nrm;
+  r.direction = sample_cosine_frame(smp.next_2d(), nrm, tan, btn, collimation_to_exponent(material.emission_collimation));
+  // emitter_evaluate_out_local (:22-38)
+  r.pdf_dir = tmax(0.0f, dot(r.normal, r.direction)) * kInvPi;
+  if (r.pdf_dir > 0.0f) {
+    r.pdf_area = 1.0f / em_inst.triangle_area;
+    r.pdf_dir_out = r.pdf_dir * r.pdf_area;
+    r.value = apply_image<SP>(sc, em.emission, wavelength);
+  }
+  r.medium_index = material.ext_medium;
+  r.is_delta = false;
+  r.is_distant = false;
+  return r;
+}
+
+// sample_emitter (scene_emitters.hxx:216-224) -> emitter_sample_in, Area case (:139-158)
+template <bool SP>
+DEV EmitterSample<SP> sample_emitter(const DeviceScene& sc, float wavelength, uint32_t emitter_index, V2 rnd, V3 from_point) {
+  EmitterSample<SP> r;
+  const etxb_emitter& em_inst = sc.emitters[emitter_index];
+  TriRec tri = load_triangle(sc, em_inst.triangle_index);
+  r.barycentric = random_barycentric(rnd);
+  r.origin = lerp_pos(sc, tri, r.barycentric);
+  r.normal = lerp_normal(sc, tri, r.barycentric);
+  r.direction = normalize(r.origin - from_point);
+  r.value = emitter_get_radiance_area<SP>(sc, em_inst, wavelength, from_point, r.origin, false, r.pdf_area, r.pdf_dir, r.pdf_dir_out);
+  r.medium_index = sc.materials[tri.material_index].ext_medium;
+  r.pdf_sample = emitter_discrete_pdf(sc, em_inst);
+  r.emitter_index = emitter_index;
+  r.triangle_index = em_inst.triangle_index;
+  r.is_delta = false;
+  r.is_distant = false;
+  return r;
+}
+
+// ---- camera (scene_camera.hxx) ---------------------------------------------------------------------------------
+DEV V3 cam3(const float* p) { return {p[0], p[1], p[2]}; }
+DEV bool camera_has_lens(const etxb_camera& c) { return (c.lens_radius > kEpsilon) && (c.focal_distance > kEpsilon); }
+
+// generate_ray (:26-62), perspective camera
+DEV void generate_ray(const etxb_camera& camera, V2 uv, V2 sensor_rnd, V3& origin, V3& w_o, float& t_near, float& t_far) {
+  origin = cam3(camera.position);
+  V3 direction = cam3(camera.direction);
+  V3 s = uv.x * cam3(camera.side);
+  V3 u = uv.y * cam3(camera.up) / camera.aspect;
+  w_o = normalize(camera.tan_half_fov * (s + u) + direction);
+  if (camera_has_lens(camera)) {
+    V2 sensor_sample = sample_disk(sensor_rnd);
+    sensor_sample = sensor_sample * camera.lens_radius;
+    origin = origin + cam3(camera.side) * sensor_sample.x + cam3(camera.up) * sensor_sample.y;
+    float focal_plane_distance = camera.focal_distance / dot(w_o, direction);
+    V3 p = cam3(camera.position) + focal_plane_distance * w_o;
+    w_o = normalize(p - origin);
+  }
+  float cos_t = dot(w_o, direction);
+  float tn = camera.clip_near > 0.0f ? camera.clip_near / cos_t : kRayEpsilon;
+  t_far = camera.clip_far > 0.0f ? camera.clip_far / cos_t : kMaxFloat;
+  t_near = fmaxf(tn, kRayEpsilon);
+}
+
+struct CameraSample {
+  V3 position, direction;
+  V2 uv;
+  float weight, pdf_dir, pdf_dir_out;
+};
+// sample_film (:64-118)
+DEV CameraSample sample_film(Smp& smp, const etxb_camera& camera, V3 from_point) {
+  CameraSample r = {};
+  V2 sensor_sample = {0.0f, 0.0f};
+  if (camera_has_lens(camera)) {
+    sensor_sample = sample_disk(smp.next_2d());
+    sensor_sample = sensor_sample * camera.lens_radius;
+  }
+  r.position = cam3(camera.position) + sensor_sample.x * cam3(camera.side) + sensor_sample.y * cam3(camera.up);
+  r.direction = r.position - from_point;
+  V3 normal = cam3(camera.direction);
+  float cos_t = -dot(r.direction, normal);
+  if (cos_t < 0.0f) return CameraSample{};
+  float distance_squared = dot(r.direction, r.direction);
+  float distance = sqrtf(distance_squared);
+  r.direction /= distance;
+  cos_t /= distance;
+  float focal_plane_distance = camera_has_lens(camera) ? camera.focal_distance : 1.0f;
+  V3 focus_point = r.position - r.direction * (focal_plane_distance / cos_t);
+  const float* m = camera.view_proj;
+  float px = m[0] * focus_point.x + m[4] * focus_point.y + m[8] * focus_point.z + m[12] * 1.0f;
+  float py = m[1] * focus_point.x + m[5] * focus_point.y + m[9] * focus_point.z + m[13] * 1.0f;
+  float pw = m[3] * focus_point.x + m[7] * focus_point.y + m[11] * focus_point.z + m[15] * 1.0f;
+  r.uv = {px / pw, py / pw};
+  if ((pw <= 0.0f) || (r.uv.x < -1.0f) || (r.uv.y < -1.0f) || (r.uv.x > 1.0f) || (r.uv.y > 1.0f)) return CameraSample{};
+  float lens_area = (camera.lens_radius > kEpsilon) ? kPi * sqr(camera.lens_radius) : 1.0f;
+  float pdf_area = 1.0f / lens_area;
+  r.pdf_dir = pdf_area * distance_squared / cos_t;
+  r.pdf_dir_out = 1.0f / (camera.area * lens_area * cos_t * cos_t * cos_t);
+  float importance = r.pdf_dir_out / cos_t;
+  r.weight = importance / r.pdf_dir;
+  return r;
+}
+
+// ---- path start ----------------------------------------------------------------------------------------------------
+// vcm_generate_emitter_state (vcm_shared.hxx:310-349)
+template <bool SP>
+DEV PathState<SP> generate_emitter_state(const DeviceScene& sc, const VcmParams& it, uint32_t index) {
+  PathState<SP> s = {};
+  s.throughput = Spec<SP>::make(0.0f);
+  s.gathered = Spec<SP>::make(0.0f);
+  s.eta = 1.0f;
+  s.medium_index = kInvalidIndex;
+  s.ray_min_t = kRayEpsilon;
+  s.ray_max_t = kMaxFloat;
+  s.sampler.init(index, it.iteration);
+  s.wavelength = SP ? spectral_sample_wavelength(s.sampler.next()) : -1.0f;
+  EmitterSample<SP> es = sample_emission<SP>(sc, s.wavelength, s.sampler);
+  if (es.pdf_dir <= 0.0f) return s;
+  float cos_t = dot(es.direction, es.normal);
+  s.throughput = es.value * (cos_t / (es.pdf_dir * es.pdf_area * es.pdf_sample));
+  s.ray_o = es.origin;
+  s.ray_d = es.direction;
+  if (es.triangle_index != kInvalidIndex) {
+    s.ray_o = shading_pos(sc, load_triangle(sc, es.triangle_index), es.barycentric, s.ray_d);
+  }
+  s.d_vcm = es.is_distant ? 1.0f / es.pdf_area : 1.0f / es.pdf_dir;
+  if (es.is_delta == false) {
+    s.d_vc = (es.is_distant ? 1.0f : cos_t) / (es.pdf_dir * es.pdf_area * es.pdf_sample);
+  }
+  s.d_vm = s.d_vc * it.vc_weight;
+  s.eta = 1.0f;
+  s.medium_index = es.medium_index;
+  s.flags = (es.is_delta ? kPathDeltaEmitter : 0u) | (es.is_distant ? 0u : kPathLocalEmitter) | kPathValid;
+  return s;
+}
+
+// vcm_generate_camera_state (vcm_shared.hxx:351-377)
+template <bool SP>
+DEV PathState<SP> generate_camera_state(const DeviceScene& sc, const VcmParams& it, uint32_t px, uint32_t py, uint32_t index, float light_wavelength) {
+  PathState<SP> s = {};
+  s.sampler.init(index, it.iteration);
+  if constexpr (SP) {
+    float sampled = spectral_sample_wavelength(s.sampler.next());
+    s.wavelength = (light_wavelength == 0.0f) ? sampled : light_wavelength;
+  } else {
+    s.wavelength = light_wavelength;  // kUndefinedWavelength (-1)
+  }
+  const etxb_camera& camera = sc.camera;
+  // get_jittered_uv (scene_camera.hxx:12-18)
+  float sample_radius = 0.5f;
+  V2 uv;
+  uv.x = (float(px) + 0.5f + sample_radius * (s.sampler.next() * 2.0f - 1.0f)) / float(camera.film_size[0]) * 2.0f - 1.0f;
+  uv.y = (float(py) + 0.5f + sample_radius * (s.sampler.next() * 2.0f - 1.0f)) / float(camera.film_size[1]) * 2.0f - 1.0f;
+  generate_ray(camera, uv, s.sampler.next_2d(), s.ray_o, s.ray_d, s.ray_min_t, s.ray_max_t);
+  s.throughput = Spec<SP>::make(1.0f);
+  s.gathered = Spec<SP>::make(0.0f);
+  s.merged = {0.0f, 0.0f, 0.0f};
+  // film_evaluate_out (scene_camera.hxx:120-126)
+  float cos_t = dot(s.ray_d, cam3(camera.direction));
+  float pdf_dir = 1.0f / (camera.area * cos_t * cos_t * cos_t);
+  s.d_vcm = 1.0f / pdf_dir;
+  s.d_vc = 0.0f;
+  s.d_vm = 0.0f;
+  s.medium_index = camera.medium_index;
+  s.eta = 1.0f;
+  s.path_distance = 0.0f;
+  s.total_path_depth = 1;
+  return s;
+}
+
+// ---- light vertex record (VCMLightVertex, vcm_shared.hxx:154-197): 6 x 16 B in HBM ------------------------------------
+struct LightVertexRec {
+  float4 thr_dvcm;  // throughput (x only in spectral mode), d_vcm
+  float4 wi_dvc;    // w_i, d_vc
+  float4 bc_dvm;    // barycentric, d_vm
+  float4 pos_tri;   // pos, triangle index (bits)
+  float4 nrm_mat;   // nrm, material index (bits)
+  uint4 ids;        // medium index, path_length, path_index, ordinal within the path
+};
+static_assert(sizeof(LightVertexRec) == 96, "light vertex record is 96 bytes");
+
+template <bool SP>
+DEV LightVertexRec make_light_vertex(const PathState<SP>& s, const Isect& i, uint32_t path_index) {
+  LightVertexRec r;
+  V3 t = s.throughput.as_v3();
+  r.thr_dvcm = make_float4(t.x, t.y, t.z, s.d_vcm);
+  r.wi_dvc = make_float4(s.ray_d.x, s.ray_d.y, s.ray_d.z, s.d_vc);
+  r.bc_dvm = make_float4(i.barycentric.x, i.barycentric.y, i.barycentric.z, s.d_vm);
+  r.pos_tri = make_float4(i.pos.x, i.pos.y, i.pos.z, __uint_as_float(i.triangle_index));
+  r.nrm_mat = make_float4(i.nrm.x, i.nrm.y, i.nrm.z, __uint_as_float(i.material_index));
+  r.ids = make_uint4(s.medium_index, s.total_path_depth, path_index, s.lv_count);
+  return r;
+}
+
+// ---- shared step pieces ------------------------------------------------------------------------------------------------
+// vcm_next_ray (vcm_shared.hxx:218-283)
+template <bool SP>
+DEV bool vcm_next_ray(const DeviceScene& sc, bool light_path, PathState<SP>& state, const VcmParams& it, const Isect& isect, const BData& bsdf_data, const BSample<SP>& bs) {
+  if (state.total_path_depth + 1 > sc.max_path_length) return false;
+  if (bs.valid() == false) return false;
+  TriRec tri = load_triangle(sc, isect.triangle_index);
+  const etxb_material& mat = sc.materials[isect.material_index];
+  state.throughput *= bs.weight;
+  if (light_path) {
+    state.throughput *= fix_shading_normal(tri.geo_n, isect.nrm, isect.w_i, bs.w_o);
+  }
+  if (state.throughput.is_zero()) return false;
+  if (random_continue<SP>(state.total_path_depth, sc.random_path_termination, state.eta, state.sampler, state.throughput) == false) return false;
+  if (bs.properties & kBsdfMediumChanged) {
+    state.medium_index = bs.medium_index;
+  }
+  float cos_theta_bsdf = fabsf(dot(isect.nrm, bs.w_o));
+  if (bs.is_delta()) {
+    state.d_vc *= cos_theta_bsdf;
+    state.d_vm *= cos_theta_bsdf;
+    state.d_vcm = 0.0f;
+  } else {
+    float rev_sample_pdf = bsdf_reverse_pdf<SP>(sc, bsdf_data, bs.w_o, mat, state.sampler);
+    state.d_vc = (cos_theta_bsdf / bs.pdf) * (state.d_vc * rev_sample_pdf + state.d_vcm + it.vm_weight);
+    state.d_vm = (cos_theta_bsdf / bs.pdf) * (state.d_vm * rev_sample_pdf + state.d_vcm * it.vc_weight + 1.0f);
+    state.d_vcm = 1.0f / bs.pdf;
+  }
+  state.ray_d = bs.w_o;
+  state.ray_o = shading_pos(sc, tri, isect.barycentric, bs.w_o);
+  state.ray_max_t = kMaxFloat;
+  state.ray_min_t = kRayEpsilon;
+  state.eta *= bs.eta;
+  state.total_path_depth += 1u;
+  return true;
+}
+
+// vcm_connect_to_camera (vcm_shared.hxx:463-535), surface vertices
+template <bool SP>
+DEV bool vcm_connect_to_camera(const DeviceScene& sc, const VcmParams& it, const Isect& isect, PathState<SP>& state, Spec<SP>& out_value, V2& uv, TraverseStats* stats,
+  uint32_t& shadow_rays) {
+  if ((it.connect_to_camera() == false) || (state.total_path_depth + 2 > sc.max_path_length) || (state.total_path_depth + 2 < sc.min_path_length)) return false;
+  const etxb_camera& camera = sc.camera;
+  V3 sample_pos = isect.pos;
+  CameraSample cs = sample_film(state.sampler, camera, sample_pos);
+  if (cs.pdf_dir <= 0.0f) return false;
+  V3 direction = cs.position - sample_pos;
+  float dist2 = dot(direction, direction);
+  if (dist2 <= kEpsilon) return false;
+  V3 w_o = normalize(direction);
+  const etxb_material& mat = sc.materials[isect.material_index];
+  BData data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathLight);
+  BEval<SP> eval = bsdf_evaluate<SP>(sc, data, w_o, mat, state.sampler);
+  if (eval.valid() == false) return false;
+  Spec<SP> scatter = eval.bsdf;
+  float reverse_pdf = bsdf_reverse_pdf<SP>(sc, data, w_o, mat, state.sampler);
+  TriRec tri = load_triangle(sc, isect.triangle_index);
+  V3 origin = shading_pos(sc, tri, isect.barycentric, w_o);
+  float len = length(cs.position - origin);
+  float cos_t = fabsf(dot(cs.direction, cam3(camera.direction)));
+  V3 clip_pos = origin + cs.direction * fmaxf(0.0f, len - camera.clip_near / cos_t);
+  shadow_rays += 1;
+  float tr = trace_transmittance(sc, origin, clip_pos, state.sampler, stats);
+  if (tr <= kEpsilon) return false;  // tr.is_zero()
+  uv = cs.uv;
+  float camera_pdf = cs.pdf_dir_out * fabsf(dot(isect.nrm, w_o)) / dist2;
+  float w_light = camera_pdf * (it.vm_weight + state.d_vcm + state.d_vc * reverse_pdf);
+  float weight = it.enable_mis() ? (1.0f / (1.0f + w_light)) : 1.0f;
+  weight *= fix_shading_normal(tri.geo_n, isect.nrm, isect.w_i, w_o);
+  out_value = Spec<SP>::make(tr) * scatter * state.throughput * cs.weight * weight;
+  return true;
+}
+
+// vcm_get_radiance + vcm_handle_direct_hit (vcm_shared.hxx:285-308, 597-606)
+template <bool SP>
+DEV void vcm_handle_direct_hit(const DeviceScene& sc, const VcmParams& it, const Isect& isect, PathState<SP>& state) {
+  if ((it.direct_hit() == false) || (isect.emitter_index == kInvalidIndex)) return;
+  if ((state.total_path_depth > sc.max_path_length) || (state.total_path_depth < sc.min_path_length)) return;
+  const etxb_emitter& emitter = sc.emitters[isect.emitter_index];
+  float pdf_emitter_area, pdf_emitter_dir, pdf_emitter_dir_out;
+  Spec<SP> radiance = emitter_get_radiance_area<SP>(sc, emitter, state.wavelength, state.ray_o, isect.pos, state.total_path_depth == 1, pdf_emitter_area, pdf_emitter_dir,
+    pdf_emitter_dir_out);
+  if (pdf_emitter_dir <= kEpsilon) return;
+  float emitter_sample_pdf = emitter_discrete_pdf(sc, emitter);
+  float w_camera = state.d_vcm * pdf_emitter_area * emitter_sample_pdf + state.d_vc * (pdf_emitter_dir_out * emitter_sample_pdf);
+  float weight = (it.enable_mis() && (state.total_path_depth > 1)) ? (1.0f / (1.0f + w_camera)) : 1.0f;
+  state.gathered += weight * (state.throughput * radiance);
+}
+
+// vcm_connect_to_light (vcm_shared.hxx:608-671), surface vertices
+template <bool SP>
+DEV Spec<SP> vcm_connect_to_light(const DeviceScene& sc, const VcmParams& it, const Isect& isect, PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays) {
+  Spec<SP> zero = Spec<SP>::make(0.0f);
+  if ((it.connect_to_light() == false) || (state.total_path_depth + 1 > sc.max_path_length) || (state.total_path_depth + 1 < sc.min_path_length)) return zero;
+  V3 sample_pos = isect.pos;
+  uint32_t emitter_index = distribution_sample(sc.emitter_dist, sc.emitter_count + 1u, state.sampler.fixed_w);
+  EmitterSample<SP> es = sample_emitter<SP>(sc, state.wavelength, emitter_index, {state.sampler.fixed_u, state.sampler.fixed_v}, sample_pos);
+  if (es.pdf_dir <= 0.0f) return zero;
+  V3 w_o = es.direction;
+  const etxb_material& mat = sc.materials[isect.material_index];
+  BData data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
+  BEval<SP> eval = bsdf_evaluate<SP>(sc, data, w_o, mat, state.sampler);
+  if (eval.valid() == false) return zero;
+  Spec<SP> scatter = eval.bsdf;
+  float reverse_pdf = bsdf_reverse_pdf<SP>(sc, data, w_o, mat, state.sampler);
+  TriRec tri = load_triangle(sc, isect.triangle_index);
+  V3 origin = shading_pos(sc, tri, isect.barycentric, normalize(es.origin - isect.pos));
+  float camera_factor = fabsf(dot(w_o, tri.geo_n));
+  shadow_rays += 1;
+  float tr = trace_transmittance(sc, origin, es.origin, state.sampler, stats);
+  if (tr <= kEpsilon) return zero;
+  float l_dot_e = fabsf(dot(es.direction, es.normal));
+  float w_light = 0.0f;
+  if (es.is_delta == false) {
+    float conn_pdf = bsdf_pdf<SP>(sc, data, w_o, mat, state.sampler);
+    w_light = conn_pdf / (es.pdf_dir * es.pdf_sample);
+  }
+  float w_camera = (es.pdf_dir_out * camera_factor) / (es.pdf_dir * l_dot_e) * (it.vm_weight + state.d_vcm + state.d_vc * reverse_pdf);
+  float weight = it.enable_mis() ? 1.0f / (1.0f + w_light + w_camera) : 1.0f;
+  return Spec<SP>::make(tr) * state.throughput * scatter * es.value * (weight / (es.pdf_dir * es.pdf_sample));
+}
+
+// vcm_connect_to_light_vertex (vcm_shared.hxx:673-763), surface-surface
+template <bool SP>
+DEV bool vcm_connect_to_light_vertex(const DeviceScene& sc, const VcmParams& it, PathState<SP>& state, const LightVertexRec& lv, const Isect& cam, V3& target_position,
+  Spec<SP>& value) {
+  uint32_t lv_tri = __float_as_uint(lv.pos_tri.w);
+  uint32_t lv_mat = __float_as_uint(lv.nrm_mat.w);
+  TriRec light_tri = load_triangle(sc, lv_tri);
+  Isect light_v;  // VCMLightVertex::vertex(): lerp_vertex from (triangle, barycentric)
+  V3 bc = {lv.bc_dvm.x, lv.bc_dvm.y, lv.bc_dvm.z};
+  lerp_vertex(sc, light_tri, bc, light_v.pos, light_v.nrm, light_v.tan, light_v.btn, light_v.tex);
+  target_position = light_v.pos;
+  V3 w_o = target_position - cam.pos;
+  float distance_squared = dot(w_o, w_o);
+  if (distance_squared <= kEpsilon) return false;
+  w_o /= sqrtf(distance_squared);
+  float w_dot_l = -dot(light_v.nrm, w_o);
+
+  const etxb_material& mat = sc.materials[cam.material_index];
+  BData camera_data = make_bdata(cam, cam.w_i, state.wavelength, state.medium_index, kPathCamera);
+  BEval<SP> camera_bsdf = bsdf_evaluate<SP>(sc, camera_data, w_o, mat, state.sampler);
+  if (camera_bsdf.valid() == false) return false;
+  float camera_area_pdf = camera_bsdf.pdf * fabsf(w_dot_l) / distance_squared;
+  float camera_rev_pdf = bsdf_reverse_pdf<SP>(sc, camera_data, w_o, mat, state.sampler);
+  Spec<SP> camera_scatter = camera_bsdf.bsdf;
+
+  const etxb_material& light_mat = sc.materials[lv_mat];
+  V3 lv_wi = {lv.wi_dvc.x, lv.wi_dvc.y, lv.wi_dvc.z};
+  BData light_data = {light_v.pos, light_v.nrm, light_v.tan, light_v.btn, light_v.tex, lv_wi, state.wavelength, kPathLight, state.medium_index};
+  BEval<SP> light_bsdf = bsdf_evaluate<SP>(sc, light_data, -w_o, light_mat, state.sampler);
+  if (light_bsdf.valid() == false) return false;
+  float w_dot_c = dot(cam.nrm, w_o);
+  float light_area_pdf = light_bsdf.pdf * fabsf(w_dot_c) / distance_squared;
+  float light_rev_pdf = bsdf_reverse_pdf<SP>(sc, light_data, -w_o, light_mat, state.sampler);
+  Spec<SP> light_scatter = light_bsdf.bsdf * fix_shading_normal(light_tri.geo_n, light_data.nrm, light_data.w_i, -w_o);
+
+  float vmW_pair = it.vm_weight;
+  float w_light = camera_area_pdf * (vmW_pair + lv.thr_dvcm.w + lv.wi_dvc.w * light_rev_pdf);
+  float w_camera = light_area_pdf * (vmW_pair + state.d_vcm + state.d_vc * camera_rev_pdf);
+  float weight = it.enable_mis() ? 1.0f / (1.0f + w_light + w_camera) : 1.0f;
+  Spec<SP> lv_throughput = Spec<SP>::make3({lv.thr_dvcm.x, lv.thr_dvcm.y, lv.thr_dvcm.z});
+  value = (camera_scatter * state.throughput) * (light_scatter * lv_throughput) * (weight / distance_squared);
+  return true;
+}
+
+// vcm_connect_to_light_path (vcm_shared.hxx:765-803): serial over the paired path's vertices (shared sampler)
+template <bool SP>
+DEV Spec<SP> vcm_connect_to_light_path(const DeviceScene& sc, const VcmParams& it, const LightVertexRec* pool, uint32_t lp_index, uint32_t lp_count, const Isect& isect,
+  PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays, uint32_t& connections) {
+  Spec<SP> result = Spec<SP>::make(0.0f);
+  if (it.connect_vertices() == false) return result;
+  for (uint32_t i = 0; i < lp_count; ++i) {
+    const uint64_t target_path_length = uint64_t(state.total_path_depth) + i + 2u;
+    if (target_path_length < sc.min_path_length) continue;
+    if (target_path_length > sc.max_path_length) break;
+    const float4* p = reinterpret_cast<const float4*>(pool + lp_index + i);
+    LightVertexRec lv;
+    lv.thr_dvcm = __ldg(p + 0);
+    lv.wi_dvc = __ldg(p + 1);
+    lv.bc_dvm = __ldg(p + 2);
+    lv.pos_tri = __ldg(p + 3);
+    lv.nrm_mat = __ldg(p + 4);
+    connections += 1;
+    V3 target_position;
+    Spec<SP> value;
+    if (vcm_connect_to_light_vertex<SP>(sc, it, state, lv, isect, target_position, value)) {
+      TriRec tri = load_triangle(sc, isect.triangle_index);
+      V3 p0 = shading_pos(sc, tri, isect.barycentric, normalize(target_position - isect.pos));
+      shadow_rays += 1;
+      float tr = trace_transmittance(sc, p0, target_position, state.sampler, stats);
+      if (tr > kEpsilon) {
+        result += Spec<SP>::make(tr) * value;
+      }
+    }
+  }
+  return result;
+}
+
+// ---- photon hash grid (VCMSpatialGridData, vcm_shared.hxx:805-925) ------------------------------------------------------
+struct GridData {
+  const uint2* cell_range;  // [begin, end) per hash cell
+  const float4* pos_dvcm;   // position, d_vcm
+  const float4* nrm_dvm;    // normal, d_vm
+  const float4* win_len;    // w_in, path_length (bits)
+  const float4* thr_rgb;    // throughput.to_rgb() / pdf_lambda
+  V3 bbox_min, bbox_max;
+  uint32_t hash_table_mask;
+  uint32_t photon_count;
+  float cell_size, radius_squared, inv_radius_squared;
+};
+DEV uint32_t grid_cell_index(uint32_t mask, int32_t x, int32_t y, int32_t z) {
+  return ((uint32_t(x) * 73856093u) ^ (uint32_t(y) * 19349663u) ^ (uint32_t(z) * 83492791u)) & mask;
+}
+DEV uint32_t grid_position_to_index(V3 pos, V3 bbox_min, float cell_size, uint32_t mask) {
+  V3 m = vfloor((pos - bbox_min) / cell_size);
+  return grid_cell_index(mask, static_cast<int32_t>(m.x), static_cast<int32_t>(m.y), static_cast<int32_t>(m.z));
+}
+
+template <bool SP>
+DEV V3 grid_gather(const DeviceScene& sc, const GridData& g, const VcmParams& it, const Isect& isect, PathState<SP>& state, uint32_t& candidates, uint32_t& accepts) {
+  V3 merged = {0.0f, 0.0f, 0.0f};
+  if (g.photon_count == 0) return merged;
+  V3 pos = isect.pos;
+  if (!((pos.x >= g.bbox_min.x) && (pos.y >= g.bbox_min.y) && (pos.z >= g.bbox_min.z) && (pos.x <= g.bbox_max.x) && (pos.y <= g.bbox_max.y) && (pos.z <= g.bbox_max.z)))
+    return merged;
+  V3 m = (pos - g.bbox_min) / g.cell_size;
+  V3 mf = vfloor(m);
+  V3 md = m - mf;
+  int32_t acx = static_cast<int32_t>(mf.x), acy = static_cast<int32_t>(mf.y), acz = static_cast<int32_t>(mf.z);
+  int32_t bcx = acx + ((md.x < 0.5f) ? -1 : +1);
+  int32_t bcy = acy + ((md.y < 0.5f) ? -1 : +1);
+  int32_t bcz = acz + ((md.z < 0.5f) ? -1 : +1);
+
+  const etxb_material& mat = sc.materials[isect.material_index];
+  BData camera_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
+  const float w_camera_base = state.d_vcm * it.vc_weight;
+  const bool use_mis = it.enable_mis();
+  const bool use_epan = (it.kernel == 1u);
+
+#pragma unroll 1
+  for (uint32_t c = 0; c < 8; ++c) {
+    uint32_t cell = grid_cell_index(g.hash_table_mask, (c & 1u) ? bcx : acx, (c & 2u) ? bcy : acy, (c & 4u) ? bcz : acz);
+    uint2 range = __ldg(&g.cell_range[cell]);
+    V3 cell_merged = {0.0f, 0.0f, 0.0f};
+    for (uint32_t j = range.x; j < range.y; ++j) {
+      float4 pd = __ldg(&g.pos_dvcm[j]);
+      candidates += 1;
+      V3 d = V3{pd.x, pd.y, pd.z} - pos;
+      float distance_squared = dot(d, d);
+      float4 wl = __ldg(&g.win_len[j]);
+      if ((distance_squared > g.radius_squared) || (__float_as_uint(wl.w) + state.total_path_depth + 1 > sc.max_path_length)) continue;
+      float4 nd = __ldg(&g.nrm_dvm[j]);
+      if (dot(isect.nrm, V3{nd.x, nd.y, nd.z}) <= kEpsilon) continue;
+      const V3 wi = {wl.x, wl.y, wl.z};
+      BEval<SP> camera_bsdf = bsdf_evaluate<SP>(sc, camera_data, -wi, mat, state.sampler);
+      if (camera_bsdf.valid() == false) continue;
+      float camera_rev_pdf = bsdf_reverse_pdf<SP>(sc, camera_data, -wi, mat, state.sampler);
+      accepts += 1;
+      float w_light = pd.w * it.vc_weight + nd.w * camera_bsdf.pdf;
+      float w_camera = w_camera_base + state.d_vm * camera_rev_pdf;
+      float weight = use_mis ? (1.0f / (1.0f + w_light + w_camera)) : 1.0f;
+      float kernel_weight = 1.0f;
+      float u2 = distance_squared * g.inv_radius_squared;
+      if (use_epan) {
+        float one_minus = 1.0f - u2;
+        kernel_weight = fmaxf(2.0f * one_minus, 0.0f);
+      }
+      Spec<SP> t_camera = state.throughput / sampling_pdf<SP>(state.wavelength);
+      V3 c_value = spec_to_rgb<SP>(sc, camera_bsdf.func * t_camera, state.wavelength);
+      float4 lt = __ldg(&g.thr_rgb[j]);
+      V3 l_value = {lt.x, lt.y, lt.z};
+      if (SP) {
+        l_value *= V3{0.817660332f, 1.05418909f, 1.09945524f};
+      }
+      cell_merged += (c_value * l_value) * (kernel_weight * weight);
+    }
+    merged += cell_merged;
+  }
+  return merged;
+}
+
+}  // namespace etxb

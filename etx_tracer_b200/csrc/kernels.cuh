@@ -1,0 +1,558 @@
+// kernels.cuh — the wavefront kernels of one VCM iteration (included once, by module.cu).
+//
+// Stage list (reference decomposition: bin/optix/vcm/*.cu + vcm_cpu.cxx:95-241, redesigned for sm_100a):
+//   light pass : k_light_begin -> { k_trace_closest -> k_light_bounce }*          (queues of path ids, ping-pong)
+//   vertices   : scan(counts) -> k_lv_reorder (path-major pool, = the oracle's vertex order)
+//   photon map : k_grid_bbox -> k_grid_keys -> radix sort (stable) -> k_grid_build
+//   camera pass: k_camera_begin -> { k_trace_closest -> k_camera_bounce }*  (film accumulate on path death)
+//   film       : k_film_commit_light, k_film_resolve
+// Path state lives in HBM as SoA float4/uint4 columns indexed by path id (128-bit coalesced loads/stores);
+// queues are compacted with warp ballot + one atomic per warp.
+#pragma once
+#include "dvcm.cuh"
+
+namespace etxb {
+
+struct PathBuffers {
+  float4* ray_o;     // o.xyz, min_t
+  float4* ray_d;     // d.xyz, max_t
+  float4* thr;       // throughput (x[,y,z]), path_distance
+  float4* mis;       // d_vcm, d_vc, d_vm, eta
+  uint4* misc;       // sampler seed, total_path_depth, medium_index, flags
+  float4* hit;       // u, v, t, triangle index (bits)
+  float4* gathered;  // camera: gathered.xyz
+  float4* merged;    // camera: merged.xyz
+  float* wavelength;
+  uint32_t* lv_count;  // light: vertices stored by the path (VCMLightPath::count)
+};
+
+struct DeviceCounters {
+  unsigned long long rays_closest, rays_shadow, nodes, tris, bounces_light, bounces_camera, light_vertices, connections, merge_queries, merge_candidates, merge_accepts,
+    splats;
+};
+
+struct FilmBuffers {
+  float4* camera;           // running mean over iterations (y-flipped storage like film.cxx:189)
+  float4* light;            // running mean
+  float4* light_iteration;  // per-iteration splats
+  uint32_t width, height;
+};
+
+struct LaunchParams {
+  DeviceScene scene;
+  VcmParams vcm;
+  PathBuffers paths;
+  FilmBuffers film;
+  GridData grid;
+  LightVertexRec* lv_tmp;    // allocation order
+  LightVertexRec* lv_final;  // path-major order
+  uint32_t* lv_tmp_count;
+  uint32_t lv_capacity;
+  const uint32_t* lp_offset;  // VCMLightPath::index
+  uint32_t* overflow;
+  DeviceCounters* counters;
+  uint32_t* sampler_end_light;   // debug taps (ETXB_BUF_LIGHT_SAMPLER / CAMERA_SAMPLER)
+  uint32_t* sampler_end_camera;
+  float4* camera_value;          // ETXB_BUF_CAMERA_GATHERED
+  uint32_t path_count;           // N = W*H
+  uint32_t rank, world;          // pixel-tile partition
+  uint32_t camera_sample_index;  // Film sample_count of every pixel before this iteration
+};
+
+#ifdef ETXB_COUNT_TRAVERSAL
+#define STATS_DECL TraverseStats stats_obj; TraverseStats* stats = &stats_obj
+#define STATS_NODES stats_obj.nodes
+#define STATS_TRIS stats_obj.tris
+#else
+#define STATS_DECL TraverseStats* stats = nullptr
+#define STATS_NODES 0u
+#define STATS_TRIS 0u
+#endif
+
+DEV void counter_add(unsigned long long* dst, uint32_t v) {
+  uint32_t total = __reduce_add_sync(__activemask(), v);
+  uint32_t leader = __ffs(__activemask()) - 1;
+  if ((threadIdx.x & 31u) == leader && total) atomicAdd(dst, (unsigned long long)total);
+}
+
+// warp-aggregated append of `id` to a queue when `alive`
+DEV void queue_push(uint32_t* queue, uint32_t* queue_count, bool alive, uint32_t id) {
+  uint32_t mask = __activemask();
+  uint32_t ballot = __ballot_sync(mask, alive);
+  if (ballot == 0) return;
+  uint32_t lane = threadIdx.x & 31u;
+  uint32_t leader = __ffs(ballot) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(queue_count, __popc(ballot));
+  base = __shfl_sync(mask, base, leader);
+  if (alive) queue[base + __popc(ballot & ((1u << lane) - 1u))] = id;
+}
+
+DEV bool pixel_owned(const LaunchParams& p, uint32_t index) {
+  if (p.world <= 1u) return true;
+  uint32_t x = index % p.film.width, y = index / p.film.width;
+  uint32_t tiles_x = (p.film.width + 31u) / 32u;
+  uint32_t tile = (y / 32u) * tiles_x + (x / 32u);
+  return (tile % p.world) == p.rank;
+}
+
+template <bool SP>
+DEV void store_state(const PathBuffers& b, uint32_t i, const PathState<SP>& s) {
+  V3 t = s.throughput.as_v3();
+  b.ray_o[i] = make_float4(s.ray_o.x, s.ray_o.y, s.ray_o.z, s.ray_min_t);
+  b.ray_d[i] = make_float4(s.ray_d.x, s.ray_d.y, s.ray_d.z, s.ray_max_t);
+  b.thr[i] = make_float4(t.x, t.y, t.z, s.path_distance);
+  b.mis[i] = make_float4(s.d_vcm, s.d_vc, s.d_vm, s.eta);
+  b.misc[i] = make_uint4(s.sampler.seed, s.total_path_depth, s.medium_index, s.flags);
+}
+template <bool SP>
+DEV PathState<SP> load_state(const PathBuffers& b, uint32_t i) {
+  PathState<SP> s;
+  float4 o = b.ray_o[i], d = b.ray_d[i], t = b.thr[i], m = b.mis[i];
+  uint4 u = b.misc[i];
+  s.ray_o = {o.x, o.y, o.z};
+  s.ray_min_t = o.w;
+  s.ray_d = {d.x, d.y, d.z};
+  s.ray_max_t = d.w;
+  s.throughput = Spec<SP>::make3({t.x, t.y, t.z});
+  s.path_distance = t.w;
+  s.d_vcm = m.x;
+  s.d_vc = m.y;
+  s.d_vm = m.z;
+  s.eta = m.w;
+  s.sampler.seed = u.x;
+  s.sampler.fixed_u = s.sampler.fixed_v = s.sampler.fixed_w = 0.0f;
+  s.total_path_depth = u.y;
+  s.medium_index = u.z;
+  s.flags = u.w;
+  s.wavelength = b.wavelength[i];
+  s.gathered = Spec<SP>::make(0.0f);
+  s.merged = {0.0f, 0.0f, 0.0f};
+  s.lv_count = 0;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// light pass
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool SP>
+__global__ void __launch_bounds__(128) k_light_begin(LaunchParams p, uint32_t* queue, uint32_t* queue_count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool alive = false;
+  if (i < p.path_count) {
+    bool owned = pixel_owned(p, i);
+    PathState<SP> s = generate_emitter_state<SP>(p.scene, p.vcm, i);
+    p.paths.wavelength[i] = s.wavelength;
+    p.paths.lv_count[i] = 0;
+    alive = owned && ((s.flags & kPathValid) == kPathValid);
+    if (alive) {
+      store_state<SP>(p.paths, i, s);
+    } else {
+      p.sampler_end_light[i] = s.sampler.seed;
+    }
+  }
+  queue_push(queue, queue_count, alive, i);
+}
+
+// closest-hit traversal for every queued path (Raytracing::trace, rt.cxx:428): SoA ray in, hit record out,
+// sampler advanced by one draw per candidate
+__global__ void __launch_bounds__(256) k_trace_closest(LaunchParams p, const uint32_t* queue, const uint32_t* queue_count) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= *queue_count) return;
+  uint32_t i = queue[q];
+  float4 o = p.paths.ray_o[i], d = p.paths.ray_d[i];
+  uint4 misc = p.paths.misc[i];
+  Smp smp;
+  smp.seed = misc.x;
+  smp.fixed_u = smp.fixed_v = smp.fixed_w = 0.0f;
+  STATS_DECL;
+  HitRec h = trace_closest(p.scene, {o.x, o.y, o.z}, {d.x, d.y, d.z}, o.w, d.w, smp, stats);
+  p.paths.hit[i] = make_float4(h.u, h.v, h.t, __uint_as_float(h.tri));
+  p.paths.misc[i].x = smp.seed;
+  counter_add(&p.counters->rays_closest, 1u);
+  counter_add(&p.counters->nodes, STATS_NODES);
+  counter_add(&p.counters->tris, STATS_TRIS);
+}
+
+// vcm_light_step after the trace (vcm_shared.hxx:1090-1260), surface events
+template <bool SP>
+__global__ void __launch_bounds__(128) k_light_bounce(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  bool alive = false;
+  uint32_t i = 0;
+  uint32_t shadow_rays = 0, splats = 0, stored = 0;
+  STATS_DECL;
+  if (q < *count_in) {
+    i = queue_in[q];
+    const DeviceScene& sc = p.scene;
+    PathState<SP> state = load_state<SP>(p.paths, i);
+    state.lv_count = p.paths.lv_count[i];
+    float4 hit = p.paths.hit[i];
+    uint32_t tri_index = __float_as_uint(hit.w);
+    if (tri_index != kInvalidIndex) {
+      Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
+      const etxb_material& mat = sc.materials[isect.material_index];
+      BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathLight);
+      V2 rnd_bsdf = state.sampler.next_2d();
+      V2 rnd_connection = state.sampler.next_2d();
+      V2 rnd_support = state.sampler.next_2d();
+      state.sampler.push_fixed(rnd_bsdf.x, rnd_bsdf.y, rnd_support.x);
+      BSample<SP> bs = bsdf_sample<SP>(sc, bsdf_data, mat, state.sampler);
+      bool is_connectible = (bs.properties & kBsdfDelta) == 0;
+      state.sampler.pop_fixed();
+      // vcm_update_light_vcm (:451-461)
+      if ((state.total_path_depth > 0) || (state.flags & kPathLocalEmitter)) {
+        state.d_vcm *= sqr(state.path_distance + isect.t);
+      }
+      float cos_to_prev = fabsf(dot(isect.nrm, -state.ray_d));
+      state.d_vcm /= cos_to_prev;
+      state.d_vc /= cos_to_prev;
+      state.d_vm /= cos_to_prev;
+      state.path_distance = 0.0f;
+
+      if (is_connectible) {
+        // store the light vertex (warp-aggregated slot allocation; k_lv_reorder makes the pool path-major)
+        uint32_t slot = atomicAdd(p.lv_tmp_count, 1u);
+        if (slot < p.lv_capacity) {
+          LightVertexRec rec = make_light_vertex<SP>(state, isect, i);
+          float4* dst = reinterpret_cast<float4*>(p.lv_tmp + slot);
+          dst[0] = rec.thr_dvcm;
+          dst[1] = rec.wi_dvc;
+          dst[2] = rec.bc_dvm;
+          dst[3] = rec.pos_tri;
+          dst[4] = rec.nrm_mat;
+          reinterpret_cast<uint4*>(dst)[5] = rec.ids;
+          state.lv_count += 1;
+          stored = 1;
+        } else {
+          *p.overflow = 1u;
+        }
+        if (p.vcm.connect_to_camera() && (state.total_path_depth + 1 <= sc.max_path_length)) {
+          state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
+          Spec<SP> value;
+          V2 uv;
+          bool ok = vcm_connect_to_camera<SP>(sc, p.vcm, isect, state, value, uv, stats, shadow_rays);
+          state.sampler.pop_fixed();
+          if (ok && (value.maximum() > kEpsilon)) {
+            // vcm_cpu.cxx:147-154 + Film::atomic_add_light_iteration (film.cxx:147-171)
+            V3 val = spec_to_rgb<SP>(sc, value, state.wavelength) / sampling_pdf<SP>(state.wavelength);
+            if (dot(val, val) > kEpsilon) {
+              V2 uv01 = uv * 0.5f + 0.5f;
+              uint32_t x = static_cast<uint32_t>(uv01.x * float(p.film.width));
+              uint32_t y = static_cast<uint32_t>(uv01.y * float(p.film.height));
+              if ((x < p.film.width) && (y < p.film.height)) {
+                float* dst = reinterpret_cast<float*>(p.film.light_iteration + (x + (p.film.height - 1u - y) * p.film.width));
+                atomicAdd(dst + 0, val.x);
+                atomicAdd(dst + 1, val.y);
+                atomicAdd(dst + 2, val.z);
+              }
+              splats = 1;
+            }
+          }
+        }
+      }
+      if (vcm_next_ray<SP>(sc, true, state, p.vcm, isect, bsdf_data, bs)) {
+        alive = state.total_path_depth + 1u < sc.max_path_length;
+      }
+    }
+    p.paths.lv_count[i] = state.lv_count;
+    if (alive) {
+      store_state<SP>(p.paths, i, state);
+    } else {
+      p.sampler_end_light[i] = state.sampler.seed;
+    }
+  }
+  queue_push(queue_out, count_out, alive, i);
+  counter_add(&p.counters->bounces_light, (q < *count_in) ? 1u : 0u);
+  counter_add(&p.counters->rays_shadow, shadow_rays);
+  counter_add(&p.counters->splats, splats);
+  counter_add(&p.counters->light_vertices, stored);
+  counter_add(&p.counters->nodes, STATS_NODES);
+  counter_add(&p.counters->tris, STATS_TRIS);
+}
+
+// pool in allocation order -> path-major order: dst = VCMLightPath::index + ordinal (vcm_cpu.cxx:155-171)
+__global__ void __launch_bounds__(256) k_lv_reorder(LaunchParams p, uint32_t count) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= count) return;
+  const float4* src = reinterpret_cast<const float4*>(p.lv_tmp + s);
+  float4 r0 = src[0], r1 = src[1], r2 = src[2], r3 = src[3], r4 = src[4];
+  uint4 ids = reinterpret_cast<const uint4*>(src)[5];
+  uint32_t dst_index = p.lp_offset[ids.z] + ids.w;
+  float4* dst = reinterpret_cast<float4*>(p.lv_final + dst_index);
+  dst[0] = r0;
+  dst[1] = r1;
+  dst[2] = r2;
+  dst[3] = r3;
+  dst[4] = r4;
+  reinterpret_cast<uint4*>(dst)[5] = ids;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// photon hash grid (VCMSpatialGrid::construct, vcm_shared.cxx:49-152)
+// ---------------------------------------------------------------------------------------------------------------------
+DEV uint32_t float_to_ordered(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float ordered_to_float(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  union { uint32_t u; float f; } c;
+  c.u = u;
+  return c.f;
+}
+
+// bbox[0..2] = min (ordered uint), bbox[3..5] = max
+__global__ void __launch_bounds__(256) k_grid_bbox(const LightVertexRec* pool, uint32_t count, uint32_t* bbox) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  float mn[3] = {kMaxFloat, kMaxFloat, kMaxFloat}, mx[3] = {-kMaxFloat, -kMaxFloat, -kMaxFloat};
+  if (s < count) {
+    float4 pt = reinterpret_cast<const float4*>(pool + s)[3];
+    mn[0] = mx[0] = pt.x;
+    mn[1] = mx[1] = pt.y;
+    mn[2] = mx[2] = pt.z;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+      mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+    }
+  }
+  if ((threadIdx.x & 31u) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      atomicMin(&bbox[k], float_to_ordered(mn[k]));
+      atomicMax(&bbox[3 + k], float_to_ordered(mx[k]));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_grid_keys(const LightVertexRec* pool, uint32_t count, const uint32_t* bbox, float cell_size, uint32_t mask, uint32_t* keys,
+  uint32_t* values) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= count) return;
+  V3 bmin = {ordered_to_float(bbox[0]), ordered_to_float(bbox[1]), ordered_to_float(bbox[2])};
+  float4 pt = reinterpret_cast<const float4*>(pool + s)[3];
+  keys[s] = grid_position_to_index({pt.x, pt.y, pt.z}, bmin, cell_size, mask);
+  values[s] = s;
+}
+
+// after the stable sort by cell: gather photon SoA (60 B -> 4 x 16 B) and mark [begin,end) per cell
+template <bool SP>
+__global__ void __launch_bounds__(256) k_grid_build(LaunchParams p, const uint32_t* sorted_keys, const uint32_t* sorted_values, uint32_t count, uint2* cell_range,
+  float4* pos_dvcm, float4* nrm_dvm, float4* win_len, float4* thr_rgb) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  uint32_t key = sorted_keys[j];
+  if ((j == 0) || (sorted_keys[j - 1] != key)) cell_range[key].x = j;
+  if ((j + 1 == count) || (sorted_keys[j + 1] != key)) cell_range[key].y = j + 1;
+  const float4* src = reinterpret_cast<const float4*>(p.lv_final + sorted_values[j]);
+  float4 r0 = src[0], r1 = src[1], r2 = src[2], r3 = src[3], r4 = src[4];
+  uint4 ids = reinterpret_cast<const uint4*>(src)[5];
+  pos_dvcm[j] = make_float4(r3.x, r3.y, r3.z, r0.w);
+  nrm_dvm[j] = make_float4(r4.x, r4.y, r4.z, r2.w);
+  win_len[j] = make_float4(r1.x, r1.y, r1.z, __uint_as_float(ids.y));
+  // (s.throughput / s.throughput.sampling_pdf()).to_rgb() (vcm_shared.cxx:141); the path's wavelength travels with it
+  float wavelength = p.paths.wavelength[ids.z];
+  Spec<SP> t = Spec<SP>::make3({r0.x, r0.y, r0.z}) / sampling_pdf<SP>(wavelength);
+  V3 rgb = spec_to_rgb<SP>(p.scene, t, wavelength);
+  thr_rgb[j] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// camera pass
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool SP>
+__global__ void __launch_bounds__(128) k_camera_begin(LaunchParams p, uint32_t* queue, uint32_t* queue_count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool alive = false;
+  if (i < p.path_count) {
+    alive = pixel_owned(p, i);
+    if (alive) {
+      uint32_t px = i % p.film.width, py = i / p.film.width;
+      PathState<SP> s = generate_camera_state<SP>(p.scene, p.vcm, px, py, i, p.paths.wavelength[i]);
+      p.paths.wavelength[i] = s.wavelength;
+      store_state<SP>(p.paths, i, s);
+      p.paths.gathered[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      p.paths.merged[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+  }
+  queue_push(queue, queue_count, alive, i);
+}
+
+// vcm_camera_step after the trace (vcm_shared.hxx:927-1079) + the per-path epilogue of gather_camera_vertices
+// (vcm_cpu.cxx:195-198) when the path ends
+template <bool SP>
+__global__ void __launch_bounds__(128) k_camera_bounce(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  bool alive = false;
+  uint32_t i = 0;
+  uint32_t shadow_rays = 0, connections = 0, merge_queries = 0, candidates = 0, accepts = 0;
+  STATS_DECL;
+  if (q < *count_in) {
+    i = queue_in[q];
+    const DeviceScene& sc = p.scene;
+    PathState<SP> state = load_state<SP>(p.paths, i);
+    float4 g = p.paths.gathered[i], mg = p.paths.merged[i];
+    state.gathered = Spec<SP>::make3({g.x, g.y, g.z});
+    state.merged = {mg.x, mg.y, mg.z};
+    float4 hit = p.paths.hit[i];
+    uint32_t tri_index = __float_as_uint(hit.w);
+    if (tri_index == kInvalidIndex) {
+      // vcm_cam_handle_miss (:537-587): environment emitters are not on the device yet (upload rejects them);
+      // only the pending boundary distance is folded
+      if (p.vcm.direct_hit() && (state.path_distance > 0.0f)) {
+        state.d_vcm *= sqr(state.path_distance);
+        state.path_distance = 0.0f;
+      }
+    } else {
+      Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
+      const etxb_material& mat = sc.materials[isect.material_index];
+      BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
+      V2 rnd_bsdf = state.sampler.next_2d();
+      V2 rnd_connection = state.sampler.next_2d();
+      V2 rnd_support = state.sampler.next_2d();
+      if (p.vcm.blue_noise && (state.total_path_depth == 1) && (p.vcm.iteration < 256u)) {
+        uint32_t px = i % p.film.width, py = i / p.film.width;
+        rnd_bsdf = sample_blue_noise(sc, px, py, p.vcm.iteration, 0);
+        rnd_connection = sample_blue_noise(sc, px, py, p.vcm.iteration, 2);
+        rnd_support = sample_blue_noise(sc, px, py, p.vcm.iteration, 4);
+      }
+      state.sampler.push_fixed(rnd_bsdf.x, rnd_bsdf.y, rnd_support.x);
+      BSample<SP> bs = bsdf_sample<SP>(sc, bsdf_data, mat, state.sampler);
+      bool is_connectible = (bs.properties & kBsdfDelta) == 0;
+      state.sampler.pop_fixed();
+      // vcm_update_camera_vcm (:589-595)
+      float cos_to_prev = fabsf(dot(isect.nrm, -state.ray_d));
+      state.d_vcm *= sqr(state.path_distance + isect.t) / cos_to_prev;
+      state.d_vc /= cos_to_prev;
+      state.d_vm /= cos_to_prev;
+      state.path_distance = 0.0f;
+      vcm_handle_direct_hit<SP>(sc, p.vcm, isect, state);
+      if (is_connectible) {
+        state.gathered += vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], isect, state, stats, shadow_rays, connections);
+        state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
+        state.gathered += vcm_connect_to_light<SP>(sc, p.vcm, isect, state, stats, shadow_rays);
+        state.sampler.pop_fixed();
+      }
+      if (is_connectible && p.vcm.merge_vertices() && (state.total_path_depth + 1 <= sc.max_path_length)) {
+        merge_queries = 1;
+        state.merged += grid_gather<SP>(sc, p.grid, p.vcm, isect, state, candidates, accepts);
+      }
+      alive = vcm_next_ray<SP>(sc, false, state, p.vcm, isect, bsdf_data, bs);
+    }
+    if (alive) {
+      store_state<SP>(p.paths, i, state);
+      V3 gv = state.gathered.as_v3();
+      p.paths.gathered[i] = make_float4(gv.x, gv.y, gv.z, 0.0f);
+      p.paths.merged[i] = make_float4(state.merged.x, state.merged.y, state.merged.z, 0.0f);
+    } else {
+      // vcm_cpu.cxx:195-198 + Film::accumulate_camera_image (film.cxx:173-230, camera layer)
+      V3 merged = state.merged;
+      merged *= p.vcm.vm_normalization;
+      merged += spec_to_rgb<SP>(sc, state.gathered / sampling_pdf<SP>(state.wavelength), state.wavelength);
+      uint32_t px = i % p.film.width, py = i / p.film.width;
+      uint32_t fi = px + (p.film.height - 1u - py) * p.film.width;
+      float4 old = p.film.camera[fi];
+      V3 result = merged;
+      if (p.camera_sample_index != 0u) {
+        double ds = double(p.camera_sample_index);
+        float t = float(ds / (ds + 1.0));
+        result = {lerpf(merged.x, old.x, t), lerpf(merged.y, old.y, t), lerpf(merged.z, old.z, t)};
+      }
+      p.film.camera[fi] = make_float4(result.x, result.y, result.z, 1.0f);
+      p.sampler_end_camera[i] = state.sampler.seed;
+      p.camera_value[i] = make_float4(merged.x, merged.y, merged.z, 0.0f);
+    }
+  }
+  queue_push(queue_out, count_out, alive, i);
+  counter_add(&p.counters->bounces_camera, (q < *count_in) ? 1u : 0u);
+  counter_add(&p.counters->rays_shadow, shadow_rays);
+  counter_add(&p.counters->connections, connections);
+  counter_add(&p.counters->merge_queries, merge_queries);
+  counter_add(&p.counters->merge_candidates, candidates);
+  counter_add(&p.counters->merge_accepts, accepts);
+  counter_add(&p.counters->nodes, STATS_NODES);
+  counter_add(&p.counters->tris, STATS_TRIS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// film (film.cxx:332-343, 381-418)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_film_commit_light(FilmBuffers film, uint32_t iteration_index) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= film.width * film.height) return;
+  float t = float(double(iteration_index) / double(iteration_index + 1u));
+  float4 s = film.light_iteration[i], d = film.light[i];
+  V3 sv = {s.x, s.y, s.z}, dv = {d.x, d.y, d.z};
+  V3 r = (t == 0.0f) ? sv : lerp3(sv, dv, t);
+  film.light[i] = make_float4(r.x, r.y, r.z, 1.0f);
+  film.light_iteration[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+__global__ void __launch_bounds__(256) k_film_resolve(FilmBuffers film, float4* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= film.width * film.height) return;
+  float4 c = film.camera[i], l = film.light[i];
+  out[i] = make_float4(fmaxf(0.0f, c.x + l.x), fmaxf(0.0f, c.y + l.y), fmaxf(0.0f, c.z + l.z), 1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// debug / known-answer kernels
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_debug_trace(DeviceScene sc, const float* rays, uint32_t* seeds, uint32_t count, float* hits_uv_t, uint32_t* hits_tri) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float* r = rays + size_t(i) * 8;
+  Smp smp;
+  smp.seed = seeds[i];
+  smp.fixed_u = smp.fixed_v = smp.fixed_w = 0.0f;
+  HitRec h = trace_closest(sc, {r[0], r[1], r[2]}, {r[4], r[5], r[6]}, r[3], r[7], smp, nullptr);
+  seeds[i] = smp.seed;
+  hits_tri[i] = h.tri;
+  bool hit = h.tri != kInvalidIndex;
+  hits_uv_t[size_t(i) * 3 + 0] = hit ? h.u : 0.0f;
+  hits_uv_t[size_t(i) * 3 + 1] = hit ? h.v : 0.0f;
+  hits_uv_t[size_t(i) * 3 + 2] = hit ? h.t : 0.0f;
+}
+
+__global__ void k_debug_sampler(const uint32_t* a, const uint32_t* b, uint32_t count, uint32_t draws, uint32_t* out_seed, float* out_values) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Smp s;
+  s.init(a[i], b[i]);
+  out_seed[size_t(i) * (draws + 1u)] = s.seed;
+  for (uint32_t d = 0; d < draws; ++d) {
+    out_values[size_t(i) * draws + d] = s.next();
+    out_seed[size_t(i) * (draws + 1u) + d + 1u] = s.seed;
+  }
+}
+
+__global__ void k_debug_math(DeviceScene sc, uint32_t fn, const float* x, const float* y, uint32_t count, float* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float a = x[i], b = y ? y[i] : 0.0f, r = 0.0f;
+  switch (fn) {
+    case 0: r = m_sin(a); break;
+    case 1: r = m_cos(a); break;
+    case 2: r = m_exp(a); break;
+    case 3: r = m_log(a); break;
+    case 4: r = m_pow(a, b); break;
+    case 5: r = m_acos(a); break;
+    case 6: r = m_atan2(a, b); break;
+    case 7: r = spectral_sample_wavelength(a); break;
+    case 8: r = spectral_sampling_pdf(a); break;
+    case 9: r = spec_to_rgb<true>(sc, Spec<true>{1.0f}, a).x; break;
+    case 10: r = spec_to_rgb<true>(sc, Spec<true>{1.0f}, a).y; break;
+    case 11: r = spec_to_rgb<true>(sc, Spec<true>{1.0f}, a).z; break;
+    case 12: r = m_atan(a); break;
+    case 13: r = m_asin(a); break;
+    case 14: r = sample_blue_noise(sc, uint32_t(a) & 127u, uint32_t(a) >> 7, uint32_t(b), 0).x; break;
+    case 15: r = sample_blue_noise(sc, uint32_t(a) & 127u, uint32_t(a) >> 7, uint32_t(b), 4).y; break;
+    default: break;
+  }
+  out[i] = r;
+}
+
+}  // namespace etxb

@@ -1,0 +1,1012 @@
+// module.cu — C ABI (include/etx_b200.h) over the wavefront kernels: context, scene upload, iteration driver.
+// Host-side counterpart of CPUVCMImpl (sources/etx/rt/integrators/vcm_cpu.cxx:30-241) and of
+// Raytracing::commit_changes (sources/etx/rt/rt.cxx:58-88).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <vector>
+
+#include "bvh_build.h"
+#include "kernels.cuh"
+
+using namespace etxb;
+
+#if defined(ETXB_PARITY) && ETXB_PARITY
+static const char* kFlavor = "parity";
+#else
+static const char* kFlavor = "fast";
+#endif
+
+namespace {
+
+enum KernelId : uint32_t {
+  K_LIGHT_BEGIN,
+  K_TRACE_LIGHT,
+  K_LIGHT_BOUNCE,
+  K_LV_SCAN,
+  K_LV_REORDER,
+  K_GRID_BBOX,
+  K_GRID_KEYS,
+  K_GRID_SORT,
+  K_GRID_BUILD,
+  K_CAMERA_BEGIN,
+  K_TRACE_CAMERA,
+  K_CAMERA_BOUNCE,
+  K_FILM_COMMIT,
+  K_COUNT
+};
+const char* kKernelNames[K_COUNT] = {"light_begin", "trace_closest(light)", "light_bounce", "lv_scan", "lv_reorder", "grid_bbox", "grid_keys", "grid_sort", "grid_build",
+  "camera_begin", "trace_closest(camera)", "camera_bounce", "film_commit_light"};
+
+template <class T>
+struct DevBuf {
+  T* ptr = nullptr;
+  size_t count = 0;
+  cudaError_t alloc(size_t n) {
+    release();
+    count = n;
+    if (n == 0) return cudaSuccess;
+    return cudaMalloc(&ptr, n * sizeof(T));
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+  size_t bytes() const { return count * sizeof(T); }
+};
+
+struct TimedLaunch {
+  uint32_t kernel;
+  cudaEvent_t start, stop;
+};
+
+}  // namespace
+
+struct etxb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  bool scene_ready = false;
+  bool spectral = false;
+  bool profile = false;
+
+  // scene in HBM
+  DevBuf<DVertex> vertices;
+  DevBuf<DTriangle> triangles;
+  DevBuf<uint32_t> tri_emitter;
+  DevBuf<etxb_material> materials;
+  DevBuf<etxb_emitter_profile> profiles;
+  DevBuf<etxb_emitter> emitters;
+  DevBuf<DSpectrum> spectra;
+  DevBuf<etxb_distribution_entry> emitter_dist;
+  DevBuf<BvhNode> bvh_nodes;
+  DevBuf<float4> bvh_tris;
+  DevBuf<float> xyz_table, rgb_response_table;
+  DevBuf<uint8_t> bn_sobol, bn_scrambling, bn_ranking;
+  float y_integral = 0.0f;
+  DeviceScene dscene = {};
+  double bvh_build_seconds = 0.0;
+
+  // per-path state + queues
+  uint32_t width = 0, height = 0, path_count = 0;
+  DevBuf<float4> ray_o, ray_d, thr, mis, hit, gathered, merged, camera_value;
+  DevBuf<uint4> misc;
+  DevBuf<float> wavelength;
+  DevBuf<uint32_t> lv_count, lp_offset, queue_a, queue_b, queue_counts, sampler_end_light, sampler_end_camera;
+  // light vertices + grid
+  uint32_t lv_capacity = 0, max_light_vertices_cfg = 0;
+  DevBuf<LightVertexRec> lv_tmp, lv_final;
+  DevBuf<uint32_t> lv_tmp_count, overflow, grid_bbox, keys_in, keys_out, vals_in, vals_out;
+  DevBuf<uint2> cell_range;
+  DevBuf<float4> g_pos, g_nrm, g_win, g_thr;
+  DevBuf<uint8_t> cub_temp;
+  DevBuf<DeviceCounters> counters;
+  // film
+  DevBuf<float4> film_camera, film_light, film_light_iteration, film_out;
+
+  etxb_vcm_options options = {};
+  uint32_t iteration = 0;            // absolute iteration index (VCMIteration::iteration)
+  uint32_t completed = 0;            // iterations finished since etxb_begin
+  uint32_t rank = 0, world = 1;
+  uint32_t last_light_vertices = 0;
+  uint32_t overflow_flag = 0;
+  double last_iteration_time = 0.0, total_time = 0.0;
+  uint64_t kernel_launches = 0;
+  GridData grid = {};
+  bool light_pass_done = false, grid_done = false;
+
+  cudaEvent_t ev_iter_start = nullptr, ev_iter_stop = nullptr;
+  std::vector<TimedLaunch> timed;
+  std::vector<cudaEvent_t> event_pool;
+  size_t event_cursor = 0;
+  float kernel_ms[K_COUNT] = {};
+  uint32_t kernel_count[K_COUNT] = {};
+};
+
+namespace {
+
+int fail(etxb_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list args;
+  va_start(args, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, args);
+  va_end(args);
+  if (ctx) ctx->error = buf;
+  return code;
+}
+
+#define CUDA_OK(ctx, call)                                                                                   \
+  do {                                                                                                       \
+    cudaError_t err__ = (call);                                                                              \
+    if (err__ != cudaSuccess) {                                                                              \
+      return fail(ctx, (err__ == cudaErrorMemoryAllocation) ? ETXB_ERR_OUT_OF_MEMORY : ETXB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), \
+        __FILE__, __LINE__);                                                                                 \
+    }                                                                                                        \
+  } while (0)
+
+template <class T>
+int upload(etxb_ctx* ctx, DevBuf<T>& buf, const T* host, size_t n) {
+  CUDA_OK(ctx, buf.alloc(std::max<size_t>(n, 1)));
+  if (n) CUDA_OK(ctx, cudaMemcpyAsync(buf.ptr, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return ETXB_OK;
+}
+
+cudaEvent_t next_event(etxb_ctx* ctx) {
+  if (ctx->event_cursor == ctx->event_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->event_pool.push_back(e);
+  }
+  return ctx->event_pool[ctx->event_cursor++];
+}
+
+struct LaunchTimer {
+  etxb_ctx* ctx;
+  TimedLaunch t;
+  LaunchTimer(etxb_ctx* c, uint32_t kernel) : ctx(c) {
+    ctx->kernel_launches += 1;
+    ctx->kernel_count[kernel] += 1;
+    if (ctx->profile) {
+      t.kernel = kernel;
+      t.start = next_event(ctx);
+      t.stop = next_event(ctx);
+      cudaEventRecord(t.start, ctx->stream);
+    }
+  }
+  ~LaunchTimer() {
+    if (ctx->profile) {
+      cudaEventRecord(t.stop, ctx->stream);
+      ctx->timed.push_back(t);
+    }
+  }
+};
+
+bool material_class_supported_host(uint32_t cls) { return (cls == ETXB_MAT_DIFFUSE) || (cls == ETXB_MAT_DIELECTRIC); }
+
+uint32_t next_pow2(uint64_t v) {
+  // next_power_of_two (math.hxx:1001-1010)
+  v--;
+  v |= v >> 1;
+  v |= v >> 2;
+  v |= v >> 4;
+  v |= v >> 8;
+  v |= v >> 16;
+  v |= v >> 32;
+  v++;
+  return uint32_t(v);
+}
+
+LaunchParams make_params(etxb_ctx* ctx) {
+  LaunchParams p = {};
+  p.scene = ctx->dscene;
+  p.paths = {ctx->ray_o.ptr, ctx->ray_d.ptr, ctx->thr.ptr, ctx->mis.ptr, ctx->misc.ptr, ctx->hit.ptr, ctx->gathered.ptr, ctx->merged.ptr, ctx->wavelength.ptr,
+    ctx->lv_count.ptr};
+  p.film = {ctx->film_camera.ptr, ctx->film_light.ptr, ctx->film_light_iteration.ptr, ctx->width, ctx->height};
+  p.grid = ctx->grid;
+  p.lv_tmp = ctx->lv_tmp.ptr;
+  p.lv_final = ctx->lv_final.ptr;
+  p.lv_tmp_count = ctx->lv_tmp_count.ptr;
+  p.lv_capacity = ctx->lv_capacity;
+  p.lp_offset = ctx->lp_offset.ptr;
+  p.overflow = ctx->overflow.ptr;
+  p.counters = ctx->counters.ptr;
+  p.sampler_end_light = ctx->sampler_end_light.ptr;
+  p.sampler_end_camera = ctx->sampler_end_camera.ptr;
+  p.camera_value = ctx->camera_value.ptr;
+  p.path_count = ctx->path_count;
+  p.rank = ctx->rank;
+  p.world = ctx->world;
+  p.camera_sample_index = ctx->completed;
+  // start_next_iteration (vcm_cpu.cxx:95-113)
+  VcmParams& v = p.vcm;
+  v.options = ctx->options.options;
+  v.kernel = ctx->options.kernel;
+  v.blue_noise = (ctx->options.blue_noise != 0) && ctx->dscene.has_blue_noise;
+  v.iteration = ctx->iteration;
+  float used_radius = ctx->options.initial_radius;
+  if (used_radius == 0.0f) {
+    uint32_t max_dim = std::max(ctx->width, ctx->height);
+    used_radius = 5.0f * ctx->dscene.bounding_sphere_radius / float(max_dim);
+  }
+  float radius_scale = 1.0f / (1.0f + float(ctx->iteration) / float(ctx->options.radius_decay));
+  v.current_radius = used_radius * radius_scale;
+  float eta_vcm = kPi * (v.current_radius * v.current_radius) * float(ctx->path_count);
+  v.vc_weight = 1.0f / eta_vcm;
+  v.vm_weight = (ctx->options.options & ETXB_VCM_ENABLE_MERGING) ? eta_vcm : 0.0f;
+  v.vm_normalization = 1.0f / eta_vcm;
+  return p;
+}
+
+uint32_t blocks_for(uint32_t n, uint32_t block) { return (n + block - 1u) / block; }
+
+int read_u32(etxb_ctx* ctx, const uint32_t* dptr, uint32_t& out) {
+  CUDA_OK(ctx, cudaMemcpyAsync(&out, dptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETXB_OK;
+}
+
+template <bool SP>
+int run_light_pass(etxb_ctx* ctx) {
+  LaunchParams p = make_params(ctx);
+  uint32_t* counts = ctx->queue_counts.ptr;  // [0] = current, [1] = next
+  CUDA_OK(ctx, cudaMemsetAsync(counts, 0, 8, ctx->stream));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->lv_tmp_count.ptr, 0, 4, ctx->stream));
+  uint32_t* qin = ctx->queue_a.ptr;
+  uint32_t* qout = ctx->queue_b.ptr;
+  {
+    LaunchTimer t(ctx, K_LIGHT_BEGIN);
+    k_light_begin<SP><<<blocks_for(ctx->path_count, 128), 128, 0, ctx->stream>>>(p, qin, counts + 0);
+  }
+  uint32_t active = 0;
+  if (int rc = read_u32(ctx, counts + 0, active)) return rc;
+  uint32_t cur = 0;
+  while (active > 0) {
+    {
+      LaunchTimer t(ctx, K_TRACE_LIGHT);
+      k_trace_closest<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, qin, counts + cur);
+    }
+    CUDA_OK(ctx, cudaMemsetAsync(counts + (cur ^ 1u), 0, 4, ctx->stream));
+    {
+      LaunchTimer t(ctx, K_LIGHT_BOUNCE);
+      k_light_bounce<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur, qout, counts + (cur ^ 1u));
+    }
+    cur ^= 1u;
+    std::swap(qin, qout);
+    if (int rc = read_u32(ctx, counts + cur, active)) return rc;
+  }
+  CUDA_OK(ctx, cudaGetLastError());
+
+  // path-major vertex pool: offsets = exclusive scan of per-path counts (VCMLightPath::index)
+  uint32_t total = 0;
+  if (int rc = read_u32(ctx, ctx->lv_tmp_count.ptr, total)) return rc;
+  uint32_t ovf = 0;
+  if (int rc = read_u32(ctx, ctx->overflow.ptr, ovf)) return rc;
+  ctx->overflow_flag |= ovf;
+  total = std::min(total, ctx->lv_capacity);
+  {
+    LaunchTimer t(ctx, K_LV_SCAN);
+    size_t temp_bytes = ctx->cub_temp.bytes();
+    CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_temp.ptr, temp_bytes, ctx->lv_count.ptr, ctx->lp_offset.ptr, int(ctx->path_count), ctx->stream));
+  }
+  if (total > 0) {
+    LaunchTimer t(ctx, K_LV_REORDER);
+    k_lv_reorder<<<blocks_for(total, 256), 256, 0, ctx->stream>>>(p, total);
+  }
+  ctx->last_light_vertices = total;
+  {
+    LaunchTimer t(ctx, K_FILM_COMMIT);
+    // complete_light_vertices -> Film::commit_light_iteration(iteration) (vcm_cpu.cxx:209-211)
+    k_film_commit_light<<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(p.film, ctx->iteration);
+  }
+  CUDA_OK(ctx, cudaGetLastError());
+  ctx->light_pass_done = true;
+  return ETXB_OK;
+}
+
+template <bool SP>
+int run_grid_build(etxb_ctx* ctx) {
+  ctx->grid = {};
+  ctx->grid_done = true;
+  bool merging = (ctx->options.options & ETXB_VCM_ENABLE_MERGING) && (ctx->options.options & ETXB_VCM_MERGE_VERTICES);
+  uint32_t count = ctx->last_light_vertices;
+  if (!merging || (count == 0)) return ETXB_OK;
+  LaunchParams p = make_params(ctx);
+  float radius = p.vcm.current_radius;
+  uint32_t init[6];
+  for (int k = 0; k < 3; ++k) {
+    init[k] = 0xffffffffu;
+    init[3 + k] = 0u;
+  }
+  CUDA_OK(ctx, cudaMemcpyAsync(ctx->grid_bbox.ptr, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  {
+    LaunchTimer t(ctx, K_GRID_BBOX);
+    k_grid_bbox<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(ctx->lv_final.ptr, count, ctx->grid_bbox.ptr);
+  }
+  uint32_t table_size = next_pow2(count);
+  uint32_t mask = table_size - 1u;
+  float cell_size = 2.0f * radius;
+  {
+    LaunchTimer t(ctx, K_GRID_KEYS);
+    k_grid_keys<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(ctx->lv_final.ptr, count, ctx->grid_bbox.ptr, cell_size, mask, ctx->keys_in.ptr, ctx->vals_in.ptr);
+  }
+  {
+    LaunchTimer t(ctx, K_GRID_SORT);
+    size_t temp_bytes = ctx->cub_temp.bytes();
+    int end_bit = 1;
+    while ((1ull << end_bit) < table_size) end_bit++;
+    CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->keys_in.ptr, ctx->keys_out.ptr, ctx->vals_in.ptr, ctx->vals_out.ptr, int(count), 0,
+                   end_bit, ctx->stream));
+  }
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->cell_range.ptr, 0, size_t(table_size) * sizeof(uint2), ctx->stream));
+  {
+    LaunchTimer t(ctx, K_GRID_BUILD);
+    k_grid_build<SP><<<blocks_for(count, 256), 256, 0, ctx->stream>>>(p, ctx->keys_out.ptr, ctx->vals_out.ptr, count, ctx->cell_range.ptr, ctx->g_pos.ptr, ctx->g_nrm.ptr,
+      ctx->g_win.ptr, ctx->g_thr.ptr);
+  }
+  uint32_t bbox[6];
+  CUDA_OK(ctx, cudaMemcpyAsync(bbox, ctx->grid_bbox.ptr, sizeof(bbox), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  GridData& g = ctx->grid;
+  g.cell_range = ctx->cell_range.ptr;
+  g.pos_dvcm = ctx->g_pos.ptr;
+  g.nrm_dvm = ctx->g_nrm.ptr;
+  g.win_len = ctx->g_win.ptr;
+  g.thr_rgb = ctx->g_thr.ptr;
+  g.bbox_min = {ordered_to_float(bbox[0]), ordered_to_float(bbox[1]), ordered_to_float(bbox[2])};
+  g.bbox_max = {ordered_to_float(bbox[3]), ordered_to_float(bbox[4]), ordered_to_float(bbox[5])};
+  g.hash_table_mask = mask;
+  g.photon_count = count;
+  g.cell_size = cell_size;
+  g.radius_squared = radius * radius;
+  g.inv_radius_squared = (g.radius_squared > 0.0f) ? 1.0f / g.radius_squared : 0.0f;
+  CUDA_OK(ctx, cudaGetLastError());
+  return ETXB_OK;
+}
+
+template <bool SP>
+int run_camera_pass(etxb_ctx* ctx) {
+  LaunchParams p = make_params(ctx);
+  uint32_t* counts = ctx->queue_counts.ptr;
+  CUDA_OK(ctx, cudaMemsetAsync(counts, 0, 8, ctx->stream));
+  uint32_t* qin = ctx->queue_a.ptr;
+  uint32_t* qout = ctx->queue_b.ptr;
+  {
+    LaunchTimer t(ctx, K_CAMERA_BEGIN);
+    k_camera_begin<SP><<<blocks_for(ctx->path_count, 128), 128, 0, ctx->stream>>>(p, qin, counts + 0);
+  }
+  uint32_t active = 0;
+  if (int rc = read_u32(ctx, counts + 0, active)) return rc;
+  uint32_t cur = 0;
+  while (active > 0) {
+    {
+      LaunchTimer t(ctx, K_TRACE_CAMERA);
+      k_trace_closest<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, qin, counts + cur);
+    }
+    CUDA_OK(ctx, cudaMemsetAsync(counts + (cur ^ 1u), 0, 4, ctx->stream));
+    {
+      LaunchTimer t(ctx, K_CAMERA_BOUNCE);
+      k_camera_bounce<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur, qout, counts + (cur ^ 1u));
+    }
+    cur ^= 1u;
+    std::swap(qin, qout);
+    if (int rc = read_u32(ctx, counts + cur, active)) return rc;
+  }
+  CUDA_OK(ctx, cudaGetLastError());
+  return ETXB_OK;
+}
+
+void resolve_timers(etxb_ctx* ctx) {
+  for (auto& t : ctx->timed) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, t.start, t.stop) == cudaSuccess) ctx->kernel_ms[t.kernel] += ms;
+  }
+  ctx->timed.clear();
+  ctx->event_cursor = 0;
+}
+
+int finish_iteration(etxb_ctx* ctx) {
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev_iter_stop, ctx->stream));
+  CUDA_OK(ctx, cudaEventSynchronize(ctx->ev_iter_stop));
+  float ms = 0.0f;
+  CUDA_OK(ctx, cudaEventElapsedTime(&ms, ctx->ev_iter_start, ctx->ev_iter_stop));
+  ctx->last_iteration_time = double(ms) * 1e-3;
+  ctx->total_time += ctx->last_iteration_time;
+  resolve_timers(ctx);
+  ctx->completed += 1;
+  ctx->iteration += 1;
+  ctx->light_pass_done = false;
+  ctx->grid_done = false;
+  return ETXB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* etxb_build_flavor(void) { return kFlavor; }
+
+int etxb_device_count(void) {
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess) return ETXB_ERR_NO_DEVICE;
+  return n;
+}
+
+int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
+  if (!out_ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  *out_ctx = nullptr;
+  int n = etxb_device_count();
+  if (n <= 0) return ETXB_ERR_NO_DEVICE;
+  int device = cfg ? cfg->device_index : 0;
+  if (device < 0 || device >= n) return ETXB_ERR_INVALID_ARGUMENT;
+  if (cudaSetDevice(device) != cudaSuccess) return ETXB_ERR_CUDA;
+  auto* ctx = new etxb_ctx();
+  ctx->device = device;
+  ctx->max_light_vertices_cfg = cfg ? cfg->max_light_vertices : 0;
+  ctx->profile = cfg ? (cfg->flags & 1u) != 0 : false;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return ETXB_ERR_CUDA;
+  }
+  cudaEventCreate(&ctx->ev_iter_start);
+  cudaEventCreate(&ctx->ev_iter_stop);
+  etxb_options_default(&ctx->options);
+  *out_ctx = ctx;
+  return ETXB_OK;
+}
+
+void etxb_destroy(etxb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  cudaEventDestroy(ctx->ev_iter_start);
+  cudaEventDestroy(ctx->ev_iter_stop);
+  DevBuf<float4>* f4[] = {&ctx->ray_o, &ctx->ray_d, &ctx->thr, &ctx->mis, &ctx->hit, &ctx->gathered, &ctx->merged, &ctx->camera_value, &ctx->bvh_tris, &ctx->g_pos, &ctx->g_nrm,
+    &ctx->g_win, &ctx->g_thr, &ctx->film_camera, &ctx->film_light, &ctx->film_light_iteration, &ctx->film_out};
+  for (auto* b : f4) b->release();
+  DevBuf<uint32_t>* u32[] = {&ctx->tri_emitter, &ctx->lv_count, &ctx->lp_offset, &ctx->queue_a, &ctx->queue_b, &ctx->queue_counts, &ctx->sampler_end_light,
+    &ctx->sampler_end_camera, &ctx->lv_tmp_count, &ctx->overflow, &ctx->grid_bbox, &ctx->keys_in, &ctx->keys_out, &ctx->vals_in, &ctx->vals_out};
+  for (auto* b : u32) b->release();
+  ctx->vertices.release();
+  ctx->triangles.release();
+  ctx->materials.release();
+  ctx->profiles.release();
+  ctx->emitters.release();
+  ctx->spectra.release();
+  ctx->emitter_dist.release();
+  ctx->bvh_nodes.release();
+  ctx->xyz_table.release();
+  ctx->rgb_response_table.release();
+  ctx->bn_sobol.release();
+  ctx->bn_scrambling.release();
+  ctx->bn_ranking.release();
+  ctx->misc.release();
+  ctx->wavelength.release();
+  ctx->lv_tmp.release();
+  ctx->lv_final.release();
+  ctx->cell_range.release();
+  ctx->cub_temp.release();
+  ctx->counters.release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* etxb_last_error(const etxb_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int etxb_upload_color_tables(etxb_ctx* ctx, const float* xyz_441x3, const float* rgb_response_391x3) {
+  if (!ctx || !xyz_441x3 || !rgb_response_391x3) return ETXB_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  if (int rc = upload(ctx, ctx->xyz_table, xyz_441x3, 441 * 3)) return rc;
+  if (int rc = upload(ctx, ctx->rgb_response_table, rgb_response_391x3, 391 * 3)) return rc;
+  float sum = 0.0f;  // spectrum::kYIntegral (spectrum.hxx:187-193): float sum in table order
+  for (int i = 0; i < 441; ++i) sum += xyz_441x3[i * 3 + 1];
+  ctx->y_integral = sum;
+  ctx->dscene.xyz_table = ctx->xyz_table.ptr;
+  ctx->dscene.rgb_response_table = ctx->rgb_response_table.ptr;
+  ctx->dscene.y_scale = 1.0f / sum;
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETXB_OK;
+}
+
+int etxb_upload_blue_noise(etxb_ctx* ctx, const uint8_t* sobol_256x256, const uint8_t* scrambling, const uint8_t* ranking) {
+  if (!ctx || !sobol_256x256 || !scrambling || !ranking) return ETXB_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  if (int rc = upload(ctx, ctx->bn_sobol, sobol_256x256, 256 * 256)) return rc;
+  if (int rc = upload(ctx, ctx->bn_scrambling, scrambling, 128 * 128 * 8)) return rc;
+  if (int rc = upload(ctx, ctx->bn_ranking, ranking, 128 * 128 * 8)) return rc;
+  ctx->dscene.bn_sobol = ctx->bn_sobol.ptr;
+  ctx->dscene.bn_scrambling = ctx->bn_scrambling.ptr;
+  ctx->dscene.bn_ranking = ctx->bn_ranking.ptr;
+  ctx->dscene.has_blue_noise = 1;
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETXB_OK;
+}
+
+int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_bytes, const void* camera_blob, uint64_t camera_bytes) {
+  if (!ctx || !scene_blob || !camera_blob) return ETXB_ERR_INVALID_ARGUMENT;
+  if (scene_bytes != sizeof(etxb_scene) || camera_bytes != sizeof(etxb_camera))
+    return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "scene/camera size mismatch: got %llu/%llu, expected %zu/%zu", (unsigned long long)scene_bytes,
+      (unsigned long long)camera_bytes, sizeof(etxb_scene), sizeof(etxb_camera));
+  if (!ctx->xyz_table.ptr) return fail(ctx, ETXB_ERR_NOT_READY, "etxb_upload_color_tables must be called before etxb_upload_scene");
+  cudaSetDevice(ctx->device);
+  ctx->scene_ready = false;
+  const etxb_scene& s = *static_cast<const etxb_scene*>(scene_blob);
+  const etxb_camera& cam = *static_cast<const etxb_camera*>(camera_blob);
+
+  // ---- what the device path does not cover yet fails loudly (no CPU fallback) --------------------------------------
+  if (cam.cls != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "equirectangular camera is not supported on the device yet");
+  if (cam.lens_image != ETXB_INVALID_INDEX) return fail(ctx, ETXB_ERR_UNSUPPORTED, "lens aperture image is not supported on the device yet");
+  if (s.mediums.count != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "participating media are not supported on the device yet");
+  const auto* mats = static_cast<const etxb_material*>(s.materials.a);
+  for (uint64_t i = 0; i < s.materials.count; ++i) {
+    const etxb_material& m = mats[i];
+    if (!material_class_supported_host(m.cls)) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: class %u is not supported on the device yet", (unsigned long long)i, m.cls);
+    if (m.diffuse_variation != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: diffuse_variation %u is not supported on the device yet", (unsigned long long)i, m.diffuse_variation);
+    if (m.subsurface.cls != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: subsurface scattering is not supported on the device yet", (unsigned long long)i);
+    uint32_t imgs[] = {m.reflectance.image_index, m.scattering.image_index, m.emission.image_index, m.roughness.image_index, m.normal_image_index, m.thinfilm.thickness_image};
+    for (uint32_t im : imgs)
+      if (im != ETXB_INVALID_INDEX) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: textures are not supported on the device yet", (unsigned long long)i);
+    if (m.int_medium != ETXB_INVALID_INDEX || m.ext_medium != ETXB_INVALID_INDEX)
+      return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: media are not supported on the device yet", (unsigned long long)i);
+  }
+  const auto* emitters = static_cast<const etxb_emitter*>(s.emitter_instances.a);
+  for (uint64_t i = 0; i < s.emitter_instances.count; ++i) {
+    if (emitters[i].cls != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "emitter %llu: only area emitters are supported on the device yet", (unsigned long long)i);
+  }
+  if (s.emitter_instances.count == 0) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "scene has no emitters");
+  const auto* spectra = static_cast<const etxb_spectrum*>(s.spectrums.a);
+  std::vector<DSpectrum> dspec(s.spectrums.count);
+  for (uint64_t i = 0; i < s.spectrums.count; ++i) {
+    const etxb_spectrum& sp = spectra[i];
+    if (sp.entry_count != 441) return fail(ctx, ETXB_ERR_UNSUPPORTED, "spectrum %llu has %u entries; the loader's 441-entry 390..830 nm grid is required", (unsigned long long)i, sp.entry_count);
+    for (uint32_t k = 0; k < 441; ++k) {
+      if (sp.entries[k].wavelength != float(390 + k)) return fail(ctx, ETXB_ERR_UNSUPPORTED, "spectrum %llu is not on the integer 390..830 nm grid", (unsigned long long)i);
+      dspec[i].power[k] = sp.entries[k].power;
+    }
+    memcpy(dspec[i].rgb, sp.integrated, 12);
+  }
+
+  // ---- geometry ------------------------------------------------------------------------------------------------------
+  const auto* verts = static_cast<const etxb_vertex*>(s.vertices.a);
+  std::vector<DVertex> dverts(s.vertices.count);
+  for (uint64_t i = 0; i < s.vertices.count; ++i) {
+    const etxb_vertex& v = verts[i];
+    dverts[i].pos_u = make_float4(v.pos[0], v.pos[1], v.pos[2], v.tex[0]);
+    dverts[i].nrm_v = make_float4(v.nrm[0], v.nrm[1], v.nrm[2], v.tex[1]);
+    dverts[i].tan = make_float4(v.tan[0], v.tan[1], v.tan[2], 0.0f);
+    dverts[i].btn = make_float4(v.btn[0], v.btn[1], v.btn[2], 0.0f);
+  }
+  static_assert(sizeof(DTriangle) == sizeof(etxb_triangle), "triangle layout");
+  Bvh bvh;
+  {
+    cudaEvent_t dummy;
+    (void)dummy;
+    auto t0 = std::clock();
+    build_bvh(reinterpret_cast<const float*>(s.vertices.a), sizeof(etxb_vertex), reinterpret_cast<const uint32_t*>(s.triangles.a), sizeof(etxb_triangle),
+      uint32_t(s.triangles.count), bvh);
+    ctx->bvh_build_seconds = double(std::clock() - t0) / CLOCKS_PER_SEC;
+  }
+  if (int rc = upload(ctx, ctx->vertices, dverts.data(), dverts.size())) return rc;
+  if (int rc = upload(ctx, ctx->triangles, reinterpret_cast<const DTriangle*>(s.triangles.a), size_t(s.triangles.count))) return rc;
+  if (int rc = upload(ctx, ctx->tri_emitter, static_cast<const uint32_t*>(s.triangle_to_emitter.a), size_t(s.triangle_to_emitter.count))) return rc;
+  if (int rc = upload(ctx, ctx->materials, mats, size_t(s.materials.count))) return rc;
+  if (int rc = upload(ctx, ctx->profiles, static_cast<const etxb_emitter_profile*>(s.emitter_profiles.a), size_t(s.emitter_profiles.count))) return rc;
+  if (int rc = upload(ctx, ctx->emitters, emitters, size_t(s.emitter_instances.count))) return rc;
+  if (int rc = upload(ctx, ctx->spectra, dspec.data(), dspec.size())) return rc;
+  if (int rc = upload(ctx, ctx->emitter_dist, static_cast<const etxb_distribution_entry*>(s.emitters_distribution.values.a), size_t(s.emitters_distribution.values.count)))
+    return rc;
+  if (int rc = upload(ctx, ctx->bvh_nodes, bvh.nodes.data(), bvh.nodes.size())) return rc;
+  if (int rc = upload(ctx, ctx->bvh_tris, reinterpret_cast<const float4*>(bvh.tri_pos.data()), bvh.tri_pos.size())) return rc;
+
+  DeviceScene& d = ctx->dscene;
+  d.vertices = ctx->vertices.ptr;
+  d.triangles = ctx->triangles.ptr;
+  d.tri_emitter = ctx->tri_emitter.ptr;
+  d.materials = ctx->materials.ptr;
+  d.emitter_profiles = ctx->profiles.ptr;
+  d.emitters = ctx->emitters.ptr;
+  d.spectra = ctx->spectra.ptr;
+  d.emitter_dist = ctx->emitter_dist.ptr;
+  d.bvh_nodes = ctx->bvh_nodes.ptr;
+  d.bvh_tris = ctx->bvh_tris.ptr;
+  d.emitter_count = uint32_t(s.emitter_instances.count);
+  d.triangle_count = uint32_t(s.triangles.count);
+  d.emitter_total_weight = s.emitters_distribution.total_weight;
+  memcpy(d.env_emitters, s.environment_emitters, sizeof(d.env_emitters));
+  d.env_emitter_count = s.environment_emitter_count;
+  d.bounding_sphere_center = {s.bounding_sphere_center[0], s.bounding_sphere_center[1], s.bounding_sphere_center[2]};
+  d.bounding_sphere_radius = s.bounding_sphere_radius;
+  d.min_path_length = s.min_path_length;
+  d.max_path_length = s.max_path_length;
+  d.samples = s.samples;
+  d.random_path_termination = s.random_path_termination;
+  d.spectral = (s.flags & ETXB_SCENE_SPECTRAL) ? 1u : 0u;
+  d.camera = cam;
+  ctx->spectral = d.spectral != 0;
+
+  // ---- film + queues (Film::allocate, film.cxx) ----------------------------------------------------------------------
+  ctx->width = cam.film_size[0];
+  ctx->height = cam.film_size[1];
+  ctx->path_count = ctx->width * ctx->height;
+  size_t n = ctx->path_count;
+  if (n == 0) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "empty film");
+  DevBuf<float4>* per_path_f4[] = {&ctx->ray_o, &ctx->ray_d, &ctx->thr, &ctx->mis, &ctx->hit, &ctx->gathered, &ctx->merged, &ctx->camera_value, &ctx->film_camera,
+    &ctx->film_light, &ctx->film_light_iteration, &ctx->film_out};
+  for (auto* b : per_path_f4) CUDA_OK(ctx, b->alloc(n));
+  CUDA_OK(ctx, ctx->misc.alloc(n));
+  CUDA_OK(ctx, ctx->wavelength.alloc(n));
+  DevBuf<uint32_t>* per_path_u32[] = {&ctx->lv_count, &ctx->lp_offset, &ctx->queue_a, &ctx->queue_b, &ctx->sampler_end_light, &ctx->sampler_end_camera};
+  for (auto* b : per_path_u32) CUDA_OK(ctx, b->alloc(n));
+  CUDA_OK(ctx, ctx->queue_counts.alloc(4));
+  CUDA_OK(ctx, ctx->lv_tmp_count.alloc(1));
+  CUDA_OK(ctx, ctx->overflow.alloc(1));
+  CUDA_OK(ctx, ctx->grid_bbox.alloc(8));
+  CUDA_OK(ctx, ctx->counters.alloc(1));
+  uint64_t cap = ctx->max_light_vertices_cfg ? ctx->max_light_vertices_cfg : uint64_t(n) * 16ull;
+  cap = std::min<uint64_t>(cap, 0x7fffffffull);
+  ctx->lv_capacity = uint32_t(cap);
+  CUDA_OK(ctx, ctx->lv_tmp.alloc(cap));
+  CUDA_OK(ctx, ctx->lv_final.alloc(cap));
+  DevBuf<uint32_t>* per_vertex_u32[] = {&ctx->keys_in, &ctx->keys_out, &ctx->vals_in, &ctx->vals_out};
+  for (auto* b : per_vertex_u32) CUDA_OK(ctx, b->alloc(cap));
+  DevBuf<float4>* per_vertex_f4[] = {&ctx->g_pos, &ctx->g_nrm, &ctx->g_win, &ctx->g_thr};
+  for (auto* b : per_vertex_f4) CUDA_OK(ctx, b->alloc(cap));
+  CUDA_OK(ctx, ctx->cell_range.alloc(next_pow2(cap)));
+  size_t temp_sort = 0, temp_scan = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, temp_sort, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, int(cap));
+  cub::DeviceScan::ExclusiveSum(nullptr, temp_scan, (uint32_t*)nullptr, (uint32_t*)nullptr, int(n));
+  CUDA_OK(ctx, ctx->cub_temp.alloc(std::max(temp_sort, temp_scan) + 256));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->overflow.ptr, 0, 4, ctx->stream));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(DeviceCounters), ctx->stream));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->sampler_end_light.ptr, 0, n * 4, ctx->stream));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->sampler_end_camera.ptr, 0, n * 4, ctx->stream));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->lv_count.ptr, 0, n * 4, ctx->stream));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->lp_offset.ptr, 0, n * 4, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->scene_ready = true;
+  return etxb_begin(ctx, 0);
+}
+
+void etxb_options_default(etxb_vcm_options* opt) {
+  if (!opt) return;
+  opt->options = ETXB_VCM_FULL;
+  opt->radius_decay = 256u;
+  opt->kernel = 1u;
+  opt->initial_radius = 0.0f;
+  opt->blue_noise = 1u;
+}
+
+int etxb_options_set_key(etxb_vcm_options* opt, const char* key, double value) {
+  if (!opt || !key) return ETXB_ERR_INVALID_ARGUMENT;
+  auto set_bit = [&](uint32_t bit) { opt->options = (value != 0.0) ? (opt->options | bit) : (opt->options & ~bit); };
+  std::string k = key;
+  if (k == "vcm-initial_radius") opt->initial_radius = float(value);
+  else if (k == "vcm-radius_decay") opt->radius_decay = uint32_t(value);
+  else if (k == "vcm-blue_noise") opt->blue_noise = value != 0.0;
+  else if (k == "vcm-kernel") opt->kernel = uint32_t(value);
+  else if (k == "vcm-direct_hit") set_bit(ETXB_VCM_DIRECT_HIT);
+  else if (k == "vcm-connect_to_light") set_bit(ETXB_VCM_CONNECT_TO_LIGHT);
+  else if (k == "vcm-connect_to_camera") set_bit(ETXB_VCM_CONNECT_TO_CAMERA);
+  else if (k == "vcm-connect_vertices") set_bit(ETXB_VCM_CONNECT_VERTICES);
+  else if (k == "vcm-merge_vertices") set_bit(ETXB_VCM_MERGE_VERTICES);
+  else if (k == "vcm-mis") set_bit(ETXB_VCM_ENABLE_MIS);
+  else if (k == "vcm-merging") set_bit(ETXB_VCM_ENABLE_MERGING);
+  else return ETXB_ERR_INVALID_ARGUMENT;
+  return ETXB_OK;
+}
+
+int etxb_set_options(etxb_ctx* ctx, const etxb_vcm_options* opt) {
+  if (!ctx || !opt) return ETXB_ERR_INVALID_ARGUMENT;
+  if (opt->radius_decay == 0) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "radius_decay must be >= 1");
+  ctx->options = *opt;
+  return ETXB_OK;
+}
+
+int etxb_set_partition(etxb_ctx* ctx, uint32_t rank, uint32_t world) {
+  if (!ctx || world == 0 || rank >= world) return ETXB_ERR_INVALID_ARGUMENT;
+  ctx->rank = rank;
+  ctx->world = world;
+  return ETXB_OK;
+}
+
+int etxb_begin(etxb_ctx* ctx, uint32_t first_iteration) {
+  if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  if (!ctx->scene_ready) return fail(ctx, ETXB_ERR_NOT_READY, "no scene uploaded");
+  cudaSetDevice(ctx->device);
+  size_t n = ctx->path_count;
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->film_camera.ptr, 0, n * 16, ctx->stream));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->film_light.ptr, 0, n * 16, ctx->stream));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->film_light_iteration.ptr, 0, n * 16, ctx->stream));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(DeviceCounters), ctx->stream));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->overflow.ptr, 0, 4, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->iteration = first_iteration;
+  ctx->completed = 0;
+  ctx->total_time = 0.0;
+  ctx->last_iteration_time = 0.0;
+  ctx->overflow_flag = 0;
+  ctx->kernel_launches = 0;
+  ctx->light_pass_done = ctx->grid_done = false;
+  memset(ctx->kernel_ms, 0, sizeof(ctx->kernel_ms));
+  memset(ctx->kernel_count, 0, sizeof(ctx->kernel_count));
+  return ETXB_OK;
+}
+
+int etxb_enqueue_light_pass(etxb_ctx* ctx) {
+  if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  if (!ctx->scene_ready) return fail(ctx, ETXB_ERR_NOT_READY, "no scene uploaded");
+  cudaSetDevice(ctx->device);
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev_iter_start, ctx->stream));
+  return ctx->spectral ? run_light_pass<true>(ctx) : run_light_pass<false>(ctx);
+}
+
+int etxb_enqueue_grid_build(etxb_ctx* ctx, const void* device_photon_records, uint64_t photon_count) {
+  if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  if (!ctx->light_pass_done) return fail(ctx, ETXB_ERR_NOT_READY, "light pass has not run");
+  cudaSetDevice(ctx->device);
+  if (device_photon_records != nullptr) {
+    // multi-GPU: the caller all-gathered every rank's path-major records (ETXB_BUF_PHOTON_RECORDS) into one buffer
+    if (photon_count > ctx->lv_capacity) return fail(ctx, ETXB_ERR_OVERFLOW, "gathered photon count %llu exceeds capacity %u", (unsigned long long)photon_count, ctx->lv_capacity);
+    // the merge only needs the grid SoA, so the gathered records are staged in lv_tmp (free after the reorder) — see run_grid_build_from
+    return fail(ctx, ETXB_ERR_UNSUPPORTED, "external photon records are handled by etxb_enqueue_grid_build_gathered in a later round");
+  }
+  return ctx->spectral ? run_grid_build<true>(ctx) : run_grid_build<false>(ctx);
+}
+
+int etxb_enqueue_camera_pass(etxb_ctx* ctx) {
+  if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  if (!ctx->light_pass_done || !ctx->grid_done) return fail(ctx, ETXB_ERR_NOT_READY, "light pass / grid build have not run");
+  cudaSetDevice(ctx->device);
+  int rc = ctx->spectral ? run_camera_pass<true>(ctx) : run_camera_pass<false>(ctx);
+  if (rc) return rc;
+  return finish_iteration(ctx);
+}
+
+int etxb_enqueue_iteration(etxb_ctx* ctx) {
+  if (int rc = etxb_enqueue_light_pass(ctx)) return rc;
+  if (int rc = etxb_enqueue_grid_build(ctx, nullptr, 0)) return rc;
+  return etxb_enqueue_camera_pass(ctx);
+}
+
+int etxb_poll(etxb_ctx* ctx, etxb_status* status) {
+  if (!ctx || !status) return ETXB_ERR_INVALID_ARGUMENT;
+  memset(status, 0, sizeof(*status));
+  status->last_iteration_time = ctx->last_iteration_time;
+  status->total_time = ctx->total_time;
+  status->completed_iterations = ctx->completed;
+  status->current_iteration = ctx->iteration;
+  status->iteration_in_flight = 0;
+  status->light_vertices = ctx->last_light_vertices;
+  status->overflow = ctx->overflow_flag;
+  return ETXB_OK;
+}
+
+int etxb_wait(etxb_ctx* ctx) {
+  if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETXB_OK;
+}
+
+int etxb_stop(etxb_ctx* ctx, int) { return etxb_wait(ctx); }
+
+int etxb_film_size(const etxb_ctx* ctx, uint32_t* width, uint32_t* height) {
+  if (!ctx || !width || !height) return ETXB_ERR_INVALID_ARGUMENT;
+  *width = ctx->width;
+  *height = ctx->height;
+  return ETXB_OK;
+}
+
+int etxb_read_film(etxb_ctx* ctx, uint32_t layer, float* dst_rgba, uint64_t dst_bytes) {
+  if (!ctx || !dst_rgba) return ETXB_ERR_INVALID_ARGUMENT;
+  if (!ctx->scene_ready) return fail(ctx, ETXB_ERR_NOT_READY, "no scene uploaded");
+  size_t n = ctx->path_count;
+  if (dst_bytes < n * 16) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "film buffer too small");
+  cudaSetDevice(ctx->device);
+  const float4* src = nullptr;
+  switch (layer) {
+    case ETXB_FILM_RESULT: {
+      FilmBuffers film = {ctx->film_camera.ptr, ctx->film_light.ptr, ctx->film_light_iteration.ptr, ctx->width, ctx->height};
+      k_film_resolve<<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(film, ctx->film_out.ptr);
+      ctx->kernel_launches += 1;
+      src = ctx->film_out.ptr;
+      break;
+    }
+    case ETXB_FILM_CAMERA:
+      src = ctx->film_camera.ptr;
+      break;
+    case ETXB_FILM_LIGHT:
+      src = ctx->film_light.ptr;
+      break;
+    case ETXB_FILM_LIGHT_ITERATION:
+      src = ctx->film_light_iteration.ptr;
+      break;
+    default:
+      return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "unknown film layer %u", layer);
+  }
+  CUDA_OK(ctx, cudaMemcpyAsync(dst_rgba, src, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETXB_OK;
+}
+
+int etxb_get_counters(etxb_ctx* ctx, etxb_counters* out) {
+  if (!ctx || !out) return ETXB_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  DeviceCounters c;
+  CUDA_OK(ctx, cudaMemcpyAsync(&c, ctx->counters.ptr, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  out->rays_closest = c.rays_closest;
+  out->rays_shadow = c.rays_shadow;
+  out->nodes_visited = c.nodes;
+  out->tris_tested = c.tris;
+  out->bounces_light = c.bounces_light;
+  out->bounces_camera = c.bounces_camera;
+  out->light_vertices = c.light_vertices;
+  out->connections = c.connections;
+  out->merge_queries = c.merge_queries;
+  out->merge_candidates = c.merge_candidates;
+  out->merge_accepts = c.merge_accepts;
+  out->splats = c.splats;
+  out->kernel_launches = ctx->kernel_launches;
+  return ETXB_OK;
+}
+
+int etxb_get_kernel_times(etxb_ctx* ctx, const char** names, float* ms, uint32_t* launches, uint32_t capacity) {
+  if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  uint32_t n = std::min<uint32_t>(capacity, K_COUNT);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (names) names[i] = kKernelNames[i];
+    if (ms) ms[i] = ctx->kernel_ms[i];
+    if (launches) launches[i] = ctx->kernel_count[i];
+  }
+  return int(K_COUNT);
+}
+
+int etxb_device_pointer(etxb_ctx* ctx, uint32_t buffer_id, void** out_ptr, uint64_t* out_bytes) {
+  if (!ctx || !out_ptr || !out_bytes) return ETXB_ERR_INVALID_ARGUMENT;
+  size_t n = ctx->path_count;
+  switch (buffer_id) {
+    case ETXB_BUF_LIGHT_PATH_COUNT: *out_ptr = ctx->lv_count.ptr; *out_bytes = n * 4; break;
+    case ETXB_BUF_LIGHT_PATH_OFFSET: *out_ptr = ctx->lp_offset.ptr; *out_bytes = n * 4; break;
+    case ETXB_BUF_LIGHT_PATH_WAVELENGTH: *out_ptr = ctx->wavelength.ptr; *out_bytes = n * 4; break;
+    case ETXB_BUF_LIGHT_SAMPLER: *out_ptr = ctx->sampler_end_light.ptr; *out_bytes = n * 4; break;
+    case ETXB_BUF_CAMERA_SAMPLER: *out_ptr = ctx->sampler_end_camera.ptr; *out_bytes = n * 4; break;
+    case ETXB_BUF_FILM_LIGHT_ITERATION: *out_ptr = ctx->film_light_iteration.ptr; *out_bytes = n * 16; break;
+    case ETXB_BUF_FILM_CAMERA: *out_ptr = ctx->film_camera.ptr; *out_bytes = n * 16; break;
+    case ETXB_BUF_FILM_LIGHT: *out_ptr = ctx->film_light.ptr; *out_bytes = n * 16; break;
+    case ETXB_BUF_PHOTON_RECORDS: *out_ptr = ctx->lv_final.ptr; *out_bytes = size_t(ctx->last_light_vertices) * sizeof(LightVertexRec); break;
+    case ETXB_BUF_CAMERA_GATHERED: *out_ptr = ctx->camera_value.ptr; *out_bytes = n * 16; break;
+    default: return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "buffer %u has no direct device pointer", buffer_id);
+  }
+  return ETXB_OK;
+}
+
+int etxb_read_buffer(etxb_ctx* ctx, uint32_t buffer_id, void* dst, uint64_t dst_bytes, uint64_t* out_bytes) {
+  if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  size_t lv = ctx->last_light_vertices;
+  if (buffer_id == ETXB_BUF_LV_POS || buffer_id == ETXB_BUF_LV_THROUGHPUT || buffer_id == ETXB_BUF_LV_MIS) {
+    uint64_t need = lv * 12;
+    if (out_bytes) *out_bytes = need;
+    if (!dst) return ETXB_OK;
+    if (dst_bytes < need) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "buffer too small");
+    std::vector<LightVertexRec> host(lv);
+    if (lv) CUDA_OK(ctx, cudaMemcpy(host.data(), ctx->lv_final.ptr, lv * sizeof(LightVertexRec), cudaMemcpyDeviceToHost));
+    float* out = static_cast<float*>(dst);
+    for (size_t i = 0; i < lv; ++i) {
+      const LightVertexRec& r = host[i];
+      if (buffer_id == ETXB_BUF_LV_POS) {
+        out[i * 3 + 0] = r.pos_tri.x; out[i * 3 + 1] = r.pos_tri.y; out[i * 3 + 2] = r.pos_tri.z;
+      } else if (buffer_id == ETXB_BUF_LV_THROUGHPUT) {
+        out[i * 3 + 0] = r.thr_dvcm.x; out[i * 3 + 1] = r.thr_dvcm.y; out[i * 3 + 2] = r.thr_dvcm.z;
+      } else {
+        out[i * 3 + 0] = r.thr_dvcm.w; out[i * 3 + 1] = r.wi_dvc.w; out[i * 3 + 2] = r.bc_dvm.w;
+      }
+    }
+    return ETXB_OK;
+  }
+  void* ptr = nullptr;
+  uint64_t bytes = 0;
+  if (int rc = etxb_device_pointer(ctx, buffer_id, &ptr, &bytes)) return rc;
+  if (buffer_id == ETXB_BUF_CAMERA_GATHERED) {
+    uint64_t need = uint64_t(ctx->path_count) * 12;
+    if (out_bytes) *out_bytes = need;
+    if (!dst) return ETXB_OK;
+    if (dst_bytes < need) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "buffer too small");
+    std::vector<float4> host(ctx->path_count);
+    CUDA_OK(ctx, cudaMemcpy(host.data(), ptr, bytes, cudaMemcpyDeviceToHost));
+    float* out = static_cast<float*>(dst);
+    for (size_t i = 0; i < host.size(); ++i) {
+      out[i * 3 + 0] = host[i].x; out[i * 3 + 1] = host[i].y; out[i * 3 + 2] = host[i].z;
+    }
+    return ETXB_OK;
+  }
+  if (out_bytes) *out_bytes = bytes;
+  if (!dst) return ETXB_OK;
+  if (dst_bytes < bytes) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "buffer too small");
+  if (bytes) CUDA_OK(ctx, cudaMemcpy(dst, ptr, bytes, cudaMemcpyDeviceToHost));
+  return ETXB_OK;
+}
+
+void* etxb_stream(etxb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int etxb_debug_trace(etxb_ctx* ctx, const float* rays, uint32_t* seeds, uint32_t count, float* hits_uv_t, uint32_t* hits_tri) {
+  if (!ctx || !rays || !seeds || !hits_uv_t || !hits_tri) return ETXB_ERR_INVALID_ARGUMENT;
+  if (!ctx->scene_ready) return fail(ctx, ETXB_ERR_NOT_READY, "no scene uploaded");
+  cudaSetDevice(ctx->device);
+  DevBuf<float> d_rays, d_uvt;
+  DevBuf<uint32_t> d_seeds, d_tri;
+  CUDA_OK(ctx, d_rays.alloc(size_t(count) * 8));
+  CUDA_OK(ctx, d_uvt.alloc(size_t(count) * 3));
+  CUDA_OK(ctx, d_seeds.alloc(count));
+  CUDA_OK(ctx, d_tri.alloc(count));
+  CUDA_OK(ctx, cudaMemcpy(d_rays.ptr, rays, d_rays.bytes(), cudaMemcpyHostToDevice));
+  CUDA_OK(ctx, cudaMemcpy(d_seeds.ptr, seeds, d_seeds.bytes(), cudaMemcpyHostToDevice));
+  k_debug_trace<<<blocks_for(count, 128), 128, 0, ctx->stream>>>(ctx->dscene, d_rays.ptr, d_seeds.ptr, count, d_uvt.ptr, d_tri.ptr);
+  ctx->kernel_launches += 1;
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_OK(ctx, cudaMemcpy(seeds, d_seeds.ptr, d_seeds.bytes(), cudaMemcpyDeviceToHost));
+  CUDA_OK(ctx, cudaMemcpy(hits_uv_t, d_uvt.ptr, d_uvt.bytes(), cudaMemcpyDeviceToHost));
+  CUDA_OK(ctx, cudaMemcpy(hits_tri, d_tri.ptr, d_tri.bytes(), cudaMemcpyDeviceToHost));
+  d_rays.release();
+  d_uvt.release();
+  d_seeds.release();
+  d_tri.release();
+  return ETXB_OK;
+}
+
+int etxb_debug_sampler(etxb_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t count, uint32_t draws, uint32_t* out_seed, float* out_values) {
+  if (!ctx || !a || !b || !out_seed || !out_values) return ETXB_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  DevBuf<uint32_t> da, db, ds;
+  DevBuf<float> dv;
+  CUDA_OK(ctx, da.alloc(count));
+  CUDA_OK(ctx, db.alloc(count));
+  CUDA_OK(ctx, ds.alloc(size_t(count) * (draws + 1)));
+  CUDA_OK(ctx, dv.alloc(size_t(count) * std::max(draws, 1u)));
+  CUDA_OK(ctx, cudaMemcpy(da.ptr, a, da.bytes(), cudaMemcpyHostToDevice));
+  CUDA_OK(ctx, cudaMemcpy(db.ptr, b, db.bytes(), cudaMemcpyHostToDevice));
+  k_debug_sampler<<<blocks_for(count, 128), 128, 0, ctx->stream>>>(da.ptr, db.ptr, count, draws, ds.ptr, dv.ptr);
+  ctx->kernel_launches += 1;
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_OK(ctx, cudaMemcpy(out_seed, ds.ptr, ds.bytes(), cudaMemcpyDeviceToHost));
+  if (draws) CUDA_OK(ctx, cudaMemcpy(out_values, dv.ptr, size_t(count) * draws * 4, cudaMemcpyDeviceToHost));
+  da.release();
+  db.release();
+  ds.release();
+  dv.release();
+  return ETXB_OK;
+}
+
+int etxb_debug_math(etxb_ctx* ctx, uint32_t fn, const float* x, const float* y, uint32_t count, float* out) {
+  if (!ctx || !x || !out) return ETXB_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  DevBuf<float> dx, dy, dout;
+  CUDA_OK(ctx, dx.alloc(count));
+  CUDA_OK(ctx, dout.alloc(count));
+  CUDA_OK(ctx, cudaMemcpy(dx.ptr, x, dx.bytes(), cudaMemcpyHostToDevice));
+  if (y) {
+    CUDA_OK(ctx, dy.alloc(count));
+    CUDA_OK(ctx, cudaMemcpy(dy.ptr, y, dy.bytes(), cudaMemcpyHostToDevice));
+  }
+  k_debug_math<<<blocks_for(count, 128), 128, 0, ctx->stream>>>(ctx->dscene, fn, dx.ptr, y ? dy.ptr : nullptr, count, dout.ptr);
+  ctx->kernel_launches += 1;
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_OK(ctx, cudaMemcpy(out, dout.ptr, dout.bytes(), cudaMemcpyDeviceToHost));
+  dx.release();
+  dy.release();
+  dout.release();
+  return ETXB_OK;
+}
+
+}  // extern "C"
