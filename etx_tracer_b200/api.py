@@ -173,8 +173,9 @@ class GPUVCM:
     def light_pass(self):
         self._check(self.lib.etxb_enqueue_light_pass(self.h))
 
-    def grid_build(self):
-        self._check(self.lib.etxb_enqueue_grid_build(self.h, None, 0))
+    def grid_build(self, records_ptr=None, count=0):
+        """complete_light_vertices: commits the light image, builds the photon grid (from gathered records in multi-GPU runs)."""
+        self._check(self.lib.etxb_enqueue_grid_build(self.h, records_ptr, count))
 
     def camera_pass(self):
         self._check(self.lib.etxb_enqueue_camera_pass(self.h))

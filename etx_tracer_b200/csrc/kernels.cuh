@@ -4,7 +4,7 @@
 //   light pass : k_light_begin -> { k_trace_closest -> k_light_bounce }*          (queues of path ids, ping-pong)
 //   vertices   : scan(counts) -> k_lv_reorder (path-major pool, = the oracle's vertex order)
 //   photon map : k_grid_bbox -> k_grid_keys -> radix sort (stable) -> k_grid_build
-//   camera pass: k_camera_begin -> { k_trace_closest -> k_camera_bounce }*  (film accumulate on path death)
+//   camera pass: k_camera_begin -> { k_trace_closest -> k_camera_shade -> k_camera_merge -> k_camera_continue }*
 //   film       : k_film_commit_light, k_film_resolve
 // Path state lives in HBM as SoA float4/uint4 columns indexed by path id (128-bit coalesced loads/stores);
 // queues are compacted with warp ballot + one atomic per warp.
@@ -24,6 +24,10 @@ struct PathBuffers {
   float4* merged;    // camera: merged.xyz
   float* wavelength;
   uint32_t* lv_count;  // light: vertices stored by the path (VCMLightPath::count)
+  float4* bs_weight_pdf;  // camera: pending BSDF sample between the shade and continue stages: weight, pdf
+  float4* bs_wo_eta;      //         w_o, eta
+  uint2* bs_props;        //         properties, medium index
+  uint32_t* merge_key;    // camera: per queue slot, Morton code of the merge query's base grid cell (0xffffffff = no merge)
 };
 
 struct DeviceCounters {
@@ -381,22 +385,41 @@ __global__ void __launch_bounds__(128) k_camera_begin(LaunchParams p, uint32_t* 
   queue_push(queue, queue_count, alive, i);
 }
 
-// vcm_camera_step after the trace (vcm_shared.hxx:927-1079) + the per-path epilogue of gather_camera_vertices
-// (vcm_cpu.cxx:195-198) when the path ends
+// Sort key of a merge query: Morton code of its base grid cell, so that queries which read the same photon cells are
+// processed back to back (L1/L2 reuse instead of ~19 KB of DRAM traffic per incoherent query).
+DEV uint32_t morton_part(uint32_t v) {
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+DEV uint32_t merge_query_key(const GridData& g, V3 pos) {
+  if (!((pos.x >= g.bbox_min.x) && (pos.y >= g.bbox_min.y) && (pos.z >= g.bbox_min.z) && (pos.x <= g.bbox_max.x) && (pos.y <= g.bbox_max.y) && (pos.z <= g.bbox_max.z)))
+    return 0xffffffffu;
+  V3 m = vfloor((pos - g.bbox_min) / g.cell_size);
+  uint32_t x = umin(uint32_t(m.x), 1023u), y = umin(uint32_t(m.y), 1023u), z = umin(uint32_t(m.z), 1023u);
+  return morton_part(x) | (morton_part(y) << 1) | (morton_part(z) << 2);
+}
+
+// vcm_camera_step after the trace (vcm_shared.hxx:927-1079), split into the wavefront stages
+//   shade    : intersection, 6 pre-drawn randoms (+ blue noise), BSDF sample, MIS update, direct hit, vertex connections, NEE
+//   merge    : hash-grid photon gather (VCMSpatialGridData::gather, :886-924) — warp-cooperative in the product build
+//   continue : vcm_next_ray (RR, recurrences, next ray) or, when the path ends, the epilogue of gather_camera_vertices
+//              (vcm_cpu.cxx:195-198) + Film::accumulate_camera_image
+// The pending BSDF sample travels between stages in `bs_*` (40 B per path).
 template <bool SP>
-__global__ void __launch_bounds__(128) k_camera_bounce(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
+__global__ void __launch_bounds__(128) k_camera_shade(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  bool alive = false;
-  uint32_t i = 0;
-  uint32_t shadow_rays = 0, connections = 0, merge_queries = 0, candidates = 0, accepts = 0;
+  uint32_t shadow_rays = 0, connections = 0;
+  uint32_t merge_key = 0xffffffffu;
   STATS_DECL;
   if (q < *count_in) {
-    i = queue_in[q];
+    uint32_t i = queue_in[q];
     const DeviceScene& sc = p.scene;
     PathState<SP> state = load_state<SP>(p.paths, i);
-    float4 g = p.paths.gathered[i], mg = p.paths.merged[i];
+    float4 g = p.paths.gathered[i];
     state.gathered = Spec<SP>::make3({g.x, g.y, g.z});
-    state.merged = {mg.x, mg.y, mg.z};
     float4 hit = p.paths.hit[i];
     uint32_t tri_index = __float_as_uint(hit.w);
     if (tri_index == kInvalidIndex) {
@@ -436,22 +459,285 @@ __global__ void __launch_bounds__(128) k_camera_bounce(LaunchParams p, const uin
         state.gathered += vcm_connect_to_light<SP>(sc, p.vcm, isect, state, stats, shadow_rays);
         state.sampler.pop_fixed();
       }
-      if (is_connectible && p.vcm.merge_vertices() && (state.total_path_depth + 1 <= sc.max_path_length)) {
-        merge_queries = 1;
-        state.merged += grid_gather<SP>(sc, p.grid, p.vcm, isect, state, candidates, accepts);
+      if (is_connectible && p.vcm.merge_vertices() && (state.total_path_depth + 1 <= sc.max_path_length) && (p.grid.photon_count != 0u)) {
+        merge_key = merge_query_key(p.grid, isect.pos);
       }
+      V3 w = bs.weight.as_v3();
+      p.paths.bs_weight_pdf[i] = make_float4(w.x, w.y, w.z, bs.pdf);
+      p.paths.bs_wo_eta[i] = make_float4(bs.w_o.x, bs.w_o.y, bs.w_o.z, bs.eta);
+      p.paths.bs_props[i] = make_uint2(bs.properties, bs.medium_index);
+    }
+    store_state<SP>(p.paths, i, state);
+    V3 gv = state.gathered.as_v3();
+    p.paths.gathered[i] = make_float4(gv.x, gv.y, gv.z, 0.0f);
+    p.paths.merge_key[q] = merge_key;
+  }
+  counter_add(&p.counters->bounces_camera, (q < *count_in) ? 1u : 0u);
+  counter_add(&p.counters->rays_shadow, shadow_rays);
+  counter_add(&p.counters->connections, connections);
+  counter_add(&p.counters->nodes, STATS_NODES);
+  counter_add(&p.counters->tris, STATS_TRIS);
+}
+
+// Lambert surfaces (Diffuse, variation 0: bsdf_various.hxx:36-133) evaluate without touching the sampler and their BSDF value does
+// not depend on the photon direction, so the product build gathers them with the whole warp: one query at a time is broadcast,
+// the 32 lanes test 32 photons of a cell per step (coalesced 16-B position loads), accepted lanes finish the MIS weight, and the
+// partial sums are reduced with shuffles.  Any other material class (stochastic evaluate) and the parity build take the serial,
+// reference-ordered path.
+DEV bool merge_is_lambert(const etxb_material& m) { return (m.cls == ETXB_MAT_DIFFUSE) && (m.diffuse_variation == 0u); }
+
+// Serial, reference-ordered gather (VCMSpatialGridData::gather): every merging vertex in the parity build, the non-Lambert
+// ones (stochastic evaluate consuming the path's sampler) in the product build.
+template <bool SP>
+__global__ void __launch_bounds__(128) k_camera_merge_serial(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  const DeviceScene& sc = p.scene;
+  uint32_t merge_queries = 0, candidates = 0, accepts = 0;
+  if ((q < *count_in) && (p.paths.merge_key[q] != 0xffffffffu)) {
+    uint32_t i = queue_in[q];
+    float4 hit = p.paths.hit[i];
+    uint32_t tri_index = __float_as_uint(hit.w);
+    PathState<SP> state = load_state<SP>(p.paths, i);
+    Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
+#if defined(ETXB_PARITY) && ETXB_PARITY
+    const bool mine = true;
+#else
+    const bool mine = !merge_is_lambert(sc.materials[isect.material_index]);
+#endif
+    if (mine) {
+      merge_queries = 1;
+      V3 m = grid_gather<SP>(sc, p.grid, p.vcm, isect, state, candidates, accepts);
+      float4 mg = p.paths.merged[i];
+      p.paths.merged[i] = make_float4(mg.x + m.x, mg.y + m.y, mg.z + m.z, 0.0f);
+      p.paths.misc[i].x = state.sampler.seed;
+    }
+  }
+  counter_add(&p.counters->merge_queries, merge_queries);
+  counter_add(&p.counters->merge_candidates, candidates);
+  counter_add(&p.counters->merge_accepts, accepts);
+}
+
+// Warp-cooperative Lambert gather (product build).  Input: the queue sorted by merge_query_key.  One query at a time is
+// broadcast to the warp; the eight cell ranges are concatenated into one virtual range that the 32 lanes sweep with coalesced
+// 16-B position loads; photons inside the radius are compacted (ballot + prefix) into a per-warp shared list and finished 32 at
+// a time with all lanes busy (normal / path-length / cosine tests, MIS weight, kernel); partial sums meet in a shuffle reduction.
+constexpr uint32_t kMergeWarpsPerBlock = 8;
+constexpr uint32_t kMergeListSize = 64;
+
+template <bool SP>
+__global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys, const uint32_t* count_in) {
+  __shared__ uint32_t s_idx[kMergeWarpsPerBlock][kMergeListSize];
+  __shared__ float s_d2[kMergeWarpsPerBlock][kMergeListSize];
+  __shared__ float s_dvcm[kMergeWarpsPerBlock][kMergeListSize];
+  const DeviceScene& sc = p.scene;
+  const GridData& g = p.grid;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t merge_queries = 0, candidates = 0, accepts = 0;
+  bool coop_active = (q < *count_in) && (sorted_keys[q] != 0xffffffffu);
+  uint32_t i = 0;
+  V3 qpos = {0, 0, 0}, qnrm = {0, 0, 0}, qfn = {0, 0, 0}, qc = {0, 0, 0};
+  float q_wcam_base = 0.0f, q_dvm = 0.0f, q_rev_cos = 0.0f;
+  uint32_t q_depth = 0;
+  if (coop_active) {
+    i = sorted_ids[q];
+    float4 hit = p.paths.hit[i];
+    PathState<SP> state = load_state<SP>(p.paths, i);
+    Isect isect = make_intersection(sc, state.ray_d, __float_as_uint(hit.w), hit.x, hit.y, hit.z);
+    const etxb_material& mat = sc.materials[isect.material_index];
+    coop_active = merge_is_lambert(mat);
+    if (coop_active) {
+      merge_queries = 1;
+      qpos = isect.pos;
+      qnrm = isect.nrm;
+      bool entering = dot(isect.nrm, isect.w_i) < 0.0f;
+      qfn = entering ? isect.nrm : -isect.nrm;  // frame normal of the camera vertex
+      Spec<SP> diffuse = apply_image<SP>(sc, mat.scattering, state.wavelength);
+      Spec<SP> t_camera = state.throughput / sampling_pdf<SP>(state.wavelength);
+      qc = spec_to_rgb<SP>(sc, (diffuse / kPi) * t_camera, state.wavelength);  // camera_bsdf.func * t_camera: direction independent
+      q_wcam_base = state.d_vcm * p.vcm.vc_weight;
+      q_dvm = state.d_vm;
+      q_rev_cos = dot(isect.nrm, -isect.w_i);  // reverse pdf = cos between -w_i(camera) and the normal facing the photon (bsdf_various.hxx:113-121)
+      q_depth = state.total_path_depth;
+    }
+  }
+  uint32_t pending = __ballot_sync(0xffffffffu, coop_active);
+  V3 my_sum = {0.0f, 0.0f, 0.0f};
+  const bool use_mis = p.vcm.enable_mis();
+  const bool use_epan = (p.vcm.kernel == 1u);
+  const float vc_weight = p.vcm.vc_weight;
+  while (pending) {
+    uint32_t src = __ffs(pending) - 1u;
+    pending &= pending - 1u;
+    V3 bpos = {__shfl_sync(0xffffffffu, qpos.x, src), __shfl_sync(0xffffffffu, qpos.y, src), __shfl_sync(0xffffffffu, qpos.z, src)};
+    V3 bnrm = {__shfl_sync(0xffffffffu, qnrm.x, src), __shfl_sync(0xffffffffu, qnrm.y, src), __shfl_sync(0xffffffffu, qnrm.z, src)};
+    V3 bfn = {__shfl_sync(0xffffffffu, qfn.x, src), __shfl_sync(0xffffffffu, qfn.y, src), __shfl_sync(0xffffffffu, qfn.z, src)};
+    float b_wcam_base = __shfl_sync(0xffffffffu, q_wcam_base, src);
+    float b_dvm = __shfl_sync(0xffffffffu, q_dvm, src);
+    float b_rev_cos = __shfl_sync(0xffffffffu, q_rev_cos, src);
+    uint32_t b_depth = __shfl_sync(0xffffffffu, q_depth, src);
+    // the eight cells (vcm_shared.hxx:895-916): lanes 0..7 fetch their ranges, then an 8-wide exclusive scan of the counts
+    uint32_t my_begin = 0, my_cnt = 0;
+    if (lane < 8u) {
+      V3 m = (bpos - g.bbox_min) / g.cell_size;
+      V3 mf = vfloor(m);
+      V3 md = m - mf;
+      int32_t acx = static_cast<int32_t>(mf.x), acy = static_cast<int32_t>(mf.y), acz = static_cast<int32_t>(mf.z);
+      int32_t cx = (lane & 1u) ? acx + ((md.x < 0.5f) ? -1 : +1) : acx;
+      int32_t cy = (lane & 2u) ? acy + ((md.y < 0.5f) ? -1 : +1) : acy;
+      int32_t cz = (lane & 4u) ? acz + ((md.z < 0.5f) ? -1 : +1) : acz;
+      uint2 r = __ldg(&g.cell_range[grid_cell_index(g.hash_table_mask, cx, cy, cz)]);
+      my_begin = r.x;
+      my_cnt = r.y - r.x;
+    }
+    uint32_t incl = my_cnt;
+#pragma unroll
+    for (uint32_t o = 1; o < 8u; o <<= 1) {
+      uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    uint32_t my_excl = incl - my_cnt;
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 7);
+    uint32_t e1 = __shfl_sync(0xffffffffu, my_excl, 1), e2 = __shfl_sync(0xffffffffu, my_excl, 2), e3 = __shfl_sync(0xffffffffu, my_excl, 3),
+             e4 = __shfl_sync(0xffffffffu, my_excl, 4), e5 = __shfl_sync(0xffffffffu, my_excl, 5), e6 = __shfl_sync(0xffffffffu, my_excl, 6),
+             e7 = __shfl_sync(0xffffffffu, my_excl, 7);
+    float wx = 0.0f, wy = 0.0f, wz = 0.0f;  // per-lane partial sums of l_value * kernel * mis
+    uint32_t n_list = 0;                    // warp-uniform fill of the shared list
+
+    auto finish = [&](uint32_t n) {
+      // lanes < n take one photon that passed the radius test
+      if (lane < n) {
+        uint32_t j = s_idx[warp][lane];
+        float distance_squared = s_d2[warp][lane];
+        float dvcm = s_dvcm[warp][lane];
+        float4 wl = __ldg(&g.win_len[j]);
+        float4 nd = __ldg(&g.nrm_dvm[j]);
+        float4 lt = __ldg(&g.thr_rgb[j]);
+        bool ok = !(__float_as_uint(wl.w) + b_depth + 1 > sc.max_path_length);
+        ok = ok && !(dot(bnrm, V3{nd.x, nd.y, nd.z}) <= kEpsilon);
+        float cos_o = -(bfn.x * wl.x + bfn.y * wl.y + bfn.z * wl.z);  // local_w_o.z of DiffuseBSDF::evaluate(-w_in)
+        ok = ok && (cos_o > kEpsilon);
+        if (ok) {
+          float bsdf_pdf_v = kInvPi * cos_o;
+          float facing = (dot(bnrm, V3{wl.x, wl.y, wl.z}) < 0.0f) ? b_rev_cos : -b_rev_cos;
+          float rev_pdf = (facing <= kEpsilon) ? 0.0f : kInvPi * facing;
+          float w_light = dvcm * vc_weight + nd.w * bsdf_pdf_v;
+          float w_camera = b_wcam_base + b_dvm * rev_pdf;
+          float weight = use_mis ? (1.0f / (1.0f + w_light + w_camera)) : 1.0f;
+          float kernel_weight = use_epan ? fmaxf(2.0f * (1.0f - distance_squared * g.inv_radius_squared), 0.0f) : 1.0f;
+          float kw = kernel_weight * weight;
+          wx += lt.x * kw;
+          wy += lt.y * kw;
+          wz += lt.z * kw;
+          accepts += 1;
+        }
+      }
+    };
+
+    for (uint32_t base = 0; base < total; base += 32u) {
+      uint32_t k = base + lane;
+      bool valid = k < total;
+      uint32_t c = uint32_t(k >= e1) + uint32_t(k >= e2) + uint32_t(k >= e3) + uint32_t(k >= e4) + uint32_t(k >= e5) + uint32_t(k >= e6) + uint32_t(k >= e7);
+      uint32_t cb = __shfl_sync(0xffffffffu, my_begin, c);
+      uint32_t ce = __shfl_sync(0xffffffffu, my_excl, c);
+      uint32_t j = cb + (k - ce);
+      bool inside = false;
+      float distance_squared = 0.0f, dvcm = 0.0f;
+      if (valid) {
+        float4 pd = __ldg(&g.pos_dvcm[j]);
+        V3 d = V3{pd.x, pd.y, pd.z} - bpos;
+        distance_squared = dot(d, d);
+        dvcm = pd.w;
+        inside = !(distance_squared > g.radius_squared);
+        candidates += 1;
+      }
+      uint32_t bal = __ballot_sync(0xffffffffu, inside);
+      if (inside) {
+        uint32_t slot = n_list + __popc(bal & lane_lt);
+        s_idx[warp][slot] = j;
+        s_d2[warp][slot] = distance_squared;
+        s_dvcm[warp][slot] = dvcm;
+      }
+      n_list += __popc(bal);
+      __syncwarp();
+      if (n_list >= 32u) {
+        finish(32u);
+        __syncwarp();
+        uint32_t rest = n_list - 32u;  // < 32: move the tail to the front
+        uint32_t tj = 0;
+        float td = 0.0f, tv = 0.0f;
+        if (lane < rest) {
+          tj = s_idx[warp][32u + lane];
+          td = s_d2[warp][32u + lane];
+          tv = s_dvcm[warp][32u + lane];
+        }
+        __syncwarp();
+        if (lane < rest) {
+          s_idx[warp][lane] = tj;
+          s_d2[warp][lane] = td;
+          s_dvcm[warp][lane] = tv;
+        }
+        n_list = rest;
+        __syncwarp();
+      }
+    }
+    if (n_list) finish(n_list);
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wx += __shfl_xor_sync(0xffffffffu, wx, o);
+      wy += __shfl_xor_sync(0xffffffffu, wy, o);
+      wz += __shfl_xor_sync(0xffffffffu, wz, o);
+    }
+    if (lane == src) {
+      V3 l = {wx, wy, wz};
+      if (SP) l *= V3{0.817660332f, 1.05418909f, 1.09945524f};  // kRGBLuminanceScale (:876-878)
+      my_sum = qc * l;
+    }
+  }
+  if (merge_queries) {
+    float4 mg = p.paths.merged[i];
+    p.paths.merged[i] = make_float4(mg.x + my_sum.x, mg.y + my_sum.y, mg.z + my_sum.z, 0.0f);
+  }
+  counter_add(&p.counters->merge_queries, merge_queries);
+  counter_add(&p.counters->merge_candidates, candidates);
+  counter_add(&p.counters->merge_accepts, accepts);
+}
+
+template <bool SP>
+__global__ void __launch_bounds__(128) k_camera_continue(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  bool alive = false;
+  uint32_t i = 0;
+  if (q < *count_in) {
+    i = queue_in[q];
+    const DeviceScene& sc = p.scene;
+    PathState<SP> state = load_state<SP>(p.paths, i);
+    float4 hit = p.paths.hit[i];
+    uint32_t tri_index = __float_as_uint(hit.w);
+    if (tri_index != kInvalidIndex) {
+      Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
+      BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
+      float4 bw = p.paths.bs_weight_pdf[i], bd = p.paths.bs_wo_eta[i];
+      uint2 bp = p.paths.bs_props[i];
+      BSample<SP> bs;
+      bs.weight = Spec<SP>::make3({bw.x, bw.y, bw.z});
+      bs.pdf = bw.w;
+      bs.w_o = {bd.x, bd.y, bd.z};
+      bs.eta = bd.w;
+      bs.properties = bp.x;
+      bs.medium_index = bp.y;
       alive = vcm_next_ray<SP>(sc, false, state, p.vcm, isect, bsdf_data, bs);
     }
     if (alive) {
       store_state<SP>(p.paths, i, state);
-      V3 gv = state.gathered.as_v3();
-      p.paths.gathered[i] = make_float4(gv.x, gv.y, gv.z, 0.0f);
-      p.paths.merged[i] = make_float4(state.merged.x, state.merged.y, state.merged.z, 0.0f);
     } else {
       // vcm_cpu.cxx:195-198 + Film::accumulate_camera_image (film.cxx:173-230, camera layer)
-      V3 merged = state.merged;
+      float4 g = p.paths.gathered[i], mg = p.paths.merged[i];
+      V3 merged = {mg.x, mg.y, mg.z};
       merged *= p.vcm.vm_normalization;
-      merged += spec_to_rgb<SP>(sc, state.gathered / sampling_pdf<SP>(state.wavelength), state.wavelength);
+      merged += spec_to_rgb<SP>(sc, Spec<SP>::make3({g.x, g.y, g.z}) / sampling_pdf<SP>(state.wavelength), state.wavelength);
       uint32_t px = i % p.film.width, py = i / p.film.width;
       uint32_t fi = px + (p.film.height - 1u - py) * p.film.width;
       float4 old = p.film.camera[fi];
@@ -467,14 +753,6 @@ __global__ void __launch_bounds__(128) k_camera_bounce(LaunchParams p, const uin
     }
   }
   queue_push(queue_out, count_out, alive, i);
-  counter_add(&p.counters->bounces_camera, (q < *count_in) ? 1u : 0u);
-  counter_add(&p.counters->rays_shadow, shadow_rays);
-  counter_add(&p.counters->connections, connections);
-  counter_add(&p.counters->merge_queries, merge_queries);
-  counter_add(&p.counters->merge_candidates, candidates);
-  counter_add(&p.counters->merge_accepts, accepts);
-  counter_add(&p.counters->nodes, STATS_NODES);
-  counter_add(&p.counters->tris, STATS_TRIS);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

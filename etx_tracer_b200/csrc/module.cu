@@ -38,12 +38,16 @@ enum KernelId : uint32_t {
   K_GRID_BUILD,
   K_CAMERA_BEGIN,
   K_TRACE_CAMERA,
-  K_CAMERA_BOUNCE,
+  K_CAMERA_SHADE,
+  K_CAMERA_MERGE_SORT,
+  K_CAMERA_MERGE,
+  K_CAMERA_MERGE_SERIAL,
+  K_CAMERA_CONTINUE,
   K_FILM_COMMIT,
   K_COUNT
 };
 const char* kKernelNames[K_COUNT] = {"light_begin", "trace_closest(light)", "light_bounce", "lv_scan", "lv_reorder", "grid_bbox", "grid_keys", "grid_sort", "grid_build",
-  "camera_begin", "trace_closest(camera)", "camera_bounce", "film_commit_light"};
+  "camera_begin", "trace_closest(camera)", "camera_shade", "camera_merge_sort", "camera_merge", "camera_merge_serial", "camera_continue", "film_commit_light"};
 
 template <class T>
 struct DevBuf {
@@ -77,6 +81,7 @@ struct etxb_ctx {
   bool scene_ready = false;
   bool spectral = false;
   bool profile = false;
+  bool has_stochastic_merge = false;  // some material that can be merged at is not Lambert (needs the serial gather)
 
   // scene in HBM
   DevBuf<DVertex> vertices;
@@ -97,10 +102,11 @@ struct etxb_ctx {
 
   // per-path state + queues
   uint32_t width = 0, height = 0, path_count = 0;
-  DevBuf<float4> ray_o, ray_d, thr, mis, hit, gathered, merged, camera_value;
+  DevBuf<float4> ray_o, ray_d, thr, mis, hit, gathered, merged, camera_value, bs_weight_pdf, bs_wo_eta;
   DevBuf<uint4> misc;
+  DevBuf<uint2> bs_props;
   DevBuf<float> wavelength;
-  DevBuf<uint32_t> lv_count, lp_offset, queue_a, queue_b, queue_counts, sampler_end_light, sampler_end_camera;
+  DevBuf<uint32_t> lv_count, lp_offset, queue_a, queue_b, queue_counts, sampler_end_light, sampler_end_camera, merge_key;
   // light vertices + grid
   uint32_t lv_capacity = 0, max_light_vertices_cfg = 0;
   DevBuf<LightVertexRec> lv_tmp, lv_final;
@@ -208,7 +214,7 @@ LaunchParams make_params(etxb_ctx* ctx) {
   LaunchParams p = {};
   p.scene = ctx->dscene;
   p.paths = {ctx->ray_o.ptr, ctx->ray_d.ptr, ctx->thr.ptr, ctx->mis.ptr, ctx->misc.ptr, ctx->hit.ptr, ctx->gathered.ptr, ctx->merged.ptr, ctx->wavelength.ptr,
-    ctx->lv_count.ptr};
+    ctx->lv_count.ptr, ctx->bs_weight_pdf.ptr, ctx->bs_wo_eta.ptr, ctx->bs_props.ptr, ctx->merge_key.ptr};
   p.film = {ctx->film_camera.ptr, ctx->film_light.ptr, ctx->film_light_iteration.ptr, ctx->width, ctx->height};
   p.grid = ctx->grid;
   p.lv_tmp = ctx->lv_tmp.ptr;
@@ -301,24 +307,25 @@ int run_light_pass(etxb_ctx* ctx) {
     k_lv_reorder<<<blocks_for(total, 256), 256, 0, ctx->stream>>>(p, total);
   }
   ctx->last_light_vertices = total;
-  {
-    LaunchTimer t(ctx, K_FILM_COMMIT);
-    // complete_light_vertices -> Film::commit_light_iteration(iteration) (vcm_cpu.cxx:209-211)
-    k_film_commit_light<<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(p.film, ctx->iteration);
-  }
   CUDA_OK(ctx, cudaGetLastError());
   ctx->light_pass_done = true;
   return ETXB_OK;
 }
 
 template <bool SP>
-int run_grid_build(etxb_ctx* ctx) {
+int run_grid_build(etxb_ctx* ctx, const LightVertexRec* records, uint32_t count) {
   ctx->grid = {};
   ctx->grid_done = true;
-  bool merging = (ctx->options.options & ETXB_VCM_ENABLE_MERGING) && (ctx->options.options & ETXB_VCM_MERGE_VERTICES);
-  uint32_t count = ctx->last_light_vertices;
-  if (!merging || (count == 0)) return ETXB_OK;
   LaunchParams p = make_params(ctx);
+  {
+    // complete_light_vertices -> Film::commit_light_iteration(iteration) (vcm_cpu.cxx:209-211); in a multi-GPU run the
+    // host has all-reduced ETXB_BUF_FILM_LIGHT_ITERATION across ranks before this call
+    LaunchTimer t(ctx, K_FILM_COMMIT);
+    k_film_commit_light<<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(p.film, ctx->iteration);
+  }
+  bool merging = (ctx->options.options & ETXB_VCM_ENABLE_MERGING) && (ctx->options.options & ETXB_VCM_MERGE_VERTICES);
+  if (!merging || (count == 0)) return ETXB_OK;
+  p.lv_final = const_cast<LightVertexRec*>(records);
   float radius = p.vcm.current_radius;
   uint32_t init[6];
   for (int k = 0; k < 3; ++k) {
@@ -328,14 +335,14 @@ int run_grid_build(etxb_ctx* ctx) {
   CUDA_OK(ctx, cudaMemcpyAsync(ctx->grid_bbox.ptr, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
   {
     LaunchTimer t(ctx, K_GRID_BBOX);
-    k_grid_bbox<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(ctx->lv_final.ptr, count, ctx->grid_bbox.ptr);
+    k_grid_bbox<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(records, count, ctx->grid_bbox.ptr);
   }
   uint32_t table_size = next_pow2(count);
   uint32_t mask = table_size - 1u;
   float cell_size = 2.0f * radius;
   {
     LaunchTimer t(ctx, K_GRID_KEYS);
-    k_grid_keys<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(ctx->lv_final.ptr, count, ctx->grid_bbox.ptr, cell_size, mask, ctx->keys_in.ptr, ctx->vals_in.ptr);
+    k_grid_keys<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(records, count, ctx->grid_bbox.ptr, cell_size, mask, ctx->keys_in.ptr, ctx->vals_in.ptr);
   }
   {
     LaunchTimer t(ctx, K_GRID_SORT);
@@ -385,6 +392,7 @@ int run_camera_pass(etxb_ctx* ctx) {
   uint32_t active = 0;
   if (int rc = read_u32(ctx, counts + 0, active)) return rc;
   uint32_t cur = 0;
+  const bool merging = (ctx->options.options & ETXB_VCM_ENABLE_MERGING) && (ctx->options.options & ETXB_VCM_MERGE_VERTICES);
   while (active > 0) {
     {
       LaunchTimer t(ctx, K_TRACE_CAMERA);
@@ -392,8 +400,36 @@ int run_camera_pass(etxb_ctx* ctx) {
     }
     CUDA_OK(ctx, cudaMemsetAsync(counts + (cur ^ 1u), 0, 4, ctx->stream));
     {
-      LaunchTimer t(ctx, K_CAMERA_BOUNCE);
-      k_camera_bounce<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur, qout, counts + (cur ^ 1u));
+      LaunchTimer t(ctx, K_CAMERA_SHADE);
+      k_camera_shade<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur);
+    }
+#if defined(ETXB_PARITY) && ETXB_PARITY
+    if (merging) {
+      LaunchTimer t(ctx, K_CAMERA_MERGE_SERIAL);
+      k_camera_merge_serial<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur);
+    }
+#else
+    if (merging && ctx->grid.photon_count) {
+      {
+        // queries sorted by the Morton code of their base cell: neighbours in the queue read the same photon cells
+        LaunchTimer t(ctx, K_CAMERA_MERGE_SORT);
+        size_t temp_bytes = ctx->cub_temp.bytes();
+        CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->merge_key.ptr, ctx->keys_out.ptr, qin, ctx->vals_out.ptr, int(active), 0, 32,
+                       ctx->stream));
+      }
+      {
+        LaunchTimer t(ctx, K_CAMERA_MERGE);
+        k_camera_merge_coop<SP><<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, ctx->vals_out.ptr, ctx->keys_out.ptr, counts + cur);
+      }
+      if (ctx->has_stochastic_merge) {
+        LaunchTimer t(ctx, K_CAMERA_MERGE_SERIAL);
+        k_camera_merge_serial<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur);
+      }
+    }
+#endif
+    {
+      LaunchTimer t(ctx, K_CAMERA_CONTINUE);
+      k_camera_continue<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur, qout, counts + (cur ^ 1u));
     }
     cur ^= 1u;
     std::swap(qin, qout);
@@ -475,7 +511,7 @@ void etxb_destroy(etxb_ctx* ctx) {
     &ctx->g_win, &ctx->g_thr, &ctx->film_camera, &ctx->film_light, &ctx->film_light_iteration, &ctx->film_out};
   for (auto* b : f4) b->release();
   DevBuf<uint32_t>* u32[] = {&ctx->tri_emitter, &ctx->lv_count, &ctx->lp_offset, &ctx->queue_a, &ctx->queue_b, &ctx->queue_counts, &ctx->sampler_end_light,
-    &ctx->sampler_end_camera, &ctx->lv_tmp_count, &ctx->overflow, &ctx->grid_bbox, &ctx->keys_in, &ctx->keys_out, &ctx->vals_in, &ctx->vals_out};
+    &ctx->sampler_end_camera, &ctx->merge_key, &ctx->lv_tmp_count, &ctx->overflow, &ctx->grid_bbox, &ctx->keys_in, &ctx->keys_out, &ctx->vals_in, &ctx->vals_out};
   for (auto* b : u32) b->release();
   ctx->vertices.release();
   ctx->triangles.release();
@@ -495,6 +531,9 @@ void etxb_destroy(etxb_ctx* ctx) {
   ctx->lv_tmp.release();
   ctx->lv_final.release();
   ctx->cell_range.release();
+  ctx->bs_props.release();
+  ctx->bs_weight_pdf.release();
+  ctx->bs_wo_eta.release();
   ctx->cub_temp.release();
   ctx->counters.release();
   cudaStreamDestroy(ctx->stream);
@@ -558,6 +597,13 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
       if (im != ETXB_INVALID_INDEX) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: textures are not supported on the device yet", (unsigned long long)i);
     if (m.int_medium != ETXB_INVALID_INDEX || m.ext_medium != ETXB_INVALID_INDEX)
       return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: media are not supported on the device yet", (unsigned long long)i);
+  }
+  ctx->has_stochastic_merge = false;
+  for (uint64_t i = 0; i < s.materials.count; ++i) {
+    const etxb_material& m = mats[i];
+    bool lambert = (m.cls == ETXB_MAT_DIFFUSE) && (m.diffuse_variation == 0);
+    bool always_delta = (m.cls == ETXB_MAT_DIELECTRIC) && (std::max(m.roughness.value[0], m.roughness.value[1]) <= 1.0e-4f);
+    if (!lambert && !always_delta) ctx->has_stochastic_merge = true;
   }
   const auto* emitters = static_cast<const etxb_emitter*>(s.emitter_instances.a);
   for (uint64_t i = 0; i < s.emitter_instances.count; ++i) {
@@ -641,11 +687,12 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   size_t n = ctx->path_count;
   if (n == 0) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "empty film");
   DevBuf<float4>* per_path_f4[] = {&ctx->ray_o, &ctx->ray_d, &ctx->thr, &ctx->mis, &ctx->hit, &ctx->gathered, &ctx->merged, &ctx->camera_value, &ctx->film_camera,
-    &ctx->film_light, &ctx->film_light_iteration, &ctx->film_out};
+    &ctx->film_light, &ctx->film_light_iteration, &ctx->film_out, &ctx->bs_weight_pdf, &ctx->bs_wo_eta};
   for (auto* b : per_path_f4) CUDA_OK(ctx, b->alloc(n));
+  CUDA_OK(ctx, ctx->bs_props.alloc(n));
   CUDA_OK(ctx, ctx->misc.alloc(n));
   CUDA_OK(ctx, ctx->wavelength.alloc(n));
-  DevBuf<uint32_t>* per_path_u32[] = {&ctx->lv_count, &ctx->lp_offset, &ctx->queue_a, &ctx->queue_b, &ctx->sampler_end_light, &ctx->sampler_end_camera};
+  DevBuf<uint32_t>* per_path_u32[] = {&ctx->lv_count, &ctx->lp_offset, &ctx->queue_a, &ctx->queue_b, &ctx->sampler_end_light, &ctx->sampler_end_camera, &ctx->merge_key};
   for (auto* b : per_path_u32) CUDA_OK(ctx, b->alloc(n));
   CUDA_OK(ctx, ctx->queue_counts.alloc(4));
   CUDA_OK(ctx, ctx->lv_tmp_count.alloc(1));
@@ -754,13 +801,15 @@ int etxb_enqueue_grid_build(etxb_ctx* ctx, const void* device_photon_records, ui
   if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
   if (!ctx->light_pass_done) return fail(ctx, ETXB_ERR_NOT_READY, "light pass has not run");
   cudaSetDevice(ctx->device);
+  const LightVertexRec* records = ctx->lv_final.ptr;
+  uint32_t count = ctx->last_light_vertices;
   if (device_photon_records != nullptr) {
-    // multi-GPU: the caller all-gathered every rank's path-major records (ETXB_BUF_PHOTON_RECORDS) into one buffer
+    // multi-GPU: the caller all-gathered every rank's path-major records (ETXB_BUF_PHOTON_RECORDS, 96 B each) into one device buffer
     if (photon_count > ctx->lv_capacity) return fail(ctx, ETXB_ERR_OVERFLOW, "gathered photon count %llu exceeds capacity %u", (unsigned long long)photon_count, ctx->lv_capacity);
-    // the merge only needs the grid SoA, so the gathered records are staged in lv_tmp (free after the reorder) — see run_grid_build_from
-    return fail(ctx, ETXB_ERR_UNSUPPORTED, "external photon records are handled by etxb_enqueue_grid_build_gathered in a later round");
+    records = static_cast<const LightVertexRec*>(device_photon_records);
+    count = uint32_t(photon_count);
   }
-  return ctx->spectral ? run_grid_build<true>(ctx) : run_grid_build<false>(ctx);
+  return ctx->spectral ? run_grid_build<true>(ctx, records, count) : run_grid_build<false>(ctx, records, count);
 }
 
 int etxb_enqueue_camera_pass(etxb_ctx* ctx) {

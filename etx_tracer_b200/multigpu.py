@@ -1,0 +1,91 @@
+"""Pixel-tile sharding of one VCM iteration across ranks (one process per GPU), SURVEY.md §8(e).
+
+Per iteration:  light pass on the rank's tiles  ->  all-reduce(sum) of the per-iteration light image (splats land anywhere)
+                ->  all-gather of the ranks' photon records (the merge queries the GLOBAL photon map; skipped when merging is off)
+                ->  grid build + camera pass on the rank's tiles.
+At the end:     reduce(sum) of the camera image to rank 0 (tiles are disjoint, non-owned pixels are zero).
+
+The exchange is plain `torch.distributed` (NCCL on GPUs; gloo on CPU for the host-logic tests), on buffers the CUDA module
+exposes through etxb_device_pointer.  There is no fused compute+collective here: the path has no dense step feeding a
+collective — each exchange happens once per iteration on data that is complete only when its pass has finished.
+"""
+import numpy as np
+
+from . import structs as S
+
+RECORD_BYTES = 96  # LightVertexRec (etx_tracer_b200/csrc/dvcm.cuh)
+
+
+def tile_owner(width, height, world, tile=32):
+    """owner[y, x] = rank owning the pixel: 32x32 tiles dealt round-robin (must match pixel_owned() in kernels.cuh)."""
+    ys, xs = np.mgrid[0:height, 0:width]
+    tiles_x = (width + tile - 1) // tile
+    return (((ys // tile) * tiles_x + (xs // tile)) % world).astype(np.int32)
+
+
+def gather_layout(counts):
+    """Offsets of each rank's block in the gathered photon buffer + total."""
+    counts = [int(c) for c in counts]
+    offsets = [0]
+    for c in counts[:-1]:
+        offsets.append(offsets[-1] + c)
+    return offsets, sum(counts)
+
+
+class DevicePointerTensor:
+    """Zero-copy torch view of a raw device pointer via __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes, dtype="<f4"):
+        item = np.dtype(dtype).itemsize
+        self.__cuda_array_interface__ = {"shape": (nbytes // item,), "typestr": dtype, "data": (ptr, False), "version": 2}
+
+
+def as_tensor(ptr, nbytes, dtype="<f4", device="cuda"):
+    import torch
+    return torch.as_tensor(DevicePointerTensor(ptr, nbytes, dtype), device=device)
+
+
+class ShardedVCM:
+    """Drives GPUVCM instances of all ranks through one iteration with the exchanges in between."""
+
+    def __init__(self, gpu, dist, rank, world):
+        import torch
+        self.g, self.dist, self.rank, self.world, self.torch = gpu, dist, rank, world, torch
+        gpu.set_partition(rank, world)
+        self._gather_buf = None
+
+    def merging(self):
+        o = int(self.g.options["options"][0])
+        return bool(o & S.VCM_ENABLE_MERGING) and bool(o & S.VCM_MERGE_VERTICES)
+
+    def iterate(self):
+        torch, dist, g = self.torch, self.dist, self.g
+        g.light_pass()
+        ptr, nbytes = g.device_pointer(S.BUF_FILM_LIGHT_ITERATION)
+        dist.all_reduce(as_tensor(ptr, nbytes), op=dist.ReduceOp.SUM)
+        records_ptr, total = None, 0
+        if self.merging():
+            ptr, nbytes = g.device_pointer(S.BUF_PHOTON_RECORDS)
+            mine = nbytes // RECORD_BYTES
+            counts = torch.zeros(self.world, dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(counts, torch.tensor([mine], dtype=torch.int64, device="cuda"))
+            counts = counts.tolist()
+            offsets, total = gather_layout(counts)
+            need = max(total, 1) * RECORD_BYTES // 4
+            if self._gather_buf is None or self._gather_buf.numel() < need:
+                self._gather_buf = torch.empty(int(need * 1.25) + 1024, dtype=torch.float32, device="cuda")
+            outs = [self._gather_buf[offsets[r] * RECORD_BYTES // 4:(offsets[r] + counts[r]) * RECORD_BYTES // 4] for r in range(self.world)]
+            src = as_tensor(ptr, nbytes) if mine else torch.empty(0, dtype=torch.float32, device="cuda")
+            dist.all_gather(outs, src)  # uneven sizes: NCCL falls back to grouped broadcasts
+            records_ptr = self._gather_buf.data_ptr()
+        torch.cuda.current_stream().synchronize()
+        g.grid_build(records_ptr, total)
+        g.camera_pass()
+
+    def reduce_film(self):
+        """Sum the (disjoint) camera tiles on rank 0; returns the Result layer there, None elsewhere."""
+        torch, dist, g = self.torch, self.dist, self.g
+        ptr, nbytes = g.device_pointer(S.BUF_FILM_CAMERA)
+        dist.reduce(as_tensor(ptr, nbytes), dst=0, op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream().synchronize()
+        return g.film(S.FILM_RESULT) if self.rank == 0 else None

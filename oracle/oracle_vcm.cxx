@@ -50,6 +50,20 @@ struct RaytracingImpl {
   OracleCounters* counters = nullptr;
 };
 
+// per-thread tallies, flushed into the shared atomics once per worker range (no cache-line ping-pong between threads)
+struct ThreadCounters {
+  uint64_t rays_closest = 0, rays_shadow = 0, nodes = 0, tris = 0;
+};
+static thread_local ThreadCounters g_thread_counters;
+static void flush_thread_counters(OracleCounters& dst) {
+  auto& t = g_thread_counters;
+  dst.rays_closest += t.rays_closest;
+  dst.rays_shadow += t.rays_shadow;
+  dst.nodes += t.nodes;
+  dst.tris += t.tris;
+  t = {};
+}
+
 static thread_local const etxb::Bvh* g_pending_bvh = nullptr;
 static thread_local OracleCounters* g_pending_counters = nullptr;
 
@@ -98,9 +112,9 @@ void run_traversal(const RaytracingImpl* impl, const Ray& r, Visitor& v, bool sh
   etxb::TraverseStats st;
   etxb::traverse(nl, tl, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.min_t, r.max_t, v, impl->counters ? &st : nullptr);
   if (impl->counters) {
-    impl->counters->nodes += st.nodes;
-    impl->counters->tris += st.tris;
-    (shadow ? impl->counters->rays_shadow : impl->counters->rays_closest) += 1;
+    g_thread_counters.nodes += st.nodes;
+    g_thread_counters.tris += st.tris;
+    (shadow ? g_thread_counters.rays_shadow : g_thread_counters.rays_closest) += 1;
   }
 }
 
@@ -529,6 +543,7 @@ void run_iteration(Oracle& o, uint32_t threads) {
       lp.pixel_index = i;
       o.light_sampler_end[i] = state.sampler.seed;
     }
+    flush_thread_counters(o.counters);
   });
   {
     uint32_t chunk = (threads <= 1) ? pixel_count : (pixel_count + threads - 1u) / threads;
@@ -571,6 +586,7 @@ void run_iteration(Oracle& o, uint32_t threads) {
       o.camera_sampler_end[pi] = state.sampler.seed;
       o.camera_value[pi] = state.merged;
     }
+    flush_thread_counters(o.counters);
   });
   for (auto b : cam_bounces)
     o.stat_bounces_camera += b;
@@ -782,6 +798,7 @@ void oracle_trace(void* h, const float* rays, uint32_t* seeds, uint32_t count, f
     hits_uv_t[size_t(i) * 3 + 1] = hit ? isect.barycentric.z : 0.0f;
     hits_uv_t[size_t(i) * 3 + 2] = hit ? isect.t : 0.0f;
   }
+  flush_thread_counters(o->counters);
 }
 
 void oracle_bvh_info(void* h, uint32_t* node_count, uint32_t* slot_count) {

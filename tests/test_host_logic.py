@@ -1,0 +1,98 @@
+"""Host-side logic that runs without a GPU: scene generators, struct layout, C-ABI surface, error behaviour."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, bit_equal
+from etx_tracer_b200 import build as etx_build
+from etx_tracer_b200 import scenes, structs as S
+
+
+def test_rgb_reflectance_restatement_matches_reference(oracle_mod):
+    # scenes.spd_rgb_reflectance restates SpectralDistribution::rgb_reflectance (render/host/spectrum.cxx:135-148)
+    lib = oracle_mod.load("parity")
+    for rgb in ([1, 1, 1], [0.906, 0.906, 0.906], [1, 0, 0], [0, 1, 0], [0.2, 0.5, 0.7]):
+        want = np.zeros(1, S.SPECTRUM)
+        lib.oracle_spectrum_rgb_reflectance(oracle_mod._p(np.array(rgb, np.float32)), oracle_mod._p(want))
+        got = scenes.spd_rgb_reflectance(rgb)
+        assert bit_equal(got["entries"]["power"], want["entries"]["power"])
+        assert bit_equal(got["integrated"], want["integrated"]) and got["entry_count"] == want["entry_count"]
+    want = np.zeros(1, S.SPECTRUM)
+    lib.oracle_spectrum_rgb_luminance(oracle_mod._p(np.array([10.018, 3.918, 0.932], np.float32)), oracle_mod._p(want))
+    got = scenes.spd_rgb_luminance([10.018, 3.918, 0.932])
+    assert bit_equal(got["entries"]["power"], want["entries"]["power"]) and bit_equal(got["integrated"], want["integrated"])
+
+
+def test_camera_restatement_matches_reference_build_camera(oracle_mod):
+    lib = oracle_mod.load("parity")
+    sd = scenes.cornell_box(40, 30, samples=4)
+    ref = sd.camera.copy()
+    o = np.array([0.0, 1.0, 3.82], np.float32)
+    t = np.array([0.0, 1.0, -6.18], np.float32)
+    u = np.array([0.0, 1.0, 0.0], np.float32)
+    lib.oracle_build_camera(oracle_mod._p(ref), oracle_mod._p(o), oracle_mod._p(t), oracle_mod._p(u), 40, 30, np.float32(39.597755335771296))
+    for f in ("position", "side", "up", "direction", "tan_half_fov", "aspect", "area", "image_plane", "view_proj"):
+        np.testing.assert_allclose(sd.camera[f], ref[f], rtol=2e-6, atol=1e-7, err_msg=f)
+
+
+def test_scene_generator_invariants():
+    sd = scenes.cornell_box(64, 64, samples=256, spectral=True, sphere=True)
+    assert sd.triangle_count == 20480 + 26  # BASELINE config 2: 20 480-triangle sphere
+    assert sd.scene["flags"][0] & S.SCENE_SPECTRAL
+    d = sd.a_dist
+    assert d["cdf"][0] == 0 and d["cdf"][-1] == 1 and np.all(np.diff(d["cdf"]) >= 0)
+    np.testing.assert_allclose(d["pdf"][:-1].sum(), 1.0, rtol=1e-6)
+    gn = sd.a_triangles["geo_n"]
+    np.testing.assert_allclose(np.linalg.norm(gn, axis=1), 1.0, rtol=1e-5)
+    em = sd.a_tri_to_emitter[sd.a_tri_to_emitter != S.INVALID]
+    assert sorted(em) == list(range(sd.a_emitters.shape[0]))
+    # every material got the defaults validate_materials would add (scene_representation.cxx:262-300)
+    for m in sd.a_materials:
+        assert m["reflectance"]["spectrum_index"] != S.INVALID and m["int_ior"]["eta_index"] != S.INVALID
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "etx_b200.h")).read()
+    return sorted(set(re.findall(r"\b(etxb_[a-z_0-9]+)\s*\(", text)))
+
+
+@pytest.mark.parametrize("flavor", ["fast", "parity"])
+def test_c_abi_library_loads_and_exports_every_declared_symbol(flavor):
+    path = etx_build.lib_path(flavor)
+    if not os.path.exists(path):
+        etx_build.build((flavor,))
+    lib = ctypes.CDLL(path)
+    names = _declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/etx_b200.h but not exported by {os.path.basename(path)}"
+    lib.etxb_build_flavor.restype = ctypes.c_char_p
+    assert lib.etxb_build_flavor().decode() == flavor
+
+
+def test_options_keys_follow_the_reference():
+    # VCMOptions::load keys (rt/integrators/vcm_shared.cxx:15-28)
+    lib = ctypes.CDLL(etx_build.lib_path("fast"))
+    lib.etxb_options_set_key.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_double]
+    o = np.zeros(1, S.VCM_OPTIONS)
+    lib.etxb_options_default(o.ctypes.data_as(ctypes.c_void_p))
+    ref = S.default_vcm_options()
+    assert o.tobytes() == ref.tobytes()
+    p = o.ctypes.data_as(ctypes.c_void_p)
+    assert lib.etxb_options_set_key(p, b"vcm-merging", 0.0) == 0 and not (o["options"][0] & S.VCM_ENABLE_MERGING)
+    assert lib.etxb_options_set_key(p, b"vcm-radius_decay", 128.0) == 0 and o["radius_decay"][0] == 128
+    assert lib.etxb_options_set_key(p, b"vcm-initial_radius", 0.25) == 0 and o["initial_radius"][0] == np.float32(0.25)
+    assert lib.etxb_options_set_key(p, b"vcm-kernel", 0.0) == 0 and o["kernel"][0] == 0
+    assert lib.etxb_options_set_key(p, b"vcm-no-such-key", 1.0) < 0
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from etx_tracer_b200.api import EtxbError, GPUVCM
+    with pytest.raises(EtxbError):
+        GPUVCM(scenes.cornell_box(16, 16, samples=1))
