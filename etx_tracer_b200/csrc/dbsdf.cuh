@@ -644,35 +644,553 @@ DEVN BEval<SP> dielectric_evaluate(const DeviceScene& sc, const BData& d, V3 in_
   return e;
 }
 
-// ---- dispatch (scene_bsdf.hxx:56-90) -----------------------------------------------------------------------
-// Material classes not implemented on the device yet are rejected by etxb_upload_scene (ETXB_ERR_UNSUPPORTED).
-DEV bool material_class_supported(uint32_t cls) { return (cls == ETXB_MAT_DIFFUSE) || (cls == ETXB_MAT_DIELECTRIC); }
+// ---- conductor pieces of the microsurface walk (bsdf_external.hxx:233-344) ------------------------------------
+template <bool SP>
+DEV V3 sample_phase_function_conductor(float wavelength, V2 slope_rnd, V3 wi, V2 alpha, const IorSample<SP>& ext_ior, const IorSample<SP>& int_ior,
+  const ThinfilmEval<SP>& thinfilm, Spec<SP>& weight) {
+  V3 wm = sample_visible_micronormal(slope_rnd, wi, alpha);
+  float i_dot_m = dot(wi, wm);
+  weight = fresnel_calculate<SP>(wavelength, i_dot_m, ext_ior, int_ior, thinfilm);
+  return -wi + 2.0f * wm * i_dot_m;
+}
+DEV float mis_weight_conductor(V3 wi, V3 wo, V2 alpha) {
+  if (wi.x == -wo.x && wi.y == -wo.y && wi.z == -wo.z) return 1.0f;
+  const V3 wh = normalize(wi + wo);
+  return d_ggx((wh.z > 0) ? wh : -wh, alpha);
+}
+template <bool SP>
+DEVN Spec<SP> eval_conductor(float wavelength, Smp& smp, V3 wi, V3 wo, V2 alpha, const IorSample<SP>& ext_ior, const IorSample<SP>& int_ior, const ThinfilmEval<SP>& thinfilm) {
+  if (wi.z <= 0 || wo.z <= 0) return Spec<SP>::make(0.0f);
+  MicroRay ray = micro_ray(-wi, alpha);
+  ray.update_height(1.0f);
+  Spec<SP> energy = Spec<SP>::make(1.0f);
+  MicroRay ray_shadowing = micro_ray(wo, alpha);
+  const V3 wh = normalize(wi + wo);
+  const float D = d_ggx(wh, alpha);
+  const float G2 = 1.0f / (1.0f + (-ray.Lambda - 1.0f) + ray_shadowing.Lambda);
+  Spec<SP> singleScattering = fresnel_calculate<SP>(wavelength, dot(ray.w, wh), ext_ior, int_ior, thinfilm) * D * G2 / (4.0f * wi.z);
+  float wi_MISweight = 0.0f;
+  Spec<SP> multipleScattering = Spec<SP>::make(0.0f);
+  uint32_t current_scatteringOrder = 0;
+  while (current_scatteringOrder < kScatteringOrderMax) {
+    ray.update_height(sample_height(ray, smp.next()));
+    if (ray.h == kMaxFloat) break;
+    current_scatteringOrder++;
+    if (current_scatteringOrder > 1) {
+      Spec<SP> phasefunction = phase_function_reflection<SP>(wavelength, ray, wo, alpha, ext_ior, int_ior, thinfilm);
+      ray_shadowing.update_height(ray.h);
+      float shadowing = ray_shadowing.G1;
+      Spec<SP> I = energy * phasefunction * shadowing;
+      const float MIS = wi_MISweight / (wi_MISweight + mis_weight_conductor(-ray.w, wo, alpha));
+      multipleScattering += I * MIS;
+    }
+    V2 slope_rnd = (current_scatteringOrder == 1) && smp.has_fixed() ? V2{smp.fixed_u, smp.fixed_v} : smp.next_2d();
+    Spec<SP> weight;
+    ray.update_direction(sample_phase_function_conductor<SP>(wavelength, slope_rnd, -ray.w, alpha, ext_ior, int_ior, thinfilm, weight), alpha);
+    energy = energy * weight;
+    ray.update_height(ray.h);
+    if (current_scatteringOrder == 1) wi_MISweight = mis_weight_conductor(wi, ray.w, alpha);
+    if ((ray.h != ray.h) || (ray.w.x != ray.w.x)) return Spec<SP>::make(0.0f);
+  }
+  return 0.5f * singleScattering + multipleScattering;
+}
 
+// ---- Conductor (bsdf_conductor.hxx) -----------------------------------------------------------------------------
+DEV float conductor_pdf_local(V3 w_i, V3 w_o, V2 roughness) {
+  MicroRay ray = micro_ray(w_i, roughness);
+  return d_ggx(normalize(w_o + w_i), roughness) / (1.0f + ray.Lambda) / (4.0f * w_i.z) + w_o.z;
+}
+template <bool SP>
+DEVN BSample<SP> conductor_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
+  Frame lf = normal_frame(d);
+  V3 w_i = lf.to_local(-d.w_i);
+  IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
+  IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  uint32_t delta_sample = dielectric_is_delta(m) ? kBsdfDelta : 0u;
+  BSample<SP> result = bsample_zero<SP>();
+  result.properties = kBsdfReflection | delta_sample;
+  result.medium_index = d.current_medium;
+  result.eta = 1.0f;
+  result.weight = Spec<SP>::make(1.0f);
+  V2 roughness = evaluate_roughness(m);
+  MicroRay ray = micro_ray(-w_i, roughness);
+  ray.update_height(1.0f);
+  uint32_t scattering_order = 0;
+  while (true) {
+    ray.update_height(sample_height(ray, smp.next()));
+    if (ray.h == kMaxFloat) break;
+    V2 slope_rnd = (scattering_order == 0) && smp.has_fixed() ? V2{smp.fixed_u, smp.fixed_v} : smp.next_2d();
+    Spec<SP> weight = Spec<SP>::make(1.0f);
+    ray.update_direction(sample_phase_function_conductor<SP>(d.wavelength, slope_rnd, -ray.w, roughness, ext_ior, int_ior, thinfilm, weight), roughness);
+    ray.update_height(ray.h);
+    result.weight *= weight;
+    if ((scattering_order++ > kScatteringOrderMax) || (ray.h != ray.h) || (ray.w.x != ray.w.x)) {
+      result.weight = Spec<SP>::make(0.0f);
+      ray.w = V3{0, 0, 1};
+      break;
+    }
+  }
+  V3 lw_o = ray.w;
+  result.weight *= apply_image<SP>(sc, m.reflectance, d.wavelength);
+  result.pdf = conductor_pdf_local(w_i, lw_o, roughness);
+  result.w_o = normalize(lf.from_local(lw_o));
+  return result;
+}
+template <bool SP>
+DEVN BEval<SP> conductor_evaluate(const DeviceScene& sc, const BData& d, V3 in_w_o, const etxb_material& m, Smp& smp) {
+  Frame lf = normal_frame(d);
+  V3 w_o = lf.to_local(in_w_o);
+  if (w_o.z <= kEpsilon) return beval_zero<SP>();
+  V3 w_i = lf.to_local(-d.w_i);
+  if (w_i.z <= kEpsilon) return beval_zero<SP>();
+  V2 roughness = evaluate_roughness(m);
+  IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
+  IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  Spec<SP> value = eval_conductor<SP>(d.wavelength, smp, w_i, w_o, roughness, ext_ior, int_ior, thinfilm);
+  BEval<SP> e;
+  e.eta = 1.0f;
+  e.bsdf = value * apply_image<SP>(sc, m.reflectance, d.wavelength);
+  e.func = e.bsdf / w_o.z;
+  e.pdf = conductor_pdf_local(w_i, w_o, roughness);
+  return e;
+}
+DEV float conductor_pdf(const BData& d, V3 in_w_o, const etxb_material& m) {
+  Frame lf = normal_frame(d);
+  V3 w_o = lf.to_local(in_w_o);
+  if (w_o.z <= kEpsilon) return 0.0f;
+  V3 w_i = lf.to_local(-d.w_i);
+  if (w_i.z <= kEpsilon) return 0.0f;
+  return conductor_pdf_local(w_i, w_o, evaluate_roughness(m));
+}
+
+// ---- Plastic (bsdf_plastic.hxx) + GGX NormalDistribution::sample (bsdf.hxx:125-142) --------------------------------
+DEV V3 ggx_sample_normal(const Frame& frame, V2 alpha_in, Smp& smp, V3 in_w_i) {
+  const float kMinAlpha = 1.0f / 256.0f;
+  V2 alpha = {fmaxf(kMinAlpha, alpha_in.x), fmaxf(kMinAlpha, alpha_in.y)};
+  V3 w_i = frame.to_local(-in_w_i);
+  V3 v_h = normalize(V3{alpha.x * w_i.x, alpha.y * w_i.y, w_i.z});
+  float v_h_len = v_h.x * v_h.x + v_h.y * v_h.y;
+  V3 u = v_h_len > 0.0f ? V3{-v_h.y, v_h.x, 0.0f} / sqrtf(v_h_len) : V3{1.0f, 0.0f, 0.0f};
+  V3 v = cross(v_h, u);
+  float r = sqrtf(smp.next());
+  float phi = kDoublePi * smp.next();
+  float t1 = r * m_cos(phi);
+  float t2 = r * m_sin(phi);
+  float s = 0.5f * (1.0f + v_h.z);
+  t2 = (1.0f - s) * sqrtf(1.0f - t1 * t1) + s * t2;
+  V3 n_h = t1 * u + t2 * v + sqrtf(tmax(0.0f, 1.0f - t1 * t1 - t2 * t2)) * v_h;
+  V3 local_m = normalize(V3{alpha.x * n_h.x, alpha.y * n_h.y, n_h.z});
+  return frame.from_local(local_m);
+}
+template <bool SP>
+DEVN Spec<SP> plastic_specular_func(const DeviceScene& sc, const BData& d, V3 in_w_o, const etxb_material& m, Smp& smp) {
+  Frame lf = {d.tan, d.btn, d.nrm, false};
+  V3 w_i = lf.to_local(-d.w_i);
+  if (w_i.z <= kEpsilon) return Spec<SP>::make(0.0f);
+  V3 w_o = lf.to_local(in_w_o);
+  if (w_o.z <= kEpsilon) return Spec<SP>::make(0.0f);
+  V2 roughness = evaluate_roughness(m);
+  IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
+  IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  Spec<SP> value = eval_dielectric<SP>(d.wavelength, smp, w_i, w_o, true, roughness, ext_ior, int_ior, thinfilm);
+  return 2.0f * value * apply_image<SP>(sc, m.reflectance, d.wavelength);
+}
+template <bool SP>
+DEVN float plastic_specular_pdf(const DeviceScene& sc, const BData& d, V3 in_w_o, const etxb_material& m, Smp& smp) {
+  Frame lf = {d.tan, d.btn, d.nrm, false};
+  V3 w_i = lf.to_local(-d.w_i);
+  if (w_i.z <= kEpsilon) return 0.0f;
+  V3 w_o = lf.to_local(in_w_o);
+  if (w_o.z <= kEpsilon) return 0.0f;
+  IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
+  IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
+  V2 roughness = evaluate_roughness(m);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  V3 wh = normalize(w_o + w_i);
+  float dwh_dwo = 1.0f / (4.0f * dot(w_o, wh));
+  MicroRay ray = micro_ray(w_i, roughness);
+  float dg = d_ggx(wh, roughness);
+  float prob = tmax(0.0f, dot(wh, ray.w) * dg / ((1.0f + ray.Lambda) * ray.w.z));
+  float f = fresnel_calculate<SP>(d.wavelength, dot(w_i, wh), ext_ior, int_ior, thinfilm).monochromatic();
+  prob *= f;
+  return fabsf(prob * dwh_dwo);
+}
+template <bool SP>
+DEVN BEval<SP> plastic_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
+  Frame frame = normal_frame(d);
+  V3 mh = normalize(w_o - d.w_i);
+  float n_dot_o = dot(frame.nrm, w_o);
+  float m_dot_o = dot(mh, w_o);
+  if ((n_dot_o <= kEpsilon) || (m_dot_o <= kEpsilon)) return beval_zero<SP>();
+  IorSample<SP> eta_e = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
+  IorSample<SP> eta_i = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  Spec<SP> fr = fresnel_calculate<SP>(d.wavelength, dot(d.w_i, mh), eta_e, eta_i, thinfilm);
+  V3 local_w_o = frame.to_local(w_o);
+  BEval<SP> diff_layer = diffuse_layer<SP>(sc, d, local_w_o, m);
+  Spec<SP> spec_layer = plastic_specular_func<SP>(sc, d, w_o, m, smp);
+  float spec_pdf = plastic_specular_pdf<SP>(sc, d, w_o, m, smp);
+  BEval<SP> e;
+  e.eta = 1.0f;
+  e.func = diff_layer.func * (1.0f - fr) + spec_layer / n_dot_o;
+  e.bsdf = diff_layer.func * (1.0f - fr) * n_dot_o + spec_layer;
+  e.pdf = diff_layer.pdf * (1.0f - fr).monochromatic() + spec_pdf;
+  return e;
+}
+template <bool SP>
+DEVN float plastic_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
+  Frame frame = normal_frame(d);
+  V3 mh = normalize(w_o - d.w_i);
+  float m_dot_o = dot(mh, w_o);
+  float n_dot_o = dot(frame.nrm, w_o);
+  if ((n_dot_o <= kEpsilon) || (m_dot_o <= kEpsilon)) return 0.0f;
+  IorSample<SP> eta_e = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
+  IorSample<SP> eta_i = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  Spec<SP> fr = fresnel_calculate<SP>(d.wavelength, dot(d.w_i, mh), eta_e, eta_i, thinfilm);
+  float diff_pdf = kInvPi * n_dot_o;
+  float spec_pdf = plastic_specular_pdf<SP>(sc, d, w_o, m, smp);
+  return diff_pdf * (1.0f - fr).monochromatic() + spec_pdf;
+}
+template <bool SP>
+DEVN BSample<SP> plastic_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
+  Frame frame = normal_frame(d);
+  V2 roughness = evaluate_roughness(m);
+  V3 mh = ggx_sample_normal(frame, roughness, smp, d.w_i);
+  IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
+  IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  Spec<SP> f = fresnel_calculate<SP>(d.wavelength, dot(d.w_i, mh), ext_ior, int_ior, thinfilm);
+  V3 w_i = frame.to_local(-d.w_i);
+  if (w_i.z <= kEpsilon) return bsample_zero<SP>();
+  V3 in_w_o = {0.0f, 0.0f, 0.0f};
+  bool sample_diffuse = smp.next() > f.monochromatic();
+  if (sample_diffuse == false) {
+    in_w_o = reflect(d.w_i, mh);
+    sample_diffuse = dot(frame.nrm, in_w_o) <= kEpsilon;
+  }
+  if (sample_diffuse) {
+    in_w_o = frame.from_local(sample_cosine_local(smp.next_2d(), 1.0f));
+  }
+  BEval<SP> eval = plastic_evaluate<SP>(sc, d, in_w_o, m, smp);
+  BSample<SP> r = bsample_zero<SP>();
+  r.w_o = in_w_o;
+  r.weight = eval.bsdf / eval.pdf;
+  r.properties = kBsdfReflection | (sample_diffuse ? kBsdfDiffuse : 0u);
+  r.medium_index = d.current_medium;
+  r.pdf = eval.pdf;
+  return r;
+}
+
+// ---- Thinfilm class (delta; bsdf_dielectric.hxx:3-58) -----------------------------------------------------------
+template <bool SP>
+DEV BSample<SP> thinfilm_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
+  Frame frame = normal_frame(d);
+  IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
+  IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  Spec<SP> fr = fresnel_calculate<SP>(d.wavelength, dot(d.w_i, d.nrm), ext_ior, int_ior, thinfilm);
+  float f = fr.monochromatic();
+  BSample<SP> r = bsample_zero<SP>();
+  if (smp.next() <= f) {
+    r.w_o = normalize(reflect(d.w_i, frame.nrm));
+    r.pdf = f;
+    r.weight = apply_image<SP>(sc, m.reflectance, d.wavelength);
+    r.weight *= fr / f;
+    r.properties = kBsdfDelta | kBsdfReflection;
+    r.medium_index = d.current_medium;
+  } else {
+    r.w_o = d.w_i;
+    r.pdf = 1.0f - f;
+    r.weight = apply_image<SP>(sc, m.scattering, d.wavelength);
+    r.weight *= (1.0f - fr) / (1.0f - f);
+    r.properties = kBsdfDelta | kBsdfTransmission | kBsdfMediumChanged;
+    r.medium_index = frame.entering ? m.int_medium : m.ext_medium;
+  }
+  return r;
+}
+
+// ---- Translucent (bsdf_various.hxx:135-215) ---------------------------------------------------------------------
+template <bool SP>
+DEV BSample<SP> translucent_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
+  Frame frame = normal_frame(d);
+  Spec<SP> tr = apply_image<SP>(sc, m.scattering, d.wavelength);
+  Spec<SP> rf = apply_image<SP>(sc, m.reflectance, d.wavelength);
+  float tr_value = tr.monochromatic(), rf_value = rf.monochromatic();
+  float total = tr_value + rf_value;
+  if (total == 0.0f) return bsample_zero<SP>();
+  V3 w_o = sample_cosine_around(smp.next_2d(), frame.nrm, 1.0f);
+  float n_dot_o = fabsf(dot(w_o, frame.nrm));
+  BSample<SP> r = bsample_zero<SP>();
+  if (smp.next() < tr_value / total) {
+    r.eta = 1.0f;
+    r.w_o = -w_o;
+    r.pdf = n_dot_o * kInvPi * (tr_value / total);
+    r.properties = kBsdfDiffuse | kBsdfTransmission | kBsdfMediumChanged;
+    r.medium_index = frame.entering ? m.int_medium : m.ext_medium;
+    r.weight = tr;
+  } else {
+    r.eta = 1.0f;
+    r.w_o = w_o;
+    r.pdf = n_dot_o * kInvPi * (rf_value / total);
+    r.properties = kBsdfDiffuse | kBsdfReflection;
+    r.medium_index = d.current_medium;
+    r.weight = rf;
+  }
+  return r;
+}
+template <bool SP>
+DEV BEval<SP> translucent_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m) {
+  Frame frame = normal_frame(d);
+  float n_dot_i = -dot(frame.nrm, d.w_i);
+  float n_dot_o = dot(frame.nrm, w_o);
+  bool reflection = n_dot_o * n_dot_i > 0.0f;
+  Spec<SP> tr = apply_image<SP>(sc, m.scattering, d.wavelength);
+  Spec<SP> rf = apply_image<SP>(sc, m.reflectance, d.wavelength);
+  float tr_value = tr.monochromatic(), rf_value = rf.monochromatic();
+  float total = tr_value + rf_value;
+  if (total == 0.0f) return beval_zero<SP>();
+  float scale = (total > 1.0f) ? 1.0f / total : 1.0f;
+  n_dot_o = fabsf(n_dot_o);
+  BEval<SP> e;
+  e.eta = 1.0f;
+  e.func = (reflection ? rf : tr) * (scale * kInvPi);
+  e.bsdf = e.func * n_dot_o;
+  e.pdf = kInvPi * n_dot_o * (reflection ? rf_value / total : tr_value / total);
+  return e;
+}
+template <bool SP>
+DEV float translucent_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m) {
+  Frame frame = normal_frame(d);
+  float n_dot_i = -dot(frame.nrm, d.w_i);
+  float n_dot_o = dot(frame.nrm, w_o);
+  float tr_value = apply_image<SP>(sc, m.scattering, d.wavelength).monochromatic();
+  float rf_value = apply_image<SP>(sc, m.reflectance, d.wavelength).monochromatic();
+  float total = tr_value + rf_value;
+  bool reflection = n_dot_o * n_dot_i > 0.0f;
+  return (total == 0.0f) ? 0.0f : kInvPi * fabsf(n_dot_o) * (reflection ? rf_value / total : tr_value / total);
+}
+
+// ---- Mirror (bsdf_various.hxx:217-262) ----------------------------------------------------------------------------
+DEV bool direction_matches(V3 ideal, V3 actual) {  // math.hxx:1087-1091
+  const V3 i = normalize(ideal);
+  const V3 a = normalize(actual);
+  return dot(i, a) > 1.0f - kInvMaxHalf;
+}
+template <bool SP>
+DEV BSample<SP> mirror_sample(const DeviceScene& sc, const BData& d, const etxb_material& m) {
+  Frame frame = normal_frame(d);
+  BSample<SP> r = bsample_zero<SP>();
+  r.w_o = normalize(reflect(d.w_i, frame.nrm));
+  r.weight = apply_image<SP>(sc, m.scattering, d.wavelength);
+  r.pdf = 1.0f;
+  r.properties = kBsdfDelta | kBsdfReflection;
+  return r;
+}
+template <bool SP>
+DEV BEval<SP> mirror_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m) {
+  BEval<SP> e = beval_zero<SP>();
+  Frame frame = normal_frame(d);
+  const V3 ideal_w_o = normalize(reflect(d.w_i, frame.nrm));
+  const V3 actual_w_o = normalize(w_o);
+  if (direction_matches(ideal_w_o, actual_w_o)) {
+    e.func = apply_image<SP>(sc, m.scattering, d.wavelength);
+    e.bsdf = e.func;
+    e.pdf = 1.0f;
+  }
+  return e;
+}
+DEV float mirror_pdf(const BData& d, V3 w_o) {
+  Frame frame = normal_frame(d);
+  const V3 ideal_w_o = normalize(reflect(d.w_i, frame.nrm));
+  const V3 actual_w_o = normalize(w_o);
+  return direction_matches(ideal_w_o, actual_w_o) ? 1.0f : 0.0f;
+}
+
+// ---- Velvet (bsdf_velvet.hxx) -------------------------------------------------------------------------------------
+DEV float lambda_velvet_l(float r, float x) {
+  x = fmaxf(x, 0.0f);
+  float t0 = sqr(1.0f - r), t1 = (1.0f - sqr(1.0f - r));
+  float a = t0 * 25.3245f + t1 * 21.5473f;
+  float b = t0 * 3.32435f + t1 * 3.82987f;
+  float c = t0 * 0.16801f + t1 * 0.19823f;
+  float dd = t0 * -1.27393f + t1 * -1.97760f;
+  float e = t0 * -4.85967f + t1 * -4.32054f;
+  return a / (1.0f + b * m_pow(x, c)) + dd * x + e;
+}
+DEV float lambda_velvet(float r, float cos_t) {
+  if (cos_t < 0.5f) return m_exp(lambda_velvet_l(r, cos_t));
+  return m_exp(2.0f * lambda_velvet_l(r, 0.5f) - lambda_velvet_l(r, 1.0f - cos_t));
+}
+DEV float fresnel_approximate(float f0, float f90, float cos_t) { return f0 + (f90 - f0) * m_pow(fmaxf(1.0f - cos_t, 0.0f), 5.0f); }
+template <bool SP>
+DEV BEval<SP> velvet_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m) {
+  Frame frame = normal_frame(d);
+  float n_dot_o = fmaxf(0.0f, dot(w_o, frame.nrm));
+  float n_dot_i = fmaxf(0.0f, -dot(d.w_i, frame.nrm));
+  if ((n_dot_o <= kEpsilon) || (n_dot_i <= kEpsilon)) return beval_zero<SP>();
+  V3 mh = normalize(w_o - d.w_i);
+  float m_dot_o = fmaxf(0.0f, dot(w_o, mh));
+  float m_dot_i = fmaxf(0.0f, -dot(d.w_i, mh));
+  if ((m_dot_o <= kEpsilon) || (m_dot_i <= kEpsilon)) return beval_zero<SP>();
+  V2 roughness = evaluate_roughness(m);
+  float specular_scale_base = 0.0f;
+  float alpha = 0.5f * (roughness.x + roughness.y);
+  if (alpha > kEpsilon) {
+    float inv_alpha = 1.0f / (kEpsilon + alpha);
+    float m_dot_n = dot(mh, frame.nrm);
+    float sin_t = (1.0f - m_dot_n * m_dot_n);
+    float dd = (2.0f + inv_alpha) * m_pow(sin_t, 0.5f * inv_alpha) / kDoublePi;
+    float l_i = lambda_velvet(alpha, n_dot_i);
+    float l_o = lambda_velvet(alpha, n_dot_o);
+    float g = 1.0f / (1.0f + l_i + l_o);
+    specular_scale_base = 0.25f * dd * g / n_dot_i;
+  }
+  Spec<SP> diffuse = apply_image<SP>(sc, m.scattering, d.wavelength);
+  Spec<SP> specular = apply_image<SP>(sc, m.reflectance, d.wavelength);
+  // diffuse_burley
+  float f90 = 0.5f + 2.0f * alpha * m_dot_o * m_dot_o;
+  float lightScatter = fresnel_approximate(1.0f, f90, n_dot_o);
+  float viewScatter = fresnel_approximate(1.0f, f90, n_dot_i);
+  float diffuse_scale = lightScatter * viewScatter * kInvPi;
+  BEval<SP> e;
+  e.eta = 1.0f;
+  e.func = diffuse * diffuse_scale + specular * specular_scale_base / n_dot_o;
+  e.bsdf = diffuse * diffuse_scale * n_dot_o + specular * specular_scale_base;
+  e.pdf = 1.0f / kDoublePi;
+  return e;
+}
+template <bool SP>
+DEV BSample<SP> velvet_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
+  Frame frame = normal_frame(d);
+  V3 w_o = sample_cosine_around(smp.next_2d(), frame.nrm, 0.0f);
+  BEval<SP> eval = velvet_evaluate<SP>(sc, d, w_o, m);
+  BSample<SP> r = bsample_zero<SP>();
+  r.w_o = w_o;
+  r.properties = kBsdfReflection | kBsdfDiffuse;
+  r.medium_index = d.current_medium;
+  r.eta = 1.0f;
+  r.pdf = eval.pdf;
+  r.weight = eval.bsdf / eval.pdf;
+  return r;
+}
+DEV float velvet_pdf(const BData& d) {
+  Frame frame = normal_frame(d);
+  if (frame.entering == false) return 0.0f;
+  return 1.0f / kDoublePi;
+}
+
+// ---- Principled: stochastic pick of Conductor / Dielectric / Plastic on a modified copy of the material (bsdf_principled.hxx) ----
+DEV void principled_as_conductor(const DeviceScene& sc, etxb_material& m) {
+  m.int_ior.cls = kSpdClassConductor;
+  m.int_ior.eta_index = sc.default_conductor_eta;
+  m.int_ior.k_index = sc.default_conductor_k;
+  m.scattering.image_index = kInvalidIndex;
+}
+DEV void principled_as_dielectric(const DeviceScene& sc, etxb_material& m) {
+  m.int_ior.cls = 3u;  // SpectralDistribution::Class::Dielectric
+  m.int_ior.eta_index = sc.default_dielectric_eta;
+  m.int_ior.k_index = kInvalidIndex;
+  m.reflectance.image_index = kInvalidIndex;
+}
+template <bool SP>
+DEVN BSample<SP> principled_sample(const DeviceScene& sc, const BData& d, const etxb_material& in_m, Smp& smp) {
+  etxb_material m = in_m;
+  float metalness = m.metalness.value[0] * 1.0f;
+  if (smp.next() < metalness) {
+    principled_as_conductor(sc, m);
+    return conductor_sample<SP>(sc, d, m, smp);
+  }
+  principled_as_dielectric(sc, m);
+  if (smp.next() < m.transmission.value[0]) return dielectric_sample<SP>(sc, d, m, smp);
+  return plastic_sample<SP>(sc, d, m, smp);
+}
+template <bool SP>
+DEVN BEval<SP> principled_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& in_m, Smp& smp) {
+  etxb_material m = in_m;
+  float metalness = m.metalness.value[0] * 1.0f;
+  if (smp.next() < metalness) {
+    principled_as_conductor(sc, m);
+    return conductor_evaluate<SP>(sc, d, w_o, m, smp);
+  }
+  principled_as_dielectric(sc, m);
+  if (smp.next() < m.transmission.value[0]) return dielectric_evaluate<SP>(sc, d, w_o, m, smp);
+  return plastic_evaluate<SP>(sc, d, w_o, m, smp);
+}
+template <bool SP>
+DEVN float principled_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& in_m, Smp& smp) {
+  etxb_material m = in_m;
+  float metalness = m.metalness.value[0] * 1.0f;
+  if (smp.next() < metalness) {
+    principled_as_conductor(sc, m);
+    return conductor_pdf(d, w_o, m);
+  }
+  principled_as_dielectric(sc, m);
+  if (smp.next() < m.transmission.value[0]) return dielectric_pdf<SP>(sc, d, w_o, m, smp);
+  return plastic_pdf<SP>(sc, d, w_o, m, smp);
+}
+
+// ---- dispatch (scene_bsdf.hxx:56-90) -----------------------------------------------------------------------
+// Classes / variants not implemented on the device are rejected by etxb_upload_scene (ETXB_ERR_UNSUPPORTED).
 template <bool SP>
 DEV BSample<SP> bsdf_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
   switch (m.cls) {
-    case ETXB_MAT_DIELECTRIC:
-      return dielectric_sample<SP>(sc, d, m, smp);
-    default:
-      return diffuse_sample<SP>(sc, d, m, smp);
+    case ETXB_MAT_DIFFUSE: return diffuse_sample<SP>(sc, d, m, smp);
+    case ETXB_MAT_TRANSLUCENT: return translucent_sample<SP>(sc, d, m, smp);
+    case ETXB_MAT_PLASTIC: return plastic_sample<SP>(sc, d, m, smp);
+    case ETXB_MAT_CONDUCTOR: return conductor_sample<SP>(sc, d, m, smp);
+    case ETXB_MAT_DIELECTRIC: return dielectric_sample<SP>(sc, d, m, smp);
+    case ETXB_MAT_THINFILM: return thinfilm_sample<SP>(sc, d, m, smp);
+    case ETXB_MAT_MIRROR: return mirror_sample<SP>(sc, d, m);
+    case ETXB_MAT_VELVET: return velvet_sample<SP>(sc, d, m, smp);
+    case ETXB_MAT_PRINCIPLED: return principled_sample<SP>(sc, d, m, smp);
+    case ETXB_MAT_BOUNDARY: {  // BoundaryBSDF::sample (bsdf_various.hxx:266-277)
+      BSample<SP> r = bsample_zero<SP>();
+      r.w_o = d.w_i;
+      r.pdf = 1.0f;
+      r.weight = Spec<SP>::make(1.0f);
+      r.properties = kBsdfTransmission | kBsdfMediumChanged;
+      r.medium_index = (dot(d.nrm, d.w_i) < 0.0f) ? m.int_medium : m.ext_medium;
+      return r;
+    }
+    default: {  // VoidBSDF::sample (bsdf_various.hxx:5-15)
+      BSample<SP> r = bsample_zero<SP>();
+      r.w_o = d.w_i;
+      r.properties = kBsdfDelta;
+      r.medium_index = d.current_medium;
+      return r;
+    }
   }
 }
 template <bool SP>
 DEV BEval<SP> bsdf_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
   switch (m.cls) {
-    case ETXB_MAT_DIELECTRIC:
-      return dielectric_evaluate<SP>(sc, d, w_o, m, smp);
-    default:
-      return diffuse_evaluate<SP>(sc, d, w_o, m);
+    case ETXB_MAT_DIFFUSE: return diffuse_evaluate<SP>(sc, d, w_o, m);
+    case ETXB_MAT_TRANSLUCENT: return translucent_evaluate<SP>(sc, d, w_o, m);
+    case ETXB_MAT_PLASTIC: return plastic_evaluate<SP>(sc, d, w_o, m, smp);
+    case ETXB_MAT_CONDUCTOR: return conductor_evaluate<SP>(sc, d, w_o, m, smp);
+    case ETXB_MAT_DIELECTRIC: return dielectric_evaluate<SP>(sc, d, w_o, m, smp);
+    case ETXB_MAT_MIRROR: return mirror_evaluate<SP>(sc, d, w_o, m);
+    case ETXB_MAT_VELVET: return velvet_evaluate<SP>(sc, d, w_o, m);
+    case ETXB_MAT_PRINCIPLED: return principled_evaluate<SP>(sc, d, w_o, m, smp);
+    default: return beval_zero<SP>();  // Thinfilm, Boundary, Void evaluate to zero
   }
 }
 template <bool SP>
 DEV float bsdf_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
   switch (m.cls) {
-    case ETXB_MAT_DIELECTRIC:
-      return dielectric_pdf<SP>(sc, d, w_o, m, smp);
-    default:
-      return diffuse_pdf(d, w_o);
+    case ETXB_MAT_DIFFUSE: return diffuse_pdf(d, w_o);
+    case ETXB_MAT_TRANSLUCENT: return translucent_pdf<SP>(sc, d, w_o, m);
+    case ETXB_MAT_PLASTIC: return plastic_pdf<SP>(sc, d, w_o, m, smp);
+    case ETXB_MAT_CONDUCTOR: return conductor_pdf(d, w_o, m);
+    case ETXB_MAT_DIELECTRIC: return dielectric_pdf<SP>(sc, d, w_o, m, smp);
+    case ETXB_MAT_MIRROR: return mirror_pdf(d, w_o);
+    case ETXB_MAT_VELVET: return velvet_pdf(d);
+    case ETXB_MAT_PRINCIPLED: return principled_pdf<SP>(sc, d, w_o, m, smp);
+    default: return 0.0f;
   }
 }
 template <bool SP>

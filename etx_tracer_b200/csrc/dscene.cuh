@@ -58,6 +58,7 @@ struct DeviceScene {
   uint32_t min_path_length, max_path_length, samples, random_path_termination;
   uint32_t spectral;
   uint32_t has_blue_noise;
+  uint32_t default_dielectric_eta, default_conductor_eta, default_conductor_k;
   etxb_camera camera;
 };
 

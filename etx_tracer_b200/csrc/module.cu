@@ -195,7 +195,7 @@ struct LaunchTimer {
   }
 };
 
-bool material_class_supported_host(uint32_t cls) { return (cls == ETXB_MAT_DIFFUSE) || (cls == ETXB_MAT_DIELECTRIC); }
+bool material_class_supported_host(uint32_t cls) { return (cls <= ETXB_MAT_VOID) && (cls != ETXB_MAT_BOUNDARY); }  // Boundary needs media (not on the device yet)
 
 uint32_t next_pow2(uint64_t v) {
   // next_power_of_two (math.hxx:1001-1010)
@@ -602,7 +602,9 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   for (uint64_t i = 0; i < s.materials.count; ++i) {
     const etxb_material& m = mats[i];
     bool lambert = (m.cls == ETXB_MAT_DIFFUSE) && (m.diffuse_variation == 0);
-    bool always_delta = (m.cls == ETXB_MAT_DIELECTRIC) && (std::max(m.roughness.value[0], m.roughness.value[1]) <= 1.0e-4f);
+    bool smooth = std::max(m.roughness.value[0], m.roughness.value[1]) <= 1.0e-4f;
+    bool always_delta = (((m.cls == ETXB_MAT_DIELECTRIC) || (m.cls == ETXB_MAT_CONDUCTOR)) && smooth) || (m.cls == ETXB_MAT_THINFILM) || (m.cls == ETXB_MAT_MIRROR) ||
+                        (m.cls == ETXB_MAT_VOID);
     if (!lambert && !always_delta) ctx->has_stochastic_merge = true;
   }
   const auto* emitters = static_cast<const etxb_emitter*>(s.emitter_instances.a);
@@ -677,6 +679,9 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   d.samples = s.samples;
   d.random_path_termination = s.random_path_termination;
   d.spectral = (s.flags & ETXB_SCENE_SPECTRAL) ? 1u : 0u;
+  d.default_dielectric_eta = s.default_dielectric_eta;
+  d.default_conductor_eta = s.default_conductor_eta;
+  d.default_conductor_k = s.default_conductor_k;
   d.camera = cam;
   ctx->spectral = d.spectral != 0;
 

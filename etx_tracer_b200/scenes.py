@@ -100,7 +100,7 @@ class SceneData:
         return len(self.spectra) - 1
 
     def add_material(self, name, cls=S.MAT_DIFFUSE, kd=None, ks=None, roughness=0.0, emission=None, two_sided=0, int_ior=None,
-                     thinfilm=None, collimation=0.0, int_medium=S.INVALID, ext_medium=S.INVALID, diffuse_variation=0):
+                     thinfilm=None, collimation=0.0, int_medium=S.INVALID, ext_medium=S.INVALID, diffuse_variation=0, metalness=0.0, transmission=0.0):
         m = np.zeros(1, dtype=S.MATERIAL)
         for fld in ("reflectance", "scattering", "emission"):
             m[fld]["spectrum_index"] = S.INVALID
@@ -131,6 +131,8 @@ class SceneData:
             m["reflectance"]["spectrum_index"] = self.add_spectrum(spd_rgb_reflectance(ks))
         r2 = f32(roughness) * f32(roughness)  # "Pr" is squared by the loader (scene_representation.cxx:1731-1738)
         m["roughness"]["value"][0][:2] = r2
+        m["metalness"]["value"][0][:] = metalness
+        m["transmission"]["value"][0][:] = transmission
         if emission is not None:
             m["emission"]["spectrum_index"] = self.add_spectrum(emission)
         if int_ior is not None:
@@ -500,6 +502,47 @@ def cornell_box(width=512, height=512, samples=16, spectral=False, sphere=False,
         sd.add_box([0.33, 0.3, 0.35], (0.3, 0.3, 0.3), -17.0, grey, s)
     sd.set_camera([0.0, 1.0, 3.82], [0.0, 1.0, -6.18], [0.0, 1.0, 0.0], width, height, 39.597755335771296, clip_near=0.1, clip_far=100.0)
     return sd.finalize(samples=samples, spectral=spectral, max_path_length=max_path_length)
+
+
+MATERIAL_KINDS = {
+    # name: add_material kwargs — one entry per Material::Class the device implements (material.hxx:53-68)
+    "conductor_rough": dict(cls=S.MAT_CONDUCTOR, ks=[1.0, 1.0, 1.0], roughness=0.45, int_ior="gold"),
+    "conductor_smooth": dict(cls=S.MAT_CONDUCTOR, ks=[0.9, 0.9, 0.9], roughness=0.0, int_ior="silver"),
+    "conductor_thinfilm": dict(cls=S.MAT_CONDUCTOR, ks=[1.0, 1.0, 1.0], roughness=0.3, int_ior="copper", thinfilm=("water", 320.0, 320.0)),
+    "plastic": dict(cls=S.MAT_PLASTIC, kd=[0.2, 0.4, 0.8], ks=[1.0, 1.0, 1.0], roughness=0.55, int_ior="plastic"),
+    "plastic_thinfilm": dict(cls=S.MAT_PLASTIC, kd=[0.7, 0.7, 0.7], ks=[1.0, 1.0, 1.0], roughness=0.4, int_ior="plastic", thinfilm=("glass", 300.0, 700.0)),
+    "dielectric_rough": dict(cls=S.MAT_DIELECTRIC, roughness=0.4, int_ior="glass"),
+    "dielectric_smooth": dict(cls=S.MAT_DIELECTRIC, roughness=0.0, int_ior="diamond"),
+    "thinfilm": dict(cls=S.MAT_THINFILM, kd=[0.9, 0.9, 0.9], ks=[1.0, 1.0, 1.0], int_ior="glass", thinfilm=("water", 250.0, 450.0)),
+    "mirror": dict(cls=S.MAT_MIRROR, kd=[0.9, 0.9, 0.9]),
+    "translucent": dict(cls=S.MAT_TRANSLUCENT, kd=[0.5, 0.5, 0.4], ks=[0.3, 0.4, 0.3]),
+    "velvet": dict(cls=S.MAT_VELVET, kd=[0.6, 0.1, 0.1], ks=[0.5, 0.5, 0.5], roughness=0.7),
+    "principled": dict(cls=S.MAT_PRINCIPLED, kd=[0.8, 0.5, 0.2], ks=[1.0, 1.0, 1.0], roughness=0.5, metalness=0.4, transmission=0.3),
+    "void": dict(cls=S.MAT_VOID),
+}
+
+
+def material_box(kind, width=32, height=32, samples=16, spectral=False, sphere_segments=16, sphere_rings=9):
+    """Cornell box whose tall box and a sphere carry one material class — the per-class parity scenes."""
+    sd = SceneData()
+    sd.name = f"material_box[{kind}]" + ("/spectral" if spectral else "/rgb")
+    white = sd.add_material("white", kd=[1.0, 1.0, 1.0], two_sided=1)
+    red = sd.add_material("leftWall", kd=[1.0, 0.0, 0.0], two_sided=1)
+    green = sd.add_material("rightWall", kd=[0.0, 1.0, 0.0], two_sided=1)
+    light = sd.add_material("light", kd=[0.0, 0.0, 0.0], emission=spd_rgb_luminance([10.018, 3.918, 0.932]), two_sided=1)
+    test = sd.add_material("test", **MATERIAL_KINDS[kind])
+    zf = 4.0
+    sd.add_quad([-1, 0, zf], [1, 0, zf], [1, 0, -1], [-1, 0, -1], white)
+    sd.add_quad([-1, 2, -1], [1, 2, -1], [1, 2, zf], [-1, 2, zf], white)
+    sd.add_quad([-1, 0, -1], [1, 0, -1], [1, 2, -1], [-1, 2, -1], white)
+    sd.add_quad([-1, 0, zf], [-1, 0, -1], [-1, 2, -1], [-1, 2, zf], red)
+    sd.add_quad([1, 0, -1], [1, 0, zf], [1, 2, zf], [1, 2, -1], green)
+    sd.add_quad([-1, 0, zf], [-1, 2, zf], [1, 2, zf], [1, 0, zf], white)
+    sd.add_quad([-0.24, 1.98, -0.22], [0.23, 1.98, -0.22], [0.23, 1.98, 0.16], [-0.24, 1.98, 0.16], light)
+    sd.add_box([-0.33, 0.6, -0.29], (0.3, 0.6, 0.3), 17.0, test)
+    sd.add_uv_sphere([0.38, 0.351, 0.35], 0.35, sphere_segments, sphere_rings, test)
+    sd.set_camera([0.0, 1.0, 3.82], [0.0, 1.0, -6.18], [0.0, 1.0, 0.0], width, height, 39.597755335771296, clip_near=0.1, clip_far=100.0)
+    return sd.finalize(samples=samples, spectral=spectral)
 
 
 def config(name, scale=1.0):
