@@ -189,9 +189,9 @@ DEV Spec<SP> fresnel_calculate(float wavelength, float cos_theta, const IorSampl
   }
 }
 
-// scene_bsdf.hxx:110-126 evaluate_thinfilm (thickness image unsupported -> t = 1)
+// scene_bsdf.hxx:110-126 evaluate_thinfilm
 template <bool SP>
-DEV ThinfilmEval<SP> evaluate_thinfilm(const DeviceScene& sc, float wavelength, const etxb_thinfilm& film, Smp& smp) {
+DEV ThinfilmEval<SP> evaluate_thinfilm(const DeviceScene& sc, float wavelength, const etxb_thinfilm& film, V2 uv, Smp& smp) {
   ThinfilmEval<SP> r;
   r.rgb_wavelengths = {610.0f, 537.0f, 450.0f};
   if (film.max_thickness * film.min_thickness <= 0.0f) {
@@ -201,7 +201,7 @@ DEV ThinfilmEval<SP> evaluate_thinfilm(const DeviceScene& sc, float wavelength, 
     r.thickness = 0.0f;
     return r;
   }
-  float t = 1.0f;
+  float t = (film.thickness_image == kInvalidIndex) ? 1.0f : image_evaluate(sc.images[film.thickness_image], uv, nullptr).x;
   r.thickness = lerpf(film.min_thickness, film.max_thickness, t);
   if constexpr (SP) {
     r.rgb_wavelengths = {wavelength, wavelength, wavelength};
@@ -476,7 +476,7 @@ DEVN Spec<SP> eval_dielectric(float wavelength, Smp& smp, V3 wi, V3 wo, bool wo_
 template <bool SP>
 DEV BEval<SP> diffuse_layer(const DeviceScene& sc, const BData& d, V3 local_w_o, const etxb_material& m) {
   if (local_w_o.z <= 0.0f) return beval_zero<SP>();
-  Spec<SP> diffuse = apply_image<SP>(sc, m.scattering, d.wavelength);
+  Spec<SP> diffuse = apply_image<SP>(sc, m.scattering, d.tex, d.wavelength);
   BEval<SP> e;
   e.eta = 1.0f;
   e.func = diffuse / kPi;
@@ -512,8 +512,8 @@ DEV float diffuse_pdf(const BData& d, V3 w_o) {
 }
 
 // ---- Dielectric (bsdf_dielectric.hxx:60-259) ---------------------------------------------------------------
-DEV bool dielectric_is_delta(const etxb_material& m) {
-  V2 r = evaluate_roughness(m);
+DEV bool dielectric_is_delta(const DeviceScene& sc, const etxb_material& m, V2 tex) {
+  V2 r = evaluate_roughness(sc, m, tex);
   return tmax(r.x, r.y) <= kDeltaAlphaTreshold;
 }
 template <bool SP>
@@ -523,10 +523,10 @@ DEVN float dielectric_pdf(const DeviceScene& sc, const BData& d, V3 in_w_o, cons
   if (fabsf(w_i.z) <= kEpsilon) return 0.0f;
   V3 w_o = lf.to_local(in_w_o);
   if (fabsf(w_o.z) <= kEpsilon) return 0.0f;
-  V2 roughness = evaluate_roughness(m);
+  V2 roughness = evaluate_roughness(sc, m, d.tex);
   IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
   IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
-  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, d.tex, smp);
   const bool outside = w_i.z > 0;
   const bool reflection = w_i.z * w_o.z > 0.0f;
   V3 wh;
@@ -556,10 +556,10 @@ DEVN BSample<SP> dielectric_sample(const DeviceScene& sc, const BData& d, const 
   float direction_scale = in_outside ? 1.0f : -1.0f;
   IorSample<SP> ext_ior = in_outside ? evaluate_ior<SP>(sc, m.ext_ior, d.wavelength) : evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
   IorSample<SP> int_ior = in_outside ? evaluate_ior<SP>(sc, m.int_ior, d.wavelength) : evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
-  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, d.tex, smp);
   BSample<SP> result = bsample_zero<SP>();
   result.weight = Spec<SP>::make(1.0f);
-  V2 roughness = evaluate_roughness(m);
+  V2 roughness = evaluate_roughness(sc, m, d.tex);
   MicroRay ray = micro_ray(-direction_scale * w_i, roughness);
   ray.update_height(1.0f);
   bool ray_outside = true;
@@ -586,17 +586,17 @@ DEVN BSample<SP> dielectric_sample(const DeviceScene& sc, const BData& d, const 
     }
   }
   V3 lw_o = direction_scale * (ray_outside ? ray.w : -ray.w);
-  uint32_t delta_sample = dielectric_is_delta(m) ? kBsdfDelta : 0u;
+  uint32_t delta_sample = dielectric_is_delta(sc, m, d.tex) ? kBsdfDelta : 0u;
   if (w_i.z * lw_o.z > 0.0f) {
     result.eta = 1.0f;
-    result.weight = (result.weight / result.weight.monochromatic()) * apply_image<SP>(sc, m.reflectance, d.wavelength);
+    result.weight = (result.weight / result.weight.monochromatic()) * apply_image<SP>(sc, m.reflectance, d.tex, d.wavelength);
     result.properties = kBsdfReflection | delta_sample;
     result.medium_index = d.current_medium;
   } else {
     float eta = (int_ior.eta / ext_ior.eta).monochromatic();
     float factor = sqr(1.0f / eta);
     result.eta = eta;
-    result.weight = (result.weight / result.weight.monochromatic()) * apply_image<SP>(sc, m.scattering, d.wavelength) * factor;
+    result.weight = (result.weight / result.weight.monochromatic()) * apply_image<SP>(sc, m.scattering, d.tex, d.wavelength) * factor;
     result.properties = kBsdfTransmission | kBsdfMediumChanged | delta_sample;
     result.medium_index = in_outside ? m.int_medium : m.ext_medium;
   }
@@ -611,10 +611,10 @@ DEVN BEval<SP> dielectric_evaluate(const DeviceScene& sc, const BData& d, V3 in_
   if (fabsf(w_i.z) <= kEpsilon) return beval_zero<SP>();
   V3 w_o = lf.to_local(in_w_o);
   if (fabsf(w_o.z) <= kEpsilon) return beval_zero<SP>();
-  V2 roughness = evaluate_roughness(m);
+  V2 roughness = evaluate_roughness(sc, m, d.tex);
   IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
   IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
-  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, d.tex, smp);
   bool forward_path = d.path_source == kPathCamera;
   float backward_scale = fabsf(1.0f / w_i.z);
   Spec<SP> value;
@@ -638,7 +638,7 @@ DEVN BEval<SP> dielectric_evaluate(const DeviceScene& sc, const BData& d, V3 in_
   bool reflection = w_i.z * w_o.z > 0.0f;
   BEval<SP> e;
   e.eta = 1.0f;
-  e.func = (2.0f * value) * apply_image<SP>(sc, reflection ? m.reflectance : m.scattering, d.wavelength);
+  e.func = (2.0f * value) * apply_image<SP>(sc, reflection ? m.reflectance : m.scattering, d.tex, d.wavelength);
   e.bsdf = e.func * fabsf(w_o.z);
   e.pdf = dielectric_pdf<SP>(sc, d, in_w_o, m, smp);
   return e;
@@ -706,14 +706,14 @@ DEVN BSample<SP> conductor_sample(const DeviceScene& sc, const BData& d, const e
   V3 w_i = lf.to_local(-d.w_i);
   IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
   IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
-  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
-  uint32_t delta_sample = dielectric_is_delta(m) ? kBsdfDelta : 0u;
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, d.tex, smp);
+  uint32_t delta_sample = dielectric_is_delta(sc, m, d.tex) ? kBsdfDelta : 0u;
   BSample<SP> result = bsample_zero<SP>();
   result.properties = kBsdfReflection | delta_sample;
   result.medium_index = d.current_medium;
   result.eta = 1.0f;
   result.weight = Spec<SP>::make(1.0f);
-  V2 roughness = evaluate_roughness(m);
+  V2 roughness = evaluate_roughness(sc, m, d.tex);
   MicroRay ray = micro_ray(-w_i, roughness);
   ray.update_height(1.0f);
   uint32_t scattering_order = 0;
@@ -732,7 +732,7 @@ DEVN BSample<SP> conductor_sample(const DeviceScene& sc, const BData& d, const e
     }
   }
   V3 lw_o = ray.w;
-  result.weight *= apply_image<SP>(sc, m.reflectance, d.wavelength);
+  result.weight *= apply_image<SP>(sc, m.reflectance, d.tex, d.wavelength);
   result.pdf = conductor_pdf_local(w_i, lw_o, roughness);
   result.w_o = normalize(lf.from_local(lw_o));
   return result;
@@ -744,25 +744,25 @@ DEVN BEval<SP> conductor_evaluate(const DeviceScene& sc, const BData& d, V3 in_w
   if (w_o.z <= kEpsilon) return beval_zero<SP>();
   V3 w_i = lf.to_local(-d.w_i);
   if (w_i.z <= kEpsilon) return beval_zero<SP>();
-  V2 roughness = evaluate_roughness(m);
+  V2 roughness = evaluate_roughness(sc, m, d.tex);
   IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
   IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
-  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, d.tex, smp);
   Spec<SP> value = eval_conductor<SP>(d.wavelength, smp, w_i, w_o, roughness, ext_ior, int_ior, thinfilm);
   BEval<SP> e;
   e.eta = 1.0f;
-  e.bsdf = value * apply_image<SP>(sc, m.reflectance, d.wavelength);
+  e.bsdf = value * apply_image<SP>(sc, m.reflectance, d.tex, d.wavelength);
   e.func = e.bsdf / w_o.z;
   e.pdf = conductor_pdf_local(w_i, w_o, roughness);
   return e;
 }
-DEV float conductor_pdf(const BData& d, V3 in_w_o, const etxb_material& m) {
+DEV float conductor_pdf(const DeviceScene& sc, const BData& d, V3 in_w_o, const etxb_material& m) {
   Frame lf = normal_frame(d);
   V3 w_o = lf.to_local(in_w_o);
   if (w_o.z <= kEpsilon) return 0.0f;
   V3 w_i = lf.to_local(-d.w_i);
   if (w_i.z <= kEpsilon) return 0.0f;
-  return conductor_pdf_local(w_i, w_o, evaluate_roughness(m));
+  return conductor_pdf_local(w_i, w_o, evaluate_roughness(sc, m, d.tex));
 }
 
 // ---- Plastic (bsdf_plastic.hxx) + GGX NormalDistribution::sample (bsdf.hxx:125-142) --------------------------------
@@ -791,12 +791,12 @@ DEVN Spec<SP> plastic_specular_func(const DeviceScene& sc, const BData& d, V3 in
   if (w_i.z <= kEpsilon) return Spec<SP>::make(0.0f);
   V3 w_o = lf.to_local(in_w_o);
   if (w_o.z <= kEpsilon) return Spec<SP>::make(0.0f);
-  V2 roughness = evaluate_roughness(m);
+  V2 roughness = evaluate_roughness(sc, m, d.tex);
   IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
   IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
-  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, d.tex, smp);
   Spec<SP> value = eval_dielectric<SP>(d.wavelength, smp, w_i, w_o, true, roughness, ext_ior, int_ior, thinfilm);
-  return 2.0f * value * apply_image<SP>(sc, m.reflectance, d.wavelength);
+  return 2.0f * value * apply_image<SP>(sc, m.reflectance, d.tex, d.wavelength);
 }
 template <bool SP>
 DEVN float plastic_specular_pdf(const DeviceScene& sc, const BData& d, V3 in_w_o, const etxb_material& m, Smp& smp) {
@@ -807,8 +807,8 @@ DEVN float plastic_specular_pdf(const DeviceScene& sc, const BData& d, V3 in_w_o
   if (w_o.z <= kEpsilon) return 0.0f;
   IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
   IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
-  V2 roughness = evaluate_roughness(m);
-  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  V2 roughness = evaluate_roughness(sc, m, d.tex);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, d.tex, smp);
   V3 wh = normalize(w_o + w_i);
   float dwh_dwo = 1.0f / (4.0f * dot(w_o, wh));
   MicroRay ray = micro_ray(w_i, roughness);
@@ -827,7 +827,7 @@ DEVN BEval<SP> plastic_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, c
   if ((n_dot_o <= kEpsilon) || (m_dot_o <= kEpsilon)) return beval_zero<SP>();
   IorSample<SP> eta_e = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
   IorSample<SP> eta_i = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
-  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, d.tex, smp);
   Spec<SP> fr = fresnel_calculate<SP>(d.wavelength, dot(d.w_i, mh), eta_e, eta_i, thinfilm);
   V3 local_w_o = frame.to_local(w_o);
   BEval<SP> diff_layer = diffuse_layer<SP>(sc, d, local_w_o, m);
@@ -849,7 +849,7 @@ DEVN float plastic_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const etxb
   if ((n_dot_o <= kEpsilon) || (m_dot_o <= kEpsilon)) return 0.0f;
   IorSample<SP> eta_e = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
   IorSample<SP> eta_i = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
-  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, d.tex, smp);
   Spec<SP> fr = fresnel_calculate<SP>(d.wavelength, dot(d.w_i, mh), eta_e, eta_i, thinfilm);
   float diff_pdf = kInvPi * n_dot_o;
   float spec_pdf = plastic_specular_pdf<SP>(sc, d, w_o, m, smp);
@@ -858,11 +858,11 @@ DEVN float plastic_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const etxb
 template <bool SP>
 DEVN BSample<SP> plastic_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
   Frame frame = normal_frame(d);
-  V2 roughness = evaluate_roughness(m);
+  V2 roughness = evaluate_roughness(sc, m, d.tex);
   V3 mh = ggx_sample_normal(frame, roughness, smp, d.w_i);
   IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
   IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
-  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, d.tex, smp);
   Spec<SP> f = fresnel_calculate<SP>(d.wavelength, dot(d.w_i, mh), ext_ior, int_ior, thinfilm);
   V3 w_i = frame.to_local(-d.w_i);
   if (w_i.z <= kEpsilon) return bsample_zero<SP>();
@@ -891,21 +891,21 @@ DEV BSample<SP> thinfilm_sample(const DeviceScene& sc, const BData& d, const etx
   Frame frame = normal_frame(d);
   IorSample<SP> ext_ior = evaluate_ior<SP>(sc, m.ext_ior, d.wavelength);
   IorSample<SP> int_ior = evaluate_ior<SP>(sc, m.int_ior, d.wavelength);
-  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, smp);
+  ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, d.tex, smp);
   Spec<SP> fr = fresnel_calculate<SP>(d.wavelength, dot(d.w_i, d.nrm), ext_ior, int_ior, thinfilm);
   float f = fr.monochromatic();
   BSample<SP> r = bsample_zero<SP>();
   if (smp.next() <= f) {
     r.w_o = normalize(reflect(d.w_i, frame.nrm));
     r.pdf = f;
-    r.weight = apply_image<SP>(sc, m.reflectance, d.wavelength);
+    r.weight = apply_image<SP>(sc, m.reflectance, d.tex, d.wavelength);
     r.weight *= fr / f;
     r.properties = kBsdfDelta | kBsdfReflection;
     r.medium_index = d.current_medium;
   } else {
     r.w_o = d.w_i;
     r.pdf = 1.0f - f;
-    r.weight = apply_image<SP>(sc, m.scattering, d.wavelength);
+    r.weight = apply_image<SP>(sc, m.scattering, d.tex, d.wavelength);
     r.weight *= (1.0f - fr) / (1.0f - f);
     r.properties = kBsdfDelta | kBsdfTransmission | kBsdfMediumChanged;
     r.medium_index = frame.entering ? m.int_medium : m.ext_medium;
@@ -917,8 +917,8 @@ DEV BSample<SP> thinfilm_sample(const DeviceScene& sc, const BData& d, const etx
 template <bool SP>
 DEV BSample<SP> translucent_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
   Frame frame = normal_frame(d);
-  Spec<SP> tr = apply_image<SP>(sc, m.scattering, d.wavelength);
-  Spec<SP> rf = apply_image<SP>(sc, m.reflectance, d.wavelength);
+  Spec<SP> tr = apply_image<SP>(sc, m.scattering, d.tex, d.wavelength);
+  Spec<SP> rf = apply_image<SP>(sc, m.reflectance, d.tex, d.wavelength);
   float tr_value = tr.monochromatic(), rf_value = rf.monochromatic();
   float total = tr_value + rf_value;
   if (total == 0.0f) return bsample_zero<SP>();
@@ -948,8 +948,8 @@ DEV BEval<SP> translucent_evaluate(const DeviceScene& sc, const BData& d, V3 w_o
   float n_dot_i = -dot(frame.nrm, d.w_i);
   float n_dot_o = dot(frame.nrm, w_o);
   bool reflection = n_dot_o * n_dot_i > 0.0f;
-  Spec<SP> tr = apply_image<SP>(sc, m.scattering, d.wavelength);
-  Spec<SP> rf = apply_image<SP>(sc, m.reflectance, d.wavelength);
+  Spec<SP> tr = apply_image<SP>(sc, m.scattering, d.tex, d.wavelength);
+  Spec<SP> rf = apply_image<SP>(sc, m.reflectance, d.tex, d.wavelength);
   float tr_value = tr.monochromatic(), rf_value = rf.monochromatic();
   float total = tr_value + rf_value;
   if (total == 0.0f) return beval_zero<SP>();
@@ -967,8 +967,8 @@ DEV float translucent_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const e
   Frame frame = normal_frame(d);
   float n_dot_i = -dot(frame.nrm, d.w_i);
   float n_dot_o = dot(frame.nrm, w_o);
-  float tr_value = apply_image<SP>(sc, m.scattering, d.wavelength).monochromatic();
-  float rf_value = apply_image<SP>(sc, m.reflectance, d.wavelength).monochromatic();
+  float tr_value = apply_image<SP>(sc, m.scattering, d.tex, d.wavelength).monochromatic();
+  float rf_value = apply_image<SP>(sc, m.reflectance, d.tex, d.wavelength).monochromatic();
   float total = tr_value + rf_value;
   bool reflection = n_dot_o * n_dot_i > 0.0f;
   return (total == 0.0f) ? 0.0f : kInvPi * fabsf(n_dot_o) * (reflection ? rf_value / total : tr_value / total);
@@ -985,7 +985,7 @@ DEV BSample<SP> mirror_sample(const DeviceScene& sc, const BData& d, const etxb_
   Frame frame = normal_frame(d);
   BSample<SP> r = bsample_zero<SP>();
   r.w_o = normalize(reflect(d.w_i, frame.nrm));
-  r.weight = apply_image<SP>(sc, m.scattering, d.wavelength);
+  r.weight = apply_image<SP>(sc, m.scattering, d.tex, d.wavelength);
   r.pdf = 1.0f;
   r.properties = kBsdfDelta | kBsdfReflection;
   return r;
@@ -997,7 +997,7 @@ DEV BEval<SP> mirror_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, con
   const V3 ideal_w_o = normalize(reflect(d.w_i, frame.nrm));
   const V3 actual_w_o = normalize(w_o);
   if (direction_matches(ideal_w_o, actual_w_o)) {
-    e.func = apply_image<SP>(sc, m.scattering, d.wavelength);
+    e.func = apply_image<SP>(sc, m.scattering, d.tex, d.wavelength);
     e.bsdf = e.func;
     e.pdf = 1.0f;
   }
@@ -1036,7 +1036,7 @@ DEV BEval<SP> velvet_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, con
   float m_dot_o = fmaxf(0.0f, dot(w_o, mh));
   float m_dot_i = fmaxf(0.0f, -dot(d.w_i, mh));
   if ((m_dot_o <= kEpsilon) || (m_dot_i <= kEpsilon)) return beval_zero<SP>();
-  V2 roughness = evaluate_roughness(m);
+  V2 roughness = evaluate_roughness(sc, m, d.tex);
   float specular_scale_base = 0.0f;
   float alpha = 0.5f * (roughness.x + roughness.y);
   if (alpha > kEpsilon) {
@@ -1049,8 +1049,8 @@ DEV BEval<SP> velvet_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, con
     float g = 1.0f / (1.0f + l_i + l_o);
     specular_scale_base = 0.25f * dd * g / n_dot_i;
   }
-  Spec<SP> diffuse = apply_image<SP>(sc, m.scattering, d.wavelength);
-  Spec<SP> specular = apply_image<SP>(sc, m.reflectance, d.wavelength);
+  Spec<SP> diffuse = apply_image<SP>(sc, m.scattering, d.tex, d.wavelength);
+  Spec<SP> specular = apply_image<SP>(sc, m.reflectance, d.tex, d.wavelength);
   // diffuse_burley
   float f90 = 0.5f + 2.0f * alpha * m_dot_o * m_dot_o;
   float lightScatter = fresnel_approximate(1.0f, f90, n_dot_o);
@@ -1099,7 +1099,7 @@ DEV void principled_as_dielectric(const DeviceScene& sc, etxb_material& m) {
 template <bool SP>
 DEVN BSample<SP> principled_sample(const DeviceScene& sc, const BData& d, const etxb_material& in_m, Smp& smp) {
   etxb_material m = in_m;
-  float metalness = m.metalness.value[0] * 1.0f;
+  float metalness = evaluate_metalness(sc, m, d.tex);
   if (smp.next() < metalness) {
     principled_as_conductor(sc, m);
     return conductor_sample<SP>(sc, d, m, smp);
@@ -1111,7 +1111,7 @@ DEVN BSample<SP> principled_sample(const DeviceScene& sc, const BData& d, const 
 template <bool SP>
 DEVN BEval<SP> principled_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& in_m, Smp& smp) {
   etxb_material m = in_m;
-  float metalness = m.metalness.value[0] * 1.0f;
+  float metalness = evaluate_metalness(sc, m, d.tex);
   if (smp.next() < metalness) {
     principled_as_conductor(sc, m);
     return conductor_evaluate<SP>(sc, d, w_o, m, smp);
@@ -1123,10 +1123,10 @@ DEVN BEval<SP> principled_evaluate(const DeviceScene& sc, const BData& d, V3 w_o
 template <bool SP>
 DEVN float principled_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& in_m, Smp& smp) {
   etxb_material m = in_m;
-  float metalness = m.metalness.value[0] * 1.0f;
+  float metalness = evaluate_metalness(sc, m, d.tex);
   if (smp.next() < metalness) {
     principled_as_conductor(sc, m);
-    return conductor_pdf(d, w_o, m);
+    return conductor_pdf(sc, d, w_o, m);
   }
   principled_as_dielectric(sc, m);
   if (smp.next() < m.transmission.value[0]) return dielectric_pdf<SP>(sc, d, w_o, m, smp);
@@ -1185,7 +1185,7 @@ DEV float bsdf_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_mat
     case ETXB_MAT_DIFFUSE: return diffuse_pdf(d, w_o);
     case ETXB_MAT_TRANSLUCENT: return translucent_pdf<SP>(sc, d, w_o, m);
     case ETXB_MAT_PLASTIC: return plastic_pdf<SP>(sc, d, w_o, m, smp);
-    case ETXB_MAT_CONDUCTOR: return conductor_pdf(d, w_o, m);
+    case ETXB_MAT_CONDUCTOR: return conductor_pdf(sc, d, w_o, m);
     case ETXB_MAT_DIELECTRIC: return dielectric_pdf<SP>(sc, d, w_o, m, smp);
     case ETXB_MAT_MIRROR: return mirror_pdf(d, w_o);
     case ETXB_MAT_VELVET: return velvet_pdf(d);

@@ -13,6 +13,7 @@
 #include "../../include/etx_b200.h"
 #include "bvh.h"
 #include "dcore.cuh"
+#include "dimage.cuh"
 
 namespace etxb {
 
@@ -47,6 +48,8 @@ struct DeviceScene {
   const uint8_t* bn_sobol;          // 256 x 256
   const uint8_t* bn_scrambling;     // 128*128*8
   const uint8_t* bn_ranking;        // 128*128*8
+  const DImage* images;
+  uint32_t image_count;
   uint32_t emitter_count;
   uint32_t triangle_count;
   float emitter_total_weight;
@@ -154,7 +157,7 @@ DEV V3 shading_pos(const DeviceScene& sc, const TriRec& tri, V3 bc, V3 w_o) {
   return offset_ray(convex ? sh_pos : geo_pos, tri.geo_n * direction);
 }
 
-// scene.hxx:202-226 make_intersection (normal maps: images are not uploaded yet -> materials with a normal map are rejected at upload)
+// scene.hxx:202-226 make_intersection (incl. normal mapping)
 DEV Isect make_intersection(const DeviceScene& sc, V3 w_i, uint32_t triangle_index, float u, float v, float t) {
   Isect r;
   V3 bc = barycentrics_uv(u, v);
@@ -166,6 +169,23 @@ DEV Isect make_intersection(const DeviceScene& sc, V3 w_i, uint32_t triangle_ind
   r.t = t;
   r.material_index = tri.material_index;
   r.emitter_index = __ldg(&sc.tri_emitter[triangle_index]);
+  const etxb_material& mat = sc.materials[r.material_index];
+  if ((mat.normal_image_index != kInvalidIndex) && (mat.normal_scale > kEpsilon)) {
+    // Image::evaluate_normal (image.hxx:109-116) + orient_normals_to_hemisphere (scene.hxx:188-200)
+    F4v value = image_evaluate(sc.images[mat.normal_image_index], r.tex, nullptr);
+    float scale = mat.normal_scale;
+    V3 sn = {scale * (value.x * 2.0f - 1.0f), scale * (value.y * 2.0f - 1.0f), scale * (value.z * 2.0f - 1.0f) + (1.0f - scale)};
+    V3 n_s = normalize(r.tan * sn.x + r.btn * sn.y + r.nrm * sn.z);
+    const float i_dot_g = dot(w_i, tri.geo_n);
+    float i_dot_s = dot(w_i, n_s);
+    for (uint32_t k = 0; ((i_dot_s * i_dot_g) <= kEpsilon) && (k < 16u); ++k) {
+      n_s = normalize(8.0f * n_s + tri.geo_n);
+      i_dot_s = dot(w_i, n_s);
+    }
+    r.nrm = n_s;
+    r.tan = normalize(r.tan - dot(r.tan, r.nrm) * r.nrm);
+    r.btn = normalize(cross(r.nrm, r.tan));
+  }
   return r;
 }
 
@@ -208,10 +228,36 @@ DEV V3 spec_to_rgb(const DeviceScene& sc, Spec<SP> s, float wavelength) {
   }
 }
 
-// scene.hxx:291-305 apply_image without a texture (image support arrives with the env-map config)
+// rgb_response (render/host/spectrum.cxx:399-): RGB -> reflectance at one wavelength through the 391-entry response table
+DEV float rgb_response(const DeviceScene& sc, float wavelength, V3 rgb) {
+  if (luminance(rgb) == 0.0f) return 0.0f;
+  if ((wavelength < 390.0f) || (wavelength > 780.0f)) return 0.0f;
+  uint32_t wi = uint32_t(wavelength - 390.0f);
+  uint32_t wj = umin(wi + 1u, 390u);
+  float dw = wavelength - floorf(wavelength);
+  const float* t = sc.rgb_response_table;
+  V3 w = lerp3({__ldg(&t[wi * 3 + 0]), __ldg(&t[wi * 3 + 1]), __ldg(&t[wi * 3 + 2])}, {__ldg(&t[wj * 3 + 0]), __ldg(&t[wj * 3 + 1]), __ldg(&t[wj * 3 + 2])}, dw);
+  return rgb.x * w.x + rgb.y * w.y + rgb.z * w.z;
+}
+// apply_rgb (scene.hxx:251-263)
 template <bool SP>
-DEV Spec<SP> apply_image(const DeviceScene& sc, const etxb_spectral_image& img, float wavelength) {
-  return spectrum_query<SP>(sc, img.spectrum_index, wavelength);
+DEV Spec<SP> apply_rgb(const DeviceScene& sc, float wavelength, Spec<SP> response, F4v value) {
+  if constexpr (SP) {
+    float scale = rgb_response(sc, wavelength, {value.x, value.y, value.z});
+    response *= scale;
+    return response;
+  } else {
+    return {response.x * value.x, response.y * value.y, response.z * value.z};
+  }
+}
+// apply_image (scene.hxx:291-305)
+template <bool SP>
+DEV Spec<SP> apply_image(const DeviceScene& sc, const etxb_spectral_image& img, V2 uv, float wavelength, float* image_pdf = nullptr) {
+  if (image_pdf) *image_pdf = 0.0f;
+  Spec<SP> result = spectrum_query<SP>(sc, img.spectrum_index, wavelength);
+  if (img.image_index == kInvalidIndex) return result;
+  F4v eval = image_evaluate(sc.images[img.image_index], uv, image_pdf);
+  return apply_rgb<SP>(sc, wavelength, result, eval);
 }
 
 // RefractiveIndex::Sample (spectrum.hxx:557-586) via evaluate_refractive_index (scene.hxx:307-313)
@@ -229,8 +275,17 @@ DEV IorSample<SP> evaluate_ior(const DeviceScene& sc, const etxb_refractive_inde
   return r;
 }
 
-// scene.hxx:273-275 evaluate_roughness (no roughness texture yet)
-DEV V2 evaluate_roughness(const etxb_material& m) { return {m.roughness.value[0] * 1.0f, m.roughness.value[1] * 1.0f}; }
+// evaluate_image / evaluate_roughness / evaluate_metalness (scene.hxx:265-289)
+DEV float evaluate_image_channel(const DeviceScene& sc, const etxb_sampled_image& img, V2 uv, float default_value) {
+  if ((img.image_index == kInvalidIndex) || (img.channel >= 4u)) return default_value;
+  F4v e = image_evaluate(sc.images[img.image_index], uv, nullptr);
+  return img.channel == 0u ? e.x : (img.channel == 1u ? e.y : (img.channel == 2u ? e.z : e.w));
+}
+DEV V2 evaluate_roughness(const DeviceScene& sc, const etxb_material& m, V2 uv) {
+  float s = evaluate_image_channel(sc, m.roughness, uv, 1.0f);
+  return {m.roughness.value[0] * s, m.roughness.value[1] * s};
+}
+DEV float evaluate_metalness(const DeviceScene& sc, const etxb_material& m, V2 uv) { return m.metalness.value[0] * evaluate_image_channel(sc, m.metalness, uv, 1.0f); }
 
 // scene.hxx:228-249 random_continue
 template <bool SP>

@@ -32,9 +32,17 @@ struct DevTriLoad {
   }
 };
 
-// alpha_test_pass (scene_bsdf.hxx:128-144); alpha textures are not uploaded yet
-DEV bool alpha_test_rejects(const etxb_material& mat, Smp& smp) {
-  float alpha_test_value = 1.0f * mat.opacity;
+// alpha_test_pass (scene_bsdf.hxx:128-144)
+DEV bool alpha_test_rejects(const DeviceScene& sc, const etxb_material& mat, uint32_t triangle_index, float u, float v, Smp& smp) {
+  float alpha_diffuse = 1.0f;
+  if (mat.scattering.image_index != kInvalidIndex) {
+    const DImage& img = sc.images[mat.scattering.image_index];
+    if (img.options & kImageHasAlpha) {
+      V2 uv = lerp_uv(sc, load_triangle(sc, triangle_index), barycentrics_uv(u, v));
+      alpha_diffuse = image_evaluate_alpha(img, uv);
+    }
+  }
+  float alpha_test_value = alpha_diffuse * mat.opacity;
   return alpha_test_value <= smp.next();
 }
 
@@ -50,7 +58,7 @@ struct ClosestVisitor {
   DEV int operator()(uint32_t triangle_index, float u, float v, float t) {
     const etxb_material& mat = sc.materials[load_triangle_material(sc, triangle_index)];
     if (mat.cls == ETXB_MAT_VOID) return kCandIgnore;
-    if (alpha_test_rejects(mat, smp)) return kCandIgnore;
+    if (alpha_test_rejects(sc, mat, triangle_index, u, v, smp)) return kCandIgnore;
     best = {u, v, t, triangle_index};
     return kCandAccept;
   }
@@ -71,7 +79,7 @@ struct ShadowVisitor {
   DEV int operator()(uint32_t triangle_index, float u, float v, float t) {
     const etxb_material& mat = sc.materials[load_triangle_material(sc, triangle_index)];
     if (mat.cls == ETXB_MAT_VOID) return kCandIgnore;
-    if (alpha_test_rejects(mat, smp)) return kCandIgnore;
+    if (alpha_test_rejects(sc, mat, triangle_index, u, v, smp)) return kCandIgnore;
     // Boundary materials (participating media interfaces) are not on the device yet: upload rejects them,
     // so any surviving candidate occludes (rt.cxx:505-509)
     occluded = true;

@@ -77,14 +77,82 @@ struct EmitterSample {
   bool is_delta, is_distant;
 };
 
-// emitter_get_radiance, Area case (scene_emitters.hxx:81-104)
+// math.hxx:809-823, 952-999, 1023-1034
+DEV float distance_to_sphere(V3 r_origin, V3 r_direction, V3 center, float radius) {
+  V3 e = r_origin - center;
+  float b = dot(r_direction, e);
+  float d = (b * b) - dot(e, e) + (radius * radius);
+  if (d < 0.0f) return 0.0f;
+  d = sqrtf(d);
+  float a0 = -b - d;
+  float a1 = -b + d;
+  return (a0 < 0.0f) ? ((a1 < 0.0f) ? 0.0f : a1) : a0;
+}
+DEV V2 disk_uv(V3 normal, V3 in_dir, float sz, float csz) {
+  V2 pc = {0.0f, 0.0f};
+  if (sz != 0.0f) {
+    Basis basis = orthonormal_basis(normal);
+    pc.x = dot(basis.u, in_dir) / (0.5f * sz * csz);
+    pc.y = dot(basis.v, in_dir) / (0.5f * sz * csz);
+  }
+  return {saturatef(pc.x * 0.5f + 0.5f), saturatef(pc.y * 0.5f + 0.5f)};
+}
+DEV V3 from_spherical(float phi, float theta) {
+  float cos_p = m_cos(phi), sin_p = m_sin(phi), cos_t = m_cos(theta), sin_t = m_sin(theta);
+  return {1.0f * cos_p * cos_t, 1.0f * sin_t, 1.0f * sin_p * cos_t};
+}
+DEV V3 uv_to_direction(V2 uv, float offset_x, float u_scale) {
+  float u = uv.x;
+  if (u_scale < 0.0f) u = 1.0f - u;
+  u = u - offset_x;
+  u = u - floorf(u);
+  float phi = (u * 2.0f - 1.0f) * kPi;
+  float theta = (0.5f - uv.y) * kPi;
+  return from_spherical(phi, theta);
+}
+DEV V2 direction_to_uv(V3 dir, float offset_x, float u_scale) {
+  float r = length(dir);
+  float phi = m_atan2(dir.z, dir.x);
+  float theta = m_asin(dir.y / r);
+  float u = (phi / kPi + 1.0f) / 2.0f;
+  if (u_scale < 0.0f) u = 1.0f - u;
+  u = u + offset_x;
+  u = u - floorf(u);
+  float v = 0.5f - theta / kPi;
+  return {u, v};
+}
+
+enum : uint32_t { kEmitterArea = 0u, kEmitterEnvironment = 1u, kEmitterDirectional = 2u };  // EmitterProfile::Class (emitter.hxx:8-13)
+
+// emitter_get_radiance (scene_emitters.hxx:40-112)
 template <bool SP>
-DEV Spec<SP> emitter_get_radiance_area(const DeviceScene& sc, const etxb_emitter& em_inst, float wavelength, V3 source_position, V3 target_position, bool directly_visible,
-  float& pdf_area, float& pdf_dir, float& pdf_dir_out) {
+DEV Spec<SP> emitter_get_radiance(const DeviceScene& sc, const etxb_emitter& em_inst, float wavelength, V3 source_position, V3 target_position, V3 direction, V2 uv,
+  bool directly_visible, float& pdf_area, float& pdf_dir, float& pdf_dir_out) {
   pdf_dir = 0.0f;
   pdf_area = 0.0f;
   pdf_dir_out = 0.0f;
   const etxb_emitter_profile& em = sc.emitter_profiles[em_inst.profile];
+  if (em_inst.cls == kEmitterDirectional) {
+    V3 em_dir = {em.direction[0], em.direction[1], em.direction[2]};
+    if ((directly_visible == false) || (em.angular_size <= 0.0f) || (dot(direction, em_dir) < em.angular_size_cosine)) return Spec<SP>::make(0.0f);
+    pdf_dir = 1.0f;
+    pdf_area = 1.0f / (kPi * sc.bounding_sphere_radius * sc.bounding_sphere_radius);
+    pdf_dir_out = pdf_dir * pdf_area;
+    V2 duv = disk_uv(em_dir, direction, em.equivalent_disk_size, em.angular_size_cosine);
+    Spec<SP> direct_scale = 1.0f / (spectrum_query<SP>(sc, em.emission.spectrum_index, wavelength) * kDoublePi * (1.0f - em.angular_size_cosine));
+    return apply_image<SP>(sc, em.emission, duv, wavelength) * direct_scale;
+  }
+  if (em_inst.cls == kEmitterEnvironment) {
+    const DImage& img = sc.images[em.emission.image_index];
+    V2 euv = direction_to_uv(direction, img.offset_x, img.scale_x);
+    float sin_t = fmaxf(kEpsilon, m_sin(euv.y * kPi));
+    float image_pdf = 0.0f;
+    Spec<SP> eval = apply_image<SP>(sc, em.emission, euv, wavelength, &image_pdf);
+    pdf_area = 1.0f / (kPi * sc.bounding_sphere_radius * sc.bounding_sphere_radius);
+    pdf_dir = image_pdf / (2.0f * kPi * kPi * sin_t);
+    pdf_dir_out = pdf_area * pdf_dir;
+    return eval;
+  }
   TriRec tri = load_triangle(sc, em_inst.triangle_index);
   const etxb_material& material = sc.materials[tri.material_index];
   if (dot(tri.geo_n, target_position - source_position) >= 0.0f) return Spec<SP>::make(0.0f);
@@ -100,60 +168,171 @@ DEV Spec<SP> emitter_get_radiance_area(const DeviceScene& sc, const etxb_emitter
       pdf_dir_out = pdf_area * cos_tx * kInvPi;
     }
   }
-  return apply_image<SP>(sc, em.emission, wavelength);
+  return apply_image<SP>(sc, em.emission, uv, wavelength);
 }
 
-// sample_emission (scene_emitters.hxx:226-305), Area emitters
+// sample_emission (scene_emitters.hxx:226-305)
 template <bool SP>
 DEV EmitterSample<SP> sample_emission(const DeviceScene& sc, float wavelength, Smp& smp) {
   EmitterSample<SP> r;
   r.value = Spec<SP>::make(0.0f);
   r.pdf_area = r.pdf_dir = r.pdf_dir_out = 0.0f;
+  r.barycentric = {0.0f, 0.0f, 0.0f};
   r.emitter_index = distribution_sample(sc.emitter_dist, sc.emitter_count + 1u, smp.next());
   r.pdf_sample = __ldg(&sc.emitter_dist[r.emitter_index].pdf);
   const etxb_emitter& em_inst = sc.emitters[r.emitter_index];
   const etxb_emitter_profile& em = sc.emitter_profiles[em_inst.profile];
-  TriRec tri = load_triangle(sc, em_inst.triangle_index);
-  const etxb_material& material = sc.materials[tri.material_index];
-  r.triangle_index = em_inst.triangle_index;
-  r.barycentric = random_barycentric(smp.next_2d());
-  V3 pos, nrm, tan, btn;
-  V2 tex;
-  lerp_vertex(sc, tri, r.barycentric, pos, nrm, tan, btn, tex);
-  r.origin = pos;
-  r.normal = nrm;
-  r.direction = sample_cosine_frame(smp.next_2d(), nrm, tan, btn, collimation_to_exponent(material.emission_collimation));
-  // emitter_evaluate_out_local (:22-38)
-  r.pdf_dir = tmax(0.0f, dot(r.normal, r.direction)) * kInvPi;
-  if (r.pdf_dir > 0.0f) {
-    r.pdf_area = 1.0f / em_inst.triangle_area;
+  r.medium_index = kInvalidIndex;
+  if (em_inst.cls == kEmitterArea) {
+    TriRec tri = load_triangle(sc, em_inst.triangle_index);
+    const etxb_material& material = sc.materials[tri.material_index];
+    r.barycentric = random_barycentric(smp.next_2d());
+    V3 pos, nrm, tan, btn;
+    V2 tex;
+    lerp_vertex(sc, tri, r.barycentric, pos, nrm, tan, btn, tex);
+    r.origin = pos;
+    r.normal = nrm;
+    r.direction = sample_cosine_frame(smp.next_2d(), nrm, tan, btn, collimation_to_exponent(material.emission_collimation));
+    // emitter_evaluate_out_local (:22-38)
+    r.pdf_dir = tmax(0.0f, dot(r.normal, r.direction)) * kInvPi;
+    if (r.pdf_dir > 0.0f) {
+      r.pdf_area = 1.0f / em_inst.triangle_area;
+      r.pdf_dir_out = r.pdf_dir * r.pdf_area;
+      r.value = apply_image<SP>(sc, em.emission, tex, wavelength);
+    }
+    r.medium_index = material.ext_medium;
+  } else if (em_inst.cls == kEmitterDirectional) {
+    V3 direction_to_scene = V3{em.direction[0], em.direction[1], em.direction[2]} * (-1.0f);
+    Basis basis = orthonormal_basis(direction_to_scene);
+    V2 pos_sample = sample_disk(smp.next_2d());
+    V2 dir_sample = sample_disk(smp.next_2d());
+    r.direction = normalize(direction_to_scene + basis.u * dir_sample.x * (0.5f * em.equivalent_disk_size) + basis.v * dir_sample.y * (0.5f * em.equivalent_disk_size));
+    r.pdf_dir = 1.0f;
+    r.pdf_area = 1.0f / (kPi * sc.bounding_sphere_radius * sc.bounding_sphere_radius);
     r.pdf_dir_out = r.pdf_dir * r.pdf_area;
-    r.value = apply_image<SP>(sc, em.emission, wavelength);
+    r.normal = direction_to_scene;
+    r.origin = sc.bounding_sphere_center + sc.bounding_sphere_radius * (pos_sample.x * basis.u + pos_sample.y * basis.v - direction_to_scene);
+    r.origin += r.direction * distance_to_sphere(r.origin, r.direction, sc.bounding_sphere_center, sc.bounding_sphere_radius);
+    r.value = apply_image<SP>(sc, em.emission, dir_sample * 0.5f + 0.5f, wavelength);
+  } else {
+    const DImage& img = sc.images[em.emission.image_index];
+    float pdf_image = 0.0f;
+    F4v image_value;
+    V2 uv = image_sample(img, smp.next_2d(), pdf_image, image_value);
+    if (pdf_image == 0.0f) {
+      r.pdf_dir = 0.0f;
+      r.triangle_index = kInvalidIndex;
+      r.is_delta = false;
+      r.is_distant = true;
+      r.origin = r.normal = r.direction = {0.0f, 0.0f, 0.0f};
+      return r;
+    }
+    float sin_t = fmaxf(kEpsilon, m_sin(uv.y * kPi));
+    V3 d = -uv_to_direction(uv, img.offset_x, img.scale_x);
+    Basis basis = orthonormal_basis(d);
+    V2 disk_sample = sample_disk(smp.next_2d());
+    r.direction = d;
+    r.normal = r.direction;
+    r.origin = sc.bounding_sphere_center + sc.bounding_sphere_radius * (disk_sample.x * basis.u + disk_sample.y * basis.v - r.direction);
+    r.origin += r.direction * distance_to_sphere(r.origin, r.direction, sc.bounding_sphere_center, sc.bounding_sphere_radius);
+    r.value = apply_rgb<SP>(sc, wavelength, spectrum_query<SP>(sc, em.emission.spectrum_index, wavelength), image_value);
+    r.pdf_area = 1.0f / (kPi * sc.bounding_sphere_radius * sc.bounding_sphere_radius);
+    r.pdf_dir = pdf_image / (2.0f * kPi * kPi * sin_t);
+    r.pdf_dir_out = r.pdf_area * r.pdf_dir;
   }
-  r.medium_index = material.ext_medium;
-  r.is_delta = false;
-  r.is_distant = false;
+  r.triangle_index = em_inst.triangle_index;
+  r.is_delta = em_inst.cls == kEmitterDirectional;
+  r.is_distant = em_inst.cls != kEmitterArea;
   return r;
 }
 
-// sample_emitter (scene_emitters.hxx:216-224) -> emitter_sample_in, Area case (:139-158)
+// sample_emitter (scene_emitters.hxx:216-224) -> emitter_sample_in (:139-203)
 template <bool SP>
 DEV EmitterSample<SP> sample_emitter(const DeviceScene& sc, float wavelength, uint32_t emitter_index, V2 rnd, V3 from_point) {
   EmitterSample<SP> r;
+  r.barycentric = {0.0f, 0.0f, 0.0f};
+  r.medium_index = kInvalidIndex;
   const etxb_emitter& em_inst = sc.emitters[emitter_index];
-  TriRec tri = load_triangle(sc, em_inst.triangle_index);
-  r.barycentric = random_barycentric(rnd);
-  r.origin = lerp_pos(sc, tri, r.barycentric);
-  r.normal = lerp_normal(sc, tri, r.barycentric);
-  r.direction = normalize(r.origin - from_point);
-  r.value = emitter_get_radiance_area<SP>(sc, em_inst, wavelength, from_point, r.origin, false, r.pdf_area, r.pdf_dir, r.pdf_dir_out);
-  r.medium_index = sc.materials[tri.material_index].ext_medium;
+  const etxb_emitter_profile& em = sc.emitter_profiles[em_inst.profile];
+  if (em_inst.cls == kEmitterArea) {
+    TriRec tri = load_triangle(sc, em_inst.triangle_index);
+    r.barycentric = random_barycentric(rnd);
+    r.origin = lerp_pos(sc, tri, r.barycentric);
+    r.normal = lerp_normal(sc, tri, r.barycentric);
+    r.direction = normalize(r.origin - from_point);
+    r.value = emitter_get_radiance<SP>(sc, em_inst, wavelength, from_point, r.origin, {0.0f, 0.0f, 0.0f}, lerp_uv(sc, tri, r.barycentric), false, r.pdf_area, r.pdf_dir,
+      r.pdf_dir_out);
+    r.medium_index = sc.materials[tri.material_index].ext_medium;
+  } else if (em_inst.cls == kEmitterDirectional) {
+    V3 em_dir = {em.direction[0], em.direction[1], em.direction[2]};
+    V2 disk_sample = {0.0f, 0.0f};
+    if (em.angular_size > 0.0f) {
+      Basis basis = orthonormal_basis(em_dir);
+      disk_sample = sample_disk(rnd);
+      r.direction = normalize(em_dir + basis.u * disk_sample.x * (0.5f * em.equivalent_disk_size) + basis.v * disk_sample.y * (0.5f * em.equivalent_disk_size));
+    } else {
+      r.direction = em_dir;
+    }
+    r.pdf_area = 1.0f / (kPi * sc.bounding_sphere_radius * sc.bounding_sphere_radius);
+    r.pdf_dir = 1.0f;
+    r.pdf_dir_out = r.pdf_dir * r.pdf_area;
+    r.origin = from_point + r.direction * distance_to_sphere(from_point, r.direction, sc.bounding_sphere_center, sc.bounding_sphere_radius);
+    r.normal = em_dir * (-1.0f);
+    r.value = apply_image<SP>(sc, em.emission, disk_sample * 0.5f + 0.5f, wavelength);
+  } else {
+    const DImage& img = sc.images[em.emission.image_index];
+    float pdf_image = 0.0f;
+    F4v image_value;
+    V2 uv = image_sample(img, rnd, pdf_image, image_value);
+    float sin_t = fmaxf(kEpsilon, m_sin(uv.y * kPi));
+    r.direction = uv_to_direction(uv, img.offset_x, img.scale_x);
+    r.normal = -r.direction;
+    r.origin = from_point + r.direction * distance_to_sphere(from_point, r.direction, sc.bounding_sphere_center, sc.bounding_sphere_radius);
+    r.pdf_dir = pdf_image / (2.0f * kPi * kPi * sin_t);
+    r.pdf_area = 1.0f / (kPi * sc.bounding_sphere_radius * sc.bounding_sphere_radius);
+    r.pdf_dir_out = r.pdf_area * r.pdf_dir;
+    r.value = apply_rgb<SP>(sc, wavelength, spectrum_query<SP>(sc, em.emission.spectrum_index, wavelength), image_value);
+  }
   r.pdf_sample = emitter_discrete_pdf(sc, em_inst);
   r.emitter_index = emitter_index;
   r.triangle_index = em_inst.triangle_index;
-  r.is_delta = false;
-  r.is_distant = false;
+  r.is_delta = em_inst.cls == kEmitterDirectional;
+  r.is_distant = em_inst.cls != kEmitterArea;
   return r;
+}
+
+// vcm_cam_handle_miss (vcm_shared.hxx:537-587)
+template <bool SP>
+DEV void vcm_cam_handle_miss(const DeviceScene& sc, const VcmParams& it, V3 ray_d, float& d_vcm, float d_vc, float& path_distance, uint32_t total_path_depth, float wavelength,
+  Spec<SP> throughput, Spec<SP>& gathered) {
+  if (it.direct_hit() == false) return;
+  if (path_distance > 0.0f) {
+    d_vcm *= sqr(path_distance);
+    path_distance = 0.0f;
+  }
+  Spec<SP> accumulated_value = Spec<SP>::make(0.0f);
+  float sum_pdf_dir_out = 0.0f, sum_pdf_dir = 0.0f;
+  for (uint32_t ie = 0; ie < sc.env_emitter_count; ++ie) {
+    const etxb_emitter& emitter_instance = sc.emitters[sc.env_emitters[ie]];
+    float pdf_area = 0.0f, pdf_dir = 0.0f, pdf_dir_out = 0.0f;
+    Spec<SP> value = emitter_get_radiance<SP>(sc, emitter_instance, wavelength, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}, ray_d, {0.0f, 0.0f}, total_path_depth <= 1, pdf_area, pdf_dir,
+      pdf_dir_out);
+    if (pdf_dir > kEpsilon) {
+      float pdf_discrete = emitter_discrete_pdf(sc, emitter_instance);
+      sum_pdf_dir_out += pdf_dir_out * pdf_discrete;
+      sum_pdf_dir += pdf_dir * pdf_discrete;
+      accumulated_value += value;
+    }
+  }
+  if (accumulated_value.maximum() > kEpsilon) {
+    float inv_count = (sc.env_emitter_count > 0u) ? (1.0f / float(sc.env_emitter_count)) : 0.0f;
+    sum_pdf_dir *= inv_count;
+    sum_pdf_dir_out *= inv_count;
+    float w_camera_sum = d_vcm * sum_pdf_dir + d_vc * sum_pdf_dir_out;
+    float weight = it.enable_mis() && (total_path_depth > 1) ? (1.0f / (1.0f + w_camera_sum)) : 1.0f;
+    Spec<SP> add = throughput * accumulated_value * weight;
+    gathered += add;
+  }
 }
 
 // ---- camera (scene_camera.hxx) ---------------------------------------------------------------------------------
@@ -391,8 +570,8 @@ DEV void vcm_handle_direct_hit(const DeviceScene& sc, const VcmParams& it, const
   if ((state.total_path_depth > sc.max_path_length) || (state.total_path_depth < sc.min_path_length)) return;
   const etxb_emitter& emitter = sc.emitters[isect.emitter_index];
   float pdf_emitter_area, pdf_emitter_dir, pdf_emitter_dir_out;
-  Spec<SP> radiance = emitter_get_radiance_area<SP>(sc, emitter, state.wavelength, state.ray_o, isect.pos, state.total_path_depth == 1, pdf_emitter_area, pdf_emitter_dir,
-    pdf_emitter_dir_out);
+  Spec<SP> radiance = emitter_get_radiance<SP>(sc, emitter, state.wavelength, state.ray_o, isect.pos, state.ray_d, isect.tex, state.total_path_depth == 1, pdf_emitter_area,
+    pdf_emitter_dir, pdf_emitter_dir_out);
   if (pdf_emitter_dir <= kEpsilon) return;
   float emitter_sample_pdf = emitter_discrete_pdf(sc, emitter);
   float w_camera = state.d_vcm * pdf_emitter_area * emitter_sample_pdf + state.d_vc * (pdf_emitter_dir_out * emitter_sample_pdf);

@@ -423,12 +423,7 @@ __global__ void __launch_bounds__(128) k_camera_shade(LaunchParams p, const uint
     float4 hit = p.paths.hit[i];
     uint32_t tri_index = __float_as_uint(hit.w);
     if (tri_index == kInvalidIndex) {
-      // vcm_cam_handle_miss (:537-587): environment emitters are not on the device yet (upload rejects them);
-      // only the pending boundary distance is folded
-      if (p.vcm.direct_hit() && (state.path_distance > 0.0f)) {
-        state.d_vcm *= sqr(state.path_distance);
-        state.path_distance = 0.0f;
-      }
+      vcm_cam_handle_miss<SP>(sc, p.vcm, state.ray_d, state.d_vcm, state.d_vc, state.path_distance, state.total_path_depth, state.wavelength, state.throughput, state.gathered);
     } else {
       Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
       const etxb_material& mat = sc.materials[isect.material_index];
@@ -553,7 +548,7 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
       qnrm = isect.nrm;
       bool entering = dot(isect.nrm, isect.w_i) < 0.0f;
       qfn = entering ? isect.nrm : -isect.nrm;  // frame normal of the camera vertex
-      Spec<SP> diffuse = apply_image<SP>(sc, mat.scattering, state.wavelength);
+      Spec<SP> diffuse = apply_image<SP>(sc, mat.scattering, isect.tex, state.wavelength);
       Spec<SP> t_camera = state.throughput / sampling_pdf<SP>(state.wavelength);
       qc = spec_to_rgb<SP>(sc, (diffuse / kPi) * t_camera, state.wavelength);  // camera_bsdf.func * t_camera: direction independent
       q_wcam_base = state.d_vcm * p.vcm.vc_weight;

@@ -91,6 +91,8 @@ struct etxb_ctx {
   DevBuf<etxb_emitter_profile> profiles;
   DevBuf<etxb_emitter> emitters;
   DevBuf<DSpectrum> spectra;
+  DevBuf<DImage> images;
+  std::vector<DevBuf<uint8_t>> image_pixels, image_dists;
   DevBuf<etxb_distribution_entry> emitter_dist;
   DevBuf<BvhNode> bvh_nodes;
   DevBuf<float4> bvh_tris;
@@ -519,6 +521,9 @@ void etxb_destroy(etxb_ctx* ctx) {
   ctx->profiles.release();
   ctx->emitters.release();
   ctx->spectra.release();
+  ctx->images.release();
+  for (auto& b : ctx->image_pixels) b.release();
+  for (auto& b : ctx->image_dists) b.release();
   ctx->emitter_dist.release();
   ctx->bvh_nodes.release();
   ctx->xyz_table.release();
@@ -594,7 +599,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
     if (m.subsurface.cls != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: subsurface scattering is not supported on the device yet", (unsigned long long)i);
     uint32_t imgs[] = {m.reflectance.image_index, m.scattering.image_index, m.emission.image_index, m.roughness.image_index, m.normal_image_index, m.thinfilm.thickness_image};
     for (uint32_t im : imgs)
-      if (im != ETXB_INVALID_INDEX) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: textures are not supported on the device yet", (unsigned long long)i);
+      if ((im != ETXB_INVALID_INDEX) && (im >= s.images.count)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu: image index %u out of range", (unsigned long long)i, im);
     if (m.int_medium != ETXB_INVALID_INDEX || m.ext_medium != ETXB_INVALID_INDEX)
       return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: media are not supported on the device yet", (unsigned long long)i);
   }
@@ -609,7 +614,61 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   }
   const auto* emitters = static_cast<const etxb_emitter*>(s.emitter_instances.a);
   for (uint64_t i = 0; i < s.emitter_instances.count; ++i) {
-    if (emitters[i].cls != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "emitter %llu: only area emitters are supported on the device yet", (unsigned long long)i);
+    if (emitters[i].cls > 2u) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "emitter %llu: unknown class %u", (unsigned long long)i, emitters[i].cls);
+    if (emitters[i].cls == 1u) {
+      const auto& prof = static_cast<const etxb_emitter_profile*>(s.emitter_profiles.a)[emitters[i].profile];
+      if (prof.emission.image_index >= s.images.count) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "environment emitter %llu has no image", (unsigned long long)i);
+      const auto& img = static_cast<const etxb_image*>(s.images.a)[prof.emission.image_index];
+      if (img.y_distribution.values.count != uint64_t(img.isize[1]) + 1u) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "environment emitter %llu: image has no sampling table", (unsigned long long)i);
+    }
+  }
+  // ---- images: pixels + flattened row/column CDFs (image.hxx:8-50) ---------------------------------------------------------------
+  {
+    const auto* imgs = static_cast<const etxb_image*>(s.images.a);
+    std::vector<DImage> dimgs(s.images.count);
+    for (auto& b : ctx->image_pixels) b.release();
+    for (auto& b : ctx->image_dists) b.release();
+    ctx->image_pixels.assign(s.images.count, {});
+    ctx->image_dists.assign(s.images.count * 2, {});
+    for (uint64_t i = 0; i < s.images.count; ++i) {
+      const etxb_image& im = imgs[i];
+      DImage& d = dimgs[i];
+      d = {};
+      if ((im.format != 1u) && (im.format != 2u)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "image %llu: unknown pixel format %u", (unsigned long long)i, im.format);
+      size_t px = size_t(im.isize[0]) * im.isize[1];
+      if (px == 0) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "image %llu is empty", (unsigned long long)i);
+      size_t bytes = px * (im.format == 1u ? 16 : 4);
+      CUDA_OK(ctx, ctx->image_pixels[i].alloc(bytes));
+      CUDA_OK(ctx, cudaMemcpyAsync(ctx->image_pixels[i].ptr, im.pixels.a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+      d.pixels_f32 = (im.format == 1u) ? reinterpret_cast<const float4*>(ctx->image_pixels[i].ptr) : nullptr;
+      d.pixels_u8 = (im.format == 2u) ? reinterpret_cast<const uchar4*>(ctx->image_pixels[i].ptr) : nullptr;
+      d.fsize_x = im.fsize[0]; d.fsize_y = im.fsize[1];
+      d.offset_x = im.offset[0]; d.offset_y = im.offset[1];
+      d.scale_x = im.scale[0]; d.scale_y = im.scale[1];
+      d.isize_x = im.isize[0]; d.isize_y = im.isize[1];
+      d.normalization = im.normalization;
+      d.options = im.options;
+      d.format = im.format;
+      if (im.y_distribution.values.count == uint64_t(im.isize[1]) + 1u) {
+        size_t nx = size_t(im.isize[0]) + 1u, ny = size_t(im.isize[1]) + 1u;
+        std::vector<etxb_distribution_entry> flat(nx * im.isize[1]);
+        const auto* rows = static_cast<const etxb_distribution*>(im.x_distributions.a);
+        for (uint32_t y = 0; y < im.isize[1]; ++y) {
+          if (rows[y].values.count != nx) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "image %llu: row %u distribution has %llu entries", (unsigned long long)i, y, (unsigned long long)rows[y].values.count);
+          memcpy(flat.data() + size_t(y) * nx, rows[y].values.a, nx * sizeof(etxb_distribution_entry));
+        }
+        CUDA_OK(ctx, ctx->image_dists[i * 2].alloc(flat.size() * sizeof(etxb_distribution_entry)));
+        CUDA_OK(ctx, cudaMemcpy(ctx->image_dists[i * 2].ptr, flat.data(), flat.size() * sizeof(etxb_distribution_entry), cudaMemcpyHostToDevice));
+        CUDA_OK(ctx, ctx->image_dists[i * 2 + 1].alloc(ny * sizeof(etxb_distribution_entry)));
+        CUDA_OK(ctx, cudaMemcpy(ctx->image_dists[i * 2 + 1].ptr, im.y_distribution.values.a, ny * sizeof(etxb_distribution_entry), cudaMemcpyHostToDevice));
+        d.x_dist = reinterpret_cast<const etxb_distribution_entry*>(ctx->image_dists[i * 2].ptr);
+        d.y_dist = reinterpret_cast<const etxb_distribution_entry*>(ctx->image_dists[i * 2 + 1].ptr);
+        d.has_distribution = 1;
+      }
+    }
+    if (int rc = upload(ctx, ctx->images, dimgs.data(), dimgs.size())) return rc;
+    ctx->dscene.images = ctx->images.ptr;
+    ctx->dscene.image_count = uint32_t(dimgs.size());
   }
   if (s.emitter_instances.count == 0) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "scene has no emitters");
   const auto* spectra = static_cast<const etxb_spectrum*>(s.spectrums.a);

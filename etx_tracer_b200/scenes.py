@@ -152,6 +152,110 @@ class SceneData:
         self.material_names[name] = len(self.materials) - 1
         return len(self.materials) - 1
 
+    # -- images / distant emitters ------------------------------------------------------------------
+    def add_image(self, pixels, repeat=True, build_table=False, uniform_table=False, offset=(0.0, 0.0), scale=(1.0, 1.0), has_alpha=None):
+        """ImagePool::add_from_data + build_image_sampling_table (render/host/image_pool.cxx:226-259), RGBA32F."""
+        px = np.ascontiguousarray(pixels, dtype=f32)
+        h, w = px.shape[:2]
+        assert px.shape[2] == 4
+        img = np.zeros(1, dtype=S.IMAGE)
+        opts = (6 if repeat else 0) | (1 if build_table else 0) | (32 if uniform_table else 0)
+        if has_alpha is None:
+            has_alpha = bool((px[..., 3] < 1.0).any())
+        if has_alpha:
+            opts |= 16
+        img["pixels"]["a"] = px.ctypes.data
+        img["pixels"]["count"] = w * h
+        img["fsize"][0] = (w, h)
+        img["isize"][0] = (w, h)
+        img["offset"][0] = offset
+        img["scale"][0] = scale
+        img["options"] = opts
+        img["format"] = 1
+        img["data_size"] = px.nbytes
+        keep = [px]
+        if build_table:
+            # Image::read at texel centres = mean of the 2x2 neighbourhood (image.hxx:173-186)
+            xs1 = (np.arange(w) + 1) % w if repeat else np.minimum(np.arange(w) + 1, w - 1)
+            ys1 = (np.arange(h) + 1) % h if repeat else np.minimum(np.arange(h) + 1, h - 1)
+            rgb = px[..., :3]
+            avg = (rgb * f32(0.25) + rgb[:, xs1] * f32(0.25) + rgb[ys1] * f32(0.25) + rgb[ys1][:, xs1] * f32(0.25)).astype(f32)
+            lum = (avg[..., 0] * f32(0.212671) + avg[..., 1] * f32(0.715160) + avg[..., 2] * f32(0.072169)).astype(f32)
+
+            def build(values):
+                n = values.shape[0]
+                e = np.zeros(n + 1, dtype=S.DIST_ENTRY)
+                e["value"][:n] = values
+                c = np.concatenate([[0.0], np.cumsum(values.astype(np.float64))]).astype(f32)
+                total = f32(c[n])
+                if total == 0:
+                    e["value"][:n] = 1.0
+                    e["pdf"][:n] = f32(1.0 / n)
+                    e["cdf"][:n] = (np.arange(n) / n).astype(f32)
+                else:
+                    e["pdf"][:n] = (values / total).astype(f32)
+                    e["cdf"][:n] = (c[:n] / total).astype(f32)
+                e["cdf"][n] = 1.0
+                return e, total
+
+            rows = np.zeros(h, dtype=S.DISTRIBUTION)
+            row_values = np.zeros(h, dtype=f32)
+            for y in range(h):
+                e, total = build(lum[y])
+                keep.append(e)
+                rows["values"]["a"][y] = e.ctypes.data
+                rows["values"]["count"][y] = w + 1
+                rows["total_weight"][y] = total
+                v = (y + 0.5) / h
+                row_values[y] = f32(lum[y].astype(np.float64).sum()) * f32(1.0 if uniform_table else math.sin(v * math.pi))
+            ey, total_y = build(row_values)
+            keep += [rows, ey]
+            img["x_distributions"]["a"] = rows.ctypes.data
+            img["x_distributions"]["count"] = h
+            img["y_distribution"]["values"]["a"] = ey.ctypes.data
+            img["y_distribution"]["values"]["count"] = h + 1
+            img["y_distribution"]["total_weight"] = total_y
+            img["normalization"] = f32(row_values.astype(np.float64).sum()) / f32(w * h)
+        self._keep.append(keep)
+        if not hasattr(self, "_images"):
+            self._images = []
+        self._images.append(img)
+        return len(self._images) - 1
+
+    def add_environment_emitter(self, image_index, rgb=(1.0, 1.0, 1.0)):
+        """et::env with an image (scene_representation.cxx: environment profile + one instance)."""
+        p = np.zeros(1, dtype=S.EMITTER_PROFILE)
+        p["emission"]["spectrum_index"] = self.add_spectrum(spd_rgb_luminance(rgb))
+        p["emission"]["image_index"] = image_index
+        p["cls"] = S.EMITTER_ENVIRONMENT
+        p["angular_size_cosine"] = 1.0
+        e = np.zeros(1, dtype=S.EMITTER)
+        e["cls"] = S.EMITTER_ENVIRONMENT
+        e["triangle_index"] = S.INVALID
+        if not hasattr(self, "_distant_emitters"):
+            self._distant_emitters = []
+        self._distant_emitters.append((p, e))
+
+    def add_directional_emitter(self, direction, rgb, angular_size_deg=0.0):
+        """et::dir (finite angular size allowed); equivalent_disk_size / angular_size_cosine as build_emitters_distribution (:2463-2466)."""
+        d = np.asarray(direction, dtype=f32)
+        d = (d / f32(math.sqrt(float(np.dot(d, d))))).astype(f32)
+        ang = f32(math.radians(angular_size_deg))
+        p = np.zeros(1, dtype=S.EMITTER_PROFILE)
+        p["emission"]["spectrum_index"] = self.add_spectrum(spd_rgb_luminance(rgb))
+        p["emission"]["image_index"] = S.INVALID
+        p["direction"][0] = d
+        p["cls"] = S.EMITTER_DIRECTIONAL
+        p["angular_size"] = ang
+        p["equivalent_disk_size"] = f32(2.0 * math.tan(float(ang) / 2.0))
+        p["angular_size_cosine"] = f32(math.cos(float(ang) / 2.0))
+        e = np.zeros(1, dtype=S.EMITTER)
+        e["cls"] = S.EMITTER_DIRECTIONAL
+        e["triangle_index"] = S.INVALID
+        if not hasattr(self, "_distant_emitters"):
+            self._distant_emitters = []
+        self._distant_emitters.append((p, e))
+
     # -- geometry --------------------------------------------------------------------------------
     def add_mesh(self, positions, normals, indices, material_index, uvs=None):
         positions = np.asarray(positions, dtype=f32).reshape(-1, 3)
@@ -383,6 +487,7 @@ class SceneData:
             instances.append(e)
         for (p, e) in getattr(self, "_distant_emitters", []):
             e = e.copy()
+            e["cls"] = p["cls"]
             e["profile"] = len(profiles)
             e["additional_weight"] = f32(math.pi) * radius * radius
             e["spectrum_weight"] = luminance(self.a_spectra["integrated"][int(p["emission"]["spectrum_index"][0])])
@@ -420,7 +525,7 @@ class SceneData:
         view("materials", self.a_materials)
         view("emitter_profiles", self.a_profiles)
         view("emitter_instances", self.a_emitters)
-        self.a_images = getattr(self, "a_images", np.zeros(0, dtype=S.IMAGE))
+        self.a_images = np.concatenate(self._images) if getattr(self, "_images", None) else np.zeros(0, dtype=S.IMAGE)
         self.a_mediums = getattr(self, "a_mediums", np.zeros(0, dtype=S.MEDIUM))
         view("images", self.a_images)
         view("mediums", self.a_mediums)
@@ -542,6 +647,73 @@ def material_box(kind, width=32, height=32, samples=16, spectral=False, sphere_s
     sd.add_box([-0.33, 0.6, -0.29], (0.3, 0.6, 0.3), 17.0, test)
     sd.add_uv_sphere([0.38, 0.351, 0.35], 0.35, sphere_segments, sphere_rings, test)
     sd.set_camera([0.0, 1.0, 3.82], [0.0, 1.0, -6.18], [0.0, 1.0, 0.0], width, height, 39.597755335771296, clip_near=0.1, clip_far=100.0)
+    return sd.finalize(samples=samples, spectral=spectral)
+
+
+def sky_image(width=64, height=32, seed=1234):
+    """Procedural RGBA32F lat-long sky: vertical gradient + a sun blob (BASELINE config 3's env map in miniature)."""
+    rng = np.random.default_rng(seed)
+    v, u = np.meshgrid((np.arange(height) + 0.5) / height, (np.arange(width) + 0.5) / width, indexing="ij")
+    up = np.cos(v * np.pi)
+    sky = np.stack([0.25 + 0.35 * np.clip(up, 0, 1), 0.35 + 0.45 * np.clip(up, 0, 1), 0.55 + 0.6 * np.clip(up, 0, 1)], axis=-1)
+    ground = np.array([0.12, 0.10, 0.08])
+    img = np.where(up[..., None] > 0, sky, ground)
+    su, sv = 0.3, 0.22
+    blob = 40.0 * np.exp(-(((u - su) * 2 * np.cos((v - 0.5) * np.pi)) ** 2 + (v - sv) ** 2) / (2 * 0.015 ** 2))
+    img = img + blob[..., None] * np.array([1.0, 0.9, 0.7])
+    img = img * (1.0 + 0.02 * rng.random(img.shape))
+    return np.concatenate([img, np.ones((height, width, 1))], axis=-1).astype(f32)
+
+
+def checker_image(n=16, a=(0.8, 0.8, 0.8), b=(0.2, 0.3, 0.6), alpha_holes=False):
+    yy, xx = np.mgrid[0:n, 0:n]
+    m = ((xx // 2 + yy // 2) % 2).astype(bool)
+    img = np.where(m[..., None], np.array(a), np.array(b))
+    alpha = np.ones((n, n, 1))
+    if alpha_holes:
+        alpha[(xx % 4 == 0) & (yy % 4 == 0)] = 0.25
+    return np.concatenate([img, alpha], axis=-1).astype(f32)
+
+
+def sky_room(width=32, height=32, samples=16, spectral=False, textures=True, sun=True, env=True, area_light=True):
+    """Open scene under an importance-sampled environment map + a finite-size sun, textured / normal-mapped floor, plastic and conductor props."""
+    sd = SceneData()
+    sd.name = "sky_room" + ("/spectral" if spectral else "/rgb")
+    floor_kw = dict(kd=[1.0, 1.0, 1.0])
+    floor = sd.add_material("floor", **floor_kw)
+    plastic = sd.add_material("plastic", cls=S.MAT_PLASTIC, kd=[0.7, 0.2, 0.2], ks=[1, 1, 1], roughness=0.5, int_ior="plastic")
+    metal = sd.add_material("metal", cls=S.MAT_CONDUCTOR, ks=[1, 1, 1], roughness=0.4, int_ior="gold")
+    panel = sd.add_material("panel", kd=[0.9, 0.9, 0.9], two_sided=1)
+    light = sd.add_material("light", kd=[0, 0, 0], emission=spd_rgb_luminance([6.0, 5.0, 4.0]), two_sided=1)
+    if textures:
+        checker = sd.add_image(checker_image(16), repeat=True)
+        holes = sd.add_image(checker_image(8, alpha_holes=True), repeat=True)
+        nrm_px = np.zeros((8, 8, 4), dtype=f32)
+        yy, xx = np.mgrid[0:8, 0:8]
+        nrm_px[..., 0] = 0.5 + 0.2 * np.sin(xx * np.pi / 4)
+        nrm_px[..., 1] = 0.5 + 0.2 * np.cos(yy * np.pi / 4)
+        nrm_px[..., 2] = 0.9
+        nrm_px[..., 3] = 1.0
+        nmap = sd.add_image(nrm_px, repeat=True)
+        rough = sd.add_image(np.concatenate([np.tile(np.linspace(0.3, 1.0, 8, dtype=f32)[None, :, None], (8, 1, 3)), np.ones((8, 8, 1), f32)], axis=-1), repeat=True)
+        sd.materials[floor]["scattering"]["image_index"] = checker
+        sd.materials[floor]["normal_image_index"] = nmap
+        sd.materials[floor]["normal_scale"] = 0.7
+        sd.materials[panel]["scattering"]["image_index"] = holes
+        sd.materials[metal]["roughness"]["image_index"] = rough
+        sd.materials[metal]["roughness"]["channel"] = 0
+    sd.add_quad([-2, 0, 2], [2, 0, 2], [2, 0, -2], [-2, 0, -2], floor, 2)
+    sd.add_box([-0.5, 0.4, -0.3], (0.35, 0.4, 0.35), 20.0, plastic)
+    sd.add_uv_sphere([0.55, 0.4, 0.2], 0.4, 16, 9, metal)
+    sd.add_quad([-1.2, 0.0, -1.2], [1.2, 0.0, -1.2], [1.2, 1.4, -1.2], [-1.2, 1.4, -1.2], panel)
+    if area_light:
+        sd.add_quad([-0.3, 1.6, -0.3], [0.3, 1.6, -0.3], [0.3, 1.6, 0.3], [-0.3, 1.6, 0.3], light)
+    if env:
+        sky = sd.add_image(sky_image(64, 32), repeat=True, build_table=True)
+        sd.add_environment_emitter(sky, rgb=(1.0, 1.0, 1.0))
+    if sun:
+        sd.add_directional_emitter([0.3, 0.8, 0.5], rgb=(3.0, 2.8, 2.5), angular_size_deg=2.0)
+    sd.set_camera([0.0, 1.2, 3.6], [0.0, 0.5, 0.0], [0.0, 1.0, 0.0], width, height, 45.0, clip_near=0.1, clip_far=100.0)
     return sd.finalize(samples=samples, spectral=spectral)
 
 
