@@ -34,9 +34,23 @@ def workload(args):
     elif args.workload == "C1":
         sd = scenes.cornell_box(args.res or 512, args.res or 512, samples=16, spectral=False)
         desc = "C1: Cornell box diffuse, RGB, %dx%d" % (sd.width, sd.height)
+    elif args.workload == "C3":
+        w, h = (args.res, args.res * 9 // 16) if args.res else (1920, 1080)
+        sd = scenes.procedural_room(w, h, samples=1024, spectral=True)
+        desc = "C3: %d-triangle procedural room (plastic/conductor/thin-film + env map), spectral, %dx%d, full VCM" % (sd.triangle_count, sd.width, sd.height)
     else:
         raise SystemExit(f"unknown workload {args.workload}")
     return sd, desc
+
+
+def scene_factory(args, res):
+    """The bench workload's scene at a reduced film size (CPU baseline samples)."""
+    from etx_tracer_b200 import scenes
+    if args.workload == "C2":
+        return scenes.cornell_box(res, res, samples=256, spectral=True, sphere=True)
+    if args.workload == "C3":
+        return scenes.procedural_room(res, max(16, res * 9 // 16), samples=1024, spectral=True)
+    return scenes.cornell_box(res, res, samples=16, spectral=False)
 
 
 class ClockSampler:
@@ -106,9 +120,9 @@ def cpu_baseline_run(sd_factory, budget_s, threads):
     o.begin(0)
     t0 = time.time()
     o.run(1, threads=threads)
-    rate = 64 * 64 / max(time.time() - t0, 1e-6)  # samples/s
+    rate = probe.width * probe.height / max(time.time() - t0, 1e-6)  # samples/s
     o.close()
-    res = int(min(1024, max(64, (rate * budget_s) ** 0.5)) // 32 * 32)
+    res = int(min(1024, max(64, (rate * budget_s * (probe.width / probe.height)) ** 0.5)) // 32 * 32)
     sd = sd_factory(res)
     o = oracle_py.Oracle(sd, flavor)
     o.begin(0)
@@ -116,8 +130,9 @@ def cpu_baseline_run(sd_factory, budget_s, threads):
     total = o.run(1, threads=threads)
     wall = time.time() - t0
     o.close()
-    return {"value": res * res / total / 1e6, "unit": UNIT, "cores": threads, "kind": "reference",
-            "sample": f"1 VCM iteration of the same scene at {res}x{res} ({res*res} samples, {wall:.1f} s) by oracle/_ref/liboracle_{flavor}.so "
+    n = sd.width * sd.height
+    return {"value": n / total / 1e6, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": f"1 VCM iteration of the same scene at {sd.width}x{sd.height} ({n} samples, {wall:.1f} s) by oracle/_ref/liboracle_{flavor}.so "
                       f"(reference headers compiled in place + our BVH instead of Embree)"}, flavor
 
 
@@ -128,7 +143,7 @@ def run_reference(args):
     from etx_tracer_b200 import scenes
     threads = os.cpu_count() or 1
     def factory(res):
-        return scenes.cornell_box(res, res, samples=256, spectral=True, sphere=True) if args.workload == "C2" else scenes.cornell_box(res, res, samples=16, spectral=False)
+        return scene_factory(args, res)
     from oracle import oracle_py
     flavor = "native"
     try:
@@ -139,11 +154,12 @@ def run_reference(args):
     probe.begin(0)
     t0 = time.time()
     probe.run(1, threads=threads)
-    rate = 64 * 64 / max(time.time() - t0, 1e-6)
+    rate = probe.width * probe.height / max(time.time() - t0, 1e-6)
     probe.close()
     per_step = max(2.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
     res = int(min(1024, max(64, (rate * per_step) ** 0.5)) // 32 * 32)
     sd = factory(res)
+    res_n = sd.width * sd.height
     o = oracle_py.Oracle(sd, flavor)
     o.begin(0)
     o.run(args.warmup, threads=threads)
@@ -151,7 +167,7 @@ def run_reference(args):
     before = o.run(0, threads=threads)
     total = o.run(args.steps, threads=threads) - before
     wall = time.time() - t0
-    value = res * res * args.steps / total / 1e6
+    value = res_n * args.steps / total / 1e6
     sd_full, desc = workload(args)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -299,9 +315,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             from etx_tracer_b200 import scenes
-            def factory(res):
-                return scenes.cornell_box(res, res, samples=256, spectral=True, sphere=True) if args.workload == "C2" else scenes.cornell_box(res, res, samples=16, spectral=False)
-            cpu, _ = cpu_baseline_run(factory, args.cpu_budget, os.cpu_count() or 1)
+            cpu, _ = cpu_baseline_run(lambda res: scene_factory(args, res), args.cpu_budget, os.cpu_count() or 1)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "parallelism": f"pixel-tile x{world}" if world > 1 else "single GPU", "l2": "inputs larger than L2 (path state + light-vertex pool + photon grid > 126 MB)",

@@ -28,6 +28,7 @@ struct PathBuffers {
   float4* bs_wo_eta;      //         w_o, eta
   uint2* bs_props;        //         properties, medium index
   uint32_t* merge_key;    // camera: per queue slot, Morton code of the merge query's base grid cell (0xffffffff = no merge)
+  uint32_t* conn_seed;    // camera (product build): sampler state the vertex-connection stage derives its per-connection streams from
 };
 
 struct DeviceCounters {
@@ -61,6 +62,10 @@ struct LaunchParams {
   uint32_t path_count;           // N = W*H
   uint32_t rank, world;          // pixel-tile partition
   uint32_t camera_sample_index;  // Film sample_count of every pixel before this iteration
+  uint2* conn_list;              // product build: (path id, light-vertex ordinal) of every pending vertex connection of this bounce
+  uint32_t* conn_count;
+  uint32_t conn_capacity;
+  uint32_t connect_stage;        // 1: vertex connections run in k_camera_connect (product build, scenes with stochastic BSDFs)
 };
 
 #ifdef ETXB_COUNT_TRAVERSAL
@@ -449,7 +454,30 @@ __global__ void __launch_bounds__(128) k_camera_shade(LaunchParams p, const uint
       state.path_distance = 0.0f;
       vcm_handle_direct_hit<SP>(sc, p.vcm, isect, state);
       if (is_connectible) {
-        state.gathered += vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], isect, state, stats, shadow_rays, connections);
+        if (!p.connect_stage) {
+          // reference order: serial over the paired path's vertices with the path's own sampler
+          state.gathered += vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], isect, state, stats, shadow_rays, connections);
+        } else if (p.vcm.connect_vertices()) {
+          // scenes with stochastic BSDFs (product build): the camera-vertex x light-vertex connections (vcm_shared.hxx:765-803)
+          // become their own wavefront stage, one thread per connection (k_camera_connect); here only the work list is emitted
+          uint32_t lp_count = p.paths.lv_count[i];
+          // target_path_length = depth + k + 2 must lie in [min_path_length, max_path_length]
+          uint32_t d2 = state.total_path_depth + 2u;
+          uint32_t k_begin = (sc.min_path_length > d2) ? (sc.min_path_length - d2) : 0u;
+          uint32_t k_end = (sc.max_path_length >= d2) ? umin(lp_count, sc.max_path_length - d2 + 1u) : 0u;
+          if (k_end > k_begin) {
+            uint32_t cnt = k_end - k_begin;
+            uint32_t base = atomicAdd(p.conn_count, cnt);
+            if (base + cnt <= p.conn_capacity) {
+              for (uint32_t k = 0; k < cnt; ++k) p.conn_list[base + k] = make_uint2(i, k_begin + k);
+            } else {
+              *p.overflow = 1u;
+            }
+            p.paths.conn_seed[i] = state.sampler.seed;
+            state.sampler.next();  // the path's own stream moves on by one draw for the whole stage
+            connections += cnt;
+          }
+        }
         state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
         state.gathered += vcm_connect_to_light<SP>(sc, p.vcm, isect, state, stats, shadow_rays);
         state.sampler.pop_fixed();
@@ -470,6 +498,54 @@ __global__ void __launch_bounds__(128) k_camera_shade(LaunchParams p, const uint
   counter_add(&p.counters->bounces_camera, (q < *count_in) ? 1u : 0u);
   counter_add(&p.counters->rays_shadow, shadow_rays);
   counter_add(&p.counters->connections, connections);
+  counter_add(&p.counters->nodes, STATS_NODES);
+  counter_add(&p.counters->tris, STATS_TRIS);
+}
+
+// Product build: one thread per (camera vertex, light vertex) connection — vcm_connect_to_light_vertex + the shadow ray of
+// vcm_connect_to_light_path (vcm_shared.hxx:673-803).  Each connection draws from its own stream derived from the path's sampler
+// (the reference shares one stream across the serial loop; the parity build keeps that order inside k_camera_shade).
+template <bool SP>
+__global__ void __launch_bounds__(128) k_camera_connect(LaunchParams p) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t shadow_rays = 0;
+  STATS_DECL;
+  uint32_t total = umin(*p.conn_count, p.conn_capacity);
+  if (t < total) {
+    const DeviceScene& sc = p.scene;
+    uint2 entry = p.conn_list[t];
+    uint32_t i = entry.x;
+    PathState<SP> state = load_state<SP>(p.paths, i);
+    float4 hit = p.paths.hit[i];
+    Isect isect = make_intersection(sc, state.ray_d, __float_as_uint(hit.w), hit.x, hit.y, hit.z);
+    state.sampler.seed = p.paths.conn_seed[i] ^ ((entry.y + 1u) * 0x9E3779B1u);
+    state.sampler.next();
+    const float4* src = reinterpret_cast<const float4*>(p.lv_final + p.lp_offset[i] + entry.y);
+    LightVertexRec lv;
+    lv.thr_dvcm = __ldg(src + 0);
+    lv.wi_dvc = __ldg(src + 1);
+    lv.bc_dvm = __ldg(src + 2);
+    lv.pos_tri = __ldg(src + 3);
+    lv.nrm_mat = __ldg(src + 4);
+    V3 target_position;
+    Spec<SP> value;
+    if (vcm_connect_to_light_vertex<SP>(sc, p.vcm, state, lv, isect, target_position, value)) {
+      TriRec tri = load_triangle(sc, isect.triangle_index);
+      V3 p0 = shading_pos(sc, tri, isect.barycentric, normalize(target_position - isect.pos));
+      shadow_rays = 1;
+      float tr = trace_transmittance(sc, p0, target_position, state.sampler, stats);
+      if (tr > kEpsilon) {
+        V3 v = (Spec<SP>::make(tr) * value).as_v3();
+        float* dst = reinterpret_cast<float*>(p.paths.gathered + i);
+        atomicAdd(dst + 0, v.x);
+        if (!SP) {
+          atomicAdd(dst + 1, v.y);
+          atomicAdd(dst + 2, v.z);
+        }
+      }
+    }
+  }
+  counter_add(&p.counters->rays_shadow, shadow_rays);
   counter_add(&p.counters->nodes, STATS_NODES);
   counter_add(&p.counters->tris, STATS_TRIS);
 }
@@ -519,7 +595,12 @@ __global__ void __launch_bounds__(128) k_camera_merge_serial(LaunchParams p, con
 constexpr uint32_t kMergeWarpsPerBlock = 8;
 constexpr uint32_t kMergeListSize = 64;
 
-template <bool SP>
+// GENERIC = false: Lambert camera vertices (BSDF value independent of the photon direction, no sampler use).
+// GENERIC = true : every other class (microfacet walks, mixtures).  Their evaluate()/pdf() are stochastic; in the product build
+//                  each in-radius photon is evaluated by its own lane with a lane-local sampler derived from (path seed, photon
+//                  index), and the path's sampler advances by one draw per query — statistically equivalent to the reference's
+//                  serial order (which the parity build keeps), 32x more parallel.
+template <bool SP, bool GENERIC>
 __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys, const uint32_t* count_in) {
   __shared__ uint32_t s_idx[kMergeWarpsPerBlock][kMergeListSize];
   __shared__ float s_d2[kMergeWarpsPerBlock][kMergeListSize];
@@ -535,26 +616,45 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
   V3 qpos = {0, 0, 0}, qnrm = {0, 0, 0}, qfn = {0, 0, 0}, qc = {0, 0, 0};
   float q_wcam_base = 0.0f, q_dvm = 0.0f, q_rev_cos = 0.0f;
   uint32_t q_depth = 0;
+  // GENERIC only: the rest of the camera vertex
+  V3 qtan = {0, 0, 0}, qbtn = {0, 0, 0}, qwi = {0, 0, 0};
+  V2 qtex = {0, 0};
+  float q_wavelength = 0.0f;
+  uint32_t q_medium = 0, q_material = 0, q_seed = 0;
   if (coop_active) {
     i = sorted_ids[q];
     float4 hit = p.paths.hit[i];
     PathState<SP> state = load_state<SP>(p.paths, i);
     Isect isect = make_intersection(sc, state.ray_d, __float_as_uint(hit.w), hit.x, hit.y, hit.z);
     const etxb_material& mat = sc.materials[isect.material_index];
-    coop_active = merge_is_lambert(mat);
+    coop_active = merge_is_lambert(mat) != GENERIC;
     if (coop_active) {
       merge_queries = 1;
       qpos = isect.pos;
       qnrm = isect.nrm;
-      bool entering = dot(isect.nrm, isect.w_i) < 0.0f;
-      qfn = entering ? isect.nrm : -isect.nrm;  // frame normal of the camera vertex
-      Spec<SP> diffuse = apply_image<SP>(sc, mat.scattering, isect.tex, state.wavelength);
-      Spec<SP> t_camera = state.throughput / sampling_pdf<SP>(state.wavelength);
-      qc = spec_to_rgb<SP>(sc, (diffuse / kPi) * t_camera, state.wavelength);  // camera_bsdf.func * t_camera: direction independent
       q_wcam_base = state.d_vcm * p.vcm.vc_weight;
       q_dvm = state.d_vm;
-      q_rev_cos = dot(isect.nrm, -isect.w_i);  // reverse pdf = cos between -w_i(camera) and the normal facing the photon (bsdf_various.hxx:113-121)
       q_depth = state.total_path_depth;
+      Spec<SP> t_camera = state.throughput / sampling_pdf<SP>(state.wavelength);
+      if constexpr (!GENERIC) {
+        bool entering = dot(isect.nrm, isect.w_i) < 0.0f;
+        qfn = entering ? isect.nrm : -isect.nrm;  // frame normal of the camera vertex
+        Spec<SP> diffuse = apply_image<SP>(sc, mat.scattering, isect.tex, state.wavelength);
+        qc = spec_to_rgb<SP>(sc, (diffuse / kPi) * t_camera, state.wavelength);  // camera_bsdf.func * t_camera: direction independent
+        q_rev_cos = dot(isect.nrm, -isect.w_i);  // reverse pdf = cos between -w_i(camera) and the normal facing the photon (bsdf_various.hxx:113-121)
+      } else {
+        qc = t_camera.as_v3();
+        qtan = isect.tan;
+        qbtn = isect.btn;
+        qwi = isect.w_i;
+        qtex = isect.tex;
+        q_wavelength = state.wavelength;
+        q_medium = state.medium_index;
+        q_material = isect.material_index;
+        q_seed = state.sampler.seed;
+        state.sampler.next();  // the path's own stream moves on by one draw per query
+        p.paths.misc[i].x = state.sampler.seed;
+      }
     }
   }
   uint32_t pending = __ballot_sync(0xffffffffu, coop_active);
@@ -568,10 +668,26 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
     V3 bpos = {__shfl_sync(0xffffffffu, qpos.x, src), __shfl_sync(0xffffffffu, qpos.y, src), __shfl_sync(0xffffffffu, qpos.z, src)};
     V3 bnrm = {__shfl_sync(0xffffffffu, qnrm.x, src), __shfl_sync(0xffffffffu, qnrm.y, src), __shfl_sync(0xffffffffu, qnrm.z, src)};
     V3 bfn = {__shfl_sync(0xffffffffu, qfn.x, src), __shfl_sync(0xffffffffu, qfn.y, src), __shfl_sync(0xffffffffu, qfn.z, src)};
+    V3 bqc = {__shfl_sync(0xffffffffu, qc.x, src), __shfl_sync(0xffffffffu, qc.y, src), __shfl_sync(0xffffffffu, qc.z, src)};
     float b_wcam_base = __shfl_sync(0xffffffffu, q_wcam_base, src);
     float b_dvm = __shfl_sync(0xffffffffu, q_dvm, src);
     float b_rev_cos = __shfl_sync(0xffffffffu, q_rev_cos, src);
     uint32_t b_depth = __shfl_sync(0xffffffffu, q_depth, src);
+    BData cam = {};
+    uint32_t b_material = 0, b_seed = 0;
+    if constexpr (GENERIC) {
+      cam.pos = bpos;
+      cam.nrm = bnrm;
+      cam.tan = {__shfl_sync(0xffffffffu, qtan.x, src), __shfl_sync(0xffffffffu, qtan.y, src), __shfl_sync(0xffffffffu, qtan.z, src)};
+      cam.btn = {__shfl_sync(0xffffffffu, qbtn.x, src), __shfl_sync(0xffffffffu, qbtn.y, src), __shfl_sync(0xffffffffu, qbtn.z, src)};
+      cam.w_i = {__shfl_sync(0xffffffffu, qwi.x, src), __shfl_sync(0xffffffffu, qwi.y, src), __shfl_sync(0xffffffffu, qwi.z, src)};
+      cam.tex = {__shfl_sync(0xffffffffu, qtex.x, src), __shfl_sync(0xffffffffu, qtex.y, src)};
+      cam.wavelength = __shfl_sync(0xffffffffu, q_wavelength, src);
+      cam.current_medium = __shfl_sync(0xffffffffu, q_medium, src);
+      cam.path_source = kPathCamera;
+      b_material = __shfl_sync(0xffffffffu, q_material, src);
+      b_seed = __shfl_sync(0xffffffffu, q_seed, src);
+    }
     // the eight cells (vcm_shared.hxx:895-916): lanes 0..7 fetch their ranges, then an 8-wide exclusive scan of the counts
     uint32_t my_begin = 0, my_cnt = 0;
     if (lane < 8u) {
@@ -597,7 +713,7 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
     uint32_t e1 = __shfl_sync(0xffffffffu, my_excl, 1), e2 = __shfl_sync(0xffffffffu, my_excl, 2), e3 = __shfl_sync(0xffffffffu, my_excl, 3),
              e4 = __shfl_sync(0xffffffffu, my_excl, 4), e5 = __shfl_sync(0xffffffffu, my_excl, 5), e6 = __shfl_sync(0xffffffffu, my_excl, 6),
              e7 = __shfl_sync(0xffffffffu, my_excl, 7);
-    float wx = 0.0f, wy = 0.0f, wz = 0.0f;  // per-lane partial sums of l_value * kernel * mis
+    float wx = 0.0f, wy = 0.0f, wz = 0.0f;  // per-lane partial sums
     uint32_t n_list = 0;                    // warp-uniform fill of the shared list
 
     auto finish = [&](uint32_t n) {
@@ -611,20 +727,40 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
         float4 lt = __ldg(&g.thr_rgb[j]);
         bool ok = !(__float_as_uint(wl.w) + b_depth + 1 > sc.max_path_length);
         ok = ok && !(dot(bnrm, V3{nd.x, nd.y, nd.z}) <= kEpsilon);
-        float cos_o = -(bfn.x * wl.x + bfn.y * wl.y + bfn.z * wl.z);  // local_w_o.z of DiffuseBSDF::evaluate(-w_in)
-        ok = ok && (cos_o > kEpsilon);
-        if (ok) {
-          float bsdf_pdf_v = kInvPi * cos_o;
+        float bsdf_pdf_v = 0.0f, rev_pdf = 0.0f;
+        V3 c_value = {1.0f, 1.0f, 1.0f};
+        if constexpr (!GENERIC) {
+          float cos_o = -(bfn.x * wl.x + bfn.y * wl.y + bfn.z * wl.z);  // local_w_o.z of DiffuseBSDF::evaluate(-w_in)
+          ok = ok && (cos_o > kEpsilon);
+          bsdf_pdf_v = kInvPi * cos_o;
           float facing = (dot(bnrm, V3{wl.x, wl.y, wl.z}) < 0.0f) ? b_rev_cos : -b_rev_cos;
-          float rev_pdf = (facing <= kEpsilon) ? 0.0f : kInvPi * facing;
+          rev_pdf = (facing <= kEpsilon) ? 0.0f : kInvPi * facing;
+        } else {
+          if (ok) {
+            Smp lane_smp;
+            lane_smp.seed = b_seed ^ ((j + 1u) * 0x9E3779B1u);
+            lane_smp.fixed_u = lane_smp.fixed_v = lane_smp.fixed_w = 0.0f;
+            lane_smp.next();
+            const etxb_material& mat = sc.materials[b_material];
+            V3 wo = {-wl.x, -wl.y, -wl.z};
+            BEval<SP> e = bsdf_evaluate<SP>(sc, cam, wo, mat, lane_smp);
+            ok = e.valid();
+            if (ok) {
+              rev_pdf = bsdf_reverse_pdf<SP>(sc, cam, wo, mat, lane_smp);
+              bsdf_pdf_v = e.pdf;
+              c_value = spec_to_rgb<SP>(sc, e.func * Spec<SP>::make3(bqc), cam.wavelength);
+            }
+          }
+        }
+        if (ok) {
           float w_light = dvcm * vc_weight + nd.w * bsdf_pdf_v;
           float w_camera = b_wcam_base + b_dvm * rev_pdf;
           float weight = use_mis ? (1.0f / (1.0f + w_light + w_camera)) : 1.0f;
           float kernel_weight = use_epan ? fmaxf(2.0f * (1.0f - distance_squared * g.inv_radius_squared), 0.0f) : 1.0f;
           float kw = kernel_weight * weight;
-          wx += lt.x * kw;
-          wy += lt.y * kw;
-          wz += lt.z * kw;
+          wx += c_value.x * lt.x * kw;
+          wy += c_value.y * lt.y * kw;
+          wz += c_value.z * lt.z * kw;
           accepts += 1;
         }
       }
@@ -688,7 +824,7 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
     if (lane == src) {
       V3 l = {wx, wy, wz};
       if (SP) l *= V3{0.817660332f, 1.05418909f, 1.09945524f};  // kRGBLuminanceScale (:876-878)
-      my_sum = qc * l;
+      my_sum = GENERIC ? l : qc * l;
     }
   }
   if (merge_queries) {

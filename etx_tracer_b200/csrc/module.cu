@@ -39,6 +39,7 @@ enum KernelId : uint32_t {
   K_CAMERA_BEGIN,
   K_TRACE_CAMERA,
   K_CAMERA_SHADE,
+  K_CAMERA_CONNECT,
   K_CAMERA_MERGE_SORT,
   K_CAMERA_MERGE,
   K_CAMERA_MERGE_SERIAL,
@@ -47,7 +48,7 @@ enum KernelId : uint32_t {
   K_COUNT
 };
 const char* kKernelNames[K_COUNT] = {"light_begin", "trace_closest(light)", "light_bounce", "lv_scan", "lv_reorder", "grid_bbox", "grid_keys", "grid_sort", "grid_build",
-  "camera_begin", "trace_closest(camera)", "camera_shade", "camera_merge_sort", "camera_merge", "camera_merge_serial", "camera_continue", "film_commit_light"};
+  "camera_begin", "trace_closest(camera)", "camera_shade", "camera_connect", "camera_merge_sort", "camera_merge", "camera_merge_generic", "camera_continue", "film_commit_light"};
 
 template <class T>
 struct DevBuf {
@@ -108,7 +109,8 @@ struct etxb_ctx {
   DevBuf<uint4> misc;
   DevBuf<uint2> bs_props;
   DevBuf<float> wavelength;
-  DevBuf<uint32_t> lv_count, lp_offset, queue_a, queue_b, queue_counts, sampler_end_light, sampler_end_camera, merge_key;
+  DevBuf<uint32_t> lv_count, lp_offset, queue_a, queue_b, queue_counts, sampler_end_light, sampler_end_camera, merge_key, conn_seed, conn_count;
+  DevBuf<uint2> conn_list;
   // light vertices + grid
   uint32_t lv_capacity = 0, max_light_vertices_cfg = 0;
   DevBuf<LightVertexRec> lv_tmp, lv_final;
@@ -216,7 +218,7 @@ LaunchParams make_params(etxb_ctx* ctx) {
   LaunchParams p = {};
   p.scene = ctx->dscene;
   p.paths = {ctx->ray_o.ptr, ctx->ray_d.ptr, ctx->thr.ptr, ctx->mis.ptr, ctx->misc.ptr, ctx->hit.ptr, ctx->gathered.ptr, ctx->merged.ptr, ctx->wavelength.ptr,
-    ctx->lv_count.ptr, ctx->bs_weight_pdf.ptr, ctx->bs_wo_eta.ptr, ctx->bs_props.ptr, ctx->merge_key.ptr};
+    ctx->lv_count.ptr, ctx->bs_weight_pdf.ptr, ctx->bs_wo_eta.ptr, ctx->bs_props.ptr, ctx->merge_key.ptr, ctx->conn_seed.ptr};
   p.film = {ctx->film_camera.ptr, ctx->film_light.ptr, ctx->film_light_iteration.ptr, ctx->width, ctx->height};
   p.grid = ctx->grid;
   p.lv_tmp = ctx->lv_tmp.ptr;
@@ -233,6 +235,14 @@ LaunchParams make_params(etxb_ctx* ctx) {
   p.rank = ctx->rank;
   p.world = ctx->world;
   p.camera_sample_index = ctx->completed;
+  p.conn_list = ctx->conn_list.ptr;
+  p.conn_count = ctx->conn_count.ptr;
+  p.conn_capacity = ctx->lv_capacity;
+#if defined(ETXB_PARITY) && ETXB_PARITY
+  p.connect_stage = 0;
+#else
+  p.connect_stage = ctx->has_stochastic_merge ? 1u : 0u;
+#endif
   // start_next_iteration (vcm_cpu.cxx:95-113)
   VcmParams& v = p.vcm;
   v.options = ctx->options.options;
@@ -401,9 +411,19 @@ int run_camera_pass(etxb_ctx* ctx) {
       k_trace_closest<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, qin, counts + cur);
     }
     CUDA_OK(ctx, cudaMemsetAsync(counts + (cur ^ 1u), 0, 4, ctx->stream));
+    if (p.connect_stage) CUDA_OK(ctx, cudaMemsetAsync(ctx->conn_count.ptr, 0, 4, ctx->stream));
     {
       LaunchTimer t(ctx, K_CAMERA_SHADE);
       k_camera_shade<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur);
+    }
+    if (p.connect_stage && (ctx->options.options & ETXB_VCM_CONNECT_VERTICES)) {
+      uint32_t pending = 0;
+      if (int rc = read_u32(ctx, ctx->conn_count.ptr, pending)) return rc;
+      pending = std::min(pending, ctx->lv_capacity);
+      if (pending) {
+        LaunchTimer t(ctx, K_CAMERA_CONNECT);
+        k_camera_connect<SP><<<blocks_for(pending, 128), 128, 0, ctx->stream>>>(p);
+      }
     }
 #if defined(ETXB_PARITY) && ETXB_PARITY
     if (merging) {
@@ -421,11 +441,11 @@ int run_camera_pass(etxb_ctx* ctx) {
       }
       {
         LaunchTimer t(ctx, K_CAMERA_MERGE);
-        k_camera_merge_coop<SP><<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, ctx->vals_out.ptr, ctx->keys_out.ptr, counts + cur);
+        k_camera_merge_coop<SP, false><<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, ctx->vals_out.ptr, ctx->keys_out.ptr, counts + cur);
       }
       if (ctx->has_stochastic_merge) {
         LaunchTimer t(ctx, K_CAMERA_MERGE_SERIAL);
-        k_camera_merge_serial<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur);
+        k_camera_merge_coop<SP, true><<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, ctx->vals_out.ptr, ctx->keys_out.ptr, counts + cur);
       }
     }
 #endif
@@ -513,7 +533,7 @@ void etxb_destroy(etxb_ctx* ctx) {
     &ctx->g_win, &ctx->g_thr, &ctx->film_camera, &ctx->film_light, &ctx->film_light_iteration, &ctx->film_out};
   for (auto* b : f4) b->release();
   DevBuf<uint32_t>* u32[] = {&ctx->tri_emitter, &ctx->lv_count, &ctx->lp_offset, &ctx->queue_a, &ctx->queue_b, &ctx->queue_counts, &ctx->sampler_end_light,
-    &ctx->sampler_end_camera, &ctx->merge_key, &ctx->lv_tmp_count, &ctx->overflow, &ctx->grid_bbox, &ctx->keys_in, &ctx->keys_out, &ctx->vals_in, &ctx->vals_out};
+    &ctx->sampler_end_camera, &ctx->merge_key, &ctx->conn_seed, &ctx->conn_count, &ctx->lv_tmp_count, &ctx->overflow, &ctx->grid_bbox, &ctx->keys_in, &ctx->keys_out, &ctx->vals_in, &ctx->vals_out};
   for (auto* b : u32) b->release();
   ctx->vertices.release();
   ctx->triangles.release();
@@ -536,6 +556,7 @@ void etxb_destroy(etxb_ctx* ctx) {
   ctx->lv_tmp.release();
   ctx->lv_final.release();
   ctx->cell_range.release();
+  ctx->conn_list.release();
   ctx->bs_props.release();
   ctx->bs_weight_pdf.release();
   ctx->bs_wo_eta.release();
@@ -756,8 +777,9 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   CUDA_OK(ctx, ctx->bs_props.alloc(n));
   CUDA_OK(ctx, ctx->misc.alloc(n));
   CUDA_OK(ctx, ctx->wavelength.alloc(n));
-  DevBuf<uint32_t>* per_path_u32[] = {&ctx->lv_count, &ctx->lp_offset, &ctx->queue_a, &ctx->queue_b, &ctx->sampler_end_light, &ctx->sampler_end_camera, &ctx->merge_key};
+  DevBuf<uint32_t>* per_path_u32[] = {&ctx->lv_count, &ctx->lp_offset, &ctx->queue_a, &ctx->queue_b, &ctx->sampler_end_light, &ctx->sampler_end_camera, &ctx->merge_key, &ctx->conn_seed};
   for (auto* b : per_path_u32) CUDA_OK(ctx, b->alloc(n));
+  CUDA_OK(ctx, ctx->conn_count.alloc(1));
   CUDA_OK(ctx, ctx->queue_counts.alloc(4));
   CUDA_OK(ctx, ctx->lv_tmp_count.alloc(1));
   CUDA_OK(ctx, ctx->overflow.alloc(1));
@@ -768,6 +790,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   ctx->lv_capacity = uint32_t(cap);
   CUDA_OK(ctx, ctx->lv_tmp.alloc(cap));
   CUDA_OK(ctx, ctx->lv_final.alloc(cap));
+  CUDA_OK(ctx, ctx->conn_list.alloc(cap));
   DevBuf<uint32_t>* per_vertex_u32[] = {&ctx->keys_in, &ctx->keys_out, &ctx->vals_in, &ctx->vals_out};
   for (auto* b : per_vertex_u32) CUDA_OK(ctx, b->alloc(cap));
   DevBuf<float4>* per_vertex_f4[] = {&ctx->g_pos, &ctx->g_nrm, &ctx->g_win, &ctx->g_thr};

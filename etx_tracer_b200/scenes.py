@@ -717,6 +717,82 @@ def sky_room(width=32, height=32, samples=16, spectral=False, textures=True, sun
     return sd.finalize(samples=samples, spectral=spectral)
 
 
+def _grid_mesh(p00, du, dv, nu, nv):
+    """Vectorised tessellated parallelogram: positions, normals, uvs, indices (two triangles per cell)."""
+    p00, du, dv = [np.asarray(x, dtype=np.float64) for x in (p00, du, dv)]
+    us, vs = np.meshgrid(np.linspace(0, 1, nu + 1), np.linspace(0, 1, nv + 1), indexing="xy")
+    pos = p00 + us[..., None] * du + vs[..., None] * dv
+    n = np.cross(du, dv)
+    n = n / np.linalg.norm(n)
+    i = (np.arange(nv)[:, None] * (nu + 1) + np.arange(nu)[None, :]).reshape(-1)
+    a, b, c, d = i, i + 1, i + nu + 2, i + nu + 1
+    idx = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)])
+    return pos.reshape(-1, 3), np.tile(n, (pos.shape[0] * pos.shape[1], 1)), np.stack([us, vs], -1).reshape(-1, 2), idx
+
+
+def _sphere_mesh(center, radius, segments, rings, bump=0.0, seed=0):
+    """Vectorised UV sphere (2*segments*(rings-1) triangles) with optional low-frequency radial displacement."""
+    theta = np.pi * np.arange(rings + 1) / rings
+    phi = 2 * np.pi * np.arange(segments + 1) / segments
+    st, ct = np.sin(theta)[:, None], np.cos(theta)[:, None]
+    d = np.stack([st * np.cos(phi)[None, :], ct * np.ones_like(phi)[None, :], st * np.sin(phi)[None, :]], -1)
+    r = radius * (1.0 + bump * np.sin(3 * phi + seed)[None, :] * np.sin(2 * theta + 0.5 * seed)[:, None])
+    pos = np.asarray(center, dtype=np.float64) + d * r[..., None]
+    rr, ss = np.meshgrid(np.arange(rings), np.arange(segments), indexing="ij")
+    a = (rr * (segments + 1) + ss).reshape(-1)
+    b, dd, e = a + 1, a + segments + 1, a + segments + 2
+    rflat = rr.reshape(-1)
+    t1 = np.stack([a, b, dd], 1)[rflat != 0]
+    t2 = np.stack([b, e, dd], 1)[rflat != rings - 1]
+    uv = np.stack(np.meshgrid(np.arange(segments + 1) / segments, np.arange(rings + 1) / rings, indexing="xy"), -1)
+    return pos.reshape(-1, 3), d.reshape(-1, 3), uv.reshape(-1, 2), np.concatenate([t1, t2])
+
+
+def procedural_room(width=1920, height=1080, samples=1024, spectral=True, target_triangles=1_000_000, props=200, env_size=(2048, 1024), seed=1234):
+    """BASELINE config 3: ~1 M-triangle room — tessellated floor/walls + `props` displaced spheres with materials round-robin
+    {plastic, conductor (gold), plastic + thin film, diffuse}, lit by a procedural sky/sun environment map through an open roof
+    plus one area light."""
+    rng = np.random.default_rng(seed)
+    sd = SceneData()
+    sd.name = f"room{target_triangles // 1000}k" + ("/spectral" if spectral else "/rgb")
+    wall = sd.add_material("wall", kd=[0.8, 0.8, 0.8], two_sided=1)
+    floor = sd.add_material("floor", kd=[0.6, 0.5, 0.4], two_sided=1)
+    mats = [
+        sd.add_material("plastic", cls=S.MAT_PLASTIC, kd=[0.7, 0.25, 0.2], ks=[1, 1, 1], roughness=0.3, int_ior="plastic"),
+        sd.add_material("gold", cls=S.MAT_CONDUCTOR, ks=[1, 1, 1], roughness=0.2, int_ior="gold"),
+        sd.add_material("plastic_film", cls=S.MAT_PLASTIC, kd=[0.2, 0.3, 0.7], ks=[1, 1, 1], roughness=0.3, int_ior="plastic", thinfilm=("glass", 300.0, 700.0)),
+        sd.add_material("diffuse", kd=[0.3, 0.7, 0.3]),
+    ]
+    light = sd.add_material("light", kd=[0, 0, 0], emission=spd_rgb_luminance([12.0, 10.0, 8.0]), two_sided=1)
+    rings = 24
+    segments = 48
+    per_prop = 2 * segments * (rings - 1)
+    structure = max(target_triangles - props * per_prop, 6 * 2)
+    n = max(1, int(math.sqrt(structure / (2 * 5.0))))  # 5 tessellated surfaces
+    X, Y, Z = 4.0, 3.0, 4.0
+    surfaces = [
+        ([-X, 0, Z], [2 * X, 0, 0], [0, 0, -2 * Z], floor),          # floor (+y)
+        ([-X, 0, -Z], [2 * X, 0, 0], [0, Y, 0], wall),               # back wall (+z)
+        ([-X, 0, Z], [0, 0, -2 * Z], [0, Y, 0], wall),               # left wall (+x)
+        ([X, 0, -Z], [0, 0, 2 * Z], [0, Y, 0], wall),                # right wall (-x)
+        ([-X, Y, -Z], [2 * X, 0, 0], [0, 0, 0.9 * Z], wall),         # half ceiling (-y), rest open to the sky
+    ]
+    for p00, du, dv, mat in surfaces:
+        pos, nrm, uv, idx = _grid_mesh(p00, du, dv, n, n)
+        sd.add_mesh(pos, nrm, idx, mat, uvs=uv)
+    for k in range(props):
+        cx, cz = rng.uniform(-X + 0.4, X - 0.4), rng.uniform(-Z + 0.4, Z - 0.4)
+        r = rng.uniform(0.12, 0.28)
+        cy = r * 1.02 + (rng.uniform(0, 1.5) if k % 5 == 0 else 0.0)
+        pos, nrm, uv, idx = _sphere_mesh([cx, cy, cz], r, segments, rings, bump=0.12, seed=k)
+        sd.add_mesh(pos, nrm, idx, mats[k % 4], uvs=uv)
+    sd.add_quad([-0.6, Y - 0.02, -2.6], [0.6, Y - 0.02, -2.6], [0.6, Y - 0.02, -1.4], [-0.6, Y - 0.02, -1.4], light)
+    sky = sd.add_image(sky_image(env_size[0], env_size[1], seed=seed), repeat=True, build_table=True)
+    sd.add_environment_emitter(sky, rgb=(1.0, 1.0, 1.0))
+    sd.set_camera([0.0, 1.6, 3.8], [0.0, 1.0, 0.0], [0.0, 1.0, 0.0], width, height, 55.0, clip_near=0.1, clip_far=100.0)
+    return sd.finalize(samples=samples, spectral=spectral)
+
+
 def config(name, scale=1.0):
     """Named BASELINE.json configs. `scale` < 1 shrinks resolution for CPU-sized tests (geometry unchanged)."""
     def dim(v):
@@ -725,4 +801,6 @@ def config(name, scale=1.0):
         return cornell_box(dim(512), dim(512), samples=16, spectral=False, sphere=False)
     if name == "C2":
         return cornell_box(dim(1024), dim(1024), samples=256, spectral=True, sphere=True)
+    if name == "C3":
+        return procedural_room(dim(1920), dim(1080), samples=1024, spectral=True)
     raise KeyError(name)

@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""torchrun --nproc-per-node N tools/multigpu_check.py : the tile-sharded render (NCCL exchanges) against the single-GPU render."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+from etx_tracer_b200 import scenes, structs as S
+from etx_tracer_b200.api import GPUVCM
+from etx_tracer_b200.multigpu import ShardedVCM
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+res, iters = int(sys.argv[1]) if len(sys.argv) > 1 else 256, 3
+ok = True
+for name, sd in (("C2", scenes.cornell_box(res, res, samples=256, spectral=True, sphere=True)), ("sky", scenes.sky_room(res, res, spectral=True))):
+    for merging in (True, False):
+        g = GPUVCM(sd, flavor="fast", device=local)
+        if not merging:
+            g.options["options"] = S.VCM_CONNECT_ONLY
+        sh = ShardedVCM(g, dist, rank, world)
+        g.run(0)
+        for _ in range(iters):
+            sh.iterate()
+        img = sh.reduce_film()
+        light = g.film(S.FILM_LIGHT)
+        if rank == 0:
+            cam = g.film(S.FILM_CAMERA)
+            ref = GPUVCM(sd, flavor="fast", device=local)
+            if not merging:
+                ref.options["options"] = S.VCM_CONNECT_ONLY
+            ref.render(iters)
+            def rel(a, b):
+                a = a[..., :3].astype(np.float64); b = b[..., :3].astype(np.float64)
+                return float(np.sqrt(((a - b) ** 2).sum()) / np.sqrt((b ** 2).sum()))
+            rc, rl = rel(cam, ref.film(S.FILM_CAMERA)), rel(light, ref.film(S.FILM_LIGHT))
+            exact = bool(np.array_equal(cam[..., :3], ref.film(S.FILM_CAMERA)[..., :3]))
+            print(f"{name} merging={merging} world={world}: camera rel-L2 {rc:.3e} (bit-identical: {exact}), light rel-L2 {rl:.3e}", flush=True)
+            ok &= (rc < 1e-4) and (rl < 1e-4)
+            ref.close()
+        g.close()
+        dist.barrier()
+if rank == 0:
+    print("MULTIGPU_CHECK", "OK" if ok else "FAILED", flush=True)
+dist.destroy_process_group()
