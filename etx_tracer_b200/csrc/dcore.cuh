@@ -272,6 +272,8 @@ template <bool SP>
 DEV Spec<SP>& operator*=(Spec<SP>& a, float b) { a = a * b; return a; }
 template <bool SP>
 DEV Spec<SP>& operator+=(Spec<SP>& a, Spec<SP> b) { a = a + b; return a; }
+DEV Spec<true> operator-(Spec<true> a) { return {-a.v}; }
+DEV Spec<false> operator-(Spec<false> a) { return {-a.x, -a.y, -a.z}; }
 DEV Spec<true> spec_exp(Spec<true> a) { return {m_exp(a.v)}; }
 DEV Spec<false> spec_exp(Spec<false> a) { return {m_exp(a.x), m_exp(a.y), m_exp(a.z)}; }
 DEV Spec<true> spec_saturate(Spec<true> a) { return {saturatef(a.v)}; }

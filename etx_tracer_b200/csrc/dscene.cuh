@@ -50,6 +50,10 @@ struct DeviceScene {
   const uint8_t* bn_ranking;        // 128*128*8
   const DImage* images;
   uint32_t image_count;
+  const struct DMedium* mediums;
+  uint32_t medium_count;
+  uint32_t spectrum_count;
+  uint32_t has_boundaries;  // some material is of class Boundary (shadow rays may cross medium interfaces)
   uint32_t emitter_count;
   uint32_t triangle_count;
   float emitter_total_weight;

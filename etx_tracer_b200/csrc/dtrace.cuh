@@ -72,34 +72,82 @@ DEV HitRec trace_closest(const DeviceScene& sc, V3 o, V3 d, float tmin, float tm
   return vis.best;
 }
 
+struct Crossing {
+  uint32_t primitive_id;
+  float u, v, t;
+};
+constexpr uint32_t kCrossingBufferSize = 63;  // rt.cxx:472
+
 struct ShadowVisitor {
   const DeviceScene& sc;
   Smp& smp;
+  Crossing* crossings;
+  uint32_t crossing_count;
   bool occluded;
   DEV int operator()(uint32_t triangle_index, float u, float v, float t) {
     const etxb_material& mat = sc.materials[load_triangle_material(sc, triangle_index)];
     if (mat.cls == ETXB_MAT_VOID) return kCandIgnore;
     if (alpha_test_rejects(sc, mat, triangle_index, u, v, smp)) return kCandIgnore;
-    // Boundary materials (participating media interfaces) are not on the device yet: upload rejects them,
-    // so any surviving candidate occludes (rt.cxx:505-509)
-    occluded = true;
-    return kCandTerminate;
+    if ((mat.cls != ETXB_MAT_BOUNDARY) || (crossing_count + 1u >= kCrossingBufferSize)) {
+      occluded = true;
+      return kCandTerminate;
+    }
+    crossings[crossing_count++] = {triangle_index, u, v, t};
+    return kCandIgnore;
   }
 };
 
-// Returns transmittance 1 or 0 between p0 and p1 (no media on the device yet).
-DEV float trace_transmittance(const DeviceScene& sc, V3 p0, V3 p1, Smp& smp, TraverseStats* stats) {
+}  // namespace etxb
+#include "dmedium.cuh"
+namespace etxb {
+
+// Raytracing::trace_transmittance (rt.cxx:468-579): occluded unless every hit is a Boundary; the (<= 63) boundary crossings are
+// sorted by t and the per-segment medium transmittance is multiplied in.
+template <bool SP>
+DEV Spec<SP> trace_transmittance(const DeviceScene& sc, float wavelength, V3 p0, V3 p1, uint32_t medium_index, Smp& smp, TraverseStats* stats) {
   V3 direction = p1 - p0;
   float t_max = dot(direction, direction);
-  if (t_max <= kRayEpsilon) return 1.0f;
+  if (t_max <= kRayEpsilon) return Spec<SP>::make(1.0f);
   t_max = sqrtf(t_max);
   direction /= t_max;
   t_max -= fmaxf(kRayEpsilon, t_max * kRayEpsilon);
-  ShadowVisitor vis{sc, smp, false};
+  Crossing crossings[kCrossingBufferSize + 1u];
+  ShadowVisitor vis{sc, smp, crossings, 0u, false};
   DevNodeLoad nl{sc.bvh_nodes};
   DevTriLoad tl{sc.bvh_tris};
   traverse(nl, tl, p0.x, p0.y, p0.z, direction.x, direction.y, direction.z, kRayEpsilon, t_max, vis, stats);
-  return vis.occluded ? 0.0f : 1.0f;
+  if (vis.occluded) return Spec<SP>::make(0.0f);
+  if ((vis.crossing_count == 0u) && (medium_index == kInvalidIndex)) return Spec<SP>::make(1.0f);
+  uint32_t n = vis.crossing_count;
+  for (uint32_t i = 0; i < n; ++i) {
+    for (uint32_t j = i + 1; j < n; ++j) {
+      if (crossings[i].t > crossings[j].t) {
+        Crossing tmp = crossings[i];
+        crossings[i] = crossings[j];
+        crossings[j] = tmp;
+      }
+    }
+  }
+  crossings[n++] = {kInvalidIndex, 0.0f, 0.0f, t_max};
+  float current_t = 0.0f;
+  V3 origin = p0;
+  Spec<SP> result = Spec<SP>::make(1.0f);
+  uint32_t current_medium = medium_index;
+  for (uint32_t i = 0; i < n; ++i) {
+    const Crossing c = crossings[i];
+    if (current_medium != kInvalidIndex) {
+      float dt = fmaxf(0.0f, c.t - current_t);
+      result *= medium_transmittance<SP>(sc, sc.mediums[current_medium], wavelength, smp, origin, direction, dt);
+    }
+    if (c.primitive_id == kInvalidIndex) break;
+    TriRec tri = load_triangle(sc, c.primitive_id);
+    const etxb_material& mat = sc.materials[tri.material_index];
+    const bool entering = dot(tri.geo_n, direction) < 0.0f;
+    current_medium = entering ? mat.int_medium : mat.ext_medium;
+    current_t = c.t;
+    origin = lerp_pos(sc, tri, barycentrics_uv(c.u, c.v));
+  }
+  return result;
 }
 
 }  // namespace etxb

@@ -490,6 +490,20 @@ DEV LightVertexRec make_light_vertex(const PathState<SP>& s, const Isect& i, uin
   return r;
 }
 
+// medium light vertex (vcm_shared.hxx:1110-1127): no triangle / material, position = the sampled medium point
+template <bool SP>
+DEV LightVertexRec make_medium_light_vertex(const PathState<SP>& s, V3 pos, uint32_t path_index) {
+  LightVertexRec r;
+  V3 t = s.throughput.as_v3();
+  r.thr_dvcm = make_float4(t.x, t.y, t.z, s.d_vcm);
+  r.wi_dvc = make_float4(s.ray_d.x, s.ray_d.y, s.ray_d.z, s.d_vc);
+  r.bc_dvm = make_float4(0.0f, 0.0f, 0.0f, s.d_vm);
+  r.pos_tri = make_float4(pos.x, pos.y, pos.z, __uint_as_float(kInvalidIndex));
+  r.nrm_mat = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(kInvalidIndex));
+  r.ids = make_uint4(s.medium_index, s.total_path_depth, path_index, s.lv_count);
+  return r;
+}
+
 // ---- shared step pieces ------------------------------------------------------------------------------------------------
 // vcm_next_ray (vcm_shared.hxx:218-283)
 template <bool SP>
@@ -527,39 +541,90 @@ DEV bool vcm_next_ray(const DeviceScene& sc, bool light_path, PathState<SP>& sta
   return true;
 }
 
-// vcm_connect_to_camera (vcm_shared.hxx:463-535), surface vertices
+// A connection endpoint on the eye/light subpath: a surface point (isect) or a medium scattering point (pos only).
+struct Endpoint {
+  bool at_medium;
+  const Isect* isect;
+  V3 medium_pos;
+  DEV V3 pos() const { return at_medium ? medium_pos : isect->pos; }
+};
+DEV float medium_phase(const DeviceScene& sc, uint32_t medium_index, V3 w_i, V3 w_o) { return phase_function(w_i, w_o, sc.mediums[medium_index].phase_function_g); }
+
+// vcm_try_sampling_medium (vcm_shared.hxx:379-388)
 template <bool SP>
-DEV bool vcm_connect_to_camera(const DeviceScene& sc, const VcmParams& it, const Isect& isect, PathState<SP>& state, Spec<SP>& out_value, V2& uv, TraverseStats* stats,
+DEV MediumSample<SP> vcm_try_sampling_medium(const DeviceScene& sc, PathState<SP>& state, float max_t) {
+  MediumSample<SP> r;
+  r.weight = Spec<SP>::make(0.0f);
+  r.pos = {0.0f, 0.0f, 0.0f};
+  r.sampled_medium_t = 0.0f;
+  if (state.medium_index == kInvalidIndex) return r;
+  r = sample_medium<SP>(sc, sc.mediums[state.medium_index], state.wavelength, state.throughput, state.sampler, state.ray_o, state.ray_d, max_t);
+  state.throughput *= r.weight;
+  return r;
+}
+
+// vcm_handle_boundary_bsdf (vcm_shared.hxx:436-449)
+template <bool SP>
+DEV bool vcm_handle_boundary(const DeviceScene& sc, const Isect& isect, PathState<SP>& state) {
+  const etxb_material& mat = sc.materials[isect.material_index];
+  if (mat.cls != ETXB_MAT_BOUNDARY) return false;
+  TriRec tri = load_triangle(sc, isect.triangle_index);
+  uint32_t new_medium = (dot(tri.geo_n, state.ray_d) < 0.0f) ? mat.int_medium : mat.ext_medium;
+  state.path_distance += isect.t;
+  state.medium_index = new_medium;
+  state.ray_o = shading_pos(sc, tri, isect.barycentric, state.ray_d);
+  state.ray_max_t = kMaxFloat;
+  state.ray_min_t = kRayEpsilon;
+  return true;
+}
+
+// vcm_connect_to_camera (vcm_shared.hxx:463-535)
+template <bool SP>
+DEV bool vcm_connect_to_camera(const DeviceScene& sc, const VcmParams& it, const Endpoint& ep, PathState<SP>& state, Spec<SP>& out_value, V2& uv, TraverseStats* stats,
   uint32_t& shadow_rays) {
   if ((it.connect_to_camera() == false) || (state.total_path_depth + 2 > sc.max_path_length) || (state.total_path_depth + 2 < sc.min_path_length)) return false;
   const etxb_camera& camera = sc.camera;
-  V3 sample_pos = isect.pos;
+  V3 sample_pos = ep.pos();
   CameraSample cs = sample_film(state.sampler, camera, sample_pos);
   if (cs.pdf_dir <= 0.0f) return false;
   V3 direction = cs.position - sample_pos;
   float dist2 = dot(direction, direction);
   if (dist2 <= kEpsilon) return false;
   V3 w_o = normalize(direction);
-  const etxb_material& mat = sc.materials[isect.material_index];
-  BData data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathLight);
-  BEval<SP> eval = bsdf_evaluate<SP>(sc, data, w_o, mat, state.sampler);
-  if (eval.valid() == false) return false;
-  Spec<SP> scatter = eval.bsdf;
-  float reverse_pdf = bsdf_reverse_pdf<SP>(sc, data, w_o, mat, state.sampler);
-  TriRec tri = load_triangle(sc, isect.triangle_index);
-  V3 origin = shading_pos(sc, tri, isect.barycentric, w_o);
+  Spec<SP> scatter = Spec<SP>::make(0.0f);
+  float reverse_pdf = 0.0f;
+  V3 origin = sample_pos;
+  if (ep.at_medium == false) {
+    const Isect& isect = *ep.isect;
+    const etxb_material& mat = sc.materials[isect.material_index];
+    BData data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathLight);
+    BEval<SP> eval = bsdf_evaluate<SP>(sc, data, w_o, mat, state.sampler);
+    if (eval.valid() == false) return false;
+    scatter = eval.bsdf;
+    reverse_pdf = bsdf_reverse_pdf<SP>(sc, data, w_o, mat, state.sampler);
+    origin = shading_pos(sc, load_triangle(sc, isect.triangle_index), isect.barycentric, w_o);
+  } else {
+    float p = medium_phase(sc, state.medium_index, state.ray_d, w_o);
+    if (p <= 0.0f) return false;
+    scatter = Spec<SP>::make(p);
+    reverse_pdf = medium_phase(sc, state.medium_index, w_o, state.ray_d);
+  }
   float len = length(cs.position - origin);
   float cos_t = fabsf(dot(cs.direction, cam3(camera.direction)));
   V3 clip_pos = origin + cs.direction * fmaxf(0.0f, len - camera.clip_near / cos_t);
   shadow_rays += 1;
-  float tr = trace_transmittance(sc, origin, clip_pos, state.sampler, stats);
-  if (tr <= kEpsilon) return false;  // tr.is_zero()
+  Spec<SP> tr = trace_transmittance<SP>(sc, state.wavelength, origin, clip_pos, state.medium_index, state.sampler, stats);
+  if (tr.is_zero()) return false;
   uv = cs.uv;
-  float camera_pdf = cs.pdf_dir_out * fabsf(dot(isect.nrm, w_o)) / dist2;
-  float w_light = camera_pdf * (it.vm_weight + state.d_vcm + state.d_vc * reverse_pdf);
+  float camera_pdf = cs.pdf_dir_out * (ep.at_medium ? 1.0f : fabsf(dot(ep.isect->nrm, w_o))) / dist2;
+  float vmW_cam = ep.at_medium ? 0.0f : it.vm_weight;
+  float w_light = camera_pdf * (vmW_cam + state.d_vcm + state.d_vc * reverse_pdf);
   float weight = it.enable_mis() ? (1.0f / (1.0f + w_light)) : 1.0f;
-  weight *= fix_shading_normal(tri.geo_n, isect.nrm, isect.w_i, w_o);
-  out_value = Spec<SP>::make(tr) * scatter * state.throughput * cs.weight * weight;
+  if (ep.at_medium == false) {
+    const Isect& isect = *ep.isect;
+    weight *= fix_shading_normal(load_triangle(sc, isect.triangle_index).geo_n, isect.nrm, isect.w_i, w_o);
+  }
+  out_value = tr * scatter * state.throughput * cs.weight * weight;
   return true;
 }
 
@@ -579,75 +644,126 @@ DEV void vcm_handle_direct_hit(const DeviceScene& sc, const VcmParams& it, const
   state.gathered += weight * (state.throughput * radiance);
 }
 
-// vcm_connect_to_light (vcm_shared.hxx:608-671), surface vertices
+// vcm_connect_to_light (vcm_shared.hxx:608-671)
 template <bool SP>
-DEV Spec<SP> vcm_connect_to_light(const DeviceScene& sc, const VcmParams& it, const Isect& isect, PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays) {
+DEV Spec<SP> vcm_connect_to_light(const DeviceScene& sc, const VcmParams& it, const Endpoint& ep, PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays) {
   Spec<SP> zero = Spec<SP>::make(0.0f);
   if ((it.connect_to_light() == false) || (state.total_path_depth + 1 > sc.max_path_length) || (state.total_path_depth + 1 < sc.min_path_length)) return zero;
-  V3 sample_pos = isect.pos;
+  V3 sample_pos = ep.pos();
   uint32_t emitter_index = distribution_sample(sc.emitter_dist, sc.emitter_count + 1u, state.sampler.fixed_w);
   EmitterSample<SP> es = sample_emitter<SP>(sc, state.wavelength, emitter_index, {state.sampler.fixed_u, state.sampler.fixed_v}, sample_pos);
   if (es.pdf_dir <= 0.0f) return zero;
   V3 w_o = es.direction;
-  const etxb_material& mat = sc.materials[isect.material_index];
-  BData data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
-  BEval<SP> eval = bsdf_evaluate<SP>(sc, data, w_o, mat, state.sampler);
-  if (eval.valid() == false) return zero;
-  Spec<SP> scatter = eval.bsdf;
-  float reverse_pdf = bsdf_reverse_pdf<SP>(sc, data, w_o, mat, state.sampler);
-  TriRec tri = load_triangle(sc, isect.triangle_index);
-  V3 origin = shading_pos(sc, tri, isect.barycentric, normalize(es.origin - isect.pos));
-  float camera_factor = fabsf(dot(w_o, tri.geo_n));
+  Spec<SP> scatter = zero;
+  float reverse_pdf = 0.0f;
+  V3 origin = sample_pos;
+  float camera_factor = 1.0f;
+  if (ep.at_medium) {
+    float p = medium_phase(sc, state.medium_index, state.ray_d, w_o);
+    if (p <= 0.0f) return zero;
+    scatter = Spec<SP>::make(p);
+    reverse_pdf = medium_phase(sc, state.medium_index, w_o, state.ray_d);
+  } else {
+    const Isect& isect = *ep.isect;
+    const etxb_material& mat = sc.materials[isect.material_index];
+    BData data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
+    BEval<SP> eval = bsdf_evaluate<SP>(sc, data, w_o, mat, state.sampler);
+    if (eval.valid() == false) return zero;
+    scatter = eval.bsdf;
+    reverse_pdf = bsdf_reverse_pdf<SP>(sc, data, w_o, mat, state.sampler);
+    TriRec tri = load_triangle(sc, isect.triangle_index);
+    origin = shading_pos(sc, tri, isect.barycentric, normalize(es.origin - isect.pos));
+    camera_factor = fabsf(dot(w_o, tri.geo_n));
+  }
   shadow_rays += 1;
-  float tr = trace_transmittance(sc, origin, es.origin, state.sampler, stats);
-  if (tr <= kEpsilon) return zero;
+  Spec<SP> tr = trace_transmittance<SP>(sc, state.wavelength, origin, es.origin, state.medium_index, state.sampler, stats);
+  if (tr.is_zero()) return zero;
   float l_dot_e = fabsf(dot(es.direction, es.normal));
   float w_light = 0.0f;
   if (es.is_delta == false) {
-    float conn_pdf = bsdf_pdf<SP>(sc, data, w_o, mat, state.sampler);
-    w_light = conn_pdf / (es.pdf_dir * es.pdf_sample);
+    if (ep.at_medium) {
+      w_light = scatter.component(0) / (es.pdf_dir * es.pdf_sample);  // SpectralResponse{spect, p}.value
+    } else {
+      const Isect& isect = *ep.isect;
+      BData data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
+      float conn_pdf = bsdf_pdf<SP>(sc, data, w_o, sc.materials[isect.material_index], state.sampler);
+      w_light = conn_pdf / (es.pdf_dir * es.pdf_sample);
+    }
   }
-  float w_camera = (es.pdf_dir_out * camera_factor) / (es.pdf_dir * l_dot_e) * (it.vm_weight + state.d_vcm + state.d_vc * reverse_pdf);
+  float vmW_nee = ep.at_medium ? 0.0f : it.vm_weight;
+  float w_camera = (es.pdf_dir_out * camera_factor) / (es.pdf_dir * l_dot_e) * (vmW_nee + state.d_vcm + state.d_vc * reverse_pdf);
   float weight = it.enable_mis() ? 1.0f / (1.0f + w_light + w_camera) : 1.0f;
-  return Spec<SP>::make(tr) * state.throughput * scatter * es.value * (weight / (es.pdf_dir * es.pdf_sample));
+  return tr * state.throughput * scatter * es.value * (weight / (es.pdf_dir * es.pdf_sample));
 }
 
-// vcm_connect_to_light_vertex (vcm_shared.hxx:673-763), surface-surface
+// vcm_connect_to_light_vertex (vcm_shared.hxx:673-763)
 template <bool SP>
-DEV bool vcm_connect_to_light_vertex(const DeviceScene& sc, const VcmParams& it, PathState<SP>& state, const LightVertexRec& lv, const Isect& cam, V3& target_position,
+DEV bool vcm_connect_to_light_vertex(const DeviceScene& sc, const VcmParams& it, PathState<SP>& state, const LightVertexRec& lv, const Endpoint& ep, V3& target_position,
   Spec<SP>& value) {
-  uint32_t lv_tri = __float_as_uint(lv.pos_tri.w);
-  uint32_t lv_mat = __float_as_uint(lv.nrm_mat.w);
-  TriRec light_tri = load_triangle(sc, lv_tri);
-  Isect light_v;  // VCMLightVertex::vertex(): lerp_vertex from (triangle, barycentric)
-  V3 bc = {lv.bc_dvm.x, lv.bc_dvm.y, lv.bc_dvm.z};
-  lerp_vertex(sc, light_tri, bc, light_v.pos, light_v.nrm, light_v.tan, light_v.btn, light_v.tex);
-  target_position = light_v.pos;
-  V3 w_o = target_position - cam.pos;
+  const uint32_t lv_tri = __float_as_uint(lv.pos_tri.w);
+  const bool lv_is_medium = lv_tri == kInvalidIndex;
+  const V3 lv_wi = {lv.wi_dvc.x, lv.wi_dvc.y, lv.wi_dvc.z};
+  Isect light_v = {};  // VCMLightVertex::vertex(): lerp_vertex from (triangle, barycentric)
+  TriRec light_tri = {};
+  if (lv_is_medium == false) {
+    light_tri = load_triangle(sc, lv_tri);
+    V3 bc = {lv.bc_dvm.x, lv.bc_dvm.y, lv.bc_dvm.z};
+    lerp_vertex(sc, light_tri, bc, light_v.pos, light_v.nrm, light_v.tan, light_v.btn, light_v.tex);
+  }
+  target_position = lv_is_medium ? V3{lv.pos_tri.x, lv.pos_tri.y, lv.pos_tri.z} : light_v.pos;
+  V3 w_o = target_position - ep.pos();
   float distance_squared = dot(w_o, w_o);
   if (distance_squared <= kEpsilon) return false;
   w_o /= sqrtf(distance_squared);
-  float w_dot_l = -dot(light_v.nrm, w_o);
+  float w_dot_l = 1.0f;
+  if (lv_is_medium == false) w_dot_l = -dot(light_v.nrm, w_o);
 
-  const etxb_material& mat = sc.materials[cam.material_index];
-  BData camera_data = make_bdata(cam, cam.w_i, state.wavelength, state.medium_index, kPathCamera);
-  BEval<SP> camera_bsdf = bsdf_evaluate<SP>(sc, camera_data, w_o, mat, state.sampler);
-  if (camera_bsdf.valid() == false) return false;
-  float camera_area_pdf = camera_bsdf.pdf * fabsf(w_dot_l) / distance_squared;
-  float camera_rev_pdf = bsdf_reverse_pdf<SP>(sc, camera_data, w_o, mat, state.sampler);
-  Spec<SP> camera_scatter = camera_bsdf.bsdf;
+  float camera_area_pdf = 0.0f, camera_rev_pdf = 0.0f;
+  Spec<SP> camera_scatter = Spec<SP>::make(0.0f);
+  const uint32_t state_medium = state.medium_index;
+  if (ep.at_medium) {
+    float p = medium_phase(sc, state_medium, state.ray_d, w_o);
+    if (p <= 0.0f) return false;
+    float p_rev = medium_phase(sc, state_medium, w_o, state.ray_d);
+    camera_area_pdf = p * fabsf(w_dot_l) / distance_squared;
+    camera_rev_pdf = p_rev;
+    camera_scatter = Spec<SP>::make(p);
+  } else {
+    const Isect& cam = *ep.isect;
+    const etxb_material& mat = sc.materials[cam.material_index];
+    BData camera_data = make_bdata(cam, cam.w_i, state.wavelength, state_medium, kPathCamera);
+    BEval<SP> camera_bsdf = bsdf_evaluate<SP>(sc, camera_data, w_o, mat, state.sampler);
+    if (camera_bsdf.valid() == false) return false;
+    camera_area_pdf = camera_bsdf.pdf * fabsf(w_dot_l) / distance_squared;
+    camera_rev_pdf = bsdf_reverse_pdf<SP>(sc, camera_data, w_o, mat, state.sampler);
+    camera_scatter = camera_bsdf.bsdf;
+  }
 
-  const etxb_material& light_mat = sc.materials[lv_mat];
-  V3 lv_wi = {lv.wi_dvc.x, lv.wi_dvc.y, lv.wi_dvc.z};
-  BData light_data = {light_v.pos, light_v.nrm, light_v.tan, light_v.btn, light_v.tex, lv_wi, state.wavelength, kPathLight, state.medium_index};
-  BEval<SP> light_bsdf = bsdf_evaluate<SP>(sc, light_data, -w_o, light_mat, state.sampler);
-  if (light_bsdf.valid() == false) return false;
-  float w_dot_c = dot(cam.nrm, w_o);
-  float light_area_pdf = light_bsdf.pdf * fabsf(w_dot_c) / distance_squared;
-  float light_rev_pdf = bsdf_reverse_pdf<SP>(sc, light_data, -w_o, light_mat, state.sampler);
-  Spec<SP> light_scatter = light_bsdf.bsdf * fix_shading_normal(light_tri.geo_n, light_data.nrm, light_data.w_i, -w_o);
+  float light_area_pdf = 0.0f, light_rev_pdf = 0.0f;
+  Spec<SP> light_scatter = Spec<SP>::make(0.0f);
+  if (lv_is_medium) {
+    float p = medium_phase(sc, lv.ids.x, lv_wi, -w_o);
+    if (p <= 0.0f) return false;
+    float p_rev = medium_phase(sc, lv.ids.x, -w_o, lv_wi);
+    light_area_pdf = p * (ep.at_medium ? 1.0f : fabsf(dot(ep.isect->nrm, w_o))) / distance_squared;
+    light_rev_pdf = p_rev;
+    light_scatter = Spec<SP>::make(p);
+  } else {
+    const etxb_material& light_mat = sc.materials[__float_as_uint(lv.nrm_mat.w)];
+    BData light_data = {light_v.pos, light_v.nrm, light_v.tan, light_v.btn, light_v.tex, lv_wi, state.wavelength, kPathLight, ep.at_medium ? lv.ids.x : state_medium};
+    BEval<SP> light_bsdf = bsdf_evaluate<SP>(sc, light_data, -w_o, light_mat, state.sampler);
+    if (light_bsdf.valid() == false) return false;
+    if (ep.at_medium) {
+      light_area_pdf = light_bsdf.pdf / distance_squared;
+    } else {
+      float w_dot_c = dot(ep.isect->nrm, w_o);
+      light_area_pdf = light_bsdf.pdf * fabsf(w_dot_c) / distance_squared;
+    }
+    light_rev_pdf = bsdf_reverse_pdf<SP>(sc, light_data, -w_o, light_mat, state.sampler);
+    light_scatter = light_bsdf.bsdf * fix_shading_normal(light_tri.geo_n, light_data.nrm, light_data.w_i, -w_o);
+  }
 
-  float vmW_pair = it.vm_weight;
+  float vmW_pair = (ep.at_medium || lv_is_medium) ? 0.0f : it.vm_weight;
   float w_light = camera_area_pdf * (vmW_pair + lv.thr_dvcm.w + lv.wi_dvc.w * light_rev_pdf);
   float w_camera = light_area_pdf * (vmW_pair + state.d_vcm + state.d_vc * camera_rev_pdf);
   float weight = it.enable_mis() ? 1.0f / (1.0f + w_light + w_camera) : 1.0f;
@@ -656,9 +772,32 @@ DEV bool vcm_connect_to_light_vertex(const DeviceScene& sc, const VcmParams& it,
   return true;
 }
 
+DEV LightVertexRec load_light_vertex(const LightVertexRec* p_rec) {
+  const float4* p = reinterpret_cast<const float4*>(p_rec);
+  LightVertexRec lv;
+  lv.thr_dvcm = __ldg(p + 0);
+  lv.wi_dvc = __ldg(p + 1);
+  lv.bc_dvm = __ldg(p + 2);
+  lv.pos_tri = __ldg(p + 3);
+  lv.nrm_mat = __ldg(p + 4);
+  lv.ids = __ldg(reinterpret_cast<const uint4*>(p) + 5);
+  return lv;
+}
+
+// the shadow segment of one vertex connection (vcm_shared.hxx:784-799)
+template <bool SP>
+DEV Spec<SP> vcm_connection_transmittance(const DeviceScene& sc, const Endpoint& ep, const LightVertexRec& lv, V3 target_position, PathState<SP>& state, TraverseStats* stats) {
+  if (ep.at_medium) {
+    return trace_transmittance<SP>(sc, state.wavelength, ep.medium_pos, {lv.pos_tri.x, lv.pos_tri.y, lv.pos_tri.z}, state.medium_index, state.sampler, stats);
+  }
+  const Isect& isect = *ep.isect;
+  V3 p0 = shading_pos(sc, load_triangle(sc, isect.triangle_index), isect.barycentric, normalize(target_position - isect.pos));
+  return trace_transmittance<SP>(sc, state.wavelength, p0, target_position, state.medium_index, state.sampler, stats);
+}
+
 // vcm_connect_to_light_path (vcm_shared.hxx:765-803): serial over the paired path's vertices (shared sampler)
 template <bool SP>
-DEV Spec<SP> vcm_connect_to_light_path(const DeviceScene& sc, const VcmParams& it, const LightVertexRec* pool, uint32_t lp_index, uint32_t lp_count, const Isect& isect,
+DEV Spec<SP> vcm_connect_to_light_path(const DeviceScene& sc, const VcmParams& it, const LightVertexRec* pool, uint32_t lp_index, uint32_t lp_count, const Endpoint& ep,
   PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays, uint32_t& connections) {
   Spec<SP> result = Spec<SP>::make(0.0f);
   if (it.connect_vertices() == false) return result;
@@ -666,23 +805,15 @@ DEV Spec<SP> vcm_connect_to_light_path(const DeviceScene& sc, const VcmParams& i
     const uint64_t target_path_length = uint64_t(state.total_path_depth) + i + 2u;
     if (target_path_length < sc.min_path_length) continue;
     if (target_path_length > sc.max_path_length) break;
-    const float4* p = reinterpret_cast<const float4*>(pool + lp_index + i);
-    LightVertexRec lv;
-    lv.thr_dvcm = __ldg(p + 0);
-    lv.wi_dvc = __ldg(p + 1);
-    lv.bc_dvm = __ldg(p + 2);
-    lv.pos_tri = __ldg(p + 3);
-    lv.nrm_mat = __ldg(p + 4);
+    LightVertexRec lv = load_light_vertex(pool + lp_index + i);
     connections += 1;
     V3 target_position;
     Spec<SP> value;
-    if (vcm_connect_to_light_vertex<SP>(sc, it, state, lv, isect, target_position, value)) {
-      TriRec tri = load_triangle(sc, isect.triangle_index);
-      V3 p0 = shading_pos(sc, tri, isect.barycentric, normalize(target_position - isect.pos));
+    if (vcm_connect_to_light_vertex<SP>(sc, it, state, lv, ep, target_position, value)) {
       shadow_rays += 1;
-      float tr = trace_transmittance(sc, p0, target_position, state.sampler, stats);
-      if (tr > kEpsilon) {
-        result += Spec<SP>::make(tr) * value;
+      Spec<SP> tr = vcm_connection_transmittance<SP>(sc, ep, lv, target_position, state, stats);
+      if (tr.is_zero() == false) {
+        result += tr * value;
       }
     }
   }

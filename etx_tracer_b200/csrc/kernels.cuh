@@ -183,7 +183,41 @@ __global__ void __launch_bounds__(256) k_trace_closest(LaunchParams p, const uin
   counter_add(&p.counters->tris, STATS_TRIS);
 }
 
-// vcm_light_step after the trace (vcm_shared.hxx:1090-1260), surface events
+// Film::atomic_add_light_iteration (film.cxx:147-171) of one light-tracing contribution (vcm_cpu.cxx:147-154)
+template <bool SP>
+DEV uint32_t splat_light(const LaunchParams& p, Spec<SP> value, V2 uv, float wavelength) {
+  V3 val = spec_to_rgb<SP>(p.scene, value, wavelength) / sampling_pdf<SP>(wavelength);
+  if (!(dot(val, val) > kEpsilon)) return 0u;
+  V2 uv01 = uv * 0.5f + 0.5f;
+  uint32_t x = static_cast<uint32_t>(uv01.x * float(p.film.width));
+  uint32_t y = static_cast<uint32_t>(uv01.y * float(p.film.height));
+  if ((x < p.film.width) && (y < p.film.height)) {
+    float* dst = reinterpret_cast<float*>(p.film.light_iteration + (x + (p.film.height - 1u - y) * p.film.width));
+    atomicAdd(dst + 0, val.x);
+    atomicAdd(dst + 1, val.y);
+    atomicAdd(dst + 2, val.z);
+  }
+  return 1u;
+}
+
+// store one light vertex in allocation order (k_lv_reorder makes the pool path-major)
+DEV bool store_light_vertex(const LaunchParams& p, const LightVertexRec& rec) {
+  uint32_t slot = atomicAdd(p.lv_tmp_count, 1u);
+  if (slot >= p.lv_capacity) {
+    *p.overflow = 1u;
+    return false;
+  }
+  float4* dst = reinterpret_cast<float4*>(p.lv_tmp + slot);
+  dst[0] = rec.thr_dvcm;
+  dst[1] = rec.wi_dvc;
+  dst[2] = rec.bc_dvm;
+  dst[3] = rec.pos_tri;
+  dst[4] = rec.nrm_mat;
+  reinterpret_cast<uint4*>(dst)[5] = rec.ids;
+  return true;
+}
+
+// vcm_light_step after the trace (vcm_shared.hxx:1090-1260): medium events, boundary crossings, surface events
 template <bool SP>
 __global__ void __launch_bounds__(128) k_light_bounce(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,70 +232,87 @@ __global__ void __launch_bounds__(128) k_light_bounce(LaunchParams p, const uint
     state.lv_count = p.paths.lv_count[i];
     float4 hit = p.paths.hit[i];
     uint32_t tri_index = __float_as_uint(hit.w);
-    if (tri_index != kInvalidIndex) {
-      Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
-      const etxb_material& mat = sc.materials[isect.material_index];
-      BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathLight);
+    const bool found = tri_index != kInvalidIndex;
+    MediumSample<SP> medium_sample = vcm_try_sampling_medium<SP>(sc, state, found ? hit.z : kMaxFloat);
+    if (medium_sample.sampled_medium()) {
+      // :1097-1170
       V2 rnd_bsdf = state.sampler.next_2d();
       V2 rnd_connection = state.sampler.next_2d();
       V2 rnd_support = state.sampler.next_2d();
-      state.sampler.push_fixed(rnd_bsdf.x, rnd_bsdf.y, rnd_support.x);
-      BSample<SP> bs = bsdf_sample<SP>(sc, bsdf_data, mat, state.sampler);
-      bool is_connectible = (bs.properties & kBsdfDelta) == 0;
-      state.sampler.pop_fixed();
-      // vcm_update_light_vcm (:451-461)
-      if ((state.total_path_depth > 0) || (state.flags & kPathLocalEmitter)) {
-        state.d_vcm *= sqr(state.path_distance + isect.t);
-      }
-      float cos_to_prev = fabsf(dot(isect.nrm, -state.ray_d));
-      state.d_vcm /= cos_to_prev;
-      state.d_vc /= cos_to_prev;
-      state.d_vm /= cos_to_prev;
+      float seg = state.path_distance + medium_sample.sampled_medium_t;
+      state.d_vcm *= sqr(seg);
       state.path_distance = 0.0f;
-
-      if (is_connectible) {
-        // store the light vertex (warp-aggregated slot allocation; k_lv_reorder makes the pool path-major)
-        uint32_t slot = atomicAdd(p.lv_tmp_count, 1u);
-        if (slot < p.lv_capacity) {
-          LightVertexRec rec = make_light_vertex<SP>(state, isect, i);
-          float4* dst = reinterpret_cast<float4*>(p.lv_tmp + slot);
-          dst[0] = rec.thr_dvcm;
-          dst[1] = rec.wi_dvc;
-          dst[2] = rec.bc_dvm;
-          dst[3] = rec.pos_tri;
-          dst[4] = rec.nrm_mat;
-          reinterpret_cast<uint4*>(dst)[5] = rec.ids;
+      const DMedium& med = sc.mediums[state.medium_index];
+      if (p.vcm.connect_vertices() && (state.total_path_depth + 1 <= sc.max_path_length)) {
+        if (store_light_vertex(p, make_medium_light_vertex<SP>(state, medium_sample.pos, i))) {
           state.lv_count += 1;
           stored = 1;
-        } else {
-          *p.overflow = 1u;
-        }
-        if (p.vcm.connect_to_camera() && (state.total_path_depth + 1 <= sc.max_path_length)) {
-          state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
-          Spec<SP> value;
-          V2 uv;
-          bool ok = vcm_connect_to_camera<SP>(sc, p.vcm, isect, state, value, uv, stats, shadow_rays);
-          state.sampler.pop_fixed();
-          if (ok && (value.maximum() > kEpsilon)) {
-            // vcm_cpu.cxx:147-154 + Film::atomic_add_light_iteration (film.cxx:147-171)
-            V3 val = spec_to_rgb<SP>(sc, value, state.wavelength) / sampling_pdf<SP>(state.wavelength);
-            if (dot(val, val) > kEpsilon) {
-              V2 uv01 = uv * 0.5f + 0.5f;
-              uint32_t x = static_cast<uint32_t>(uv01.x * float(p.film.width));
-              uint32_t y = static_cast<uint32_t>(uv01.y * float(p.film.height));
-              if ((x < p.film.width) && (y < p.film.height)) {
-                float* dst = reinterpret_cast<float*>(p.film.light_iteration + (x + (p.film.height - 1u - y) * p.film.width));
-                atomicAdd(dst + 0, val.x);
-                atomicAdd(dst + 1, val.y);
-                atomicAdd(dst + 2, val.z);
-              }
-              splats = 1;
-            }
-          }
         }
       }
-      if (vcm_next_ray<SP>(sc, true, state, p.vcm, isect, bsdf_data, bs)) {
-        alive = state.total_path_depth + 1u < sc.max_path_length;
+      if (p.vcm.connect_to_camera() && med.enable_explicit_connections && (state.total_path_depth + 1 <= sc.max_path_length)) {
+        state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
+        Spec<SP> value;
+        V2 uv;
+        Endpoint ep{true, nullptr, medium_sample.pos};
+        bool ok = vcm_connect_to_camera<SP>(sc, p.vcm, ep, state, value, uv, stats, shadow_rays);
+        state.sampler.pop_fixed();
+        if (ok && (value.maximum() > kEpsilon)) splats += splat_light<SP>(p, value, uv, state.wavelength);
+      }
+      V3 w_i = state.ray_d;
+      V3 w_o_smp = sample_phase_function(w_i, med.phase_function_g, rnd_bsdf);
+      float pdf_fwd = phase_function(w_i, w_o_smp, med.phase_function_g);
+      float pdf_rev = phase_function(w_o_smp, w_i, med.phase_function_g);
+      state.d_vc = (1.0f / pdf_fwd) * (state.d_vc * pdf_rev + state.d_vcm);
+      state.d_vm = (1.0f / pdf_fwd) * (state.d_vm * pdf_rev + 0.0f);
+      state.d_vcm = 1.0f / pdf_fwd;
+      state.ray_o = medium_sample.pos;
+      state.ray_d = w_o_smp;
+      state.ray_max_t = kMaxFloat;
+      state.ray_min_t = kRayEpsilon;
+      state.total_path_depth += 1;
+      alive = (state.total_path_depth + 1 <= sc.max_path_length) &&
+              random_continue<SP>(state.total_path_depth, sc.random_path_termination, state.eta, state.sampler, state.throughput);
+    } else if (found) {
+      Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
+      if (vcm_handle_boundary<SP>(sc, isect, state)) {
+        alive = true;
+      } else {
+        const etxb_material& mat = sc.materials[isect.material_index];
+        BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathLight);
+        V2 rnd_bsdf = state.sampler.next_2d();
+        V2 rnd_connection = state.sampler.next_2d();
+        V2 rnd_support = state.sampler.next_2d();
+        state.sampler.push_fixed(rnd_bsdf.x, rnd_bsdf.y, rnd_support.x);
+        BSample<SP> bs = bsdf_sample<SP>(sc, bsdf_data, mat, state.sampler);
+        bool is_connectible = (bs.properties & kBsdfDelta) == 0;
+        state.sampler.pop_fixed();
+        // vcm_update_light_vcm (:451-461)
+        if ((state.total_path_depth > 0) || (state.flags & kPathLocalEmitter)) {
+          state.d_vcm *= sqr(state.path_distance + isect.t);
+        }
+        float cos_to_prev = fabsf(dot(isect.nrm, -state.ray_d));
+        state.d_vcm /= cos_to_prev;
+        state.d_vc /= cos_to_prev;
+        state.d_vm /= cos_to_prev;
+        state.path_distance = 0.0f;
+        if (is_connectible) {
+          if (store_light_vertex(p, make_light_vertex<SP>(state, isect, i))) {
+            state.lv_count += 1;
+            stored = 1;
+          }
+          if (p.vcm.connect_to_camera() && (state.total_path_depth + 1 <= sc.max_path_length)) {
+            state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
+            Spec<SP> value;
+            V2 uv;
+            Endpoint ep{false, &isect, {0.0f, 0.0f, 0.0f}};
+            bool ok = vcm_connect_to_camera<SP>(sc, p.vcm, ep, state, value, uv, stats, shadow_rays);
+            state.sampler.pop_fixed();
+            if (ok && (value.maximum() > kEpsilon)) splats += splat_light<SP>(p, value, uv, state.wavelength);
+          }
+        }
+        if (vcm_next_ray<SP>(sc, true, state, p.vcm, isect, bsdf_data, bs)) {
+          alive = state.total_path_depth + 1u < sc.max_path_length;
+        }
       }
     }
     p.paths.lv_count[i] = state.lv_count;
@@ -317,9 +368,11 @@ __global__ void __launch_bounds__(256) k_grid_bbox(const LightVertexRec* pool, u
   float mn[3] = {kMaxFloat, kMaxFloat, kMaxFloat}, mx[3] = {-kMaxFloat, -kMaxFloat, -kMaxFloat};
   if (s < count) {
     float4 pt = reinterpret_cast<const float4*>(pool + s)[3];
-    mn[0] = mx[0] = pt.x;
-    mn[1] = mx[1] = pt.y;
-    mn[2] = mx[2] = pt.z;
+    if (__float_as_uint(pt.w) != kInvalidIndex) {  // medium vertices are never merged (vcm_shared.cxx:70)
+      mn[0] = mx[0] = pt.x;
+      mn[1] = mx[1] = pt.y;
+      mn[2] = mx[2] = pt.z;
+    }
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -343,7 +396,7 @@ __global__ void __launch_bounds__(256) k_grid_keys(const LightVertexRec* pool, u
   if (s >= count) return;
   V3 bmin = {ordered_to_float(bbox[0]), ordered_to_float(bbox[1]), ordered_to_float(bbox[2])};
   float4 pt = reinterpret_cast<const float4*>(pool + s)[3];
-  keys[s] = grid_position_to_index({pt.x, pt.y, pt.z}, bmin, cell_size, mask);
+  keys[s] = (__float_as_uint(pt.w) == kInvalidIndex) ? 0xffffffffu : grid_position_to_index({pt.x, pt.y, pt.z}, bmin, cell_size, mask);
   values[s] = s;
 }
 
@@ -354,6 +407,7 @@ __global__ void __launch_bounds__(256) k_grid_build(LaunchParams p, const uint32
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= count) return;
   uint32_t key = sorted_keys[j];
+  if (key == 0xffffffffu) return;  // medium vertices sort to the end and stay out of the grid
   if ((j == 0) || (sorted_keys[j - 1] != key)) cell_range[key].x = j;
   if ((j + 1 == count) || (sorted_keys[j + 1] != key)) cell_range[key].y = j + 1;
   const float4* src = reinterpret_cast<const float4*>(p.lv_final + sorted_values[j]);
@@ -413,6 +467,39 @@ DEV uint32_t merge_query_key(const GridData& g, V3 pos) {
 //   continue : vcm_next_ray (RR, recurrences, next ray) or, when the path ends, the epilogue of gather_camera_vertices
 //              (vcm_cpu.cxx:195-198) + Film::accumulate_camera_image
 // The pending BSDF sample travels between stages in `bs_*` (40 B per path).
+// bs_props.x markers for bounces that do not end in a pending BSDF sample (medium scattering, boundary crossing)
+constexpr uint32_t kBounceResolvedAlive = 0x80000001u;
+constexpr uint32_t kBounceResolvedDead = 0x80000000u;
+
+// emit / run the camera-vertex x light-vertex connections of one endpoint
+template <bool SP>
+DEV void camera_vertex_connections(const LaunchParams& p, uint32_t i, const Endpoint& ep, PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays, uint32_t& connections) {
+  const DeviceScene& sc = p.scene;
+  if (!p.connect_stage) {
+    // reference order: serial over the paired path's vertices with the path's own sampler
+    state.gathered += vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], ep, state, stats, shadow_rays, connections);
+  } else if (p.vcm.connect_vertices()) {
+    // scenes with stochastic BSDFs (product build): the connections (vcm_shared.hxx:765-803) become their own wavefront stage,
+    // one thread per connection (k_camera_connect); here only the work list is emitted
+    uint32_t lp_count = p.paths.lv_count[i];
+    uint32_t d2 = state.total_path_depth + 2u;  // target_path_length = depth + k + 2 must lie in [min_path_length, max_path_length]
+    uint32_t k_begin = (sc.min_path_length > d2) ? (sc.min_path_length - d2) : 0u;
+    uint32_t k_end = (sc.max_path_length >= d2) ? umin(lp_count, sc.max_path_length - d2 + 1u) : 0u;
+    if (k_end > k_begin) {
+      uint32_t cnt = k_end - k_begin;
+      uint32_t base = atomicAdd(p.conn_count, cnt);
+      if (base + cnt <= p.conn_capacity) {
+        for (uint32_t k = 0; k < cnt; ++k) p.conn_list[base + k] = make_uint2(i, k_begin + k);
+      } else {
+        *p.overflow = 1u;
+      }
+      p.paths.conn_seed[i] = state.sampler.seed;
+      state.sampler.next();  // the path's own stream moves on by one draw for the whole stage
+      connections += cnt;
+    }
+  }
+}
+
 template <bool SP>
 __global__ void __launch_bounds__(128) k_camera_shade(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -427,12 +514,12 @@ __global__ void __launch_bounds__(128) k_camera_shade(LaunchParams p, const uint
     state.gathered = Spec<SP>::make3({g.x, g.y, g.z});
     float4 hit = p.paths.hit[i];
     uint32_t tri_index = __float_as_uint(hit.w);
-    if (tri_index == kInvalidIndex) {
-      vcm_cam_handle_miss<SP>(sc, p.vcm, state.ray_d, state.d_vcm, state.d_vc, state.path_distance, state.total_path_depth, state.wavelength, state.throughput, state.gathered);
-    } else {
-      Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
-      const etxb_material& mat = sc.materials[isect.material_index];
-      BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
+    const bool found = tri_index != kInvalidIndex;
+    uint2 resolved = make_uint2(kBounceResolvedDead, kInvalidIndex);
+    bool pending_sample = false;
+    MediumSample<SP> medium_sample = vcm_try_sampling_medium<SP>(sc, state, found ? hit.z : kMaxFloat);
+    if (medium_sample.sampled_medium()) {
+      // :934-995
       V2 rnd_bsdf = state.sampler.next_2d();
       V2 rnd_connection = state.sampler.next_2d();
       V2 rnd_support = state.sampler.next_2d();
@@ -442,54 +529,83 @@ __global__ void __launch_bounds__(128) k_camera_shade(LaunchParams p, const uint
         rnd_connection = sample_blue_noise(sc, px, py, p.vcm.iteration, 2);
         rnd_support = sample_blue_noise(sc, px, py, p.vcm.iteration, 4);
       }
-      state.sampler.push_fixed(rnd_bsdf.x, rnd_bsdf.y, rnd_support.x);
-      BSample<SP> bs = bsdf_sample<SP>(sc, bsdf_data, mat, state.sampler);
-      bool is_connectible = (bs.properties & kBsdfDelta) == 0;
-      state.sampler.pop_fixed();
-      // vcm_update_camera_vcm (:589-595)
-      float cos_to_prev = fabsf(dot(isect.nrm, -state.ray_d));
-      state.d_vcm *= sqr(state.path_distance + isect.t) / cos_to_prev;
-      state.d_vc /= cos_to_prev;
-      state.d_vm /= cos_to_prev;
+      float seg = state.path_distance + medium_sample.sampled_medium_t;
+      state.d_vcm *= sqr(seg);
       state.path_distance = 0.0f;
-      vcm_handle_direct_hit<SP>(sc, p.vcm, isect, state);
-      if (is_connectible) {
-        if (!p.connect_stage) {
-          // reference order: serial over the paired path's vertices with the path's own sampler
-          state.gathered += vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], isect, state, stats, shadow_rays, connections);
-        } else if (p.vcm.connect_vertices()) {
-          // scenes with stochastic BSDFs (product build): the camera-vertex x light-vertex connections (vcm_shared.hxx:765-803)
-          // become their own wavefront stage, one thread per connection (k_camera_connect); here only the work list is emitted
-          uint32_t lp_count = p.paths.lv_count[i];
-          // target_path_length = depth + k + 2 must lie in [min_path_length, max_path_length]
-          uint32_t d2 = state.total_path_depth + 2u;
-          uint32_t k_begin = (sc.min_path_length > d2) ? (sc.min_path_length - d2) : 0u;
-          uint32_t k_end = (sc.max_path_length >= d2) ? umin(lp_count, sc.max_path_length - d2 + 1u) : 0u;
-          if (k_end > k_begin) {
-            uint32_t cnt = k_end - k_begin;
-            uint32_t base = atomicAdd(p.conn_count, cnt);
-            if (base + cnt <= p.conn_capacity) {
-              for (uint32_t k = 0; k < cnt; ++k) p.conn_list[base + k] = make_uint2(i, k_begin + k);
-            } else {
-              *p.overflow = 1u;
-            }
-            p.paths.conn_seed[i] = state.sampler.seed;
-            state.sampler.next();  // the path's own stream moves on by one draw for the whole stage
-            connections += cnt;
-          }
+      const DMedium& med = sc.mediums[state.medium_index];
+      V3 w_o_smp = sample_phase_function(state.ray_d, med.phase_function_g, rnd_bsdf);
+      float pdf_fwd = phase_function(state.ray_d, w_o_smp, med.phase_function_g);
+      float pdf_rev = phase_function(w_o_smp, state.ray_d, med.phase_function_g);
+      if (med.enable_explicit_connections && (state.total_path_depth + 1 <= sc.max_path_length)) {
+        Endpoint ep{true, nullptr, medium_sample.pos};
+        if (p.vcm.connect_to_light()) {
+          state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
+          state.gathered += vcm_connect_to_light<SP>(sc, p.vcm, ep, state, stats, shadow_rays);
+          state.sampler.pop_fixed();
         }
-        state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
-        state.gathered += vcm_connect_to_light<SP>(sc, p.vcm, isect, state, stats, shadow_rays);
+        if (p.vcm.connect_vertices()) {
+          // medium endpoints always take the serial path (they are rare and need the pre-scatter direction)
+          state.gathered += vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], ep, state, stats, shadow_rays, connections);
+        }
+      }
+      state.d_vc = (1.0f / pdf_fwd) * (state.d_vc * pdf_rev + state.d_vcm);
+      state.d_vm = (1.0f / pdf_fwd) * (state.d_vm * pdf_rev + 0.0f);
+      state.d_vcm = 1.0f / pdf_fwd;
+      state.ray_o = medium_sample.pos;
+      state.ray_d = w_o_smp;
+      state.ray_max_t = kMaxFloat;
+      state.ray_min_t = kRayEpsilon;
+      state.total_path_depth += 1;
+      bool cont = !(state.total_path_depth + 1 > sc.max_path_length) &&
+                  random_continue<SP>(state.total_path_depth, sc.random_path_termination, state.eta, state.sampler, state.throughput);
+      resolved.x = cont ? kBounceResolvedAlive : kBounceResolvedDead;
+    } else if (!found) {
+      vcm_cam_handle_miss<SP>(sc, p.vcm, state.ray_d, state.d_vcm, state.d_vc, state.path_distance, state.total_path_depth, state.wavelength, state.throughput, state.gathered);
+    } else {
+      Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
+      if (vcm_handle_boundary<SP>(sc, isect, state)) {
+        resolved.x = kBounceResolvedAlive;  // :1002-1007
+      } else {
+        const etxb_material& mat = sc.materials[isect.material_index];
+        BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
+        V2 rnd_bsdf = state.sampler.next_2d();
+        V2 rnd_connection = state.sampler.next_2d();
+        V2 rnd_support = state.sampler.next_2d();
+        if (p.vcm.blue_noise && (state.total_path_depth == 1) && (p.vcm.iteration < 256u)) {
+          uint32_t px = i % p.film.width, py = i / p.film.width;
+          rnd_bsdf = sample_blue_noise(sc, px, py, p.vcm.iteration, 0);
+          rnd_connection = sample_blue_noise(sc, px, py, p.vcm.iteration, 2);
+          rnd_support = sample_blue_noise(sc, px, py, p.vcm.iteration, 4);
+        }
+        state.sampler.push_fixed(rnd_bsdf.x, rnd_bsdf.y, rnd_support.x);
+        BSample<SP> bs = bsdf_sample<SP>(sc, bsdf_data, mat, state.sampler);
+        bool is_connectible = (bs.properties & kBsdfDelta) == 0;
         state.sampler.pop_fixed();
+        // vcm_update_camera_vcm (:589-595)
+        float cos_to_prev = fabsf(dot(isect.nrm, -state.ray_d));
+        state.d_vcm *= sqr(state.path_distance + isect.t) / cos_to_prev;
+        state.d_vc /= cos_to_prev;
+        state.d_vm /= cos_to_prev;
+        state.path_distance = 0.0f;
+        vcm_handle_direct_hit<SP>(sc, p.vcm, isect, state);
+        if (is_connectible) {
+          Endpoint ep{false, &isect, {0.0f, 0.0f, 0.0f}};
+          camera_vertex_connections<SP>(p, i, ep, state, stats, shadow_rays, connections);
+          state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
+          state.gathered += vcm_connect_to_light<SP>(sc, p.vcm, ep, state, stats, shadow_rays);
+          state.sampler.pop_fixed();
+        }
+        if (is_connectible && p.vcm.merge_vertices() && (state.total_path_depth + 1 <= sc.max_path_length) && (p.grid.photon_count != 0u)) {
+          merge_key = merge_query_key(p.grid, isect.pos);
+        }
+        V3 w = bs.weight.as_v3();
+        p.paths.bs_weight_pdf[i] = make_float4(w.x, w.y, w.z, bs.pdf);
+        p.paths.bs_wo_eta[i] = make_float4(bs.w_o.x, bs.w_o.y, bs.w_o.z, bs.eta);
+        p.paths.bs_props[i] = make_uint2(bs.properties, bs.medium_index);
+        pending_sample = true;
       }
-      if (is_connectible && p.vcm.merge_vertices() && (state.total_path_depth + 1 <= sc.max_path_length) && (p.grid.photon_count != 0u)) {
-        merge_key = merge_query_key(p.grid, isect.pos);
-      }
-      V3 w = bs.weight.as_v3();
-      p.paths.bs_weight_pdf[i] = make_float4(w.x, w.y, w.z, bs.pdf);
-      p.paths.bs_wo_eta[i] = make_float4(bs.w_o.x, bs.w_o.y, bs.w_o.z, bs.eta);
-      p.paths.bs_props[i] = make_uint2(bs.properties, bs.medium_index);
     }
+    if (!pending_sample) p.paths.bs_props[i] = resolved;
     store_state<SP>(p.paths, i, state);
     V3 gv = state.gathered.as_v3();
     p.paths.gathered[i] = make_float4(gv.x, gv.y, gv.z, 0.0f);
@@ -520,22 +636,15 @@ __global__ void __launch_bounds__(128) k_camera_connect(LaunchParams p) {
     Isect isect = make_intersection(sc, state.ray_d, __float_as_uint(hit.w), hit.x, hit.y, hit.z);
     state.sampler.seed = p.paths.conn_seed[i] ^ ((entry.y + 1u) * 0x9E3779B1u);
     state.sampler.next();
-    const float4* src = reinterpret_cast<const float4*>(p.lv_final + p.lp_offset[i] + entry.y);
-    LightVertexRec lv;
-    lv.thr_dvcm = __ldg(src + 0);
-    lv.wi_dvc = __ldg(src + 1);
-    lv.bc_dvm = __ldg(src + 2);
-    lv.pos_tri = __ldg(src + 3);
-    lv.nrm_mat = __ldg(src + 4);
+    LightVertexRec lv = load_light_vertex(p.lv_final + p.lp_offset[i] + entry.y);
+    Endpoint ep{false, &isect, {0.0f, 0.0f, 0.0f}};
     V3 target_position;
     Spec<SP> value;
-    if (vcm_connect_to_light_vertex<SP>(sc, p.vcm, state, lv, isect, target_position, value)) {
-      TriRec tri = load_triangle(sc, isect.triangle_index);
-      V3 p0 = shading_pos(sc, tri, isect.barycentric, normalize(target_position - isect.pos));
+    if (vcm_connect_to_light_vertex<SP>(sc, p.vcm, state, lv, ep, target_position, value)) {
       shadow_rays = 1;
-      float tr = trace_transmittance(sc, p0, target_position, state.sampler, stats);
-      if (tr > kEpsilon) {
-        V3 v = (Spec<SP>::make(tr) * value).as_v3();
+      Spec<SP> tr = vcm_connection_transmittance<SP>(sc, ep, lv, target_position, state, stats);
+      if (tr.is_zero() == false) {
+        V3 v = (tr * value).as_v3();
         float* dst = reinterpret_cast<float*>(p.paths.gathered + i);
         atomicAdd(dst + 0, v.x);
         if (!SP) {
@@ -847,11 +956,13 @@ __global__ void __launch_bounds__(128) k_camera_continue(LaunchParams p, const u
     PathState<SP> state = load_state<SP>(p.paths, i);
     float4 hit = p.paths.hit[i];
     uint32_t tri_index = __float_as_uint(hit.w);
-    if (tri_index != kInvalidIndex) {
+    uint2 bp = p.paths.bs_props[i];
+    if (bp.x & 0x80000000u) {
+      alive = bp.x == kBounceResolvedAlive;  // medium scattering / boundary crossing / miss: the shade stage already advanced the path
+    } else if (tri_index != kInvalidIndex) {
       Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
       BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
       float4 bw = p.paths.bs_weight_pdf[i], bd = p.paths.bs_wo_eta[i];
-      uint2 bp = p.paths.bs_props[i];
       BSample<SP> bs;
       bs.weight = Spec<SP>::make3({bw.x, bw.y, bw.z});
       bs.pdf = bw.w;

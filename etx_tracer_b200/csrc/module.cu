@@ -93,6 +93,8 @@ struct etxb_ctx {
   DevBuf<etxb_emitter> emitters;
   DevBuf<DSpectrum> spectra;
   DevBuf<DImage> images;
+  DevBuf<DMedium> mediums;
+  std::vector<DevBuf<float>> medium_density;
   std::vector<DevBuf<uint8_t>> image_pixels, image_dists;
   DevBuf<etxb_distribution_entry> emitter_dist;
   DevBuf<BvhNode> bvh_nodes;
@@ -199,7 +201,7 @@ struct LaunchTimer {
   }
 };
 
-bool material_class_supported_host(uint32_t cls) { return (cls <= ETXB_MAT_VOID) && (cls != ETXB_MAT_BOUNDARY); }  // Boundary needs media (not on the device yet)
+bool material_class_supported_host(uint32_t cls) { return cls <= ETXB_MAT_VOID; }
 
 uint32_t next_pow2(uint64_t v) {
   // next_power_of_two (math.hxx:1001-1010)
@@ -361,6 +363,7 @@ int run_grid_build(etxb_ctx* ctx, const LightVertexRec* records, uint32_t count)
     size_t temp_bytes = ctx->cub_temp.bytes();
     int end_bit = 1;
     while ((1ull << end_bit) < table_size) end_bit++;
+    if (ctx->dscene.medium_count) end_bit = 32;  // medium vertices carry the key 0xffffffff and must sort behind every cell
     CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->keys_in.ptr, ctx->keys_out.ptr, ctx->vals_in.ptr, ctx->vals_out.ptr, int(count), 0,
                    end_bit, ctx->stream));
   }
@@ -542,6 +545,8 @@ void etxb_destroy(etxb_ctx* ctx) {
   ctx->emitters.release();
   ctx->spectra.release();
   ctx->images.release();
+  ctx->mediums.release();
+  for (auto& b : ctx->medium_density) b.release();
   for (auto& b : ctx->image_pixels) b.release();
   for (auto& b : ctx->image_dists) b.release();
   ctx->emitter_dist.release();
@@ -611,7 +616,6 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   // ---- what the device path does not cover yet fails loudly (no CPU fallback) --------------------------------------
   if (cam.cls != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "equirectangular camera is not supported on the device yet");
   if (cam.lens_image != ETXB_INVALID_INDEX) return fail(ctx, ETXB_ERR_UNSUPPORTED, "lens aperture image is not supported on the device yet");
-  if (s.mediums.count != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "participating media are not supported on the device yet");
   const auto* mats = static_cast<const etxb_material*>(s.materials.a);
   for (uint64_t i = 0; i < s.materials.count; ++i) {
     const etxb_material& m = mats[i];
@@ -621,8 +625,8 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
     uint32_t imgs[] = {m.reflectance.image_index, m.scattering.image_index, m.emission.image_index, m.roughness.image_index, m.normal_image_index, m.thinfilm.thickness_image};
     for (uint32_t im : imgs)
       if ((im != ETXB_INVALID_INDEX) && (im >= s.images.count)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu: image index %u out of range", (unsigned long long)i, im);
-    if (m.int_medium != ETXB_INVALID_INDEX || m.ext_medium != ETXB_INVALID_INDEX)
-      return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: media are not supported on the device yet", (unsigned long long)i);
+    if (((m.int_medium != ETXB_INVALID_INDEX) && (m.int_medium >= s.mediums.count)) || ((m.ext_medium != ETXB_INVALID_INDEX) && (m.ext_medium >= s.mediums.count)))
+      return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu: medium index out of range", (unsigned long long)i);
   }
   ctx->has_stochastic_merge = false;
   for (uint64_t i = 0; i < s.materials.count; ++i) {
@@ -642,6 +646,45 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
       const auto& img = static_cast<const etxb_image*>(s.images.a)[prof.emission.image_index];
       if (img.y_distribution.values.count != uint64_t(img.isize[1]) + 1u) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "environment emitter %llu: image has no sampling table", (unsigned long long)i);
     }
+  }
+  // ---- media (medium.hxx:8-47): dense density grids go to HBM as they are -------------------------------------------------------
+  {
+    const auto* meds = static_cast<const etxb_medium*>(s.mediums.a);
+    std::vector<DMedium> dmeds(s.mediums.count);
+    for (auto& b : ctx->medium_density) b.release();
+    ctx->medium_density.assign(s.mediums.count, {});
+    for (uint64_t i = 0; i < s.mediums.count; ++i) {
+      const etxb_medium& md = meds[i];
+      DMedium& d = dmeds[i];
+      d = {};
+      d.bounds_min = {md.bounds_min[0], md.bounds_min[1], md.bounds_min[2]};
+      d.bounds_max = {md.bounds_max[0], md.bounds_max[1], md.bounds_max[2]};
+      d.cls = md.cls;
+      d.enable_explicit_connections = md.enable_explicit_connections;
+      d.absorption_index = md.absorption_index;
+      d.scattering_index = md.scattering_index;
+      d.phase_function_g = md.phase_function_g;
+      d.max_sigma = md.max_sigma;
+      d.dim_x = md.dimensions[0];
+      d.dim_y = md.dimensions[1];
+      d.dim_z = md.dimensions[2];
+      if (md.cls == 1u) {
+        size_t n = size_t(d.dim_x) * d.dim_y * d.dim_z;
+        if ((n == 0) || (md.density.count != n)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "medium %llu: density grid does not match its dimensions", (unsigned long long)i);
+        CUDA_OK(ctx, ctx->medium_density[i].alloc(n));
+        CUDA_OK(ctx, cudaMemcpyAsync(ctx->medium_density[i].ptr, md.density.a, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d.density = ctx->medium_density[i].ptr;
+      } else if (md.cls != 0u) {
+        return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "medium %llu: unknown class %u", (unsigned long long)i, md.cls);
+      }
+    }
+    if (int rc = upload(ctx, ctx->mediums, dmeds.data(), dmeds.size())) return rc;
+    ctx->dscene.mediums = ctx->mediums.ptr;
+    ctx->dscene.medium_count = uint32_t(dmeds.size());
+    ctx->dscene.has_boundaries = 0;
+    for (uint64_t i = 0; i < s.materials.count; ++i)
+      if (mats[i].cls == ETXB_MAT_BOUNDARY) ctx->dscene.has_boundaries = 1;
+    if ((cam.medium_index != ETXB_INVALID_INDEX) && (cam.medium_index >= s.mediums.count)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "camera medium index out of range");
   }
   // ---- images: pixels + flattened row/column CDFs (image.hxx:8-50) ---------------------------------------------------------------
   {
@@ -759,6 +802,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   d.samples = s.samples;
   d.random_path_termination = s.random_path_termination;
   d.spectral = (s.flags & ETXB_SCENE_SPECTRAL) ? 1u : 0u;
+  d.spectrum_count = uint32_t(s.spectrums.count);
   d.default_dielectric_eta = s.default_dielectric_eta;
   d.default_conductor_eta = s.default_conductor_eta;
   d.default_conductor_k = s.default_conductor_k;

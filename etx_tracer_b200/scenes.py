@@ -256,6 +256,31 @@ class SceneData:
             self._distant_emitters = []
         self._distant_emitters.append((p, e))
 
+    def add_medium(self, absorption=(0.0, 0.0, 0.0), scattering=(0.8, 0.8, 0.8), g=0.0, explicit_connections=True, density=None, bounds=None, max_sigma=None):
+        """MediumPool::add (render/host/medium_pool.cxx:23-60): homogeneous, or heterogeneous with a dense grid normalised to max 1."""
+        m = np.zeros(1, dtype=S.MEDIUM)
+        m["absorption_index"] = self.add_spectrum(spd_rgb_reflectance(absorption))
+        m["scattering_index"] = self.add_spectrum(spd_rgb_reflectance(scattering))
+        m["phase_function_g"] = g
+        m["enable_explicit_connections"] = 1 if explicit_connections else 0
+        ext = np.asarray(absorption, dtype=f32) + np.asarray(scattering, dtype=f32)
+        m["max_sigma"] = f32(max_sigma if max_sigma is not None else float(ext.max()))
+        if density is not None:
+            d = np.ascontiguousarray(density, dtype=f32)
+            d = (d / max(float(d.max()), 1e-20)).astype(f32)
+            m["cls"] = 1
+            m["density"]["a"] = d.ctypes.data
+            m["density"]["count"] = d.size
+            m["dimensions"][0] = (d.shape[2], d.shape[1], d.shape[0])  # x fastest
+            lo, hi = bounds
+            m["bounds_min"][0] = lo
+            m["bounds_max"][0] = hi
+            self._keep.append(d)
+        if not hasattr(self, "_mediums"):
+            self._mediums = []
+        self._mediums.append(m)
+        return len(self._mediums) - 1
+
     # -- geometry --------------------------------------------------------------------------------
     def add_mesh(self, positions, normals, indices, material_index, uvs=None):
         positions = np.asarray(positions, dtype=f32).reshape(-1, 3)
@@ -526,7 +551,7 @@ class SceneData:
         view("emitter_profiles", self.a_profiles)
         view("emitter_instances", self.a_emitters)
         self.a_images = np.concatenate(self._images) if getattr(self, "_images", None) else np.zeros(0, dtype=S.IMAGE)
-        self.a_mediums = getattr(self, "a_mediums", np.zeros(0, dtype=S.MEDIUM))
+        self.a_mediums = np.concatenate(self._mediums) if getattr(self, "_mediums", None) else np.zeros(0, dtype=S.MEDIUM)
         view("images", self.a_images)
         view("mediums", self.a_mediums)
         view("spectrums", self.a_spectra)
@@ -790,6 +815,79 @@ def procedural_room(width=1920, height=1080, samples=1024, spectral=True, target
     sky = sd.add_image(sky_image(env_size[0], env_size[1], seed=seed), repeat=True, build_table=True)
     sd.add_environment_emitter(sky, rgb=(1.0, 1.0, 1.0))
     sd.set_camera([0.0, 1.6, 3.8], [0.0, 1.0, 0.0], [0.0, 1.0, 0.0], width, height, 55.0, clip_near=0.1, clip_far=100.0)
+    return sd.finalize(samples=samples, spectral=spectral)
+
+
+def fbm_density(n=16, seed=42):
+    """Deterministic value-noise fBm on an n^3 grid, normalised to max 1 (BASELINE config 5's cloud in miniature)."""
+    rng = np.random.default_rng(seed)
+    total = np.zeros((n, n, n))
+    amp, freq = 1.0, 2
+    z, y, x = np.mgrid[0:n, 0:n, 0:n] / n
+    while freq <= n:
+        lattice = rng.random((freq + 1, freq + 1, freq + 1))
+        fx, fy, fz = x * freq, y * freq, z * freq
+        ix, iy, iz = fx.astype(int), fy.astype(int), fz.astype(int)
+        tx, ty, tz = fx - ix, fy - iy, fz - iz
+        def L(a, b, c):
+            return lattice[iz + c, iy + b, ix + a]
+        v = ((L(0, 0, 0) * (1 - tx) + L(1, 0, 0) * tx) * (1 - ty) + (L(0, 1, 0) * (1 - tx) + L(1, 1, 0) * tx) * ty) * (1 - tz) + \
+            ((L(0, 0, 1) * (1 - tx) + L(1, 0, 1) * tx) * (1 - ty) + (L(0, 1, 1) * (1 - tx) + L(1, 1, 1) * tx) * ty) * tz
+        total += amp * v
+        amp *= 0.5
+        freq *= 2
+    r = np.sqrt((x - 0.5) ** 2 + (y - 0.5) ** 2 + (z - 0.5) ** 2)
+    total = np.clip(total * np.clip(1.0 - 2.0 * r, 0, 1) - 0.15, 0, None)
+    return (total / total.max()).astype(f32)
+
+
+def media_box(kind="fog", width=32, height=32, samples=16, spectral=False):
+    """Cornell box with participating media behind Boundary materials:
+    fog      — homogeneous scattering medium in a box (boundary crossings, medium light vertices, explicit connections)
+    cloud    — heterogeneous fBm density (delta tracking / ratio tracking), anisotropic phase function
+    tinted   — absorbing homogeneous medium inside a smooth dielectric sphere + thin fog without explicit connections
+    camera   — the camera itself sits inside a homogeneous medium that fills the room"""
+    sd = SceneData()
+    sd.name = f"media_box[{kind}]" + ("/spectral" if spectral else "/rgb")
+    white = sd.add_material("white", kd=[1.0, 1.0, 1.0], two_sided=1)
+    red = sd.add_material("leftWall", kd=[1.0, 0.0, 0.0], two_sided=1)
+    green = sd.add_material("rightWall", kd=[0.0, 1.0, 0.0], two_sided=1)
+    light = sd.add_material("light", kd=[0.0, 0.0, 0.0], emission=spd_rgb_luminance([10.018, 3.918, 0.932]), two_sided=1)
+    zf = 4.0
+    sd.add_quad([-1, 0, zf], [1, 0, zf], [1, 0, -1], [-1, 0, -1], white)
+    sd.add_quad([-1, 2, -1], [1, 2, -1], [1, 2, zf], [-1, 2, zf], white)
+    sd.add_quad([-1, 0, -1], [1, 0, -1], [1, 2, -1], [-1, 2, -1], white)
+    sd.add_quad([-1, 0, zf], [-1, 0, -1], [-1, 2, -1], [-1, 2, zf], red)
+    sd.add_quad([1, 0, -1], [1, 0, zf], [1, 2, zf], [1, 2, -1], green)
+    sd.add_quad([-1, 0, zf], [-1, 2, zf], [1, 2, zf], [1, 0, zf], white)
+    sd.add_quad([-0.24, 1.98, -0.22], [0.23, 1.98, -0.22], [0.23, 1.98, 0.16], [-0.24, 1.98, 0.16], light)
+    cam_medium = S.INVALID
+    if kind == "fog":
+        fog = sd.add_medium(absorption=(0.05, 0.05, 0.05), scattering=(1.6, 1.4, 1.2), g=0.3)
+        b = sd.add_material("fog", cls=S.MAT_BOUNDARY, int_medium=fog)
+        sd.add_box([0.0, 0.7, 0.0], (0.6, 0.55, 0.6), 10.0, b)
+        sd.add_box([-0.3, 0.3, 0.2], (0.15, 0.3, 0.15), 30.0, white)  # an object inside the fog
+    elif kind == "cloud":
+        cloud = sd.add_medium(absorption=(0.2, 0.2, 0.2), scattering=(18.0, 18.0, 18.0), g=0.8, density=fbm_density(16), bounds=([-0.6, 0.4, -0.6], [0.6, 1.6, 0.6]), max_sigma=18.2)
+        b = sd.add_material("cloud", cls=S.MAT_BOUNDARY, int_medium=cloud)
+        sd.add_box([0.0, 1.0, 0.0], (0.6, 0.6, 0.6), 0.0, b)
+    elif kind == "tinted":
+        tint = sd.add_medium(absorption=(0.2, 1.5, 3.0), scattering=(0.0, 0.0, 0.0))
+        thin = sd.add_medium(absorption=(0.0, 0.0, 0.0), scattering=(0.5, 0.5, 0.5), explicit_connections=False)
+        glass = sd.add_material("glass", cls=S.MAT_DIELECTRIC, roughness=0.0, int_ior="glass", int_medium=tint)
+        sd.add_uv_sphere([0.35, 0.41, 0.3], 0.4, 16, 9, glass)
+        b = sd.add_material("haze", cls=S.MAT_BOUNDARY, int_medium=thin)
+        sd.add_box([-0.4, 0.9, -0.2], (0.35, 0.8, 0.35), 0.0, b)
+    elif kind == "camera":
+        room = sd.add_medium(absorption=(0.02, 0.02, 0.02), scattering=(0.25, 0.25, 0.3), g=0.0)
+        cam_medium = room
+        for m in sd.materials:
+            m["ext_medium"] = room  # emitters start their paths in the room's medium (emitter_external_medium_index)
+        sd.add_box([0.3, 0.3, 0.2], (0.3, 0.3, 0.3), -17.0, white)
+    else:
+        raise KeyError(kind)
+    sd.set_camera([0.0, 1.0, 3.82], [0.0, 1.0, -6.18], [0.0, 1.0, 0.0], width, height, 39.597755335771296, clip_near=0.1, clip_far=100.0)
+    sd.camera["medium_index"] = cam_medium
     return sd.finalize(samples=samples, spectral=spectral)
 
 
