@@ -25,7 +25,7 @@ class EtxbError(RuntimeError):
 def load_library(flavor="fast"):
     if flavor in _libs:
         return _libs[flavor]
-    path = _build.lib_path(flavor)
+    path = os.environ.get("ETXB_LIB_" + flavor.upper()) or _build.lib_path(flavor)  # the override is for A/B experiments only
     if not os.path.exists(path):
         raise EtxbError(-100, f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
     lib = C.CDLL(path)

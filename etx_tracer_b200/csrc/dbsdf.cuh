@@ -118,14 +118,14 @@ DEV RsRp fresnel_transmittance(Cx ni, Cx ci, Cx nj, Cx cj) {
   Cx tp = cx_div_conj((2.0f * ni) * ci, ni * cj + nj * ci);
   return {ts, tp};
 }
-DEV float fresnel_generic(float cos_theta_i, Cx ext_ior, Cx int_ior) {
+DEVN float fresnel_generic(float cos_theta_i, Cx ext_ior, Cx int_ior) {
   Cx q = ext_ior / int_ior;
   Cx sin_theta_o_squared = (q * q) * (1.0f - cos_theta_i * cos_theta_i);
   Cx cos_theta_o = cx_sqrt(1.0f - sin_theta_o_squared);
   RsRp r = fresnel_reflectance(ext_ior, cx(cos_theta_i), int_ior, cos_theta_o);
   return 0.5f * (cx_norm(r.a) + cx_norm(r.b));
 }
-DEV float fresnel_thinfilm(float wavelength, float cos_theta_0, Cx ext_ior, Cx film_ior, Cx int_ior, float thickness) {
+DEVN float fresnel_thinfilm(float wavelength, float cos_theta_0, Cx ext_ior, Cx film_ior, Cx int_ior, float thickness) {
   const Cx i = {0.0f, 1.0f};
   if (cos_theta_0 == 0.0f) return 0.0f;
   Cx q1 = ext_ior / film_ior;
@@ -1135,8 +1135,11 @@ DEVN float principled_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const e
 
 // ---- dispatch (scene_bsdf.hxx:56-90) -----------------------------------------------------------------------
 // Classes / variants not implemented on the device are rejected by etxb_upload_scene (ETXB_ERR_UNSUPPORTED).
+// The Lambert case is inlined at every call site; all other classes go through ONE out-of-line copy of the switch per kernel
+// module (the microfacet random walks are large: inlining them at each of the ~10 call sites of a bounce kernel multiplies code
+// size, instruction-cache misses and compile time for no gain).
 template <bool SP>
-DEV BSample<SP> bsdf_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
+DEVG_BSDF BSample<SP> bsdf_sample_generic(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
   switch (m.cls) {
     case ETXB_MAT_DIFFUSE: return diffuse_sample<SP>(sc, d, m, smp);
     case ETXB_MAT_TRANSLUCENT: return translucent_sample<SP>(sc, d, m, smp);
@@ -1166,7 +1169,12 @@ DEV BSample<SP> bsdf_sample(const DeviceScene& sc, const BData& d, const etxb_ma
   }
 }
 template <bool SP>
-DEV BEval<SP> bsdf_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
+DEV BSample<SP> bsdf_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
+  if (m.cls == ETXB_MAT_DIFFUSE) return diffuse_sample<SP>(sc, d, m, smp);
+  return bsdf_sample_generic<SP>(sc, d, m, smp);
+}
+template <bool SP>
+DEVG_BSDF BEval<SP> bsdf_evaluate_generic(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
   switch (m.cls) {
     case ETXB_MAT_DIFFUSE: return diffuse_evaluate<SP>(sc, d, w_o, m);
     case ETXB_MAT_TRANSLUCENT: return translucent_evaluate<SP>(sc, d, w_o, m);
@@ -1180,7 +1188,12 @@ DEV BEval<SP> bsdf_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const
   }
 }
 template <bool SP>
-DEV float bsdf_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
+DEV BEval<SP> bsdf_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
+  if (m.cls == ETXB_MAT_DIFFUSE) return diffuse_evaluate<SP>(sc, d, w_o, m);
+  return bsdf_evaluate_generic<SP>(sc, d, w_o, m, smp);
+}
+template <bool SP>
+DEVG_BSDF float bsdf_pdf_generic(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
   switch (m.cls) {
     case ETXB_MAT_DIFFUSE: return diffuse_pdf(d, w_o);
     case ETXB_MAT_TRANSLUCENT: return translucent_pdf<SP>(sc, d, w_o, m);
@@ -1192,6 +1205,11 @@ DEV float bsdf_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_mat
     case ETXB_MAT_PRINCIPLED: return principled_pdf<SP>(sc, d, w_o, m, smp);
     default: return 0.0f;
   }
+}
+template <bool SP>
+DEV float bsdf_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
+  if (m.cls == ETXB_MAT_DIFFUSE) return diffuse_pdf(d, w_o);
+  return bsdf_pdf_generic<SP>(sc, d, w_o, m, smp);
 }
 template <bool SP>
 DEV float bsdf_reverse_pdf(const DeviceScene& sc, const BData& in_d, V3 in_w_o, const etxb_material& m, Smp& smp) {

@@ -12,6 +12,17 @@
 
 #define DEV __device__ __forceinline__
 #define DEVN __device__ __noinline__
+// experiment switches (default: out of line)
+#if defined(ETXB_BSDF_INLINE)
+#define DEVG_BSDF DEV
+#else
+#define DEVG_BSDF DEVN
+#endif
+#if defined(ETXB_MATH_INLINE)
+#define DEVG_MATH DEV
+#else
+#define DEVG_MATH DEVN
+#endif
 
 namespace etxb {
 
@@ -30,30 +41,32 @@ constexpr float kDeltaAlphaTreshold = 1.0e-4f;
 constexpr uint32_t kInvalidIndex = ~0u;
 
 // ---- transcendental switch ----------------------------------------------------------------------------
+// Out of line where the body is large (the portable double-precision routines of the parity build; powf / inverse trig of the CUDA
+// math library in the product build): these are called from dozens of inlined sites per kernel.
 #if defined(ETXB_PARITY) && ETXB_PARITY
-DEV float m_sin(float x) { return pm::sinf_(x); }
-DEV float m_cos(float x) { return pm::cosf_(x); }
-DEV float m_exp(float x) { return pm::expf_(x); }
-DEV float m_log(float x) { return pm::logf_(x); }
-DEV float m_pow(float x, float y) { return pm::powf_(x, y); }
-DEV float m_acos(float x) { return pm::acosf_(x); }
-DEV float m_asin(float x) { return pm::asinf_(x); }
-DEV float m_atan(float x) { return pm::atanf_(x); }
-DEV float m_atan2(float y, float x) { return pm::atan2f_(y, x); }
-DEV float m_cosh(float x) { return pm::coshf_(x); }
-DEV float m_atanh(float x) { return pm::atanhf_(x); }
+DEVN float m_sin(float x) { return pm::sinf_(x); }
+DEVN float m_cos(float x) { return pm::cosf_(x); }
+DEVN float m_exp(float x) { return pm::expf_(x); }
+DEVN float m_log(float x) { return pm::logf_(x); }
+DEVN float m_pow(float x, float y) { return pm::powf_(x, y); }
+DEVN float m_acos(float x) { return pm::acosf_(x); }
+DEVN float m_asin(float x) { return pm::asinf_(x); }
+DEVN float m_atan(float x) { return pm::atanf_(x); }
+DEVN float m_atan2(float y, float x) { return pm::atan2f_(y, x); }
+DEVN float m_cosh(float x) { return pm::coshf_(x); }
+DEVN float m_atanh(float x) { return pm::atanhf_(x); }
 #else
 DEV float m_sin(float x) { return sinf(x); }
 DEV float m_cos(float x) { return cosf(x); }
 DEV float m_exp(float x) { return expf(x); }
 DEV float m_log(float x) { return logf(x); }
-DEV float m_pow(float x, float y) { return powf(x, y); }
-DEV float m_acos(float x) { return acosf(x); }
-DEV float m_asin(float x) { return asinf(x); }
-DEV float m_atan(float x) { return atanf(x); }
-DEV float m_atan2(float y, float x) { return atan2f(y, x); }
-DEV float m_cosh(float x) { return coshf(x); }
-DEV float m_atanh(float x) { return atanhf(x); }
+DEVG_MATH float m_pow(float x, float y) { return powf(x, y); }
+DEVG_MATH float m_acos(float x) { return acosf(x); }
+DEVG_MATH float m_asin(float x) { return asinf(x); }
+DEVG_MATH float m_atan(float x) { return atanf(x); }
+DEVG_MATH float m_atan2(float y, float x) { return atan2f(y, x); }
+DEVG_MATH float m_cosh(float x) { return coshf(x); }
+DEVG_MATH float m_atanh(float x) { return atanhf(x); }
 #endif
 
 DEV float sqr(float t) { return t * t; }

@@ -72,8 +72,8 @@ DEV ImageGather image_gather(const DImage& img, V2 in_uv) {
   g.p11 = image_pixel(img, col_1, row_1) * (dx) * (dy);
   return g;
 }
-// Image::evaluate (image.hxx:76-90)
-DEV F4v image_evaluate(const DImage& img, V2 in_uv, float* pdf) {
+// Image::evaluate (image.hxx:76-90); out of line: every material parameter lookup lands here
+DEVN F4v image_evaluate(const DImage& img, V2 in_uv, float* pdf) {
   ImageGather g = image_gather(img, in_uv);
   if (pdf) {
     bool flat = (img.options & kImageUniformSamplingTable) || (img.fsize_y == 1.0f);
@@ -87,10 +87,7 @@ DEV F4v image_evaluate(const DImage& img, V2 in_uv, float* pdf) {
   }
   return g.p00 + g.p01 + g.p10 + g.p11;
 }
-DEV float image_evaluate_alpha(const DImage& img, V2 in_uv) {
-  ImageGather g = image_gather(img, in_uv);
-  return g.p00.w + g.p01.w + g.p10.w + g.p11.w;
-}
+DEV float image_evaluate_alpha(const DImage& img, V2 in_uv) { return image_evaluate(img, in_uv, nullptr).w; }
 
 // Distribution::sample (distribution.hxx:16-35) over `count` entries
 DEV uint32_t dist_sample(const etxb_distribution_entry* values, uint32_t count, float rnd) {

@@ -53,6 +53,8 @@ struct DeviceScene {
   const struct DMedium* mediums;
   uint32_t medium_count;
   uint32_t spectrum_count;
+  uint32_t has_subsurface;  // some material has subsurface scattering enabled
+  uint32_t subsurface_exit_material;
   uint32_t has_boundaries;  // some material is of class Boundary (shadow rays may cross medium interfaces)
   uint32_t emitter_count;
   uint32_t triangle_count;

@@ -103,8 +103,9 @@ namespace etxb {
 
 // Raytracing::trace_transmittance (rt.cxx:468-579): occluded unless every hit is a Boundary; the (<= 63) boundary crossings are
 // sorted by t and the per-segment medium transmittance is multiplied in.
+// Out of line: every kernel reaches it from several connection routines, and one BVH traversal dwarfs the call.
 template <bool SP>
-DEV Spec<SP> trace_transmittance(const DeviceScene& sc, float wavelength, V3 p0, V3 p1, uint32_t medium_index, Smp& smp, TraverseStats* stats) {
+DEVN Spec<SP> trace_transmittance(const DeviceScene& sc, float wavelength, V3 p0, V3 p1, uint32_t medium_index, Smp& smp, TraverseStats* stats) {
   V3 direction = p1 - p0;
   float t_max = dot(direction, direction);
   if (t_max <= kRayEpsilon) return Spec<SP>::make(1.0f);

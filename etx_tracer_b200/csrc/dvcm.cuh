@@ -507,7 +507,8 @@ DEV LightVertexRec make_medium_light_vertex(const PathState<SP>& s, V3 pos, uint
 // ---- shared step pieces ------------------------------------------------------------------------------------------------
 // vcm_next_ray (vcm_shared.hxx:218-283)
 template <bool SP>
-DEV bool vcm_next_ray(const DeviceScene& sc, bool light_path, PathState<SP>& state, const VcmParams& it, const Isect& isect, const BData& bsdf_data, const BSample<SP>& bs) {
+DEV bool vcm_next_ray(const DeviceScene& sc, bool light_path, PathState<SP>& state, const VcmParams& it, const Isect& isect, const BData& bsdf_data, const BSample<SP>& bs,
+                      bool subsurface_sample = false) {
   if (state.total_path_depth + 1 > sc.max_path_length) return false;
   if (bs.valid() == false) return false;
   TriRec tri = load_triangle(sc, isect.triangle_index);
@@ -527,7 +528,7 @@ DEV bool vcm_next_ray(const DeviceScene& sc, bool light_path, PathState<SP>& sta
     state.d_vm *= cos_theta_bsdf;
     state.d_vcm = 0.0f;
   } else {
-    float rev_sample_pdf = bsdf_reverse_pdf<SP>(sc, bsdf_data, bs.w_o, mat, state.sampler);
+    float rev_sample_pdf = subsurface_sample ? fabsf(dot(bsdf_data.w_i, isect.nrm)) / kPi : bsdf_reverse_pdf<SP>(sc, bsdf_data, bs.w_o, mat, state.sampler);
     state.d_vc = (cos_theta_bsdf / bs.pdf) * (state.d_vc * rev_sample_pdf + state.d_vcm + it.vm_weight);
     state.d_vm = (cos_theta_bsdf / bs.pdf) * (state.d_vm * rev_sample_pdf + state.d_vcm * it.vc_weight + 1.0f);
     state.d_vcm = 1.0f / bs.pdf;

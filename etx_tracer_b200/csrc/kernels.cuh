@@ -10,6 +10,7 @@
 // queues are compacted with warp ballot + one atomic per warp.
 #pragma once
 #include "dvcm.cuh"
+#include "dsss.cuh"
 
 namespace etxb {
 
@@ -218,6 +219,12 @@ DEV bool store_light_vertex(const LaunchParams& p, const LightVertexRec& rec) {
 }
 
 // vcm_light_step after the trace (vcm_shared.hxx:1090-1260): medium events, boundary crossings, surface events
+// which endpoints of the current vertex run explicit connections
+enum : uint32_t { kEpNone = 0u, kEpMedium = 1u, kEpSurface = 2u, kEpSubsurface = 3u };
+
+// vcm_light_step (vcm_shared.hxx:1086-1259).  Three phases so that every heavy routine has ONE call site: (A) the event at the end of
+// the segment (medium scattering, boundary crossing, surface hit incl. the subsurface walk), (B) camera connections from the
+// endpoint(s) it produced — one, or every gathered subsurface exit (:1207-1222), (C) the continuation.
 template <bool SP>
 __global__ void __launch_bounds__(128) k_light_bounce(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,57 +240,47 @@ __global__ void __launch_bounds__(128) k_light_bounce(LaunchParams p, const uint
     float4 hit = p.paths.hit[i];
     uint32_t tri_index = __float_as_uint(hit.w);
     const bool found = tri_index != kInvalidIndex;
+    uint32_t ep_mode = kEpNone;
+    bool at_medium = false, at_surface = false, ss_path = false, ss_sampled = false;
+    V2 rnd_bsdf = {0.0f, 0.0f}, rnd_connection = {0.0f, 0.0f}, rnd_support = {0.0f, 0.0f};
+    V3 medium_pos = {0.0f, 0.0f, 0.0f};
+    Isect isect{};
+    BSample<SP> bs;
+    SSGather<SP> ssg;
+    ssg.count = 0;
+    // ---- (A) ----
     MediumSample<SP> medium_sample = vcm_try_sampling_medium<SP>(sc, state, found ? hit.z : kMaxFloat);
     if (medium_sample.sampled_medium()) {
       // :1097-1170
-      V2 rnd_bsdf = state.sampler.next_2d();
-      V2 rnd_connection = state.sampler.next_2d();
-      V2 rnd_support = state.sampler.next_2d();
+      at_medium = true;
+      medium_pos = medium_sample.pos;
+      rnd_bsdf = state.sampler.next_2d();
+      rnd_connection = state.sampler.next_2d();
+      rnd_support = state.sampler.next_2d();
       float seg = state.path_distance + medium_sample.sampled_medium_t;
       state.d_vcm *= sqr(seg);
       state.path_distance = 0.0f;
       const DMedium& med = sc.mediums[state.medium_index];
       if (p.vcm.connect_vertices() && (state.total_path_depth + 1 <= sc.max_path_length)) {
-        if (store_light_vertex(p, make_medium_light_vertex<SP>(state, medium_sample.pos, i))) {
+        if (store_light_vertex(p, make_medium_light_vertex<SP>(state, medium_pos, i))) {
           state.lv_count += 1;
           stored = 1;
         }
       }
-      if (p.vcm.connect_to_camera() && med.enable_explicit_connections && (state.total_path_depth + 1 <= sc.max_path_length)) {
-        state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
-        Spec<SP> value;
-        V2 uv;
-        Endpoint ep{true, nullptr, medium_sample.pos};
-        bool ok = vcm_connect_to_camera<SP>(sc, p.vcm, ep, state, value, uv, stats, shadow_rays);
-        state.sampler.pop_fixed();
-        if (ok && (value.maximum() > kEpsilon)) splats += splat_light<SP>(p, value, uv, state.wavelength);
-      }
-      V3 w_i = state.ray_d;
-      V3 w_o_smp = sample_phase_function(w_i, med.phase_function_g, rnd_bsdf);
-      float pdf_fwd = phase_function(w_i, w_o_smp, med.phase_function_g);
-      float pdf_rev = phase_function(w_o_smp, w_i, med.phase_function_g);
-      state.d_vc = (1.0f / pdf_fwd) * (state.d_vc * pdf_rev + state.d_vcm);
-      state.d_vm = (1.0f / pdf_fwd) * (state.d_vm * pdf_rev + 0.0f);
-      state.d_vcm = 1.0f / pdf_fwd;
-      state.ray_o = medium_sample.pos;
-      state.ray_d = w_o_smp;
-      state.ray_max_t = kMaxFloat;
-      state.ray_min_t = kRayEpsilon;
-      state.total_path_depth += 1;
-      alive = (state.total_path_depth + 1 <= sc.max_path_length) &&
-              random_continue<SP>(state.total_path_depth, sc.random_path_termination, state.eta, state.sampler, state.throughput);
+      if (p.vcm.connect_to_camera() && med.enable_explicit_connections && (state.total_path_depth + 1 <= sc.max_path_length)) ep_mode = kEpMedium;
     } else if (found) {
-      Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
+      isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
       if (vcm_handle_boundary<SP>(sc, isect, state)) {
         alive = true;
       } else {
+        at_surface = true;
         const etxb_material& mat = sc.materials[isect.material_index];
         BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathLight);
-        V2 rnd_bsdf = state.sampler.next_2d();
-        V2 rnd_connection = state.sampler.next_2d();
-        V2 rnd_support = state.sampler.next_2d();
+        rnd_bsdf = state.sampler.next_2d();
+        rnd_connection = state.sampler.next_2d();
+        rnd_support = state.sampler.next_2d();
         state.sampler.push_fixed(rnd_bsdf.x, rnd_bsdf.y, rnd_support.x);
-        BSample<SP> bs = bsdf_sample<SP>(sc, bsdf_data, mat, state.sampler);
+        bs = bsdf_sample<SP>(sc, bsdf_data, mat, state.sampler);
         bool is_connectible = (bs.properties & kBsdfDelta) == 0;
         state.sampler.pop_fixed();
         // vcm_update_light_vcm (:451-461)
@@ -295,24 +292,66 @@ __global__ void __launch_bounds__(128) k_light_bounce(LaunchParams p, const uint
         state.d_vc /= cos_to_prev;
         state.d_vm /= cos_to_prev;
         state.path_distance = 0.0f;
+        ss_path = sc.has_subsurface && (bs.properties & kBsdfDiffuse) && (mat.subsurface.cls != 0u);
+        if (ss_path) ss_sampled = ss_gather<SP>(sc, state.wavelength, isect, state.sampler, ssg, stats, shadow_rays);
         if (is_connectible) {
-          if (store_light_vertex(p, make_light_vertex<SP>(state, isect, i))) {
+          if (store_light_vertex(p, make_light_vertex<SP>(state, isect, i))) {  // the vertex stays at the entry point (:1204)
             state.lv_count += 1;
             stored = 1;
           }
-          if (p.vcm.connect_to_camera() && (state.total_path_depth + 1 <= sc.max_path_length)) {
-            state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
-            Spec<SP> value;
-            V2 uv;
-            Endpoint ep{false, &isect, {0.0f, 0.0f, 0.0f}};
-            bool ok = vcm_connect_to_camera<SP>(sc, p.vcm, ep, state, value, uv, stats, shadow_rays);
-            state.sampler.pop_fixed();
-            if (ok && (value.maximum() > kEpsilon)) splats += splat_light<SP>(p, value, uv, state.wavelength);
-          }
+          if (p.vcm.connect_to_camera() && (state.total_path_depth + 1 <= sc.max_path_length)) ep_mode = ss_sampled ? kEpSubsurface : kEpSurface;
         }
-        if (vcm_next_ray<SP>(sc, true, state, p.vcm, isect, bsdf_data, bs)) {
-          alive = state.total_path_depth + 1u < sc.max_path_length;
+      }
+    }
+    // ---- (B) ----
+    if (ep_mode != kEpNone) {
+      uint32_t n = (ep_mode == kEpSubsurface) ? ssg.count : 1u;
+      Isect ep_isect = isect;
+#pragma unroll 1
+      for (uint32_t k = 0; k < n; ++k) {
+        Spec<SP> w = Spec<SP>::make(1.0f);
+        if (ep_mode == kEpSubsurface) {
+          ep_isect = ss_exit_intersection<SP>(sc, ssg, k, sc.subsurface_exit_material);
+          w = ssg.weights[k];
         }
+        Endpoint ep{ep_mode == kEpMedium, &ep_isect, medium_pos};  // one object behind the pointer: it stays in registers
+        state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
+        Spec<SP> value;
+        V2 uv;
+        bool ok = vcm_connect_to_camera<SP>(sc, p.vcm, ep, state, value, uv, stats, shadow_rays);
+        state.sampler.pop_fixed();
+        if (ok && (value.maximum() > kEpsilon)) splats += splat_light<SP>(p, (ep_mode == kEpSubsurface) ? (w * value) : value, uv, state.wavelength);
+      }
+    }
+    // ---- (C) ----
+    if (at_medium) {
+      const DMedium& med = sc.mediums[state.medium_index];
+      V3 w_i = state.ray_d;
+      V3 w_o_smp = sample_phase_function(w_i, med.phase_function_g, rnd_bsdf);
+      float pdf_fwd = phase_function(w_i, w_o_smp, med.phase_function_g);
+      float pdf_rev = phase_function(w_o_smp, w_i, med.phase_function_g);
+      state.d_vc = (1.0f / pdf_fwd) * (state.d_vc * pdf_rev + state.d_vcm);
+      state.d_vm = (1.0f / pdf_fwd) * (state.d_vm * pdf_rev + 0.0f);
+      state.d_vcm = 1.0f / pdf_fwd;
+      state.ray_o = medium_pos;
+      state.ray_d = w_o_smp;
+      state.ray_max_t = kMaxFloat;
+      state.ray_min_t = kRayEpsilon;
+      state.total_path_depth += 1;
+      alive = (state.total_path_depth + 1 <= sc.max_path_length) &&
+              random_continue<SP>(state.total_path_depth, sc.random_path_termination, state.eta, state.sampler, state.throughput);
+    } else if (at_surface && !(ss_path && !ss_sampled)) {
+      if (ss_sampled) {
+        // :1237-1249 — continue from the selected exit with a cosine lobe; the light step keeps the hit's own material
+        state.throughput *= ssg.weights[ssg.selected] * ssg.selected_sample_weight;
+        isect = ss_exit_intersection<SP>(sc, ssg, ssg.selected, isect.material_index);
+        bs.w_o = sample_cosine_around(state.sampler.next_2d(), isect.nrm, 1.0f);
+        bs.pdf = fabsf(dot(bs.w_o, isect.nrm)) / kPi;
+        bs.eta = 1.0f;
+      }
+      BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathLight);
+      if (vcm_next_ray<SP>(sc, true, state, p.vcm, isect, bsdf_data, bs, ss_sampled)) {
+        alive = state.total_path_depth + 1u < sc.max_path_length;
       }
     }
     p.paths.lv_count[i] = state.lv_count;
@@ -471,35 +510,45 @@ DEV uint32_t merge_query_key(const GridData& g, V3 pos) {
 constexpr uint32_t kBounceResolvedAlive = 0x80000001u;
 constexpr uint32_t kBounceResolvedDead = 0x80000000u;
 
-// emit / run the camera-vertex x light-vertex connections of one endpoint
+// bs_props.x flag: the pending sample leaves from a subsurface exit point — the hit record holds the exit, ray_d holds its w_i, and the
+// vertex uses the scene's exit material (vcm_shared.hxx:1062-1064)
+constexpr uint32_t kBounceSubsurfaceExit = 0x40000000u;
+
+// the camera vertex the merge / continue stages work on, rebuilt from the path's hit record
 template <bool SP>
-DEV void camera_vertex_connections(const LaunchParams& p, uint32_t i, const Endpoint& ep, PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays, uint32_t& connections) {
+DEV Isect stage_intersection(const LaunchParams& p, const PathState<SP>& state, uint32_t i, float4 hit) {
+  Isect isect = make_intersection(p.scene, state.ray_d, __float_as_uint(hit.w), hit.x, hit.y, hit.z);
+  if (p.scene.has_subsurface && (p.paths.bs_props[i].x & kBounceSubsurfaceExit)) isect.material_index = p.scene.subsurface_exit_material;
+  return isect;
+}
+
+// Scenes with stochastic BSDFs (product build): the camera-vertex x light-vertex connections (vcm_shared.hxx:765-803) become their
+// own wavefront stage, one thread per connection (k_camera_connect); the shade stage only emits the work list.
+template <bool SP>
+DEV void camera_emit_connections(const LaunchParams& p, uint32_t i, PathState<SP>& state, uint32_t& connections) {
   const DeviceScene& sc = p.scene;
-  if (!p.connect_stage) {
-    // reference order: serial over the paired path's vertices with the path's own sampler
-    state.gathered += vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], ep, state, stats, shadow_rays, connections);
-  } else if (p.vcm.connect_vertices()) {
-    // scenes with stochastic BSDFs (product build): the connections (vcm_shared.hxx:765-803) become their own wavefront stage,
-    // one thread per connection (k_camera_connect); here only the work list is emitted
-    uint32_t lp_count = p.paths.lv_count[i];
-    uint32_t d2 = state.total_path_depth + 2u;  // target_path_length = depth + k + 2 must lie in [min_path_length, max_path_length]
-    uint32_t k_begin = (sc.min_path_length > d2) ? (sc.min_path_length - d2) : 0u;
-    uint32_t k_end = (sc.max_path_length >= d2) ? umin(lp_count, sc.max_path_length - d2 + 1u) : 0u;
-    if (k_end > k_begin) {
-      uint32_t cnt = k_end - k_begin;
-      uint32_t base = atomicAdd(p.conn_count, cnt);
-      if (base + cnt <= p.conn_capacity) {
-        for (uint32_t k = 0; k < cnt; ++k) p.conn_list[base + k] = make_uint2(i, k_begin + k);
-      } else {
-        *p.overflow = 1u;
-      }
-      p.paths.conn_seed[i] = state.sampler.seed;
-      state.sampler.next();  // the path's own stream moves on by one draw for the whole stage
-      connections += cnt;
+  if (p.vcm.connect_vertices() == false) return;
+  uint32_t lp_count = p.paths.lv_count[i];
+  uint32_t d2 = state.total_path_depth + 2u;  // target_path_length = depth + k + 2 must lie in [min_path_length, max_path_length]
+  uint32_t k_begin = (sc.min_path_length > d2) ? (sc.min_path_length - d2) : 0u;
+  uint32_t k_end = (sc.max_path_length >= d2) ? umin(lp_count, sc.max_path_length - d2 + 1u) : 0u;
+  if (k_end > k_begin) {
+    uint32_t cnt = k_end - k_begin;
+    uint32_t base = atomicAdd(p.conn_count, cnt);
+    if (base + cnt <= p.conn_capacity) {
+      for (uint32_t k = 0; k < cnt; ++k) p.conn_list[base + k] = make_uint2(i, k_begin + k);
+    } else {
+      *p.overflow = 1u;
     }
+    p.paths.conn_seed[i] = state.sampler.seed;
+    state.sampler.next();  // the path's own stream moves on by one draw for the whole stage
+    connections += cnt;
   }
 }
 
+// vcm_camera_step (vcm_shared.hxx:921-1080) up to the merge: same three phases as k_light_bounce — (A) the event, (B) connections to
+// the paired light path and to a sampled emitter from the endpoint(s) the event produced (one, or every gathered subsurface exit,
+// :1037-1053), (C) the MIS update / pending continuation sample handed to the merge and continue stages.
 template <bool SP>
 __global__ void __launch_bounds__(128) k_camera_shade(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -517,69 +566,52 @@ __global__ void __launch_bounds__(128) k_camera_shade(LaunchParams p, const uint
     const bool found = tri_index != kInvalidIndex;
     uint2 resolved = make_uint2(kBounceResolvedDead, kInvalidIndex);
     bool pending_sample = false;
+    uint32_t ep_mode = kEpNone;
+    bool at_medium = false, at_surface = false, is_connectible = false, ss_path = false, ss_sampled = false;
+    V2 rnd_bsdf = {0.0f, 0.0f}, rnd_connection = {0.0f, 0.0f}, rnd_support = {0.0f, 0.0f};
+    V3 medium_pos = {0.0f, 0.0f, 0.0f};
+    Isect isect{};
+    BSample<SP> bs;
+    SSGather<SP> ssg;
+    ssg.count = 0;
+    // ---- (A) ----
     MediumSample<SP> medium_sample = vcm_try_sampling_medium<SP>(sc, state, found ? hit.z : kMaxFloat);
-    if (medium_sample.sampled_medium()) {
-      // :934-995
-      V2 rnd_bsdf = state.sampler.next_2d();
-      V2 rnd_connection = state.sampler.next_2d();
-      V2 rnd_support = state.sampler.next_2d();
-      if (p.vcm.blue_noise && (state.total_path_depth == 1) && (p.vcm.iteration < 256u)) {
-        uint32_t px = i % p.film.width, py = i / p.film.width;
-        rnd_bsdf = sample_blue_noise(sc, px, py, p.vcm.iteration, 0);
-        rnd_connection = sample_blue_noise(sc, px, py, p.vcm.iteration, 2);
-        rnd_support = sample_blue_noise(sc, px, py, p.vcm.iteration, 4);
-      }
-      float seg = state.path_distance + medium_sample.sampled_medium_t;
-      state.d_vcm *= sqr(seg);
-      state.path_distance = 0.0f;
-      const DMedium& med = sc.mediums[state.medium_index];
-      V3 w_o_smp = sample_phase_function(state.ray_d, med.phase_function_g, rnd_bsdf);
-      float pdf_fwd = phase_function(state.ray_d, w_o_smp, med.phase_function_g);
-      float pdf_rev = phase_function(w_o_smp, state.ray_d, med.phase_function_g);
-      if (med.enable_explicit_connections && (state.total_path_depth + 1 <= sc.max_path_length)) {
-        Endpoint ep{true, nullptr, medium_sample.pos};
-        if (p.vcm.connect_to_light()) {
-          state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
-          state.gathered += vcm_connect_to_light<SP>(sc, p.vcm, ep, state, stats, shadow_rays);
-          state.sampler.pop_fixed();
-        }
-        if (p.vcm.connect_vertices()) {
-          // medium endpoints always take the serial path (they are rare and need the pre-scatter direction)
-          state.gathered += vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], ep, state, stats, shadow_rays, connections);
-        }
-      }
-      state.d_vc = (1.0f / pdf_fwd) * (state.d_vc * pdf_rev + state.d_vcm);
-      state.d_vm = (1.0f / pdf_fwd) * (state.d_vm * pdf_rev + 0.0f);
-      state.d_vcm = 1.0f / pdf_fwd;
-      state.ray_o = medium_sample.pos;
-      state.ray_d = w_o_smp;
-      state.ray_max_t = kMaxFloat;
-      state.ray_min_t = kRayEpsilon;
-      state.total_path_depth += 1;
-      bool cont = !(state.total_path_depth + 1 > sc.max_path_length) &&
-                  random_continue<SP>(state.total_path_depth, sc.random_path_termination, state.eta, state.sampler, state.throughput);
-      resolved.x = cont ? kBounceResolvedAlive : kBounceResolvedDead;
-    } else if (!found) {
-      vcm_cam_handle_miss<SP>(sc, p.vcm, state.ray_d, state.d_vcm, state.d_vc, state.path_distance, state.total_path_depth, state.wavelength, state.throughput, state.gathered);
-    } else {
-      Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
-      if (vcm_handle_boundary<SP>(sc, isect, state)) {
-        resolved.x = kBounceResolvedAlive;  // :1002-1007
+    if (medium_sample.sampled_medium() || found) {
+      if (medium_sample.sampled_medium()) {
+        at_medium = true;
+        medium_pos = medium_sample.pos;
       } else {
-        const etxb_material& mat = sc.materials[isect.material_index];
-        BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
-        V2 rnd_bsdf = state.sampler.next_2d();
-        V2 rnd_connection = state.sampler.next_2d();
-        V2 rnd_support = state.sampler.next_2d();
+        isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
+        if (vcm_handle_boundary<SP>(sc, isect, state)) {
+          resolved.x = kBounceResolvedAlive;  // :1002-1007
+        } else {
+          at_surface = true;
+        }
+      }
+      if (at_medium || at_surface) {
+        rnd_bsdf = state.sampler.next_2d();
+        rnd_connection = state.sampler.next_2d();
+        rnd_support = state.sampler.next_2d();
         if (p.vcm.blue_noise && (state.total_path_depth == 1) && (p.vcm.iteration < 256u)) {
           uint32_t px = i % p.film.width, py = i / p.film.width;
           rnd_bsdf = sample_blue_noise(sc, px, py, p.vcm.iteration, 0);
           rnd_connection = sample_blue_noise(sc, px, py, p.vcm.iteration, 2);
           rnd_support = sample_blue_noise(sc, px, py, p.vcm.iteration, 4);
         }
+      }
+      if (at_medium) {
+        // :934-970
+        float seg = state.path_distance + medium_sample.sampled_medium_t;
+        state.d_vcm *= sqr(seg);
+        state.path_distance = 0.0f;
+        const DMedium& med = sc.mediums[state.medium_index];
+        if (med.enable_explicit_connections && (state.total_path_depth + 1 <= sc.max_path_length)) ep_mode = kEpMedium;
+      } else if (at_surface) {
+        const etxb_material& mat = sc.materials[isect.material_index];
+        BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
         state.sampler.push_fixed(rnd_bsdf.x, rnd_bsdf.y, rnd_support.x);
-        BSample<SP> bs = bsdf_sample<SP>(sc, bsdf_data, mat, state.sampler);
-        bool is_connectible = (bs.properties & kBsdfDelta) == 0;
+        bs = bsdf_sample<SP>(sc, bsdf_data, mat, state.sampler);
+        is_connectible = (bs.properties & kBsdfDelta) == 0;
         state.sampler.pop_fixed();
         // vcm_update_camera_vcm (:589-595)
         float cos_to_prev = fabsf(dot(isect.nrm, -state.ray_d));
@@ -588,22 +620,85 @@ __global__ void __launch_bounds__(128) k_camera_shade(LaunchParams p, const uint
         state.d_vm /= cos_to_prev;
         state.path_distance = 0.0f;
         vcm_handle_direct_hit<SP>(sc, p.vcm, isect, state);
-        if (is_connectible) {
-          Endpoint ep{false, &isect, {0.0f, 0.0f, 0.0f}};
-          camera_vertex_connections<SP>(p, i, ep, state, stats, shadow_rays, connections);
-          state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
-          state.gathered += vcm_connect_to_light<SP>(sc, p.vcm, ep, state, stats, shadow_rays);
-          state.sampler.pop_fixed();
-        }
-        if (is_connectible && p.vcm.merge_vertices() && (state.total_path_depth + 1 <= sc.max_path_length) && (p.grid.photon_count != 0u)) {
-          merge_key = merge_query_key(p.grid, isect.pos);
-        }
-        V3 w = bs.weight.as_v3();
-        p.paths.bs_weight_pdf[i] = make_float4(w.x, w.y, w.z, bs.pdf);
-        p.paths.bs_wo_eta[i] = make_float4(bs.w_o.x, bs.w_o.y, bs.w_o.z, bs.eta);
-        p.paths.bs_props[i] = make_uint2(bs.properties, bs.medium_index);
-        pending_sample = true;
+        ss_path = sc.has_subsurface && (bs.properties & kBsdfDiffuse) && (mat.subsurface.cls != 0u);
+        if (ss_path) ss_sampled = ss_gather<SP>(sc, state.wavelength, isect, state.sampler, ssg, stats, shadow_rays);
+        if (is_connectible) ep_mode = ss_sampled ? kEpSubsurface : kEpSurface;
       }
+    } else {
+      vcm_cam_handle_miss<SP>(sc, p.vcm, state.ray_d, state.d_vcm, state.d_vc, state.path_distance, state.total_path_depth, state.wavelength, state.throughput, state.gathered);
+    }
+    // ---- (B) ----
+    if (ep_mode != kEpNone) {
+      uint32_t n = (ep_mode == kEpSubsurface) ? ssg.count : 1u;
+      Isect ep_isect = isect;
+#pragma unroll 1
+      for (uint32_t k = 0; k < n; ++k) {
+        Spec<SP> w = Spec<SP>::make(1.0f);
+        if (ep_mode == kEpSubsurface) {
+          ep_isect = ss_exit_intersection<SP>(sc, ssg, k, sc.subsurface_exit_material);
+          w = ssg.weights[k];
+        }
+        Endpoint ep{ep_mode == kEpMedium, &ep_isect, medium_pos};  // one object behind the pointer: it stays in registers
+        // a surface vertex connects to the light path first and to the emitter second; a medium vertex the other way round (:961-970)
+#pragma unroll 1
+        for (uint32_t step = 0; step < 2u; ++step) {
+          Spec<SP> c;
+          if ((step == 0u) == (ep_mode == kEpMedium)) {
+            state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
+            c = vcm_connect_to_light<SP>(sc, p.vcm, ep, state, stats, shadow_rays);
+            state.sampler.pop_fixed();
+          } else if (p.connect_stage && (ep_mode == kEpSurface)) {
+            camera_emit_connections<SP>(p, i, state, connections);
+            continue;
+          } else {
+            // reference order: serial over the paired path's vertices with the path's own sampler
+            c = vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], ep, state, stats, shadow_rays, connections);
+          }
+          state.gathered += (ep_mode == kEpSubsurface) ? (w * c) : c;
+        }
+      }
+    }
+    // ---- (C) ----
+    if (at_medium) {
+      // :974-995
+      const DMedium& med = sc.mediums[state.medium_index];
+      V3 w_o_smp = sample_phase_function(state.ray_d, med.phase_function_g, rnd_bsdf);
+      float pdf_fwd = phase_function(state.ray_d, w_o_smp, med.phase_function_g);
+      float pdf_rev = phase_function(w_o_smp, state.ray_d, med.phase_function_g);
+      state.d_vc = (1.0f / pdf_fwd) * (state.d_vc * pdf_rev + state.d_vcm);
+      state.d_vm = (1.0f / pdf_fwd) * (state.d_vm * pdf_rev + 0.0f);
+      state.d_vcm = 1.0f / pdf_fwd;
+      state.ray_o = medium_pos;
+      state.ray_d = w_o_smp;
+      state.ray_max_t = kMaxFloat;
+      state.ray_min_t = kRayEpsilon;
+      state.total_path_depth += 1;
+      bool cont = !(state.total_path_depth + 1 > sc.max_path_length) &&
+                  random_continue<SP>(state.total_path_depth, sc.random_path_termination, state.eta, state.sampler, state.throughput);
+      resolved.x = cont ? kBounceResolvedAlive : kBounceResolvedDead;
+    } else if (at_surface) {
+      uint32_t ss_flag = 0u;
+      if (ss_sampled) {
+        // :1056-1067 — the vertex moves to the selected exit: the hit record, w_i (kept in ray_d) and the pending cosine-lobe sample are
+        // rewritten for the merge and continue stages
+        state.throughput *= ssg.weights[ssg.selected] * ssg.selected_sample_weight;
+        isect = ss_exit_intersection<SP>(sc, ssg, ssg.selected, sc.subsurface_exit_material);
+        bs.w_o = sample_cosine_around(state.sampler.next_2d(), isect.nrm, 1.0f);
+        bs.pdf = fabsf(dot(bs.w_o, isect.nrm)) / kPi;
+        bs.eta = 1.0f;
+        HitRec h = ssg.hits[ssg.selected];
+        p.paths.hit[i] = make_float4(h.u, h.v, h.t, __uint_as_float(h.tri));
+        state.ray_d = ssg.w_i[ssg.selected];
+        ss_flag = kBounceSubsurfaceExit;
+      }
+      if (is_connectible && p.vcm.merge_vertices() && (state.total_path_depth + 1 <= sc.max_path_length) && (p.grid.photon_count != 0u)) {
+        merge_key = merge_query_key(p.grid, isect.pos);
+      }
+      V3 w = bs.weight.as_v3();
+      p.paths.bs_weight_pdf[i] = make_float4(w.x, w.y, w.z, bs.pdf);
+      p.paths.bs_wo_eta[i] = make_float4(bs.w_o.x, bs.w_o.y, bs.w_o.z, bs.eta);
+      p.paths.bs_props[i] = make_uint2(bs.properties | ss_flag, bs.medium_index);
+      pending_sample = !(ss_path && !ss_sampled);  // a failed walk ends the path after the merge (:1072-1074)
     }
     if (!pending_sample) p.paths.bs_props[i] = resolved;
     store_state<SP>(p.paths, i, state);
@@ -678,7 +773,7 @@ __global__ void __launch_bounds__(128) k_camera_merge_serial(LaunchParams p, con
     float4 hit = p.paths.hit[i];
     uint32_t tri_index = __float_as_uint(hit.w);
     PathState<SP> state = load_state<SP>(p.paths, i);
-    Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
+    Isect isect = stage_intersection<SP>(p, state, i, hit);
 #if defined(ETXB_PARITY) && ETXB_PARITY
     const bool mine = true;
 #else
@@ -734,7 +829,7 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
     i = sorted_ids[q];
     float4 hit = p.paths.hit[i];
     PathState<SP> state = load_state<SP>(p.paths, i);
-    Isect isect = make_intersection(sc, state.ray_d, __float_as_uint(hit.w), hit.x, hit.y, hit.z);
+    Isect isect = stage_intersection<SP>(p, state, i, hit);
     const etxb_material& mat = sc.materials[isect.material_index];
     coop_active = merge_is_lambert(mat) != GENERIC;
     if (coop_active) {
@@ -960,7 +1055,7 @@ __global__ void __launch_bounds__(128) k_camera_continue(LaunchParams p, const u
     if (bp.x & 0x80000000u) {
       alive = bp.x == kBounceResolvedAlive;  // medium scattering / boundary crossing / miss: the shade stage already advanced the path
     } else if (tri_index != kInvalidIndex) {
-      Isect isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
+      Isect isect = stage_intersection<SP>(p, state, i, hit);
       BData bsdf_data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
       float4 bw = p.paths.bs_weight_pdf[i], bd = p.paths.bs_wo_eta[i];
       BSample<SP> bs;
@@ -968,9 +1063,9 @@ __global__ void __launch_bounds__(128) k_camera_continue(LaunchParams p, const u
       bs.pdf = bw.w;
       bs.w_o = {bd.x, bd.y, bd.z};
       bs.eta = bd.w;
-      bs.properties = bp.x;
+      bs.properties = bp.x & ~kBounceSubsurfaceExit;
       bs.medium_index = bp.y;
-      alive = vcm_next_ray<SP>(sc, false, state, p.vcm, isect, bsdf_data, bs);
+      alive = vcm_next_ray<SP>(sc, false, state, p.vcm, isect, bsdf_data, bs, (bp.x & kBounceSubsurfaceExit) != 0u);
     }
     if (alive) {
       store_state<SP>(p.paths, i, state);

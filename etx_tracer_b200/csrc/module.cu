@@ -621,7 +621,12 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
     const etxb_material& m = mats[i];
     if (!material_class_supported_host(m.cls)) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: class %u is not supported on the device yet", (unsigned long long)i, m.cls);
     if (m.diffuse_variation != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: diffuse_variation %u is not supported on the device yet", (unsigned long long)i, m.diffuse_variation);
-    if (m.subsurface.cls != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: subsurface scattering is not supported on the device yet", (unsigned long long)i);
+    if (m.subsurface.cls > 2u) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu: unknown subsurface class %u", (unsigned long long)i, m.subsurface.cls);
+    if (m.subsurface.cls != 0) {
+      if (s.subsurface_exit_material >= s.materials.count) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu uses subsurface scattering but scene.subsurface_exit_material is not set", (unsigned long long)i);
+      if ((m.subsurface.image_index != ETXB_INVALID_INDEX) && (m.subsurface.image_index >= s.images.count))
+        return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu: subsurface image index out of range", (unsigned long long)i);
+    }
     uint32_t imgs[] = {m.reflectance.image_index, m.scattering.image_index, m.emission.image_index, m.roughness.image_index, m.normal_image_index, m.thinfilm.thickness_image};
     for (uint32_t im : imgs)
       if ((im != ETXB_INVALID_INDEX) && (im >= s.images.count)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu: image index %u out of range", (unsigned long long)i, im);
@@ -682,8 +687,12 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
     ctx->dscene.mediums = ctx->mediums.ptr;
     ctx->dscene.medium_count = uint32_t(dmeds.size());
     ctx->dscene.has_boundaries = 0;
-    for (uint64_t i = 0; i < s.materials.count; ++i)
+    ctx->dscene.has_subsurface = 0;
+    ctx->dscene.subsurface_exit_material = s.subsurface_exit_material;
+    for (uint64_t i = 0; i < s.materials.count; ++i) {
       if (mats[i].cls == ETXB_MAT_BOUNDARY) ctx->dscene.has_boundaries = 1;
+      if (mats[i].subsurface.cls != 0) ctx->dscene.has_subsurface = 1;
+    }
     if ((cam.medium_index != ETXB_INVALID_INDEX) && (cam.medium_index >= s.mediums.count)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "camera medium index out of range");
   }
   // ---- images: pixels + flattened row/column CDFs (image.hxx:8-50) ---------------------------------------------------------------

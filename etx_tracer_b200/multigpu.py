@@ -48,11 +48,18 @@ def as_tensor(ptr, nbytes, dtype="<f4", device="cuda"):
 class ShardedVCM:
     """Drives GPUVCM instances of all ranks through one iteration with the exchanges in between."""
 
-    def __init__(self, gpu, dist, rank, world):
+    def __init__(self, gpu, dist, rank, world, device="cuda", view=as_tensor):
+        """`gpu` is an api.GPUVCM; `device`/`view` exist so the exchange logic can be driven on CPU tensors over gloo
+        (tests/test_multigpu_host.py) with a stand-in that exposes the same light_pass / grid_build / camera_pass / device_pointer."""
         import torch
         self.g, self.dist, self.rank, self.world, self.torch = gpu, dist, rank, world, torch
+        self.device, self.view = device, view
         gpu.set_partition(rank, world)
         self._gather_buf = None
+
+    def _sync(self):
+        if self.device == "cuda":
+            self.torch.cuda.current_stream().synchronize()
 
     def merging(self):
         o = int(self.g.options["options"][0])
@@ -62,23 +69,27 @@ class ShardedVCM:
         torch, dist, g = self.torch, self.dist, self.g
         g.light_pass()
         ptr, nbytes = g.device_pointer(S.BUF_FILM_LIGHT_ITERATION)
-        dist.all_reduce(as_tensor(ptr, nbytes), op=dist.ReduceOp.SUM)
+        dist.all_reduce(self.view(ptr, nbytes), op=dist.ReduceOp.SUM)
         records_ptr, total = None, 0
         if self.merging():
             ptr, nbytes = g.device_pointer(S.BUF_PHOTON_RECORDS)
             mine = nbytes // RECORD_BYTES
-            counts = torch.zeros(self.world, dtype=torch.int64, device="cuda")
-            dist.all_gather_into_tensor(counts, torch.tensor([mine], dtype=torch.int64, device="cuda"))
+            counts = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(counts, torch.tensor([mine], dtype=torch.int64, device=self.device))
             counts = counts.tolist()
             offsets, total = gather_layout(counts)
             need = max(total, 1) * RECORD_BYTES // 4
             if self._gather_buf is None or self._gather_buf.numel() < need:
-                self._gather_buf = torch.empty(int(need * 1.25) + 1024, dtype=torch.float32, device="cuda")
+                self._gather_buf = torch.empty(int(need * 1.25) + 1024, dtype=torch.float32, device=self.device)
             outs = [self._gather_buf[offsets[r] * RECORD_BYTES // 4:(offsets[r] + counts[r]) * RECORD_BYTES // 4] for r in range(self.world)]
-            src = as_tensor(ptr, nbytes) if mine else torch.empty(0, dtype=torch.float32, device="cuda")
-            dist.all_gather(outs, src)  # uneven sizes: NCCL falls back to grouped broadcasts
+            if mine:
+                outs[self.rank].copy_(self.view(ptr, nbytes))
+            # blocks differ in size per rank: one broadcast per owner into its slice (what an uneven all_gather lowers to)
+            pending = [dist.broadcast(outs[r], src=r, async_op=True) for r in range(self.world) if counts[r]]
+            for work in pending:
+                work.wait()
             records_ptr = self._gather_buf.data_ptr()
-        torch.cuda.current_stream().synchronize()
+        self._sync()
         g.grid_build(records_ptr, total)
         g.camera_pass()
 
@@ -86,6 +97,6 @@ class ShardedVCM:
         """Sum the (disjoint) camera tiles on rank 0; returns the Result layer there, None elsewhere."""
         torch, dist, g = self.torch, self.dist, self.g
         ptr, nbytes = g.device_pointer(S.BUF_FILM_CAMERA)
-        dist.reduce(as_tensor(ptr, nbytes), dst=0, op=dist.ReduceOp.SUM)
-        torch.cuda.current_stream().synchronize()
+        dist.reduce(self.view(ptr, nbytes), dst=0, op=dist.ReduceOp.SUM)
+        self._sync()
         return g.film(S.FILM_RESULT) if self.rank == 0 else None

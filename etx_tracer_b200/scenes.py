@@ -100,7 +100,8 @@ class SceneData:
         return len(self.spectra) - 1
 
     def add_material(self, name, cls=S.MAT_DIFFUSE, kd=None, ks=None, roughness=0.0, emission=None, two_sided=0, int_ior=None,
-                     thinfilm=None, collimation=0.0, int_medium=S.INVALID, ext_medium=S.INVALID, diffuse_variation=0, metalness=0.0, transmission=0.0):
+                     thinfilm=None, collimation=0.0, int_medium=S.INVALID, ext_medium=S.INVALID, diffuse_variation=0, metalness=0.0, transmission=0.0,
+                     subsurface=None):
         m = np.zeros(1, dtype=S.MATERIAL)
         for fld in ("reflectance", "scattering", "emission"):
             m[fld]["spectrum_index"] = S.INVALID
@@ -148,6 +149,15 @@ class SceneData:
             m["thinfilm"]["ior"]["k_index"] = self.add_spectrum(k)
             m["thinfilm"]["min_thickness"] = tmin
             m["thinfilm"]["max_thickness"] = tmax
+        if subsurface is not None:
+            # "subsurface [refracted|diffuse-path] [burley] distances r g b scale s" (scene_representation.cxx:1972-2007)
+            m["subsurface"]["cls"] = {"random_walk": 1, "burley": 2}[subsurface.get("cls", "random_walk")]
+            m["subsurface"]["path"] = {"diffuse": 0, "refracted": 1}[subsurface.get("path", "diffuse")]
+            spd = spd_rgb_reflectance(subsurface.get("distances", [1.0, 0.2, 0.04]))
+            scale = f32(subsurface.get("scale", 1.0))
+            spd["entries"]["power"][0] = (spd["entries"]["power"][0] * scale).astype(f32)
+            spd["integrated"][0] = (spd["integrated"][0] * scale).astype(f32)
+            m["subsurface"]["spectrum_index"] = self.add_spectrum(spd)
         self.materials.append(m)
         self.material_names[name] = len(self.materials) - 1
         return len(self.materials) - 1
@@ -442,6 +452,15 @@ class SceneData:
         def_diel = self.add_spectrum(glass_eta)
         gold_eta, gold_k, _ = spd_named_ior("gold")
         def_cond_eta, def_cond_k = self.add_spectrum(gold_eta), self.add_spectrum(gold_k)
+        ss_scatter = ss_exit = S.INVALID
+        if any(int(m["subsurface"]["cls"][0]) != 0 for m in self.materials):
+            # init_default_values (scene_representation.cxx:216-224)
+            ss_scatter = self.add_material("etx::subsurface-scatter", cls=S.MAT_TRANSLUCENT)
+            self.materials[ss_scatter]["reflectance"]["spectrum_index"] = black
+            self.materials[ss_scatter]["scattering"]["spectrum_index"] = white
+            ss_exit = self.add_material("etx::subsurface-exit", cls=S.MAT_DIFFUSE)
+            self.materials[ss_exit]["reflectance"]["spectrum_index"] = white
+            self.materials[ss_exit]["scattering"]["spectrum_index"] = white
         for m in self.materials:
             if m["reflectance"]["spectrum_index"][0] == S.INVALID:
                 m["reflectance"]["spectrum_index"] = white
@@ -573,8 +592,10 @@ class SceneData:
         sc["radiance_clamp"] = 0.0
         sc["black_spectrum"] = black
         sc["white_spectrum"] = white
-        for fld in ("rayleigh_spectrum", "mie_spectrum", "ozone_spectrum", "subsurface_scatter_material", "subsurface_exit_material"):
+        for fld in ("rayleigh_spectrum", "mie_spectrum", "ozone_spectrum"):
             sc[fld] = S.INVALID
+        sc["subsurface_scatter_material"] = ss_scatter
+        sc["subsurface_exit_material"] = ss_exit
         sc["default_dielectric_eta"] = def_diel
         sc["default_conductor_eta"] = def_cond_eta
         sc["default_conductor_k"] = def_cond_k
@@ -649,6 +670,11 @@ MATERIAL_KINDS = {
     "velvet": dict(cls=S.MAT_VELVET, kd=[0.6, 0.1, 0.1], ks=[0.5, 0.5, 0.5], roughness=0.7),
     "principled": dict(cls=S.MAT_PRINCIPLED, kd=[0.8, 0.5, 0.2], ks=[1.0, 1.0, 1.0], roughness=0.5, metalness=0.4, transmission=0.3),
     "void": dict(cls=S.MAT_VOID),
+    # subsurface scattering on top of a diffuse-lobe class (material.hxx:36-51)
+    "sss_random_walk": dict(kd=[0.8, 0.6, 0.4], subsurface=dict(cls="random_walk", path="diffuse", distances=[1.0, 0.4, 0.15], scale=0.12)),
+    "sss_refracted": dict(cls=S.MAT_PLASTIC, kd=[0.7, 0.8, 0.6], ks=[1.0, 1.0, 1.0], roughness=0.3, int_ior="plastic",
+                          subsurface=dict(cls="random_walk", path="refracted", distances=[0.3, 0.6, 1.0], scale=0.1)),
+    "sss_burley": dict(kd=[0.9, 0.5, 0.4], subsurface=dict(cls="burley", distances=[1.0, 0.3, 0.1], scale=0.08)),
 }
 
 
