@@ -188,6 +188,9 @@ def main():
     ap.add_argument("--res", type=int, default=0, help="override the film size (debug only; the default is the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--parallelism", default="iteration", choices=["iteration", "tile"],
+                    help="N > 1: 'iteration' = every rank renders its own whole-frame iterations (weak scaling, no data-path collective); "
+                         "'tile' = pixel-tile sharding of each iteration (strong scaling, photon exchange per iteration)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -213,16 +216,29 @@ def main():
     sd, desc = workload(args)
     n_pixels = sd.width * sd.height
     g = GPUVCM(sd, flavor="fast", device=local_rank, profile=True)
-    sharded = None
-    if world > 1:
+    sharded = interleaved = None
+    if world > 1 and args.parallelism == "tile":
         from etx_tracer_b200.multigpu import ShardedVCM
         sharded = ShardedVCM(g, dist, rank, world)
+    elif world > 1:
+        from etx_tracer_b200.multigpu import InterleavedVCM
+        interleaved = InterleavedVCM(g, dist, rank, world)
+    # a step: tile mode = ONE iteration of the frame split over the ranks; iteration mode = one whole-frame iteration PER RANK
+    samples_per_step = n_pixels * (world if interleaved else 1)
+
+    def begin():
+        if interleaved:
+            interleaved.begin()
+        else:
+            g.run(0)
 
     def step():
         if sharded:
             sharded.iterate()
         else:
             g.iterate()
+            if interleaved:
+                interleaved.done += 1
 
     def sync_all():
         torch.cuda.synchronize()
@@ -231,7 +247,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ---------------------------------------------------------------------------------------------
-    g.run(0)
+    begin()
     for _ in range(args.warmup):
         step()
     g.wait()
@@ -254,20 +270,21 @@ def main():
     k1 = g.kernel_times()
     dev_s = st1["total_time"] - st0["total_time"]  # CUDA events on the module's stream around every iteration
     if world > 1:
-        # exchanges sit between the passes: use the barrier-to-barrier wall clock (max over ranks), device events cover the rest
-        t = torch.tensor([max(t_wall, dev_s)], dtype=torch.float64, device="cuda")
+        # iteration mode: device events, max over ranks.  tile mode: the exchanges sit between the passes, so the barrier-to-barrier wall
+        # clock (max over ranks) is what covers them
+        t = torch.tensor([dev_s if interleaved else max(t_wall, dev_s)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
     else:
         elapsed = dev_s
-    value = n_pixels * args.steps / elapsed / 1e6
+    value = samples_per_step * args.steps / elapsed / 1e6
     counters = {k: c1[k] - c0[k] for k in c1}
     ktimes = {k: (k1[k][0] - k0[k][0], k1[k][1] - k0[k][1]) for k in k1}
 
     # ---- end to end through the public API, host buffers inside the timed region ---------------------------------------------
     pinned = torch.empty((sd.height, sd.width, 4), dtype=torch.float32).pin_memory()
     host_film = pinned.numpy()
-    g.run(0)
+    begin()
     for _ in range(args.warmup):
         step()
     sync_all()
@@ -277,7 +294,11 @@ def main():
         step()
         if sharded:
             sharded.reduce_film()
-        if rank == 0:
+        if interleaved:
+            combined = interleaved.reduce_film()                      # mean over every rank's iterations, on rank 0
+            if rank == 0:
+                pinned.view(-1, 4).copy_(combined, non_blocking=False)  # device -> pinned host
+        elif rank == 0:
             g.film(S.FILM_RESULT, out=host_film)                      # device -> pinned host: the float4 Result layer (what the UI reads each frame)
     sync_all()
     e2e_s = time.time() - t0
@@ -285,7 +306,7 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": n_pixels * args.steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(g.options.nbytes), "d2h_bytes_per_step": int(host_film.nbytes)}
+    e2e = {"value": samples_per_step * args.steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(g.options.nbytes), "d2h_bytes_per_step": int(host_film.nbytes)}
 
     if rank == 0:
         peaks = measured_peaks()
@@ -317,8 +338,9 @@ def main():
             from etx_tracer_b200 import scenes
             cpu, _ = cpu_baseline_run(lambda res: scene_factory(args, res), args.cpu_budget, os.cpu_count() or 1)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "parallelism": f"pixel-tile x{world}" if world > 1 else "single GPU", "l2": "inputs larger than L2 (path state + light-vertex pool + photon grid > 126 MB)",
+                "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak" if interleaved else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "parallelism": (f"iteration-interleaved x{world}: each step every rank renders one whole-frame iteration (indices rank + j*{world}), film reduce at the end"
+                                           if interleaved else f"pixel-tile x{world}, photon exchange per iteration") if world > 1 else "single GPU", "l2": "inputs larger than L2 (path state + light-vertex pool + photon grid > 126 MB)",
                            "light_vertices_per_iteration": st1["light_vertices"], "per_kernel_event_timing": True},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(counters["kernel_launches"]), "clocks": clk,
                 "counters": counters}

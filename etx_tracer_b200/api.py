@@ -44,6 +44,8 @@ def load_library(flavor="fast"):
     lib.etxb_options_set_key.argtypes = [vp, C.c_char_p, C.c_double]
     lib.etxb_set_options.argtypes = [vp, vp]
     lib.etxb_set_partition.argtypes = [vp, u32, u32]
+    if hasattr(lib, "etxb_set_iteration_stride"):  # absent only from older builds loaded through the ETXB_LIB_* override
+        lib.etxb_set_iteration_stride.argtypes = [vp, u32]
     lib.etxb_begin.argtypes = [vp, u32]
     lib.etxb_enqueue_iteration.argtypes = [vp]
     lib.etxb_enqueue_light_pass.argtypes = [vp]
@@ -142,6 +144,10 @@ class GPUVCM:
 
     def set_partition(self, rank, world):
         self._check(self.lib.etxb_set_partition(self.h, rank, world))
+
+    def set_iteration_stride(self, stride):
+        """This context renders iterations first, first + stride, ... (iteration-interleaved multi-GPU runs)."""
+        self._check(self.lib.etxb_set_iteration_stride(self.h, stride))
 
     def run(self, first_iteration=0):
         """CPUVCM::run -> CPUVCMImpl::start: clears the film and arms iteration 0."""

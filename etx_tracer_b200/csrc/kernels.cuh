@@ -805,7 +805,8 @@ constexpr uint32_t kMergeListSize = 64;
 //                  index), and the path's sampler advances by one draw per query — statistically equivalent to the reference's
 //                  serial order (which the parity build keeps), 32x more parallel.
 template <bool SP, bool GENERIC>
-__global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys, const uint32_t* count_in) {
+__global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys, const uint32_t* count_in,
+                                                                                uint32_t queries_per_warp) {
   __shared__ uint32_t s_idx[kMergeWarpsPerBlock][kMergeListSize];
   __shared__ float s_d2[kMergeWarpsPerBlock][kMergeListSize];
   __shared__ float s_dvcm[kMergeWarpsPerBlock][kMergeListSize];
@@ -813,9 +814,11 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
   const GridData& g = p.grid;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lane_lt = (1u << lane) - 1u;
-  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  // A warp works through its queries one after the other, so a query's latency is paid `queries_per_warp` times per warp: 32 when the
+  // queue is long (every lane brings one query), fewer when it is short (the tail of the pass), so that the queries spread over more warps.
+  uint32_t q = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * queries_per_warp + lane;
   uint32_t merge_queries = 0, candidates = 0, accepts = 0;
-  bool coop_active = (q < *count_in) && (sorted_keys[q] != 0xffffffffu);
+  bool coop_active = (lane < queries_per_warp) && (q < *count_in) && (sorted_keys[q] != 0xffffffffu);
   uint32_t i = 0;
   V3 qpos = {0, 0, 0}, qnrm = {0, 0, 0}, qfn = {0, 0, 0}, qc = {0, 0, 0};
   float q_wcam_base = 0.0f, q_dvm = 0.0f, q_rev_cos = 0.0f;

@@ -126,6 +126,7 @@ struct etxb_ctx {
 
   etxb_vcm_options options = {};
   uint32_t iteration = 0;            // absolute iteration index (VCMIteration::iteration)
+  uint32_t iteration_stride = 1;     // etxb_set_iteration_stride: this context renders iterations first, first + stride, ...
   uint32_t completed = 0;            // iterations finished since etxb_begin
   uint32_t rank = 0, world = 1;
   uint32_t last_light_vertices = 0;
@@ -266,11 +267,27 @@ LaunchParams make_params(etxb_ctx* ctx) {
 }
 
 uint32_t blocks_for(uint32_t n, uint32_t block) { return (n + block - 1u) / block; }
+constexpr uint32_t kMergeSortMinQueries = 16384u;  // below this the merge queries are not sorted
+constexpr uint32_t kMergeMinWarps = 148u * 32u;    // the merge wants at least this many warps in flight (148 SMs)
 
 int read_u32(etxb_ctx* ctx, const uint32_t* dptr, uint32_t& out) {
   CUDA_OK(ctx, cudaMemcpyAsync(&out, dptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return ETXB_OK;
+}
+
+// Size of the next bounce's queue.  A long queue is read back every bounce (the grids are sized by it).  In the tail of a pass the
+// queue only shrinks and every kernel guards on the device-side count, so the previous size stays a valid upper bound for the launch
+// grids: the host then enqueues several bounces back to back and reads the count only every kTailBatch bounces.
+constexpr uint32_t kTailQueue = 8192u;
+constexpr uint32_t kTailBatch = 4u;
+int next_queue_size(etxb_ctx* ctx, const uint32_t* dptr, uint32_t& active, uint32_t& unsynced) {
+  if ((active < kTailQueue) && (unsynced + 1u < kTailBatch)) {
+    unsynced += 1u;
+    return ETXB_OK;
+  }
+  unsynced = 0;
+  return read_u32(ctx, dptr, active);
 }
 
 template <bool SP>
@@ -287,7 +304,7 @@ int run_light_pass(etxb_ctx* ctx) {
   }
   uint32_t active = 0;
   if (int rc = read_u32(ctx, counts + 0, active)) return rc;
-  uint32_t cur = 0;
+  uint32_t cur = 0, unsynced = 0;
   while (active > 0) {
     {
       LaunchTimer t(ctx, K_TRACE_LIGHT);
@@ -300,7 +317,7 @@ int run_light_pass(etxb_ctx* ctx) {
     }
     cur ^= 1u;
     std::swap(qin, qout);
-    if (int rc = read_u32(ctx, counts + cur, active)) return rc;
+    if (int rc = next_queue_size(ctx, counts + cur, active, unsynced)) return rc;
   }
   CUDA_OK(ctx, cudaGetLastError());
 
@@ -335,7 +352,10 @@ int run_grid_build(etxb_ctx* ctx, const LightVertexRec* records, uint32_t count)
     // complete_light_vertices -> Film::commit_light_iteration(iteration) (vcm_cpu.cxx:209-211); in a multi-GPU run the
     // host has all-reduced ETXB_BUF_FILM_LIGHT_ITERATION across ranks before this call
     LaunchTimer t(ctx, K_FILM_COMMIT);
-    k_film_commit_light<<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(p.film, ctx->iteration);
+    // the running mean counts the iterations THIS context has accumulated; that is the absolute index unless iterations are interleaved
+    // across contexts (etxb_set_iteration_stride)
+    uint32_t sample_index = (ctx->iteration_stride == 1u) ? ctx->iteration : ctx->completed;
+    k_film_commit_light<<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(p.film, sample_index);
   }
   bool merging = (ctx->options.options & ETXB_VCM_ENABLE_MERGING) && (ctx->options.options & ETXB_VCM_MERGE_VERTICES);
   if (!merging || (count == 0)) return ETXB_OK;
@@ -406,7 +426,7 @@ int run_camera_pass(etxb_ctx* ctx) {
   }
   uint32_t active = 0;
   if (int rc = read_u32(ctx, counts + 0, active)) return rc;
-  uint32_t cur = 0;
+  uint32_t cur = 0, unsynced = 0;
   const bool merging = (ctx->options.options & ETXB_VCM_ENABLE_MERGING) && (ctx->options.options & ETXB_VCM_MERGE_VERTICES);
   while (active > 0) {
     {
@@ -435,20 +455,29 @@ int run_camera_pass(etxb_ctx* ctx) {
     }
 #else
     if (merging && ctx->grid.photon_count) {
-      {
-        // queries sorted by the Morton code of their base cell: neighbours in the queue read the same photon cells
+      const uint32_t* ids = qin;
+      const uint32_t* keys = ctx->merge_key.ptr;
+      if (active >= kMergeSortMinQueries) {
+        // queries sorted by the Morton code of their base cell: neighbours in the queue read the same photon cells.  A short queue
+        // (the tail of the pass) is latency bound, not bandwidth bound: it goes in queue order and saves the sort launches.
         LaunchTimer t(ctx, K_CAMERA_MERGE_SORT);
         size_t temp_bytes = ctx->cub_temp.bytes();
         CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->merge_key.ptr, ctx->keys_out.ptr, qin, ctx->vals_out.ptr, int(active), 0, 32,
                        ctx->stream));
+        ids = ctx->vals_out.ptr;
+        keys = ctx->keys_out.ptr;
       }
+      // queries per warp: 32 while that still fills the machine, fewer for short queues (a warp serialises its queries)
+      uint32_t qpw = 32u;
+      while ((qpw > 1u) && (active / qpw < kMergeMinWarps)) qpw >>= 1;
+      const uint32_t merge_blocks = blocks_for(blocks_for(active, qpw), kMergeWarpsPerBlock);
       {
         LaunchTimer t(ctx, K_CAMERA_MERGE);
-        k_camera_merge_coop<SP, false><<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, ctx->vals_out.ptr, ctx->keys_out.ptr, counts + cur);
+        k_camera_merge_coop<SP, false><<<merge_blocks, kMergeWarpsPerBlock * 32, 0, ctx->stream>>>(p, ids, keys, counts + cur, qpw);
       }
       if (ctx->has_stochastic_merge) {
         LaunchTimer t(ctx, K_CAMERA_MERGE_SERIAL);
-        k_camera_merge_coop<SP, true><<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, ctx->vals_out.ptr, ctx->keys_out.ptr, counts + cur);
+        k_camera_merge_coop<SP, true><<<merge_blocks, kMergeWarpsPerBlock * 32, 0, ctx->stream>>>(p, ids, keys, counts + cur, qpw);
       }
     }
 #endif
@@ -458,7 +487,7 @@ int run_camera_pass(etxb_ctx* ctx) {
     }
     cur ^= 1u;
     std::swap(qin, qout);
-    if (int rc = read_u32(ctx, counts + cur, active)) return rc;
+    if (int rc = next_queue_size(ctx, counts + cur, active, unsynced)) return rc;
   }
   CUDA_OK(ctx, cudaGetLastError());
   return ETXB_OK;
@@ -482,7 +511,7 @@ int finish_iteration(etxb_ctx* ctx) {
   ctx->total_time += ctx->last_iteration_time;
   resolve_timers(ctx);
   ctx->completed += 1;
-  ctx->iteration += 1;
+  ctx->iteration += ctx->iteration_stride;
   ctx->light_pass_done = false;
   ctx->grid_done = false;
   return ETXB_OK;
@@ -903,6 +932,12 @@ int etxb_set_partition(etxb_ctx* ctx, uint32_t rank, uint32_t world) {
   if (!ctx || world == 0 || rank >= world) return ETXB_ERR_INVALID_ARGUMENT;
   ctx->rank = rank;
   ctx->world = world;
+  return ETXB_OK;
+}
+
+int etxb_set_iteration_stride(etxb_ctx* ctx, uint32_t stride) {
+  if (!ctx || (stride == 0u)) return ETXB_ERR_INVALID_ARGUMENT;
+  ctx->iteration_stride = stride;
   return ETXB_OK;
 }
 

@@ -1,4 +1,16 @@
-"""Pixel-tile sharding of one VCM iteration across ranks (one process per GPU), SURVEY.md §8(e).
+"""Multi-GPU drivers (one process per GPU), SURVEY.md §8(e).
+
+Two ways to spread a render over the ranks:
+
+* InterleavedVCM (default of bench.py): the unit of work is one ITERATION of the whole frame.  Rank r renders iterations r, r + N,
+  r + 2N, ... (the iteration index drives the merge radius and the sampler seeds, so the set of iterations rendered is exactly the
+  single-GPU sequence); there is no data-path collective, only one reduce of the float4 film when a frame is wanted.  VCM
+  iterations are independent by construction (vcm_cpu.cxx:95-113), and this keeps every GPU on full-size wavefronts.
+* ShardedVCM: pixel-tile sharding of ONE iteration, below.  Needed when a single iteration must finish sooner (interactive
+  preview); it pays for replicating the photon map on every rank and for the latency-bound tails of the bounce loops, which do not
+  shrink with the tile count.
+
+Pixel-tile sharding of one VCM iteration across ranks:
 
 Per iteration:  light pass on the rank's tiles  ->  all-reduce(sum) of the per-iteration light image (splats land anywhere)
                 ->  all-gather of the ranks' photon records (the merge queries the GLOBAL photon map; skipped when merging is off)
@@ -56,6 +68,20 @@ class ShardedVCM:
         self.device, self.view = device, view
         gpu.set_partition(rank, world)
         self._gather_buf = None
+        self.phase_seconds = None  # set to {} to collect per-phase wall time (adds a device sync at every phase boundary)
+        self._t = 0.0
+
+    def _mark(self, name):
+        if self.phase_seconds is None:
+            return
+        import time
+        if self.device == "cuda":
+            self.g.wait()
+            self.torch.cuda.synchronize()
+        now = time.perf_counter()
+        if name is not None:
+            self.phase_seconds[name] = self.phase_seconds.get(name, 0.0) + (now - self._t)
+        self._t = now
 
     def _sync(self):
         if self.device == "cuda":
@@ -67,9 +93,12 @@ class ShardedVCM:
 
     def iterate(self):
         torch, dist, g = self.torch, self.dist, self.g
+        self._mark(None)
         g.light_pass()
+        self._mark("light_pass")
         ptr, nbytes = g.device_pointer(S.BUF_FILM_LIGHT_ITERATION)
         dist.all_reduce(self.view(ptr, nbytes), op=dist.ReduceOp.SUM)
+        self._mark("light_image_all_reduce")
         records_ptr, total = None, 0
         if self.merging():
             ptr, nbytes = g.device_pointer(S.BUF_PHOTON_RECORDS)
@@ -90,8 +119,11 @@ class ShardedVCM:
                 work.wait()
             records_ptr = self._gather_buf.data_ptr()
         self._sync()
+        self._mark("photon_exchange")
         g.grid_build(records_ptr, total)
+        self._mark("grid_build")
         g.camera_pass()
+        self._mark("camera_pass")
 
     def reduce_film(self):
         """Sum the (disjoint) camera tiles on rank 0; returns the Result layer there, None elsewhere."""
@@ -100,3 +132,54 @@ class ShardedVCM:
         dist.reduce(self.view(ptr, nbytes), dst=0, op=dist.ReduceOp.SUM)
         self._sync()
         return g.film(S.FILM_RESULT) if self.rank == 0 else None
+
+
+class InterleavedVCM:
+    """Iteration-interleaved rendering: rank r owns iterations r, r + world, r + 2 world, ...
+
+    `run_steps(k0, k1)` renders the global iterations k in [k0, k1) that belong to this rank.  `reduce_film()` combines the per-rank
+    films (each the mean over the iterations that rank rendered) into the mean over all iterations on rank 0:
+    sum_r n_r * film_r / sum_r n_r, one reduce per film layer."""
+
+    def __init__(self, gpu, dist, rank, world, device="cuda", view=as_tensor):
+        import torch
+        self.g, self.dist, self.rank, self.world, self.torch = gpu, dist, rank, world, torch
+        self.device, self.view = device, view
+        gpu.set_iteration_stride(world)
+        self.done = 0
+
+    def begin(self):
+        """Integrator::run: clears the film; this rank's first iteration is `rank`."""
+        self.g.run(self.rank)
+        self.done = 0
+
+    def owned(self, k0, k1):
+        return [k for k in range(k0, k1) if k % self.world == self.rank]
+
+    def run_steps(self, k0, k1):
+        n = len(self.owned(k0, k1))
+        for _ in range(n):
+            self.g.iterate()
+        self.done += n
+        return n
+
+    def reduce_film(self):
+        """Mean over all iterations rendered so far, on rank 0 (float4 camera + light layers -> Result layer); None elsewhere."""
+        torch, dist, g = self.torch, self.dist, self.g
+        if self.device == "cuda":
+            g.wait()
+        counts = torch.tensor([float(self.done)], dtype=torch.float64, device=self.device)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        total = float(counts.item())
+        weight = (self.done / total) if total > 0 else 0.0
+        layers = []
+        for buf in (S.BUF_FILM_CAMERA, S.BUF_FILM_LIGHT):
+            ptr, nbytes = g.device_pointer(buf)
+            t = self.view(ptr, nbytes) * weight  # out of place: the rank's own running mean stays intact
+            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+            layers.append(t)
+        if self.rank != 0:
+            return None
+        result = torch.clamp_min(layers[0] + layers[1], 0.0).view(-1, 4)  # Film::layer(Result) (film.cxx:381-418): max(0, camera + light)
+        result[:, 3] = 1.0
+        return result

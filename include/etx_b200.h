@@ -317,6 +317,11 @@ int etxb_set_options(etxb_ctx* ctx, const etxb_vcm_options* opt);
  * world == 1 (default) renders the full frame. */
 int etxb_set_partition(etxb_ctx* ctx, uint32_t rank, uint32_t world);
 
+/* Iteration-interleaved multi-GPU runs: this context renders iterations first_iteration, first_iteration + stride, ...
+ * (VCMIteration::iteration drives the merge radius, vcm_cpu.cxx:95-113, and the per-path sampler seeds, vcm_shared.hxx:286-300),
+ * and its film is the mean over the iterations it rendered.  Default stride 1 = the reference's sequence. */
+int etxb_set_iteration_stride(etxb_ctx* ctx, uint32_t stride);
+
 /* CPUVCMImpl::start (vcm_cpu.cxx:81-93): clears film, sets iteration = first_iteration. */
 int etxb_begin(etxb_ctx* ctx, uint32_t first_iteration);
 

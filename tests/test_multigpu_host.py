@@ -131,3 +131,64 @@ def test_tile_owner_is_a_partition():
 def test_gather_layout():
     assert multigpu.gather_layout([3, 0, 5]) == ([0, 3, 3], 8)
     assert multigpu.gather_layout([0]) == ([0], 0)
+
+
+class StandInIterationGPU:
+    """api.GPUVCM stand-in for InterleavedVCM: every iteration k contributes the constant k to the camera layer and 10 k to the light
+    layer; the films are running means over the iterations this context rendered."""
+
+    def __init__(self):
+        self.stride, self.iteration, self.rendered = 1, 0, []
+        self.t = {S.BUF_FILM_CAMERA: torch.zeros(H * W * 4), S.BUF_FILM_LIGHT: torch.zeros(H * W * 4)}
+
+    def set_iteration_stride(self, stride):
+        self.stride = stride
+
+    def run(self, first_iteration=0):
+        self.iteration, self.rendered = first_iteration, []
+        for t in self.t.values():
+            t.zero_()
+
+    def iterate(self):
+        n = len(self.rendered)
+        self.t[S.BUF_FILM_CAMERA].mul_(n / (n + 1.0)).add_(float(self.iteration) / (n + 1.0))
+        self.t[S.BUF_FILM_LIGHT].mul_(n / (n + 1.0)).add_(10.0 * self.iteration / (n + 1.0))
+        self.rendered.append(self.iteration)
+        self.iteration += self.stride
+
+    def device_pointer(self, buf):
+        return buf, self.t[buf].numel() * 4
+
+    def view(self, ptr, nbytes, dtype="<f4"):
+        return self.t[ptr][:nbytes // 4]
+
+
+def _interleaved_worker(rank, world, port, steps, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = StandInIterationGPU()
+        iv = multigpu.InterleavedVCM(g, dist, rank, world, device="cpu", view=g.view)
+        iv.begin()
+        iv.run_steps(0, 3)       # warm-up block
+        iv.run_steps(3, steps)   # timed block: the global step counter keeps running
+        film = iv.reduce_film()
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), rendered=np.array(g.rendered), film=np.zeros(0) if film is None else film.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("steps", [7, 8])
+def test_interleaved_iterations_over_gloo(tmp_path, steps):
+    """Iterations 0..steps-1 are rendered exactly once across the ranks, and the reduced film is their mean (rank 0 only)."""
+    world = 2
+    mp.spawn(_interleaved_worker, args=(world, _free_port(), steps, str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
+    assert sorted(np.concatenate([r[0]["rendered"], r[1]["rendered"]]).tolist()) == list(range(steps))
+    assert all(k % world == 0 for k in r[0]["rendered"]) and all(k % world == 1 for k in r[1]["rendered"])
+    mean = sum(range(steps)) / steps
+    film = r[0]["film"]
+    assert film.shape == (H * W, 4) and r[1]["film"].size == 0
+    np.testing.assert_allclose(film[:, 0], mean + 10.0 * mean, rtol=1e-6)
+    assert (film[:, 3] == 1.0).all()

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 from etx_tracer_b200 import scenes, structs as S
 from etx_tracer_b200.api import GPUVCM
-from etx_tracer_b200.multigpu import ShardedVCM
+from etx_tracer_b200.multigpu import ShardedVCM, InterleavedVCM
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -37,10 +37,32 @@ for name, sd in (("C2", scenes.cornell_box(res, res, samples=256, spectral=True,
             rc, rl = rel(cam, ref.film(S.FILM_CAMERA)), rel(light, ref.film(S.FILM_LIGHT))
             exact = bool(np.array_equal(cam[..., :3], ref.film(S.FILM_CAMERA)[..., :3]))
             print(f"{name} merging={merging} world={world}: camera rel-L2 {rc:.3e} (bit-identical: {exact}), light rel-L2 {rl:.3e}", flush=True)
-            ok &= (rc < 1e-4) and (rl < 1e-4)
+            # merging off: tiles are independent -> exact.  merging on: per-cell photon order differs from the single-GPU pool, so float sums
+            # round differently (1e-4); with stochastic BSDFs the per-lane merge streams see photons in another order -> Monte-Carlo level
+            stochastic = name != "C2"
+            ok &= (rc < ((2e-2 if stochastic else 1e-4) if merging else 1e-6)) and (rl < 1e-4)
             ref.close()
         g.close()
         dist.barrier()
+# iteration-interleaved mode: the union of the ranks' iterations is the single-GPU sequence, the reduced film is its mean
+sd = scenes.cornell_box(res, res, samples=256, spectral=True, sphere=True)
+g = GPUVCM(sd, flavor="fast", device=local)
+iv = InterleavedVCM(g, dist, rank, world)
+iv.begin()
+total_iterations = 2 * world + 1  # uneven on purpose: rank 0 renders one more than the others
+iv.run_steps(0, total_iterations)
+combined = iv.reduce_film()
+if rank == 0:
+    ref = GPUVCM(sd, flavor="fast", device=local)
+    ref.render(total_iterations)
+    a = combined.cpu().numpy().reshape(res, res, 4)[..., :3].astype(np.float64)
+    b = ref.film(S.FILM_RESULT)[..., :3].astype(np.float64)
+    r = float(np.sqrt(((a - b) ** 2).sum()) / np.sqrt((b ** 2).sum()))
+    print(f"interleaved world={world}: {total_iterations} iterations, result rel-L2 vs single GPU {r:.3e}", flush=True)
+    ok &= r < 1e-5
+    ref.close()
+g.close()
+dist.barrier()
 if rank == 0:
     print("MULTIGPU_CHECK", "OK" if ok else "FAILED", flush=True)
 dist.destroy_process_group()
