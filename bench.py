@@ -181,13 +181,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--res", type=int, default=0, help="override the film size (debug only; the default is the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--lanes", type=int, default=4, help="iterations in flight per GPU (etxb_group); 1 = the plain one-context pump")
     ap.add_argument("--parallelism", default="iteration", choices=["iteration", "tile"],
                     help="N > 1: 'iteration' = every rank renders its own whole-frame iterations (weak scaling, no data-path collective); "
                          "'tile' = pixel-tile sharding of each iteration (strong scaling, photon exchange per iteration)")
@@ -215,16 +216,24 @@ def main():
 
     sd, desc = workload(args)
     n_pixels = sd.width * sd.height
-    g = GPUVCM(sd, flavor="fast", device=local_rank, profile=True)
+    tile_mode = world > 1 and args.parallelism == "tile"
     sharded = interleaved = None
-    if world > 1 and args.parallelism == "tile":
+    if tile_mode:
+        # ONE iteration of the frame split over the ranks by pixel tile; photon exchange per iteration (strong scaling)
         from etx_tracer_b200.multigpu import ShardedVCM
+        g = GPUVCM(sd, flavor="fast", device=local_rank, profile=True)
         sharded = ShardedVCM(g, dist, rank, world)
-    elif world > 1:
-        from etx_tracer_b200.multigpu import InterleavedVCM
-        interleaved = InterleavedVCM(g, dist, rank, world)
-    # a step: tile mode = ONE iteration of the frame split over the ranks; iteration mode = one whole-frame iteration PER RANK
-    samples_per_step = n_pixels * (world if interleaved else 1)
+        lanes = 1
+    else:
+        # whole-frame iterations, `lanes` of them in flight per GPU; with N ranks, rank r renders indices r, r + N, ... (weak scaling:
+        # a step is one iteration PER RANK, no data-path collective)
+        from etx_tracer_b200.api import GPUVCMGroup
+        lanes = max(1, min(args.lanes, 8))
+        g = GPUVCMGroup(sd, lanes=lanes, flavor="fast", device=local_rank, profile=True)
+        if world > 1:
+            from etx_tracer_b200.multigpu import InterleavedVCM
+            interleaved = InterleavedVCM(g, dist, rank, world)
+    samples_per_step = n_pixels * (1 if tile_mode else world)
 
     def begin():
         if interleaved:
@@ -232,13 +241,13 @@ def main():
         else:
             g.run(0)
 
-    def step():
-        if sharded:
-            sharded.iterate()
+    def run_steps(n):
+        if tile_mode:
+            for _ in range(n):
+                sharded.iterate()
         else:
-            g.iterate()
-            if interleaved:
-                interleaved.done += 1
+            g.enqueue(n)
+        g.wait()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -248,9 +257,7 @@ def main():
 
     # ---- device-resident timing ---------------------------------------------------------------------------------------------
     begin()
-    for _ in range(args.warmup):
-        step()
-    g.wait()
+    run_steps(args.warmup)
     sync_all()
     st0 = g.status()
     c0 = g.counters()
@@ -259,54 +266,70 @@ def main():
     if rank == 0:
         clocks.start()
     t_wall = time.time()
-    for _ in range(args.steps):
-        step()
-    g.wait()
+    run_steps(args.steps)
     sync_all()
     t_wall = time.time() - t_wall
     clk = clocks.stop() if rank == 0 else None
     st1 = g.status()
     c1 = g.counters()
     k1 = g.kernel_times()
-    dev_s = st1["total_time"] - st0["total_time"]  # CUDA events on the module's stream around every iteration
+    # one context: CUDA events on the module's stream around every iteration.  several iterations in flight: the streams overlap, so the
+    # module reports the span from the first enqueue (every lane idle and synchronised) to the last lane's end-of-iteration synchronise
+    mod_s = st1["total_time"] - st0["total_time"]
+    elapsed = max(t_wall, mod_s) if tile_mode else mod_s  # tile mode: the exchanges sit between the passes, the wall clock covers them
     if world > 1:
-        # iteration mode: device events, max over ranks.  tile mode: the exchanges sit between the passes, so the barrier-to-barrier wall
-        # clock (max over ranks) is what covers them
-        t = torch.tensor([dev_s if interleaved else max(t_wall, dev_s)], dtype=torch.float64, device="cuda")
+        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
-    else:
-        elapsed = dev_s
     value = samples_per_step * args.steps / elapsed / 1e6
     counters = {k: c1[k] - c0[k] for k in c1}
     ktimes = {k: (k1[k][0] - k0[k][0], k1[k][1] - k0[k][1]) for k in k1}
 
     # ---- end to end through the public API, host buffers inside the timed region ---------------------------------------------
+    # every step: options host -> module, one more iteration queued, the current film device -> pinned host (what a UI pumping the
+    # integrator does each frame; with iterations in flight the per-step film is the mean over the iterations finished so far); the
+    # region ends when every queued iteration has finished and the final film is on the host
     pinned = torch.empty((sd.height, sd.width, 4), dtype=torch.float32).pin_memory()
     host_film = pinned.numpy()
     begin()
-    for _ in range(args.warmup):
-        step()
+    run_steps(args.warmup)
     sync_all()
     t0 = time.time()
+    film_reads = 0
     for _ in range(args.steps):
-        g._check(g.lib.etxb_set_options(g.h, g.options.ctypes.data))  # host -> module: the integrator options of this step
-        step()
-        if sharded:
+        if tile_mode:
+            g._check(g.lib.etxb_set_options(g.h, g.options.ctypes.data))
+            sharded.iterate()
             sharded.reduce_film()
-        if interleaved:
-            combined = interleaved.reduce_film()                      # mean over every rank's iterations, on rank 0
             if rank == 0:
-                pinned.view(-1, 4).copy_(combined, non_blocking=False)  # device -> pinned host
-        elif rank == 0:
-            g.film(S.FILM_RESULT, out=host_film)                      # device -> pinned host: the float4 Result layer (what the UI reads each frame)
+                g.film(S.FILM_RESULT, out=host_film)
+        else:
+            g.set_options()
+            g.enqueue(1)
+            if interleaved:
+                combined = interleaved.reduce_film()
+                if rank == 0:
+                    pinned.view(-1, 4).copy_(combined)
+            else:
+                g.film(S.FILM_RESULT, out=host_film)
+        film_reads += 1
+    g.wait()
+    if not tile_mode:
+        if interleaved:
+            combined = interleaved.reduce_film()
+            if rank == 0:
+                pinned.view(-1, 4).copy_(combined)
+        else:
+            g.film(S.FILM_RESULT, out=host_film)
+        film_reads += 1
     sync_all()
     e2e_s = time.time() - t0
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": samples_per_step * args.steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(g.options.nbytes), "d2h_bytes_per_step": int(host_film.nbytes)}
+    e2e = {"value": samples_per_step * args.steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(g.options.nbytes) * lanes,
+           "d2h_bytes_per_step": int(host_film.nbytes * film_reads / args.steps)}
 
     if rank == 0:
         peaks = measured_peaks()
@@ -338,9 +361,14 @@ def main():
             from etx_tracer_b200 import scenes
             cpu, _ = cpu_baseline_run(lambda res: scene_factory(args, res), args.cpu_budget, os.cpu_count() or 1)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak" if interleaved else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "parallelism": (f"iteration-interleaved x{world}: each step every rank renders one whole-frame iteration (indices rank + j*{world}), film reduce at the end"
-                                           if interleaved else f"pixel-tile x{world}, photon exchange per iteration") if world > 1 else "single GPU", "l2": "inputs larger than L2 (path state + light-vertex pool + photon grid > 126 MB)",
+                "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if tile_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc,
+                           "parallelism": (f"pixel-tile x{world}, photon exchange per iteration" if tile_mode else
+                                           f"{lanes} iterations in flight per GPU" + (f"; iteration-interleaved x{world}: a step = one whole-frame iteration per rank "
+                                                                                      f"(indices rank + j*{world}), one film reduce" if world > 1 else "")),
+                           "timing": ("barrier-to-barrier wall clock, max over ranks" if tile_mode else
+                                      "span from the first enqueue (all lanes idle, device synchronised) to the last lane's end-of-iteration stream synchronise, max over ranks"),
+                           "l2": "inputs larger than L2 (path state + light-vertex pool + photon grid > 126 MB)",
                            "light_vertices_per_iteration": st1["light_vertices"], "per_kernel_event_timing": True},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(counters["kernel_launches"]), "clocks": clk,
                 "counters": counters}

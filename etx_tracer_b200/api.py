@@ -43,6 +43,24 @@ def load_library(flavor="fast"):
     lib.etxb_options_default.restype = None
     lib.etxb_options_set_key.argtypes = [vp, C.c_char_p, C.c_double]
     lib.etxb_set_options.argtypes = [vp, vp]
+    if hasattr(lib, "etxb_group_create"):
+        lib.etxb_set_next_iteration.argtypes = [vp, u32]
+        lib.etxb_group_create.argtypes = [C.POINTER(vp), vp, u32]
+        lib.etxb_group_destroy.argtypes = [vp]
+        lib.etxb_group_destroy.restype = None
+        lib.etxb_group_lanes.argtypes = [vp]
+        lib.etxb_group_lanes.restype = u32
+        lib.etxb_group_lane.argtypes = [vp, u32]
+        lib.etxb_group_lane.restype = vp
+        lib.etxb_group_last_error.argtypes = [vp]
+        lib.etxb_group_last_error.restype = C.c_char_p
+        lib.etxb_group_begin.argtypes = [vp, u32]
+        lib.etxb_group_enqueue.argtypes = [vp, u32]
+        lib.etxb_group_wait.argtypes = [vp]
+        lib.etxb_group_poll.argtypes = [vp, vp]
+        lib.etxb_group_read_film.argtypes = [vp, u32, vp, u64]
+        lib.etxb_group_set_stride.argtypes = [vp, u32]
+        lib.etxb_group_combine.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u32)]
     lib.etxb_set_partition.argtypes = [vp, u32, u32]
     if hasattr(lib, "etxb_set_iteration_stride"):  # absent only from older builds loaded through the ETXB_LIB_* override
         lib.etxb_set_iteration_stride.argtypes = [vp, u32]
@@ -76,17 +94,21 @@ def _p(a):
 class GPUVCM:
     """`name()/run()/update()/stop()/status()/options` like the reference's CPUVCM, driving the CUDA module."""
 
-    def __init__(self, scene_data=None, flavor="fast", device=0, max_light_vertices=0, profile=False):
+    def __init__(self, scene_data=None, flavor="fast", device=0, max_light_vertices=0, profile=False, _adopt=None):
         self.lib = load_library(flavor)
         self.flavor = flavor
         self.h = C.c_void_p()
-        cfg = np.zeros(1, dtype=S.DEVICE_CONFIG)
-        cfg["device_index"] = device
-        cfg["max_light_vertices"] = max_light_vertices
-        cfg["flags"] = 1 if profile else 0
-        rc = self.lib.etxb_create(C.byref(self.h), _p(cfg))
-        if rc != 0:
-            raise EtxbError(rc, "etxb_create failed (no CUDA device? the module has no CPU fallback)")
+        self._owned = _adopt is None
+        if _adopt is not None:
+            self.h = C.c_void_p(_adopt)  # a lane of an etxb_group: the group owns the context
+        else:
+            cfg = np.zeros(1, dtype=S.DEVICE_CONFIG)
+            cfg["device_index"] = device
+            cfg["max_light_vertices"] = max_light_vertices
+            cfg["flags"] = 1 if profile else 0
+            rc = self.lib.etxb_create(C.byref(self.h), _p(cfg))
+            if rc != 0:
+                raise EtxbError(rc, "etxb_create failed (no CUDA device? the module has no CPU fallback)")
         self.options = S.default_vcm_options()
         self.scene_data = None
         self._running = False
@@ -106,7 +128,8 @@ class GPUVCM:
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:
-            self.lib.etxb_destroy(self.h)
+            if self._owned:
+                self.lib.etxb_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):
@@ -259,3 +282,98 @@ class GPUVCM:
         yy = np.ascontiguousarray(y, dtype=np.float32) if y is not None else None
         self._check(self.lib.etxb_debug_math(self.h, fn, _p(x), _p(yy) if yy is not None else None, x.shape[0], _p(out)))
         return out
+
+
+class GPUVCMGroup:
+    """Several iterations in flight on one device (etxb_group): `lanes` contexts, one host thread each inside the module, pulling
+    iteration indices from a shared counter.  Same Integrator-style surface as GPUVCM: run / enqueue / wait / status / film."""
+
+    def __init__(self, scene_data, lanes=4, flavor="fast", device=0, max_light_vertices=0, profile=False):
+        self.lib = load_library(flavor)
+        self.h = C.c_void_p()
+        cfg = np.zeros(1, dtype=S.DEVICE_CONFIG)
+        cfg["device_index"] = device
+        cfg["max_light_vertices"] = max_light_vertices
+        cfg["flags"] = 1 if profile else 0
+        rc = self.lib.etxb_group_create(C.byref(self.h), _p(cfg), lanes)
+        if rc != 0:
+            raise EtxbError(rc, "etxb_group_create failed (no CUDA device? the module has no CPU fallback)")
+        self.lanes = [GPUVCM(scene_data, flavor=flavor, _adopt=self.lib.etxb_group_lane(self.h, k)) for k in range(lanes)]
+        self.options = self.lanes[0].options
+        self.scene_data = scene_data
+        self.width, self.height = self.lanes[0].width, self.lanes[0].height
+
+    def _check(self, rc):
+        if rc < 0:
+            raise EtxbError(rc, self.lib.etxb_group_last_error(self.h).decode() or self.lib.etxb_last_error(self.lanes[0].h).decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            for g in self.lanes:
+                g.close()
+            self.lib.etxb_group_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_options(self):
+        """Pushes self.options (the Integrator options) to every lane."""
+        for g in self.lanes:
+            g._check(self.lib.etxb_set_options(g.h, _p(self.options)))
+
+    def run(self, first_iteration=0):
+        self.set_options()
+        self._check(self.lib.etxb_group_begin(self.h, first_iteration))
+
+    def set_stride(self, stride):
+        """Iteration-interleaved multi-GPU runs: this group renders indices first, first + stride, ..."""
+        self._check(self.lib.etxb_group_set_stride(self.h, stride))
+
+    def enqueue(self, iterations=1):
+        self._check(self.lib.etxb_group_enqueue(self.h, iterations))
+
+    def combined(self, layer=S.FILM_RESULT):
+        """(device pointer, bytes, iterations) of the combined layer, left on the device."""
+        ptr, n, done = C.c_void_p(), C.c_uint64(0), C.c_uint32(0)
+        self._check(self.lib.etxb_group_combine(self.h, layer, C.byref(ptr), C.byref(n), C.byref(done)))
+        return ptr.value, n.value, done.value
+
+    def wait(self):
+        self._check(self.lib.etxb_group_wait(self.h))
+
+    def render(self, iterations, first_iteration=0):
+        self.run(first_iteration)
+        self.enqueue(iterations)
+        self.wait()
+        return self.status()
+
+    def status(self):
+        st = np.zeros(1, dtype=S.STATUS)
+        self._check(self.lib.etxb_group_poll(self.h, _p(st)))
+        return {k: st[k][0].item() for k in st.dtype.names}
+
+    def film(self, layer=S.FILM_RESULT, out=None):
+        if out is None:
+            out = np.zeros((self.height, self.width, 4), dtype=np.float32)
+        self._check(self.lib.etxb_group_read_film(self.h, layer, _p(out), out.nbytes))
+        return out
+
+    def counters(self):
+        total = {}
+        for g in self.lanes:
+            for k, v in g.counters().items():
+                total[k] = total.get(k, 0) + v
+        return total
+
+    def kernel_times(self):
+        total = {}
+        for g in self.lanes:
+            for k, (ms, n) in g.kernel_times().items():
+                a = total.get(k, (0.0, 0))
+                total[k] = (a[0] + ms, a[1] + n)
+        return total

@@ -5,6 +5,10 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -941,6 +945,13 @@ int etxb_set_iteration_stride(etxb_ctx* ctx, uint32_t stride) {
   return ETXB_OK;
 }
 
+int etxb_set_next_iteration(etxb_ctx* ctx, uint32_t iteration) {
+  if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  ctx->iteration = iteration;
+  ctx->iteration_stride = 0;  // externally driven: no auto-advance, the film mean counts this context's own iterations
+  return ETXB_OK;
+}
+
 int etxb_begin(etxb_ctx* ctx, uint32_t first_iteration) {
   if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
   if (!ctx->scene_ready) return fail(ctx, ETXB_ERR_NOT_READY, "no scene uploaded");
@@ -1230,6 +1241,224 @@ int etxb_debug_math(etxb_ctx* ctx, uint32_t fn, const float* x, const float* y, 
   dx.release();
   dy.release();
   dout.release();
+  return ETXB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Iterations in flight (etxb_group): L contexts on one device, one host thread each, pulling iteration indices from a shared
+// counter.  VCM iterations are independent (vcm_cpu.cxx:95-113: the index only sets the merge radius and the sampler seeds), and
+// the bounce loop of one iteration ends in a long latency-bound tail (a few thousand paths, ~50 bounces); with several iterations in
+// flight that tail overlaps the full-width head of another iteration.  The film is the mean of the lanes' films weighted by the
+// iterations each lane finished — the same set of iterations, hence the same estimate, as one context running them in sequence.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kMaxLanes = 8;
+struct FilmLanes {
+  const float4* camera[kMaxLanes];
+  const float4* light[kMaxLanes];
+  float weight[kMaxLanes];
+  uint32_t lanes, layer, pixels;
+};
+__global__ void __launch_bounds__(256) k_film_combine(FilmLanes f, float4* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= f.pixels) return;
+  float x = 0.0f, y = 0.0f, z = 0.0f;
+  for (uint32_t l = 0; l < f.lanes; ++l) {
+    float4 c = (f.layer != ETXB_FILM_LIGHT) ? f.camera[l][i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 g = (f.layer != ETXB_FILM_CAMERA) ? f.light[l][i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    x += f.weight[l] * (c.x + g.x);
+    y += f.weight[l] * (c.y + g.y);
+    z += f.weight[l] * (c.z + g.z);
+  }
+  if (f.layer == ETXB_FILM_RESULT) {  // Film::layer(Result): max(0, camera + light) (film.cxx:381-418)
+    x = fmaxf(0.0f, x);
+    y = fmaxf(0.0f, y);
+    z = fmaxf(0.0f, z);
+  }
+  out[i] = make_float4(x, y, z, 1.0f);
+}
+
+struct etxb_group {
+  std::vector<etxb_ctx*> lanes;
+  std::vector<std::thread> workers;
+  std::mutex m;
+  std::condition_variable cv_work, cv_idle;
+  uint32_t first_iteration = 0, stride = 1, taken = 0;  // the k-th iteration handed out renders index first + k * stride
+  uint32_t pending = 0, in_flight = 0;
+  bool quit = false;
+  int error = ETXB_OK;
+  std::string error_text;
+  std::chrono::steady_clock::time_point busy_since;
+  double busy_seconds = 0.0;   // wall time with at least one iteration queued or in flight
+  double last_iteration_seconds = 0.0;
+  DevBuf<float4> combined;
+  int device = 0;
+};
+
+static void group_worker(etxb_group* grp, uint32_t lane) {
+  cudaSetDevice(grp->device);
+  etxb_ctx* ctx = grp->lanes[lane];
+  std::unique_lock<std::mutex> lock(grp->m);
+  for (;;) {
+    grp->cv_work.wait(lock, [&] { return grp->quit || (grp->pending > 0); });
+    if (grp->quit) return;
+    uint32_t iteration = grp->first_iteration + (grp->taken++) * grp->stride;
+    grp->pending -= 1;
+    grp->in_flight += 1;
+    lock.unlock();
+    int rc = etxb_set_next_iteration(ctx, iteration);
+    if (rc == ETXB_OK) rc = etxb_enqueue_iteration(ctx);  // returns when the iteration has finished (the bounce loops read queue sizes back)
+    lock.lock();
+    grp->in_flight -= 1;
+    grp->last_iteration_seconds = ctx->last_iteration_time;
+    if ((rc != ETXB_OK) && (grp->error == ETXB_OK)) {
+      grp->error = rc;
+      grp->error_text = etxb_last_error(ctx);
+      grp->pending = 0;
+    }
+    if ((grp->pending == 0) && (grp->in_flight == 0)) {
+      grp->busy_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - grp->busy_since).count();
+      grp->cv_idle.notify_all();
+    }
+  }
+}
+
+int etxb_group_create(etxb_group** out, const etxb_device_config* cfg, uint32_t lanes) {
+  if (!out || (lanes == 0) || (lanes > kMaxLanes)) return ETXB_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  auto* grp = new etxb_group();
+  grp->device = cfg ? cfg->device_index : 0;
+  for (uint32_t l = 0; l < lanes; ++l) {
+    etxb_ctx* ctx = nullptr;
+    int rc = etxb_create(&ctx, cfg);
+    if (rc != ETXB_OK) {
+      for (auto* c : grp->lanes) etxb_destroy(c);
+      delete grp;
+      return rc;
+    }
+    grp->lanes.push_back(ctx);
+  }
+  for (uint32_t l = 0; l < lanes; ++l) grp->workers.emplace_back(group_worker, grp, l);
+  *out = grp;
+  return ETXB_OK;
+}
+
+void etxb_group_destroy(etxb_group* grp) {
+  if (!grp) return;
+  {
+    std::lock_guard<std::mutex> lock(grp->m);
+    grp->quit = true;
+    grp->pending = 0;
+  }
+  grp->cv_work.notify_all();
+  for (auto& w : grp->workers) w.join();
+  cudaSetDevice(grp->device);
+  grp->combined.release();
+  for (auto* c : grp->lanes) etxb_destroy(c);
+  delete grp;
+}
+
+uint32_t etxb_group_lanes(const etxb_group* grp) { return grp ? uint32_t(grp->lanes.size()) : 0u; }
+etxb_ctx* etxb_group_lane(etxb_group* grp, uint32_t lane) { return (grp && (lane < grp->lanes.size())) ? grp->lanes[lane] : nullptr; }
+const char* etxb_group_last_error(const etxb_group* grp) { return grp ? grp->error_text.c_str() : "null group"; }
+
+int etxb_group_wait(etxb_group* grp) {
+  if (!grp) return ETXB_ERR_INVALID_ARGUMENT;
+  std::unique_lock<std::mutex> lock(grp->m);
+  grp->cv_idle.wait(lock, [&] { return (grp->pending == 0) && (grp->in_flight == 0); });
+  return grp->error;
+}
+
+int etxb_group_begin(etxb_group* grp, uint32_t first_iteration) {
+  if (!grp) return ETXB_ERR_INVALID_ARGUMENT;
+  if (int rc = etxb_group_wait(grp)) return rc;
+  for (auto* c : grp->lanes)
+    if (int rc = etxb_begin(c, first_iteration)) return rc;
+  std::lock_guard<std::mutex> lock(grp->m);
+  grp->first_iteration = first_iteration;
+  grp->taken = 0;
+  grp->busy_seconds = 0.0;
+  grp->error = ETXB_OK;
+  grp->error_text.clear();
+  return ETXB_OK;
+}
+
+int etxb_group_set_stride(etxb_group* grp, uint32_t stride) {
+  if (!grp || (stride == 0u)) return ETXB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(grp->m);
+  grp->stride = stride;
+  return ETXB_OK;
+}
+
+int etxb_group_enqueue(etxb_group* grp, uint32_t iterations) {
+  if (!grp) return ETXB_ERR_INVALID_ARGUMENT;
+  {
+    std::lock_guard<std::mutex> lock(grp->m);
+    if (grp->error != ETXB_OK) return grp->error;
+    if (iterations == 0) return ETXB_OK;
+    if ((grp->pending == 0) && (grp->in_flight == 0)) grp->busy_since = std::chrono::steady_clock::now();
+    grp->pending += iterations;
+  }
+  grp->cv_work.notify_all();
+  return ETXB_OK;
+}
+
+int etxb_group_poll(etxb_group* grp, etxb_status* status) {
+  if (!grp || !status) return ETXB_ERR_INVALID_ARGUMENT;
+  memset(status, 0, sizeof(*status));
+  std::lock_guard<std::mutex> lock(grp->m);
+  for (auto* c : grp->lanes) {
+    status->completed_iterations += c->completed;
+    status->light_vertices = std::max(status->light_vertices, c->last_light_vertices);
+    status->overflow |= c->overflow_flag;
+  }
+  status->current_iteration = grp->first_iteration + grp->taken * grp->stride;
+  status->iteration_in_flight = ((grp->pending > 0) || (grp->in_flight > 0)) ? 1u : 0u;
+  status->last_iteration_time = grp->last_iteration_seconds;
+  status->total_time = grp->busy_seconds;
+  if (status->iteration_in_flight) status->total_time += std::chrono::duration<double>(std::chrono::steady_clock::now() - grp->busy_since).count();
+  return ETXB_OK;
+}
+
+int etxb_group_combine(etxb_group* grp, uint32_t layer, void** device_ptr, uint64_t* bytes, uint32_t* completed) {
+  if (!grp || (layer > ETXB_FILM_LIGHT)) return ETXB_ERR_INVALID_ARGUMENT;
+  etxb_ctx* first = grp->lanes[0];
+  if (!first->scene_ready) return fail(first, ETXB_ERR_NOT_READY, "no scene uploaded");
+  size_t n = first->path_count;
+  cudaSetDevice(grp->device);
+  if (grp->combined.count < n) {
+    grp->combined.release();
+    CUDA_OK(first, grp->combined.alloc(n));
+  }
+  FilmLanes f = {};
+  f.lanes = uint32_t(grp->lanes.size());
+  f.layer = layer;
+  f.pixels = uint32_t(n);
+  uint32_t total = 0;
+  for (auto* c : grp->lanes) total += c->completed;
+  for (uint32_t l = 0; l < f.lanes; ++l) {
+    f.camera[l] = grp->lanes[l]->film_camera.ptr;
+    f.light[l] = grp->lanes[l]->film_light.ptr;
+    f.weight[l] = total ? float(double(grp->lanes[l]->completed) / double(total)) : 0.0f;
+  }
+  // lanes that are still rendering keep updating their films (a preview, like reading the reference's film while it runs); after
+  // etxb_group_wait every lane has synchronised its stream and the result is exact
+  k_film_combine<<<blocks_for(f.pixels, 256), 256, 0, first->stream>>>(f, grp->combined.ptr);
+  CUDA_OK(first, cudaStreamSynchronize(first->stream));
+  if (device_ptr) *device_ptr = grp->combined.ptr;
+  if (bytes) *bytes = n * 16;
+  if (completed) *completed = total;
+  return ETXB_OK;
+}
+
+int etxb_group_read_film(etxb_group* grp, uint32_t layer, float* dst_rgba, uint64_t dst_bytes) {
+  if (!grp || !dst_rgba) return ETXB_ERR_INVALID_ARGUMENT;
+  void* src = nullptr;
+  uint64_t bytes = 0;
+  if (int rc = etxb_group_combine(grp, layer, &src, &bytes, nullptr)) return rc;
+  etxb_ctx* first = grp->lanes[0];
+  if (dst_bytes < bytes) return fail(first, ETXB_ERR_INVALID_ARGUMENT, "film buffer too small");
+  CUDA_OK(first, cudaMemcpy(dst_rgba, src, bytes, cudaMemcpyDeviceToHost));
   return ETXB_OK;
 }
 

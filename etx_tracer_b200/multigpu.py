@@ -137,49 +137,49 @@ class ShardedVCM:
 class InterleavedVCM:
     """Iteration-interleaved rendering: rank r owns iterations r, r + world, r + 2 world, ...
 
-    `run_steps(k0, k1)` renders the global iterations k in [k0, k1) that belong to this rank.  `reduce_film()` combines the per-rank
-    films (each the mean over the iterations that rank rendered) into the mean over all iterations on rank 0:
-    sum_r n_r * film_r / sum_r n_r, one reduce per film layer."""
+    `group` is an api.GPUVCMGroup (several iterations in flight on this rank's GPU).  `enqueue(n)` queues n more of this rank's
+    iterations, `reduce_film()` combines the per-rank means (each over the iterations that rank finished) into the mean over all
+    iterations on rank 0: sum_r n_r * film_r / sum_r n_r, one reduce of the float4 Result layer."""
 
-    def __init__(self, gpu, dist, rank, world, device="cuda", view=as_tensor):
+    def __init__(self, group, dist, rank, world, device="cuda", view=as_tensor):
         import torch
-        self.g, self.dist, self.rank, self.world, self.torch = gpu, dist, rank, world, torch
+        self.g, self.dist, self.rank, self.world, self.torch = group, dist, rank, world, torch
         self.device, self.view = device, view
-        gpu.set_iteration_stride(world)
-        self.done = 0
+        group.set_stride(world)
 
     def begin(self):
         """Integrator::run: clears the film; this rank's first iteration is `rank`."""
         self.g.run(self.rank)
-        self.done = 0
 
-    def owned(self, k0, k1):
-        return [k for k in range(k0, k1) if k % self.world == self.rank]
+    def enqueue(self, iterations=1):
+        self.g.enqueue(iterations)
 
-    def run_steps(self, k0, k1):
-        n = len(self.owned(k0, k1))
-        for _ in range(n):
-            self.g.iterate()
-        self.done += n
-        return n
+    def wait(self):
+        self.g.wait()
 
-    def reduce_film(self):
-        """Mean over all iterations rendered so far, on rank 0 (float4 camera + light layers -> Result layer); None elsewhere."""
-        torch, dist, g = self.torch, self.dist, self.g
-        if self.device == "cuda":
-            g.wait()
-        counts = torch.tensor([float(self.done)], dtype=torch.float64, device=self.device)
+    def reduce_film(self, layer=S.FILM_RESULT):
+        """Mean over all iterations finished so far, on rank 0 (a float4 [pixels, 4] tensor); None elsewhere.
+        Camera / Light layers are linear in the per-rank means; Result = max(0, camera + light) is reduced as the sum of those two."""
+        torch, dist = self.torch, self.dist
+        ptr, nbytes, done = self.g.combined(S.FILM_CAMERA)
+        cam = self.view(ptr, nbytes).clone()
+        ptr, nbytes, done = self.g.combined(S.FILM_LIGHT)
+        light = self.view(ptr, nbytes).clone()
+        counts = torch.tensor([float(done)], dtype=torch.float64, device=self.device)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
         total = float(counts.item())
-        weight = (self.done / total) if total > 0 else 0.0
-        layers = []
-        for buf in (S.BUF_FILM_CAMERA, S.BUF_FILM_LIGHT):
-            ptr, nbytes = g.device_pointer(buf)
-            t = self.view(ptr, nbytes) * weight  # out of place: the rank's own running mean stays intact
-            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
-            layers.append(t)
+        weight = (done / total) if total > 0 else 0.0
+        if layer == S.FILM_CAMERA:
+            t = cam * weight
+        elif layer == S.FILM_LIGHT:
+            t = light * weight
+        else:
+            t = (cam + light) * weight
+        dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
         if self.rank != 0:
             return None
-        result = torch.clamp_min(layers[0] + layers[1], 0.0).view(-1, 4)  # Film::layer(Result) (film.cxx:381-418): max(0, camera + light)
-        result[:, 3] = 1.0
-        return result
+        t = t.view(-1, 4)
+        if layer == S.FILM_RESULT:
+            t = torch.clamp_min(t, 0.0)  # Film::layer(Result) (film.cxx:381-418): max(0, camera + light)
+        t[:, 3] = 1.0
+        return t

@@ -322,6 +322,10 @@ int etxb_set_partition(etxb_ctx* ctx, uint32_t rank, uint32_t world);
  * and its film is the mean over the iterations it rendered.  Default stride 1 = the reference's sequence. */
 int etxb_set_iteration_stride(etxb_ctx* ctx, uint32_t stride);
 
+/* Externally driven iteration index: the next enqueued iteration renders VCMIteration::iteration = `iteration`; the index no
+ * longer advances by itself (used by etxb_group below). */
+int etxb_set_next_iteration(etxb_ctx* ctx, uint32_t iteration);
+
 /* CPUVCMImpl::start (vcm_cpu.cxx:81-93): clears film, sets iteration = first_iteration. */
 int etxb_begin(etxb_ctx* ctx, uint32_t first_iteration);
 
@@ -361,6 +365,29 @@ int etxb_debug_trace(etxb_ctx* ctx, const float* rays, uint32_t* seeds, uint32_t
 /* Sampler / spectral KATs evaluated on the device (sampler.hxx:54,66; spectrum.hxx:219,234). */
 int etxb_debug_sampler(etxb_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t count, uint32_t draws, uint32_t* out_seed, float* out_values);
 int etxb_debug_math(etxb_ctx* ctx, uint32_t fn, const float* x, const float* y, uint32_t count, float* out);
+
+/* ---- several iterations in flight on one device -----------------------------------------------------------------------
+ * The reference runs ONE iteration at a time and spreads its paths over the CPU's threads (vcm_cpu.cxx:115-171, TaskScheduler).
+ * A GPU wavefront iteration ends in a long, latency-bound tail (few paths, ~50 more bounces); an etxb_group keeps `lanes`
+ * independent contexts on one device, one host thread each, pulling iteration indices from a shared counter, so that tail overlaps
+ * other iterations.  Uploads/options go to every lane (etxb_group_lane); the film is the mean of the lanes' films weighted by the
+ * iterations each finished — the same set of iterations as a single context running them in order.
+ * Replaces the run()/update() pump of CPUVCM (vcm_cpu.cxx:247-276) for throughput rendering. */
+typedef struct etxb_group etxb_group;
+int etxb_group_create(etxb_group** out_group, const etxb_device_config* config, uint32_t lanes); /* 1..8 lanes */
+void etxb_group_destroy(etxb_group* group);
+uint32_t etxb_group_lanes(const etxb_group* group);
+etxb_ctx* etxb_group_lane(etxb_group* group, uint32_t lane);
+const char* etxb_group_last_error(const etxb_group* group);
+int etxb_group_begin(etxb_group* group, uint32_t first_iteration);   /* Integrator::run: clears every lane's film */
+int etxb_group_set_stride(etxb_group* group, uint32_t stride);       /* the k-th iteration handed out renders index first + k * stride
+                                                                        (iteration-interleaved multi-GPU runs: first = rank, stride = ranks) */
+int etxb_group_enqueue(etxb_group* group, uint32_t iterations);      /* asynchronous: queues `iterations` more iterations */
+int etxb_group_wait(etxb_group* group);                              /* blocks until the queue has drained; returns the first error */
+int etxb_group_poll(etxb_group* group, etxb_status* status);         /* completed = sum over lanes; total_time = wall time with work in flight */
+int etxb_group_read_film(etxb_group* group, uint32_t layer, float* dst_rgba, uint64_t dst_bytes);
+/* The same combined layer left on the device (float4[N]) + the number of iterations behind it: what a multi-GPU host reduces. */
+int etxb_group_combine(etxb_group* group, uint32_t layer, void** device_ptr, uint64_t* bytes, uint32_t* completed_iterations);
 
 #ifdef __cplusplus
 }

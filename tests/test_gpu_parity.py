@@ -279,3 +279,31 @@ def test_participating_media_are_bit_exact(api, oracle_mod, kind, spectral):
     img, ref = f.film(S.FILM_RESULT)[..., :3], o.film(S.FILM_RESULT)[..., :3]
     assert np.isfinite(img).all() and rel_l2(img, ref) < 0.2
     f.close()
+
+
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_iterations_in_flight_render_the_same_frame(api, lanes):
+    """etxb_group: `lanes` contexts render the iteration indices 0..n-1 between them (each index exactly once, whichever lane takes it);
+    the combined film is the mean over those iterations, i.e. the single-context frame up to float summation order."""
+    sd = scenes.cornell_box(64, 64, samples=16, spectral=True, sphere=True)
+    n = 7
+    ref = api.GPUVCM(sd, flavor="fast")
+    ref.render(n)
+    grp = api.GPUVCMGroup(sd, lanes=lanes, flavor="fast")
+    st = grp.render(n)
+    assert st["completed_iterations"] == n and st["iteration_in_flight"] == 0 and st["overflow"] == 0 and st["total_time"] > 0.0
+    assert sum(g.status()["completed_iterations"] for g in grp.lanes) == n
+    for layer in (S.FILM_RESULT, S.FILM_CAMERA, S.FILM_LIGHT):
+        a, b = grp.film(layer)[..., :3], ref.film(layer)[..., :3]
+        assert np.isfinite(a).all() and rel_l2(a, b) < 1e-5, f"layer {layer}: {rel_l2(a, b):.3e}"
+    # a second batch continues the same sequence (indices n .. 2n-1)
+    grp.enqueue(n)
+    grp.wait()
+    ref.run(0)
+    for _ in range(2 * n):
+        ref.iterate()
+    ref.wait()
+    assert grp.status()["completed_iterations"] == 2 * n
+    assert rel_l2(grp.film(S.FILM_RESULT)[..., :3], ref.film(S.FILM_RESULT)[..., :3]) < 1e-5
+    grp.close()
+    ref.close()

@@ -133,61 +133,65 @@ def test_gather_layout():
     assert multigpu.gather_layout([0]) == ([0], 0)
 
 
-class StandInIterationGPU:
-    """api.GPUVCM stand-in for InterleavedVCM: every iteration k contributes the constant k to the camera layer and 10 k to the light
-    layer; the films are running means over the iterations this context rendered."""
+class StandInGroup:
+    """api.GPUVCMGroup stand-in for InterleavedVCM: iteration k contributes the constant k to the camera layer and 10 k to the light
+    layer; the layers are means over the iterations this group rendered."""
 
     def __init__(self):
-        self.stride, self.iteration, self.rendered = 1, 0, []
-        self.t = {S.BUF_FILM_CAMERA: torch.zeros(H * W * 4), S.BUF_FILM_LIGHT: torch.zeros(H * W * 4)}
+        self.stride, self.first, self.rendered = 1, 0, []
 
-    def set_iteration_stride(self, stride):
+    def set_stride(self, stride):
         self.stride = stride
 
     def run(self, first_iteration=0):
-        self.iteration, self.rendered = first_iteration, []
-        for t in self.t.values():
-            t.zero_()
+        self.first, self.rendered = first_iteration, []
 
-    def iterate(self):
-        n = len(self.rendered)
-        self.t[S.BUF_FILM_CAMERA].mul_(n / (n + 1.0)).add_(float(self.iteration) / (n + 1.0))
-        self.t[S.BUF_FILM_LIGHT].mul_(n / (n + 1.0)).add_(10.0 * self.iteration / (n + 1.0))
-        self.rendered.append(self.iteration)
-        self.iteration += self.stride
+    def enqueue(self, iterations=1):
+        for _ in range(iterations):
+            self.rendered.append(self.first + len(self.rendered) * self.stride)
 
-    def device_pointer(self, buf):
-        return buf, self.t[buf].numel() * 4
+    def wait(self):
+        pass
+
+    def combined(self, layer):
+        mean = float(np.mean(self.rendered)) if self.rendered else 0.0
+        value = {S.FILM_CAMERA: mean, S.FILM_LIGHT: 10.0 * mean}[layer]
+        self.t = torch.full((H * W * 4,), value, dtype=torch.float32)
+        return "combined", self.t.numel() * 4, len(self.rendered)
 
     def view(self, ptr, nbytes, dtype="<f4"):
-        return self.t[ptr][:nbytes // 4]
+        return self.t[:nbytes // 4]
 
 
-def _interleaved_worker(rank, world, port, steps, out_dir):
+def _interleaved_worker(rank, world, port, per_rank, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        g = StandInIterationGPU()
+        g = StandInGroup()
         iv = multigpu.InterleavedVCM(g, dist, rank, world, device="cpu", view=g.view)
         iv.begin()
-        iv.run_steps(0, 3)       # warm-up block
-        iv.run_steps(3, steps)   # timed block: the global step counter keeps running
+        iv.enqueue(2)                   # warm-up block
+        iv.enqueue(per_rank[rank] - 2)  # timed block: the rank's sequence keeps running
+        iv.wait()
         film = iv.reduce_film()
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), rendered=np.array(g.rendered), film=np.zeros(0) if film is None else film.numpy())
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("steps", [7, 8])
-def test_interleaved_iterations_over_gloo(tmp_path, steps):
-    """Iterations 0..steps-1 are rendered exactly once across the ranks, and the reduced film is their mean (rank 0 only)."""
+@pytest.mark.parametrize("per_rank", [(4, 4), (5, 3)])
+def test_interleaved_iterations_over_gloo(tmp_path, per_rank):
+    """Rank r renders indices r, r + N, ...; the reduced film is the mean over every iteration rendered anywhere, weighted by how many
+    each rank finished (rank 0 only)."""
     world = 2
-    mp.spawn(_interleaved_worker, args=(world, _free_port(), steps, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_interleaved_worker, args=(world, _free_port(), per_rank, str(tmp_path)), nprocs=world, join=True)
     r = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
-    assert sorted(np.concatenate([r[0]["rendered"], r[1]["rendered"]]).tolist()) == list(range(steps))
-    assert all(k % world == 0 for k in r[0]["rendered"]) and all(k % world == 1 for k in r[1]["rendered"])
-    mean = sum(range(steps)) / steps
+    for k in range(world):
+        assert r[k]["rendered"].tolist() == [k + j * world for j in range(per_rank[k])]
+    everything = np.concatenate([r[0]["rendered"], r[1]["rendered"]])
+    assert len(set(everything.tolist())) == len(everything)
+    mean = float(everything.mean())
     film = r[0]["film"]
     assert film.shape == (H * W, 4) and r[1]["film"].size == 0
     np.testing.assert_allclose(film[:, 0], mean + 10.0 * mean, rtol=1e-6)

@@ -44,24 +44,27 @@ for name, sd in (("C2", scenes.cornell_box(res, res, samples=256, spectral=True,
             ref.close()
         g.close()
         dist.barrier()
-# iteration-interleaved mode: the union of the ranks' iterations is the single-GPU sequence, the reduced film is its mean
+# iteration-interleaved mode (2 iterations in flight per GPU): the union of the ranks' iterations is a set of distinct indices, the
+# reduced film is their mean -> compare with a single context rendering the same indices
+from etx_tracer_b200.api import GPUVCMGroup
 sd = scenes.cornell_box(res, res, samples=256, spectral=True, sphere=True)
-g = GPUVCM(sd, flavor="fast", device=local)
-iv = InterleavedVCM(g, dist, rank, world)
+grp = GPUVCMGroup(sd, lanes=2, flavor="fast", device=local)
+iv = InterleavedVCM(grp, dist, rank, world)
 iv.begin()
-total_iterations = 2 * world + 1  # uneven on purpose: rank 0 renders one more than the others
-iv.run_steps(0, total_iterations)
+per_rank = 3
+iv.enqueue(per_rank)
+iv.wait()
 combined = iv.reduce_film()
 if rank == 0:
     ref = GPUVCM(sd, flavor="fast", device=local)
-    ref.render(total_iterations)
+    ref.render(per_rank * world)  # indices 0 .. per_rank * world - 1 = the union of r + j * world
     a = combined.cpu().numpy().reshape(res, res, 4)[..., :3].astype(np.float64)
     b = ref.film(S.FILM_RESULT)[..., :3].astype(np.float64)
     r = float(np.sqrt(((a - b) ** 2).sum()) / np.sqrt((b ** 2).sum()))
-    print(f"interleaved world={world}: {total_iterations} iterations, result rel-L2 vs single GPU {r:.3e}", flush=True)
+    print(f"interleaved world={world}: {per_rank * world} iterations, result rel-L2 vs single GPU {r:.3e}", flush=True)
     ok &= r < 1e-5
     ref.close()
-g.close()
+grp.close()
 dist.barrier()
 if rank == 0:
     print("MULTIGPU_CHECK", "OK" if ok else "FAILED", flush=True)
