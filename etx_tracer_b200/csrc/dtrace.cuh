@@ -106,6 +106,9 @@ namespace etxb {
 // Out of line: every kernel reaches it from several connection routines, and one BVH traversal dwarfs the call.
 template <bool SP>
 DEVN Spec<SP> trace_transmittance(const DeviceScene& sc, float wavelength, V3 p0, V3 p1, uint32_t medium_index, Smp& smp, TraverseStats* stats) {
+#ifdef ETXB_EXPERIMENT_NO_SHADOW
+  return Spec<SP>::make(1.0f);
+#endif
   V3 direction = p1 - p0;
   float t_max = dot(direction, direction);
   if (t_max <= kRayEpsilon) return Spec<SP>::make(1.0f);

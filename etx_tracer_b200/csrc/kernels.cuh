@@ -12,6 +12,10 @@
 #include "dvcm.cuh"
 #include "dsss.cuh"
 
+#ifndef ETXB_BOUNCE_MIN_BLOCKS
+#define ETXB_BOUNCE_MIN_BLOCKS 1
+#endif
+
 namespace etxb {
 
 struct PathBuffers {
@@ -226,7 +230,7 @@ enum : uint32_t { kEpNone = 0u, kEpMedium = 1u, kEpSurface = 2u, kEpSubsurface =
 // the segment (medium scattering, boundary crossing, surface hit incl. the subsurface walk), (B) camera connections from the
 // endpoint(s) it produced — one, or every gathered subsurface exit (:1207-1222), (C) the continuation.
 template <bool SP>
-__global__ void __launch_bounds__(128) k_light_bounce(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
+__global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_light_bounce(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   bool alive = false;
   uint32_t i = 0;
@@ -550,7 +554,7 @@ DEV void camera_emit_connections(const LaunchParams& p, uint32_t i, PathState<SP
 // the paired light path and to a sampled emitter from the endpoint(s) the event produced (one, or every gathered subsurface exit,
 // :1037-1053), (C) the MIS update / pending continuation sample handed to the merge and continue stages.
 template <bool SP>
-__global__ void __launch_bounds__(128) k_camera_shade(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in) {
+__global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t shadow_rays = 0, connections = 0;
   uint32_t merge_key = 0xffffffffu;
