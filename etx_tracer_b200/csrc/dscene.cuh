@@ -53,6 +53,7 @@ struct DeviceScene {
   const struct DMedium* mediums;
   uint32_t medium_count;
   uint32_t spectrum_count;
+  uint32_t deferred_shadow_rays;  // camera-vertex shadow rays may run in their own kernel (see k_shadow_trace)
   uint32_t has_subsurface;  // some material has subsurface scattering enabled
   uint32_t subsurface_exit_material;
   uint32_t has_boundaries;  // some material is of class Boundary (shadow rays may cross medium interfaces)

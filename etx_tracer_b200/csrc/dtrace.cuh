@@ -103,12 +103,34 @@ namespace etxb {
 
 // Raytracing::trace_transmittance (rt.cxx:468-579): occluded unless every hit is a Boundary; the (<= 63) boundary crossings are
 // sorted by t and the per-segment medium transmittance is multiplied in.
+// The occlusion half of trace_transmittance for scenes without Boundary materials and media: any non-Void hit on the segment
+// occludes (same segment set-up as rt.cxx:468-490).  Used by k_shadow_trace.
+struct OcclusionVisitor {
+  const DeviceScene& sc;
+  bool occluded;
+  DEV int operator()(uint32_t triangle_index, float, float, float) {
+    if (sc.materials[load_triangle_material(sc, triangle_index)].cls == ETXB_MAT_VOID) return kCandIgnore;
+    occluded = true;
+    return kCandTerminate;
+  }
+};
+DEV bool trace_occluded(const DeviceScene& sc, V3 p0, V3 p1) {
+  V3 direction = p1 - p0;
+  float t_max = dot(direction, direction);
+  if (t_max <= kRayEpsilon) return false;
+  t_max = sqrtf(t_max);
+  direction /= t_max;
+  t_max -= fmaxf(kRayEpsilon, t_max * kRayEpsilon);
+  OcclusionVisitor vis{sc, false};
+  DevNodeLoad nl{sc.bvh_nodes};
+  DevTriLoad tl{sc.bvh_tris};
+  traverse(nl, tl, p0.x, p0.y, p0.z, direction.x, direction.y, direction.z, kRayEpsilon, t_max, vis, static_cast<TraverseStats*>(nullptr));
+  return vis.occluded;
+}
+
 // Out of line: every kernel reaches it from several connection routines, and one BVH traversal dwarfs the call.
 template <bool SP>
 DEVN Spec<SP> trace_transmittance(const DeviceScene& sc, float wavelength, V3 p0, V3 p1, uint32_t medium_index, Smp& smp, TraverseStats* stats) {
-#ifdef ETXB_EXPERIMENT_NO_SHADOW
-  return Spec<SP>::make(1.0f);
-#endif
   V3 direction = p1 - p0;
   float t_max = dot(direction, direction);
   if (t_max <= kRayEpsilon) return Spec<SP>::make(1.0f);

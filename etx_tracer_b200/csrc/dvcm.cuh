@@ -645,9 +645,33 @@ DEV void vcm_handle_direct_hit(const DeviceScene& sc, const VcmParams& it, const
   state.gathered += weight * (state.throughput * radiance);
 }
 
+// Deferred shadow rays.  In a scene where every surface is opaque (no alpha test can reject), without Boundary materials, media
+// or stochastic BSDFs, a shadow ray of the camera step does exactly two things (rt.cxx:468-579): it decides visible / occluded, and it
+// draws ONE value from the path's sampler if it is occluded (the alpha test of the hit that blocks it), none if it is visible.  Neither
+// depends on the order candidates are met, and nothing else draws between a vertex's connections and its continuation.  So the
+// connection routines only WRITE the segment and the unoccluded contribution here; k_shadow_trace resolves all segments of the bounce in
+// a traversal-only kernel, and k_camera_continue adds the visible contributions in the reference's order and advances the sampler by the
+// number of occluded ones — bit-identical to tracing inline.
+struct ShadowBatch {
+  float4* p0;
+  float4* p1;
+  float4* value;
+  uint32_t base, count;
+  template <bool SP>
+  DEV void push(V3 a, V3 b, Spec<SP> v) {
+    uint32_t k = base + count;
+    count += 1u;
+    V3 c = v.as_v3();
+    p0[k] = make_float4(a.x, a.y, a.z, 0.0f);
+    p1[k] = make_float4(b.x, b.y, b.z, 0.0f);
+    value[k] = make_float4(c.x, c.y, c.z, 0.0f);
+  }
+};
+
 // vcm_connect_to_light (vcm_shared.hxx:608-671)
 template <bool SP>
-DEV Spec<SP> vcm_connect_to_light(const DeviceScene& sc, const VcmParams& it, const Endpoint& ep, PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays) {
+DEV Spec<SP> vcm_connect_to_light(const DeviceScene& sc, const VcmParams& it, const Endpoint& ep, PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays,
+                                  ShadowBatch* batch = nullptr) {
   Spec<SP> zero = Spec<SP>::make(0.0f);
   if ((it.connect_to_light() == false) || (state.total_path_depth + 1 > sc.max_path_length) || (state.total_path_depth + 1 < sc.min_path_length)) return zero;
   V3 sample_pos = ep.pos();
@@ -677,8 +701,11 @@ DEV Spec<SP> vcm_connect_to_light(const DeviceScene& sc, const VcmParams& it, co
     camera_factor = fabsf(dot(w_o, tri.geo_n));
   }
   shadow_rays += 1;
-  Spec<SP> tr = trace_transmittance<SP>(sc, state.wavelength, origin, es.origin, state.medium_index, state.sampler, stats);
-  if (tr.is_zero()) return zero;
+  Spec<SP> tr = Spec<SP>::make(1.0f);
+  if (batch == nullptr) {
+    tr = trace_transmittance<SP>(sc, state.wavelength, origin, es.origin, state.medium_index, state.sampler, stats);
+    if (tr.is_zero()) return zero;
+  }
   float l_dot_e = fabsf(dot(es.direction, es.normal));
   float w_light = 0.0f;
   if (es.is_delta == false) {
@@ -694,7 +721,12 @@ DEV Spec<SP> vcm_connect_to_light(const DeviceScene& sc, const VcmParams& it, co
   float vmW_nee = ep.at_medium ? 0.0f : it.vm_weight;
   float w_camera = (es.pdf_dir_out * camera_factor) / (es.pdf_dir * l_dot_e) * (vmW_nee + state.d_vcm + state.d_vc * reverse_pdf);
   float weight = it.enable_mis() ? 1.0f / (1.0f + w_light + w_camera) : 1.0f;
-  return tr * state.throughput * scatter * es.value * (weight / (es.pdf_dir * es.pdf_sample));
+  Spec<SP> result = tr * state.throughput * scatter * es.value * (weight / (es.pdf_dir * es.pdf_sample));
+  if (batch != nullptr) {
+    batch->push<SP>(origin, es.origin, result);  // tr == 1 here: the product above is the unoccluded contribution, bit for bit
+    return zero;
+  }
+  return result;
 }
 
 // vcm_connect_to_light_vertex (vcm_shared.hxx:673-763)
@@ -799,7 +831,7 @@ DEV Spec<SP> vcm_connection_transmittance(const DeviceScene& sc, const Endpoint&
 // vcm_connect_to_light_path (vcm_shared.hxx:765-803): serial over the paired path's vertices (shared sampler)
 template <bool SP>
 DEV Spec<SP> vcm_connect_to_light_path(const DeviceScene& sc, const VcmParams& it, const LightVertexRec* pool, uint32_t lp_index, uint32_t lp_count, const Endpoint& ep,
-  PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays, uint32_t& connections) {
+  PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays, uint32_t& connections, ShadowBatch* batch = nullptr) {
   Spec<SP> result = Spec<SP>::make(0.0f);
   if (it.connect_vertices() == false) return result;
   for (uint32_t i = 0; i < lp_count; ++i) {
@@ -812,6 +844,12 @@ DEV Spec<SP> vcm_connect_to_light_path(const DeviceScene& sc, const VcmParams& i
     Spec<SP> value;
     if (vcm_connect_to_light_vertex<SP>(sc, it, state, lv, ep, target_position, value)) {
       shadow_rays += 1;
+      if (batch != nullptr) {  // surface endpoints only
+        const Isect& isect = *ep.isect;
+        V3 p0 = shading_pos(sc, load_triangle(sc, isect.triangle_index), isect.barycentric, normalize(target_position - isect.pos));
+        batch->push<SP>(p0, target_position, value);
+        continue;
+      }
       Spec<SP> tr = vcm_connection_transmittance<SP>(sc, ep, lv, target_position, state, stats);
       if (tr.is_zero() == false) {
         result += tr * value;

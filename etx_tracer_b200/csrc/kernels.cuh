@@ -34,6 +34,7 @@ struct PathBuffers {
   uint2* bs_props;        //         properties, medium index
   uint32_t* merge_key;    // camera: per queue slot, Morton code of the merge query's base grid cell (0xffffffff = no merge)
   uint32_t* conn_seed;    // camera (product build): sampler state the vertex-connection stage derives its per-connection streams from
+  uint2* shadow_span;     // camera: (first deferred shadow ray, path connections | NEE << 16) of the vertex shaded this bounce
 };
 
 struct DeviceCounters {
@@ -71,6 +72,14 @@ struct LaunchParams {
   uint32_t* conn_count;
   uint32_t conn_capacity;
   uint32_t connect_stage;        // 1: vertex connections run in k_camera_connect (product build, scenes with stochastic BSDFs)
+  // deferred shadow rays of the camera step (ShadowBatch, dvcm.cuh): segment end points, unoccluded contribution, result (1 = occluded)
+  float4* shadow_p0;
+  float4* shadow_p1;
+  float4* shadow_value;
+  uint32_t* shadow_result;
+  uint32_t* shadow_count;        // [0] rays reserved this bounce, [1] work cursor of k_shadow_trace
+  uint32_t shadow_capacity;
+  uint32_t shadow_stage;         // 1: the scene qualifies (DeviceScene::deferred_shadow_rays) and the buffers exist
 };
 
 #ifdef ETXB_COUNT_TRAVERSAL
@@ -632,9 +641,19 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
       vcm_cam_handle_miss<SP>(sc, p.vcm, state.ray_d, state.d_vcm, state.d_vc, state.path_distance, state.total_path_depth, state.wavelength, state.throughput, state.gathered);
     }
     // ---- (B) ----
+    uint2 shadow_span = make_uint2(0u, 0u);
     if (ep_mode != kEpNone) {
       uint32_t n = (ep_mode == kEpSubsurface) ? ssg.count : 1u;
       Isect ep_isect = isect;
+      // deferred shadow rays: reserve one slot per possible segment of this vertex (its light path + the emitter sample)
+      ShadowBatch batch = {p.shadow_p0, p.shadow_p1, p.shadow_value, 0u, 0u};
+      ShadowBatch* deferred = nullptr;
+      uint32_t reserved = 0;
+      if (p.shadow_stage && (ep_mode == kEpSurface) && !p.connect_stage) {
+        reserved = p.paths.lv_count[i] + 1u;
+        batch.base = atomicAdd(p.shadow_count, reserved);
+        if (batch.base + reserved <= p.shadow_capacity) deferred = &batch;  // otherwise this vertex traces inline (same result)
+      }
 #pragma unroll 1
       for (uint32_t k = 0; k < n; ++k) {
         Spec<SP> w = Spec<SP>::make(1.0f);
@@ -649,19 +668,29 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
           Spec<SP> c;
           if ((step == 0u) == (ep_mode == kEpMedium)) {
             state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
-            c = vcm_connect_to_light<SP>(sc, p.vcm, ep, state, stats, shadow_rays);
+            c = vcm_connect_to_light<SP>(sc, p.vcm, ep, state, stats, shadow_rays, deferred);
             state.sampler.pop_fixed();
           } else if (p.connect_stage && (ep_mode == kEpSurface)) {
             camera_emit_connections<SP>(p, i, state, connections);
             continue;
           } else {
             // reference order: serial over the paired path's vertices with the path's own sampler
-            c = vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], ep, state, stats, shadow_rays, connections);
+            c = vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], ep, state, stats, shadow_rays, connections, deferred);
+            if (deferred) shadow_span.y = batch.count;  // segments to light vertices come first, the emitter segment (if any) last
           }
           state.gathered += (ep_mode == kEpSubsurface) ? (w * c) : c;
         }
       }
+      if (reserved) {
+        if (deferred) {
+          shadow_span.x = batch.base;
+          shadow_span.y |= (batch.count - shadow_span.y) << 16;
+        }
+        // reserved slots that were not used (failed connections, or a reservation that ran past the capacity) are marked empty
+        for (uint32_t k = batch.base + batch.count; (k < batch.base + reserved) && (k < p.shadow_capacity); ++k) p.shadow_p0[k].w = -1.0f;
+      }
     }
+    if (p.shadow_stage) p.paths.shadow_span[i] = shadow_span;
     // ---- (C) ----
     if (at_medium) {
       // :974-995
@@ -1047,6 +1076,27 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
   counter_add(&p.counters->merge_accepts, accepts);
 }
 
+// The deferred shadow rays of one camera bounce (ShadowBatch, dvcm.cuh): a traversal-only kernel — persistent warps take 32 segments at a
+// time from a shared cursor, every lane answers "is anything but a Void surface on this segment?".
+__global__ void __launch_bounds__(256) k_shadow_trace(LaunchParams p) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t total = umin(p.shadow_count[0], p.shadow_capacity);
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(p.shadow_count + 1, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= total) break;
+    uint32_t k = base + lane;
+    if (k < total) {
+      float4 a = p.shadow_p0[k];
+      if (a.w >= 0.0f) {
+        float4 b = p.shadow_p1[k];
+        p.shadow_result[k] = trace_occluded(p.scene, V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z}) ? 1u : 0u;
+      }
+    }
+  }
+}
+
 template <bool SP>
 __global__ void __launch_bounds__(128) k_camera_continue(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1059,6 +1109,34 @@ __global__ void __launch_bounds__(128) k_camera_continue(LaunchParams p, const u
     float4 hit = p.paths.hit[i];
     uint32_t tri_index = __float_as_uint(hit.w);
     uint2 bp = p.paths.bs_props[i];
+    if (p.shadow_stage) {
+      // resolve the vertex's deferred shadow rays: visible contributions are added in the reference's order (the sum over the light path
+      // first, vcm_shared.hxx:765-803, then the emitter sample), and the sampler moves on by one draw per occluded segment
+      uint2 span = p.paths.shadow_span[i];
+      uint32_t n_path = span.y & 0xffffu, n_total = n_path + (span.y >> 16);
+      if (n_total) {
+        float4 g = p.paths.gathered[i];
+        Spec<SP> gathered = Spec<SP>::make3({g.x, g.y, g.z});
+        Spec<SP> path_sum = Spec<SP>::make(0.0f);
+        for (uint32_t k = 0; k < n_total; ++k) {
+          if (k == n_path) gathered += path_sum;
+          if (p.shadow_result[span.x + k]) {
+            state.sampler.next();
+          } else {
+            float4 v = p.shadow_value[span.x + k];
+            Spec<SP> c = Spec<SP>::make3({v.x, v.y, v.z});
+            if (k < n_path) {
+              path_sum += c;
+            } else {
+              gathered += c;
+            }
+          }
+        }
+        if (n_total == n_path) gathered += path_sum;
+        V3 gv = gathered.as_v3();
+        p.paths.gathered[i] = make_float4(gv.x, gv.y, gv.z, 0.0f);
+      }
+    }
     if (bp.x & 0x80000000u) {
       alive = bp.x == kBounceResolvedAlive;  // medium scattering / boundary crossing / miss: the shade stage already advanced the path
     } else if (tri_index != kInvalidIndex) {

@@ -44,6 +44,7 @@ enum KernelId : uint32_t {
   K_TRACE_CAMERA,
   K_CAMERA_SHADE,
   K_CAMERA_CONNECT,
+  K_SHADOW_TRACE,
   K_CAMERA_MERGE_SORT,
   K_CAMERA_MERGE,
   K_CAMERA_MERGE_SERIAL,
@@ -52,7 +53,7 @@ enum KernelId : uint32_t {
   K_COUNT
 };
 const char* kKernelNames[K_COUNT] = {"light_begin", "trace_closest(light)", "light_bounce", "lv_scan", "lv_reorder", "grid_bbox", "grid_keys", "grid_sort", "grid_build",
-  "camera_begin", "trace_closest(camera)", "camera_shade", "camera_connect", "camera_merge_sort", "camera_merge", "camera_merge_generic", "camera_continue", "film_commit_light"};
+  "camera_begin", "trace_closest(camera)", "camera_shade", "camera_connect", "shadow_trace", "camera_merge_sort", "camera_merge", "camera_merge_generic", "camera_continue", "film_commit_light"};
 
 template <class T>
 struct DevBuf {
@@ -116,7 +117,9 @@ struct etxb_ctx {
   DevBuf<uint2> bs_props;
   DevBuf<float> wavelength;
   DevBuf<uint32_t> lv_count, lp_offset, queue_a, queue_b, queue_counts, sampler_end_light, sampler_end_camera, merge_key, conn_seed, conn_count;
-  DevBuf<uint2> conn_list;
+  DevBuf<uint2> conn_list, shadow_span;
+  DevBuf<float4> shadow_p0, shadow_p1, shadow_value;
+  DevBuf<uint32_t> shadow_result, shadow_count;
   // light vertices + grid
   uint32_t lv_capacity = 0, max_light_vertices_cfg = 0;
   DevBuf<LightVertexRec> lv_tmp, lv_final;
@@ -245,6 +248,14 @@ LaunchParams make_params(etxb_ctx* ctx) {
   p.conn_list = ctx->conn_list.ptr;
   p.conn_count = ctx->conn_count.ptr;
   p.conn_capacity = ctx->lv_capacity;
+  p.paths.shadow_span = ctx->shadow_span.ptr;
+  p.shadow_p0 = ctx->shadow_p0.ptr;
+  p.shadow_p1 = ctx->shadow_p1.ptr;
+  p.shadow_value = ctx->shadow_value.ptr;
+  p.shadow_result = ctx->shadow_result.ptr;
+  p.shadow_count = ctx->shadow_count.ptr;
+  p.shadow_capacity = uint32_t(ctx->shadow_p0.count);
+  p.shadow_stage = (ctx->dscene.deferred_shadow_rays && ctx->shadow_p0.count) ? 1u : 0u;
 #if defined(ETXB_PARITY) && ETXB_PARITY
   p.connect_stage = 0;
 #else
@@ -439,9 +450,16 @@ int run_camera_pass(etxb_ctx* ctx) {
     }
     CUDA_OK(ctx, cudaMemsetAsync(counts + (cur ^ 1u), 0, 4, ctx->stream));
     if (p.connect_stage) CUDA_OK(ctx, cudaMemsetAsync(ctx->conn_count.ptr, 0, 4, ctx->stream));
+    if (p.shadow_stage) CUDA_OK(ctx, cudaMemsetAsync(ctx->shadow_count.ptr, 0, 8, ctx->stream));
     {
       LaunchTimer t(ctx, K_CAMERA_SHADE);
       k_camera_shade<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur);
+    }
+    if (p.shadow_stage) {
+      // persistent warps over the bounce's deferred shadow rays (the number of rays stays on the device)
+      LaunchTimer t(ctx, K_SHADOW_TRACE);
+      uint32_t blocks = std::min<uint32_t>(148u * 8u, blocks_for(std::min<uint64_t>(uint64_t(active) * 32ull, 0x7fffffffull), 256));
+      k_shadow_trace<<<blocks, 256, 0, ctx->stream>>>(p);
     }
     if (p.connect_stage && (ctx->options.options & ETXB_VCM_CONNECT_VERTICES)) {
       uint32_t pending = 0;
@@ -595,6 +613,12 @@ void etxb_destroy(etxb_ctx* ctx) {
   ctx->lv_final.release();
   ctx->cell_range.release();
   ctx->conn_list.release();
+  ctx->shadow_span.release();
+  ctx->shadow_p0.release();
+  ctx->shadow_p1.release();
+  ctx->shadow_value.release();
+  ctx->shadow_result.release();
+  ctx->shadow_count.release();
   ctx->bs_props.release();
   ctx->bs_weight_pdf.release();
   ctx->bs_wo_eta.release();
@@ -670,7 +694,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   for (uint64_t i = 0; i < s.materials.count; ++i) {
     const etxb_material& m = mats[i];
     bool lambert = (m.cls == ETXB_MAT_DIFFUSE) && (m.diffuse_variation == 0);
-    bool smooth = std::max(m.roughness.value[0], m.roughness.value[1]) <= 1.0e-4f;
+    bool smooth = (std::max(m.roughness.value[0], m.roughness.value[1]) <= 1.0e-4f) && (m.roughness.image_index == ETXB_INVALID_INDEX);
     bool always_delta = (((m.cls == ETXB_MAT_DIELECTRIC) || (m.cls == ETXB_MAT_CONDUCTOR)) && smooth) || (m.cls == ETXB_MAT_THINFILM) || (m.cls == ETXB_MAT_MIRROR) ||
                         (m.cls == ETXB_MAT_VOID);
     if (!lambert && !always_delta) ctx->has_stochastic_merge = true;
@@ -727,6 +751,16 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
       if (mats[i].subsurface.cls != 0) ctx->dscene.has_subsurface = 1;
     }
     if ((cam.medium_index != ETXB_INVALID_INDEX) && (cam.medium_index >= s.mediums.count)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "camera medium index out of range");
+    // deferred shadow rays (ShadowBatch, dvcm.cuh) need: no alpha test that can reject, no Boundary surfaces / media (transmittance is 0 or 1),
+    // no BSDF whose evaluation draws from the sampler, no subsurface exits
+    bool deferred = !ctx->has_stochastic_merge && !ctx->dscene.has_boundaries && !ctx->dscene.has_subsurface && (s.mediums.count == 0) && (cam.medium_index == ETXB_INVALID_INDEX);
+    const auto* all_images = static_cast<const etxb_image*>(s.images.a);
+    for (uint64_t i = 0; deferred && (i < s.materials.count); ++i) {
+      if (mats[i].opacity != 1.0f) deferred = false;
+      uint32_t im = mats[i].scattering.image_index;
+      if ((im != ETXB_INVALID_INDEX) && (all_images[im].options & kImageHasAlpha)) deferred = false;
+    }
+    ctx->dscene.deferred_shadow_rays = deferred ? 1u : 0u;
   }
   // ---- images: pixels + flattened row/column CDFs (image.hxx:8-50) ---------------------------------------------------------------
   {
@@ -877,6 +911,20 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   CUDA_OK(ctx, ctx->lv_tmp.alloc(cap));
   CUDA_OK(ctx, ctx->lv_final.alloc(cap));
   CUDA_OK(ctx, ctx->conn_list.alloc(cap));
+  if (ctx->dscene.deferred_shadow_rays) {
+    CUDA_OK(ctx, ctx->shadow_span.alloc(n));
+    CUDA_OK(ctx, ctx->shadow_p0.alloc(cap));
+    CUDA_OK(ctx, ctx->shadow_p1.alloc(cap));
+    CUDA_OK(ctx, ctx->shadow_value.alloc(cap));
+    CUDA_OK(ctx, ctx->shadow_result.alloc(cap));
+    CUDA_OK(ctx, ctx->shadow_count.alloc(2));
+  } else {
+    ctx->shadow_span.release();
+    ctx->shadow_p0.release();
+    ctx->shadow_p1.release();
+    ctx->shadow_value.release();
+    ctx->shadow_result.release();
+  }
   DevBuf<uint32_t>* per_vertex_u32[] = {&ctx->keys_in, &ctx->keys_out, &ctx->vals_in, &ctx->vals_out};
   for (auto* b : per_vertex_u32) CUDA_OK(ctx, b->alloc(cap));
   DevBuf<float4>* per_vertex_f4[] = {&ctx->g_pos, &ctx->g_nrm, &ctx->g_win, &ctx->g_thr};
