@@ -511,6 +511,115 @@ DEV float diffuse_pdf(const BData& d, V3 w_o) {
   return kInvPi * n_dot_o;
 }
 
+// ---- Diffuse, diffuse_variation 1: Heitz/Dupuy rough diffuse microsurface, a random walk in BOTH sample and evaluate
+// (bsdf_external.hxx:177-205 sampleVNDF, :557-578 samplePhaseFunction_diffuse, :580-629 eval_diffuse, :660-693 sample_diffuse) ----
+DEV V3 sample_vndf(Smp& smp, V3 wi, V2 alpha) {
+  const V3 wi_11 = normalize(V3{alpha.x * wi.x, alpha.y * wi.y, wi.z});
+  V2 slope_11 = sample_p22_11(m_acos(wi_11.z), smp.next_2d(), alpha);
+  const float phi = m_atan2(wi_11.y, wi_11.x);
+  V2 slope = {m_cos(phi) * slope_11.x - m_sin(phi) * slope_11.y, m_sin(phi) * slope_11.x + m_cos(phi) * slope_11.y};
+  slope.x *= alpha.x;
+  slope.y *= alpha.y;
+  if ((slope.x != slope.x) || !finitef(slope.x)) {
+    return (wi.z > 0) ? V3{0.0f, 0.0f, 1.0f} : normalize(V3{wi.x, wi.y, 0.0f});
+  }
+  return normalize(V3{-slope.x, -slope.y, 1.0f});
+}
+DEV V3 sample_phase_function_diffuse(Smp& smp, V3 wm) {
+  float r1 = 2.0f * smp.next() - 1.0f;
+  float r2 = 2.0f * smp.next() - 1.0f;
+  float phi = 0.0f;
+  float r = (r1 * r1 > r2 * r2) ? r1 : r2;
+  if (r1 * r1 > r2 * r2) {
+    phi = (kPi / 4.0f) * (r2 / r1);
+  } else if ((r1 != 0.0f) && (r2 != 0.0f)) {
+    phi = (kPi / 2.0f) - (r1 / r2) * (kPi / 4.0f);
+  }
+  float x = r * m_cos(phi);
+  float y = r * m_sin(phi);
+  float z = sqrtf(tmax(0.0f, 1.0f - x * x - y * y));
+  Basis basis = orthonormal_basis(wm);
+  return x * basis.u + y * basis.v + z * wm;
+}
+template <bool SP>
+DEVN Spec<SP> eval_rough_diffuse(Smp& smp, V3 wi, V3 wo, V2 alpha, Spec<SP> albedo) {
+  MicroRay ray_shadowing = micro_ray(wo, alpha);
+  MicroRay ray = micro_ray(-wi, alpha);
+  ray.update_height(1.0f);
+  Spec<SP> res = Spec<SP>::make(0.0f);
+  Spec<SP> energy = Spec<SP>::make(1.0f);
+  int scattering_order = 0;
+  while (true) {
+    ray.update_height(sample_height(ray, smp.next()));
+    if (ray.h == kMaxFloat) break;
+    V3 wm = sample_vndf(smp, -ray.w, alpha);
+    Spec<SP> phasefunction = energy * albedo * tmax(0.0f, dot(wm, wo) * kInvPi);
+    if (scattering_order == 0) {
+      float G2_G1 = -ray.Lambda / (ray_shadowing.Lambda - ray.Lambda);
+      if (G2_G1 > 0) res += phasefunction * G2_G1;
+    } else {
+      ray_shadowing.update_height(ray.h);
+      res += phasefunction * ray_shadowing.G1;
+    }
+    ray.update_direction(sample_phase_function_diffuse(smp, wm), alpha);
+    ray.update_height(ray.h);
+    energy = energy * albedo;
+    if ((scattering_order++ > int(kScatteringOrderMax)) || (ray.h != ray.h) || (ray.w.x != ray.w.x)) return Spec<SP>::make(0.0f);
+  }
+  return res;
+}
+template <bool SP>
+DEVN V3 sample_rough_diffuse(Smp& smp, V3 wi, V2 alpha, Spec<SP> albedo, Spec<SP>& energy) {
+  energy = Spec<SP>::make(1.0f);
+  MicroRay ray = micro_ray(-wi, alpha);
+  ray.update_height(1.0f);
+  int current_scatteringOrder = 0;
+  while (true) {
+    ray.update_height(sample_height(ray, smp.next()));
+    if (ray.h == kMaxFloat) break;
+    current_scatteringOrder++;
+    V3 wm = sample_vndf(smp, -ray.w, alpha);
+    ray.update_direction(sample_phase_function_diffuse(smp, wm), alpha);
+    ray.update_height(ray.h);
+    energy = energy * albedo;
+    if (current_scatteringOrder > int(kScatteringOrderMax)) {
+      energy = Spec<SP>::make(0.0f);
+      return V3{0.0f, 0.0f, 1.0f};
+    }
+  }
+  return ray.w;
+}
+// DiffuseBSDF::sample / evaluate for diffuse_variation 1 (bsdf_various.hxx:36-112)
+template <bool SP>
+DEV BSample<SP> rough_diffuse_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
+  Frame frame = normal_frame(d);
+  V3 local_w_i = frame.to_local(-d.w_i);
+  V2 roughness = evaluate_roughness(sc, m, d.tex);
+  BSample<SP> r = bsample_zero<SP>();
+  r.eta = 1.0f;
+  r.properties = kBsdfReflection | kBsdfDiffuse;
+  Spec<SP> diffuse = apply_image<SP>(sc, m.scattering, d.tex, d.wavelength);
+  V3 local_w_o = sample_rough_diffuse<SP>(smp, local_w_i, roughness, diffuse, r.weight);
+  r.pdf = kInvPi * local_w_o.z;
+  r.w_o = frame.from_local(local_w_o);
+  return r;
+}
+template <bool SP>
+DEV BEval<SP> rough_diffuse_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
+  Frame frame = normal_frame(d);
+  V3 local_w_o = frame.to_local(w_o);
+  if (local_w_o.z <= kEpsilon) return beval_zero<SP>();
+  V3 local_w_i = frame.to_local(-d.w_i);
+  Spec<SP> diffuse = apply_image<SP>(sc, m.scattering, d.tex, d.wavelength);
+  V2 roughness = evaluate_roughness(sc, m, d.tex);
+  BEval<SP> e;
+  e.eta = 1.0f;
+  e.bsdf = eval_rough_diffuse<SP>(smp, local_w_i, local_w_o, roughness, diffuse);
+  e.func = e.bsdf / local_w_o.z;
+  e.pdf = kInvPi * local_w_o.z;
+  return e;
+}
+
 // ---- Dielectric (bsdf_dielectric.hxx:60-259) ---------------------------------------------------------------
 DEV bool dielectric_is_delta(const DeviceScene& sc, const etxb_material& m, V2 tex) {
   V2 r = evaluate_roughness(sc, m, tex);
@@ -1141,7 +1250,7 @@ DEVN float principled_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const e
 template <bool SP>
 DEVG_BSDF BSample<SP> bsdf_sample_generic(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
   switch (m.cls) {
-    case ETXB_MAT_DIFFUSE: return diffuse_sample<SP>(sc, d, m, smp);
+    case ETXB_MAT_DIFFUSE: return rough_diffuse_sample<SP>(sc, d, m, smp);  // diffuse_variation 1 (0 is handled inline by the caller)
     case ETXB_MAT_TRANSLUCENT: return translucent_sample<SP>(sc, d, m, smp);
     case ETXB_MAT_PLASTIC: return plastic_sample<SP>(sc, d, m, smp);
     case ETXB_MAT_CONDUCTOR: return conductor_sample<SP>(sc, d, m, smp);
@@ -1170,13 +1279,13 @@ DEVG_BSDF BSample<SP> bsdf_sample_generic(const DeviceScene& sc, const BData& d,
 }
 template <bool SP>
 DEV BSample<SP> bsdf_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
-  if (m.cls == ETXB_MAT_DIFFUSE) return diffuse_sample<SP>(sc, d, m, smp);
+  if ((m.cls == ETXB_MAT_DIFFUSE) && (m.diffuse_variation == 0u)) return diffuse_sample<SP>(sc, d, m, smp);
   return bsdf_sample_generic<SP>(sc, d, m, smp);
 }
 template <bool SP>
 DEVG_BSDF BEval<SP> bsdf_evaluate_generic(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
   switch (m.cls) {
-    case ETXB_MAT_DIFFUSE: return diffuse_evaluate<SP>(sc, d, w_o, m);
+    case ETXB_MAT_DIFFUSE: return rough_diffuse_evaluate<SP>(sc, d, w_o, m, smp);
     case ETXB_MAT_TRANSLUCENT: return translucent_evaluate<SP>(sc, d, w_o, m);
     case ETXB_MAT_PLASTIC: return plastic_evaluate<SP>(sc, d, w_o, m, smp);
     case ETXB_MAT_CONDUCTOR: return conductor_evaluate<SP>(sc, d, w_o, m, smp);
@@ -1189,7 +1298,7 @@ DEVG_BSDF BEval<SP> bsdf_evaluate_generic(const DeviceScene& sc, const BData& d,
 }
 template <bool SP>
 DEV BEval<SP> bsdf_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
-  if (m.cls == ETXB_MAT_DIFFUSE) return diffuse_evaluate<SP>(sc, d, w_o, m);
+  if ((m.cls == ETXB_MAT_DIFFUSE) && (m.diffuse_variation == 0u)) return diffuse_evaluate<SP>(sc, d, w_o, m);
   return bsdf_evaluate_generic<SP>(sc, d, w_o, m, smp);
 }
 template <bool SP>

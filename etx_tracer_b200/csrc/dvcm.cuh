@@ -339,15 +339,30 @@ DEV void vcm_cam_handle_miss(const DeviceScene& sc, const VcmParams& it, V3 ray_
 DEV V3 cam3(const float* p) { return {p[0], p[1], p[2]}; }
 DEV bool camera_has_lens(const etxb_camera& c) { return (c.lens_radius > kEpsilon) && (c.focal_distance > kEpsilon); }
 
-// generate_ray (:26-62), perspective camera
-DEV void generate_ray(const etxb_camera& camera, V2 uv, V2 sensor_rnd, V3& origin, V3& w_o, float& t_near, float& t_far) {
+// point on the lens in [-1, 1]^2: the unit disk, or the camera's aperture image sampled by its luminance table (:44-48, 73-81)
+DEV V2 sample_lens(const DeviceScene& sc, const etxb_camera& camera, V2 rnd) {
+  if (camera.lens_image == kInvalidIndex) return sample_disk(rnd);
+  float pdf = 0.0f;
+  F4v value;
+  V2 uv = image_sample(sc.images[camera.lens_image], rnd, pdf, value);
+  return uv * 2.0f - 1.0f;
+}
+
+// generate_ray (:26-62)
+DEV void generate_ray(const DeviceScene& sc, const etxb_camera& camera, V2 uv, V2 sensor_rnd, V3& origin, V3& w_o, float& t_near, float& t_far) {
   origin = cam3(camera.position);
+  if (camera.cls == 1u) {  // Camera::Class::Equirectangular (:29-31)
+    w_o = from_spherical(uv.x * kPi, uv.y * kHalfPi);
+    t_near = kRayEpsilon;
+    t_far = kMaxFloat;
+    return;
+  }
   V3 direction = cam3(camera.direction);
   V3 s = uv.x * cam3(camera.side);
   V3 u = uv.y * cam3(camera.up) / camera.aspect;
   w_o = normalize(camera.tan_half_fov * (s + u) + direction);
   if (camera_has_lens(camera)) {
-    V2 sensor_sample = sample_disk(sensor_rnd);
+    V2 sensor_sample = sample_lens(sc, camera, sensor_rnd);
     sensor_sample = sensor_sample * camera.lens_radius;
     origin = origin + cam3(camera.side) * sensor_sample.x + cam3(camera.up) * sensor_sample.y;
     float focal_plane_distance = camera.focal_distance / dot(w_o, direction);
@@ -366,11 +381,12 @@ struct CameraSample {
   float weight, pdf_dir, pdf_dir_out;
 };
 // sample_film (:64-118)
-DEV CameraSample sample_film(Smp& smp, const etxb_camera& camera, V3 from_point) {
+DEV CameraSample sample_film(Smp& smp, const DeviceScene& sc, const etxb_camera& camera, V3 from_point) {
   CameraSample r = {};
+  if (camera.cls == 1u) return r;  // the reference has no film sampling for the equirectangular camera (:65-68): light paths never connect to it
   V2 sensor_sample = {0.0f, 0.0f};
   if (camera_has_lens(camera)) {
-    sensor_sample = sample_disk(smp.next_2d());
+    sensor_sample = sample_lens(sc, camera, smp.next_2d());
     sensor_sample = sensor_sample * camera.lens_radius;
   }
   r.position = cam3(camera.position) + sensor_sample.x * cam3(camera.side) + sensor_sample.y * cam3(camera.up);
@@ -449,13 +465,13 @@ DEV PathState<SP> generate_camera_state(const DeviceScene& sc, const VcmParams& 
   V2 uv;
   uv.x = (float(px) + 0.5f + sample_radius * (s.sampler.next() * 2.0f - 1.0f)) / float(camera.film_size[0]) * 2.0f - 1.0f;
   uv.y = (float(py) + 0.5f + sample_radius * (s.sampler.next() * 2.0f - 1.0f)) / float(camera.film_size[1]) * 2.0f - 1.0f;
-  generate_ray(camera, uv, s.sampler.next_2d(), s.ray_o, s.ray_d, s.ray_min_t, s.ray_max_t);
+  generate_ray(sc, camera, uv, s.sampler.next_2d(), s.ray_o, s.ray_d, s.ray_min_t, s.ray_max_t);
   s.throughput = Spec<SP>::make(1.0f);
   s.gathered = Spec<SP>::make(0.0f);
   s.merged = {0.0f, 0.0f, 0.0f};
   // film_evaluate_out (scene_camera.hxx:120-126)
   float cos_t = dot(s.ray_d, cam3(camera.direction));
-  float pdf_dir = 1.0f / (camera.area * cos_t * cos_t * cos_t);
+  float pdf_dir = (camera.cls == 1u) ? 1.0f : 1.0f / (camera.area * cos_t * cos_t * cos_t);
   s.d_vcm = 1.0f / pdf_dir;
   s.d_vc = 0.0f;
   s.d_vm = 0.0f;
@@ -586,7 +602,7 @@ DEV bool vcm_connect_to_camera(const DeviceScene& sc, const VcmParams& it, const
   if ((it.connect_to_camera() == false) || (state.total_path_depth + 2 > sc.max_path_length) || (state.total_path_depth + 2 < sc.min_path_length)) return false;
   const etxb_camera& camera = sc.camera;
   V3 sample_pos = ep.pos();
-  CameraSample cs = sample_film(state.sampler, camera, sample_pos);
+  CameraSample cs = sample_film(state.sampler, sc, camera, sample_pos);
   if (cs.pdf_dir <= 0.0f) return false;
   V3 direction = cs.position - sample_pos;
   float dist2 = dot(direction, direction);

@@ -671,13 +671,20 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   const etxb_camera& cam = *static_cast<const etxb_camera*>(camera_blob);
 
   // ---- what the device path does not cover yet fails loudly (no CPU fallback) --------------------------------------
-  if (cam.cls != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "equirectangular camera is not supported on the device yet");
-  if (cam.lens_image != ETXB_INVALID_INDEX) return fail(ctx, ETXB_ERR_UNSUPPORTED, "lens aperture image is not supported on the device yet");
+  if (cam.cls > 1u) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "unknown camera class %u", cam.cls);
+  if (cam.lens_image != ETXB_INVALID_INDEX) {
+    if (cam.lens_image >= s.images.count) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "camera lens image index out of range");
+    const auto& lens = static_cast<const etxb_image*>(s.images.a)[cam.lens_image];
+    if (lens.y_distribution.values.count != uint64_t(lens.isize[1]) + 1u) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "camera lens image has no sampling table");
+  }
   const auto* mats = static_cast<const etxb_material*>(s.materials.a);
   for (uint64_t i = 0; i < s.materials.count; ++i) {
     const etxb_material& m = mats[i];
     if (!material_class_supported_host(m.cls)) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: class %u is not supported on the device yet", (unsigned long long)i, m.cls);
-    if (m.diffuse_variation != 0) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: diffuse_variation %u is not supported on the device yet", (unsigned long long)i, m.diffuse_variation);
+    if (m.diffuse_variation > 2u) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu: unknown diffuse_variation %u", (unsigned long long)i, m.diffuse_variation);
+    if (m.diffuse_variation == 2u) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: diffuse_variation 2 (vMF diffuse) is not supported on the device yet", (unsigned long long)i);
+    if ((m.diffuse_variation == 1u) && (m.cls != ETXB_MAT_DIFFUSE))
+      return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: diffuse_variation 1 under class %u (rough diffuse base layer) is not supported on the device yet", (unsigned long long)i, m.cls);
     if (m.subsurface.cls > 2u) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu: unknown subsurface class %u", (unsigned long long)i, m.subsurface.cls);
     if (m.subsurface.cls != 0) {
       if (s.subsurface_exit_material >= s.materials.count) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu uses subsurface scattering but scene.subsurface_exit_material is not set", (unsigned long long)i);

@@ -619,7 +619,7 @@ class SceneData:
 # BASELINE.json configs
 # ---------------------------------------------------------------------------------------------------
 def cornell_box(width=512, height=512, samples=16, spectral=False, sphere=False, sphere_segments=128, sphere_rings=81, wall_subdiv=1,
-                sphere_roughness=0.0, max_path_length=1023, tall_box_material="diffuse"):
+                sphere_roughness=0.0, max_path_length=1023, tall_box_material="diffuse", finalize=True):
     """C1 (sphere=False, spectral=False) / C2 (sphere=True, spectral=True): SURVEY.md §8(d).
 
     Closed box x,z in [-1,1], y in [0,2] (the reference asset's dimensions, bin/assets/cornellbox/cornellbox.json:9-34 camera),
@@ -652,6 +652,8 @@ def cornell_box(width=512, height=512, samples=16, spectral=False, sphere=False,
     else:
         sd.add_box([0.33, 0.3, 0.35], (0.3, 0.3, 0.3), -17.0, grey, s)
     sd.set_camera([0.0, 1.0, 3.82], [0.0, 1.0, -6.18], [0.0, 1.0, 0.0], width, height, 39.597755335771296, clip_near=0.1, clip_far=100.0)
+    if not finalize:
+        return sd  # the caller still changes the camera / adds images
     return sd.finalize(samples=samples, spectral=spectral, max_path_length=max_path_length)
 
 
@@ -670,6 +672,7 @@ MATERIAL_KINDS = {
     "velvet": dict(cls=S.MAT_VELVET, kd=[0.6, 0.1, 0.1], ks=[0.5, 0.5, 0.5], roughness=0.7),
     "principled": dict(cls=S.MAT_PRINCIPLED, kd=[0.8, 0.5, 0.2], ks=[1.0, 1.0, 1.0], roughness=0.5, metalness=0.4, transmission=0.3),
     "void": dict(cls=S.MAT_VOID),
+    "diffuse_rough": dict(kd=[0.8, 0.7, 0.5], roughness=0.6, diffuse_variation=1),  # Heitz rough diffuse: random walk in sample AND evaluate
     # subsurface scattering on top of a diffuse-lobe class (material.hxx:36-51)
     "sss_random_walk": dict(kd=[0.8, 0.6, 0.4], subsurface=dict(cls="random_walk", path="diffuse", distances=[1.0, 0.4, 0.15], scale=0.12)),
     "sss_refracted": dict(cls=S.MAT_PLASTIC, kd=[0.7, 0.8, 0.6], ks=[1.0, 1.0, 1.0], roughness=0.3, int_ior="plastic",
@@ -698,6 +701,32 @@ def material_box(kind, width=32, height=32, samples=16, spectral=False, sphere_s
     sd.add_box([-0.33, 0.6, -0.29], (0.3, 0.6, 0.3), 17.0, test)
     sd.add_uv_sphere([0.38, 0.351, 0.35], 0.35, sphere_segments, sphere_rings, test)
     sd.set_camera([0.0, 1.0, 3.82], [0.0, 1.0, -6.18], [0.0, 1.0, 0.0], width, height, 39.597755335771296, clip_near=0.1, clip_far=100.0)
+    return sd.finalize(samples=samples, spectral=spectral)
+
+
+CAMERA_KINDS = ("thin_lens", "lens_image", "equirectangular")
+
+
+def camera_box(kind, width=32, height=32, samples=16, spectral=False):
+    """Cornell box seen through the camera variants of scene_camera.hxx: thin lens (disk aperture), aperture image, equirectangular."""
+    sd = cornell_box(width, height, samples=samples, spectral=spectral, sphere=False, finalize=False)
+    sd.name = f"camera_box[{kind}]" + ("/spectral" if spectral else "/rgb")
+    if kind == "equirectangular":
+        sd.set_camera([0.0, 1.0, 1.5], [0.0, 1.0, -6.18], [0.0, 1.0, 0.0], width, height, 39.597755335771296, clip_near=0.1, clip_far=100.0)
+        sd.camera["cls"] = 1
+    else:
+        sd.set_camera([0.0, 1.0, 3.82], [0.0, 1.0, -6.18], [0.0, 1.0, 0.0], width, height, 39.597755335771296, clip_near=0.1, clip_far=100.0,
+                      lens_radius=0.08, focal_distance=3.9)
+        if kind == "lens_image":
+            # a hexagon-ish aperture with a bright rim (the loader builds the table with BuildSamplingTable | UniformSamplingTable,
+            # scene_representation.cxx:1137)
+            n = 16
+            yy, xx = np.mgrid[0:n, 0:n]
+            cx, cy = (xx + 0.5) / n * 2 - 1, (yy + 0.5) / n * 2 - 1
+            r = np.maximum(np.abs(cx), np.abs(cx) * 0.5 + np.abs(cy) * 0.866)
+            v = np.where(r < 0.9, 0.3 + 0.7 * (r / 0.9) ** 4, 0.0)
+            px = np.stack([v, v, v, np.ones_like(v)], axis=-1).astype(f32)
+            sd.camera["lens_image"] = sd.add_image(px, repeat=False, build_table=True, uniform_table=True)
     return sd.finalize(samples=samples, spectral=spectral)
 
 

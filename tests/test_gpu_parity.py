@@ -307,3 +307,39 @@ def test_iterations_in_flight_render_the_same_frame(api, lanes):
     assert rel_l2(grp.film(S.FILM_RESULT)[..., :3], ref.film(S.FILM_RESULT)[..., :3]) < 1e-5
     grp.close()
     ref.close()
+
+
+@pytest.mark.parametrize("spectral", [False, True])
+@pytest.mark.parametrize("kind", scenes.CAMERA_KINDS)
+def test_camera_variants_are_bit_exact(api, oracle_mod, kind, spectral):
+    """scene_camera.hxx: thin lens with a disk aperture, aperture image sampled through its table, equirectangular camera (which the
+    reference's light paths cannot connect to: its sample_film returns nothing)."""
+    sd = scenes.camera_box(kind, 32, 32, spectral=spectral)
+    # a small merge radius: with the default one the lens' MIS weights push every light-image splat below the driver's
+    # dot(val, val) > eps cut (vcm_cpu.cxx:160-166) and the light image would be empty
+    opts = S.default_vcm_options()
+    opts["initial_radius"] = 0.02
+    o = oracle_mod.Oracle(sd)
+    o.set_options(opts)
+    o.begin(0)
+    o.run(2, threads=1)
+    g = api.GPUVCM(sd, flavor="parity")
+    g.options[:] = opts
+    g.render(2)
+    if kind != "equirectangular":
+        assert o.film(S.FILM_LIGHT)[..., :3].any()
+    for bid, dt in ((S.BUF_LIGHT_SAMPLER, np.uint32), (S.BUF_LV_POS, np.float32), (S.BUF_CAMERA_SAMPLER, np.uint32), (S.BUF_CAMERA_GATHERED, np.float32)):
+        a, b = g.buffer(bid, dt), o.buffer(bid, dt)
+        same = (a.view(np.uint32) == b.view(np.uint32))
+        assert a.shape == b.shape and same.all(), f"{kind} buffer {bid}: {100.0 * same.mean():.3f}% identical"
+    assert bit_equal(g.film(S.FILM_CAMERA)[..., :3], o.film(S.FILM_CAMERA)[..., :3])
+    assert rel_l2(g.film(S.FILM_LIGHT)[..., :3], o.film(S.FILM_LIGHT)[..., :3]) < 1e-6
+    if kind == "equirectangular":
+        assert not g.film(S.FILM_LIGHT)[..., :3].any()
+    g.close()
+    f = api.GPUVCM(sd, flavor="fast")
+    f.options[:] = opts
+    f.render(2)
+    img, ref = f.film(S.FILM_RESULT)[..., :3], o.film(S.FILM_RESULT)[..., :3]
+    assert np.isfinite(img).all() and rel_l2(img, ref) < 0.05
+    f.close()
