@@ -38,9 +38,24 @@ def workload(args):
         w, h = (args.res, args.res * 9 // 16) if args.res else (1920, 1080)
         sd = scenes.procedural_room(w, h, samples=1024, spectral=True)
         desc = "C3: %d-triangle procedural room (plastic/conductor/thin-film + env map), spectral, %dx%d, full VCM" % (sd.triangle_count, sd.width, sd.height)
+    elif args.workload == "C4":
+        sd = scenes.sss_dragon(args.res or 1024, args.res or 1024, samples=512, spectral=True)
+        desc = "C4: %d-triangle displaced mesh, plastic + random-walk subsurface, 3 area emitters, spectral, %dx%d, full VCM" % (sd.triangle_count, sd.width, sd.height)
+    elif args.workload == "C5":
+        sd = scenes.cloud_box(args.res or 1024, args.res or 1024, samples=256, spectral=True, grid=256)
+        desc = "C5: heterogeneous cloud (256^3 density grid) in a Boundary cube, sun + sky, spectral, %dx%d, VCM connect-only (volumetric BDPT)" % (sd.width, sd.height)
     else:
         raise SystemExit(f"unknown workload {args.workload}")
     return sd, desc
+
+
+def workload_vcm_options(args):
+    """Integrator options of the workload: the VCMOptions defaults (vcm_shared.cxx:6-28), C5 with merging off (= volumetric BDPT)."""
+    from etx_tracer_b200 import structs as S
+    opts = S.default_vcm_options()
+    if args.workload == "C5":
+        opts["options"] = S.VCM_CONNECT_ONLY
+    return opts
 
 
 def scene_factory(args, res):
@@ -50,6 +65,10 @@ def scene_factory(args, res):
         return scenes.cornell_box(res, res, samples=256, spectral=True, sphere=True)
     if args.workload == "C3":
         return scenes.procedural_room(res, max(16, res * 9 // 16), samples=1024, spectral=True)
+    if args.workload == "C4":
+        return scenes.sss_dragon(res, res, samples=512, spectral=True)
+    if args.workload == "C5":
+        return scenes.cloud_box(res, res, samples=256, spectral=True, grid=256)
     return scenes.cornell_box(res, res, samples=16, spectral=False)
 
 
@@ -107,7 +126,7 @@ def algorithmic_bytes(counters, n_pixels, steps):
     return total, camera_bounce
 
 
-def cpu_baseline_run(sd_factory, budget_s, threads):
+def cpu_baseline_run(sd_factory, budget_s, threads, opts=None):
     """Times the reference's CPU VCM (oracle/_ref) on a bounded sample: same scene, resolution reduced until one iteration fits the budget."""
     from oracle import oracle_py
     flavor = "native"
@@ -117,6 +136,8 @@ def cpu_baseline_run(sd_factory, budget_s, threads):
         flavor = "parity"
     probe = sd_factory(64)
     o = oracle_py.Oracle(probe, flavor)
+    if opts is not None:
+        o.set_options(opts)
     o.begin(0)
     t0 = time.time()
     o.run(1, threads=threads)
@@ -125,6 +146,8 @@ def cpu_baseline_run(sd_factory, budget_s, threads):
     res = int(min(1024, max(64, (rate * budget_s * (probe.width / probe.height)) ** 0.5)) // 32 * 32)
     sd = sd_factory(res)
     o = oracle_py.Oracle(sd, flavor)
+    if opts is not None:
+        o.set_options(opts)
     o.begin(0)
     t0 = time.time()
     total = o.run(1, threads=threads)
@@ -150,7 +173,9 @@ def run_reference(args):
         oracle_py.load(flavor)
     except OSError:
         flavor = "parity"
+    opts = workload_vcm_options(args)
     probe = oracle_py.Oracle(factory(64), flavor)
+    probe.set_options(opts)
     probe.begin(0)
     t0 = time.time()
     probe.run(1, threads=threads)
@@ -161,6 +186,7 @@ def run_reference(args):
     sd = factory(res)
     res_n = sd.width * sd.height
     o = oracle_py.Oracle(sd, flavor)
+    o.set_options(opts)
     o.begin(0)
     o.run(args.warmup, threads=threads)
     t0 = time.time()
@@ -234,6 +260,7 @@ def main():
             from etx_tracer_b200.multigpu import InterleavedVCM
             interleaved = InterleavedVCM(g, dist, rank, world)
     samples_per_step = n_pixels * (1 if tile_mode else world)
+    g.options[:] = workload_vcm_options(args)
 
     def begin():
         if interleaved:
@@ -359,7 +386,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             from etx_tracer_b200 import scenes
-            cpu, _ = cpu_baseline_run(lambda res: scene_factory(args, res), args.cpu_budget, os.cpu_count() or 1)
+            cpu, _ = cpu_baseline_run(lambda res: scene_factory(args, res), args.cpu_budget, os.cpu_count() or 1, workload_vcm_options(args))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if tile_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc,

@@ -472,9 +472,15 @@ DEVN Spec<SP> eval_dielectric(float wavelength, Smp& smp, V3 wi, V3 wo, bool wo_
   return 0.5f * singleScattering + multipleScattering;
 }
 
-// ---- Diffuse (bsdf_various.hxx:36-133), diffuse_variation 0 (Lambert) -------------------------------------
+// ---- Diffuse (bsdf_various.hxx:36-133).  diffuse_variation 0 (Lambert) stays inline; 1 (rough microsurface walk) and 2 (vMF fit)
+// go through ONE out-of-line routine (defined further down) ----------------------------------------------------------
 template <bool SP>
-DEV BEval<SP> diffuse_layer(const DeviceScene& sc, const BData& d, V3 local_w_o, const etxb_material& m) {
+DEVN BEval<SP> diffuse_layer_variation(const DeviceScene& sc, const BData& d, V3 local_w_i, V3 local_w_o, const etxb_material& m, Smp& smp);
+
+// DiffuseBSDF::diffuse_layer (bsdf_various.hxx:36-71) — also the base layer of PlasticBSDF::evaluate (bsdf_plastic.hxx:136)
+template <bool SP>
+DEV BEval<SP> diffuse_layer(const DeviceScene& sc, const BData& d, V3 local_w_i, V3 local_w_o, const etxb_material& m, Smp& smp) {
+  if (m.diffuse_variation != 0u) return diffuse_layer_variation<SP>(sc, d, local_w_i, local_w_o, m, smp);
   if (local_w_o.z <= 0.0f) return beval_zero<SP>();
   Spec<SP> diffuse = apply_image<SP>(sc, m.scattering, d.tex, d.wavelength);
   BEval<SP> e;
@@ -484,26 +490,30 @@ DEV BEval<SP> diffuse_layer(const DeviceScene& sc, const BData& d, V3 local_w_o,
   e.pdf = kInvPi * local_w_o.z;
   return e;
 }
+// DiffuseBSDF::sample for variations 0 and 2 (bsdf_various.hxx:73-100): cosine lobe, weight = layer.bsdf / layer.pdf
 template <bool SP>
 DEV BSample<SP> diffuse_sample(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
   Frame frame = normal_frame(d);
+  V3 local_w_i = frame.to_local(-d.w_i);
   BSample<SP> r = bsample_zero<SP>();
   r.eta = 1.0f;
   r.properties = kBsdfReflection | kBsdfDiffuse;
   V2 cos_rnd = smp.has_fixed() ? V2{smp.fixed_u, smp.fixed_v} : smp.next_2d();
   V3 local_w_o = sample_cosine_local(cos_rnd, 1.0f);
-  BEval<SP> dl = diffuse_layer<SP>(sc, d, local_w_o, m);
+  BEval<SP> dl = diffuse_layer<SP>(sc, d, local_w_i, local_w_o, m, smp);
   r.weight = dl.pdf == 0.0f ? Spec<SP>::make(0.0f) : dl.bsdf / dl.pdf;
   r.pdf = dl.pdf;
   r.w_o = frame.from_local(local_w_o);
   return r;
 }
+// DiffuseBSDF::evaluate (bsdf_various.hxx:102-111), every variation
 template <bool SP>
-DEV BEval<SP> diffuse_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m) {
+DEV BEval<SP> diffuse_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
   Frame frame = normal_frame(d);
   V3 local_w_o = frame.to_local(w_o);
   if (local_w_o.z <= kEpsilon) return beval_zero<SP>();
-  return diffuse_layer<SP>(sc, d, local_w_o, m);
+  V3 local_w_i = frame.to_local(-d.w_i);
+  return diffuse_layer<SP>(sc, d, local_w_i, local_w_o, m, smp);
 }
 DEV float diffuse_pdf(const BData& d, V3 w_o) {
   float n_dot_o = dot(front_facing_normal(d), w_o);
@@ -604,18 +614,174 @@ DEV BSample<SP> rough_diffuse_sample(const DeviceScene& sc, const BData& d, cons
   r.w_o = frame.from_local(local_w_o);
   return r;
 }
+// ---- Diffuse, diffuse_variation 2: d'Eon & Weidlich, "VMF Diffuse: A Unified Rough Diffuse BRDF" — a closed-form fit, no sampler
+// draws (bsdf_external.hxx:696-897; the coefficients are the paper's, the operation order is the reference's) ----
+DEV float erf_buermann(float x) {  // :700-705, Buermann series
+  float e = m_exp(-x * x);
+  return (x >= 0.0f ? 1.0f : -1.0f) * 2.0f / kSqrtPi * sqrtf(1.0f - e) * (kSqrtPi / 2.0f + 31.0f / 200.0f * e - 341.0f / 8000.0f * e * e);
+}
+DEV Spec<true> spec_erf(Spec<true> x) { return {erf_buermann(x.v)}; }
+DEV Spec<false> spec_erf(Spec<false> x) {  // :707-715: the RGB overload works on whole responses (float3 sign / sqrt / exp)
+  Spec<false> e = spec_exp(-(x * x));
+  Spec<false> sg = {x.x >= 0.0f ? 1.0f : -1.0f, x.y >= 0.0f ? 1.0f : -1.0f, x.z >= 0.0f ? 1.0f : -1.0f};
+  Spec<false> om = 1.0f - e;
+  Spec<false> root = {sqrtf(om.x), sqrtf(om.y), sqrtf(om.z)};
+  return sg * 2.0f / kSqrtPi * root * (31.0f / 200.0f * e + kSqrtPi / 2.0f - 341.0f / 8000.0f * e * e);
+}
+DEV Spec<true> spec_sqrt(Spec<true> a) { return {sqrtf(a.v)}; }
+DEV Spec<false> spec_sqrt(Spec<false> a) { return {sqrtf(a.x), sqrtf(a.y), sqrtf(a.z)}; }
+DEV Spec<true> spec_atan(Spec<true> a) { return {m_atan(a.v)}; }
+DEV Spec<false> spec_atan(Spec<false> a) { return {m_atan(a.x), m_atan(a.y), m_atan(a.z)}; }
+DEV Spec<true> spec_pow(Spec<true> a, Spec<true> b) { return {m_pow(a.v, b.v)}; }
+DEV Spec<false> spec_pow(Spec<false> a, Spec<false> b) { return {m_pow(a.x, b.x), m_pow(a.y, b.y), m_pow(a.z, b.z)}; }
+DEV Spec<true> spec_max0(Spec<true> a) { return {fmaxf(a.v, 0.0f)}; }
+DEV Spec<false> spec_max0(Spec<false> a) { return {fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f), fmaxf(a.z, 0.0f)}; }
+
+// multiple-scattering term of the fit (:717-722)
 template <bool SP>
-DEV BEval<SP> rough_diffuse_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
-  Frame frame = normal_frame(d);
-  V3 local_w_o = frame.to_local(w_o);
-  if (local_w_o.z <= kEpsilon) return beval_zero<SP>();
-  V3 local_w_i = frame.to_local(-d.w_i);
+DEV Spec<SP> vmf_fm(float ui, float uo, float r, Spec<SP> c) {
+  Spec<SP> C = spec_sqrt(1.0f - c);
+  Spec<SP> Ck = (1.0f - 0.5441615108674713f * C - 0.45302863761693374f * (1.0f - c)) / (1.4293127703064865f * C + 1.0f);
+  Spec<SP> Ca = c / spec_pow(1.16942f * C + 1.0075f, spec_atan((0.0225272f + (-0.264641f + r) * r) * spec_erf(c)));
+  return spec_max0(0.384016f * (Ca + -0.341969f) * Ca * Ck * (-0.0578978f / (0.287663f + ui * uo) + fabsf(-0.0898863f + m_tanh(r))));
+}
+// cross section of a Beckmann surface, expanded for small m (:724-738)
+DEV float vmf_sigma_beckmann_expanded(float u, float m) {
+  if (0.0f == m) return (u + fabsf(u)) / 2.0f;
+  float m2 = m * m;
+  if (1.0f == u) return 1.0f - 0.5f * m2;
+  float expansion_term = -0.25f * m2 * (u + fabsf(u));
+  float u2 = u * u;
+  return ((m_exp(u2 / (m2 * (-1.0f + u2))) * m * sqrtf(1.0f - u2)) / sqrtf(kPi) + u * (1.0f + erf_buermann(u / (m * sqrtf(1.0f - u2))))) / 2.0f + expansion_term;
+}
+DEV float vmf_coth(float x) { return (m_exp(-x) + m_exp(x)) / (-m_exp(-x) + m_exp(x)); }  // :739-741
+// vMF cross section (:743-785): Legendre-style expansion in u with closed-form coefficients in m
+DEVN float vmf_sigma(float u, float m) {
+  if (m < 0.25f) return vmf_sigma_beckmann_expanded(u, m);
+  float m2 = m * m, m4 = m2 * m2, m8 = m4 * m4;
+  float u2 = u * u, u4 = u2 * u2, u6 = u2 * u4, u8 = u4 * u4, u10 = u6 * u4, u12 = u6 * u6;
+  float coth2m2 = vmf_coth(2.0f / m2);
+  float sinh2m2 = m_sinh(2.0f / m2);
+  if (m > 0.9f) return 0.25f - 0.25f * u * (m2 - 2.0f * coth2m2) + 0.0390625f * (-1.0f + 3.0f * u2) * (4.0f + 3.0f * m4 - 6.0f * m2 * coth2m2);
+  float q2 = 1.0132789611816406e-6f * (35.0f - 1260.0f * u2 + 6930.0f * u4 - 12012.0f * u6 + 6435.0f * u8) * (1.0f + coth2m2) *
+             (-256.0f - 315.0f * m4 * (128.0f + 33.0f * m4 * (80.0f + 364.0f * m4 + 195.0f * m8)) +
+              18.0f * m2 * (256.0f + 385.0f * m4 * (32.0f + 312.0f * m4 + 585.0f * m8)) * coth2m2) *
+             sinh2m2;
+  float q1 = 9.12696123123169e-8f * (-63.0f + 3465.0f * u2 - 30030.0f * u4 + 90090.0f * u6 - 109395.0f * u8 + 46189.0f * u10) * (1.0f + coth2m2) *
+             (-1024.0f - 495.0f * m4 * (768.0f + 91.0f * m4 * (448.0f + 15.0f * m4 * (448.0f + 1836.0f * m4 + 969.0f * m8))) +
+              110.0f * m2 * (256.0f + 117.0f * m4 * (256.0f + 21.0f * m4 * (336.0f + 85.0f * m4 * (32.0f + 57.0f * m4)))) * coth2m2) *
+             sinh2m2;
+  float q0 = 4.3655745685100555e-9f * (231.0f - 18018.0f * u2 + 225225.0f * u4 - 1.02102e6f * u6 + 2.078505e6f * u8 - 1.939938e6f * u10 + 676039.0f * u12) *
+             (1.0f + coth2m2) *
+             (-4096.0f - 3003.0f * m4 * (1024.0f + 45.0f * m4 * (2560.0f + 51.0f * m4 * (1792.0f + 285.0f * m4 * (80.0f + 308.0f * m4 + 161.0f * m8)))) +
+              78.0f * m2 * (2048.0f + 385.0f * m4 * (1280.0f + 153.0f * m4 * (512.0f + 57.0f * m4 * (192.0f + 35.0f * m4 * (40.0f + 69.0f * m4))))) * coth2m2) *
+             sinh2m2;
+  float e2m2 = m_exp(2.0f / m2);
+  return 0.25f - 0.25f * u * (m2 - 2.0f * coth2m2) + 0.0390625f * (-1.0f + 3.0f * u2) * (4.0f + 3.0f * m4 - 6.0f * m2 * coth2m2) -
+         0.000732421875f * (3.0f - 30.0f * u2 + 35.0f * u4) * (16.0f + 180.0f * m4 + 105.0f * m8 - 10.0f * m2 * (8.0f + 21.0f * m4) * coth2m2) +
+         0.000049591064453125f * (-5.0f + 105.0f * u2 - 315.0f * u4 + 231.0f * u6) *
+           (64.0f + 105.0f * m4 * (32.0f + 180.0f * m4 + 99.0f * m8) - 42.0f * m2 * (16.0f + 240.0f * m4 + 495.0f * m8) * coth2m2) +
+         (q2 / e2m2) - (q1 / e2m2) + (q0 / e2m2);
+}
+// vMFdiffuseBRDF (:787-894): three single/multiple-scattering orders as low-order Fourier series in the azimuth difference
+template <bool SP>
+DEVN Spec<SP> vmf_diffuse_brdf(V3 w_i, V3 w_o, V2 roughness, Spec<SP> albedo) {
+  float r = sqrtf(roughness.x * roughness.y);
+  const float r_max = 1.0f - 4.0f * kEpsilon;
+  r = (r < 0.0f) ? 0.0f : (r > r_max ? r_max : r);
+  if (r == 0.0f) return albedo * kInvPi;
+  float cos_theta_i = w_i.z;
+  float sin_theta_i = sqrtf(1.0f - cos_theta_i * cos_theta_i);
+  float cos_theta_o = w_o.z;
+  float sin_theta_o = sqrtf(1.0f - cos_theta_o * cos_theta_o);
+  float cos_phi_diff = 0.0f;
+  if (sin_theta_i > 0.0f && sin_theta_o > 0.0f) {
+    auto clamp11 = [](float v) { return (v < -1.0f) ? -1.0f : (v > 1.0f ? 1.0f : v); };
+    float sin_phi_i = clamp11(w_i.y / sin_theta_i);
+    float cos_phi_i = clamp11(w_i.x / sin_theta_i);
+    float sin_phi_o = clamp11(w_o.y / sin_theta_o);
+    float cos_phi_o = clamp11(w_o.x / sin_theta_o);
+    cos_phi_diff = clamp11(cos_phi_i * cos_phi_o + sin_phi_i * sin_phi_o);
+  }
+  float phi = m_acos(cos_phi_diff);
+  float ui = w_i.z, uo = w_o.z;
+  float m = -m_log(1.0f - sqrtf(r));
+  float sigmai = vmf_sigma(ui, m);
+  float sigmao = vmf_sigma(uo, m);
+  float sigmano = vmf_sigma(-uo, m);
+  float sigio = sigmai * sigmao;
+  float sigdenom = uo * sigmai + ui * sigmano;
+  float r2 = r * r;
+  float r25 = r2 * sqrtf(r);
+  float r3 = r * r2;
+  float r4 = r2 * r2;
+  float r45 = r4 * sqrtf(r);
+  float r5 = r3 * r2;
+  float ui2 = saturatef(ui * ui);
+  float uo2 = saturatef(uo * uo);
+  float sqrtuiuo = sqrtf((1.0f - ui2) * (1.0f - uo2));
+
+  float C100 = 1.0f + (-0.1f * r + 0.84f * r4) / (1.0f + 9.0f * r3);
+  float C101 = (0.0173f * r + 20.4f * r2 - 9.47f * r3) / (1.0f + 7.46f * r);
+  float C102 = (-0.927f * r + 2.37f * r2) / (1.24f + r2);
+  float C103 = (-0.110f * r - 1.54f * r2) / (1.0f - 1.05f * r + 7.1f * r2);
+  float f10 = ((C100 + C101 * ui * uo + C102 * ui2 * uo2 + C103 * (ui2 + uo2)) * sigio) / sigdenom;
+
+  float C110 = (0.54f * r - 0.182f * r3) / (1.0f + 1.32f * r2);
+  float C111 = (-0.097f * r + 0.62f * r2 - 0.375f * r3) / (1.0f + 0.4f * r3);
+  float C112 = 0.283f + 0.862f * r - 0.681f * r2;
+  float f11 = (sqrtuiuo * (C110 + C111 * ui * uo)) * m_pow(sigio, C112) / sigdenom;
+
+  float C120 = (2.25f * r + 5.1f * r2) / (1.0f + 9.8f * r + 32.4f * r2);
+  float C121 = (-4.32f * r + 6.0f * r3) / (1.0f + 9.7f * r + 287.0f * r3);
+  float f12 = ((1.0f - ui2) * (1.0f - uo2) * (C120 + C121 * uo) * (C120 + C121 * ui)) / (ui + uo);
+
+  float C200 = (0.00056f * r + 0.226f * r2) / (1.0f + 7.07f * r2);
+  float C201 = (-0.268f * r + 4.57f * r2 - 12.04f * r3) / (1.0f + 36.7f * r3);
+  float C202 = (0.418f * r + 2.52f * r2 - 0.97f * r3) / (1.0f + 10.0f * r2);
+  float C203 = (0.068f * r - 2.25f * r2 + 2.65f * r3) / (1.0f + 21.4f * r3);
+  float C204 = (0.050f * r - 4.22f * r3) / (1.0f + 17.6f * r2 + 43.1f * r3);
+  float f20 = (C200 + C201 * ui * uo + C203 * ui2 * uo2 + C202 * (ui + uo) + C204 * (ui2 + uo2)) / (ui + uo);
+
+  float C210 = (-0.049f * r - 0.027f * r3) / (1.0f + 3.36f * r2);
+  float C211 = (2.77f * r2 - 8.332f * r25 + 6.073f * r3) / (1.0f + 50.0f * r4);
+  float C212 = (-0.431f * r2 - 0.295f * r3) / (1.0f + 23.9f * r3);
+  float f21 = (sqrtuiuo * (C210 + C211 * ui * uo + C212 * (ui + uo))) / (ui + uo);
+
+  float C300 = (-0.083f * r3 + 0.262f * r4) / (1.0f - 1.9f * r2 + 38.6f * r4);
+  float C301 = (-0.627f * r2 + 4.95f * r25 - 2.44f * r3) / (1.0f + 31.5f * r4);
+  float C302 = (0.33f * r2 + 0.31f * r25 + 1.4f * r3) / (1.0f + 20.0f * r3);
+  float C303 = (-0.74f * r2 + 1.77f * r25 - 4.06f * r3) / (1.0f + 215.0f * r5);
+  float C304 = (-1.026f * r3) / (1.0f + 5.81f * r2 + 13.2f * r3);
+  float f30 = (C300 + C301 * ui * uo + C303 * ui2 * uo2 + C302 * (ui + uo) + C304 * (ui2 + uo2)) / (ui + uo);
+
+  float C310 = (0.028f * r2 - 0.0132f * r3) / (1.0f + 7.46f * r2 - 3.315f * r4);
+  float C311 = (-0.134f * r2 + 0.162f * r25 + 0.302f * r3) / (1.0f + 57.5f * r45);
+  float C312 = (-0.119f * r2 + 0.5f * r25 - 0.207f * r3) / (1.0f + 18.7f * r3);
+  float f31 = (sqrtuiuo * (C310 + C311 * ui * uo + C312 * (ui + uo))) / (ui + uo);
+
+  Spec<SP> t0 = albedo * tmax(0.0f, f10 + f11 * m_cos(phi) * 2.0f + f12 * m_cos(2.0f * phi) * 2.0f);
+  Spec<SP> t1 = albedo * albedo * tmax(0.0f, f20 + f21 * m_cos(phi) * 2.0f);
+  Spec<SP> t2 = albedo * albedo * albedo * tmax(0.0f, f30 + f31 * m_cos(phi) * 2.0f);
+  Spec<SP> t4 = vmf_fm<SP>(ui, uo, r, albedo);
+  return kInvPi * (t0 + t1 + t2) + t4;
+}
+
+// DiffuseBSDF::diffuse_layer for variations 1 and 2 (bsdf_various.hxx:36-71)
+template <bool SP>
+DEVN BEval<SP> diffuse_layer_variation(const DeviceScene& sc, const BData& d, V3 local_w_i, V3 local_w_o, const etxb_material& m, Smp& smp) {
+  if (local_w_o.z <= 0.0f) return beval_zero<SP>();
   Spec<SP> diffuse = apply_image<SP>(sc, m.scattering, d.tex, d.wavelength);
   V2 roughness = evaluate_roughness(sc, m, d.tex);
   BEval<SP> e;
   e.eta = 1.0f;
-  e.bsdf = eval_rough_diffuse<SP>(smp, local_w_i, local_w_o, roughness, diffuse);
-  e.func = e.bsdf / local_w_o.z;
+  if (m.diffuse_variation == 1u) {
+    e.bsdf = eval_rough_diffuse<SP>(smp, local_w_i, local_w_o, roughness, diffuse);
+    e.func = e.bsdf / local_w_o.z;
+  } else {
+    e.func = vmf_diffuse_brdf<SP>(local_w_i, local_w_o, roughness, diffuse);
+    e.bsdf = e.func * local_w_o.z;
+  }
   e.pdf = kInvPi * local_w_o.z;
   return e;
 }
@@ -939,7 +1105,8 @@ DEVN BEval<SP> plastic_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, c
   ThinfilmEval<SP> thinfilm = evaluate_thinfilm<SP>(sc, d.wavelength, m.thinfilm, d.tex, smp);
   Spec<SP> fr = fresnel_calculate<SP>(d.wavelength, dot(d.w_i, mh), eta_e, eta_i, thinfilm);
   V3 local_w_o = frame.to_local(w_o);
-  BEval<SP> diff_layer = diffuse_layer<SP>(sc, d, local_w_o, m);
+  V3 local_w_i = frame.to_local(-d.w_i);
+  BEval<SP> diff_layer = diffuse_layer<SP>(sc, d, local_w_i, local_w_o, m, smp);
   Spec<SP> spec_layer = plastic_specular_func<SP>(sc, d, w_o, m, smp);
   float spec_pdf = plastic_specular_pdf<SP>(sc, d, w_o, m, smp);
   BEval<SP> e;
@@ -1250,7 +1417,8 @@ DEVN float principled_pdf(const DeviceScene& sc, const BData& d, V3 w_o, const e
 template <bool SP>
 DEVG_BSDF BSample<SP> bsdf_sample_generic(const DeviceScene& sc, const BData& d, const etxb_material& m, Smp& smp) {
   switch (m.cls) {
-    case ETXB_MAT_DIFFUSE: return rough_diffuse_sample<SP>(sc, d, m, smp);  // diffuse_variation 1 (0 is handled inline by the caller)
+    case ETXB_MAT_DIFFUSE:  // diffuse_variation 1 walks the microsurface, 2 samples the cosine lobe like 0 (which the caller handles inline)
+      return (m.diffuse_variation == 1u) ? rough_diffuse_sample<SP>(sc, d, m, smp) : diffuse_sample<SP>(sc, d, m, smp);
     case ETXB_MAT_TRANSLUCENT: return translucent_sample<SP>(sc, d, m, smp);
     case ETXB_MAT_PLASTIC: return plastic_sample<SP>(sc, d, m, smp);
     case ETXB_MAT_CONDUCTOR: return conductor_sample<SP>(sc, d, m, smp);
@@ -1285,7 +1453,7 @@ DEV BSample<SP> bsdf_sample(const DeviceScene& sc, const BData& d, const etxb_ma
 template <bool SP>
 DEVG_BSDF BEval<SP> bsdf_evaluate_generic(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
   switch (m.cls) {
-    case ETXB_MAT_DIFFUSE: return rough_diffuse_evaluate<SP>(sc, d, w_o, m, smp);
+    case ETXB_MAT_DIFFUSE: return diffuse_evaluate<SP>(sc, d, w_o, m, smp);
     case ETXB_MAT_TRANSLUCENT: return translucent_evaluate<SP>(sc, d, w_o, m);
     case ETXB_MAT_PLASTIC: return plastic_evaluate<SP>(sc, d, w_o, m, smp);
     case ETXB_MAT_CONDUCTOR: return conductor_evaluate<SP>(sc, d, w_o, m, smp);
@@ -1298,7 +1466,7 @@ DEVG_BSDF BEval<SP> bsdf_evaluate_generic(const DeviceScene& sc, const BData& d,
 }
 template <bool SP>
 DEV BEval<SP> bsdf_evaluate(const DeviceScene& sc, const BData& d, V3 w_o, const etxb_material& m, Smp& smp) {
-  if ((m.cls == ETXB_MAT_DIFFUSE) && (m.diffuse_variation == 0u)) return diffuse_evaluate<SP>(sc, d, w_o, m);
+  if ((m.cls == ETXB_MAT_DIFFUSE) && (m.diffuse_variation == 0u)) return diffuse_evaluate<SP>(sc, d, w_o, m, smp);
   return bsdf_evaluate_generic<SP>(sc, d, w_o, m, smp);
 }
 template <bool SP>

@@ -32,6 +32,7 @@ constexpr float kHalfPi = 1.5707963267948966192313216916398f;
 constexpr float kPi = 3.1415926535897932384626433832795f;
 constexpr float kDoublePi = 6.283185307179586476925286766559f;
 constexpr float kInvPi = 0.31830988618379067153776752674503f;
+constexpr float kSqrtPi = 1.7724538509055160272981674833411f;
 constexpr float kEpsilon = 1.192092896e-07f;
 constexpr float kMaxFloat = 3.402823466e+38f;
 constexpr float kMaxHalf = 65504.0f;
@@ -55,6 +56,8 @@ DEVN float m_atan(float x) { return pm::atanf_(x); }
 DEVN float m_atan2(float y, float x) { return pm::atan2f_(y, x); }
 DEVN float m_cosh(float x) { return pm::coshf_(x); }
 DEVN float m_atanh(float x) { return pm::atanhf_(x); }
+DEVN float m_sinh(float x) { return pm::sinhf_(x); }
+DEVN float m_tanh(float x) { return pm::tanhf_(x); }
 #else
 DEV float m_sin(float x) { return sinf(x); }
 DEV float m_cos(float x) { return cosf(x); }
@@ -67,6 +70,8 @@ DEVG_MATH float m_atan(float x) { return atanf(x); }
 DEVG_MATH float m_atan2(float y, float x) { return atan2f(y, x); }
 DEVG_MATH float m_cosh(float x) { return coshf(x); }
 DEVG_MATH float m_atanh(float x) { return atanhf(x); }
+DEVG_MATH float m_sinh(float x) { return sinhf(x); }
+DEVG_MATH float m_tanh(float x) { return tanhf(x); }
 #endif
 
 DEV float sqr(float t) { return t * t; }

@@ -682,9 +682,6 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
     const etxb_material& m = mats[i];
     if (!material_class_supported_host(m.cls)) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: class %u is not supported on the device yet", (unsigned long long)i, m.cls);
     if (m.diffuse_variation > 2u) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu: unknown diffuse_variation %u", (unsigned long long)i, m.diffuse_variation);
-    if (m.diffuse_variation == 2u) return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: diffuse_variation 2 (vMF diffuse) is not supported on the device yet", (unsigned long long)i);
-    if ((m.diffuse_variation == 1u) && (m.cls != ETXB_MAT_DIFFUSE))
-      return fail(ctx, ETXB_ERR_UNSUPPORTED, "material %llu: diffuse_variation 1 under class %u (rough diffuse base layer) is not supported on the device yet", (unsigned long long)i, m.cls);
     if (m.subsurface.cls > 2u) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu: unknown subsurface class %u", (unsigned long long)i, m.subsurface.cls);
     if (m.subsurface.cls != 0) {
       if (s.subsurface_exit_material >= s.materials.count) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "material %llu uses subsurface scattering but scene.subsurface_exit_material is not set", (unsigned long long)i);

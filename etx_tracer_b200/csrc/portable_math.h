@@ -301,6 +301,22 @@ PM_FN float sinhf_(float x) {
   }
   return float(sign_d(d) ? -r : r);
 }
+PM_FN float tanhf_(float x) {
+  double d = double(x);
+  if (is_nan(d)) return x;
+  double a = abs_d(d);
+  double r;
+  if (a < 0.125) {
+    double a2 = a * a;
+    r = a * (1.0 + a2 * (-1.0 / 3.0 + a2 * (2.0 / 15.0 + a2 * (-17.0 / 315.0 + a2 * (62.0 / 2835.0 + a2 * (-1382.0 / 155925.0))))));
+  } else if (a > 20.0) {
+    r = 1.0;
+  } else {
+    double e = exp_d(2.0 * a);
+    r = (e - 1.0) / (e + 1.0);
+  }
+  return float(sign_d(d) ? -r : r);
+}
 PM_FN float atanhf_(float x) {
   double d = double(x);
   if (is_nan(d)) return x;

@@ -673,6 +673,13 @@ MATERIAL_KINDS = {
     "principled": dict(cls=S.MAT_PRINCIPLED, kd=[0.8, 0.5, 0.2], ks=[1.0, 1.0, 1.0], roughness=0.5, metalness=0.4, transmission=0.3),
     "void": dict(cls=S.MAT_VOID),
     "diffuse_rough": dict(kd=[0.8, 0.7, 0.5], roughness=0.6, diffuse_variation=1),  # Heitz rough diffuse: random walk in sample AND evaluate
+    # vMF diffuse fit (diffuse_variation 2): the three branches of its cross section — m > 0.9, 0.25 <= m <= 0.9, m < 0.25 (m = -log(1 - Pr))
+    "diffuse_vmf": dict(kd=[0.8, 0.7, 0.5], roughness=0.62, diffuse_variation=2),
+    "diffuse_vmf_mid": dict(kd=[0.6, 0.7, 0.8], roughness=0.4, diffuse_variation=2),
+    "diffuse_vmf_low": dict(kd=[0.8, 0.8, 0.8], roughness=0.15, diffuse_variation=2),
+    # the diffuse variations as the base layer of PlasticBSDF::evaluate (bsdf_plastic.hxx:136)
+    "plastic_rough_base": dict(cls=S.MAT_PLASTIC, kd=[0.3, 0.6, 0.4], ks=[1.0, 1.0, 1.0], roughness=0.5, int_ior="plastic", diffuse_variation=1),
+    "plastic_vmf_base": dict(cls=S.MAT_PLASTIC, kd=[0.7, 0.4, 0.3], ks=[1.0, 1.0, 1.0], roughness=0.45, int_ior="plastic", diffuse_variation=2),
     # subsurface scattering on top of a diffuse-lobe class (material.hxx:36-51)
     "sss_random_walk": dict(kd=[0.8, 0.6, 0.4], subsurface=dict(cls="random_walk", path="diffuse", distances=[1.0, 0.4, 0.15], scale=0.12)),
     "sss_refracted": dict(cls=S.MAT_PLASTIC, kd=[0.7, 0.8, 0.6], ks=[1.0, 1.0, 1.0], roughness=0.3, int_ior="plastic",
@@ -946,6 +953,89 @@ def media_box(kind="fog", width=32, height=32, samples=16, spectral=False):
     return sd.finalize(samples=samples, spectral=spectral)
 
 
+def fbm_density_fast(n=256, seed=42):
+    """fbm_density for large grids (float32, one z-slab at a time; same recipe, its own lattice order) — BASELINE config 5 uses 256^3."""
+    rng = np.random.default_rng(seed)
+    total = np.zeros((n, n, n), dtype=f32)
+    c = ((np.arange(n, dtype=f32) + f32(0.0)) / f32(n)).astype(f32)
+    amp, freq = f32(1.0), 2
+    while freq <= n:
+        lattice = rng.random((freq + 1, freq + 1, freq + 1), dtype=f32)
+        f = c * f32(freq)
+        i0 = f.astype(np.int64)
+        t = (f - i0).astype(f32)
+        i1 = i0 + 1
+        # separable trilinear interpolation: z, then y, then x
+        a = lattice[i0] * (1 - t)[:, None, None] + lattice[i1] * t[:, None, None]            # (n, F, F)
+        a = a[:, i0, :] * (1 - t)[None, :, None] + a[:, i1, :] * t[None, :, None]          # (n, n, F)
+        a = a[:, :, i0] * (1 - t)[None, None, :] + a[:, :, i1] * t[None, None, :]          # (n, n, n)
+        total += amp * a.astype(f32)
+        amp *= f32(0.5)
+        freq *= 2
+    r2 = (c[:, None, None] - f32(0.5)) ** 2 + (c[None, :, None] - f32(0.5)) ** 2 + (c[None, None, :] - f32(0.5)) ** 2
+    total = np.clip(total * np.clip(1.0 - 2.0 * np.sqrt(r2), 0, 1) - f32(0.15), 0, None).astype(f32)
+    return (total / total.max()).astype(f32)
+
+
+def sss_dragon(width=1024, height=1024, samples=512, spectral=True, target_triangles=871_000, seed=7):
+    """BASELINE config 4: the dragon stand-in — one displaced sphere of ~871 k triangles, `material class plastic` with
+    `subsurface distances 1.0 0.2 0.04 scale 0.1` (random walk, diffuse entry: the loader's defaults, scene_representation.cxx:1972-2007),
+    on a diffuse floor/backdrop, lit by three area emitters."""
+    sd = SceneData()
+    sd.name = f"sss_dragon{target_triangles // 1000}k" + ("/spectral" if spectral else "/rgb")
+    floor = sd.add_material("floor", kd=[0.7, 0.7, 0.7], two_sided=1)
+    skin = sd.add_material("dragon", cls=S.MAT_PLASTIC, kd=[0.8, 0.75, 0.6], ks=[1, 1, 1], roughness=0.3, int_ior="plastic",
+                           subsurface=dict(cls="random_walk", path="diffuse", distances=[1.0, 0.2, 0.04], scale=0.1))
+    lights = [sd.add_material(f"light{k}", kd=[0, 0, 0], emission=spd_rgb_luminance(rgb), two_sided=1)
+              for k, rgb in enumerate(([14.0, 12.0, 10.0], [4.0, 6.0, 10.0], [10.0, 5.0, 3.0]))]
+    # 2*segments*(rings-1) triangles with segments = 2*rings
+    rings = max(4, int(round(math.sqrt(target_triangles / 4.0))))
+    segments = 2 * rings
+    pos, nrm, uv, idx = _sphere_mesh([0.0, 0.75, 0.0], 0.62, segments, rings, bump=0.0)
+    # "dragon" relief: three octaves of low-frequency lobes along the smooth normal (positions only; shading normals stay the sphere's)
+    d = nrm
+    relief = (0.10 * np.sin(5.0 * d[:, 0] + 0.3 * seed) * np.sin(4.0 * d[:, 1] + 1.1) + 0.05 * np.sin(11.0 * d[:, 2] + 0.7 * seed) * np.cos(9.0 * d[:, 0])
+              + 0.02 * np.sin(23.0 * d[:, 1]) * np.sin(19.0 * d[:, 2] + seed))
+    pos = pos + d * (0.62 * relief)[:, None]
+    sd.add_mesh(pos, nrm, idx, skin, uvs=uv)
+    sd.add_quad([-3, 0, 3], [3, 0, 3], [3, 0, -3], [-3, 0, -3], floor, 2)
+    sd.add_quad([-3, 0, -1.6], [3, 0, -1.6], [3, 3, -1.6], [-3, 3, -1.6], floor, 2)
+    sd.add_quad([-0.5, 2.4, -0.5], [0.5, 2.4, -0.5], [0.5, 2.4, 0.5], [-0.5, 2.4, 0.5], lights[0])          # key, overhead (faces down: two-sided)
+    sd.add_quad([-1.9, 0.3, 0.2], [-1.9, 0.3, 1.0], [-1.9, 1.3, 1.0], [-1.9, 1.3, 0.2], lights[1])          # cool fill from the left
+    sd.add_quad([1.7, 0.2, -0.9], [1.7, 0.2, -0.3], [1.7, 1.5, -0.3], [1.7, 1.5, -0.9], lights[2])          # warm rim from behind right
+    sd.set_camera([0.0, 1.0, 3.2], [0.0, 0.75, 0.0], [0.0, 1.0, 0.0], width, height, 40.0, clip_near=0.1, clip_far=100.0)
+    return sd.finalize(samples=samples, spectral=spectral)
+
+
+def cloud_box(width=1024, height=1024, samples=256, spectral=True, grid=256, seed=42):
+    """BASELINE config 5: unit-cube `boundary` mesh holding a heterogeneous cloud (fBm density grid^3 normalised to max 1 like
+    medium_pool.cxx:44-55; scattering : absorption = 0.9 : 0.01; majorant max_sigma = 20, i.e. ~20 tracking steps with 8-tap density
+    gathers per crossing; g = 0.8) under a sun (directional emitter) and a sky environment map, over a diffuse ground plane.
+    The reference's tracker attenuates every segment by the medium's FULL extinction whatever the local density
+    (scene_medium.hxx:306-346), so sigma_t is kept at ~2 per unit length (the cube stays translucent) while max_sigma sets the step rate.
+    Rendered connect-only (`vcm-merging` off = volumetric BDPT); the caller sets that option (workload_options)."""
+    sd = SceneData()
+    sd.name = f"cloud{grid}" + ("/spectral" if spectral else "/rgb")
+    ground = sd.add_material("ground", kd=[0.35, 0.4, 0.3], two_sided=1)
+    k = 2.0 / 0.91
+    density = fbm_density(grid, seed) if grid <= 32 else fbm_density_fast(grid, seed)
+    cloud = sd.add_medium(absorption=(0.01 * k,) * 3, scattering=(0.9 * k,) * 3, g=0.8, density=density,
+                          bounds=([-0.5, 0.6, -0.5], [0.5, 1.6, 0.5]), max_sigma=20.0)
+    b = sd.add_material("cloud", cls=S.MAT_BOUNDARY, int_medium=cloud)
+    sd.add_box([0.0, 1.1, 0.0], (0.5, 0.5, 0.5), 0.0, b)
+    sd.add_quad([-6, 0, 6], [6, 0, 6], [6, 0, -6], [-6, 0, -6], ground, 2)
+    sky = sd.add_image(sky_image(256 if grid > 32 else 64, 128 if grid > 32 else 32, seed=1234), repeat=True, build_table=True)
+    sd.add_environment_emitter(sky, rgb=(1.0, 1.0, 1.0))
+    sd.add_directional_emitter([0.35, 0.8, 0.45], rgb=(6.0, 5.6, 5.0), angular_size_deg=1.0)
+    sd.set_camera([0.0, 1.0, 3.4], [0.0, 1.1, 0.0], [0.0, 1.0, 0.0], width, height, 35.0, clip_near=0.1, clip_far=100.0)
+    return sd.finalize(samples=samples, spectral=spectral)
+
+
+def workload_options(name):
+    """Integrator options a named config runs with beyond the defaults (vcm_shared.cxx:6-28)."""
+    return {"vcm-merging": 0.0} if name == "C5" else {}
+
+
 def config(name, scale=1.0):
     """Named BASELINE.json configs. `scale` < 1 shrinks resolution for CPU-sized tests (geometry unchanged)."""
     def dim(v):
@@ -956,4 +1046,8 @@ def config(name, scale=1.0):
         return cornell_box(dim(1024), dim(1024), samples=256, spectral=True, sphere=True)
     if name == "C3":
         return procedural_room(dim(1920), dim(1080), samples=1024, spectral=True)
+    if name == "C4":
+        return sss_dragon(dim(1024), dim(1024), samples=512, spectral=True)
+    if name == "C5":
+        return cloud_box(dim(1024), dim(1024), samples=256, spectral=True)
     raise KeyError(name)

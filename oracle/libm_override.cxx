@@ -28,6 +28,7 @@ float logf(float x) { return pm::logf_(x); }
 float powf(float x, float y) { return pm::powf_(x, y); }
 float coshf(float x) { return pm::coshf_(x); }
 float sinhf(float x) { return pm::sinhf_(x); }
+float tanhf(float x) { return pm::tanhf_(x); }
 float atanhf(float x) { return pm::atanhf_(x); }
 
 float _Complex csqrtf(float _Complex z) {

@@ -281,6 +281,52 @@ def test_participating_media_are_bit_exact(api, oracle_mod, kind, spectral):
     f.close()
 
 
+def _compare_with_oracle(api, oracle_mod, sd, iterations, opts=None, fast_tolerance=None):
+    o = oracle_mod.Oracle(sd)
+    if opts is not None:
+        o.set_options(opts)
+    o.begin(0)
+    o.run(iterations, threads=1)
+    g = api.GPUVCM(sd, flavor="parity")
+    if opts is not None:
+        g.options[:] = opts
+    g.render(iterations)
+    for bid, dt in ((S.BUF_LIGHT_PATH_COUNT, np.uint32), (S.BUF_LIGHT_SAMPLER, np.uint32), (S.BUF_LV_POS, np.float32), (S.BUF_LV_THROUGHPUT, np.float32),
+                    (S.BUF_LV_MIS, np.float32), (S.BUF_CAMERA_SAMPLER, np.uint32), (S.BUF_CAMERA_GATHERED, np.float32)):
+        a, b = g.buffer(bid, dt), o.buffer(bid, dt)
+        assert a.shape == b.shape, f"buffer {bid}: {a.shape} vs {b.shape}"
+        same = (a.view(np.uint32) == b.view(np.uint32))
+        assert same.all(), f"buffer {bid}: {100.0 * same.mean():.3f}% identical, first mismatch at {int(np.argmin(same))}"
+    assert bit_equal(g.film(S.FILM_CAMERA)[..., :3], o.film(S.FILM_CAMERA)[..., :3])
+    assert rel_l2(g.film(S.FILM_LIGHT)[..., :3], o.film(S.FILM_LIGHT)[..., :3]) < 1e-6
+    g.close()
+    if fast_tolerance is not None:
+        f = api.GPUVCM(sd, flavor="fast")
+        if opts is not None:
+            f.options[:] = opts
+        f.render(iterations)
+        img, ref = f.film(S.FILM_RESULT)[..., :3], o.film(S.FILM_RESULT)[..., :3]
+        assert np.isfinite(img).all() and rel_l2(img, ref) < fast_tolerance
+        f.close()
+
+
+def test_config4_sss_dragon_is_bit_exact(api, oracle_mod):
+    """BASELINE config 4's scene (displaced ~871 k-triangle mesh, plastic + random-walk subsurface, three area emitters) at a small film:
+    trace_material / continuous_trace inside a deep BVH, subsurface exits as light and camera vertices."""
+    sd = scenes.sss_dragon(40, 40)
+    assert sd.triangle_count > 860_000
+    _compare_with_oracle(api, oracle_mod, sd, 1, fast_tolerance=0.3)
+
+
+def test_config5_cloud_is_bit_exact_connect_only(api, oracle_mod):
+    """BASELINE config 5: heterogeneous cloud in a Boundary cube under sun + sky, VCM with merging off (= volumetric BDPT),
+    delta tracking through a 64^3 grid here (256^3 in the bench workload; the tracker is the same)."""
+    sd = scenes.cloud_box(40, 40, grid=64)
+    opts = S.default_vcm_options()
+    opts["options"] = S.VCM_CONNECT_ONLY
+    _compare_with_oracle(api, oracle_mod, sd, 2, opts=opts, fast_tolerance=0.3)
+
+
 @pytest.mark.parametrize("lanes", [2, 3])
 def test_iterations_in_flight_render_the_same_frame(api, lanes):
     """etxb_group: `lanes` contexts render the iteration indices 0..n-1 between them (each index exactly once, whichever lane takes it);
