@@ -80,6 +80,8 @@ struct LaunchParams {
   uint32_t* shadow_count;        // [0] rays reserved this bounce, [1] work cursor of k_shadow_trace
   uint32_t shadow_capacity;
   uint32_t shadow_stage;         // 1: the scene qualifies (DeviceScene::deferred_shadow_rays) and the buffers exist
+  uint32_t connect_deferred;     // 1 (needs shadow_stage): the camera-vertex x light-vertex connections of such a scene run one per thread in
+                                 //    k_camera_connect_deferred — conn_list[slot] names the (path, light vertex) pair that fills shadow slot `slot`
 };
 
 #ifdef ETXB_COUNT_TRAVERSAL
@@ -673,6 +675,19 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
           } else if (p.connect_stage && (ep_mode == kEpSurface)) {
             camera_emit_connections<SP>(p, i, state, connections);
             continue;
+          } else if (deferred && p.connect_deferred) {
+            // one slot per connection of this vertex, in the reference's order (vcm_shared.hxx:765-803); k_camera_connect_deferred
+            // evaluates each pair in its own thread and fills (or voids) the slot — no BSDF of such a scene draws from the sampler
+            if (p.vcm.connect_vertices()) {
+              uint32_t lp_count = p.paths.lv_count[i];
+              uint32_t d2 = state.total_path_depth + 2u;  // target_path_length = depth + k + 2 must lie in [min_path_length, max_path_length]
+              uint32_t k_begin = (sc.min_path_length > d2) ? (sc.min_path_length - d2) : 0u;
+              uint32_t k_end = (sc.max_path_length >= d2) ? umin(lp_count, sc.max_path_length - d2 + 1u) : 0u;
+              for (uint32_t k = k_begin; k < k_end; ++k) p.conn_list[batch.base + batch.count++] = make_uint2(i, k);
+              connections += batch.count;
+            }
+            shadow_span.y = batch.count;
+            continue;
           } else {
             // reference order: serial over the paired path's vertices with the path's own sampler
             c = vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], ep, state, stats, shadow_rays, connections, deferred);
@@ -688,6 +703,10 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
         }
         // reserved slots that were not used (failed connections, or a reservation that ran past the capacity) are marked empty
         for (uint32_t k = batch.base + batch.count; (k < batch.base + reserved) && (k < p.shadow_capacity); ++k) p.shadow_p0[k].w = -1.0f;
+        // slots that are no vertex connection (the emitter segment, unused ones) carry no pair
+        if (p.connect_deferred) {
+          for (uint32_t k = batch.base + (shadow_span.y & 0xffffu); (k < batch.base + reserved) && (k < p.shadow_capacity); ++k) p.conn_list[k].x = kInvalidIndex;
+        }
       }
     }
     if (p.shadow_stage) p.paths.shadow_span[i] = shadow_span;
@@ -785,6 +804,42 @@ __global__ void __launch_bounds__(128) k_camera_connect(LaunchParams p) {
   counter_add(&p.counters->rays_shadow, shadow_rays);
   counter_add(&p.counters->nodes, STATS_NODES);
   counter_add(&p.counters->tris, STATS_TRIS);
+}
+
+// Scenes with deferred shadow rays (no stochastic BSDF, no media): the connections of vcm_connect_to_light_path (vcm_shared.hxx:765-803)
+// one per thread.  Shadow slot `t` of the bounce was reserved by the shade stage; conn_list[t] names its (path, light vertex) pair.  A
+// connection that succeeds writes the slot's segment and unoccluded contribution (k_shadow_trace resolves it, k_camera_continue adds the
+// visible ones in slot order = reference order); one that fails voids the slot.  Same values, same order as the serial loop.
+template <bool SP>
+__global__ void __launch_bounds__(128) k_camera_connect_deferred(LaunchParams p) {
+  const uint32_t total = umin(p.shadow_count[0], p.shadow_capacity);
+  const DeviceScene& sc = p.scene;
+  uint32_t shadow_rays = 0;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    uint2 entry = p.conn_list[t];
+    if (entry.x == kInvalidIndex) continue;
+    uint32_t i = entry.x;
+    PathState<SP> state = load_state<SP>(p.paths, i);
+    float4 hit = p.paths.hit[i];
+    Isect isect = make_intersection(sc, state.ray_d, __float_as_uint(hit.w), hit.x, hit.y, hit.z);
+    LightVertexRec lv = load_light_vertex(p.lv_final + p.lp_offset[i] + entry.y);
+    Endpoint ep{false, &isect, {0.0f, 0.0f, 0.0f}};
+    V3 target_position;
+    Spec<SP> value;
+    if (vcm_connect_to_light_vertex<SP>(sc, p.vcm, state, lv, ep, target_position, value)) {
+      V3 p0 = shading_pos(sc, load_triangle(sc, isect.triangle_index), isect.barycentric, normalize(target_position - isect.pos));
+      V3 c = value.as_v3();
+      p.shadow_p0[t] = make_float4(p0.x, p0.y, p0.z, 0.0f);
+      p.shadow_p1[t] = make_float4(target_position.x, target_position.y, target_position.z, 0.0f);
+      p.shadow_value[t] = make_float4(c.x, c.y, c.z, 0.0f);
+      shadow_rays += 1;
+    } else {
+      p.shadow_p0[t].w = -1.0f;  // not traced; "visible" with a zero contribution
+      p.shadow_value[t] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      p.shadow_result[t] = 0u;
+    }
+  }
+  counter_add(&p.counters->rays_shadow, shadow_rays);
 }
 
 // Lambert surfaces (Diffuse, variation 0: bsdf_various.hxx:36-133) evaluate without touching the sampler and their BSDF value does
@@ -902,9 +957,32 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
   const bool use_mis = p.vcm.enable_mis();
   const bool use_epan = (p.vcm.kernel == 1u);
   const float vc_weight = p.vcm.vc_weight;
+  // the eight cells of a query (vcm_shared.hxx:895-916): lanes 0..7 fetch one range each.  The ranges of the NEXT query are requested
+  // before the current query's candidate sweep starts, so their L2 round trip is off the critical path.
+  auto fetch_cell_ranges = [&](uint32_t s, uint32_t& begin, uint32_t& cnt) {
+    V3 sp = {__shfl_sync(0xffffffffu, qpos.x, s), __shfl_sync(0xffffffffu, qpos.y, s), __shfl_sync(0xffffffffu, qpos.z, s)};
+    begin = 0;
+    cnt = 0;
+    if (lane < 8u) {
+      V3 m = (sp - g.bbox_min) / g.cell_size;
+      V3 mf = vfloor(m);
+      V3 md = m - mf;
+      int32_t acx = static_cast<int32_t>(mf.x), acy = static_cast<int32_t>(mf.y), acz = static_cast<int32_t>(mf.z);
+      int32_t cx = (lane & 1u) ? acx + ((md.x < 0.5f) ? -1 : +1) : acx;
+      int32_t cy = (lane & 2u) ? acy + ((md.y < 0.5f) ? -1 : +1) : acy;
+      int32_t cz = (lane & 4u) ? acz + ((md.z < 0.5f) ? -1 : +1) : acz;
+      uint2 r = __ldg(&g.cell_range[grid_cell_index(g.hash_table_mask, cx, cy, cz)]);
+      begin = r.x;
+      cnt = r.y - r.x;
+    }
+  };
+  uint32_t next_begin = 0, next_cnt = 0;
+  if (pending) fetch_cell_ranges(__ffs(pending) - 1u, next_begin, next_cnt);
   while (pending) {
     uint32_t src = __ffs(pending) - 1u;
     pending &= pending - 1u;
+    uint32_t my_begin = next_begin, my_cnt = next_cnt;
+    if (pending) fetch_cell_ranges(__ffs(pending) - 1u, next_begin, next_cnt);
     V3 bpos = {__shfl_sync(0xffffffffu, qpos.x, src), __shfl_sync(0xffffffffu, qpos.y, src), __shfl_sync(0xffffffffu, qpos.z, src)};
     V3 bnrm = {__shfl_sync(0xffffffffu, qnrm.x, src), __shfl_sync(0xffffffffu, qnrm.y, src), __shfl_sync(0xffffffffu, qnrm.z, src)};
     V3 bfn = {__shfl_sync(0xffffffffu, qfn.x, src), __shfl_sync(0xffffffffu, qfn.y, src), __shfl_sync(0xffffffffu, qfn.z, src)};
@@ -928,20 +1006,7 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
       b_material = __shfl_sync(0xffffffffu, q_material, src);
       b_seed = __shfl_sync(0xffffffffu, q_seed, src);
     }
-    // the eight cells (vcm_shared.hxx:895-916): lanes 0..7 fetch their ranges, then an 8-wide exclusive scan of the counts
-    uint32_t my_begin = 0, my_cnt = 0;
-    if (lane < 8u) {
-      V3 m = (bpos - g.bbox_min) / g.cell_size;
-      V3 mf = vfloor(m);
-      V3 md = m - mf;
-      int32_t acx = static_cast<int32_t>(mf.x), acy = static_cast<int32_t>(mf.y), acz = static_cast<int32_t>(mf.z);
-      int32_t cx = (lane & 1u) ? acx + ((md.x < 0.5f) ? -1 : +1) : acx;
-      int32_t cy = (lane & 2u) ? acy + ((md.y < 0.5f) ? -1 : +1) : acy;
-      int32_t cz = (lane & 4u) ? acz + ((md.z < 0.5f) ? -1 : +1) : acz;
-      uint2 r = __ldg(&g.cell_range[grid_cell_index(g.hash_table_mask, cx, cy, cz)]);
-      my_begin = r.x;
-      my_cnt = r.y - r.x;
-    }
+    // an 8-wide exclusive scan of the eight cells' photon counts
     uint32_t incl = my_cnt;
 #pragma unroll
     for (uint32_t o = 1; o < 8u; o <<= 1) {
@@ -1006,17 +1071,26 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
       }
     };
 
-    for (uint32_t base = 0; base < total; base += 32u) {
-      uint32_t k = base + lane;
-      bool valid = k < total;
+    // candidate k of the concatenated range lives at photon index locate(k)
+    auto locate = [&](uint32_t k) {
       uint32_t c = uint32_t(k >= e1) + uint32_t(k >= e2) + uint32_t(k >= e3) + uint32_t(k >= e4) + uint32_t(k >= e5) + uint32_t(k >= e6) + uint32_t(k >= e7);
       uint32_t cb = __shfl_sync(0xffffffffu, my_begin, c);
       uint32_t ce = __shfl_sync(0xffffffffu, my_excl, c);
-      uint32_t j = cb + (k - ce);
+      return cb + (k - ce);
+    };
+    // software pipeline, distance one: the positions of candidates base+32.. are in flight while those of base.. are tested
+    uint32_t j_next = locate(lane);
+    float4 pd_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (lane < total) pd_next = __ldg(&g.pos_dvcm[j_next]);
+    for (uint32_t base = 0; base < total; base += 32u) {
+      const bool valid = (base + lane) < total;
+      const uint32_t j = j_next;
+      const float4 pd = pd_next;
+      j_next = locate(base + 32u + lane);
+      if ((base + 32u + lane) < total) pd_next = __ldg(&g.pos_dvcm[j_next]);
       bool inside = false;
       float distance_squared = 0.0f, dvcm = 0.0f;
       if (valid) {
-        float4 pd = __ldg(&g.pos_dvcm[j]);
         V3 d = V3{pd.x, pd.y, pd.z} - bpos;
         distance_squared = dot(d, d);
         dvcm = pd.w;

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <string>
@@ -88,6 +89,7 @@ struct etxb_ctx {
   bool spectral = false;
   bool profile = false;
   bool has_stochastic_merge = false;  // some material that can be merged at is not Lambert (needs the serial gather)
+  bool connect_deferred = true;       // per-connection stage for scenes with deferred shadow rays (ETXB_CONNECT_DEFERRED=0: A/B switch, serial loop)
 
   // scene in HBM
   DevBuf<DVertex> vertices;
@@ -256,6 +258,7 @@ LaunchParams make_params(etxb_ctx* ctx) {
   p.shadow_count = ctx->shadow_count.ptr;
   p.shadow_capacity = uint32_t(ctx->shadow_p0.count);
   p.shadow_stage = (ctx->dscene.deferred_shadow_rays && ctx->shadow_p0.count) ? 1u : 0u;
+  p.connect_deferred = (p.shadow_stage && ctx->connect_deferred) ? 1u : 0u;
 #if defined(ETXB_PARITY) && ETXB_PARITY
   p.connect_stage = 0;
 #else
@@ -455,6 +458,12 @@ int run_camera_pass(etxb_ctx* ctx) {
       LaunchTimer t(ctx, K_CAMERA_SHADE);
       k_camera_shade<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur);
     }
+    if (p.connect_deferred && (ctx->options.options & ETXB_VCM_CONNECT_VERTICES)) {
+      // one thread per (camera vertex, light vertex) pair of the bounce, grid-stride over the reserved shadow slots (count on the device)
+      LaunchTimer t(ctx, K_CAMERA_CONNECT);
+      uint32_t blocks = std::min<uint32_t>(148u * 16u, blocks_for(std::min<uint64_t>(uint64_t(active) * 8ull, 0x7fffffffull), 128));
+      k_camera_connect_deferred<SP><<<blocks, 128, 0, ctx->stream>>>(p);
+    }
     if (p.shadow_stage) {
       // persistent warps over the bounce's deferred shadow rays (the number of rays stays on the device)
       LaunchTimer t(ctx, K_SHADOW_TRACE);
@@ -565,6 +574,7 @@ int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
   ctx->device = device;
   ctx->max_light_vertices_cfg = cfg ? cfg->max_light_vertices : 0;
   ctx->profile = cfg ? (cfg->flags & 1u) != 0 : false;
+  if (const char* e = getenv("ETXB_CONNECT_DEFERRED")) ctx->connect_deferred = (e[0] != '0');
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return ETXB_ERR_CUDA;

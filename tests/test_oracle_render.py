@@ -69,3 +69,34 @@ def test_native_oracle_agrees_statistically(oracle_mod):
     a.begin(0), b.begin(0)
     a.run(4, threads=2), b.run(4, threads=2)
     assert rel_l2(b.film(0)[..., :3], a.film(0)[..., :3]) < 0.05
+
+
+def test_baseline_configs_4_and_5_render_on_the_oracle(oracle_mod):
+    """The generators of BASELINE configs 4 (subsurface 'dragon' stand-in) and 5 (heterogeneous cloud, connect-only) produce what SURVEY.md
+    8(d) names, and the reference's CPU VCM renders them (small film; the mesh / grid sizes are reduced only where the CPU suite needs it)."""
+    c4 = scenes.sss_dragon(24, 24, target_triangles=60_000)
+    assert 55_000 < c4.triangle_count < 65_000
+    assert any(int(m["subsurface"]["cls"][0]) == 1 for m in c4.materials)  # random walk
+    o = oracle_mod.Oracle(c4)
+    o.begin(0)
+    o.run(2, threads=4)
+    img = o.film(S.FILM_RESULT)[..., :3]
+    assert np.isfinite(img).all() and img.mean() > 0.01
+    c5 = scenes.cloud_box(24, 24, grid=32)
+    opts = S.default_vcm_options()
+    opts["options"] = S.VCM_CONNECT_ONLY
+    o = oracle_mod.Oracle(c5)
+    o.set_options(opts)
+    o.begin(0)
+    o.run(4, threads=4)
+    img = o.film(S.FILM_RESULT)[..., :3]
+    assert np.isfinite(img).all() and img.mean() > 0.01
+    assert int(o.counters()["merge_queries"][0]) == 0  # merging off = volumetric BDPT
+    # the cloud attenuates what is behind it: the film's centre (through the cube) is darker than its top rows (open sky)
+    assert img[8:16, 8:16].mean() < img[:4].mean()
+
+
+def test_fbm_density_variants_are_normalised():
+    for d in (scenes.fbm_density(16), scenes.fbm_density_fast(64)):
+        assert d.dtype == np.float32 and float(d.max()) == 1.0 and float(d.min()) == 0.0
+        assert 0.02 < float(d.mean()) < 0.3
