@@ -137,6 +137,26 @@ DEVN Spec<SP> trace_transmittance(const DeviceScene& sc, float wavelength, V3 p0
   t_max = sqrtf(t_max);
   direction /= t_max;
   t_max -= fmaxf(kRayEpsilon, t_max * kRayEpsilon);
+#if defined(ETXB_EXP_PLAIN)
+  {
+    struct PlainShadowVisitor {
+      const DeviceScene& sc;
+      Smp& smp;
+      bool occluded;
+      DEV int operator()(uint32_t triangle_index, float u, float v, float) {
+        const etxb_material& mat = sc.materials[load_triangle_material(sc, triangle_index)];
+        if (mat.cls == ETXB_MAT_VOID) return kCandIgnore;
+        if (alpha_test_rejects(sc, mat, triangle_index, u, v, smp)) return kCandIgnore;
+        occluded = true;
+        return kCandTerminate;
+      }
+    } pvis{sc, smp, false};
+    DevNodeLoad pnl{sc.bvh_nodes};
+    DevTriLoad ptl{sc.bvh_tris};
+    traverse(pnl, ptl, p0.x, p0.y, p0.z, direction.x, direction.y, direction.z, kRayEpsilon, t_max, pvis, stats);
+    return Spec<SP>::make(pvis.occluded ? 0.0f : 1.0f);
+  }
+#endif
   Crossing crossings[kCrossingBufferSize + 1u];
   ShadowVisitor vis{sc, smp, crossings, 0u, false};
   DevNodeLoad nl{sc.bvh_nodes};

@@ -574,6 +574,9 @@ DEV MediumSample<SP> vcm_try_sampling_medium(const DeviceScene& sc, PathState<SP
   r.weight = Spec<SP>::make(0.0f);
   r.pos = {0.0f, 0.0f, 0.0f};
   r.sampled_medium_t = 0.0f;
+#if defined(ETXB_EXP_PLAIN)
+  return r;  // experiment: scenes without media / Boundary surfaces / subsurface only (measures what a compile-time specialisation buys)
+#endif
   if (state.medium_index == kInvalidIndex) return r;
   r = sample_medium<SP>(sc, sc.mediums[state.medium_index], state.wavelength, state.throughput, state.sampler, state.ray_o, state.ray_d, max_t);
   state.throughput *= r.weight;
@@ -583,6 +586,9 @@ DEV MediumSample<SP> vcm_try_sampling_medium(const DeviceScene& sc, PathState<SP
 // vcm_handle_boundary_bsdf (vcm_shared.hxx:436-449)
 template <bool SP>
 DEV bool vcm_handle_boundary(const DeviceScene& sc, const Isect& isect, PathState<SP>& state) {
+#if defined(ETXB_EXP_PLAIN)
+  return false;
+#endif
   const etxb_material& mat = sc.materials[isect.material_index];
   if (mat.cls != ETXB_MAT_BOUNDARY) return false;
   TriRec tri = load_triangle(sc, isect.triangle_index);

@@ -71,6 +71,8 @@ struct LaunchParams {
   uint2* conn_list;              // product build: (path id, light-vertex ordinal) of every pending vertex connection of this bounce
   uint32_t* conn_count;
   uint32_t conn_capacity;
+  uint32_t* conn_key;            // per conn_list entry: (camera vertex material << 8) | light vertex material, or null — the host sorts the list by
+                                 // it so that a warp of k_camera_connect evaluates one pair of BSDF classes instead of up to 32
   uint32_t connect_stage;        // 1: vertex connections run in k_camera_connect (product build, scenes with stochastic BSDFs)
   // deferred shadow rays of the camera step (ShadowBatch, dvcm.cuh): segment end points, unoccluded contribution, result (1 = occluded)
   float4* shadow_p0;
@@ -93,6 +95,14 @@ struct LaunchParams {
 #define STATS_NODES 0u
 #define STATS_TRIS 0u
 #endif
+
+DEV bool scene_has_subsurface(const DeviceScene& sc) {
+#if defined(ETXB_EXP_PLAIN)
+  return false;
+#else
+  return sc.has_subsurface != 0u;
+#endif
+}
 
 DEV void counter_add(unsigned long long* dst, uint32_t v) {
   uint32_t total = __reduce_add_sync(__activemask(), v);
@@ -181,9 +191,13 @@ __global__ void __launch_bounds__(128) k_light_begin(LaunchParams p, uint32_t* q
 
 // closest-hit traversal for every queued path (Raytracing::trace, rt.cxx:428): SoA ray in, hit record out,
 // sampler advanced by one draw per candidate
-__global__ void __launch_bounds__(256) k_trace_closest(LaunchParams p, const uint32_t* queue, const uint32_t* queue_count) {
+__global__ void __launch_bounds__(256) k_trace_closest(LaunchParams p, const uint32_t* queue, const uint32_t* queue_count, uint32_t* material_keys, uint32_t key_limit) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= *queue_count) return;
+  if (q >= *queue_count) {
+    // the host sorts `key_limit` (its upper bound of the queue size) slots by material: slots past the device-side count sort last
+    if ((material_keys != nullptr) && (q < key_limit)) material_keys[q] = 0x100u;
+    return;
+  }
   uint32_t i = queue[q];
   float4 o = p.paths.ray_o[i], d = p.paths.ray_d[i];
   uint4 misc = p.paths.misc[i];
@@ -194,6 +208,8 @@ __global__ void __launch_bounds__(256) k_trace_closest(LaunchParams p, const uin
   HitRec h = trace_closest(p.scene, {o.x, o.y, o.z}, {d.x, d.y, d.z}, o.w, d.w, smp, stats);
   p.paths.hit[i] = make_float4(h.u, h.v, h.t, __uint_as_float(h.tri));
   p.paths.misc[i].x = smp.seed;
+  // the bounce kernels' cost is the BSDF class of the surface that was hit: paths are grouped by material before they are shaded
+  if (material_keys != nullptr) material_keys[q] = (h.tri == kInvalidIndex) ? 0xffu : umin(load_triangle_material(p.scene, h.tri), 0xfeu);
   counter_add(&p.counters->rays_closest, 1u);
   counter_add(&p.counters->nodes, STATS_NODES);
   counter_add(&p.counters->tris, STATS_TRIS);
@@ -307,7 +323,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_light_bounce(La
         state.d_vc /= cos_to_prev;
         state.d_vm /= cos_to_prev;
         state.path_distance = 0.0f;
-        ss_path = sc.has_subsurface && (bs.properties & kBsdfDiffuse) && (mat.subsurface.cls != 0u);
+        ss_path = scene_has_subsurface(sc) && (bs.properties & kBsdfDiffuse) && (mat.subsurface.cls != 0u);
         if (ss_path) ss_sampled = ss_gather<SP>(sc, state.wavelength, isect, state.sampler, ssg, stats, shadow_rays);
         if (is_connectible) {
           if (store_light_vertex(p, make_light_vertex<SP>(state, isect, i))) {  // the vertex stays at the entry point (:1204)
@@ -418,14 +434,18 @@ __host__ __device__ inline float ordered_to_float(uint32_t o) {
 
 // bbox[0..2] = min (ordered uint), bbox[3..5] = max
 __global__ void __launch_bounds__(256) k_grid_bbox(const LightVertexRec* pool, uint32_t count, uint32_t* bbox) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  // grid-stride over the pool, then warp -> block -> 6 atomics per block (min / max are order independent: same box as any other order)
+  __shared__ float s_mn[8][3], s_mx[8][3];
   float mn[3] = {kMaxFloat, kMaxFloat, kMaxFloat}, mx[3] = {-kMaxFloat, -kMaxFloat, -kMaxFloat};
-  if (s < count) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < count; s += gridDim.x * blockDim.x) {
     float4 pt = reinterpret_cast<const float4*>(pool + s)[3];
     if (__float_as_uint(pt.w) != kInvalidIndex) {  // medium vertices are never merged (vcm_shared.cxx:70)
-      mn[0] = mx[0] = pt.x;
-      mn[1] = mx[1] = pt.y;
-      mn[2] = mx[2] = pt.z;
+      mn[0] = fminf(mn[0], pt.x);
+      mx[0] = fmaxf(mx[0], pt.x);
+      mn[1] = fminf(mn[1], pt.y);
+      mx[1] = fmaxf(mx[1], pt.y);
+      mn[2] = fminf(mn[2], pt.z);
+      mx[2] = fmaxf(mx[2], pt.z);
     }
   }
 #pragma unroll
@@ -435,12 +455,23 @@ __global__ void __launch_bounds__(256) k_grid_bbox(const LightVertexRec* pool, u
       mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
     }
   }
-  if ((threadIdx.x & 31u) == 0) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      atomicMin(&bbox[k], float_to_ordered(mn[k]));
-      atomicMax(&bbox[3 + k], float_to_ordered(mx[k]));
+      s_mn[warp][k] = mn[k];
+      s_mx[warp][k] = mx[k];
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3u) {
+    float a = s_mn[0][threadIdx.x], b = s_mx[0][threadIdx.x];
+    for (uint32_t w = 1; w < (blockDim.x >> 5); ++w) {
+      a = fminf(a, s_mn[w][threadIdx.x]);
+      b = fmaxf(b, s_mx[w][threadIdx.x]);
+    }
+    atomicMin(&bbox[threadIdx.x], float_to_ordered(a));
+    atomicMax(&bbox[3 + threadIdx.x], float_to_ordered(b));
   }
 }
 
@@ -533,14 +564,14 @@ constexpr uint32_t kBounceSubsurfaceExit = 0x40000000u;
 template <bool SP>
 DEV Isect stage_intersection(const LaunchParams& p, const PathState<SP>& state, uint32_t i, float4 hit) {
   Isect isect = make_intersection(p.scene, state.ray_d, __float_as_uint(hit.w), hit.x, hit.y, hit.z);
-  if (p.scene.has_subsurface && (p.paths.bs_props[i].x & kBounceSubsurfaceExit)) isect.material_index = p.scene.subsurface_exit_material;
+  if (scene_has_subsurface(p.scene) && (p.paths.bs_props[i].x & kBounceSubsurfaceExit)) isect.material_index = p.scene.subsurface_exit_material;
   return isect;
 }
 
 // Scenes with stochastic BSDFs (product build): the camera-vertex x light-vertex connections (vcm_shared.hxx:765-803) become their
 // own wavefront stage, one thread per connection (k_camera_connect); the shade stage only emits the work list.
 template <bool SP>
-DEV void camera_emit_connections(const LaunchParams& p, uint32_t i, PathState<SP>& state, uint32_t& connections) {
+DEV void camera_emit_connections(const LaunchParams& p, uint32_t i, uint32_t camera_material, PathState<SP>& state, uint32_t& connections) {
   const DeviceScene& sc = p.scene;
   if (p.vcm.connect_vertices() == false) return;
   uint32_t lp_count = p.paths.lv_count[i];
@@ -552,6 +583,11 @@ DEV void camera_emit_connections(const LaunchParams& p, uint32_t i, PathState<SP
     uint32_t base = atomicAdd(p.conn_count, cnt);
     if (base + cnt <= p.conn_capacity) {
       for (uint32_t k = 0; k < cnt; ++k) p.conn_list[base + k] = make_uint2(i, k_begin + k);
+      if (p.conn_key != nullptr) {
+        uint32_t cam_mat = umin(camera_material, 0xffu) << 8;
+        const LightVertexRec* lvs = p.lv_final + p.lp_offset[i] + k_begin;
+        for (uint32_t k = 0; k < cnt; ++k) p.conn_key[base + k] = cam_mat | umin(__float_as_uint(__ldg(&lvs[k].nrm_mat.w)), 0xffu);
+      }
     } else {
       *p.overflow = 1u;
     }
@@ -635,7 +671,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
         state.d_vm /= cos_to_prev;
         state.path_distance = 0.0f;
         vcm_handle_direct_hit<SP>(sc, p.vcm, isect, state);
-        ss_path = sc.has_subsurface && (bs.properties & kBsdfDiffuse) && (mat.subsurface.cls != 0u);
+        ss_path = scene_has_subsurface(sc) && (bs.properties & kBsdfDiffuse) && (mat.subsurface.cls != 0u);
         if (ss_path) ss_sampled = ss_gather<SP>(sc, state.wavelength, isect, state.sampler, ssg, stats, shadow_rays);
         if (is_connectible) ep_mode = ss_sampled ? kEpSubsurface : kEpSurface;
       }
@@ -673,7 +709,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
             c = vcm_connect_to_light<SP>(sc, p.vcm, ep, state, stats, shadow_rays, deferred);
             state.sampler.pop_fixed();
           } else if (p.connect_stage && (ep_mode == kEpSurface)) {
-            camera_emit_connections<SP>(p, i, state, connections);
+            camera_emit_connections<SP>(p, i, isect.material_index, state, connections);
             continue;
           } else if (deferred && p.connect_deferred) {
             // one slot per connection of this vertex, in the reference's order (vcm_shared.hxx:765-803); k_camera_connect_deferred
@@ -769,14 +805,14 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
 // vcm_connect_to_light_path (vcm_shared.hxx:673-803).  Each connection draws from its own stream derived from the path's sampler
 // (the reference shares one stream across the serial loop; the parity build keeps that order inside k_camera_shade).
 template <bool SP>
-__global__ void __launch_bounds__(128) k_camera_connect(LaunchParams p) {
+__global__ void __launch_bounds__(128) k_camera_connect(LaunchParams p, const uint2* conn_list) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t shadow_rays = 0;
   STATS_DECL;
   uint32_t total = umin(*p.conn_count, p.conn_capacity);
   if (t < total) {
     const DeviceScene& sc = p.scene;
-    uint2 entry = p.conn_list[t];
+    uint2 entry = conn_list[t];
     uint32_t i = entry.x;
     PathState<SP> state = load_state<SP>(p.paths, i);
     float4 hit = p.paths.hit[i];
@@ -957,32 +993,9 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
   const bool use_mis = p.vcm.enable_mis();
   const bool use_epan = (p.vcm.kernel == 1u);
   const float vc_weight = p.vcm.vc_weight;
-  // the eight cells of a query (vcm_shared.hxx:895-916): lanes 0..7 fetch one range each.  The ranges of the NEXT query are requested
-  // before the current query's candidate sweep starts, so their L2 round trip is off the critical path.
-  auto fetch_cell_ranges = [&](uint32_t s, uint32_t& begin, uint32_t& cnt) {
-    V3 sp = {__shfl_sync(0xffffffffu, qpos.x, s), __shfl_sync(0xffffffffu, qpos.y, s), __shfl_sync(0xffffffffu, qpos.z, s)};
-    begin = 0;
-    cnt = 0;
-    if (lane < 8u) {
-      V3 m = (sp - g.bbox_min) / g.cell_size;
-      V3 mf = vfloor(m);
-      V3 md = m - mf;
-      int32_t acx = static_cast<int32_t>(mf.x), acy = static_cast<int32_t>(mf.y), acz = static_cast<int32_t>(mf.z);
-      int32_t cx = (lane & 1u) ? acx + ((md.x < 0.5f) ? -1 : +1) : acx;
-      int32_t cy = (lane & 2u) ? acy + ((md.y < 0.5f) ? -1 : +1) : acy;
-      int32_t cz = (lane & 4u) ? acz + ((md.z < 0.5f) ? -1 : +1) : acz;
-      uint2 r = __ldg(&g.cell_range[grid_cell_index(g.hash_table_mask, cx, cy, cz)]);
-      begin = r.x;
-      cnt = r.y - r.x;
-    }
-  };
-  uint32_t next_begin = 0, next_cnt = 0;
-  if (pending) fetch_cell_ranges(__ffs(pending) - 1u, next_begin, next_cnt);
   while (pending) {
     uint32_t src = __ffs(pending) - 1u;
     pending &= pending - 1u;
-    uint32_t my_begin = next_begin, my_cnt = next_cnt;
-    if (pending) fetch_cell_ranges(__ffs(pending) - 1u, next_begin, next_cnt);
     V3 bpos = {__shfl_sync(0xffffffffu, qpos.x, src), __shfl_sync(0xffffffffu, qpos.y, src), __shfl_sync(0xffffffffu, qpos.z, src)};
     V3 bnrm = {__shfl_sync(0xffffffffu, qnrm.x, src), __shfl_sync(0xffffffffu, qnrm.y, src), __shfl_sync(0xffffffffu, qnrm.z, src)};
     V3 bfn = {__shfl_sync(0xffffffffu, qfn.x, src), __shfl_sync(0xffffffffu, qfn.y, src), __shfl_sync(0xffffffffu, qfn.z, src)};
@@ -1006,7 +1019,21 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
       b_material = __shfl_sync(0xffffffffu, q_material, src);
       b_seed = __shfl_sync(0xffffffffu, q_seed, src);
     }
-    // an 8-wide exclusive scan of the eight cells' photon counts
+    // the eight cells (vcm_shared.hxx:895-916): lanes 0..7 fetch their ranges, then an 8-wide exclusive scan of the counts
+    // (prefetching the next query's ranges and the next 32 candidate positions was measured: no gain, the sweep is L2-bandwidth bound)
+    uint32_t my_begin = 0, my_cnt = 0;
+    if (lane < 8u) {
+      V3 m = (bpos - g.bbox_min) / g.cell_size;
+      V3 mf = vfloor(m);
+      V3 md = m - mf;
+      int32_t acx = static_cast<int32_t>(mf.x), acy = static_cast<int32_t>(mf.y), acz = static_cast<int32_t>(mf.z);
+      int32_t cx = (lane & 1u) ? acx + ((md.x < 0.5f) ? -1 : +1) : acx;
+      int32_t cy = (lane & 2u) ? acy + ((md.y < 0.5f) ? -1 : +1) : acy;
+      int32_t cz = (lane & 4u) ? acz + ((md.z < 0.5f) ? -1 : +1) : acz;
+      uint2 r = __ldg(&g.cell_range[grid_cell_index(g.hash_table_mask, cx, cy, cz)]);
+      my_begin = r.x;
+      my_cnt = r.y - r.x;
+    }
     uint32_t incl = my_cnt;
 #pragma unroll
     for (uint32_t o = 1; o < 8u; o <<= 1) {
@@ -1071,26 +1098,17 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
       }
     };
 
-    // candidate k of the concatenated range lives at photon index locate(k)
-    auto locate = [&](uint32_t k) {
+    for (uint32_t base = 0; base < total; base += 32u) {
+      uint32_t k = base + lane;
+      bool valid = k < total;
       uint32_t c = uint32_t(k >= e1) + uint32_t(k >= e2) + uint32_t(k >= e3) + uint32_t(k >= e4) + uint32_t(k >= e5) + uint32_t(k >= e6) + uint32_t(k >= e7);
       uint32_t cb = __shfl_sync(0xffffffffu, my_begin, c);
       uint32_t ce = __shfl_sync(0xffffffffu, my_excl, c);
-      return cb + (k - ce);
-    };
-    // software pipeline, distance one: the positions of candidates base+32.. are in flight while those of base.. are tested
-    uint32_t j_next = locate(lane);
-    float4 pd_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    if (lane < total) pd_next = __ldg(&g.pos_dvcm[j_next]);
-    for (uint32_t base = 0; base < total; base += 32u) {
-      const bool valid = (base + lane) < total;
-      const uint32_t j = j_next;
-      const float4 pd = pd_next;
-      j_next = locate(base + 32u + lane);
-      if ((base + 32u + lane) < total) pd_next = __ldg(&g.pos_dvcm[j_next]);
+      uint32_t j = cb + (k - ce);
       bool inside = false;
       float distance_squared = 0.0f, dvcm = 0.0f;
       if (valid) {
+        float4 pd = __ldg(&g.pos_dvcm[j]);
         V3 d = V3{pd.x, pd.y, pd.z} - bpos;
         distance_squared = dot(d, d);
         dvcm = pd.w;
@@ -1144,6 +1162,219 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
   if (merge_queries) {
     float4 mg = p.paths.merged[i];
     p.paths.merged[i] = make_float4(mg.x + my_sum.x, mg.y + my_sum.y, mg.z + my_sum.z, 0.0f);
+  }
+  counter_add(&p.counters->merge_queries, merge_queries);
+  counter_add(&p.counters->merge_candidates, candidates);
+  counter_add(&p.counters->merge_accepts, accepts);
+}
+
+// Generic gather with the evaluations batched ACROSS the queries of a warp.  k_camera_merge_coop<SP, true> evaluates the in-radius photons
+// of one query at a time, 32 per step: a query with 20 of them leaves 12 lanes idle through two stochastic BSDF evaluations.  Here the
+// (query, photon) pairs of all the warp's queries go through one shared list; a step takes 32 pairs whatever query they belong to, each
+// lane fetches ITS query's camera vertex from the owning lane by shuffle, and the contributions meet in per-query shared accumulators.
+// Same pairs, same per-pair streams (path seed x photon index) as the per-query kernel; only the summation order differs.
+template <bool SP>
+__global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_generic_batched(LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys,
+                                                                                           const uint32_t* count_in, uint32_t queries_per_warp) {
+  __shared__ uint32_t s_idx[kMergeWarpsPerBlock][kMergeListSize];
+  __shared__ float s_d2[kMergeWarpsPerBlock][kMergeListSize];
+  __shared__ float s_dvcm[kMergeWarpsPerBlock][kMergeListSize];
+  __shared__ uint32_t s_src[kMergeWarpsPerBlock][kMergeListSize];
+  __shared__ float s_sum[kMergeWarpsPerBlock][32][3];
+  constexpr uint32_t kFull = 0xffffffffu;
+  const DeviceScene& sc = p.scene;
+  const GridData& g = p.grid;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  uint32_t q = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * queries_per_warp + lane;
+  uint32_t merge_queries = 0, candidates = 0, accepts = 0;
+  bool active = (lane < queries_per_warp) && (q < *count_in) && (sorted_keys[q] != 0xffffffffu);
+  uint32_t i = 0;
+  // this lane's query: the camera vertex and what its MIS weight needs
+  V3 qpos = {0, 0, 0}, qnrm = {0, 0, 0}, qtan = {0, 0, 0}, qbtn = {0, 0, 0}, qwi = {0, 0, 0}, qc = {0, 0, 0};
+  V2 qtex = {0, 0};
+  float q_wcam_base = 0.0f, q_dvm = 0.0f, q_wavelength = 0.0f;
+  uint32_t q_depth = 0, q_medium = 0, q_material = 0, q_seed = 0;
+  if (active) {
+    i = sorted_ids[q];
+    float4 hit = p.paths.hit[i];
+    PathState<SP> state = load_state<SP>(p.paths, i);
+    Isect isect = stage_intersection<SP>(p, state, i, hit);
+    active = !merge_is_lambert(sc.materials[isect.material_index]);
+    if (active) {
+      merge_queries = 1;
+      qpos = isect.pos;
+      qnrm = isect.nrm;
+      qtan = isect.tan;
+      qbtn = isect.btn;
+      qwi = isect.w_i;
+      qtex = isect.tex;
+      q_wcam_base = state.d_vcm * p.vcm.vc_weight;
+      q_dvm = state.d_vm;
+      q_depth = state.total_path_depth;
+      qc = (state.throughput / sampling_pdf<SP>(state.wavelength)).as_v3();
+      q_wavelength = state.wavelength;
+      q_medium = state.medium_index;
+      q_material = isect.material_index;
+      q_seed = state.sampler.seed;
+      state.sampler.next();  // the path's own stream moves on by one draw per query
+      p.paths.misc[i].x = state.sampler.seed;
+    }
+  }
+  s_sum[warp][lane][0] = 0.0f;
+  s_sum[warp][lane][1] = 0.0f;
+  s_sum[warp][lane][2] = 0.0f;
+  __syncwarp();
+  uint32_t pending = __ballot_sync(kFull, active);
+  const bool use_mis = p.vcm.enable_mis();
+  const bool use_epan = (p.vcm.kernel == 1u);
+  const float vc_weight = p.vcm.vc_weight;
+  uint32_t n_list = 0;  // warp-uniform fill of the shared pair list
+
+  auto shfl3 = [&](V3 v, uint32_t s) { return V3{__shfl_sync(kFull, v.x, s), __shfl_sync(kFull, v.y, s), __shfl_sync(kFull, v.z, s)}; };
+  auto finish = [&](uint32_t n) {
+    // lanes < n take one (query, photon) pair; every lane takes part in the shuffles that fetch its pair's query
+    uint32_t j = 0, s = 0;
+    float distance_squared = 0.0f, dvcm = 0.0f;
+    if (lane < n) {
+      j = s_idx[warp][lane];
+      distance_squared = s_d2[warp][lane];
+      dvcm = s_dvcm[warp][lane];
+      s = s_src[warp][lane];
+    }
+    BData cam = {};
+    cam.pos = shfl3(qpos, s);
+    cam.nrm = shfl3(qnrm, s);
+    cam.tan = shfl3(qtan, s);
+    cam.btn = shfl3(qbtn, s);
+    cam.w_i = shfl3(qwi, s);
+    cam.tex = {__shfl_sync(kFull, qtex.x, s), __shfl_sync(kFull, qtex.y, s)};
+    cam.wavelength = __shfl_sync(kFull, q_wavelength, s);
+    cam.current_medium = __shfl_sync(kFull, q_medium, s);
+    cam.path_source = kPathCamera;
+    V3 bqc = shfl3(qc, s);
+    float b_wcam_base = __shfl_sync(kFull, q_wcam_base, s);
+    float b_dvm = __shfl_sync(kFull, q_dvm, s);
+    uint32_t b_depth = __shfl_sync(kFull, q_depth, s);
+    uint32_t b_material = __shfl_sync(kFull, q_material, s);
+    uint32_t b_seed = __shfl_sync(kFull, q_seed, s);
+    if (lane < n) {
+      float4 wl = __ldg(&g.win_len[j]);
+      float4 nd = __ldg(&g.nrm_dvm[j]);
+      float4 lt = __ldg(&g.thr_rgb[j]);
+      bool ok = !(__float_as_uint(wl.w) + b_depth + 1 > sc.max_path_length);
+      ok = ok && !(dot(cam.nrm, V3{nd.x, nd.y, nd.z}) <= kEpsilon);
+      if (ok) {
+        Smp lane_smp;
+        lane_smp.seed = b_seed ^ ((j + 1u) * 0x9E3779B1u);
+        lane_smp.fixed_u = lane_smp.fixed_v = lane_smp.fixed_w = 0.0f;
+        lane_smp.next();
+        const etxb_material& mat = sc.materials[b_material];
+        V3 wo = {-wl.x, -wl.y, -wl.z};
+        BEval<SP> e = bsdf_evaluate<SP>(sc, cam, wo, mat, lane_smp);
+        if (e.valid()) {
+          float rev_pdf = bsdf_reverse_pdf<SP>(sc, cam, wo, mat, lane_smp);
+          V3 c_value = spec_to_rgb<SP>(sc, e.func * Spec<SP>::make3(bqc), cam.wavelength);
+          float w_light = dvcm * vc_weight + nd.w * e.pdf;
+          float w_camera = b_wcam_base + b_dvm * rev_pdf;
+          float weight = use_mis ? (1.0f / (1.0f + w_light + w_camera)) : 1.0f;
+          float kernel_weight = use_epan ? fmaxf(2.0f * (1.0f - distance_squared * g.inv_radius_squared), 0.0f) : 1.0f;
+          float kw = kernel_weight * weight;
+          atomicAdd(&s_sum[warp][s][0], c_value.x * lt.x * kw);
+          atomicAdd(&s_sum[warp][s][1], c_value.y * lt.y * kw);
+          atomicAdd(&s_sum[warp][s][2], c_value.z * lt.z * kw);
+          accepts += 1;
+        }
+      }
+    }
+  };
+
+  while (pending) {
+    uint32_t src = __ffs(pending) - 1u;
+    pending &= pending - 1u;
+    V3 bpos = shfl3(qpos, src);
+    // the eight cells (vcm_shared.hxx:895-916): lanes 0..7 fetch their ranges, then an 8-wide exclusive scan of the counts
+    uint32_t my_begin = 0, my_cnt = 0;
+    if (lane < 8u) {
+      V3 m = (bpos - g.bbox_min) / g.cell_size;
+      V3 mf = vfloor(m);
+      V3 md = m - mf;
+      int32_t acx = static_cast<int32_t>(mf.x), acy = static_cast<int32_t>(mf.y), acz = static_cast<int32_t>(mf.z);
+      int32_t cx = (lane & 1u) ? acx + ((md.x < 0.5f) ? -1 : +1) : acx;
+      int32_t cy = (lane & 2u) ? acy + ((md.y < 0.5f) ? -1 : +1) : acy;
+      int32_t cz = (lane & 4u) ? acz + ((md.z < 0.5f) ? -1 : +1) : acz;
+      uint2 r = __ldg(&g.cell_range[grid_cell_index(g.hash_table_mask, cx, cy, cz)]);
+      my_begin = r.x;
+      my_cnt = r.y - r.x;
+    }
+    uint32_t incl = my_cnt;
+#pragma unroll
+    for (uint32_t o = 1; o < 8u; o <<= 1) {
+      uint32_t v = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += v;
+    }
+    uint32_t my_excl = incl - my_cnt;
+    const uint32_t total = __shfl_sync(kFull, incl, 7);
+    uint32_t e1 = __shfl_sync(kFull, my_excl, 1), e2 = __shfl_sync(kFull, my_excl, 2), e3 = __shfl_sync(kFull, my_excl, 3), e4 = __shfl_sync(kFull, my_excl, 4),
+             e5 = __shfl_sync(kFull, my_excl, 5), e6 = __shfl_sync(kFull, my_excl, 6), e7 = __shfl_sync(kFull, my_excl, 7);
+    for (uint32_t base = 0; base < total; base += 32u) {
+      uint32_t k = base + lane;
+      bool valid = k < total;
+      uint32_t c = uint32_t(k >= e1) + uint32_t(k >= e2) + uint32_t(k >= e3) + uint32_t(k >= e4) + uint32_t(k >= e5) + uint32_t(k >= e6) + uint32_t(k >= e7);
+      uint32_t cb = __shfl_sync(kFull, my_begin, c);
+      uint32_t ce = __shfl_sync(kFull, my_excl, c);
+      uint32_t j = cb + (k - ce);
+      bool inside = false;
+      float distance_squared = 0.0f, dvcm = 0.0f;
+      if (valid) {
+        float4 pd = __ldg(&g.pos_dvcm[j]);
+        V3 d = V3{pd.x, pd.y, pd.z} - bpos;
+        distance_squared = dot(d, d);
+        dvcm = pd.w;
+        inside = !(distance_squared > g.radius_squared);
+        candidates += 1;
+      }
+      uint32_t bal = __ballot_sync(kFull, inside);
+      if (inside) {
+        uint32_t slot = n_list + __popc(bal & lane_lt);
+        s_idx[warp][slot] = j;
+        s_d2[warp][slot] = distance_squared;
+        s_dvcm[warp][slot] = dvcm;
+        s_src[warp][slot] = src;
+      }
+      n_list += __popc(bal);
+      __syncwarp();
+      if (n_list >= 32u) {
+        finish(32u);
+        __syncwarp();
+        uint32_t rest = n_list - 32u;  // < 32: move the tail to the front
+        uint32_t tj = 0, ts = 0;
+        float td = 0.0f, tv = 0.0f;
+        if (lane < rest) {
+          tj = s_idx[warp][32u + lane];
+          td = s_d2[warp][32u + lane];
+          tv = s_dvcm[warp][32u + lane];
+          ts = s_src[warp][32u + lane];
+        }
+        __syncwarp();
+        if (lane < rest) {
+          s_idx[warp][lane] = tj;
+          s_d2[warp][lane] = td;
+          s_dvcm[warp][lane] = tv;
+          s_src[warp][lane] = ts;
+        }
+        n_list = rest;
+        __syncwarp();
+      }
+    }
+  }
+  if (n_list) finish(n_list);
+  __syncwarp();
+  if (merge_queries) {
+    V3 l = {s_sum[warp][lane][0], s_sum[warp][lane][1], s_sum[warp][lane][2]};
+    if (SP) l *= V3{0.817660332f, 1.05418909f, 1.09945524f};  // kRGBLuminanceScale (:876-878)
+    float4 mg = p.paths.merged[i];
+    p.paths.merged[i] = make_float4(mg.x + l.x, mg.y + l.y, mg.z + l.z, 0.0f);
   }
   counter_add(&p.counters->merge_queries, merge_queries);
   counter_add(&p.counters->merge_candidates, candidates);

@@ -46,6 +46,7 @@ enum KernelId : uint32_t {
   K_CAMERA_SHADE,
   K_CAMERA_CONNECT,
   K_SHADOW_TRACE,
+  K_QUEUE_SORT,
   K_CAMERA_MERGE_SORT,
   K_CAMERA_MERGE,
   K_CAMERA_MERGE_SERIAL,
@@ -54,7 +55,7 @@ enum KernelId : uint32_t {
   K_COUNT
 };
 const char* kKernelNames[K_COUNT] = {"light_begin", "trace_closest(light)", "light_bounce", "lv_scan", "lv_reorder", "grid_bbox", "grid_keys", "grid_sort", "grid_build",
-  "camera_begin", "trace_closest(camera)", "camera_shade", "camera_connect", "shadow_trace", "camera_merge_sort", "camera_merge", "camera_merge_generic", "camera_continue", "film_commit_light"};
+  "camera_begin", "trace_closest(camera)", "camera_shade", "camera_connect", "shadow_trace", "queue_sort", "camera_merge_sort", "camera_merge", "camera_merge_generic", "camera_continue", "film_commit_light"};
 
 template <class T>
 struct DevBuf {
@@ -89,6 +90,8 @@ struct etxb_ctx {
   bool spectral = false;
   bool profile = false;
   bool has_stochastic_merge = false;  // some material that can be merged at is not Lambert (needs the serial gather)
+  bool merge_batched = true;          // generic photon gather batches its BSDF evaluations across the queries of a warp (ETXB_MERGE_BATCHED=0: per query)
+  bool sort_by_material = true;       // group path queues and the connection list by material where BSDFs are costly (ETXB_SORT_MATERIAL=0: A/B switch)
   bool connect_deferred = true;       // per-connection stage for scenes with deferred shadow rays (ETXB_CONNECT_DEFERRED=0: A/B switch, serial loop)
 
   // scene in HBM
@@ -118,6 +121,8 @@ struct etxb_ctx {
   DevBuf<uint4> misc;
   DevBuf<uint2> bs_props;
   DevBuf<float> wavelength;
+  DevBuf<uint32_t> queue_sorted, queue_keys, queue_keys_sorted;  // path queue grouped by hit material (scenes with stochastic BSDFs)
+  DevBuf<uint2> conn_list_sorted;
   DevBuf<uint32_t> lv_count, lp_offset, queue_a, queue_b, queue_counts, sampler_end_light, sampler_end_camera, merge_key, conn_seed, conn_count;
   DevBuf<uint2> conn_list, shadow_span;
   DevBuf<float4> shadow_p0, shadow_p1, shadow_value;
@@ -250,6 +255,7 @@ LaunchParams make_params(etxb_ctx* ctx) {
   p.conn_list = ctx->conn_list.ptr;
   p.conn_count = ctx->conn_count.ptr;
   p.conn_capacity = ctx->lv_capacity;
+  p.conn_key = (ctx->sort_by_material && ctx->has_stochastic_merge && ctx->conn_list_sorted.count) ? ctx->keys_in.ptr : nullptr;  // keys_in / vals_in are free after the grid build
   p.paths.shadow_span = ctx->shadow_span.ptr;
   p.shadow_p0 = ctx->shadow_p0.ptr;
   p.shadow_p1 = ctx->shadow_p1.ptr;
@@ -308,6 +314,20 @@ int next_queue_size(etxb_ctx* ctx, const uint32_t* dptr, uint32_t& active, uint3
   return read_u32(ctx, dptr, active);
 }
 
+// Scenes with stochastic BSDFs: the bounce kernels spend their time in the BSDF class of the surface that was hit, and a warp that holds
+// several classes runs them one after the other.  k_trace_closest leaves one key per queue slot (material index; 0xff = miss; 0x100 = slot
+// past the device-side count); a stable 9-bit radix sort groups the queue, slots past the count stay at the end.  Returns the queue the
+// rest of the bounce must use.  Short queues (the tail of a pass) are latency bound and skip it.
+constexpr uint32_t kSortQueueMin = 1024u;
+inline bool sorts_queue(const etxb_ctx* ctx, uint32_t active) { return ctx->sort_by_material && ctx->has_stochastic_merge && (active >= kSortQueueMin) && ctx->queue_sorted.count; }
+int sort_queue_by_material(etxb_ctx* ctx, const uint32_t* queue, uint32_t active, const uint32_t** sorted) {
+  size_t temp_bytes = ctx->cub_temp.bytes();
+  CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->queue_keys.ptr, ctx->queue_keys_sorted.ptr, queue, ctx->queue_sorted.ptr, int(active), 0, 9,
+                 ctx->stream));
+  *sorted = ctx->queue_sorted.ptr;
+  return ETXB_OK;
+}
+
 template <bool SP>
 int run_light_pass(etxb_ctx* ctx) {
   LaunchParams p = make_params(ctx);
@@ -324,14 +344,20 @@ int run_light_pass(etxb_ctx* ctx) {
   if (int rc = read_u32(ctx, counts + 0, active)) return rc;
   uint32_t cur = 0, unsynced = 0;
   while (active > 0) {
+    const bool sorted = sorts_queue(ctx, active);
+    const uint32_t* q = qin;
     {
       LaunchTimer t(ctx, K_TRACE_LIGHT);
-      k_trace_closest<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, qin, counts + cur);
+      k_trace_closest<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, qin, counts + cur, sorted ? ctx->queue_keys.ptr : nullptr, active);
+    }
+    if (sorted) {
+      LaunchTimer t(ctx, K_QUEUE_SORT);
+      if (int rc = sort_queue_by_material(ctx, qin, active, &q)) return rc;
     }
     CUDA_OK(ctx, cudaMemsetAsync(counts + (cur ^ 1u), 0, 4, ctx->stream));
     {
       LaunchTimer t(ctx, K_LIGHT_BOUNCE);
-      k_light_bounce<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur, qout, counts + (cur ^ 1u));
+      k_light_bounce<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, q, counts + cur, qout, counts + (cur ^ 1u));
     }
     cur ^= 1u;
     std::swap(qin, qout);
@@ -387,7 +413,7 @@ int run_grid_build(etxb_ctx* ctx, const LightVertexRec* records, uint32_t count)
   CUDA_OK(ctx, cudaMemcpyAsync(ctx->grid_bbox.ptr, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
   {
     LaunchTimer t(ctx, K_GRID_BBOX);
-    k_grid_bbox<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(records, count, ctx->grid_bbox.ptr);
+    k_grid_bbox<<<std::min<uint32_t>(blocks_for(count, 256), 148u * 8u), 256, 0, ctx->stream>>>(records, count, ctx->grid_bbox.ptr);
   }
   uint32_t table_size = next_pow2(count);
   uint32_t mask = table_size - 1u;
@@ -447,16 +473,22 @@ int run_camera_pass(etxb_ctx* ctx) {
   uint32_t cur = 0, unsynced = 0;
   const bool merging = (ctx->options.options & ETXB_VCM_ENABLE_MERGING) && (ctx->options.options & ETXB_VCM_MERGE_VERTICES);
   while (active > 0) {
+    const bool sorted = sorts_queue(ctx, active);
+    const uint32_t* q = qin;  // the queue every stage of this bounce reads
     {
       LaunchTimer t(ctx, K_TRACE_CAMERA);
-      k_trace_closest<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, qin, counts + cur);
+      k_trace_closest<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, qin, counts + cur, sorted ? ctx->queue_keys.ptr : nullptr, active);
+    }
+    if (sorted) {
+      LaunchTimer t(ctx, K_QUEUE_SORT);
+      if (int rc = sort_queue_by_material(ctx, qin, active, &q)) return rc;
     }
     CUDA_OK(ctx, cudaMemsetAsync(counts + (cur ^ 1u), 0, 4, ctx->stream));
     if (p.connect_stage) CUDA_OK(ctx, cudaMemsetAsync(ctx->conn_count.ptr, 0, 4, ctx->stream));
     if (p.shadow_stage) CUDA_OK(ctx, cudaMemsetAsync(ctx->shadow_count.ptr, 0, 8, ctx->stream));
     {
       LaunchTimer t(ctx, K_CAMERA_SHADE);
-      k_camera_shade<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur);
+      k_camera_shade<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, q, counts + cur);
     }
     if (p.connect_deferred && (ctx->options.options & ETXB_VCM_CONNECT_VERTICES)) {
       // one thread per (camera vertex, light vertex) pair of the bounce, grid-stride over the reserved shadow slots (count on the device)
@@ -475,25 +507,34 @@ int run_camera_pass(etxb_ctx* ctx) {
       if (int rc = read_u32(ctx, ctx->conn_count.ptr, pending)) return rc;
       pending = std::min(pending, ctx->lv_capacity);
       if (pending) {
+        const uint2* list = ctx->conn_list.ptr;
+        if (p.conn_key && (pending >= kSortQueueMin)) {
+          // connections grouped by (camera vertex material, light vertex material): one pair of BSDF classes per warp
+          LaunchTimer t(ctx, K_QUEUE_SORT);
+          size_t temp_bytes = ctx->cub_temp.bytes();
+          CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->keys_in.ptr, ctx->vals_in.ptr, reinterpret_cast<const unsigned long long*>(ctx->conn_list.ptr),
+                         reinterpret_cast<unsigned long long*>(ctx->conn_list_sorted.ptr), int(pending), 0, 16, ctx->stream));
+          list = ctx->conn_list_sorted.ptr;
+        }
         LaunchTimer t(ctx, K_CAMERA_CONNECT);
-        k_camera_connect<SP><<<blocks_for(pending, 128), 128, 0, ctx->stream>>>(p);
+        k_camera_connect<SP><<<blocks_for(pending, 128), 128, 0, ctx->stream>>>(p, list);
       }
     }
 #if defined(ETXB_PARITY) && ETXB_PARITY
     if (merging) {
       LaunchTimer t(ctx, K_CAMERA_MERGE_SERIAL);
-      k_camera_merge_serial<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur);
+      k_camera_merge_serial<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, q, counts + cur);
     }
 #else
     if (merging && ctx->grid.photon_count) {
-      const uint32_t* ids = qin;
+      const uint32_t* ids = q;
       const uint32_t* keys = ctx->merge_key.ptr;
       if (active >= kMergeSortMinQueries) {
         // queries sorted by the Morton code of their base cell: neighbours in the queue read the same photon cells.  A short queue
         // (the tail of the pass) is latency bound, not bandwidth bound: it goes in queue order and saves the sort launches.
         LaunchTimer t(ctx, K_CAMERA_MERGE_SORT);
         size_t temp_bytes = ctx->cub_temp.bytes();
-        CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->merge_key.ptr, ctx->keys_out.ptr, qin, ctx->vals_out.ptr, int(active), 0, 32,
+        CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->merge_key.ptr, ctx->keys_out.ptr, q, ctx->vals_out.ptr, int(active), 0, 32,
                        ctx->stream));
         ids = ctx->vals_out.ptr;
         keys = ctx->keys_out.ptr;
@@ -508,13 +549,17 @@ int run_camera_pass(etxb_ctx* ctx) {
       }
       if (ctx->has_stochastic_merge) {
         LaunchTimer t(ctx, K_CAMERA_MERGE_SERIAL);
-        k_camera_merge_coop<SP, true><<<merge_blocks, kMergeWarpsPerBlock * 32, 0, ctx->stream>>>(p, ids, keys, counts + cur, qpw);
+        if (ctx->merge_batched) {
+          k_camera_merge_generic_batched<SP><<<merge_blocks, kMergeWarpsPerBlock * 32, 0, ctx->stream>>>(p, ids, keys, counts + cur, qpw);
+        } else {
+          k_camera_merge_coop<SP, true><<<merge_blocks, kMergeWarpsPerBlock * 32, 0, ctx->stream>>>(p, ids, keys, counts + cur, qpw);
+        }
       }
     }
 #endif
     {
       LaunchTimer t(ctx, K_CAMERA_CONTINUE);
-      k_camera_continue<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, qin, counts + cur, qout, counts + (cur ^ 1u));
+      k_camera_continue<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, q, counts + cur, qout, counts + (cur ^ 1u));
     }
     cur ^= 1u;
     std::swap(qin, qout);
@@ -575,6 +620,8 @@ int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
   ctx->max_light_vertices_cfg = cfg ? cfg->max_light_vertices : 0;
   ctx->profile = cfg ? (cfg->flags & 1u) != 0 : false;
   if (const char* e = getenv("ETXB_CONNECT_DEFERRED")) ctx->connect_deferred = (e[0] != '0');
+  if (const char* e = getenv("ETXB_SORT_MATERIAL")) ctx->sort_by_material = (e[0] != '0');
+  if (const char* e = getenv("ETXB_MERGE_BATCHED")) ctx->merge_batched = (e[0] != '0');
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return ETXB_ERR_CUDA;
@@ -623,6 +670,10 @@ void etxb_destroy(etxb_ctx* ctx) {
   ctx->lv_final.release();
   ctx->cell_range.release();
   ctx->conn_list.release();
+  ctx->conn_list_sorted.release();
+  ctx->queue_sorted.release();
+  ctx->queue_keys.release();
+  ctx->queue_keys_sorted.release();
   ctx->shadow_span.release();
   ctx->shadow_p0.release();
   ctx->shadow_p1.release();
@@ -925,6 +976,17 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   CUDA_OK(ctx, ctx->lv_tmp.alloc(cap));
   CUDA_OK(ctx, ctx->lv_final.alloc(cap));
   CUDA_OK(ctx, ctx->conn_list.alloc(cap));
+  if (ctx->has_stochastic_merge && ctx->sort_by_material) {
+    CUDA_OK(ctx, ctx->conn_list_sorted.alloc(cap));
+    CUDA_OK(ctx, ctx->queue_sorted.alloc(n));
+    CUDA_OK(ctx, ctx->queue_keys.alloc(n));
+    CUDA_OK(ctx, ctx->queue_keys_sorted.alloc(n));
+  } else {
+    ctx->conn_list_sorted.release();
+    ctx->queue_sorted.release();
+    ctx->queue_keys.release();
+    ctx->queue_keys_sorted.release();
+  }
   if (ctx->dscene.deferred_shadow_rays) {
     CUDA_OK(ctx, ctx->shadow_span.alloc(n));
     CUDA_OK(ctx, ctx->shadow_p0.alloc(cap));

@@ -19,7 +19,7 @@ if [ -f etx_tracer_b200/exp_e13.so ]; then
     ETXB_CONNECT_DEFERRED=0 ETXB_LIB_FAST=$PWD/etx_tracer_b200/exp_e13.so timeout 200 python bench.py --steps 12 --warmup 3 --lanes $lanes --no-cpu-baseline > gpurun_out/${tag}_ab_e1_l${lanes}.json 2>/dev/null
     ETXB_LIB_FAST=$PWD/etx_tracer_b200/exp_e13.so timeout 200 python bench.py --steps 12 --warmup 3 --lanes $lanes --no-cpu-baseline > gpurun_out/${tag}_ab_e13_l${lanes}.json 2>/dev/null
   done
-  for v in mb2 mb3; do
+  for v in mb2 mb3 plain; do
     if [ -f etx_tracer_b200/exp_e13_$v.so ]; then
       ETXB_LIB_FAST=$PWD/etx_tracer_b200/exp_e13_$v.so timeout 200 python bench.py --steps 12 --warmup 3 --lanes 1 --no-cpu-baseline > gpurun_out/${tag}_ab_e13_${v}_l1.json 2>/dev/null
       ETXB_LIB_FAST=$PWD/etx_tracer_b200/exp_e13_$v.so timeout 200 python bench.py --steps 12 --warmup 3 --lanes 4 --no-cpu-baseline > gpurun_out/${tag}_ab_e13_${v}_l4.json 2>/dev/null
