@@ -114,16 +114,27 @@ def measured_peaks():
 
 
 def algorithmic_bytes(counters, n_pixels, steps):
-    """SURVEY.md §8(d) event-counter formula, BVH node/triangle traffic excluded (counted only in ETXB_COUNT_TRAVERSAL builds)."""
+    """device event counters x fixed byte costs (reference struct sizes), BVH node/triangle traffic excluded (those
+    counters exist only in ETXB_COUNT_TRAVERSAL builds).  Returns (whole-step bytes, {kernel name: the bytes of ITS units})."""
     c = counters
-    bounces = c["bounces_light"] + c["bounces_camera"]
-    rays = c["rays_closest"] + c["rays_shadow"]
-    total = (352 * bounces + 48 * rays + 404 * bounces + 112 * c["light_vertices"] + 20 * n_pixels * steps + (112 + 404) * c["connections"]
-             + 128 * c["merge_queries"] + 12 * c["merge_candidates"] + 48 * c["merge_accepts"] + (2 * 112 + 60 + 8) * c["light_vertices"]
-             + 24 * c["splats"] + 104 * n_pixels * steps)
-    camera_bounce = (352 * c["bounces_camera"] + 404 * c["bounces_camera"] + (112 + 404) * c["connections"] + 128 * c["merge_queries"] + 12 * c["merge_candidates"]
-                     + 48 * c["merge_accepts"] + 104 * n_pixels * steps)
-    return total, camera_bounce
+    bl, bc, lv = c["bounces_light"], c["bounces_camera"], c["light_vertices"]
+    merge = 128 * c["merge_queries"] + 12 * c["merge_candidates"] + 48 * c["merge_accepts"]
+    per_kernel = {
+        "trace_closest(light)": 48 * bl,                       # ray in (32 B) + hit record out (16 B)
+        "trace_closest(camera)": 48 * bc,
+        "light_bounce": (352 + 404) * bl + 112 * lv + 24 * c["splats"] + 48 * lv + 20 * n_pixels * steps,  # state RMW + hit geometry/material + vertex store + splat + its shadow ray
+        "camera_shade": (352 + 404) * bc,                      # state RMW + hit geometry/material (connections and shadow rays are their own stages)
+        "camera_connect": (112 + 404) * c["connections"],      # light vertex + its geometry/material per vertex connection
+        "shadow_trace": 48 * max(c["rays_shadow"] - lv, 0),    # camera-side segments
+        "camera_merge": merge,
+        "camera_merge_generic": merge,
+        "camera_continue": 352 * bc + 104 * n_pixels * steps,  # state RMW + film accumulate
+        "lv_reorder": 2 * 112 * lv,
+        "grid_build": (60 + 8) * lv,
+    }
+    total = (per_kernel["trace_closest(light)"] + per_kernel["trace_closest(camera)"] + per_kernel["light_bounce"] + per_kernel["camera_shade"] + per_kernel["camera_connect"]
+             + per_kernel["shadow_trace"] + merge + per_kernel["camera_continue"] + per_kernel["lv_reorder"] + per_kernel["grid_build"])
+    return total, per_kernel
 
 
 def cpu_baseline_run(sd_factory, budget_s, threads, opts=None):
@@ -361,13 +372,32 @@ def main():
     if rank == 0:
         peaks = measured_peaks()
         peak = peaks["hbm_gbs"] if peaks else 6650.0
-        total_bytes, cb_bytes = algorithmic_bytes(counters, n_pixels, args.steps)
+        total_bytes, _ = algorithmic_bytes(counters, n_pixels, args.steps)
+        # per-kernel numbers come from a pass of their own: ONE iteration at a time on one context, so that the CUDA events around a launch
+        # bracket that kernel alone (with several iterations in flight the streams overlap and every bracket also holds other lanes' work)
+        kt_steps = max(2, min(args.steps, 6))
+        single = GPUVCM(sd, flavor="fast", device=local_rank, profile=True)
+        single.options[:] = workload_vcm_options(args)
+        single.run(0)
+        for _ in range(2):
+            single.iterate()
+        single._check(single.lib.etxb_wait(single.h))
+        kc0, kk0 = single.counters(), single.kernel_times()
+        for _ in range(kt_steps):
+            single.iterate()
+        single._check(single.lib.etxb_wait(single.h))
+        kc1, kk1 = single.counters(), single.kernel_times()
+        single.close()
+        kcounters = {k: kc1[k] - kc0[k] for k in kc1}
+        ktimes = {k: (kk1[k][0] - kk0[k][0], kk1[k][1] - kk0[k][1]) for k in kk1}
+        _, kbytes = algorithmic_bytes(kcounters, n_pixels, kt_steps)
+        if ktimes.get("camera_merge", (0, 0))[0] and ktimes.get("camera_merge_generic", (0, 0))[0]:
+            # two gather kernels share the merge counters: split the bytes by their time
+            tm, tg = ktimes["camera_merge"][0], ktimes["camera_merge_generic"][0]
+            kbytes["camera_merge"], kbytes["camera_merge_generic"] = kbytes["camera_merge"] * tm / (tm + tg), kbytes["camera_merge_generic"] * tg / (tm + tg)
         dominant = max(ktimes, key=lambda k: ktimes[k][0])
         dom_ms, dom_launches = ktimes[dominant]
-        if dominant == "camera_bounce":
-            dom_bytes = cb_bytes
-        else:
-            dom_bytes = total_bytes * (dom_ms / max(sum(v[0] for v in ktimes.values()), 1e-9))
+        dom_bytes = kbytes.get(dominant, 0.0)
         achieved = dom_bytes / max(dom_ms * 1e-3, 1e-12) / 1e9
         traffic = None
         prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -376,13 +406,18 @@ def main():
                 traffic = json.load(open(prof)).get(dominant)
             except Exception:
                 traffic = None
+        step_ms = sum(v[0] for v in ktimes.values())
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s",
                     "bytes_per_launch": dom_bytes / max(dom_launches, 1), "launches": dom_launches, "avg_launch_ms": dom_ms / max(dom_launches, 1),
+                    "kernel_share_of_step": dom_ms / max(step_ms, 1e-9),
                     "step_algorithmic_GBps": total_bytes / elapsed / 1e9,
-                    "kernel_share_ms": {k: round(v[0], 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0]) if v[1]},
-                    "note": "algorithmic bytes from device event counters x SURVEY.md 8(d) byte costs, BVH node/triangle traffic excluded; the dominant kernel is "
-                            "FP32/latency bound (photon merge: ~900 candidate distance tests + ~100 BSDF evaluations per query), not HBM bound"}
+                    "timing_pass": f"{kt_steps} iterations, one at a time on one context (events bracket single kernels); the headline value uses {lanes} iterations in flight",
+                    "kernel_ms_per_iteration": {k: round(v[0] / kt_steps, 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0]) if v[1]},
+                    "kernel_GBps": {k: round(kbytes[k] / max(ktimes[k][0] * 1e-3, 1e-12) / 1e9, 1) for k in kbytes if ktimes.get(k, (0, 0))[0] > 0},
+                    "note": "algorithmic bytes = device event counters x SURVEY.md 8(d) byte costs of the units THAT kernel processes, BVH node/triangle traffic excluded; "
+                            "`traffic` = ncu dram read+write of one head-of-pass launch of the kernel (profiles/ncu_traffic.json).  The photon gather is served from L2 "
+                            "(82 % hit rate) and the bounce kernels are latency / FP32 bound, so these fractions of the HBM copy peak are not DRAM utilisation"}
         cpu = None
         if not args.no_cpu_baseline:
             from etx_tracer_b200 import scenes

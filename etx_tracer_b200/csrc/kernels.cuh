@@ -15,6 +15,9 @@
 #ifndef ETXB_BOUNCE_MIN_BLOCKS
 #define ETXB_BOUNCE_MIN_BLOCKS 1
 #endif
+#ifndef ETXB_CONNECT_MIN_BLOCKS
+#define ETXB_CONNECT_MIN_BLOCKS 1
+#endif
 
 namespace etxb {
 
@@ -805,7 +808,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
 // vcm_connect_to_light_path (vcm_shared.hxx:673-803).  Each connection draws from its own stream derived from the path's sampler
 // (the reference shares one stream across the serial loop; the parity build keeps that order inside k_camera_shade).
 template <bool SP>
-__global__ void __launch_bounds__(128) k_camera_connect(LaunchParams p, const uint2* conn_list) {
+__global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect(LaunchParams p, const uint2* conn_list) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t shadow_rays = 0;
   STATS_DECL;
@@ -847,7 +850,7 @@ __global__ void __launch_bounds__(128) k_camera_connect(LaunchParams p, const ui
 // connection that succeeds writes the slot's segment and unoccluded contribution (k_shadow_trace resolves it, k_camera_continue adds the
 // visible ones in slot order = reference order); one that fails voids the slot.  Same values, same order as the serial loop.
 template <bool SP>
-__global__ void __launch_bounds__(128) k_camera_connect_deferred(LaunchParams p) {
+__global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect_deferred(LaunchParams p) {
   const uint32_t total = umin(p.shadow_count[0], p.shadow_capacity);
   const DeviceScene& sc = p.scene;
   uint32_t shadow_rays = 0;

@@ -92,6 +92,27 @@ def test_iteration_is_bit_exact_against_golden_render(api, name, kwargs):
     g.close()
 
 
+@pytest.mark.parametrize("name", ["oracle_c3_24.npz", "oracle_c4_24.npz", "oracle_c5_24.npz", "oracle_vmf_24.npz"])
+def test_configs_3_to_5_are_bit_exact_against_golden_renders(api, name):
+    """Committed oracle renders of BASELINE configs 3-5 (full geometry, small film) and of the vMF diffuse box: the fixtures travel to the
+    GPU box, the reference does not."""
+    import golden_scenes
+    factory, iters, opts = golden_scenes.SCENES[name]
+    ref = golden(name)
+    g = api.GPUVCM(factory(), flavor="parity")
+    if opts:
+        g.options[:] = opts()
+    st = g.render(iters)
+    assert st["overflow"] == 0 and st["completed_iterations"] == int(ref["iterations"][0]) == iters
+    assert bit_equal(g.buffer(S.BUF_LIGHT_SAMPLER, np.uint32), ref["light_sampler"])
+    assert bit_equal(g.buffer(S.BUF_LIGHT_PATH_COUNT, np.uint32), ref["light_path_count"])
+    assert bit_equal(g.buffer(S.BUF_LV_POS, np.float32), ref["lv_pos"])
+    assert bit_equal(g.buffer(S.BUF_CAMERA_SAMPLER, np.uint32), ref["camera_sampler"])
+    assert bit_equal(g.film(S.FILM_CAMERA)[..., :3], ref["film_camera"][..., :3])
+    assert rel_l2(g.film(S.FILM_LIGHT)[..., :3], ref["film_light"][..., :3]) < 1e-6
+    g.close()
+
+
 @pytest.mark.parametrize("kwargs,options", [
     (C1, None), (C2, None),
     (C1, dict(options=S.VCM_CONNECT_ONLY)),                                  # "volumetric BDPT" = VCM without merging (BASELINE config 5)

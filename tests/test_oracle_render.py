@@ -26,6 +26,26 @@ def test_oracle_render_is_pinned(oracle_mod, name, kwargs):
     assert np.isfinite(img).all() and img.min() >= 0.0 and 0.05 < img.mean() < 1.0
 
 
+@pytest.mark.parametrize("name", ["oracle_c3_24.npz", "oracle_c4_24.npz", "oracle_c5_24.npz", "oracle_vmf_24.npz"])
+def test_oracle_renders_of_configs_3_to_5_are_pinned(oracle_mod, name):
+    """The oracle (reference headers compiled in place) reproduces its committed renders of BASELINE configs 3-5 and the vMF diffuse box."""
+    import golden_scenes
+    factory, iters, opts = golden_scenes.SCENES[name]
+    g = golden(name)
+    o = oracle_mod.Oracle(factory())
+    if opts:
+        o.set_options(opts())
+    o.begin(0)
+    o.run(iters, threads=1)
+    assert bit_equal(o.buffer(S.BUF_LIGHT_SAMPLER, np.uint32), g["light_sampler"])
+    assert bit_equal(o.buffer(S.BUF_CAMERA_SAMPLER, np.uint32), g["camera_sampler"])
+    assert bit_equal(o.buffer(S.BUF_LV_POS, np.float32), g["lv_pos"])
+    for layer, key in ((S.FILM_RESULT, "film_result"), (S.FILM_CAMERA, "film_camera"), (S.FILM_LIGHT, "film_light")):
+        assert bit_equal(o.film(layer), g[key]), key
+    img = o.film(S.FILM_RESULT)[..., :3]
+    assert np.isfinite(img).all() and img.min() >= 0.0 and img.mean() > 0.01
+
+
 def test_oracle_threads_agree_on_the_camera_image(oracle_mod):
     # thread-local vertex vectors are appended in thread order -> the pool and every camera sample are independent of the thread count;
     # only the light image's float atomics may reorder

@@ -4,6 +4,9 @@
 kat.npz         : known-answer vectors of the integer / scalar pieces (Sampler, spectral sampling, to_rgb, hash cell, offset_ray, blue noise)
 oracle_c1_32.npz: a 32x32, 3-iteration render of config C1 by the parity oracle (film layers + per-path sampler states + light-vertex pool digest)
 oracle_c2_32.npz: same for config C2 (spectral, dielectric sphere)
+oracle_c3_24.npz, oracle_c4_24.npz, oracle_c5_24.npz, oracle_vmf_24.npz: the scenes of tests/golden_scenes.py (BASELINE configs 3-5 with their full geometry at a
+                  small film, the vMF diffuse material box)
+Existing files are kept (zip metadata would change their bytes); delete one to regenerate it.
 trace_c2.npz    : 4096 rays against the C2 scene -> (tri,u,v,t, sampler state)
 """
 import os, sys
@@ -49,8 +52,13 @@ def kat():
         d[f"pm_{nm}"] = oracle_py.math_kat(fn, xs, ys)
     np.savez_compressed(os.path.join(OUT, "kat.npz"), **d)
 
-def render(name, sd, iters):
-    o = oracle_py.Oracle(sd); o.begin(0); o.run(iters, threads=1)
+def render(name, sd, iters, opts=None):
+    if os.path.exists(os.path.join(OUT, name)):
+        return None
+    o = oracle_py.Oracle(sd)
+    if opts is not None:
+        o.set_options(opts)
+    o.begin(0); o.run(iters, threads=1)
     lv = o.buffer(S.BUF_LV_POS, np.float32)
     d = dict(film_result=o.film(S.FILM_RESULT), film_camera=o.film(S.FILM_CAMERA), film_light=o.film(S.FILM_LIGHT),
              light_sampler=o.buffer(S.BUF_LIGHT_SAMPLER, np.uint32), camera_sampler=o.buffer(S.BUF_CAMERA_SAMPLER, np.uint32),
@@ -59,6 +67,8 @@ def render(name, sd, iters):
     return o
 
 def trace(sd):
+    if os.path.exists(os.path.join(OUT, "trace_c2.npz")):
+        return
     o = oracle_py.Oracle(sd)
     n = 4096
     org = (rng.random((n, 3)) * np.array([1.8, 1.8, 4.6]) + np.array([-0.9, 0.1, -0.9])).astype(np.float32)
@@ -68,9 +78,14 @@ def trace(sd):
     uvt, tri, seeds_out = o.trace(rays, seeds)
     np.savez_compressed(os.path.join(OUT, "trace_c2.npz"), rays=rays, seeds=seeds, uvt=uvt, tri=tri, seeds_out=seeds_out)
 
-kat()
+if not os.path.exists(os.path.join(OUT, "kat.npz")):
+    kat()
 render("oracle_c1_32.npz", scenes.cornell_box(32, 32, samples=16, spectral=False), 3)
 render("oracle_c2_32.npz", scenes.cornell_box(32, 32, samples=256, spectral=True, sphere=True), 3)
 trace(scenes.cornell_box(32, 32, samples=256, spectral=True, sphere=True))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import golden_scenes
+for name, (factory, iters, opts) in golden_scenes.SCENES.items():
+    render(name, factory(), iters, opts() if opts else None)
 for f in sorted(os.listdir(OUT)):
     print(f, os.path.getsize(os.path.join(OUT, f)))
