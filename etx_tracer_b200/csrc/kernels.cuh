@@ -12,11 +12,13 @@
 #include "dvcm.cuh"
 #include "dsss.cuh"
 
+// resident blocks per SM the bounce / connection kernels are compiled for (128 threads each: 4 blocks = 128 registers per thread).
+// Measured on the B200 (bench.py --lanes 1): 1|1 -> 4|4 gives C2 11.04 -> 11.36 and C3 5.55 -> 5.79 Msamples/s; 2 and 3 change nothing.
 #ifndef ETXB_BOUNCE_MIN_BLOCKS
-#define ETXB_BOUNCE_MIN_BLOCKS 1
+#define ETXB_BOUNCE_MIN_BLOCKS 4
 #endif
 #ifndef ETXB_CONNECT_MIN_BLOCKS
-#define ETXB_CONNECT_MIN_BLOCKS 1
+#define ETXB_CONNECT_MIN_BLOCKS 4
 #endif
 
 namespace etxb {
@@ -809,12 +811,13 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
 // (the reference shares one stream across the serial loop; the parity build keeps that order inside k_camera_shade).
 template <bool SP>
 __global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect(LaunchParams p, const uint2* conn_list) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t shadow_rays = 0;
   STATS_DECL;
-  uint32_t total = umin(*p.conn_count, p.conn_capacity);
-  if (t < total) {
-    const DeviceScene& sc = p.scene;
+  const DeviceScene& sc = p.scene;
+  // grid-stride over the device-side pair count: the host sizes the grid by the count when it has read it (long queues) and by the
+  // queue size when it has not (the tail of a pass runs without a host round trip per bounce)
+  const uint32_t total = umin(*p.conn_count, p.conn_capacity);
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     uint2 entry = conn_list[t];
     uint32_t i = entry.x;
     PathState<SP> state = load_state<SP>(p.paths, i);
@@ -827,7 +830,7 @@ __global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect
     V3 target_position;
     Spec<SP> value;
     if (vcm_connect_to_light_vertex<SP>(sc, p.vcm, state, lv, ep, target_position, value)) {
-      shadow_rays = 1;
+      shadow_rays += 1;
       Spec<SP> tr = vcm_connection_transmittance<SP>(sc, ep, lv, target_position, state, stats);
       if (tr.is_zero() == false) {
         V3 v = (tr * value).as_v3();

@@ -503,21 +503,27 @@ int run_camera_pass(etxb_ctx* ctx) {
       k_shadow_trace<<<blocks, 256, 0, ctx->stream>>>(p);
     }
     if (p.connect_stage && (ctx->options.options & ETXB_VCM_CONNECT_VERTICES)) {
-      uint32_t pending = 0;
-      if (int rc = read_u32(ctx, ctx->conn_count.ptr, pending)) return rc;
-      pending = std::min(pending, ctx->lv_capacity);
-      if (pending) {
-        const uint2* list = ctx->conn_list.ptr;
-        if (p.conn_key && (pending >= kSortQueueMin)) {
-          // connections grouped by (camera vertex material, light vertex material): one pair of BSDF classes per warp
-          LaunchTimer t(ctx, K_QUEUE_SORT);
-          size_t temp_bytes = ctx->cub_temp.bytes();
-          CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->keys_in.ptr, ctx->vals_in.ptr, reinterpret_cast<const unsigned long long*>(ctx->conn_list.ptr),
-                         reinterpret_cast<unsigned long long*>(ctx->conn_list_sorted.ptr), int(pending), 0, 16, ctx->stream));
-          list = ctx->conn_list_sorted.ptr;
-        }
+      if (active < kTailQueue) {
+        // tail of the pass: the pair count stays on the device (k_camera_connect is grid-stride), no host round trip per bounce
         LaunchTimer t(ctx, K_CAMERA_CONNECT);
-        k_camera_connect<SP><<<blocks_for(pending, 128), 128, 0, ctx->stream>>>(p, list);
+        k_camera_connect<SP><<<std::min<uint32_t>(148u * 4u, blocks_for(active * 4u, 128)), 128, 0, ctx->stream>>>(p, ctx->conn_list.ptr);
+      } else {
+        uint32_t pending = 0;
+        if (int rc = read_u32(ctx, ctx->conn_count.ptr, pending)) return rc;
+        pending = std::min(pending, ctx->lv_capacity);
+        if (pending) {
+          const uint2* list = ctx->conn_list.ptr;
+          if (p.conn_key && (pending >= kSortQueueMin)) {
+            // connections grouped by (camera vertex material, light vertex material): one pair of BSDF classes per warp
+            LaunchTimer t(ctx, K_QUEUE_SORT);
+            size_t temp_bytes = ctx->cub_temp.bytes();
+            CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->keys_in.ptr, ctx->vals_in.ptr, reinterpret_cast<const unsigned long long*>(ctx->conn_list.ptr),
+                           reinterpret_cast<unsigned long long*>(ctx->conn_list_sorted.ptr), int(pending), 0, 16, ctx->stream));
+            list = ctx->conn_list_sorted.ptr;
+          }
+          LaunchTimer t(ctx, K_CAMERA_CONNECT);
+          k_camera_connect<SP><<<blocks_for(pending, 128), 128, 0, ctx->stream>>>(p, list);
+        }
       }
     }
 #if defined(ETXB_PARITY) && ETXB_PARITY
