@@ -128,8 +128,22 @@ DEV bool trace_occluded(const DeviceScene& sc, V3 p0, V3 p1) {
   return vis.occluded;
 }
 
+struct PlainShadowVisitor {
+  const DeviceScene& sc;
+  Smp& smp;
+  bool occluded;
+  DEV int operator()(uint32_t triangle_index, float u, float v, float) {
+    const etxb_material& mat = sc.materials[load_triangle_material(sc, triangle_index)];
+    if (mat.cls == ETXB_MAT_VOID) return kCandIgnore;
+    if (alpha_test_rejects(sc, mat, triangle_index, u, v, smp)) return kCandIgnore;
+    occluded = true;
+    return kCandTerminate;
+  }
+};
+
 // Out of line: every kernel reaches it from several connection routines, and one BVH traversal dwarfs the call.
-template <bool SP>
+// PLAIN: compile-time promise that the scene has no Boundary surfaces, media or subsurface materials (DeviceScene flags, checked by the host).
+template <bool SP, bool PLAIN = false>
 DEVN Spec<SP> trace_transmittance(const DeviceScene& sc, float wavelength, V3 p0, V3 p1, uint32_t medium_index, Smp& smp, TraverseStats* stats) {
   V3 direction = p1 - p0;
   float t_max = dot(direction, direction);
@@ -137,26 +151,14 @@ DEVN Spec<SP> trace_transmittance(const DeviceScene& sc, float wavelength, V3 p0
   t_max = sqrtf(t_max);
   direction /= t_max;
   t_max -= fmaxf(kRayEpsilon, t_max * kRayEpsilon);
-#if defined(ETXB_EXP_PLAIN)
-  {
-    struct PlainShadowVisitor {
-      const DeviceScene& sc;
-      Smp& smp;
-      bool occluded;
-      DEV int operator()(uint32_t triangle_index, float u, float v, float) {
-        const etxb_material& mat = sc.materials[load_triangle_material(sc, triangle_index)];
-        if (mat.cls == ETXB_MAT_VOID) return kCandIgnore;
-        if (alpha_test_rejects(sc, mat, triangle_index, u, v, smp)) return kCandIgnore;
-        occluded = true;
-        return kCandTerminate;
-      }
-    } pvis{sc, smp, false};
+  if constexpr (PLAIN) {
+    // scenes without Boundary surfaces and media: the first candidate that passes the alpha test occludes — no crossing list, no media walk
+    PlainShadowVisitor pvis{sc, smp, false};
     DevNodeLoad pnl{sc.bvh_nodes};
     DevTriLoad ptl{sc.bvh_tris};
     traverse(pnl, ptl, p0.x, p0.y, p0.z, direction.x, direction.y, direction.z, kRayEpsilon, t_max, pvis, stats);
     return Spec<SP>::make(pvis.occluded ? 0.0f : 1.0f);
   }
-#endif
   Crossing crossings[kCrossingBufferSize + 1u];
   ShadowVisitor vis{sc, smp, crossings, 0u, false};
   DevNodeLoad nl{sc.bvh_nodes};

@@ -568,15 +568,13 @@ struct Endpoint {
 DEV float medium_phase(const DeviceScene& sc, uint32_t medium_index, V3 w_i, V3 w_o) { return phase_function(w_i, w_o, sc.mediums[medium_index].phase_function_g); }
 
 // vcm_try_sampling_medium (vcm_shared.hxx:379-388)
-template <bool SP>
+template <bool SP, bool PLAIN = false>
 DEV MediumSample<SP> vcm_try_sampling_medium(const DeviceScene& sc, PathState<SP>& state, float max_t) {
   MediumSample<SP> r;
   r.weight = Spec<SP>::make(0.0f);
   r.pos = {0.0f, 0.0f, 0.0f};
   r.sampled_medium_t = 0.0f;
-#if defined(ETXB_EXP_PLAIN)
-  return r;  // experiment: scenes without media / Boundary surfaces / subsurface only (measures what a compile-time specialisation buys)
-#endif
+  if constexpr (PLAIN) return r;  // no media in the scene
   if (state.medium_index == kInvalidIndex) return r;
   r = sample_medium<SP>(sc, sc.mediums[state.medium_index], state.wavelength, state.throughput, state.sampler, state.ray_o, state.ray_d, max_t);
   state.throughput *= r.weight;
@@ -584,11 +582,9 @@ DEV MediumSample<SP> vcm_try_sampling_medium(const DeviceScene& sc, PathState<SP
 }
 
 // vcm_handle_boundary_bsdf (vcm_shared.hxx:436-449)
-template <bool SP>
+template <bool SP, bool PLAIN = false>
 DEV bool vcm_handle_boundary(const DeviceScene& sc, const Isect& isect, PathState<SP>& state) {
-#if defined(ETXB_EXP_PLAIN)
-  return false;
-#endif
+  if constexpr (PLAIN) return false;  // no Boundary surfaces in the scene
   const etxb_material& mat = sc.materials[isect.material_index];
   if (mat.cls != ETXB_MAT_BOUNDARY) return false;
   TriRec tri = load_triangle(sc, isect.triangle_index);
@@ -602,7 +598,7 @@ DEV bool vcm_handle_boundary(const DeviceScene& sc, const Isect& isect, PathStat
 }
 
 // vcm_connect_to_camera (vcm_shared.hxx:463-535)
-template <bool SP>
+template <bool SP, bool PLAIN = false>
 DEV bool vcm_connect_to_camera(const DeviceScene& sc, const VcmParams& it, const Endpoint& ep, PathState<SP>& state, Spec<SP>& out_value, V2& uv, TraverseStats* stats,
   uint32_t& shadow_rays) {
   if ((it.connect_to_camera() == false) || (state.total_path_depth + 2 > sc.max_path_length) || (state.total_path_depth + 2 < sc.min_path_length)) return false;
@@ -636,7 +632,7 @@ DEV bool vcm_connect_to_camera(const DeviceScene& sc, const VcmParams& it, const
   float cos_t = fabsf(dot(cs.direction, cam3(camera.direction)));
   V3 clip_pos = origin + cs.direction * fmaxf(0.0f, len - camera.clip_near / cos_t);
   shadow_rays += 1;
-  Spec<SP> tr = trace_transmittance<SP>(sc, state.wavelength, origin, clip_pos, state.medium_index, state.sampler, stats);
+  Spec<SP> tr = trace_transmittance<SP, PLAIN>(sc, state.wavelength, origin, clip_pos, state.medium_index, state.sampler, stats);
   if (tr.is_zero()) return false;
   uv = cs.uv;
   float camera_pdf = cs.pdf_dir_out * (ep.at_medium ? 1.0f : fabsf(dot(ep.isect->nrm, w_o))) / dist2;
@@ -691,7 +687,7 @@ struct ShadowBatch {
 };
 
 // vcm_connect_to_light (vcm_shared.hxx:608-671)
-template <bool SP>
+template <bool SP, bool PLAIN = false>
 DEV Spec<SP> vcm_connect_to_light(const DeviceScene& sc, const VcmParams& it, const Endpoint& ep, PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays,
                                   ShadowBatch* batch = nullptr) {
   Spec<SP> zero = Spec<SP>::make(0.0f);
@@ -725,7 +721,7 @@ DEV Spec<SP> vcm_connect_to_light(const DeviceScene& sc, const VcmParams& it, co
   shadow_rays += 1;
   Spec<SP> tr = Spec<SP>::make(1.0f);
   if (batch == nullptr) {
-    tr = trace_transmittance<SP>(sc, state.wavelength, origin, es.origin, state.medium_index, state.sampler, stats);
+    tr = trace_transmittance<SP, PLAIN>(sc, state.wavelength, origin, es.origin, state.medium_index, state.sampler, stats);
     if (tr.is_zero()) return zero;
   }
   float l_dot_e = fabsf(dot(es.direction, es.normal));
@@ -840,18 +836,18 @@ DEV LightVertexRec load_light_vertex(const LightVertexRec* p_rec) {
 }
 
 // the shadow segment of one vertex connection (vcm_shared.hxx:784-799)
-template <bool SP>
+template <bool SP, bool PLAIN = false>
 DEV Spec<SP> vcm_connection_transmittance(const DeviceScene& sc, const Endpoint& ep, const LightVertexRec& lv, V3 target_position, PathState<SP>& state, TraverseStats* stats) {
   if (ep.at_medium) {
-    return trace_transmittance<SP>(sc, state.wavelength, ep.medium_pos, {lv.pos_tri.x, lv.pos_tri.y, lv.pos_tri.z}, state.medium_index, state.sampler, stats);
+    return trace_transmittance<SP, PLAIN>(sc, state.wavelength, ep.medium_pos, {lv.pos_tri.x, lv.pos_tri.y, lv.pos_tri.z}, state.medium_index, state.sampler, stats);
   }
   const Isect& isect = *ep.isect;
   V3 p0 = shading_pos(sc, load_triangle(sc, isect.triangle_index), isect.barycentric, normalize(target_position - isect.pos));
-  return trace_transmittance<SP>(sc, state.wavelength, p0, target_position, state.medium_index, state.sampler, stats);
+  return trace_transmittance<SP, PLAIN>(sc, state.wavelength, p0, target_position, state.medium_index, state.sampler, stats);
 }
 
 // vcm_connect_to_light_path (vcm_shared.hxx:765-803): serial over the paired path's vertices (shared sampler)
-template <bool SP>
+template <bool SP, bool PLAIN = false>
 DEV Spec<SP> vcm_connect_to_light_path(const DeviceScene& sc, const VcmParams& it, const LightVertexRec* pool, uint32_t lp_index, uint32_t lp_count, const Endpoint& ep,
   PathState<SP>& state, TraverseStats* stats, uint32_t& shadow_rays, uint32_t& connections, ShadowBatch* batch = nullptr) {
   Spec<SP> result = Spec<SP>::make(0.0f);
@@ -872,7 +868,7 @@ DEV Spec<SP> vcm_connect_to_light_path(const DeviceScene& sc, const VcmParams& i
         batch->push<SP>(p0, target_position, value);
         continue;
       }
-      Spec<SP> tr = vcm_connection_transmittance<SP>(sc, ep, lv, target_position, state, stats);
+      Spec<SP> tr = vcm_connection_transmittance<SP, PLAIN>(sc, ep, lv, target_position, state, stats);
       if (tr.is_zero() == false) {
         result += tr * value;
       }

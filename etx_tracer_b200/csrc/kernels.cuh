@@ -101,12 +101,13 @@ struct LaunchParams {
 #define STATS_TRIS 0u
 #endif
 
+// PLAIN (template parameter of the bounce kernels): compile-time promise that the scene has no media, Boundary surfaces or subsurface
+// materials — what C1-C3-class scenes otherwise pay for in registers, stack and instruction footprint (measured +4 % C2, +6 % on C3's bounce
+// kernels).  The host picks the instantiation from the DeviceScene flags.
+template <bool PLAIN = false>
 DEV bool scene_has_subsurface(const DeviceScene& sc) {
-#if defined(ETXB_EXP_PLAIN)
-  return false;
-#else
+  if constexpr (PLAIN) return false;
   return sc.has_subsurface != 0u;
-#endif
 }
 
 DEV void counter_add(unsigned long long* dst, uint32_t v) {
@@ -261,7 +262,7 @@ enum : uint32_t { kEpNone = 0u, kEpMedium = 1u, kEpSurface = 2u, kEpSubsurface =
 // vcm_light_step (vcm_shared.hxx:1086-1259).  Three phases so that every heavy routine has ONE call site: (A) the event at the end of
 // the segment (medium scattering, boundary crossing, surface hit incl. the subsurface walk), (B) camera connections from the
 // endpoint(s) it produced — one, or every gathered subsurface exit (:1207-1222), (C) the continuation.
-template <bool SP>
+template <bool SP, bool PLAIN>
 __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_light_bounce(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   bool alive = false;
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_light_bounce(La
     SSGather<SP> ssg;
     ssg.count = 0;
     // ---- (A) ----
-    MediumSample<SP> medium_sample = vcm_try_sampling_medium<SP>(sc, state, found ? hit.z : kMaxFloat);
+    MediumSample<SP> medium_sample = vcm_try_sampling_medium<SP, PLAIN>(sc, state, found ? hit.z : kMaxFloat);
     if (medium_sample.sampled_medium()) {
       // :1097-1170
       at_medium = true;
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_light_bounce(La
       if (p.vcm.connect_to_camera() && med.enable_explicit_connections && (state.total_path_depth + 1 <= sc.max_path_length)) ep_mode = kEpMedium;
     } else if (found) {
       isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
-      if (vcm_handle_boundary<SP>(sc, isect, state)) {
+      if (vcm_handle_boundary<SP, PLAIN>(sc, isect, state)) {
         alive = true;
       } else {
         at_surface = true;
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_light_bounce(La
         state.d_vc /= cos_to_prev;
         state.d_vm /= cos_to_prev;
         state.path_distance = 0.0f;
-        ss_path = scene_has_subsurface(sc) && (bs.properties & kBsdfDiffuse) && (mat.subsurface.cls != 0u);
+        ss_path = scene_has_subsurface<PLAIN>(sc) && (bs.properties & kBsdfDiffuse) && (mat.subsurface.cls != 0u);
         if (ss_path) ss_sampled = ss_gather<SP>(sc, state.wavelength, isect, state.sampler, ssg, stats, shadow_rays);
         if (is_connectible) {
           if (store_light_vertex(p, make_light_vertex<SP>(state, isect, i))) {  // the vertex stays at the entry point (:1204)
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_light_bounce(La
         state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
         Spec<SP> value;
         V2 uv;
-        bool ok = vcm_connect_to_camera<SP>(sc, p.vcm, ep, state, value, uv, stats, shadow_rays);
+        bool ok = vcm_connect_to_camera<SP, PLAIN>(sc, p.vcm, ep, state, value, uv, stats, shadow_rays);
         state.sampler.pop_fixed();
         if (ok && (value.maximum() > kEpsilon)) splats += splat_light<SP>(p, (ep_mode == kEpSubsurface) ? (w * value) : value, uv, state.wavelength);
       }
@@ -605,7 +606,7 @@ DEV void camera_emit_connections(const LaunchParams& p, uint32_t i, uint32_t cam
 // vcm_camera_step (vcm_shared.hxx:921-1080) up to the merge: same three phases as k_light_bounce — (A) the event, (B) connections to
 // the paired light path and to a sampled emitter from the endpoint(s) the event produced (one, or every gathered subsurface exit,
 // :1037-1053), (C) the MIS update / pending continuation sample handed to the merge and continue stages.
-template <bool SP>
+template <bool SP, bool PLAIN>
 __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t shadow_rays = 0, connections = 0;
@@ -631,14 +632,14 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
     SSGather<SP> ssg;
     ssg.count = 0;
     // ---- (A) ----
-    MediumSample<SP> medium_sample = vcm_try_sampling_medium<SP>(sc, state, found ? hit.z : kMaxFloat);
+    MediumSample<SP> medium_sample = vcm_try_sampling_medium<SP, PLAIN>(sc, state, found ? hit.z : kMaxFloat);
     if (medium_sample.sampled_medium() || found) {
       if (medium_sample.sampled_medium()) {
         at_medium = true;
         medium_pos = medium_sample.pos;
       } else {
         isect = make_intersection(sc, state.ray_d, tri_index, hit.x, hit.y, hit.z);
-        if (vcm_handle_boundary<SP>(sc, isect, state)) {
+        if (vcm_handle_boundary<SP, PLAIN>(sc, isect, state)) {
           resolved.x = kBounceResolvedAlive;  // :1002-1007
         } else {
           at_surface = true;
@@ -676,7 +677,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
         state.d_vm /= cos_to_prev;
         state.path_distance = 0.0f;
         vcm_handle_direct_hit<SP>(sc, p.vcm, isect, state);
-        ss_path = scene_has_subsurface(sc) && (bs.properties & kBsdfDiffuse) && (mat.subsurface.cls != 0u);
+        ss_path = scene_has_subsurface<PLAIN>(sc) && (bs.properties & kBsdfDiffuse) && (mat.subsurface.cls != 0u);
         if (ss_path) ss_sampled = ss_gather<SP>(sc, state.wavelength, isect, state.sampler, ssg, stats, shadow_rays);
         if (is_connectible) ep_mode = ss_sampled ? kEpSubsurface : kEpSurface;
       }
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
           Spec<SP> c;
           if ((step == 0u) == (ep_mode == kEpMedium)) {
             state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
-            c = vcm_connect_to_light<SP>(sc, p.vcm, ep, state, stats, shadow_rays, deferred);
+            c = vcm_connect_to_light<SP, PLAIN>(sc, p.vcm, ep, state, stats, shadow_rays, deferred);
             state.sampler.pop_fixed();
           } else if (p.connect_stage && (ep_mode == kEpSurface)) {
             camera_emit_connections<SP>(p, i, isect.material_index, state, connections);
@@ -731,7 +732,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
             continue;
           } else {
             // reference order: serial over the paired path's vertices with the path's own sampler
-            c = vcm_connect_to_light_path<SP>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], ep, state, stats, shadow_rays, connections, deferred);
+            c = vcm_connect_to_light_path<SP, PLAIN>(sc, p.vcm, p.lv_final, p.lp_offset[i], p.paths.lv_count[i], ep, state, stats, shadow_rays, connections, deferred);
             if (deferred) shadow_span.y = batch.count;  // segments to light vertices come first, the emitter segment (if any) last
           }
           state.gathered += (ep_mode == kEpSubsurface) ? (w * c) : c;
@@ -809,7 +810,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
 // Product build: one thread per (camera vertex, light vertex) connection — vcm_connect_to_light_vertex + the shadow ray of
 // vcm_connect_to_light_path (vcm_shared.hxx:673-803).  Each connection draws from its own stream derived from the path's sampler
 // (the reference shares one stream across the serial loop; the parity build keeps that order inside k_camera_shade).
-template <bool SP>
+template <bool SP, bool PLAIN>
 __global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect(LaunchParams p, const uint2* conn_list) {
   uint32_t shadow_rays = 0;
   STATS_DECL;
@@ -831,7 +832,7 @@ __global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect
     Spec<SP> value;
     if (vcm_connect_to_light_vertex<SP>(sc, p.vcm, state, lv, ep, target_position, value)) {
       shadow_rays += 1;
-      Spec<SP> tr = vcm_connection_transmittance<SP>(sc, ep, lv, target_position, state, stats);
+      Spec<SP> tr = vcm_connection_transmittance<SP, PLAIN>(sc, ep, lv, target_position, state, stats);
       if (tr.is_zero() == false) {
         V3 v = (tr * value).as_v3();
         float* dst = reinterpret_cast<float*>(p.paths.gathered + i);

@@ -90,6 +90,8 @@ struct etxb_ctx {
   bool spectral = false;
   bool profile = false;
   bool has_stochastic_merge = false;  // some material that can be merged at is not Lambert (needs the serial gather)
+  bool plain_kernels = true;          // bounce kernels specialised for scenes without media / Boundary surfaces / subsurface (ETXB_PLAIN_KERNELS=0: general ones)
+  bool plain_scene = false;           // set at upload: the scene qualifies
   bool merge_batched = true;          // generic photon gather batches its BSDF evaluations across the queries of a warp (ETXB_MERGE_BATCHED=0: per query)
   bool sort_by_material = true;       // group path queues and the connection list by material where BSDFs are costly (ETXB_SORT_MATERIAL=0: A/B switch)
   bool connect_deferred = true;       // per-connection stage for scenes with deferred shadow rays (ETXB_CONNECT_DEFERRED=0: A/B switch, serial loop)
@@ -357,7 +359,11 @@ int run_light_pass(etxb_ctx* ctx) {
     CUDA_OK(ctx, cudaMemsetAsync(counts + (cur ^ 1u), 0, 4, ctx->stream));
     {
       LaunchTimer t(ctx, K_LIGHT_BOUNCE);
-      k_light_bounce<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, q, counts + cur, qout, counts + (cur ^ 1u));
+      if (ctx->plain_scene && ctx->plain_kernels) {
+        k_light_bounce<SP, true><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, q, counts + cur, qout, counts + (cur ^ 1u));
+      } else {
+        k_light_bounce<SP, false><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, q, counts + cur, qout, counts + (cur ^ 1u));
+      }
     }
     cur ^= 1u;
     std::swap(qin, qout);
@@ -488,7 +494,11 @@ int run_camera_pass(etxb_ctx* ctx) {
     if (p.shadow_stage) CUDA_OK(ctx, cudaMemsetAsync(ctx->shadow_count.ptr, 0, 8, ctx->stream));
     {
       LaunchTimer t(ctx, K_CAMERA_SHADE);
-      k_camera_shade<SP><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, q, counts + cur);
+      if (ctx->plain_scene && ctx->plain_kernels) {
+        k_camera_shade<SP, true><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, q, counts + cur);
+      } else {
+        k_camera_shade<SP, false><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, q, counts + cur);
+      }
     }
     if (p.connect_deferred && (ctx->options.options & ETXB_VCM_CONNECT_VERTICES)) {
       // one thread per (camera vertex, light vertex) pair of the bounce, grid-stride over the reserved shadow slots (count on the device)
@@ -506,7 +516,12 @@ int run_camera_pass(etxb_ctx* ctx) {
       if (active < kTailQueue) {
         // tail of the pass: the pair count stays on the device (k_camera_connect is grid-stride), no host round trip per bounce
         LaunchTimer t(ctx, K_CAMERA_CONNECT);
-        k_camera_connect<SP><<<std::min<uint32_t>(148u * 4u, blocks_for(active * 4u, 128)), 128, 0, ctx->stream>>>(p, ctx->conn_list.ptr);
+        const uint32_t blocks = std::min<uint32_t>(148u * 4u, blocks_for(active * 4u, 128));
+        if (ctx->plain_scene && ctx->plain_kernels) {
+          k_camera_connect<SP, true><<<blocks, 128, 0, ctx->stream>>>(p, ctx->conn_list.ptr);
+        } else {
+          k_camera_connect<SP, false><<<blocks, 128, 0, ctx->stream>>>(p, ctx->conn_list.ptr);
+        }
       } else {
         uint32_t pending = 0;
         if (int rc = read_u32(ctx, ctx->conn_count.ptr, pending)) return rc;
@@ -522,7 +537,11 @@ int run_camera_pass(etxb_ctx* ctx) {
             list = ctx->conn_list_sorted.ptr;
           }
           LaunchTimer t(ctx, K_CAMERA_CONNECT);
-          k_camera_connect<SP><<<blocks_for(pending, 128), 128, 0, ctx->stream>>>(p, list);
+          if (ctx->plain_scene && ctx->plain_kernels) {
+            k_camera_connect<SP, true><<<blocks_for(pending, 128), 128, 0, ctx->stream>>>(p, list);
+          } else {
+            k_camera_connect<SP, false><<<blocks_for(pending, 128), 128, 0, ctx->stream>>>(p, list);
+          }
         }
       }
     }
@@ -628,6 +647,7 @@ int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
   if (const char* e = getenv("ETXB_CONNECT_DEFERRED")) ctx->connect_deferred = (e[0] != '0');
   if (const char* e = getenv("ETXB_SORT_MATERIAL")) ctx->sort_by_material = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_BATCHED")) ctx->merge_batched = (e[0] != '0');
+  if (const char* e = getenv("ETXB_PLAIN_KERNELS")) ctx->plain_kernels = (e[0] != '0');
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return ETXB_ERR_CUDA;
@@ -832,6 +852,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
       if ((im != ETXB_INVALID_INDEX) && (all_images[im].options & kImageHasAlpha)) deferred = false;
     }
     ctx->dscene.deferred_shadow_rays = deferred ? 1u : 0u;
+    ctx->plain_scene = !ctx->dscene.has_boundaries && !ctx->dscene.has_subsurface && (s.mediums.count == 0) && (cam.medium_index == ETXB_INVALID_INDEX);
   }
   // ---- images: pixels + flattened row/column CDFs (image.hxx:8-50) ---------------------------------------------------------------
   {
