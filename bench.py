@@ -248,6 +248,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # stdout carries ONE JSON line: whatever NCCL logs (its version banner under NCCL_DEBUG=VERSION/INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
