@@ -247,9 +247,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the module has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
+    json_fd = None
     if world > 1:
-        # stdout carries ONE JSON line: whatever NCCL logs (its version banner under NCCL_DEBUG=VERSION/INFO) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries ONE JSON line.  NCCL prints its version banner on stdout (NCCL_DEBUG=VERSION|WARN ignore NCCL_DEBUG_FILE), so for the
+        # whole multi-rank run file descriptor 1 points at stderr and rank 0 writes the JSON line to the saved descriptor
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -436,7 +440,11 @@ def main():
                            "light_vertices_per_iteration": st1["light_vertices"], "per_kernel_event_timing": True},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(counters["kernel_launches"]), "clocks": clk,
                 "counters": counters}
-        print(json.dumps(line), flush=True)
+        if json_fd is not None:
+            sys.stdout.flush()
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     g.close()
     if dist:
         dist.destroy_process_group()
