@@ -96,3 +96,48 @@ def test_no_cpu_fallback_without_a_device():
     from etx_tracer_b200.api import EtxbError, GPUVCM
     with pytest.raises(EtxbError):
         GPUVCM(scenes.cornell_box(16, 16, samples=1))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU VCM through oracle/_ref) runs without a GPU: one JSON line with the keys the driver
+    reads — same metric/unit as the GPU arm, impl = reference, zero host<->device bytes, a cpu_baseline describing the run."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from oracle import oracle_py
+    if not (oracle_py.available("native") or oracle_py.available("parity")):
+        import pytest
+        pytest.skip("oracle/_ref not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "C1", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Msamples/s" and d["higher_is_better"] is True and d["metric"].startswith("Msamples/s")
+    assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
+    assert d["e2e"] == {"value": d["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "C1" in d["config"]["workload"]
+
+
+def test_bench_algorithmic_bytes_follow_the_survey_formula():
+    """per-kernel byte costs x event counters; the whole-step figure is their sum."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c = dict(bounces_light=10, bounces_camera=20, light_vertices=7, connections=30, merge_queries=5, merge_candidates=400, merge_accepts=60, splats=3, rays_shadow=50,
+             rays_closest=30)
+    total, per = bench.algorithmic_bytes(c, n_pixels=16, steps=2)
+    assert per["camera_merge"] == 128 * 5 + 12 * 400 + 48 * 60
+    assert per["camera_connect"] == 516 * 30
+    assert per["camera_shade"] == 756 * 20 and per["trace_closest(camera)"] == 48 * 20
+    assert per["camera_continue"] == 352 * 20 + 104 * 16 * 2
+    assert per["shadow_trace"] == 48 * (50 - 7)
+    once = {k: v for k, v in per.items() if k != "camera_merge_generic"}  # the two gather kernels share one figure
+    assert total == sum(once.values())
