@@ -87,6 +87,7 @@ struct LaunchParams {
   uint32_t* shadow_count;        // [0] rays reserved this bounce, [1] work cursor of k_shadow_trace
   uint32_t shadow_capacity;
   uint32_t shadow_stage;         // 1: the scene qualifies (DeviceScene::deferred_shadow_rays) and the buffers exist
+  uint32_t merge_material_major; // 1: the gather queue is ordered by (material, Morton code) instead of the Morton code alone (ETXB_MERGE_MATERIAL_MAJOR=1)
   uint32_t connect_deferred;     // 1 (needs shadow_stage): the camera-vertex x light-vertex connections of such a scene run one per thread in
                                  //    k_camera_connect_deferred — conn_list[slot] names the (path, light vertex) pair that fills shadow slot `slot`
 };
@@ -787,6 +788,9 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
       }
       if (is_connectible && p.vcm.merge_vertices() && (state.total_path_depth + 1 <= sc.max_path_length) && (p.grid.photon_count != 0u)) {
         merge_key = merge_query_key(p.grid, isect.pos);
+        // experiment switch (default off, not yet measured): material-major order of the gather queue, so that the warps in flight evaluate ONE
+        // BSDF class at a time (ncu: k_camera_merge_generic_batched waits on instruction fetch, profiles/r1b_c3_k_*.raw.csv)
+        if (p.merge_material_major && (merge_key != 0xffffffffu)) merge_key = (umin(isect.material_index, 0x7eu) << 24) | (merge_key >> 6);
       }
       V3 w = bs.weight.as_v3();
       p.paths.bs_weight_pdf[i] = make_float4(w.x, w.y, w.z, bs.pdf);

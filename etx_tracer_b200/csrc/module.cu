@@ -90,6 +90,7 @@ struct etxb_ctx {
   bool spectral = false;
   bool profile = false;
   bool has_stochastic_merge = false;  // some material that can be merged at is not Lambert (needs the serial gather)
+  bool merge_material_major = false;  // experiment, default off: gather queue ordered by (material, Morton code) (ETXB_MERGE_MATERIAL_MAJOR=1)
   bool plain_kernels = true;          // bounce kernels specialised for scenes without media / Boundary surfaces / subsurface (ETXB_PLAIN_KERNELS=0: general ones)
   bool plain_scene = false;           // set at upload: the scene qualifies
   bool merge_batched = true;          // generic photon gather batches its BSDF evaluations across the queries of a warp (ETXB_MERGE_BATCHED=0: per query)
@@ -267,6 +268,7 @@ LaunchParams make_params(etxb_ctx* ctx) {
   p.shadow_capacity = uint32_t(ctx->shadow_p0.count);
   p.shadow_stage = (ctx->dscene.deferred_shadow_rays && ctx->shadow_p0.count) ? 1u : 0u;
   p.connect_deferred = (p.shadow_stage && ctx->connect_deferred) ? 1u : 0u;
+  p.merge_material_major = (ctx->merge_material_major && ctx->has_stochastic_merge) ? 1u : 0u;
 #if defined(ETXB_PARITY) && ETXB_PARITY
   p.connect_stage = 0;
 #else
@@ -648,6 +650,7 @@ int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
   if (const char* e = getenv("ETXB_SORT_MATERIAL")) ctx->sort_by_material = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_BATCHED")) ctx->merge_batched = (e[0] != '0');
   if (const char* e = getenv("ETXB_PLAIN_KERNELS")) ctx->plain_kernels = (e[0] != '0');
+  if (const char* e = getenv("ETXB_MERGE_MATERIAL_MAJOR")) ctx->merge_material_major = (e[0] != '0');
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return ETXB_ERR_CUDA;
