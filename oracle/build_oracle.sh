@@ -31,4 +31,26 @@ build() { # name flags extra_sources
 }
 build oracle_parity "-O2 -ffp-contract=off -fno-builtin-sincos" "$HERE/libm_override.cxx"
 build oracle_native "-O3 -march=x86-64-v3"
+
+# libreference_loader.so : the reference's OWN scene loader (scene_representation.cxx + pools + third-party readers) compiled in place,
+# with the three pieces that have no Linux implementation supplied by oracle/ref_loader.cxx (TaskScheduler, console colour, filter image).
+build_loader() {
+  local T="$REF/thirdparty" R="$REF/sources/etx"
+  local LINC="-I$REF/sources -I$T -I$T/json -I$T/tinyobjloader -I$T/stb_image -I$T/tinyexr -I$T/mikktspace -I$T/enkits -I$T/nanovdb -I$T/tinygltf"
+  local LFLAGS="-std=c++23 -DNDEBUG -fPIC -w -O2 -D_stricmp=strcasecmp -include etx/core/log.hxx"
+  local objs=""
+  for s in "$HERE/ref_loader.cxx" "$R/render/host/scene_representation.cxx" "$R/render/host/medium_pool.cxx" "$R/render/host/image_pool.cxx" \
+           "$R/render/host/scattering.cxx" "$R/render/host/gltf_accessor.cxx" "$R/render/host/spectrum.cxx" "$R/core/core.cxx" "$R/core/environment.cxx" \
+           "$R/core/log.cxx" "$T/tinyobjloader/tiny_obj_loader.cxx" "$T/stb_image/stb_image.cxx" "$T/tinyexr/tinyexr.cxx" "$T/tinygltf/tiny_gltf.cxx"; do
+    local o="$OUT/loader.$(basename "$s").o"
+    g++ $LFLAGS $LINC -c "$s" -o "$o" &
+    objs="$objs $o"
+  done
+  gcc -fPIC -w -O2 -c "$T/mikktspace/mikktspace.c" -o "$OUT/loader.mikktspace.o" &
+  objs="$objs $OUT/loader.mikktspace.o"
+  wait
+  g++ -shared -o "$OUT/libreference_loader.so" $objs -pthread
+  rm -f $objs
+}
+if build_loader; then :; else echo "reference loader did not build; tests that use it will skip" >&2; fi
 echo "built: $(ls $OUT/*.so)"

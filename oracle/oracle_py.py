@@ -64,8 +64,88 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+REFERENCE_ROOT = os.environ.get("ETX_REFERENCE", "/root/reference")
+
+
+class ReferenceScene:
+    """A scene file loaded by the reference's OWN loader (oracle/_ref/libreference_loader.so = scene_representation.cxx and friends compiled
+    in place, oracle/ref_loader.cxx).  Exposes what Oracle / GPUVCM read from a SceneData: `.scene` and `.camera` as numpy views over the
+    Scene / Camera PODs the loader owns (528 / 176 bytes, host pointers inside), plus width / height / triangle_count.  Only usable where the
+    reference tree (assets, IOR database) exists; `resize()` rebuilds the camera for a smaller film (build_camera, same view)."""
+
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(HERE, "_ref", "libreference_loader.so")) and os.path.isdir(os.path.join(REFERENCE_ROOT, "bin", "assets"))
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            lib = C.CDLL(os.path.join(HERE, "_ref", "libreference_loader.so"))
+            lib.refloader_load.restype = C.c_void_p
+            lib.refloader_load.argtypes = [C.c_char_p, C.c_char_p]
+            lib.refloader_free.argtypes = [C.c_void_p]
+            lib.refloader_free.restype = None
+            for fn in (lib.refloader_scene, lib.refloader_camera):
+                fn.restype = C.c_void_p
+                fn.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+            lib.refloader_material_index.restype = C.c_uint32
+            lib.refloader_material_index.argtypes = [C.c_void_p, C.c_char_p]
+            cls._lib = lib
+        return cls._lib
+
+    def __init__(self, scene_file, data_folder=None):
+        from etx_tracer_b200 import structs as S
+        lib = self.lib()
+        path = scene_file if os.path.isabs(scene_file) else os.path.join(REFERENCE_ROOT, "bin", scene_file)
+        self.h = lib.refloader_load((data_folder or os.path.join(REFERENCE_ROOT, "bin")).encode(), path.encode())
+        if not self.h:
+            raise RuntimeError(f"the reference loader rejected {path}")
+        n = C.c_uint64(0)
+        sp = lib.refloader_scene(self.h, C.byref(n))
+        assert n.value == S.SCENE.itemsize, (n.value, S.SCENE.itemsize)
+        self.scene = np.frombuffer((C.c_char * S.SCENE.itemsize).from_address(sp), dtype=S.SCENE)
+        cp = lib.refloader_camera(self.h, C.byref(n))
+        assert n.value == S.CAMERA.itemsize, (n.value, S.CAMERA.itemsize)
+        self.camera = np.frombuffer((C.c_char * S.CAMERA.itemsize).from_address(cp), dtype=S.CAMERA).copy()  # resize() edits the copy
+        self.name = "reference:" + os.path.basename(path)
+
+    @property
+    def width(self):
+        return int(self.camera["film_size"][0][0])
+
+    @property
+    def height(self):
+        return int(self.camera["film_size"][0][1])
+
+    @property
+    def triangle_count(self):
+        return int(self.scene["triangles"]["count"][0])
+
+    def material_index(self, name):
+        return int(self.lib().refloader_material_index(self.h, name.encode()))
+
+    def resize(self, width, height, origin, target, up, fov):
+        """build_camera (scene_representation.cxx:579-598) for another film size, through the oracle's export of the reference function."""
+        o, t, u = (np.asarray(v, dtype=np.float32) for v in (origin, target, up))
+        load("parity").oracle_build_camera(_p(self.camera), _p(o), _p(t), _p(u), int(width), int(height), C.c_float(fov))
+        return self
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib().refloader_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Oracle:
-    """One oracle instance bound to a SceneData (etx_tracer_b200.scenes.SceneData)."""
+    """One oracle instance bound to a SceneData (etx_tracer_b200.scenes.SceneData) or a ReferenceScene."""
 
     def __init__(self, scene_data, flavor="parity"):
         from etx_tracer_b200 import structs as S
