@@ -104,3 +104,17 @@ def test_oracle_renders_the_reference_loaded_scene(cornell, oracle_mod):
         o.close()
     finally:
         cornell.resize(640, 640, CAMERA["origin"], CAMERA["target"], CAMERA["up"], CAMERA["fov"])
+
+
+def test_named_ior_convention_matches_the_loader(cornell):
+    """`int_ior silver` -> the IOR database's eta / k spectra: the generator's tables (tools/make_data.py) hold the loader's bytes."""
+    mats = _view(cornell.scene["materials"], S.MATERIAL)
+    spectra = _view(cornell.scene["spectrums"], S.SPECTRUM)
+    ref = mats[cornell.material_index("tallbox")]
+    sd = scenes.SceneData()
+    mine = sd.materials[sd.add_material("metal", cls=S.MAT_CONDUCTOR, ks=[1.0, 1.0, 1.0], roughness=0.0, int_ior="silver")][0]
+    assert int(ref["cls"]) == int(mine["cls"]) == S.MAT_CONDUCTOR
+    assert int(ref["int_ior"]["cls"]) == int(mine["int_ior"]["cls"])
+    for part in ("eta_index", "k_index"):
+        a, b = spectra[int(ref["int_ior"][part])], np.asarray(sd.spectra[int(mine["int_ior"][part])])
+        assert bytes(a.tobytes()) == bytes(b.tobytes()), part
