@@ -300,10 +300,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ---------------------------------------------------------------------------------------------
-    # every lane renders at least one untimed iteration (W warm-up steps spread over `lanes` contexts would leave a lane cold when W < lanes)
-    warmup_steps = max(args.warmup, lanes)
     begin()
-    run_steps(warmup_steps)
+    run_steps(args.warmup)
     sync_all()
     st0 = g.status()
     c0 = g.counters()
@@ -338,7 +336,7 @@ def main():
     pinned = torch.empty((sd.height, sd.width, 4), dtype=torch.float32).pin_memory()
     host_film = pinned.numpy()
     begin()
-    run_steps(warmup_steps)
+    run_steps(args.warmup)
     sync_all()
     t0 = time.time()
     film_reads = 0
@@ -430,7 +428,7 @@ def main():
         if not args.no_cpu_baseline:
             from etx_tracer_b200 import scenes
             cpu, _ = cpu_baseline_run(lambda res: scene_factory(args, res), args.cpu_budget, os.cpu_count() or 1, workload_vcm_options(args))
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup_steps,
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if tile_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc,
                            "parallelism": (f"pixel-tile x{world}, photon exchange per iteration" if tile_mode else
