@@ -1392,6 +1392,194 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_gener
   counter_add(&p.counters->merge_accepts, accepts);
 }
 
+// EXPERIMENT (ETXB_MERGE_TILED=1, default off: written after the round's GPU budget ended, not yet run on the device).
+// Cell-tiled Lambert gather.  k_camera_merge_coop<SP, false> re-reads the ~530 candidate positions of a query's eight cells from L2 for every
+// query, although the 32 queries of a warp (sorted by base cell) share almost all of them: measured, the sweep streams ~3.9 TB/s out of L2.
+// Here the lanes ARE the queries: for every distinct base cell among the warp's queries, each of the up-to-27 neighbouring cells some lane
+// needs is read ONCE (coalesced, 32 photons per step), each photon is broadcast by shuffle and tested by every lane that has that cell
+// among its eight (same hash entries, same duplicates as VCMSpatialGridData::gather, vcm_shared.hxx:886-924); accepted (query, photon)
+// pairs go through the shared list and per-query accumulators of the batched generic kernel.  Candidate traffic per warp: ~29 KB instead
+// of ~270 KB.
+template <bool SP>
+__global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_tiled(LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys, const uint32_t* count_in,
+                                                                                 uint32_t queries_per_warp) {
+  __shared__ uint32_t s_idx[kMergeWarpsPerBlock][kMergeListSize];
+  __shared__ float s_d2[kMergeWarpsPerBlock][kMergeListSize];
+  __shared__ float s_dvcm[kMergeWarpsPerBlock][kMergeListSize];
+  __shared__ uint32_t s_src[kMergeWarpsPerBlock][kMergeListSize];
+  __shared__ float s_sum[kMergeWarpsPerBlock][32][3];
+  constexpr uint32_t kFull = 0xffffffffu;
+  const DeviceScene& sc = p.scene;
+  const GridData& g = p.grid;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  uint32_t q = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * queries_per_warp + lane;
+  uint32_t merge_queries = 0, candidates = 0, accepts = 0;
+  bool active = (lane < queries_per_warp) && (q < *count_in) && (sorted_keys[q] != 0xffffffffu);
+  uint32_t i = 0;
+  V3 qpos = {0, 0, 0}, qnrm = {0, 0, 0}, qfn = {0, 0, 0}, qc = {0, 0, 0};
+  float q_wcam_base = 0.0f, q_dvm = 0.0f, q_rev_cos = 0.0f;
+  uint32_t q_depth = 0;
+  int32_t acx = 0, acy = 0, acz = 0, sx = 0, sy = 0, sz = 0;  // base cell and the side of it the query lies on (vcm_shared.hxx:895-905)
+  if (active) {
+    i = sorted_ids[q];
+    float4 hit = p.paths.hit[i];
+    PathState<SP> state = load_state<SP>(p.paths, i);
+    Isect isect = stage_intersection<SP>(p, state, i, hit);
+    const etxb_material& mat = sc.materials[isect.material_index];
+    active = merge_is_lambert(mat);
+    if (active) {
+      merge_queries = 1;
+      qpos = isect.pos;
+      qnrm = isect.nrm;
+      q_wcam_base = state.d_vcm * p.vcm.vc_weight;
+      q_dvm = state.d_vm;
+      q_depth = state.total_path_depth;
+      Spec<SP> t_camera = state.throughput / sampling_pdf<SP>(state.wavelength);
+      bool entering = dot(isect.nrm, isect.w_i) < 0.0f;
+      qfn = entering ? isect.nrm : -isect.nrm;
+      Spec<SP> diffuse = apply_image<SP>(sc, mat.scattering, isect.tex, state.wavelength);
+      qc = spec_to_rgb<SP>(sc, (diffuse / kPi) * t_camera, state.wavelength);
+      q_rev_cos = dot(isect.nrm, -isect.w_i);
+      V3 m = (qpos - g.bbox_min) / g.cell_size;
+      V3 mf = vfloor(m);
+      V3 md = m - mf;
+      acx = static_cast<int32_t>(mf.x);
+      acy = static_cast<int32_t>(mf.y);
+      acz = static_cast<int32_t>(mf.z);
+      sx = (md.x < 0.5f) ? -1 : +1;
+      sy = (md.y < 0.5f) ? -1 : +1;
+      sz = (md.z < 0.5f) ? -1 : +1;
+    }
+  }
+  s_sum[warp][lane][0] = 0.0f;
+  s_sum[warp][lane][1] = 0.0f;
+  s_sum[warp][lane][2] = 0.0f;
+  __syncwarp();
+  const bool use_mis = p.vcm.enable_mis();
+  const bool use_epan = (p.vcm.kernel == 1u);
+  const float vc_weight = p.vcm.vc_weight;
+  uint32_t n_list = 0;
+
+  auto shfl3 = [&](V3 v, uint32_t s) { return V3{__shfl_sync(kFull, v.x, s), __shfl_sync(kFull, v.y, s), __shfl_sync(kFull, v.z, s)}; };
+  auto finish = [&](uint32_t n) {
+    uint32_t j = 0, s = 0;
+    float distance_squared = 0.0f, dvcm = 0.0f;
+    if (lane < n) {
+      j = s_idx[warp][lane];
+      distance_squared = s_d2[warp][lane];
+      dvcm = s_dvcm[warp][lane];
+      s = s_src[warp][lane];
+    }
+    V3 bnrm = shfl3(qnrm, s), bfn = shfl3(qfn, s);
+    float b_wcam_base = __shfl_sync(kFull, q_wcam_base, s);
+    float b_dvm = __shfl_sync(kFull, q_dvm, s);
+    float b_rev_cos = __shfl_sync(kFull, q_rev_cos, s);
+    uint32_t b_depth = __shfl_sync(kFull, q_depth, s);
+    if (lane < n) {
+      float4 wl = __ldg(&g.win_len[j]);
+      float4 nd = __ldg(&g.nrm_dvm[j]);
+      float4 lt = __ldg(&g.thr_rgb[j]);
+      bool ok = !(__float_as_uint(wl.w) + b_depth + 1 > sc.max_path_length);
+      ok = ok && !(dot(bnrm, V3{nd.x, nd.y, nd.z}) <= kEpsilon);
+      float cos_o = -(bfn.x * wl.x + bfn.y * wl.y + bfn.z * wl.z);  // local_w_o.z of DiffuseBSDF::evaluate(-w_in)
+      ok = ok && (cos_o > kEpsilon);
+      if (ok) {
+        float bsdf_pdf_v = kInvPi * cos_o;
+        float facing = (dot(bnrm, V3{wl.x, wl.y, wl.z}) < 0.0f) ? b_rev_cos : -b_rev_cos;
+        float rev_pdf = (facing <= kEpsilon) ? 0.0f : kInvPi * facing;
+        float w_light = dvcm * vc_weight + nd.w * bsdf_pdf_v;
+        float w_camera = b_wcam_base + b_dvm * rev_pdf;
+        float weight = use_mis ? (1.0f / (1.0f + w_light + w_camera)) : 1.0f;
+        float kernel_weight = use_epan ? fmaxf(2.0f * (1.0f - distance_squared * g.inv_radius_squared), 0.0f) : 1.0f;
+        float kw = kernel_weight * weight;
+        atomicAdd(&s_sum[warp][s][0], lt.x * kw);
+        atomicAdd(&s_sum[warp][s][1], lt.y * kw);
+        atomicAdd(&s_sum[warp][s][2], lt.z * kw);
+        accepts += 1;
+      }
+    }
+  };
+
+  uint32_t todo = __ballot_sync(kFull, active);
+  while (todo) {
+    // one group = the queries of this warp that share a base cell
+    const uint32_t leader = __ffs(todo) - 1u;
+    const int32_t bx = __shfl_sync(kFull, acx, leader), by = __shfl_sync(kFull, acy, leader), bz = __shfl_sync(kFull, acz, leader);
+    const bool in_group = active && (acx == bx) && (acy == by) && (acz == bz);
+    todo &= ~__ballot_sync(kFull, in_group);
+#pragma unroll 1
+    for (int32_t o = 0; o < 27; ++o) {
+      const int32_t ox = (o % 3) - 1, oy = ((o / 3) % 3) - 1, oz = (o / 9) - 1;
+      // a query's eight cells: base or the neighbour on its side, per axis
+      const bool need = in_group && ((ox == 0) || (ox == sx)) && ((oy == 0) || (oy == sy)) && ((oz == 0) || (oz == sz));
+      if (__ballot_sync(kFull, need) == 0u) continue;
+      const uint2 range = __ldg(&g.cell_range[grid_cell_index(g.hash_table_mask, bx + ox, by + oy, bz + oz)]);
+      for (uint32_t base = range.x; base < range.y; base += 32u) {
+        const uint32_t chunk = umin(32u, range.y - base);
+        float4 pd = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (lane < chunk) pd = __ldg(&g.pos_dvcm[base + lane]);
+        for (uint32_t t = 0; t < chunk; ++t) {
+          const float px = __shfl_sync(kFull, pd.x, t), py = __shfl_sync(kFull, pd.y, t), pz = __shfl_sync(kFull, pd.z, t), pw = __shfl_sync(kFull, pd.w, t);
+          bool inside = false;
+          float distance_squared = 0.0f;
+          if (need) {
+            V3 d = V3{px, py, pz} - qpos;
+            distance_squared = dot(d, d);
+            inside = !(distance_squared > g.radius_squared);
+            candidates += 1;
+          }
+          const uint32_t bal = __ballot_sync(kFull, inside);
+          if (bal == 0u) continue;
+          if (inside) {
+            uint32_t slot = n_list + __popc(bal & lane_lt);
+            s_idx[warp][slot] = base + t;
+            s_d2[warp][slot] = distance_squared;
+            s_dvcm[warp][slot] = pw;
+            s_src[warp][slot] = lane;
+          }
+          n_list += __popc(bal);
+          __syncwarp();
+          if (n_list >= 32u) {
+            finish(32u);
+            __syncwarp();
+            uint32_t rest = n_list - 32u;  // < 32: move the tail to the front
+            uint32_t tj = 0, ts = 0;
+            float td = 0.0f, tv = 0.0f;
+            if (lane < rest) {
+              tj = s_idx[warp][32u + lane];
+              td = s_d2[warp][32u + lane];
+              tv = s_dvcm[warp][32u + lane];
+              ts = s_src[warp][32u + lane];
+            }
+            __syncwarp();
+            if (lane < rest) {
+              s_idx[warp][lane] = tj;
+              s_d2[warp][lane] = td;
+              s_dvcm[warp][lane] = tv;
+              s_src[warp][lane] = ts;
+            }
+            n_list = rest;
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+  if (n_list) finish(n_list);
+  __syncwarp();
+  if (merge_queries) {
+    V3 l = {s_sum[warp][lane][0], s_sum[warp][lane][1], s_sum[warp][lane][2]};
+    if (SP) l *= V3{0.817660332f, 1.05418909f, 1.09945524f};  // kRGBLuminanceScale (:876-878)
+    l = qc * l;
+    float4 mg = p.paths.merged[i];
+    p.paths.merged[i] = make_float4(mg.x + l.x, mg.y + l.y, mg.z + l.z, 0.0f);
+  }
+  counter_add(&p.counters->merge_queries, merge_queries);
+  counter_add(&p.counters->merge_candidates, candidates);
+  counter_add(&p.counters->merge_accepts, accepts);
+}
+
 // The deferred shadow rays of one camera bounce (ShadowBatch, dvcm.cuh): a traversal-only kernel — persistent warps take 32 segments at a
 // time from a shared cursor, every lane answers "is anything but a Void surface on this segment?".
 __global__ void __launch_bounds__(256) k_shadow_trace(LaunchParams p) {

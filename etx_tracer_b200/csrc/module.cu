@@ -90,6 +90,7 @@ struct etxb_ctx {
   bool spectral = false;
   bool profile = false;
   bool has_stochastic_merge = false;  // some material that can be merged at is not Lambert (needs the serial gather)
+  bool merge_tiled = false;           // experiment, default off: cell-tiled Lambert gather k_camera_merge_tiled (ETXB_MERGE_TILED=1)
   bool merge_material_major = false;  // experiment, default off: gather queue ordered by (material, Morton code) (ETXB_MERGE_MATERIAL_MAJOR=1)
   bool plain_kernels = true;          // bounce kernels specialised for scenes without media / Boundary surfaces / subsurface (ETXB_PLAIN_KERNELS=0: general ones)
   bool plain_scene = false;           // set at upload: the scene qualifies
@@ -572,7 +573,11 @@ int run_camera_pass(etxb_ctx* ctx) {
       const uint32_t merge_blocks = blocks_for(blocks_for(active, qpw), kMergeWarpsPerBlock);
       {
         LaunchTimer t(ctx, K_CAMERA_MERGE);
-        k_camera_merge_coop<SP, false><<<merge_blocks, kMergeWarpsPerBlock * 32, 0, ctx->stream>>>(p, ids, keys, counts + cur, qpw);
+        if (ctx->merge_tiled) {
+          k_camera_merge_tiled<SP><<<merge_blocks, kMergeWarpsPerBlock * 32, 0, ctx->stream>>>(p, ids, keys, counts + cur, qpw);
+        } else {
+          k_camera_merge_coop<SP, false><<<merge_blocks, kMergeWarpsPerBlock * 32, 0, ctx->stream>>>(p, ids, keys, counts + cur, qpw);
+        }
       }
       if (ctx->has_stochastic_merge) {
         LaunchTimer t(ctx, K_CAMERA_MERGE_SERIAL);
@@ -651,6 +656,7 @@ int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
   if (const char* e = getenv("ETXB_MERGE_BATCHED")) ctx->merge_batched = (e[0] != '0');
   if (const char* e = getenv("ETXB_PLAIN_KERNELS")) ctx->plain_kernels = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_MATERIAL_MAJOR")) ctx->merge_material_major = (e[0] != '0');
+  if (const char* e = getenv("ETXB_MERGE_TILED")) ctx->merge_tiled = (e[0] != '0');
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return ETXB_ERR_CUDA;
