@@ -1042,10 +1042,13 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   DevBuf<float4>* per_vertex_f4[] = {&ctx->g_pos, &ctx->g_nrm, &ctx->g_win, &ctx->g_thr};
   for (auto* b : per_vertex_f4) CUDA_OK(ctx, b->alloc(cap));
   CUDA_OK(ctx, ctx->cell_range.alloc(next_pow2(cap)));
-  size_t temp_sort = 0, temp_scan = 0;
+  // one scratch buffer for every CUB call of an iteration: the 32-bit pair sorts (photon grid, gather queue, path queues), the pair-list
+  // sort with its 64-bit (path, light vertex) values, and the scan over the per-path vertex counts
+  size_t temp_sort = 0, temp_sort64 = 0, temp_scan = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, temp_sort, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, int(cap));
+  cub::DeviceRadixSort::SortPairs(nullptr, temp_sort64, (uint32_t*)nullptr, (uint32_t*)nullptr, (unsigned long long*)nullptr, (unsigned long long*)nullptr, int(cap), 0, 16);
   cub::DeviceScan::ExclusiveSum(nullptr, temp_scan, (uint32_t*)nullptr, (uint32_t*)nullptr, int(n));
-  CUDA_OK(ctx, ctx->cub_temp.alloc(std::max(temp_sort, temp_scan) + 256));
+  CUDA_OK(ctx, ctx->cub_temp.alloc(std::max(std::max(temp_sort, temp_sort64), temp_scan) + 256));
   CUDA_OK(ctx, cudaMemsetAsync(ctx->overflow.ptr, 0, 4, ctx->stream));
   CUDA_OK(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(DeviceCounters), ctx->stream));
   CUDA_OK(ctx, cudaMemsetAsync(ctx->sampler_end_light.ptr, 0, n * 4, ctx->stream));
