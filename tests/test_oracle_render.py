@@ -120,3 +120,34 @@ def test_fbm_density_variants_are_normalised():
     for d in (scenes.fbm_density(16), scenes.fbm_density_fast(64)):
         assert d.dtype == np.float32 and float(d.max()) == 1.0 and float(d.min()) == 0.0
         assert 0.02 < float(d.mean()) < 0.3
+
+
+def test_traversal_order_changes_the_image_only_statistically(oracle_mod):
+    """SURVEY.md 8(c) tier C.  The reference draws one sampler value per CANDIDATE hit, so the candidate order of the ray caster (Embree there,
+    the shared BVH here) decides which random numbers a path sees.  Rendering the same scene with its triangles in another order (another
+    BVH, another candidate order, other emitter indices) must change the image only like another set of samples does: the relative MSE between
+    the two orders stays within 2x of the oracle's own run-to-run relative MSE at equal sample counts."""
+    def build(shuffle):
+        sd = scenes.cornell_box(32, 32, samples=256, spectral=True, sphere=True, sphere_segments=24, sphere_rings=13, finalize=False)
+        if shuffle:
+            tris = np.concatenate(sd.triangles)
+            sd.triangles = [tris[np.random.default_rng(11).permutation(len(tris))]]
+        return sd.finalize(samples=256, spectral=True)
+
+    def render(sd, first):
+        o = oracle_mod.Oracle(sd, "native")
+        o.begin(first)
+        o.run(24, threads=8)
+        img = o.film(S.FILM_RESULT)[..., :3].astype(np.float64)
+        o.close()
+        return img
+
+    a, b, a2 = render(build(False), 0), render(build(True), 0), render(build(False), 24)
+
+    def rel_mse(x, y):
+        m = 0.5 * (x + y)
+        return float((((x - y) ** 2) / (m ** 2 + 1e-3)).mean())
+
+    run_to_run, order_to_order = rel_mse(a, a2), rel_mse(a, b)
+    assert order_to_order < 2.0 * run_to_run, (order_to_order, run_to_run)
+    assert abs(a.mean() - b.mean()) / a.mean() < 0.05
