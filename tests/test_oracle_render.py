@@ -124,14 +124,25 @@ def test_fbm_density_variants_are_normalised():
 
 def test_traversal_order_changes_the_image_only_statistically(oracle_mod):
     """SURVEY.md 8(c) tier C.  The reference draws one sampler value per CANDIDATE hit, so the candidate order of the ray caster (Embree there,
-    the shared BVH here) decides which random numbers a path sees.  Rendering the same scene with its triangles in another order (another
-    BVH, another candidate order, other emitter indices) must change the image only like another set of samples does: the relative MSE between
-    the two orders stays within 2x of the oracle's own run-to-run relative MSE at equal sample counts."""
-    def build(shuffle):
+    the shared BVH here) decides which random numbers a path sees.  Rendering the same view of the same scene ROTATED by 33 degrees about the
+    vertical axis (camera included: another axis-aligned BVH, other near/far decisions, another candidate order, other roundings) must change
+    the image only like another set of samples does: the relative MSE between the two stays within 2x of the oracle's own run-to-run relative
+    MSE at equal sample counts — and is not zero, i.e. the rotation really changed some sample paths."""
+    import math
+    ang = math.radians(33.0)
+    rot = np.array([[math.cos(ang), 0.0, math.sin(ang)], [0.0, 1.0, 0.0], [-math.sin(ang), 0.0, math.cos(ang)]])
+
+    def build(rotated):
         sd = scenes.cornell_box(32, 32, samples=256, spectral=True, sphere=True, sphere_segments=24, sphere_rings=13, finalize=False)
-        if shuffle:
-            tris = np.concatenate(sd.triangles)
-            sd.triangles = [tris[np.random.default_rng(11).permutation(len(tris))]]
+        origin, target, up = np.array([0.0, 1.0, 3.82]), np.array([0.0, 1.0, -6.18]), np.array([0.0, 1.0, 0.0])
+        if rotated:
+            for v in sd.vertices:
+                for f in ("pos", "nrm", "tan", "btn"):
+                    v[f] = (v[f].astype(np.float64) @ rot.T).astype(np.float32)
+            for t in sd.triangles:
+                t["geo_n"] = (t["geo_n"].astype(np.float64) @ rot.T).astype(np.float32)
+            origin, target = rot @ origin, rot @ target
+        sd.set_camera(origin, target, up, 32, 32, 39.597755335771296, clip_near=0.1, clip_far=100.0)
         return sd.finalize(samples=256, spectral=True)
 
     def render(sd, first):
@@ -149,5 +160,6 @@ def test_traversal_order_changes_the_image_only_statistically(oracle_mod):
         return float((((x - y) ** 2) / (m ** 2 + 1e-3)).mean())
 
     run_to_run, order_to_order = rel_mse(a, a2), rel_mse(a, b)
-    assert order_to_order < 2.0 * run_to_run, (order_to_order, run_to_run)
+    # measured: 0.014 against 0.29 run to run — most rays meet ONE candidate (near-first traversal prunes the rest), so few paths change at all
+    assert 1e-6 < order_to_order < 2.0 * run_to_run, (order_to_order, run_to_run)
     assert abs(a.mean() - b.mean()) / a.mean() < 0.05
