@@ -163,3 +163,53 @@ def test_traversal_order_changes_the_image_only_statistically(oracle_mod):
     # measured: 0.014 against 0.29 run to run — most rays meet ONE candidate (near-first traversal prunes the rest), so few paths change at all
     assert 1e-6 < order_to_order < 2.0 * run_to_run, (order_to_order, run_to_run)
     assert abs(a.mean() - b.mean()) / a.mean() < 0.05
+
+
+def test_restated_ray_caster_finds_the_brute_force_closest_hit(oracle_mod):
+    """The one piece of the oracle that is restated rather than compiled from the reference is the ray caster over the shared BVH (Embree is
+    absent).  Independent check: for random rays the BVH traversal must return the closest triangle a float64 brute-force Moeller-Trumbore over
+    ALL triangles finds (same triangle, or one at an indistinguishable distance), and miss exactly when brute force misses."""
+    sd = scenes.cornell_box(16, 16, samples=16, spectral=False, sphere=True, sphere_segments=24, sphere_rings=13)
+    o = oracle_mod.Oracle(sd)
+    rng = np.random.default_rng(5)
+    n = 3000
+    org = (rng.random((n, 3)) * np.array([1.8, 1.8, 4.6]) + np.array([-0.9, 0.1, -0.9])).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    tmin = np.float32(2.28997145e-4)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3], rays[:, 3], rays[:, 4:7], rays[:, 7] = org, tmin, d, 3.0e38
+    uvt, tri, _ = o.trace(rays, rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32))
+    o.close()
+    import ctypes as C
+    nv, nt = int(sd.scene["vertices"]["count"][0]), int(sd.scene["triangles"]["count"][0])
+    V = np.frombuffer((C.c_char * (nv * S.VERTEX.itemsize)).from_address(int(sd.scene["vertices"]["a"][0])), dtype=S.VERTEX)["pos"].astype(np.float64)
+    T = np.frombuffer((C.c_char * (nt * S.TRIANGLE.itemsize)).from_address(int(sd.scene["triangles"]["a"][0])), dtype=S.TRIANGLE)["i"].astype(np.int64)
+    a, b, c = V[T[:, 0]], V[T[:, 1]], V[T[:, 2]]
+    e1, e2 = b - a, c - a
+    best_t = np.full(n, np.inf)
+    best_tri = np.full(n, -1, dtype=np.int64)
+    for k in range(n):
+        o64, d64 = org[k].astype(np.float64), d[k].astype(np.float64)
+        p = np.cross(d64, e2)
+        det = (e1 * p).sum(1)
+        ok = np.abs(det) > 0
+        inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+        tv = o64 - a
+        u = (tv * p).sum(1) * inv
+        qv = np.cross(tv, e1)
+        v = (qv @ d64) * inv
+        t = (e2 * qv).sum(1) * inv
+        hit = ok & (u >= 0) & (v >= 0) & (u + v <= 1) & (t > float(tmin))
+        if hit.any():
+            tt = np.where(hit, t, np.inf)
+            best_tri[k], best_t[k] = int(np.argmin(tt)), float(tt.min())
+    found = tri != 0xFFFFFFFF
+    # rays that graze an edge can fall on either side in float32 vs float64: tolerate a handful, require exactness elsewhere
+    miss_mismatch = int((found != np.isfinite(best_t)).sum())
+    assert miss_mismatch <= 3, miss_mismatch
+    both = found & np.isfinite(best_t)
+    same_tri = tri[both].astype(np.int64) == best_tri[both]
+    close_t = np.abs(uvt[both, 2].astype(np.float64) - best_t[both]) <= 1e-4 * np.maximum(1.0, best_t[both])
+    assert close_t.mean() > 0.999, float(close_t.mean())
+    assert (same_tri | close_t).mean() > 0.999 and same_tri.mean() > 0.99, (float(same_tri.mean()), float(close_t.mean()))
