@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""bench.py — Msamples/s of the VCM hot path on BASELINE.json's headline config, one JSON line on stdout.
+"""bench.py — Msamples/s of the VCM hot path on BASELINE.json's headline config (C3: the 1M-triangle spectral room at 1920x1080, the config the
+north-star targets are quoted on; --workload C1|C2|C4|C5 select the other configs), one JSON line on stdout.
 
   python bench.py --gpus N --steps K --warmup W            # the CUDA module (N>1: launched by torch.distributed.run, one rank per GPU)
   python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU VCM (oracle/_ref, all host threads), rank 0 only
@@ -113,9 +114,15 @@ def measured_peaks():
         return None
 
 
+def bvh_bytes(nodes, tris):
+    """64 B per BVH node visited + 48 B per triangle tested."""
+    return 64 * nodes + 48 * tris
+
+
 def algorithmic_bytes(counters, n_pixels, steps):
-    """device event counters x fixed byte costs (reference struct sizes), BVH node/triangle traffic excluded (those
-    counters exist only in ETXB_COUNT_TRAVERSAL builds).  Returns (whole-step bytes, {kernel name: the bytes of ITS units})."""
+    """device event counters x fixed byte costs (reference struct sizes), BVH node/triangle traffic excluded here (those
+    counters exist only in the ETXB_COUNT_TRAVERSAL build, which main() runs for one extra pass: `roofline.bvh`).
+    Returns (whole-step bytes, {kernel name: the bytes of ITS units})."""
     c = counters
     bl, bc, lv = c["bounces_light"], c["bounces_camera"], c["light_vertices"]
     merge = 128 * c["merge_queries"] + 12 * c["merge_candidates"] + 48 * c["merge_accepts"]
@@ -192,9 +199,13 @@ def run_reference(args):
     probe.run(1, threads=threads)
     rate = probe.width * probe.height / max(time.time() - t0, 1e-6)
     probe.close()
+    # same film as the GPU arm when one iteration of it fits the per-step budget (the whole --steps/--warmup run must end within minutes),
+    # else the largest film that does
+    sd_full, _ = workload(args)
     per_step = max(2.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
-    res = int(min(1024, max(64, (rate * per_step) ** 0.5)) // 32 * 32)
-    sd = factory(res)
+    aspect = sd_full.height / sd_full.width
+    res = int(min(sd_full.width, max(64, (rate * per_step / aspect) ** 0.5)) // 32 * 32)
+    sd = sd_full if res >= sd_full.width // 32 * 32 else factory(res)
     res_n = sd.width * sd.height
     o = oracle_py.Oracle(sd, flavor)
     o.set_options(opts)
@@ -205,12 +216,13 @@ def run_reference(args):
     total = o.run(args.steps, threads=threads) - before
     wall = time.time() - t0
     value = res_n * args.steps / total / 1e6
-    sd_full, desc = workload(args)
+    _, desc = workload(args)
+    res = f"{sd.width}x{sd.height}"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "sample": f"each step = 1 VCM iteration of the same scene at {res}x{res} on {threads} host threads"},
+            "config": {"workload": desc, "sample": f"each step = 1 VCM iteration of the same scene at {res} on {threads} host threads (pixel grains of 256 handed out dynamically, like the reference's task scheduler)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
-                             "sample": f"{args.steps} iterations at {res}x{res}, liboracle_{flavor}.so (reference headers + our BVH instead of Embree), wall {wall:.1f} s"},
+                             "sample": f"{args.steps} iterations at {res}, liboracle_{flavor}.so (reference headers + our BVH instead of Embree), wall {wall:.1f} s"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -221,7 +233,7 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--workload", default="C3")
     ap.add_argument("--res", type=int, default=0, help="override the film size (debug only; the default is the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
@@ -413,6 +425,41 @@ def main():
             except Exception:
                 traffic = None
         step_ms = sum(v[0] for v in ktimes.values())
+        # SURVEY 8(d) asks for the fractions with AND without the BVH term: one iteration (the first timed index) through the counting build
+        bvh = None
+        try:
+            cnt = GPUVCM(sd, flavor="count", device=local_rank)
+            cnt.options[:] = workload_vcm_options(args)
+            cnt.run(args.warmup)
+            cnt.iterate()
+            cnt._check(cnt.lib.etxb_wait(cnt.h))
+            cc = cnt.counters()
+            cnt.close()
+            it_bvh = bvh_bytes(cc["nodes_visited"], cc["tris_tested"])
+            it_bvh_closest = bvh_bytes(cc["nodes_closest"], cc["tris_closest"])
+            trace_ms = (ktimes.get("trace_closest(light)", (0, 0))[0] + ktimes.get("trace_closest(camera)", (0, 0))[0]) / kt_steps
+            trace_bytes = (kbytes["trace_closest(light)"] + kbytes["trace_closest(camera)"]) / kt_steps
+            bvh = {"n_node_per_iteration": int(cc["nodes_visited"]), "n_tri_per_iteration": int(cc["tris_tested"]),
+                   "n_node_closest_hit_kernel": int(cc["nodes_closest"]), "n_tri_closest_hit_kernel": int(cc["tris_closest"]),
+                   "rays_per_iteration": int(cc["rays_closest"] + cc["rays_shadow"]),
+                   "nodes_per_ray": cc["nodes_visited"] / max(cc["rays_closest"] + cc["rays_shadow"], 1),
+                   "tris_per_ray": cc["tris_tested"] / max(cc["rays_closest"] + cc["rays_shadow"], 1),
+                   "bytes_per_iteration": int(it_bvh),
+                   "step_algorithmic_GBps_without_bvh": total_bytes / elapsed / 1e9,
+                   "step_algorithmic_GBps_with_bvh": (total_bytes + it_bvh * args.steps * (world if not tile_mode else 1)) / elapsed / 1e9,
+                   "trace_closest_GBps_without_bvh": trace_bytes / max(trace_ms * 1e-3, 1e-12) / 1e9,
+                   "trace_closest_GBps_with_bvh": (trace_bytes + it_bvh_closest) / max(trace_ms * 1e-3, 1e-12) / 1e9}
+            bvh["step_frac_without_bvh"] = bvh["step_algorithmic_GBps_without_bvh"] / peak
+            bvh["step_frac_with_bvh"] = bvh["step_algorithmic_GBps_with_bvh"] / peak
+            bvh["trace_closest_frac_with_bvh"] = bvh["trace_closest_GBps_with_bvh"] / peak
+        except Exception as e:  # the counting build is an extra; the headline does not depend on it
+            bvh = {"unavailable": str(e)[:200]}
+        # the ceilings that actually bind (L2 bandwidth, issue slots, lanes per instruction) come from the committed ncu summaries
+        ncu = None
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(args.workload)
+        except Exception:
+            ncu = None
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s",
                     "bytes_per_launch": dom_bytes / max(dom_launches, 1), "launches": dom_launches, "avg_launch_ms": dom_ms / max(dom_launches, 1),
@@ -421,6 +468,7 @@ def main():
                     "timing_pass": f"{kt_steps} iterations, one at a time on one context (events bracket single kernels); the headline value uses {lanes} iterations in flight",
                     "kernel_ms_per_iteration": {k: round(v[0] / kt_steps, 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0]) if v[1]},
                     "kernel_GBps": {k: round(kbytes[k] / max(ktimes[k][0] * 1e-3, 1e-12) / 1e9, 1) for k in kbytes if ktimes.get(k, (0, 0))[0] > 0},
+                    "bvh": bvh, "ncu": ncu,
                     "note": "algorithmic bytes = device event counters x SURVEY.md 8(d) byte costs of the units THAT kernel processes, BVH node/triangle traffic excluded; "
                             "`traffic` = ncu dram read+write of one head-of-pass launch of the kernel (profiles/ncu_traffic.json).  The photon gather is served from L2 "
                             "(82 % hit rate) and the bounce kernels are latency / FP32 bound, so these fractions of the HBM copy peak are not DRAM utilisation"}
@@ -437,6 +485,8 @@ def main():
                            "timing": ("barrier-to-barrier wall clock, max over ranks" if tile_mode else
                                       "span from the first enqueue (all lanes idle, device synchronised) to the last lane's end-of-iteration stream synchronise, max over ranks"),
                            "l2": "inputs larger than L2 (path state + light-vertex pool + photon grid > 126 MB)",
+                           "iterations": f"a fixed index set: {args.warmup} warm-up iterations (indices 0..{args.warmup - 1}), then the timed indices "
+                                         f"{args.warmup}..{args.warmup + args.steps - 1} of the 1/(1 + i/256) merge-radius schedule (the most expensive end of a render)",
                            "light_vertices_per_iteration": st1["light_vertices"], "per_kernel_event_timing": True},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(counters["kernel_launches"]), "clocks": clk,
                 "counters": counters}

@@ -2,6 +2,7 @@
 
   libetx_b200.so         product build ("fast": FMA contraction, CUDA math library)
   libetx_b200_parity.so  strict-IEEE build (-fmad=false, portable transcendentals) used by the bit-exact parity tests
+  libetx_b200_count.so   product build + traversal counters (bench.py roofline pass)
 """
 import os
 import subprocess
@@ -15,7 +16,14 @@ HEADERS = ["bvh.h", "bvh_build.h", "dcore.cuh", "dscene.cuh", "dimage.cuh", "dbs
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets"]
 FLAVORS = {
-    "fast": (os.path.join(HERE, "libetx_b200.so"), []),
+    # product build: approximate division / square root (div.approx 2 ulp, no slow-path subroutine at each of the ~500 division sites of a
+    # BSDF kernel), flush-to-zero; transcendentals are the special-function unit's (dcore.cuh)
+    "fast": (os.path.join(HERE, "libetx_b200.so"), ["-prec-div=false", "-prec-sqrt=false", "-ftz=true"]),
+    # "fast" + per-ray node / triangle counters in every traversal (bench.py's roofline pass reads n_node / n_tri from it: SURVEY 8(d) wants the
+    # algorithmic bytes with and without the BVH term; the counters cost registers, so the timed build does not carry them)
+    "count": (os.path.join(HERE, "libetx_b200_count.so"), ["-prec-div=false", "-prec-sqrt=false", "-ftz=true", "-DETXB_COUNT_TRAVERSAL=1"]),
+    # A/B partner of "fast": round 1's arithmetic (IEEE division / sqrt, CUDA math library)
+    "fast_precise": (os.path.join(HERE, "libetx_b200_precise.so"), ["-DETXB_PRECISE_MATH=1"]),
     "parity": (os.path.join(HERE, "libetx_b200_parity.so"), ["-fmad=false", "-DETXB_PARITY=1"]),
 }
 
@@ -32,7 +40,7 @@ def _stale(out):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(flavors=("fast", "parity"), force=False, verbose=False, extra=()):
+def build(flavors=("fast", "parity", "count"), force=False, verbose=False, extra=()):
     procs = []
     for fl in flavors:
         out, flags = FLAVORS[fl]
@@ -53,5 +61,6 @@ def build(flavors=("fast", "parity"), force=False, verbose=False, extra=()):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print("built", [lib_path(f) for f in FLAVORS])
+    which = tuple(a for a in sys.argv[1:] if a in FLAVORS) or ("fast", "parity", "count")
+    build(which, force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built", [lib_path(f) for f in which])

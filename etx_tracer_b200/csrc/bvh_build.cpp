@@ -46,6 +46,7 @@ struct Builder {
 
   std::vector<BvhNode> nodes;
   std::vector<uint32_t> leaf_tris;  // slot -> original triangle index
+  uint32_t max_depth = 0;           // deepest inner node (root = 1): what the traversal stack must hold
 
   static constexpr int kBins = 16;
 
@@ -62,7 +63,8 @@ struct Builder {
   }
 
   // returns child reference; writes bounds of the subtree into `bounds`
-  int32_t build(uint32_t begin, uint32_t end, Box& bounds, bool force_inner) {
+  int32_t build(uint32_t begin, uint32_t end, Box& bounds, bool force_inner, uint32_t depth = 1) {
+    max_depth = std::max(max_depth, depth);
     bounds = Box();
     Box cbox;
     for (uint32_t i = begin; i < end; ++i) {
@@ -76,7 +78,18 @@ struct Builder {
 
     uint32_t mid = begin;
     bool split_found = false;
-    if (count > 1u) {
+    // The traversal keeps at most one stack entry per level (kBvhStackSize).  SAH splits of clustered input can peel off a few triangles
+    // per level without bound; once the levels left would not fit a median-split subtree of this range any more, the range is halved in
+    // its current order instead (never reached by the scenes of the BASELINE configs: their trees are 30-40 levels deep).
+    uint32_t levels_needed = 1;
+    while ((1ull << levels_needed) < count) levels_needed++;
+    const bool depth_limited = depth + levels_needed + 2u >= uint32_t(kBvhStackSize);
+    if ((count > 1u) && depth_limited) {
+      if ((count > uint32_t(kBvhMaxLeafTris)) || force_inner) {
+        mid = begin + count / 2u;
+        split_found = true;
+      }
+    } else if (count > 1u) {
       float best_cost = std::numeric_limits<float>::max();
       int best_axis = -1, best_bin = -1;
       for (int axis = 0; axis < 3; ++axis) {
@@ -159,8 +172,8 @@ struct Builder {
     uint32_t node_index = uint32_t(nodes.size());
     nodes.emplace_back();
     Box b0, b1;
-    int32_t c0 = build(begin, mid, b0, false);
-    int32_t c1 = build(mid, end, b1, false);
+    int32_t c0 = build(begin, mid, b0, false, depth + 1u);
+    int32_t c1 = build(mid, end, b1, false, depth + 1u);
     BvhNode n = {};
     std::memcpy(n.lo0, b0.lo, 12);
     std::memcpy(n.hi0, b0.hi, 12);
@@ -198,6 +211,7 @@ void build_bvh(const float* positions, uint32_t position_stride_bytes, const uin
     out.nodes.push_back(n);
     out.tri_pos.resize(3, F4{0, 0, 0, 0});
     out.tri_index.push_back(0xffffffffu);
+    out.max_depth = 1;
     return;
   }
 
@@ -217,6 +231,7 @@ void build_bvh(const float* positions, uint32_t position_stride_bytes, const uin
   Box root_box;
   b.build(0, tri_count, root_box, true);
 
+  out.max_depth = b.max_depth;
   out.nodes = std::move(b.nodes);
   out.tri_index = std::move(b.leaf_tris);
   out.tri_pos.resize(out.tri_index.size() * 3);

@@ -10,6 +10,7 @@ struct Bvh {
   std::vector<BvhNode> nodes;       // nodes[0] is the root and always an inner node
   std::vector<F4> tri_pos;          // 3 entries per leaf slot
   std::vector<uint32_t> tri_index;  // leaf slot -> original triangle index
+  uint32_t max_depth = 0;           // levels of inner nodes; build_bvh keeps it below kBvhStackSize (median splits once SAH would exceed it)
 };
 
 // positions: first 3 floats of each vertex record; indices: first 3 uint32 of each triangle record

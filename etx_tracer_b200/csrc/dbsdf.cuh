@@ -119,6 +119,19 @@ DEV RsRp fresnel_transmittance(Cx ni, Cx ci, Cx nj, Cx cj) {
   return {ts, tp};
 }
 DEVN float fresnel_generic(float cos_theta_i, Cx ext_ior, Cx int_ior) {
+#if !(defined(ETXB_PARITY) && ETXB_PARITY)
+  if ((ext_ior.im == 0.0f) && (int_ior.im == 0.0f)) {
+    // two dielectrics: the same Fresnel equations in real arithmetic (total internal reflection = the complex cosine turning imaginary)
+    const float q = __fdividef(ext_ior.re, int_ior.re);
+    const float sin2_o = q * q * (1.0f - cos_theta_i * cos_theta_i);
+    if (sin2_o >= 1.0f) return 1.0f;
+    const float cos_o = sqrtf(1.0f - sin2_o);
+    const float a = ext_ior.re * cos_theta_i, b = int_ior.re * cos_o, c = int_ior.re * cos_theta_i, d = ext_ior.re * cos_o;
+    if ((a + b == 0.0f) || (c + d == 0.0f)) return 1.0f;
+    const float rs = __fdividef(a - b, a + b), rp = __fdividef(c - d, c + d);
+    return 0.5f * (rs * rs + rp * rp);
+  }
+#endif
   Cx q = ext_ior / int_ior;
   Cx sin_theta_o_squared = (q * q) * (1.0f - cos_theta_i * cos_theta_i);
   Cx cos_theta_o = cx_sqrt(1.0f - sin_theta_o_squared);
@@ -231,6 +244,7 @@ struct MicroRay {
       Lambda = -1.0f;
       return;
     }
+#if defined(ETXB_PARITY) && ETXB_PARITY
     const float theta = m_acos(w.z);
     const float cosTheta = w.z;
     const float sinTheta = m_sin(theta);
@@ -241,6 +255,13 @@ struct MicroRay {
     const float alpha_value = sqrtf(cosPhi2 * alpha.x * alpha.x + sinPhi2 * alpha.y * alpha.y);
     const float a = 1.0f / tanTheta / alpha_value;
     Lambda = 0.5f * (-1.0f + ((a > 0) ? 1.0f : -1.0f) * sqrtf(1.0f + 1.0f / (a * a)));
+#else
+    // the same Smith Lambda without the trip through the angle: tan(theta) * alpha(phi) = sqrt((x ax)^2 + (y ay)^2) / z, so
+    // 1 / a^2 = ((x ax)^2 + (y ay)^2) / z^2 and sign(a) = sign(z)
+    const float ax = w.x * alpha.x, ay = w.y * alpha.y;
+    const float inv_a2 = __fdividef(ax * ax + ay * ay, w.z * w.z);
+    Lambda = 0.5f * (-1.0f + copysignf(sqrtf(1.0f + inv_a2), w.z));
+#endif
   }
   DEV void update_height(float in_h) {
     h = in_h;
@@ -284,17 +305,9 @@ DEV float d_ggx(V3 wm, V2 alpha) {
   const float P22 = 1.0f / (kPi * axy * tmp * tmp);
   return P22 / (wm.z * wm.z * wm.z * wm.z);
 }
-DEV V2 sample_p22_11(float theta_i, V2 rnd, V2 alpha) {
+// slopes of the visible normals of a unit-roughness GGX surface seen from (sin_theta_i, 0, cos_theta_i)
+DEV V2 sample_p22_11_cs(float cos_theta_i, float sin_theta_i, V2 rnd) {
   V2 slope = {0.0f, 0.0f};
-  if (theta_i < 0.0001f) {
-    const float r = sqrtf(rnd.x / (1.0f - rnd.x));
-    const float phi = kDoublePi * rnd.y;
-    slope.x = r * m_cos(phi);
-    slope.y = r * m_sin(phi);
-    return slope;
-  }
-  const float sin_theta_i = m_sin(theta_i);
-  const float cos_theta_i = m_cos(theta_i);
   const float tan_theta_i = sin_theta_i / cos_theta_i;
   const float projectedarea = 0.5f * (cos_theta_i + 1.0f);
   if (projectedarea < 0.0001f) return {0.0f, 0.0f};
@@ -318,12 +331,42 @@ DEV V2 sample_p22_11(float theta_i, V2 rnd, V2 alpha) {
   slope.y = S * z * sqrtf(1.0f + slope.x * slope.x);
   return slope;
 }
-// shared head of samplePhaseFunction_{conductor,dielectric} (bsdf_external.hxx:239-266, 413-441): visible micro-normal
-DEV V3 sample_visible_micronormal(V2 slope_rnd, V3 wi, V2 alpha) {
+DEV V2 sample_p22_11(float theta_i, V2 rnd, V2 alpha) {
+  if (theta_i < 0.0001f) {
+    const float r = sqrtf(rnd.x / (1.0f - rnd.x));
+    const float phi = kDoublePi * rnd.y;
+    return {r * m_cos(phi), r * m_sin(phi)};
+  }
+  return sample_p22_11_cs(m_cos(theta_i), m_sin(theta_i), rnd);
+}
+// sampleVNDF / the head of samplePhaseFunction_* (bsdf_external.hxx:177-205, 239-266): a visible micro-normal for the direction wi.
+// Parity build: through acos / atan2 / sin / cos like the reference.  Product build: the stretched direction's own components ARE the
+// cosine and sine of both angles, no transcendental is needed.
+DEV V3 visible_micronormal(V2 rnd, V3 wi, V2 alpha) {
   const V3 wi_11 = normalize(V3{alpha.x * wi.x, alpha.y * wi.y, wi.z});
-  V2 slope_11 = sample_p22_11(m_acos(wi_11.z), slope_rnd, alpha);
+#if defined(ETXB_PARITY) && ETXB_PARITY
+  V2 slope_11 = sample_p22_11(m_acos(wi_11.z), rnd, alpha);
   const float phi = m_atan2(wi_11.y, wi_11.x);
   V2 slope = {m_cos(phi) * slope_11.x - m_sin(phi) * slope_11.y, m_sin(phi) * slope_11.x + m_cos(phi) * slope_11.y};
+#else
+  const float sin_theta = sqrtf(wi_11.x * wi_11.x + wi_11.y * wi_11.y);
+  V2 slope_11;
+  float cos_phi = 1.0f, sin_phi = 0.0f;
+  if ((sin_theta < 0.0001f) && (wi_11.z > 0.0f)) {  // theta_i < 1e-4: the isotropic closed form
+    const float r = sqrtf(rnd.x / (1.0f - rnd.x));
+    float s, c;
+    __sincosf(kDoublePi * rnd.y - kPi, &s, &c);
+    slope_11 = {-r * c, -r * s};
+  } else {
+    slope_11 = sample_p22_11_cs(wi_11.z, sin_theta, rnd);
+  }
+  if (sin_theta > 0.0f) {
+    const float inv = 1.0f / sin_theta;
+    cos_phi = wi_11.x * inv;
+    sin_phi = wi_11.y * inv;
+  }
+  V2 slope = {cos_phi * slope_11.x - sin_phi * slope_11.y, sin_phi * slope_11.x + cos_phi * slope_11.y};
+#endif
   slope.x *= alpha.x;
   slope.y *= alpha.y;
   if ((slope.x != slope.x) || !finitef(slope.x)) {
@@ -331,6 +374,8 @@ DEV V3 sample_visible_micronormal(V2 slope_rnd, V3 wi, V2 alpha) {
   }
   return normalize(V3{-slope.x, -slope.y, 1.0f});
 }
+// shared head of samplePhaseFunction_{conductor,dielectric} (bsdf_external.hxx:239-266, 413-441): visible micro-normal
+DEV V3 sample_visible_micronormal(V2 slope_rnd, V3 wi, V2 alpha) { return visible_micronormal(slope_rnd, wi, alpha); }
 
 template <bool SP>
 DEV Spec<SP> phase_function_reflection(float wavelength, const MicroRay& ray, V3 wo, V2 alpha, const IorSample<SP>& ext_ior, const IorSample<SP>& int_ior,
@@ -523,18 +568,7 @@ DEV float diffuse_pdf(const BData& d, V3 w_o) {
 
 // ---- Diffuse, diffuse_variation 1: Heitz/Dupuy rough diffuse microsurface, a random walk in BOTH sample and evaluate
 // (bsdf_external.hxx:177-205 sampleVNDF, :557-578 samplePhaseFunction_diffuse, :580-629 eval_diffuse, :660-693 sample_diffuse) ----
-DEV V3 sample_vndf(Smp& smp, V3 wi, V2 alpha) {
-  const V3 wi_11 = normalize(V3{alpha.x * wi.x, alpha.y * wi.y, wi.z});
-  V2 slope_11 = sample_p22_11(m_acos(wi_11.z), smp.next_2d(), alpha);
-  const float phi = m_atan2(wi_11.y, wi_11.x);
-  V2 slope = {m_cos(phi) * slope_11.x - m_sin(phi) * slope_11.y, m_sin(phi) * slope_11.x + m_cos(phi) * slope_11.y};
-  slope.x *= alpha.x;
-  slope.y *= alpha.y;
-  if ((slope.x != slope.x) || !finitef(slope.x)) {
-    return (wi.z > 0) ? V3{0.0f, 0.0f, 1.0f} : normalize(V3{wi.x, wi.y, 0.0f});
-  }
-  return normalize(V3{-slope.x, -slope.y, 1.0f});
-}
+DEV V3 sample_vndf(Smp& smp, V3 wi, V2 alpha) { return visible_micronormal(smp.next_2d(), wi, alpha); }
 DEV V3 sample_phase_function_diffuse(Smp& smp, V3 wm) {
   float r1 = 2.0f * smp.next() - 1.0f;
   float r2 = 2.0f * smp.next() - 1.0f;

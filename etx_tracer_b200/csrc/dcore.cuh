@@ -58,7 +58,8 @@ DEVN float m_cosh(float x) { return pm::coshf_(x); }
 DEVN float m_atanh(float x) { return pm::atanhf_(x); }
 DEVN float m_sinh(float x) { return pm::sinhf_(x); }
 DEVN float m_tanh(float x) { return pm::tanhf_(x); }
-#else
+#elif defined(ETXB_PRECISE_MATH)
+// A/B switch: the CUDA math library's full-precision routines (what round 1 shipped)
 DEV float m_sin(float x) { return sinf(x); }
 DEV float m_cos(float x) { return cosf(x); }
 DEV float m_exp(float x) { return expf(x); }
@@ -72,6 +73,28 @@ DEVG_MATH float m_cosh(float x) { return coshf(x); }
 DEVG_MATH float m_atanh(float x) { return atanhf(x); }
 DEVG_MATH float m_sinh(float x) { return sinhf(x); }
 DEVG_MATH float m_tanh(float x) { return tanhf(x); }
+#else
+// Product build: the special-function unit.  sin / cos / exp2 / log2 are single MUFU instructions (2^-21 absolute error on the reduced
+// range); the library routines they replace are 40-150 instructions each and were inlined at ~100 sites of the BSDF code, which made the
+// bounce and gather kernels instruction-fetch bound (profiles/r1b_c3_k_camera_merge_generic_batched.raw.csv: 31 no_instruction stalls per
+// issue).  The estimators stay the reference's; only roundings move, and the product build is held to the statistical parity tests.
+DEV float m_wrap_pi(float x) { return x - kDoublePi * rintf(x * (1.0f / kDoublePi)); }  // [-pi, pi]: where sin.approx / cos.approx are accurate
+DEV float m_sin(float x) { return __sinf(m_wrap_pi(x)); }
+DEV float m_cos(float x) { return __cosf(m_wrap_pi(x)); }
+DEV float m_exp(float x) { return __expf(x); }
+DEV float m_log(float x) { return __logf(x); }
+DEV float m_pow(float x, float y) {
+  // exp2(y * log2(x)) for x >= 0; pow(x, 0) = 1 and pow(0, y > 0) = 0 like powf (0 * -inf would be NaN)
+  return (y == 0.0f) ? 1.0f : ((x <= 0.0f) ? ((y > 0.0f) ? 0.0f : kMaxFloat) : exp2f(y * __log2f(x)));
+}
+DEVG_MATH float m_acos(float x) { return acosf(x); }
+DEVG_MATH float m_asin(float x) { return asinf(x); }
+DEVG_MATH float m_atan(float x) { return atanf(x); }
+DEVG_MATH float m_atan2(float y, float x) { return atan2f(y, x); }
+DEV float m_cosh(float x) { float e = __expf(x); return 0.5f * (e + __fdividef(1.0f, e)); }
+DEVG_MATH float m_atanh(float x) { return atanhf(x); }
+DEV float m_sinh(float x) { float e = __expf(x); return 0.5f * (e - __fdividef(1.0f, e)); }
+DEV float m_tanh(float x) { float e = __expf(2.0f * fminf(fmaxf(x, -40.0f), 40.0f)); return __fdividef(e - 1.0f, e + 1.0f); }
 #endif
 
 DEV float sqr(float t) { return t * t; }

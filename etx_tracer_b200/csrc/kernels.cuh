@@ -44,7 +44,7 @@ struct PathBuffers {
 
 struct DeviceCounters {
   unsigned long long rays_closest, rays_shadow, nodes, tris, bounces_light, bounces_camera, light_vertices, connections, merge_queries, merge_candidates, merge_accepts,
-    splats;
+    splats, nodes_closest, tris_closest;
 };
 
 struct FilmBuffers {
@@ -220,6 +220,10 @@ __global__ void __launch_bounds__(256) k_trace_closest(LaunchParams p, const uin
   counter_add(&p.counters->rays_closest, 1u);
   counter_add(&p.counters->nodes, STATS_NODES);
   counter_add(&p.counters->tris, STATS_TRIS);
+#ifdef ETXB_COUNT_TRAVERSAL
+  counter_add(&p.counters->nodes_closest, STATS_NODES);
+  counter_add(&p.counters->tris_closest, STATS_TRIS);
+#endif
 }
 
 // Film::atomic_add_light_iteration (film.cxx:147-171) of one light-tracing contribution (vcm_cpu.cxx:147-154)

@@ -405,10 +405,10 @@ int run_grid_build(etxb_ctx* ctx, const LightVertexRec* records, uint32_t count)
     // complete_light_vertices -> Film::commit_light_iteration(iteration) (vcm_cpu.cxx:209-211); in a multi-GPU run the
     // host has all-reduced ETXB_BUF_FILM_LIGHT_ITERATION across ranks before this call
     LaunchTimer t(ctx, K_FILM_COMMIT);
-    // the running mean counts the iterations THIS context has accumulated; that is the absolute index unless iterations are interleaved
-    // across contexts (etxb_set_iteration_stride)
-    uint32_t sample_index = (ctx->iteration_stride == 1u) ? ctx->iteration : ctx->completed;
-    k_film_commit_light<<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(p.film, sample_index);
+    // the running mean counts the iterations THIS context has accumulated since etxb_begin (= the absolute index in the reference's flow,
+    // which always starts at 0; after etxb_begin(ctx, k != 0) or with interleaved iterations the absolute index would scale the first
+    // commit by 1/(k+1) against a cleared film)
+    k_film_commit_light<<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(p.film, ctx->completed);
   }
   bool merging = (ctx->options.options & ETXB_VCM_ENABLE_MERGING) && (ctx->options.options & ETXB_VCM_MERGE_VERTICES);
   if (!merging || (count == 0)) return ETXB_OK;
@@ -925,6 +925,27 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   }
 
   // ---- geometry ------------------------------------------------------------------------------------------------------
+  // every index the host builder and the kernels follow is checked here: a malformed scene is an error, not an out-of-bounds read
+  {
+    const auto* tris = static_cast<const etxb_triangle*>(s.triangles.a);
+    for (uint64_t i = 0; i < s.triangles.count; ++i) {
+      const etxb_triangle& t = tris[i];
+      if ((t.i[0] >= s.vertices.count) || (t.i[1] >= s.vertices.count) || (t.i[2] >= s.vertices.count))
+        return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "triangle %llu: vertex index out of range", (unsigned long long)i);
+      if (t.material_index >= s.materials.count) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "triangle %llu: material index %u out of range", (unsigned long long)i, t.material_index);
+    }
+    if (s.triangle_to_emitter.count != s.triangles.count)
+      return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "triangle_to_emitter has %llu entries for %llu triangles", (unsigned long long)s.triangle_to_emitter.count, (unsigned long long)s.triangles.count);
+    const auto* t2e = static_cast<const uint32_t*>(s.triangle_to_emitter.a);
+    for (uint64_t i = 0; i < s.triangle_to_emitter.count; ++i)
+      if ((t2e[i] != ETXB_INVALID_INDEX) && (t2e[i] >= s.emitter_instances.count)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "triangle %llu: emitter index out of range", (unsigned long long)i);
+    for (uint64_t i = 0; i < s.emitter_instances.count; ++i) {
+      if (emitters[i].profile >= s.emitter_profiles.count) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "emitter %llu: profile index out of range", (unsigned long long)i);
+      if ((emitters[i].cls == 0u) && (emitters[i].triangle_index >= s.triangles.count)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "area emitter %llu: triangle index out of range", (unsigned long long)i);
+    }
+    if (s.emitters_distribution.values.count < s.emitter_instances.count + 1u)
+      return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "emitter distribution has %llu entries for %llu emitters", (unsigned long long)s.emitters_distribution.values.count, (unsigned long long)s.emitter_instances.count);
+  }
   const auto* verts = static_cast<const etxb_vertex*>(s.vertices.a);
   std::vector<DVertex> dverts(s.vertices.count);
   for (uint64_t i = 0; i < s.vertices.count; ++i) {
@@ -944,6 +965,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
       uint32_t(s.triangles.count), bvh);
     ctx->bvh_build_seconds = double(std::clock() - t0) / CLOCKS_PER_SEC;
   }
+  if (bvh.max_depth >= uint32_t(kBvhStackSize)) return fail(ctx, ETXB_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack (%d)", bvh.max_depth, kBvhStackSize);
   if (int rc = upload(ctx, ctx->vertices, dverts.data(), dverts.size())) return rc;
   if (int rc = upload(ctx, ctx->triangles, reinterpret_cast<const DTriangle*>(s.triangles.a), size_t(s.triangles.count))) return rc;
   if (int rc = upload(ctx, ctx->tri_emitter, static_cast<const uint32_t*>(s.triangle_to_emitter.a), size_t(s.triangle_to_emitter.count))) return rc;
@@ -1037,16 +1059,18 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
     ctx->shadow_value.release();
     ctx->shadow_result.release();
   }
+  // the sort buffers also hold the gather queue and the path queues (up to one entry per path), whatever the configured pool capacity
+  const uint64_t sort_cap = std::max<uint64_t>(cap, n);
   DevBuf<uint32_t>* per_vertex_u32[] = {&ctx->keys_in, &ctx->keys_out, &ctx->vals_in, &ctx->vals_out};
-  for (auto* b : per_vertex_u32) CUDA_OK(ctx, b->alloc(cap));
+  for (auto* b : per_vertex_u32) CUDA_OK(ctx, b->alloc(sort_cap));
   DevBuf<float4>* per_vertex_f4[] = {&ctx->g_pos, &ctx->g_nrm, &ctx->g_win, &ctx->g_thr};
   for (auto* b : per_vertex_f4) CUDA_OK(ctx, b->alloc(cap));
   CUDA_OK(ctx, ctx->cell_range.alloc(next_pow2(cap)));
   // one scratch buffer for every CUB call of an iteration: the 32-bit pair sorts (photon grid, gather queue, path queues), the pair-list
   // sort with its 64-bit (path, light vertex) values, and the scan over the per-path vertex counts
   size_t temp_sort = 0, temp_sort64 = 0, temp_scan = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, temp_sort, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, int(cap));
-  cub::DeviceRadixSort::SortPairs(nullptr, temp_sort64, (uint32_t*)nullptr, (uint32_t*)nullptr, (unsigned long long*)nullptr, (unsigned long long*)nullptr, int(cap), 0, 16);
+  cub::DeviceRadixSort::SortPairs(nullptr, temp_sort, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, int(sort_cap));
+  cub::DeviceRadixSort::SortPairs(nullptr, temp_sort64, (uint32_t*)nullptr, (uint32_t*)nullptr, (unsigned long long*)nullptr, (unsigned long long*)nullptr, int(sort_cap), 0, 16);
   cub::DeviceScan::ExclusiveSum(nullptr, temp_scan, (uint32_t*)nullptr, (uint32_t*)nullptr, int(n));
   CUDA_OK(ctx, ctx->cub_temp.alloc(std::max(std::max(temp_sort, temp_sort64), temp_scan) + 256));
   CUDA_OK(ctx, cudaMemsetAsync(ctx->overflow.ptr, 0, 4, ctx->stream));
@@ -1256,6 +1280,8 @@ int etxb_get_counters(etxb_ctx* ctx, etxb_counters* out) {
   out->merge_accepts = c.merge_accepts;
   out->splats = c.splats;
   out->kernel_launches = ctx->kernel_launches;
+  out->nodes_closest = c.nodes_closest;
+  out->tris_closest = c.tris_closest;
   return ETXB_OK;
 }
 

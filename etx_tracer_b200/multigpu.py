@@ -129,9 +129,20 @@ class ShardedVCM:
         """Sum the (disjoint) camera tiles on rank 0; returns the Result layer there, None elsewhere."""
         torch, dist, g = self.torch, self.dist, self.g
         ptr, nbytes = g.device_pointer(S.BUF_FILM_CAMERA)
-        dist.reduce(self.view(ptr, nbytes), dst=0, op=dist.ReduceOp.SUM)
+        # reduce a COPY: the live film keeps only this rank's own tiles, so a second call (progressive preview) does not double-count
+        live = self.view(ptr, nbytes)
+        total = live.clone()
+        dist.reduce(total, dst=0, op=dist.ReduceOp.SUM)
         self._sync()
-        return g.film(S.FILM_RESULT) if self.rank == 0 else None
+        if self.rank != 0:
+            return None
+        mine = live.clone()
+        live.copy_(total)
+        self._sync()
+        result = g.film(S.FILM_RESULT).copy()
+        live.copy_(mine)
+        self._sync()
+        return result
 
 
 class InterleavedVCM:
@@ -147,6 +158,10 @@ class InterleavedVCM:
         self.device, self.view = device, view
         group.set_stride(world)
 
+    def _sync(self):
+        if str(self.device) != "cpu":
+            self.torch.cuda.current_stream().synchronize()
+
     def begin(self):
         """Integrator::run: clears the film; this rank's first iteration is `rank`."""
         self.g.run(self.rank)
@@ -161,10 +176,15 @@ class InterleavedVCM:
         """Mean over all iterations finished so far, on rank 0 (a float4 [pixels, 4] tensor); None elsewhere.
         Camera / Light layers are linear in the per-rank means; Result = max(0, camera + light) is reduced as the sum of those two."""
         torch, dist = self.torch, self.dist
-        ptr, nbytes, done = self.g.combined(S.FILM_CAMERA)
+        # both layers come back in the group's ONE combine buffer, filled on a lane's (non-blocking) stream: each copy must have finished on
+        # torch's stream before the next combine may overwrite the buffer
+        ptr, nbytes, done_cam = self.g.combined(S.FILM_CAMERA)
         cam = self.view(ptr, nbytes).clone()
+        self._sync()
         ptr, nbytes, done = self.g.combined(S.FILM_LIGHT)
         light = self.view(ptr, nbytes).clone()
+        self._sync()
+        done = min(done, done_cam)
         counts = torch.tensor([float(done)], dtype=torch.float64, device=self.device)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
         total = float(counts.item())

@@ -99,7 +99,7 @@ STATUS = np.dtype([
 ])
 COUNTERS = np.dtype([(n, u8) for n in (
     "rays_closest", "rays_shadow", "nodes_visited", "tris_tested", "bounces_light", "bounces_camera", "light_vertices",
-    "connections", "merge_queries", "merge_candidates", "merge_accepts", "splats", "kernel_launches")])
+    "connections", "merge_queries", "merge_candidates", "merge_accepts", "splats", "kernel_launches", "nodes_closest", "tris_closest")])
 DEVICE_CONFIG = np.dtype([("device_index", np.int32), ("max_light_vertices", u4), ("flags", u4), ("pad", u4)])
 
 EXPECTED_SIZES = {

@@ -248,11 +248,13 @@ typedef struct etxb_counters {
   uint64_t merge_accepts;
   uint64_t splats;
   uint64_t kernel_launches; /* kernels of this module launched */
+  uint64_t nodes_closest;   /* the part of nodes_visited / tris_tested spent by the closest-hit kernel (k_trace_closest) */
+  uint64_t tris_closest;
 } etxb_counters;
 
 typedef struct etxb_device_config {
   int32_t device_index;        /* CUDA device ordinal */
-  uint32_t max_light_vertices; /* pool capacity; 0 => 8 per pixel */
+  uint32_t max_light_vertices; /* pool capacity; 0 => 16 per pixel */
   uint32_t flags;              /* reserved */
   uint32_t pad;
 } etxb_device_config;

@@ -465,18 +465,28 @@ void build_grid(Oracle& o) {
   data.throughput_rgb_div_pdf = make_array_view<float3>(o.g_throughput.data(), o.g_throughput.size());
 }
 
+// The reference hands pixel ranges to its workers dynamically (enkiTS task sets, render/host/tasks.cxx:57-66,91-96).  Same here: grains of
+// kGrain pixels, pulled from a shared counter by `threads` workers, so that an expensive image region does not leave the other threads idle.
+// fn(begin, end, grain index, thread index).
+constexpr uint32_t kGrain = 256u;
+inline uint32_t grain_count(uint32_t count, uint32_t threads) { return (threads <= 1) ? 1u : (count + kGrain - 1u) / kGrain; }
 template <class F>
 void parallel_ranges(uint32_t count, uint32_t threads, F&& fn) {
   if (threads <= 1) {
-    fn(0u, count, 0u);
+    fn(0u, count, 0u, 0u);
     return;
   }
+  const uint32_t grains = grain_count(count, threads);
+  std::atomic<uint32_t> next{0u};
   std::vector<std::thread> pool;
-  uint32_t chunk = (count + threads - 1u) / threads;
   for (uint32_t t = 0; t < threads; ++t) {
-    uint32_t b = std::min(count, t * chunk), e = std::min(count, b + chunk);
-    pool.emplace_back([&fn, b, e, t]() {
-      fn(b, e, t);
+    pool.emplace_back([&fn, &next, grains, count, t]() {
+      for (;;) {
+        uint32_t g = next.fetch_add(1u, std::memory_order_relaxed);
+        if (g >= grains) break;
+        uint32_t b = g * kGrain, e = std::min(count, b + kGrain);
+        fn(b, e, g, t);
+      }
     });
   }
   for (auto& th : pool)
@@ -512,10 +522,11 @@ void run_iteration(Oracle& o, uint32_t threads) {
 
   // gather_light_vertices (:126-172); thread-local vectors are appended in thread order so that the vertex
   // pool is path-major regardless of the thread count
-  std::vector<std::vector<VCMLightVertex>> local_vertices(std::max(1u, threads));
+  const uint32_t grains = grain_count(pixel_count, threads);
+  std::vector<std::vector<VCMLightVertex>> local_vertices(grains);  // per grain: appended in grain order below = path-major, whatever the thread count
   std::vector<uint64_t> local_bounces(std::max(1u, threads), 0), local_splats(std::max(1u, threads), 0);
-  parallel_ranges(pixel_count, threads, [&](uint32_t begin, uint32_t end, uint32_t tid) {
-    auto& verts = local_vertices[tid];
+  parallel_ranges(pixel_count, threads, [&](uint32_t begin, uint32_t end, uint32_t grain, uint32_t tid) {
+    auto& verts = local_vertices[grain];
     verts.reserve(4llu * (end - begin));
     for (uint32_t i = begin; i < end; ++i) {
       VCMPathState state = vcm_generate_emitter_state(i, scene, it);
@@ -546,13 +557,15 @@ void run_iteration(Oracle& o, uint32_t threads) {
     flush_thread_counters(o.counters);
   });
   {
-    uint32_t chunk = (threads <= 1) ? pixel_count : (pixel_count + threads - 1u) / threads;
-    for (uint32_t t = 0; t < local_vertices.size(); ++t) {
+    const uint32_t chunk = (threads <= 1) ? pixel_count : kGrain;
+    for (uint32_t g = 0; g < local_vertices.size(); ++g) {
       uint32_t base = static_cast<uint32_t>(o.light_vertices.size());
-      uint32_t b = std::min(pixel_count, t * chunk), e = std::min(pixel_count, b + chunk);
+      uint32_t b = std::min(pixel_count, g * chunk), e = std::min(pixel_count, b + chunk);
       for (uint32_t i = b; i < e; ++i)
         o.light_paths[i].index += base;
-      o.light_vertices.insert(o.light_vertices.end(), local_vertices[t].begin(), local_vertices[t].end());
+      o.light_vertices.insert(o.light_vertices.end(), local_vertices[g].begin(), local_vertices[g].end());
+    }
+    for (uint32_t t = 0; t < local_bounces.size(); ++t) {
       o.stat_bounces_light += local_bounces[t];
       o.stat_splats += local_splats[t];
     }
@@ -570,7 +583,7 @@ void run_iteration(Oracle& o, uint32_t threads) {
   auto light_vertices = make_array_view<VCMLightVertex>(o.light_vertices.data(), o.light_vertices.size());
   auto light_paths = make_array_view<VCMLightPath>(o.light_paths.data(), o.light_paths.size());
   std::vector<uint64_t> cam_bounces(std::max(1u, threads), 0);
-  parallel_ranges(pixel_count, threads, [&](uint32_t begin, uint32_t end, uint32_t tid) {
+  parallel_ranges(pixel_count, threads, [&](uint32_t begin, uint32_t end, uint32_t, uint32_t tid) {
     for (uint32_t pi = begin; pi < end; ++pi) {
       uint2 pixel = {pi % o.width, pi / o.width};  // Film::active_pixel with pixel_size == 1 (film.cxx:434-461)
       const auto& light_path = o.light_paths[pi];

@@ -349,15 +349,16 @@ def test_config5_cloud_is_bit_exact_connect_only(api, oracle_mod):
 
 
 def test_reference_loaded_cornell_asset_is_bit_exact(api, oracle_mod):
-    """Where the reference tree AND a GPU exist (a developer machine; skipped on the GPU box, which has no /root/reference): the Scene / Camera
-    PODs built by the reference's own loader from its shipped Cornell asset (fog volume behind a 137k-triangle Boundary mesh, sun + sky,
-    conductor box) go unchanged into etxb_upload_scene and into the oracle."""
-    if not oracle_mod.ReferenceScene.available():
-        pytest.skip("reference tree not present")
-    rs = oracle_mod.ReferenceScene("assets/cornellbox/cornellbox.json")
-    rs.resize(40, 40, [0.0, 1.000000238418579, 3.819999933242798], [0.0, 1.000000238418579, -6.179999351501465], [0.0, 0.9999999403953552, -0.0], 39.597755335771296)
-    _compare_with_oracle(api, oracle_mod, rs, 2, fast_tolerance=0.3)
-    rs.close()
+    """The Scene / Camera PODs built by the reference's OWN loader from its shipped Cornell asset (fog volume behind a 137k-triangle
+    Boundary mesh, sun + sky, conductor box), committed as a byte dump (tests/golden/ref_cornell_40.npz, tools/dump_reference_scene.py;
+    tests/test_reference_loader.py checks the dump against the live loader where the reference tree exists), go unchanged into
+    etxb_upload_scene and into the oracle."""
+    import os
+    from conftest import GOLDEN
+    from etx_tracer_b200 import pod_io
+    sd = pod_io.load(os.path.join(GOLDEN, "ref_cornell_40.npz"))
+    assert sd.triangle_count == 138318 and (sd.width, sd.height) == (40, 40)
+    _compare_with_oracle(api, oracle_mod, sd, 2, fast_tolerance=0.3)
 
 
 @pytest.mark.parametrize("lanes", [2, 3])

@@ -118,3 +118,27 @@ def test_named_ior_convention_matches_the_loader(cornell):
     for part in ("eta_index", "k_index"):
         a, b = spectra[int(ref["int_ior"][part])], np.asarray(sd.spectra[int(mine["int_ior"][part])])
         assert bytes(a.tobytes()) == bytes(b.tobytes()), part
+
+
+def test_committed_pod_dump_is_what_the_loader_builds(oracle_mod):
+    """tests/golden/ref_cornell_40.npz (tools/dump_reference_scene.py) is the loader's Scene / Camera byte for byte: the oracle renders the
+    dump and the live PODs to the same bits (film, sampler states).  The GPU box has only the dump."""
+    import os
+    from conftest import GOLDEN
+    from etx_tracer_b200 import pod_io
+    if not oracle_mod.ReferenceScene.available():
+        pytest.skip("reference tree or oracle/_ref/libreference_loader.so not present")
+    rs = oracle_mod.ReferenceScene("assets/cornellbox/cornellbox.json")
+    rs.resize(40, 40, CAMERA["origin"], CAMERA["target"], CAMERA["up"], CAMERA["fov"])
+    sd = pod_io.load(os.path.join(GOLDEN, "ref_cornell_40.npz"))
+    assert bytes(sd.camera.tobytes()) == bytes(rs.camera.tobytes())
+    out = []
+    for scene in (sd, rs):
+        o = oracle_mod.Oracle(scene)
+        o.begin(0)
+        o.run(1, threads=1)
+        out.append((o.film(S.FILM_CAMERA).copy(), o.film(S.FILM_LIGHT).copy(), o.buffer(S.BUF_CAMERA_SAMPLER, np.uint32), o.buffer(S.BUF_LIGHT_SAMPLER, np.uint32)))
+        o.close()
+    for x, y in zip(*out):
+        assert bit_equal(x, y)
+    rs.close()
