@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["module.cu", "bvh_build.cpp"]
-HEADERS = ["bvh.h", "bvh_build.h", "dcore.cuh", "dscene.cuh", "dimage.cuh", "dbsdf.cuh", "dtrace.cuh", "dmedium.cuh", "dsss.cuh", "dvcm.cuh", "kernels.cuh", "portable_math.h",
+HEADERS = ["bvh.h", "bvh_build.h", "dcore.cuh", "dscene.cuh", "dimage.cuh", "dbsdf.cuh", "dclosure.cuh", "dtrace.cuh", "dmedium.cuh", "dsss.cuh", "dvcm.cuh", "kernels.cuh", "portable_math.h",
            os.path.join("..", "..", "include", "etx_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets"]
@@ -22,6 +22,8 @@ FLAVORS = {
     # "fast" + per-ray node / triangle counters in every traversal (bench.py's roofline pass reads n_node / n_tri from it: SURVEY 8(d) wants the
     # algorithmic bytes with and without the BVH term; the counters cost registers, so the timed build does not carry them)
     "count": (os.path.join(HERE, "libetx_b200_count.so"), ["-prec-div=false", "-prec-sqrt=false", "-ftz=true", "-DETXB_COUNT_TRAVERSAL=1"]),
+    # A/B partner of "fast": the closure gather compiled for 3 resident blocks per SM (168 registers, no spills) instead of 4 (128)
+    "fast_cl3": (os.path.join(HERE, "libetx_b200_cl3.so"), ["-prec-div=false", "-prec-sqrt=false", "-ftz=true", "-DETXB_CLOSURE_MIN_BLOCKS=3"]),
     # A/B partner of "fast": round 1's arithmetic (IEEE division / sqrt, CUDA math library)
     "fast_precise": (os.path.join(HERE, "libetx_b200_precise.so"), ["-DETXB_PRECISE_MATH=1"]),
     "parity": (os.path.join(HERE, "libetx_b200_parity.so"), ["-fmad=false", "-DETXB_PARITY=1"]),

@@ -3,6 +3,7 @@
 // scene_camera.hxx for the device.  One sampler per path; every consumer draws in the oracle's order.
 #pragma once
 #include "dbsdf.cuh"
+#include "dclosure.cuh"
 #include "dtrace.cuh"
 
 namespace etxb {
@@ -617,10 +618,25 @@ DEV bool vcm_connect_to_camera(const DeviceScene& sc, const VcmParams& it, const
     const Isect& isect = *ep.isect;
     const etxb_material& mat = sc.materials[isect.material_index];
     BData data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathLight);
+#if defined(ETXB_PARITY) && ETXB_PARITY
     BEval<SP> eval = bsdf_evaluate<SP>(sc, data, w_o, mat, state.sampler);
     if (eval.valid() == false) return false;
     scatter = eval.bsdf;
     reverse_pdf = bsdf_reverse_pdf<SP>(sc, data, w_o, mat, state.sampler);
+#else
+    if ((mat.cls == ETXB_MAT_DIFFUSE) && (mat.diffuse_variation == 0u)) {
+      BEval<SP> eval = bsdf_evaluate<SP>(sc, data, w_o, mat, state.sampler);
+      if (eval.valid() == false) return false;
+      scatter = eval.bsdf;
+      reverse_pdf = bsdf_reverse_pdf<SP>(sc, data, w_o, mat, state.sampler);
+    } else {  // product build: value and reverse pdf from one prepared closure (dclosure.cuh)
+      Closure<SP> cl = make_closure<SP>(sc, data, isect.material_index, state.sampler);
+      CEval<SP> ce = closure_evaluate<SP>(sc, cl, w_o, state.sampler);
+      if (ce.valid() == false) return false;
+      scatter = ce.bsdf;
+      reverse_pdf = ce.rev_pdf;
+    }
+#endif
     origin = shading_pos(sc, load_triangle(sc, isect.triangle_index), isect.barycentric, w_o);
   } else {
     float p = medium_phase(sc, state.medium_index, state.ray_d, w_o);
@@ -701,6 +717,7 @@ DEV Spec<SP> vcm_connect_to_light(const DeviceScene& sc, const VcmParams& it, co
   float reverse_pdf = 0.0f;
   V3 origin = sample_pos;
   float camera_factor = 1.0f;
+  float closure_pdf = -1.0f;  // product build: the forward pdf that came with the evaluation (the reference asks bsdf::pdf again, :650-653)
   if (ep.at_medium) {
     float p = medium_phase(sc, state.medium_index, state.ray_d, w_o);
     if (p <= 0.0f) return zero;
@@ -710,10 +727,27 @@ DEV Spec<SP> vcm_connect_to_light(const DeviceScene& sc, const VcmParams& it, co
     const Isect& isect = *ep.isect;
     const etxb_material& mat = sc.materials[isect.material_index];
     BData data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
+#if defined(ETXB_PARITY) && ETXB_PARITY
     BEval<SP> eval = bsdf_evaluate<SP>(sc, data, w_o, mat, state.sampler);
     if (eval.valid() == false) return zero;
     scatter = eval.bsdf;
     reverse_pdf = bsdf_reverse_pdf<SP>(sc, data, w_o, mat, state.sampler);
+#else
+    if ((mat.cls == ETXB_MAT_DIFFUSE) && (mat.diffuse_variation == 0u)) {
+      BEval<SP> eval = bsdf_evaluate<SP>(sc, data, w_o, mat, state.sampler);
+      if (eval.valid() == false) return zero;
+      scatter = eval.bsdf;
+      reverse_pdf = bsdf_reverse_pdf<SP>(sc, data, w_o, mat, state.sampler);
+      closure_pdf = eval.pdf;
+    } else {  // product build: value, pdf and reverse pdf from one prepared closure (dclosure.cuh)
+      Closure<SP> cl = make_closure<SP>(sc, data, isect.material_index, state.sampler);
+      CEval<SP> ce = closure_evaluate<SP>(sc, cl, w_o, state.sampler);
+      if (ce.valid() == false) return zero;
+      scatter = ce.bsdf;
+      reverse_pdf = ce.rev_pdf;
+      closure_pdf = (cl.kind == kClGeneric) ? -1.0f : ce.pdf;  // classes without a closure form answer bsdf::pdf themselves
+    }
+#endif
     TriRec tri = load_triangle(sc, isect.triangle_index);
     origin = shading_pos(sc, tri, isect.barycentric, normalize(es.origin - isect.pos));
     camera_factor = fabsf(dot(w_o, tri.geo_n));
@@ -732,7 +766,7 @@ DEV Spec<SP> vcm_connect_to_light(const DeviceScene& sc, const VcmParams& it, co
     } else {
       const Isect& isect = *ep.isect;
       BData data = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
-      float conn_pdf = bsdf_pdf<SP>(sc, data, w_o, sc.materials[isect.material_index], state.sampler);
+      float conn_pdf = (closure_pdf >= 0.0f) ? closure_pdf : bsdf_pdf<SP>(sc, data, w_o, sc.materials[isect.material_index], state.sampler);
       w_light = conn_pdf / (es.pdf_dir * es.pdf_sample);
     }
   }

@@ -6,11 +6,14 @@
 //   photon map : k_grid_bbox -> k_grid_keys -> radix sort (stable) -> k_grid_build
 //   camera pass: k_camera_begin -> { k_trace_closest -> k_camera_shade -> k_camera_merge -> k_camera_continue }*
 //   film       : k_film_commit_light, k_film_resolve
+// Kernel parameters are `const __grid_constant__`: the out-of-line BSDF / traversal routines take the scene by reference, and without it every
+// thread first copies the whole parameter block to its local-memory stack frame (ncu, round 2: 1.6 KB written per thread of k_camera_connect).
 // Path state lives in HBM as SoA float4/uint4 columns indexed by path id (128-bit coalesced loads/stores);
 // queues are compacted with warp ballot + one atomic per warp.
 #pragma once
 #include "dvcm.cuh"
 #include "dsss.cuh"
+#include "dclosure.cuh"
 
 // resident blocks per SM the bounce / connection kernels are compiled for (128 threads each: 4 blocks = 128 registers per thread).
 // Measured on the B200 (bench.py --lanes 1): 1|1 -> 4|4 gives C2 11.04 -> 11.36 and C3 5.55 -> 5.79 Msamples/s; 2 and 3 change nothing.
@@ -87,6 +90,7 @@ struct LaunchParams {
   uint32_t* shadow_count;        // [0] rays reserved this bounce, [1] work cursor of k_shadow_trace
   uint32_t shadow_capacity;
   uint32_t shadow_stage;         // 1: the scene qualifies (DeviceScene::deferred_shadow_rays) and the buffers exist
+  uint32_t closures;             // 1 (product build): connections and the generic gather evaluate vertex closures (dclosure.cuh); 0: A/B switch
   uint32_t merge_material_major; // 1: the gather queue is ordered by (material, Morton code) instead of the Morton code alone (ETXB_MERGE_MATERIAL_MAJOR=1)
   uint32_t connect_deferred;     // 1 (needs shadow_stage): the camera-vertex x light-vertex connections of such a scene run one per thread in
                                  //    k_camera_connect_deferred — conn_list[slot] names the (path, light vertex) pair that fills shadow slot `slot`
@@ -178,7 +182,7 @@ DEV PathState<SP> load_state(const PathBuffers& b, uint32_t i) {
 // light pass
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool SP>
-__global__ void __launch_bounds__(128) k_light_begin(LaunchParams p, uint32_t* queue, uint32_t* queue_count) {
+__global__ void __launch_bounds__(128) k_light_begin(const __grid_constant__ LaunchParams p, uint32_t* queue, uint32_t* queue_count) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool alive = false;
   if (i < p.path_count) {
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(128) k_light_begin(LaunchParams p, uint32_t* q
 
 // closest-hit traversal for every queued path (Raytracing::trace, rt.cxx:428): SoA ray in, hit record out,
 // sampler advanced by one draw per candidate
-__global__ void __launch_bounds__(256) k_trace_closest(LaunchParams p, const uint32_t* queue, const uint32_t* queue_count, uint32_t* material_keys, uint32_t key_limit) {
+__global__ void __launch_bounds__(256) k_trace_closest(const __grid_constant__ LaunchParams p, const uint32_t* queue, const uint32_t* queue_count, uint32_t* material_keys, uint32_t key_limit) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= *queue_count) {
     // the host sorts `key_limit` (its upper bound of the queue size) slots by material: slots past the device-side count sort last
@@ -268,7 +272,7 @@ enum : uint32_t { kEpNone = 0u, kEpMedium = 1u, kEpSurface = 2u, kEpSubsurface =
 // the segment (medium scattering, boundary crossing, surface hit incl. the subsurface walk), (B) camera connections from the
 // endpoint(s) it produced — one, or every gathered subsurface exit (:1207-1222), (C) the continuation.
 template <bool SP, bool PLAIN>
-__global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_light_bounce(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
+__global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_light_bounce(const __grid_constant__ LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   bool alive = false;
   uint32_t i = 0;
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_light_bounce(La
 }
 
 // pool in allocation order -> path-major order: dst = VCMLightPath::index + ordinal (vcm_cpu.cxx:155-171)
-__global__ void __launch_bounds__(256) k_lv_reorder(LaunchParams p, uint32_t count) {
+__global__ void __launch_bounds__(256) k_lv_reorder(const __grid_constant__ LaunchParams p, uint32_t count) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= count) return;
   const float4* src = reinterpret_cast<const float4*>(p.lv_tmp + s);
@@ -498,7 +502,7 @@ __global__ void __launch_bounds__(256) k_grid_keys(const LightVertexRec* pool, u
 
 // after the stable sort by cell: gather photon SoA (60 B -> 4 x 16 B) and mark [begin,end) per cell
 template <bool SP>
-__global__ void __launch_bounds__(256) k_grid_build(LaunchParams p, const uint32_t* sorted_keys, const uint32_t* sorted_values, uint32_t count, uint2* cell_range,
+__global__ void __launch_bounds__(256) k_grid_build(const __grid_constant__ LaunchParams p, const uint32_t* sorted_keys, const uint32_t* sorted_values, uint32_t count, uint2* cell_range,
   float4* pos_dvcm, float4* nrm_dvm, float4* win_len, float4* thr_rgb) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= count) return;
@@ -523,7 +527,7 @@ __global__ void __launch_bounds__(256) k_grid_build(LaunchParams p, const uint32
 // camera pass
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool SP>
-__global__ void __launch_bounds__(128) k_camera_begin(LaunchParams p, uint32_t* queue, uint32_t* queue_count) {
+__global__ void __launch_bounds__(128) k_camera_begin(const __grid_constant__ LaunchParams p, uint32_t* queue, uint32_t* queue_count) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool alive = false;
   if (i < p.path_count) {
@@ -612,7 +616,7 @@ DEV void camera_emit_connections(const LaunchParams& p, uint32_t i, uint32_t cam
 // the paired light path and to a sampled emitter from the endpoint(s) the event produced (one, or every gathered subsurface exit,
 // :1037-1053), (C) the MIS update / pending continuation sample handed to the merge and continue stages.
 template <bool SP, bool PLAIN>
-__global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in) {
+__global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(const __grid_constant__ LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t shadow_rays = 0, connections = 0;
   uint32_t merge_key = 0xffffffffu;
@@ -815,11 +819,67 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(La
   counter_add(&p.counters->tris, STATS_TRIS);
 }
 
+// vcm_connect_to_light_vertex (vcm_shared.hxx:673-763) on vertex closures: both end points are prepared once and each closure_evaluate returns
+// value, pdf and reverse pdf together (the generic routine re-derives IORs / thin film / tints from the Material record in each of its four
+// evaluate / reverse_pdf calls).  Surface camera vertices only; the light vertex may be a medium vertex.
+template <bool SP>
+DEV bool vcm_connect_to_light_vertex_closure(const DeviceScene& sc, const VcmParams& it, PathState<SP>& state, const LightVertexRec& lv, const Isect& cam, V3& target_position,
+  Spec<SP>& value) {
+  const uint32_t lv_tri = __float_as_uint(lv.pos_tri.w);
+  const bool lv_is_medium = lv_tri == kInvalidIndex;
+  const V3 lv_wi = {lv.wi_dvc.x, lv.wi_dvc.y, lv.wi_dvc.z};
+  Isect light_v = {};
+  TriRec light_tri = {};
+  if (lv_is_medium == false) {
+    light_tri = load_triangle(sc, lv_tri);
+    V3 bc = {lv.bc_dvm.x, lv.bc_dvm.y, lv.bc_dvm.z};
+    lerp_vertex(sc, light_tri, bc, light_v.pos, light_v.nrm, light_v.tan, light_v.btn, light_v.tex);
+  }
+  target_position = lv_is_medium ? V3{lv.pos_tri.x, lv.pos_tri.y, lv.pos_tri.z} : light_v.pos;
+  V3 w_o = target_position - cam.pos;
+  float distance_squared = dot(w_o, w_o);
+  if (distance_squared <= kEpsilon) return false;
+  w_o /= sqrtf(distance_squared);
+  float w_dot_l = 1.0f;
+  if (lv_is_medium == false) w_dot_l = -dot(light_v.nrm, w_o);
+
+  BData camera_data = make_bdata(cam, cam.w_i, state.wavelength, state.medium_index, kPathCamera);
+  Closure<SP> cc = make_closure<SP>(sc, camera_data, cam.material_index, state.sampler);
+  CEval<SP> ce = closure_evaluate<SP>(sc, cc, w_o, state.sampler);
+  if (ce.valid() == false) return false;
+  const float camera_area_pdf = ce.pdf * fabsf(w_dot_l) / distance_squared;
+
+  float light_area_pdf = 0.0f, light_rev_pdf = 0.0f;
+  Spec<SP> light_scatter = Spec<SP>::make(0.0f);
+  if (lv_is_medium) {
+    float pf = medium_phase(sc, lv.ids.x, lv_wi, -w_o);
+    if (pf <= 0.0f) return false;
+    light_area_pdf = pf * fabsf(dot(cam.nrm, w_o)) / distance_squared;
+    light_rev_pdf = medium_phase(sc, lv.ids.x, -w_o, lv_wi);
+    light_scatter = Spec<SP>::make(pf);
+  } else {
+    BData light_data = {light_v.pos, light_v.nrm, light_v.tan, light_v.btn, light_v.tex, lv_wi, state.wavelength, kPathLight, state.medium_index};
+    Closure<SP> lc = make_closure<SP>(sc, light_data, __float_as_uint(lv.nrm_mat.w), state.sampler);
+    CEval<SP> le = closure_evaluate<SP>(sc, lc, -w_o, state.sampler);
+    if (le.valid() == false) return false;
+    light_area_pdf = le.pdf * fabsf(dot(cam.nrm, w_o)) / distance_squared;
+    light_rev_pdf = le.rev_pdf;
+    light_scatter = le.bsdf * fix_shading_normal(light_tri.geo_n, light_data.nrm, light_data.w_i, -w_o);
+  }
+  float vmW_pair = lv_is_medium ? 0.0f : it.vm_weight;
+  float w_light = camera_area_pdf * (vmW_pair + lv.thr_dvcm.w + lv.wi_dvc.w * light_rev_pdf);
+  float w_camera = light_area_pdf * (vmW_pair + state.d_vcm + state.d_vc * ce.rev_pdf);
+  float weight = it.enable_mis() ? 1.0f / (1.0f + w_light + w_camera) : 1.0f;
+  Spec<SP> lv_throughput = Spec<SP>::make3({lv.thr_dvcm.x, lv.thr_dvcm.y, lv.thr_dvcm.z});
+  value = (ce.bsdf * state.throughput) * (light_scatter * lv_throughput) * (weight / distance_squared);
+  return true;
+}
+
 // Product build: one thread per (camera vertex, light vertex) connection — vcm_connect_to_light_vertex + the shadow ray of
 // vcm_connect_to_light_path (vcm_shared.hxx:673-803).  Each connection draws from its own stream derived from the path's sampler
 // (the reference shares one stream across the serial loop; the parity build keeps that order inside k_camera_shade).
 template <bool SP, bool PLAIN>
-__global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect(LaunchParams p, const uint2* conn_list) {
+__global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect(const __grid_constant__ LaunchParams p, const uint2* conn_list) {
   uint32_t shadow_rays = 0;
   STATS_DECL;
   const DeviceScene& sc = p.scene;
@@ -838,7 +898,13 @@ __global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect
     Endpoint ep{false, &isect, {0.0f, 0.0f, 0.0f}};
     V3 target_position;
     Spec<SP> value;
-    if (vcm_connect_to_light_vertex<SP>(sc, p.vcm, state, lv, ep, target_position, value)) {
+#if defined(ETXB_PARITY) && ETXB_PARITY
+    const bool connected = vcm_connect_to_light_vertex<SP>(sc, p.vcm, state, lv, ep, target_position, value);
+#else
+    const bool connected = p.closures ? vcm_connect_to_light_vertex_closure<SP>(sc, p.vcm, state, lv, isect, target_position, value)
+                                      : vcm_connect_to_light_vertex<SP>(sc, p.vcm, state, lv, ep, target_position, value);
+#endif
+    if (connected) {
       shadow_rays += 1;
       Spec<SP> tr = vcm_connection_transmittance<SP, PLAIN>(sc, ep, lv, target_position, state, stats);
       if (tr.is_zero() == false) {
@@ -862,7 +928,7 @@ __global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect
 // connection that succeeds writes the slot's segment and unoccluded contribution (k_shadow_trace resolves it, k_camera_continue adds the
 // visible ones in slot order = reference order); one that fails voids the slot.  Same values, same order as the serial loop.
 template <bool SP>
-__global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect_deferred(LaunchParams p) {
+__global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect_deferred(const __grid_constant__ LaunchParams p) {
   const uint32_t total = umin(p.shadow_count[0], p.shadow_capacity);
   const DeviceScene& sc = p.scene;
   uint32_t shadow_rays = 0;
@@ -903,7 +969,7 @@ DEV bool merge_is_lambert(const etxb_material& m) { return (m.cls == ETXB_MAT_DI
 // Serial, reference-ordered gather (VCMSpatialGridData::gather): every merging vertex in the parity build, the non-Lambert
 // ones (stochastic evaluate consuming the path's sampler) in the product build.
 template <bool SP>
-__global__ void __launch_bounds__(128) k_camera_merge_serial(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in) {
+__global__ void __launch_bounds__(128) k_camera_merge_serial(const __grid_constant__ LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceScene& sc = p.scene;
   uint32_t merge_queries = 0, candidates = 0, accepts = 0;
@@ -944,7 +1010,7 @@ constexpr uint32_t kMergeListSize = 64;
 //                  index), and the path's sampler advances by one draw per query — statistically equivalent to the reference's
 //                  serial order (which the parity build keeps), 32x more parallel.
 template <bool SP, bool GENERIC>
-__global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys, const uint32_t* count_in,
+__global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(const __grid_constant__ LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys, const uint32_t* count_in,
                                                                                 uint32_t queries_per_warp) {
   __shared__ uint32_t s_idx[kMergeWarpsPerBlock][kMergeListSize];
   __shared__ float s_d2[kMergeWarpsPerBlock][kMergeListSize];
@@ -1189,7 +1255,7 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_coop(
 // lane fetches ITS query's camera vertex from the owning lane by shuffle, and the contributions meet in per-query shared accumulators.
 // Same pairs, same per-pair streams (path seed x photon index) as the per-query kernel; only the summation order differs.
 template <bool SP>
-__global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_generic_batched(LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys,
+__global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_generic_batched(const __grid_constant__ LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys,
                                                                                            const uint32_t* count_in, uint32_t queries_per_warp) {
   __shared__ uint32_t s_idx[kMergeWarpsPerBlock][kMergeListSize];
   __shared__ float s_d2[kMergeWarpsPerBlock][kMergeListSize];
@@ -1396,6 +1462,204 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_gener
   counter_add(&p.counters->merge_accepts, accepts);
 }
 
+// Product build, scenes with stochastic BSDFs: the generic gather on vertex closures (dclosure.cuh).  Same structure as the batched kernel
+// above — the (query, photon) pairs of a warp's queries go through one shared list, 32 pairs per step whatever query they belong to — but the
+// camera vertex of a query is PREPARED once (material record -> evaluated IORs, thin film, roughness, tints: a Closure in shared memory)
+// instead of being re-derived from the Material inside every evaluate / pdf call of every pair, and one closure_evaluate returns value,
+// pdf and reverse pdf together.  Same pairs and per-pair sampler streams (path seed x photon index) as the batched kernel.
+constexpr uint32_t kClosureWarpsPerBlock = 4;
+#ifndef ETXB_CLOSURE_MIN_BLOCKS
+#define ETXB_CLOSURE_MIN_BLOCKS 4
+#endif
+struct MergeQueryAux {
+  float qc[3];  // t_camera = throughput / pdf(lambda)
+  float wcam_base, dvm;
+  uint32_t depth, seed;
+};
+template <bool SP>
+__global__ void __launch_bounds__(kClosureWarpsPerBlock * 32, ETXB_CLOSURE_MIN_BLOCKS) k_camera_merge_closure(const __grid_constant__ LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys, const uint32_t* count_in,
+                                                                                     uint32_t queries_per_warp) {
+  __shared__ Closure<SP> s_cl[kClosureWarpsPerBlock][32];
+  __shared__ MergeQueryAux s_aux[kClosureWarpsPerBlock][32];
+  __shared__ uint32_t s_idx[kClosureWarpsPerBlock][kMergeListSize];
+  __shared__ float s_d2[kClosureWarpsPerBlock][kMergeListSize];
+  __shared__ float s_dvcm[kClosureWarpsPerBlock][kMergeListSize];
+  __shared__ uint32_t s_src[kClosureWarpsPerBlock][kMergeListSize];
+  __shared__ float s_sum[kClosureWarpsPerBlock][32][3];
+  constexpr uint32_t kFull = 0xffffffffu;
+  const DeviceScene& sc = p.scene;
+  const GridData& g = p.grid;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  uint32_t q = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * queries_per_warp + lane;
+  uint32_t merge_queries = 0, candidates = 0, accepts = 0;
+  bool active = (lane < queries_per_warp) && (q < *count_in) && (sorted_keys[q] != 0xffffffffu);
+  uint32_t i = 0;
+  V3 qpos = {0, 0, 0};
+  if (active) {
+    i = sorted_ids[q];
+    float4 hit = p.paths.hit[i];
+    PathState<SP> state = load_state<SP>(p.paths, i);
+    Isect isect = stage_intersection<SP>(p, state, i, hit);
+    active = !merge_is_lambert(sc.materials[isect.material_index]);
+    if (active) {
+      merge_queries = 1;
+      qpos = isect.pos;
+      MergeQueryAux aux;
+      V3 t_camera = (state.throughput / sampling_pdf<SP>(state.wavelength)).as_v3();
+      aux.qc[0] = t_camera.x;
+      aux.qc[1] = t_camera.y;
+      aux.qc[2] = t_camera.z;
+      aux.wcam_base = state.d_vcm * p.vcm.vc_weight;
+      aux.dvm = state.d_vm;
+      aux.depth = state.total_path_depth;
+      aux.seed = state.sampler.seed;
+      state.sampler.next();  // the path's own stream moves on by one draw per query
+      p.paths.misc[i].x = state.sampler.seed;
+      Smp prep;  // the closure's own stream (RGB thin-film wavelength jitter)
+      prep.seed = aux.seed ^ 0x85ebca6bu;
+      prep.fixed_u = prep.fixed_v = prep.fixed_w = 0.0f;
+      prep.next();
+      BData cam = make_bdata(isect, isect.w_i, state.wavelength, state.medium_index, kPathCamera);
+      s_cl[warp][lane] = make_closure<SP>(sc, cam, isect.material_index, prep);
+      s_aux[warp][lane] = aux;
+    }
+  }
+  s_sum[warp][lane][0] = 0.0f;
+  s_sum[warp][lane][1] = 0.0f;
+  s_sum[warp][lane][2] = 0.0f;
+  __syncwarp();
+  uint32_t pending = __ballot_sync(kFull, active);
+  const bool use_mis = p.vcm.enable_mis();
+  const bool use_epan = (p.vcm.kernel == 1u);
+  const float vc_weight = p.vcm.vc_weight;
+  uint32_t n_list = 0;  // warp-uniform fill of the shared pair list
+
+  auto finish = [&](uint32_t n) {
+    if (lane < n) {
+      const uint32_t j = s_idx[warp][lane], s = s_src[warp][lane];
+      const float distance_squared = s_d2[warp][lane], dvcm = s_dvcm[warp][lane];
+      const Closure<SP>& c = s_cl[warp][s];
+      const MergeQueryAux& aux = s_aux[warp][s];
+      float4 wl = __ldg(&g.win_len[j]);
+      float4 nd = __ldg(&g.nrm_dvm[j]);
+      bool ok = !(__float_as_uint(wl.w) + aux.depth + 1 > sc.max_path_length);
+      ok = ok && !(dot(c.nrm, V3{nd.x, nd.y, nd.z}) <= kEpsilon);
+      if (ok) {
+        Smp lane_smp;
+        lane_smp.seed = aux.seed ^ ((j + 1u) * 0x9E3779B1u);
+        lane_smp.fixed_u = lane_smp.fixed_v = lane_smp.fixed_w = 0.0f;
+        lane_smp.next();
+        CEval<SP> e = closure_evaluate<SP>(sc, c, V3{-wl.x, -wl.y, -wl.z}, lane_smp);
+        if (e.valid()) {
+          float4 lt = __ldg(&g.thr_rgb[j]);
+          V3 c_value = spec_to_rgb<SP>(sc, e.func * Spec<SP>::make3(V3{aux.qc[0], aux.qc[1], aux.qc[2]}), c.wavelength);
+          float w_light = dvcm * vc_weight + nd.w * e.pdf;
+          float w_camera = aux.wcam_base + aux.dvm * e.rev_pdf;
+          float weight = use_mis ? (1.0f / (1.0f + w_light + w_camera)) : 1.0f;
+          float kernel_weight = use_epan ? fmaxf(2.0f * (1.0f - distance_squared * g.inv_radius_squared), 0.0f) : 1.0f;
+          float kw = kernel_weight * weight;
+          atomicAdd(&s_sum[warp][s][0], c_value.x * lt.x * kw);
+          atomicAdd(&s_sum[warp][s][1], c_value.y * lt.y * kw);
+          atomicAdd(&s_sum[warp][s][2], c_value.z * lt.z * kw);
+          accepts += 1;
+        }
+      }
+    }
+  };
+
+  while (pending) {
+    uint32_t src = __ffs(pending) - 1u;
+    pending &= pending - 1u;
+    V3 bpos = {__shfl_sync(kFull, qpos.x, src), __shfl_sync(kFull, qpos.y, src), __shfl_sync(kFull, qpos.z, src)};
+    // the eight cells (vcm_shared.hxx:895-916): lanes 0..7 fetch their ranges, then an 8-wide exclusive scan of the counts
+    uint32_t my_begin = 0, my_cnt = 0;
+    if (lane < 8u) {
+      V3 m = (bpos - g.bbox_min) / g.cell_size;
+      V3 mf = vfloor(m);
+      V3 md = m - mf;
+      int32_t acx = static_cast<int32_t>(mf.x), acy = static_cast<int32_t>(mf.y), acz = static_cast<int32_t>(mf.z);
+      int32_t cx = (lane & 1u) ? acx + ((md.x < 0.5f) ? -1 : +1) : acx;
+      int32_t cy = (lane & 2u) ? acy + ((md.y < 0.5f) ? -1 : +1) : acy;
+      int32_t cz = (lane & 4u) ? acz + ((md.z < 0.5f) ? -1 : +1) : acz;
+      uint2 r = __ldg(&g.cell_range[grid_cell_index(g.hash_table_mask, cx, cy, cz)]);
+      my_begin = r.x;
+      my_cnt = r.y - r.x;
+    }
+    uint32_t incl = my_cnt;
+#pragma unroll
+    for (uint32_t o = 1; o < 8u; o <<= 1) {
+      uint32_t v = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += v;
+    }
+    uint32_t my_excl = incl - my_cnt;
+    const uint32_t total = __shfl_sync(kFull, incl, 7);
+    uint32_t e1 = __shfl_sync(kFull, my_excl, 1), e2 = __shfl_sync(kFull, my_excl, 2), e3 = __shfl_sync(kFull, my_excl, 3), e4 = __shfl_sync(kFull, my_excl, 4),
+             e5 = __shfl_sync(kFull, my_excl, 5), e6 = __shfl_sync(kFull, my_excl, 6), e7 = __shfl_sync(kFull, my_excl, 7);
+    for (uint32_t base = 0; base < total; base += 32u) {
+      uint32_t k = base + lane;
+      bool valid = k < total;
+      uint32_t c = uint32_t(k >= e1) + uint32_t(k >= e2) + uint32_t(k >= e3) + uint32_t(k >= e4) + uint32_t(k >= e5) + uint32_t(k >= e6) + uint32_t(k >= e7);
+      uint32_t cb = __shfl_sync(kFull, my_begin, c);
+      uint32_t ce = __shfl_sync(kFull, my_excl, c);
+      uint32_t j = cb + (k - ce);
+      bool inside = false;
+      float distance_squared = 0.0f, dvcm = 0.0f;
+      if (valid) {
+        float4 pd = __ldg(&g.pos_dvcm[j]);
+        V3 d = V3{pd.x, pd.y, pd.z} - bpos;
+        distance_squared = dot(d, d);
+        dvcm = pd.w;
+        inside = !(distance_squared > g.radius_squared);
+        candidates += 1;
+      }
+      uint32_t bal = __ballot_sync(kFull, inside);
+      if (inside) {
+        uint32_t slot = n_list + __popc(bal & lane_lt);
+        s_idx[warp][slot] = j;
+        s_d2[warp][slot] = distance_squared;
+        s_dvcm[warp][slot] = dvcm;
+        s_src[warp][slot] = src;
+      }
+      n_list += __popc(bal);
+      __syncwarp();
+      if (n_list >= 32u) {
+        finish(32u);
+        __syncwarp();
+        uint32_t rest = n_list - 32u;  // < 32: move the tail to the front
+        uint32_t tj = 0, ts = 0;
+        float td = 0.0f, tv = 0.0f;
+        if (lane < rest) {
+          tj = s_idx[warp][32u + lane];
+          td = s_d2[warp][32u + lane];
+          tv = s_dvcm[warp][32u + lane];
+          ts = s_src[warp][32u + lane];
+        }
+        __syncwarp();
+        if (lane < rest) {
+          s_idx[warp][lane] = tj;
+          s_d2[warp][lane] = td;
+          s_dvcm[warp][lane] = tv;
+          s_src[warp][lane] = ts;
+        }
+        n_list = rest;
+        __syncwarp();
+      }
+    }
+  }
+  if (n_list) finish(n_list);
+  __syncwarp();
+  if (merge_queries) {
+    V3 l = {s_sum[warp][lane][0], s_sum[warp][lane][1], s_sum[warp][lane][2]};
+    if (SP) l *= V3{0.817660332f, 1.05418909f, 1.09945524f};  // kRGBLuminanceScale (:876-878)
+    float4 mg = p.paths.merged[i];
+    p.paths.merged[i] = make_float4(mg.x + l.x, mg.y + l.y, mg.z + l.z, 0.0f);
+  }
+  counter_add(&p.counters->merge_queries, merge_queries);
+  counter_add(&p.counters->merge_candidates, candidates);
+  counter_add(&p.counters->merge_accepts, accepts);
+}
+
 // EXPERIMENT (ETXB_MERGE_TILED=1, default off: written after the round's GPU budget ended, not yet run on the device).
 // Cell-tiled Lambert gather.  k_camera_merge_coop<SP, false> re-reads the ~530 candidate positions of a query's eight cells from L2 for every
 // query, although the 32 queries of a warp (sorted by base cell) share almost all of them: measured, the sweep streams ~3.9 TB/s out of L2.
@@ -1405,7 +1669,7 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_gener
 // pairs go through the shared list and per-query accumulators of the batched generic kernel.  Candidate traffic per warp: ~29 KB instead
 // of ~270 KB.
 template <bool SP>
-__global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_tiled(LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys, const uint32_t* count_in,
+__global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_tiled(const __grid_constant__ LaunchParams p, const uint32_t* sorted_ids, const uint32_t* sorted_keys, const uint32_t* count_in,
                                                                                  uint32_t queries_per_warp) {
   __shared__ uint32_t s_idx[kMergeWarpsPerBlock][kMergeListSize];
   __shared__ float s_d2[kMergeWarpsPerBlock][kMergeListSize];
@@ -1586,7 +1850,7 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_tiled
 
 // The deferred shadow rays of one camera bounce (ShadowBatch, dvcm.cuh): a traversal-only kernel — persistent warps take 32 segments at a
 // time from a shared cursor, every lane answers "is anything but a Void surface on this segment?".
-__global__ void __launch_bounds__(256) k_shadow_trace(LaunchParams p) {
+__global__ void __launch_bounds__(256) k_shadow_trace(const __grid_constant__ LaunchParams p) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t total = umin(p.shadow_count[0], p.shadow_capacity);
   for (;;) {
@@ -1606,7 +1870,7 @@ __global__ void __launch_bounds__(256) k_shadow_trace(LaunchParams p) {
 }
 
 template <bool SP>
-__global__ void __launch_bounds__(128) k_camera_continue(LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
+__global__ void __launch_bounds__(128) k_camera_continue(const __grid_constant__ LaunchParams p, const uint32_t* queue_in, const uint32_t* count_in, uint32_t* queue_out, uint32_t* count_out) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   bool alive = false;
   uint32_t i = 0;
@@ -1688,7 +1952,7 @@ __global__ void __launch_bounds__(128) k_camera_continue(LaunchParams p, const u
 // ---------------------------------------------------------------------------------------------------------------------
 // film (film.cxx:332-343, 381-418)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_film_commit_light(FilmBuffers film, uint32_t iteration_index) {
+__global__ void __launch_bounds__(256) k_film_commit_light(const __grid_constant__ FilmBuffers film, uint32_t iteration_index) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= film.width * film.height) return;
   float t = float(double(iteration_index) / double(iteration_index + 1u));
@@ -1699,7 +1963,7 @@ __global__ void __launch_bounds__(256) k_film_commit_light(FilmBuffers film, uin
   film.light_iteration[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
-__global__ void __launch_bounds__(256) k_film_resolve(FilmBuffers film, float4* out) {
+__global__ void __launch_bounds__(256) k_film_resolve(const __grid_constant__ FilmBuffers film, float4* out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= film.width * film.height) return;
   float4 c = film.camera[i], l = film.light[i];
@@ -1709,7 +1973,7 @@ __global__ void __launch_bounds__(256) k_film_resolve(FilmBuffers film, float4* 
 // ---------------------------------------------------------------------------------------------------------------------
 // debug / known-answer kernels
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void k_debug_trace(DeviceScene sc, const float* rays, uint32_t* seeds, uint32_t count, float* hits_uv_t, uint32_t* hits_tri) {
+__global__ void k_debug_trace(const __grid_constant__ DeviceScene sc, const float* rays, uint32_t* seeds, uint32_t count, float* hits_uv_t, uint32_t* hits_tri) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const float* r = rays + size_t(i) * 8;
@@ -1737,7 +2001,7 @@ __global__ void k_debug_sampler(const uint32_t* a, const uint32_t* b, uint32_t c
   }
 }
 
-__global__ void k_debug_math(DeviceScene sc, uint32_t fn, const float* x, const float* y, uint32_t count, float* out) {
+__global__ void k_debug_math(const __grid_constant__ DeviceScene sc, uint32_t fn, const float* x, const float* y, uint32_t count, float* out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   float a = x[i], b = y ? y[i] : 0.0f, r = 0.0f;

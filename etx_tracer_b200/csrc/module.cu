@@ -91,9 +91,11 @@ struct etxb_ctx {
   bool profile = false;
   bool has_stochastic_merge = false;  // some material that can be merged at is not Lambert (needs the serial gather)
   bool merge_tiled = false;           // experiment, default off: cell-tiled Lambert gather k_camera_merge_tiled (ETXB_MERGE_TILED=1)
-  bool merge_material_major = false;  // experiment, default off: gather queue ordered by (material, Morton code) (ETXB_MERGE_MATERIAL_MAJOR=1)
+  bool merge_material_major = true;   // gather queue ordered by (material, Morton code): the warps in flight evaluate one BSDF class at a time (measured on the B200,
+                                      // round 2: C3 generic gather 60.6 -> 46.1 ms per iteration; ETXB_MERGE_MATERIAL_MAJOR=0 switches it off)
   bool plain_kernels = true;          // bounce kernels specialised for scenes without media / Boundary surfaces / subsurface (ETXB_PLAIN_KERNELS=0: general ones)
   bool plain_scene = false;           // set at upload: the scene qualifies
+  bool merge_closure = true;          // generic photon gather on vertex closures (dclosure.cuh; ETXB_MERGE_CLOSURE=0: the batched generic kernel of round 1)
   bool merge_batched = true;          // generic photon gather batches its BSDF evaluations across the queries of a warp (ETXB_MERGE_BATCHED=0: per query)
   bool sort_by_material = true;       // group path queues and the connection list by material where BSDFs are costly (ETXB_SORT_MATERIAL=0: A/B switch)
   bool connect_deferred = true;       // per-connection stage for scenes with deferred shadow rays (ETXB_CONNECT_DEFERRED=0: A/B switch, serial loop)
@@ -222,6 +224,11 @@ struct LaunchTimer {
 
 bool material_class_supported_host(uint32_t cls) { return cls <= ETXB_MAT_VOID; }
 
+// A Distribution over `size` items holds size + 1 entries (DistributionBuilder allocates the closing {0, 0, 1} entry, distribution_builder.hxx:8-14,
+// 52) while `values.count` says `size` (the reference's loader) or size + 1 (hosts that count the closing entry): both are accepted, and the
+// device always gets the size + 1 entries.
+bool distribution_covers(uint64_t count, uint64_t size) { return (count == size) || (count == size + 1u); }
+
 uint32_t next_pow2(uint64_t v) {
   // next_power_of_two (math.hxx:1001-1010)
   v--;
@@ -269,6 +276,7 @@ LaunchParams make_params(etxb_ctx* ctx) {
   p.shadow_capacity = uint32_t(ctx->shadow_p0.count);
   p.shadow_stage = (ctx->dscene.deferred_shadow_rays && ctx->shadow_p0.count) ? 1u : 0u;
   p.connect_deferred = (p.shadow_stage && ctx->connect_deferred) ? 1u : 0u;
+  p.closures = ctx->merge_closure ? 1u : 0u;
   p.merge_material_major = (ctx->merge_material_major && ctx->has_stochastic_merge) ? 1u : 0u;
 #if defined(ETXB_PARITY) && ETXB_PARITY
   p.connect_stage = 0;
@@ -581,7 +589,10 @@ int run_camera_pass(etxb_ctx* ctx) {
       }
       if (ctx->has_stochastic_merge) {
         LaunchTimer t(ctx, K_CAMERA_MERGE_SERIAL);
-        if (ctx->merge_batched) {
+        if (ctx->merge_closure) {
+          const uint32_t closure_blocks = blocks_for(blocks_for(active, qpw), kClosureWarpsPerBlock);
+          k_camera_merge_closure<SP><<<closure_blocks, kClosureWarpsPerBlock * 32, 0, ctx->stream>>>(p, ids, keys, counts + cur, qpw);
+        } else if (ctx->merge_batched) {
           k_camera_merge_generic_batched<SP><<<merge_blocks, kMergeWarpsPerBlock * 32, 0, ctx->stream>>>(p, ids, keys, counts + cur, qpw);
         } else {
           k_camera_merge_coop<SP, true><<<merge_blocks, kMergeWarpsPerBlock * 32, 0, ctx->stream>>>(p, ids, keys, counts + cur, qpw);
@@ -654,6 +665,7 @@ int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
   if (const char* e = getenv("ETXB_CONNECT_DEFERRED")) ctx->connect_deferred = (e[0] != '0');
   if (const char* e = getenv("ETXB_SORT_MATERIAL")) ctx->sort_by_material = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_BATCHED")) ctx->merge_batched = (e[0] != '0');
+  if (const char* e = getenv("ETXB_MERGE_CLOSURE")) ctx->merge_closure = (e[0] != '0');
   if (const char* e = getenv("ETXB_PLAIN_KERNELS")) ctx->plain_kernels = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_MATERIAL_MAJOR")) ctx->merge_material_major = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_TILED")) ctx->merge_tiled = (e[0] != '0');
@@ -771,7 +783,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   if (cam.lens_image != ETXB_INVALID_INDEX) {
     if (cam.lens_image >= s.images.count) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "camera lens image index out of range");
     const auto& lens = static_cast<const etxb_image*>(s.images.a)[cam.lens_image];
-    if (lens.y_distribution.values.count != uint64_t(lens.isize[1]) + 1u) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "camera lens image has no sampling table");
+    if (!distribution_covers(lens.y_distribution.values.count, lens.isize[1])) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "camera lens image has no sampling table");
   }
   const auto* mats = static_cast<const etxb_material*>(s.materials.a);
   for (uint64_t i = 0; i < s.materials.count; ++i) {
@@ -806,7 +818,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
       const auto& prof = static_cast<const etxb_emitter_profile*>(s.emitter_profiles.a)[emitters[i].profile];
       if (prof.emission.image_index >= s.images.count) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "environment emitter %llu has no image", (unsigned long long)i);
       const auto& img = static_cast<const etxb_image*>(s.images.a)[prof.emission.image_index];
-      if (img.y_distribution.values.count != uint64_t(img.isize[1]) + 1u) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "environment emitter %llu: image has no sampling table", (unsigned long long)i);
+      if (!distribution_covers(img.y_distribution.values.count, img.isize[1])) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "environment emitter %llu: image has no sampling table", (unsigned long long)i);
     }
   }
   // ---- media (medium.hxx:8-47): dense density grids go to HBM as they are -------------------------------------------------------
@@ -890,12 +902,12 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
       d.normalization = im.normalization;
       d.options = im.options;
       d.format = im.format;
-      if (im.y_distribution.values.count == uint64_t(im.isize[1]) + 1u) {
+      if ((im.y_distribution.values.a != nullptr) && distribution_covers(im.y_distribution.values.count, im.isize[1]) && (im.x_distributions.count == im.isize[1])) {
         size_t nx = size_t(im.isize[0]) + 1u, ny = size_t(im.isize[1]) + 1u;
         std::vector<etxb_distribution_entry> flat(nx * im.isize[1]);
         const auto* rows = static_cast<const etxb_distribution*>(im.x_distributions.a);
         for (uint32_t y = 0; y < im.isize[1]; ++y) {
-          if (rows[y].values.count != nx) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "image %llu: row %u distribution has %llu entries", (unsigned long long)i, y, (unsigned long long)rows[y].values.count);
+          if (!distribution_covers(rows[y].values.count, im.isize[0])) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "image %llu: row %u distribution has %llu entries", (unsigned long long)i, y, (unsigned long long)rows[y].values.count);
           memcpy(flat.data() + size_t(y) * nx, rows[y].values.a, nx * sizeof(etxb_distribution_entry));
         }
         CUDA_OK(ctx, ctx->image_dists[i * 2].alloc(flat.size() * sizeof(etxb_distribution_entry)));
@@ -943,7 +955,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
       if (emitters[i].profile >= s.emitter_profiles.count) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "emitter %llu: profile index out of range", (unsigned long long)i);
       if ((emitters[i].cls == 0u) && (emitters[i].triangle_index >= s.triangles.count)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "area emitter %llu: triangle index out of range", (unsigned long long)i);
     }
-    if (s.emitters_distribution.values.count < s.emitter_instances.count + 1u)
+    if (!distribution_covers(s.emitters_distribution.values.count, s.emitter_instances.count))
       return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "emitter distribution has %llu entries for %llu emitters", (unsigned long long)s.emitters_distribution.values.count, (unsigned long long)s.emitter_instances.count);
   }
   const auto* verts = static_cast<const etxb_vertex*>(s.vertices.a);
@@ -973,7 +985,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   if (int rc = upload(ctx, ctx->profiles, static_cast<const etxb_emitter_profile*>(s.emitter_profiles.a), size_t(s.emitter_profiles.count))) return rc;
   if (int rc = upload(ctx, ctx->emitters, emitters, size_t(s.emitter_instances.count))) return rc;
   if (int rc = upload(ctx, ctx->spectra, dspec.data(), dspec.size())) return rc;
-  if (int rc = upload(ctx, ctx->emitter_dist, static_cast<const etxb_distribution_entry*>(s.emitters_distribution.values.a), size_t(s.emitters_distribution.values.count)))
+  if (int rc = upload(ctx, ctx->emitter_dist, static_cast<const etxb_distribution_entry*>(s.emitters_distribution.values.a), size_t(s.emitter_instances.count) + 1u))
     return rc;
   if (int rc = upload(ctx, ctx->bvh_nodes, bvh.nodes.data(), bvh.nodes.size())) return rc;
   if (int rc = upload(ctx, ctx->bvh_tris, reinterpret_cast<const float4*>(bvh.tri_pos.data()), bvh.tri_pos.size())) return rc;

@@ -34,14 +34,17 @@ def dump(path, scene_obj):
     for name, dt in _TOP:
         arrays[name] = _read(sc[name]["a"][0], sc[name]["count"][0], dt)
         out[name] = arrays[name].view(np.uint8)
-    out["emitters_distribution"] = _read(sc["emitters_distribution"]["values"]["a"][0], sc["emitters_distribution"]["values"]["count"][0], S.DIST_ENTRY).view(np.uint8)
+    # a Distribution over n items owns n + 1 entries (the closing {0, 0, 1} one, distribution_builder.hxx:8-14,52) whatever `values.count` says
+    # (the reference's loader writes n, scenes.py n + 1): always carry n + 1 and keep the count field as it was
+    out["emitters_distribution"] = _read(sc["emitters_distribution"]["values"]["a"][0], int(sc["emitter_instances"]["count"][0]) + 1, S.DIST_ENTRY).view(np.uint8)
     for i, im in enumerate(arrays["images"]):
         px_bytes = int(im["isize"][0]) * int(im["isize"][1]) * (16 if int(im["format"]) == 1 else 4)
         out[f"image{i}_pixels"] = _read(im["pixels"]["a"], px_bytes, np.uint8)
-        out[f"image{i}_ydist"] = _read(im["y_distribution"]["values"]["a"], im["y_distribution"]["values"]["count"], S.DIST_ENTRY).view(np.uint8)
+        has_table = int(im["y_distribution"]["values"]["a"]) != 0
+        out[f"image{i}_ydist"] = _read(im["y_distribution"]["values"]["a"], (int(im["isize"][1]) + 1) if has_table else 0, S.DIST_ENTRY).view(np.uint8)
         rows = _read(im["x_distributions"]["a"], im["x_distributions"]["count"], S.DISTRIBUTION)
         out[f"image{i}_xdist_rows"] = rows.view(np.uint8)
-        flat = [_read(r["values"]["a"], r["values"]["count"], S.DIST_ENTRY) for r in rows]
+        flat = [_read(r["values"]["a"], int(im["isize"][0]) + 1, S.DIST_ENTRY) for r in rows]
         out[f"image{i}_xdist_values"] = (np.concatenate(flat) if flat else np.zeros(0, dtype=S.DIST_ENTRY)).view(np.uint8)
     for i, md in enumerate(arrays["mediums"]):
         out[f"medium{i}_density"] = _read(md["density"]["a"], md["density"]["count"], np.float32).view(np.uint8)
@@ -74,14 +77,14 @@ class LoadedScene:
             px = own(z[f"image{i}_pixels"], np.uint8)
             im["pixels"]["a"] = px.ctypes.data if px.size else 0  # count keeps the loader's pixel count
             yd = own(z[f"image{i}_ydist"], S.DIST_ENTRY)
-            point(im["y_distribution"]["values"], yd)
+            point(im["y_distribution"]["values"], yd, int(im["y_distribution"]["values"]["count"][0]))
             rows = own(z[f"image{i}_xdist_rows"], S.DISTRIBUTION)
             vals = own(z[f"image{i}_xdist_values"], S.DIST_ENTRY)
             at = 0
+            per_row = int(im["isize"][0][0]) + 1
             for r in range(rows.shape[0]):
-                n = int(rows[r]["values"]["count"])
-                rows[r]["values"]["a"] = vals[at:at + n].ctypes.data if n else 0
-                at += n
+                rows[r]["values"]["a"] = vals[at:at + per_row].ctypes.data
+                at += per_row
             point(im["x_distributions"], rows)
         for i in range(mediums.shape[0]):
             d = own(z[f"medium{i}_density"], np.float32)
@@ -89,7 +92,7 @@ class LoadedScene:
         for name, _ in _TOP:
             point(self.scene[name], top[name])
         ed = own(z["emitters_distribution"], S.DIST_ENTRY)
-        point(self.scene["emitters_distribution"]["values"], ed)
+        point(self.scene["emitters_distribution"]["values"], ed, int(self.scene["emitters_distribution"]["values"]["count"][0]))
 
     @property
     def width(self):
