@@ -238,9 +238,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--lanes", type=int, default=4, help="iterations in flight per GPU (etxb_group); 1 = the plain one-context pump")
-    ap.add_argument("--parallelism", default="iteration", choices=["iteration", "tile"],
-                    help="N > 1: 'iteration' = every rank renders its own whole-frame iterations (weak scaling, no data-path collective); "
-                         "'tile' = pixel-tile sharding of each iteration (strong scaling, photon exchange per iteration)")
+    ap.add_argument("--parallelism", default="tile", choices=["tile", "iteration"],
+                    help="N > 1: 'tile' (default, the north star's mode) = every iteration split by pixel tile over the GPUs inside the module (strong "
+                         "scaling, NCCL all-reduce / all-gather per iteration); 'iteration' = every rank renders its own whole-frame iterations "
+                         "(weak scaling, no data-path collective)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -272,23 +273,22 @@ def main():
     sd, desc = workload(args)
     n_pixels = sd.width * sd.height
     tile_mode = world > 1 and args.parallelism == "tile"
-    sharded = interleaved = None
+    interleaved = None
+    from etx_tracer_b200.api import GPUVCMGroup, comm_unique_ids
+    lanes = max(1, min(args.lanes, 8))
+    g = GPUVCMGroup(sd, lanes=lanes, flavor="fast", device=local_rank, profile=True)
     if tile_mode:
-        # ONE iteration of the frame split over the ranks by pixel tile; photon exchange per iteration (strong scaling)
-        from etx_tracer_b200.multigpu import ShardedVCM
-        g = GPUVCM(sd, flavor="fast", device=local_rank, profile=True)
-        sharded = ShardedVCM(g, dist, rank, world)
-        lanes = 1
-    else:
-        # whole-frame iterations, `lanes` of them in flight per GPU; with N ranks, rank r renders indices r, r + N, ... (weak scaling:
-        # a step is one iteration PER RANK, no data-path collective)
-        from etx_tracer_b200.api import GPUVCMGroup
-        lanes = max(1, min(args.lanes, 8))
-        g = GPUVCMGroup(sd, lanes=lanes, flavor="fast", device=local_rank, profile=True)
-        if world > 1:
-            from etx_tracer_b200.multigpu import InterleavedVCM
-            interleaved = InterleavedVCM(g, dist, rank, world)
-    samples_per_step = n_pixels * (1 if tile_mode else world)
+        # north-star mode: every iteration of the frame is split over the ranks by 32x32 pixel tile INSIDE the module (NCCL communicators created by
+        # etxb_group_comm_init: all-reduce of the light image + all-gather of the photon records per iteration, reduce of the film per frame);
+        # the host only hands out the NCCL ids.  Strong scaling: a step = one whole-frame iteration, whatever the number of GPUs.
+        from etx_tracer_b200.multigpu import distribute_comm_ids
+        ids = distribute_comm_ids(dist, rank, lanes + 1, comm_unique_ids, device=torch.device("cuda", local_rank))
+        g.comm_init(world, rank, ids)
+    elif world > 1:
+        # whole-frame iterations, rank r renders indices r, r + N, ... (weak scaling: a step is one iteration PER RANK, no data-path collective)
+        from etx_tracer_b200.multigpu import InterleavedVCM
+        interleaved = InterleavedVCM(g, dist, rank, world)
+    samples_per_step = n_pixels * (1 if (tile_mode or world == 1) else world)
     g.options[:] = workload_vcm_options(args)
 
     def begin():
@@ -298,11 +298,7 @@ def main():
             g.run(0)
 
     def run_steps(n):
-        if tile_mode:
-            for _ in range(n):
-                sharded.iterate()
-        else:
-            g.enqueue(n)
+        g.enqueue(n)
         g.wait()
 
     def sync_all():
@@ -332,14 +328,20 @@ def main():
     # one context: CUDA events on the module's stream around every iteration.  several iterations in flight: the streams overlap, so the
     # module reports the span from the first enqueue (every lane idle and synchronised) to the last lane's end-of-iteration synchronise
     mod_s = st1["total_time"] - st0["total_time"]
-    elapsed = max(t_wall, mod_s) if tile_mode else mod_s  # tile mode: the exchanges sit between the passes, the wall clock covers them
+    elapsed = mod_s  # tile mode: the collectives run inside the iterations, on the lanes' streams
     if world > 1:
         t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
     value = samples_per_step * args.steps / elapsed / 1e6
     counters = {k: c1[k] - c0[k] for k in c1}
+    if tile_mode:  # every rank counted its own tiles
+        keys = sorted(counters)
+        t = torch.tensor([float(counters[k]) for k in keys], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        counters = {k: int(v) for k, v in zip(keys, t.tolist())}
     ktimes = {k: (k1[k][0] - k0[k][0], k1[k][1] - k0[k][1]) for k in k1}
+    comm_ms = {k: round(v[0] / max(args.steps, 1), 3) for k, v in ktimes.items() if k.startswith("nccl_")}
 
     # ---- end to end through the public API, host buffers inside the timed region ---------------------------------------------
     # every step: options host -> module, one more iteration queued, the current film device -> pinned host (what a UI pumping the
@@ -354,11 +356,9 @@ def main():
     film_reads = 0
     for _ in range(args.steps):
         if tile_mode:
-            g._check(g.lib.etxb_set_options(g.h, g.options.ctypes.data))
-            sharded.iterate()
-            sharded.reduce_film()
-            if rank == 0:
-                g.film(S.FILM_RESULT, out=host_film)
+            g.set_options()
+            g.enqueue(1)
+            g.comm_reduce_film(S.FILM_RESULT, out=host_film)  # collective: ncclReduce of the camera tiles, Result layer to rank 0's host buffer
         else:
             g.set_options()
             g.enqueue(1)
@@ -370,7 +370,10 @@ def main():
                 g.film(S.FILM_RESULT, out=host_film)
         film_reads += 1
     g.wait()
-    if not tile_mode:
+    if tile_mode:
+        g.comm_reduce_film(S.FILM_RESULT, out=host_film)
+        film_reads += 1
+    else:
         if interleaved:
             combined = interleaved.reduce_film()
             if rank == 0:
@@ -479,11 +482,12 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if tile_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc,
-                           "parallelism": (f"pixel-tile x{world}, photon exchange per iteration" if tile_mode else
+                           "parallelism": (f"pixel tiles (32x32, round-robin) over {world} GPUs inside the module, {lanes} iterations in flight per GPU; per iteration: "
+                                           f"ncclAllReduce of the light image + all-gather of the photon records; per frame: ncclReduce of the film" if tile_mode else
                                            f"{lanes} iterations in flight per GPU" + (f"; iteration-interleaved x{world}: a step = one whole-frame iteration per rank "
                                                                                       f"(indices rank + j*{world}), one film reduce" if world > 1 else "")),
-                           "timing": ("barrier-to-barrier wall clock, max over ranks" if tile_mode else
-                                      "span from the first enqueue (all lanes idle, device synchronised) to the last lane's end-of-iteration stream synchronise, max over ranks"),
+                           "collective_ms_per_iteration": (comm_ms if tile_mode else None),
+                           "timing": ("span from the first enqueue (all lanes idle, device synchronised) to the last lane's end-of-iteration stream synchronise, max over ranks"),
                            "l2": "inputs larger than L2 (path state + light-vertex pool + photon grid > 126 MB)",
                            "iterations": f"a fixed index set: {args.warmup} warm-up iterations (indices 0..{args.warmup - 1}), then the timed indices "
                                          f"{args.warmup}..{args.warmup + args.steps - 1} of the 1/(1 + i/256) merge-radius schedule (the most expensive end of a render)",

@@ -61,6 +61,13 @@ def load_library(flavor="fast"):
         lib.etxb_group_read_film.argtypes = [vp, u32, vp, u64]
         lib.etxb_group_set_stride.argtypes = [vp, u32]
         lib.etxb_group_combine.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u32)]
+    if hasattr(lib, "etxb_comm_init"):
+        lib.etxb_comm_unique_id.argtypes = [vp, u64]
+        lib.etxb_comm_init.argtypes = [vp, u32, u32, vp, u64]
+        lib.etxb_comm_world.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+        lib.etxb_comm_reduce_film.argtypes = [vp, u32, vp, u64]
+        lib.etxb_group_comm_init.argtypes = [vp, u32, u32, vp, u32]
+        lib.etxb_group_comm_reduce_film.argtypes = [vp, u32, vp, u64]
     lib.etxb_set_partition.argtypes = [vp, u32, u32]
     if hasattr(lib, "etxb_set_iteration_stride"):  # absent only from older builds loaded through the ETXB_LIB_* override
         lib.etxb_set_iteration_stride.argtypes = [vp, u32]
@@ -89,6 +96,20 @@ def load_library(flavor="fast"):
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_ids(count, flavor="fast"):
+    """`count` NCCL unique ids (ETXB_COMM_ID_BYTES each) from the module, for rank 0 to hand to the other ranks by any transport."""
+    lib = load_library(flavor)
+    ids = np.zeros(count * COMM_ID_BYTES, dtype=np.uint8)
+    for k in range(count):
+        rc = lib.etxb_comm_unique_id(ids[k * COMM_ID_BYTES:].ctypes.data_as(C.c_void_p), COMM_ID_BYTES)
+        if rc != 0:
+            raise EtxbError(rc, "etxb_comm_unique_id failed (libnccl.so.2 missing?)")
+    return ids
 
 
 class GPUVCM:
@@ -167,6 +188,20 @@ class GPUVCM:
 
     def set_partition(self, rank, world):
         self._check(self.lib.etxb_set_partition(self.h, rank, world))
+
+    def comm_init(self, world, rank, comm_id):
+        """Pixel tiles over `world` processes (one GPU each): collective; comm_id = the 128 bytes rank 0 got from comm_unique_ids(1)."""
+        comm_id = np.ascontiguousarray(comm_id, dtype=np.uint8)
+        self._check(self.lib.etxb_comm_init(self.h, world, rank, _p(comm_id), comm_id.nbytes))
+
+    def comm_reduce_film(self, layer=S.FILM_RESULT, out=None):
+        """Collective: the whole frame on rank 0 (returned there; None elsewhere)."""
+        w, r = C.c_uint32(1), C.c_uint32(0)
+        self._check(self.lib.etxb_comm_world(self.h, C.byref(w), C.byref(r)))
+        if (out is None) and (r.value == 0):
+            out = np.zeros((self.height, self.width, 4), dtype=np.float32)
+        self._check(self.lib.etxb_comm_reduce_film(self.h, layer, _p(out) if r.value == 0 else None, out.nbytes if r.value == 0 else 0))
+        return out if r.value == 0 else None
 
     def set_iteration_stride(self, stride):
         """This context renders iterations first, first + stride, ... (iteration-interleaved multi-GPU runs)."""
@@ -329,6 +364,21 @@ class GPUVCMGroup:
     def run(self, first_iteration=0):
         self.set_options()
         self._check(self.lib.etxb_group_begin(self.h, first_iteration))
+
+    def comm_init(self, world, rank, comm_ids):
+        """Pixel tiles over `world` processes with len(self.lanes) iterations in flight on each: collective; comm_ids = the (lanes + 1) x 128
+        bytes rank 0 got from comm_unique_ids(lanes + 1)."""
+        comm_ids = np.ascontiguousarray(comm_ids, dtype=np.uint8)
+        self._check(self.lib.etxb_group_comm_init(self.h, world, rank, _p(comm_ids), comm_ids.nbytes // COMM_ID_BYTES))
+        self.comm_rank, self.comm_world = rank, world
+
+    def comm_reduce_film(self, layer=S.FILM_RESULT, out=None):
+        """Collective: the whole frame (mean over the iterations finished so far) on rank 0; None elsewhere."""
+        rank = getattr(self, "comm_rank", 0)
+        if (out is None) and (rank == 0):
+            out = np.zeros((self.height, self.width, 4), dtype=np.float32)
+        self._check(self.lib.etxb_group_comm_reduce_film(self.h, layer, _p(out) if rank == 0 else None, out.nbytes if rank == 0 else 0))
+        return out if rank == 0 else None
 
     def set_stride(self, stride):
         """Iteration-interleaved multi-GPU runs: this group renders indices first, first + stride, ..."""

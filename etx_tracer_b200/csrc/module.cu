@@ -18,6 +18,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "bvh_build.h"
 #include "kernels.cuh"
 
@@ -52,10 +55,12 @@ enum KernelId : uint32_t {
   K_CAMERA_MERGE_SERIAL,
   K_CAMERA_CONTINUE,
   K_FILM_COMMIT,
+  K_COMM_LIGHT_IMAGE,
+  K_COMM_PHOTONS,
   K_COUNT
 };
 const char* kKernelNames[K_COUNT] = {"light_begin", "trace_closest(light)", "light_bounce", "lv_scan", "lv_reorder", "grid_bbox", "grid_keys", "grid_sort", "grid_build",
-  "camera_begin", "trace_closest(camera)", "camera_shade", "camera_connect", "shadow_trace", "queue_sort", "camera_merge_sort", "camera_merge", "camera_merge_generic", "camera_continue", "film_commit_light"};
+  "camera_begin", "trace_closest(camera)", "camera_shade", "camera_connect", "shadow_trace", "queue_sort", "camera_merge_sort", "camera_merge", "camera_merge_generic", "camera_continue", "film_commit_light", "nccl_allreduce_light_image", "nccl_allgather_photons"};
 
 template <class T>
 struct DevBuf {
@@ -156,6 +161,21 @@ struct etxb_ctx {
   GridData grid = {};
   bool light_pass_done = false, grid_done = false;
 
+  // pixel-tile sharding across processes (one per GPU): NCCL communicator over NVLink, created by etxb_comm_init
+  ncclComm_t comm = nullptr;
+  DevBuf<uint32_t> comm_counts;   // [world] stored light vertices per rank (all-gathered every iteration)
+  DevBuf<float4> film_reduced;    // rank 0: sum of every rank's camera tiles (etxb_comm_reduce_film)
+  double comm_ms = 0.0;           // device time of the collectives of the iterations since etxb_begin
+
+  // etxb_enqueue_iteration is asynchronous (CPUVCM::update returns at once, vcm_cpu.cxx:264-276): the iteration's host loop — it reads queue
+  // sizes back between bounces — runs on this context's own worker thread; etxb_poll never blocks, etxb_wait drains
+  std::thread worker;
+  std::mutex worker_m;
+  std::condition_variable worker_cv, worker_idle;
+  uint32_t worker_queued = 0;
+  bool worker_busy = false, worker_quit = false;
+  int worker_error = ETXB_OK;
+
   cudaEvent_t ev_iter_start = nullptr, ev_iter_stop = nullptr;
   std::vector<TimedLaunch> timed;
   std::vector<cudaEvent_t> event_pool;
@@ -165,6 +185,50 @@ struct etxb_ctx {
 };
 
 namespace {
+
+// NCCL is bound at run time: a single-GPU host needs no libnccl, and a torch host that already loaded its bundled libnccl.so.2 shares it.
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    bool ok = true;
+    auto bind = [&](auto& fn, const char* name) {
+      fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(h, name));
+      ok = ok && (fn != nullptr);
+    };
+    bind(api.GetUniqueId, "ncclGetUniqueId");
+    bind(api.CommInitRank, "ncclCommInitRank");
+    bind(api.CommDestroy, "ncclCommDestroy");
+    bind(api.AllReduce, "ncclAllReduce");
+    bind(api.AllGather, "ncclAllGather");
+    bind(api.Reduce, "ncclReduce");
+    bind(api.Broadcast, "ncclBroadcast");
+    bind(api.GroupStart, "ncclGroupStart");
+    bind(api.GroupEnd, "ncclGroupEnd");
+    bind(api.GetErrorString, "ncclGetErrorString");
+    if (ok) api.handle = h;
+  });
+  return api.handle ? &api : nullptr;
+}
+
+int ctx_drain_impl(etxb_ctx* ctx);
 
 int fail(etxb_ctx* ctx, int code, const char* fmt, ...) {
   char buf[1024];
@@ -183,6 +247,12 @@ int fail(etxb_ctx* ctx, int code, const char* fmt, ...) {
       return fail(ctx, (err__ == cudaErrorMemoryAllocation) ? ETXB_ERR_OUT_OF_MEMORY : ETXB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), \
         __FILE__, __LINE__);                                                                                 \
     }                                                                                                        \
+  } while (0)
+
+#define NCCL_OK(ctx, call)                                                                                                 \
+  do {                                                                                                                     \
+    ncclResult_t res__ = (call);                                                                                           \
+    if (res__ != ncclSuccess) return fail(ctx, ETXB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, nccl_api()->GetErrorString(res__), __FILE__, __LINE__); \
   } while (0)
 
 template <class T>
@@ -612,6 +682,56 @@ int run_camera_pass(etxb_ctx* ctx) {
   return ETXB_OK;
 }
 
+// Pixel-tile sharding (north star): between the light pass and the grid build of an iteration the ranks exchange what is global —
+//   (a) the light-tracing splats land on ANY pixel (vcm_cpu.cxx:147-154): all-reduce(sum) of the per-iteration light image, after which every
+//       rank commits the same running mean (film.cxx:332-343);
+//   (b) merging queries the photon map of ALL light paths (vcm_cpu.cxx:219-221): all-gather of the path-major vertex records (96 B each, block
+//       sizes differ per rank: counts first, then one broadcast per owner inside a group call = an uneven all-gather), into the allocation-order
+//       pool, which is free once the path-major pool exists; every rank then builds the same grid.
+// Camera tiles are disjoint: they meet only when a frame is wanted (etxb_comm_reduce_film).
+int comm_exchange(etxb_ctx* ctx, const void** records, uint64_t* count) {
+  NcclApi* n = nccl_api();
+  *records = nullptr;
+  *count = 0;
+  {
+    LaunchTimer t(ctx, K_COMM_LIGHT_IMAGE);
+    NCCL_OK(ctx, n->AllReduce(ctx->film_light_iteration.ptr, ctx->film_light_iteration.ptr, size_t(ctx->path_count) * 4u, ncclFloat, ncclSum, ctx->comm, ctx->stream));
+  }
+  const bool merging = (ctx->options.options & ETXB_VCM_ENABLE_MERGING) && (ctx->options.options & ETXB_VCM_MERGE_VERTICES);
+  if (!merging) return ETXB_OK;
+  const uint32_t world = ctx->world, rank = ctx->rank;
+  std::vector<uint32_t> counts(world, 0u);
+  {
+    LaunchTimer t(ctx, K_COMM_PHOTONS);
+    uint32_t mine = ctx->last_light_vertices;
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->comm_counts.ptr + rank, &mine, 4, cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_OK(ctx, n->AllGather(ctx->comm_counts.ptr + rank, ctx->comm_counts.ptr, 1, ncclUint32, ctx->comm, ctx->stream));
+    CUDA_OK(ctx, cudaMemcpyAsync(counts.data(), ctx->comm_counts.ptr, size_t(world) * 4u, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t total = 0;
+    std::vector<uint64_t> offsets(world, 0u);
+    for (uint32_t r = 0; r < world; ++r) {
+      offsets[r] = total;
+      total += counts[r];
+    }
+    if (total > ctx->lv_capacity) return fail(ctx, ETXB_ERR_OVERFLOW, "gathered photon count %llu exceeds the pool capacity %u", (unsigned long long)total, ctx->lv_capacity);
+    constexpr size_t kRecordFloats = sizeof(LightVertexRec) / 4u;
+    NCCL_OK(ctx, n->GroupStart());
+    for (uint32_t r = 0; r < world; ++r) {
+      if (counts[r] == 0u) continue;
+      ncclResult_t res = n->Broadcast(ctx->lv_final.ptr, ctx->lv_tmp.ptr + offsets[r], size_t(counts[r]) * kRecordFloats, ncclFloat, int(r), ctx->comm, ctx->stream);
+      if (res != ncclSuccess) {
+        n->GroupEnd();
+        return fail(ctx, ETXB_ERR_CUDA, "ncclBroadcast failed: %s", n->GetErrorString(res));
+      }
+    }
+    NCCL_OK(ctx, n->GroupEnd());
+    *records = ctx->lv_tmp.ptr;
+    *count = total;
+  }
+  return ETXB_OK;
+}
+
 void resolve_timers(etxb_ctx* ctx) {
   for (auto& t : ctx->timed) {
     float ms = 0.0f;
@@ -682,8 +802,23 @@ int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
 
 void etxb_destroy(etxb_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->worker.joinable()) {
+    {
+      std::lock_guard<std::mutex> lock(ctx->worker_m);
+      ctx->worker_queued = 0;
+      ctx->worker_quit = true;
+    }
+    ctx->worker_cv.notify_all();
+    ctx->worker.join();
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm != nullptr) {
+    if (NcclApi* n = nccl_api()) n->CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  ctx->comm_counts.release();
+  ctx->film_reduced.release();
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_iter_start);
   cudaEventDestroy(ctx->ev_iter_stop);
@@ -773,6 +908,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
     return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "scene/camera size mismatch: got %llu/%llu, expected %zu/%zu", (unsigned long long)scene_bytes,
       (unsigned long long)camera_bytes, sizeof(etxb_scene), sizeof(etxb_camera));
   if (!ctx->xyz_table.ptr) return fail(ctx, ETXB_ERR_NOT_READY, "etxb_upload_color_tables must be called before etxb_upload_scene");
+  ctx_drain_impl(ctx);
   cudaSetDevice(ctx->device);
   ctx->scene_ready = false;
   const etxb_scene& s = *static_cast<const etxb_scene*>(scene_blob);
@@ -1154,6 +1290,7 @@ int etxb_set_next_iteration(etxb_ctx* ctx, uint32_t iteration) {
 int etxb_begin(etxb_ctx* ctx, uint32_t first_iteration) {
   if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
   if (!ctx->scene_ready) return fail(ctx, ETXB_ERR_NOT_READY, "no scene uploaded");
+  ctx_drain_impl(ctx);  // Integrator::run first stops what is running (vcm_cpu.cxx:255-262)
   cudaSetDevice(ctx->device);
   size_t n = ctx->path_count;
   CUDA_OK(ctx, cudaMemsetAsync(ctx->film_camera.ptr, 0, n * 16, ctx->stream));
@@ -1206,10 +1343,128 @@ int etxb_enqueue_camera_pass(etxb_ctx* ctx) {
   return finish_iteration(ctx);
 }
 
-int etxb_enqueue_iteration(etxb_ctx* ctx) {
+// one whole iteration on the calling thread; returns when it has finished (the bounce loops read queue sizes back)
+static int run_iteration_blocking(etxb_ctx* ctx) {
   if (int rc = etxb_enqueue_light_pass(ctx)) return rc;
-  if (int rc = etxb_enqueue_grid_build(ctx, nullptr, 0)) return rc;
+  const void* records = nullptr;
+  uint64_t count = 0;
+  if (ctx->comm != nullptr) {  // pixel tiles over several GPUs: light image + photon records are exchanged here (comm_exchange)
+    if (int rc = comm_exchange(ctx, &records, &count)) return rc;
+  }
+  if (int rc = etxb_enqueue_grid_build(ctx, records, count)) return rc;
   return etxb_enqueue_camera_pass(ctx);
+}
+
+static void ctx_worker(etxb_ctx* ctx) {
+  std::unique_lock<std::mutex> lock(ctx->worker_m);
+  for (;;) {
+    ctx->worker_cv.wait(lock, [&] { return ctx->worker_quit || (ctx->worker_queued > 0); });
+    if (ctx->worker_quit) return;
+    ctx->worker_queued -= 1;
+    ctx->worker_busy = true;
+    lock.unlock();
+    int rc = run_iteration_blocking(ctx);
+    lock.lock();
+    ctx->worker_busy = false;
+    if ((rc != ETXB_OK) && (ctx->worker_error == ETXB_OK)) {
+      ctx->worker_error = rc;
+      ctx->worker_queued = 0;
+    }
+    if (ctx->worker_queued == 0) ctx->worker_idle.notify_all();
+  }
+}
+
+// blocks until every queued iteration has finished; returns (and clears) the first error one of them hit
+static int ctx_drain(etxb_ctx* ctx) { return ctx_drain_impl(ctx); }
+extern "C++" {
+namespace {
+int ctx_drain_impl(etxb_ctx* ctx) {
+  std::unique_lock<std::mutex> lock(ctx->worker_m);
+  ctx->worker_idle.wait(lock, [&] { return (ctx->worker_queued == 0) && !ctx->worker_busy; });
+  int rc = ctx->worker_error;
+  ctx->worker_error = ETXB_OK;
+  return rc;
+}
+}  // namespace
+}  // extern "C++"
+
+int etxb_enqueue_iteration(etxb_ctx* ctx) {
+  if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  if (!ctx->scene_ready) return fail(ctx, ETXB_ERR_NOT_READY, "no scene uploaded");
+  std::lock_guard<std::mutex> lock(ctx->worker_m);
+  if (ctx->worker_error != ETXB_OK) {
+    int rc = ctx->worker_error;
+    ctx->worker_error = ETXB_OK;
+    return rc;
+  }
+  if (!ctx->worker.joinable()) ctx->worker = std::thread(ctx_worker, ctx);
+  ctx->worker_queued += 1;
+  ctx->worker_cv.notify_one();
+  return ETXB_OK;
+}
+
+// ---- pixel-tile sharding over NCCL -------------------------------------------------------------------------------------------------------
+int etxb_comm_unique_id(void* out_id, uint64_t bytes) {
+  if (!out_id || (bytes < sizeof(ncclUniqueId))) return ETXB_ERR_INVALID_ARGUMENT;
+  NcclApi* n = nccl_api();
+  if (!n) return ETXB_ERR_NOT_READY;
+  ncclUniqueId id;
+  if (n->GetUniqueId(&id) != ncclSuccess) return ETXB_ERR_CUDA;
+  memcpy(out_id, &id, sizeof(id));
+  return ETXB_OK;
+}
+
+int etxb_comm_init(etxb_ctx* ctx, uint32_t world, uint32_t rank, const void* id, uint64_t bytes) {
+  if (!ctx || !id || (bytes < sizeof(ncclUniqueId)) || (world == 0u) || (rank >= world)) return ETXB_ERR_INVALID_ARGUMENT;
+  NcclApi* n = nccl_api();
+  if (!n) return fail(ctx, ETXB_ERR_NOT_READY, "libnccl.so.2 could not be loaded");
+  if (ctx->comm != nullptr) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "the context already has a communicator");
+  cudaSetDevice(ctx->device);
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  NCCL_OK(ctx, n->CommInitRank(&ctx->comm, int(world), uid, int(rank)));
+  ctx->rank = rank;
+  ctx->world = world;
+  CUDA_OK(ctx, ctx->comm_counts.alloc(world));
+  return ETXB_OK;
+}
+
+int etxb_comm_world(const etxb_ctx* ctx, uint32_t* world, uint32_t* rank) {
+  if (!ctx || !world || !rank) return ETXB_ERR_INVALID_ARGUMENT;
+  *world = (ctx->comm != nullptr) ? ctx->world : 1u;
+  *rank = (ctx->comm != nullptr) ? ctx->rank : 0u;
+  return ETXB_OK;
+}
+
+// Collective: every rank calls it.  The disjoint camera tiles are summed on rank 0 (ncclReduce of the float4 film); the light layer is already
+// complete on every rank.  On rank 0 `dst_rgba` (may be null elsewhere) receives the layer like etxb_read_film.
+int etxb_comm_reduce_film(etxb_ctx* ctx, uint32_t layer, float* dst_rgba, uint64_t dst_bytes) {
+  if (!ctx || (layer > ETXB_FILM_LIGHT)) return ETXB_ERR_INVALID_ARGUMENT;
+  if (!ctx->scene_ready) return fail(ctx, ETXB_ERR_NOT_READY, "no scene uploaded");
+  if (ctx->comm == nullptr) return etxb_read_film(ctx, layer, dst_rgba, dst_bytes);
+  if (int rc = ctx_drain_impl(ctx)) return rc;
+  NcclApi* n = nccl_api();
+  cudaSetDevice(ctx->device);
+  const size_t px = ctx->path_count;
+  if (ctx->film_reduced.count < px) CUDA_OK(ctx, ctx->film_reduced.alloc(px));
+  if (layer != ETXB_FILM_LIGHT)
+    NCCL_OK(ctx, n->Reduce(ctx->film_camera.ptr, ctx->film_reduced.ptr, px * 4u, ncclFloat, ncclSum, 0, ctx->comm, ctx->stream));
+  if (ctx->rank != 0u) {
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ETXB_OK;
+  }
+  if (!dst_rgba || (dst_bytes < px * 16u)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "film buffer too small");
+  const float4* src = ctx->film_light.ptr;
+  if (layer == ETXB_FILM_CAMERA) src = ctx->film_reduced.ptr;
+  if (layer == ETXB_FILM_RESULT) {
+    FilmBuffers film = {ctx->film_reduced.ptr, ctx->film_light.ptr, ctx->film_light_iteration.ptr, ctx->width, ctx->height};
+    k_film_resolve<<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(film, ctx->film_out.ptr);
+    ctx->kernel_launches += 1;
+    src = ctx->film_out.ptr;
+  }
+  CUDA_OK(ctx, cudaMemcpyAsync(dst_rgba, src, px * 16u, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETXB_OK;
 }
 
 int etxb_poll(etxb_ctx* ctx, etxb_status* status) {
@@ -1219,7 +1474,10 @@ int etxb_poll(etxb_ctx* ctx, etxb_status* status) {
   status->total_time = ctx->total_time;
   status->completed_iterations = ctx->completed;
   status->current_iteration = ctx->iteration;
-  status->iteration_in_flight = 0;
+  {
+    std::lock_guard<std::mutex> lock(ctx->worker_m);
+    status->iteration_in_flight = ((ctx->worker_queued > 0) || ctx->worker_busy) ? 1u : 0u;
+  }
   status->light_vertices = ctx->last_light_vertices;
   status->overflow = ctx->overflow_flag;
   return ETXB_OK;
@@ -1227,12 +1485,22 @@ int etxb_poll(etxb_ctx* ctx, etxb_status* status) {
 
 int etxb_wait(etxb_ctx* ctx) {
   if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  if (int rc = ctx_drain(ctx)) return rc;
   cudaSetDevice(ctx->device);
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return ETXB_OK;
 }
 
-int etxb_stop(etxb_ctx* ctx, int) { return etxb_wait(ctx); }
+// CPUVCM::stop (vcm_cpu.cxx:278-288): Immediate drops the queued iterations (the one in flight still completes: its film update is atomic per
+// iteration), WaitForCompletion lets everything queued finish
+int etxb_stop(etxb_ctx* ctx, int wait_for_iteration) {
+  if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  if (!wait_for_iteration) {
+    std::lock_guard<std::mutex> lock(ctx->worker_m);
+    ctx->worker_queued = 0;
+  }
+  return etxb_wait(ctx);
+}
 
 int etxb_film_size(const etxb_ctx* ctx, uint32_t* width, uint32_t* height) {
   if (!ctx || !width || !height) return ETXB_ERR_INVALID_ARGUMENT;
@@ -1329,6 +1597,7 @@ int etxb_device_pointer(etxb_ctx* ctx, uint32_t buffer_id, void** out_ptr, uint6
 
 int etxb_read_buffer(etxb_ctx* ctx, uint32_t buffer_id, void* dst, uint64_t dst_bytes, uint64_t* out_bytes) {
   if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  if (int rc = ctx_drain_impl(ctx)) return rc;
   cudaSetDevice(ctx->device);
   size_t lv = ctx->last_light_vertices;
   if (buffer_id == ETXB_BUF_LV_POS || buffer_id == ETXB_BUF_LV_THROUGHPUT || buffer_id == ETXB_BUF_LV_MIS) {
@@ -1494,21 +1763,47 @@ struct etxb_group {
   double last_iteration_seconds = 0.0;
   DevBuf<float4> combined;
   int device = 0;
+  // pixel-tile sharding over several processes (etxb_group_comm_init): every lane has its own communicator, and the k-th iteration of lane l is
+  // the ordinal l + k * lanes on EVERY rank (the shared counter of the single-GPU mode would pair different iterations across ranks)
+  bool sharded = false;
+  uint32_t world = 1, rank = 0;
+  uint32_t enqueued_total = 0;
+  std::vector<uint32_t> lane_next;
+  ncclComm_t reduce_comm = nullptr;  // the frame reduce has its own communicator: the lanes' ones are busy with iterations in flight
+  cudaStream_t stream = nullptr;
+  DevBuf<float4> combined_light, reduced;
 };
+
+static bool group_has_work(const etxb_group* grp, uint32_t lane) { return grp->sharded ? (grp->lane_next[lane] < grp->enqueued_total) : (grp->pending > 0); }
+static bool group_idle(const etxb_group* grp) {
+  if (grp->in_flight > 0) return false;
+  if (!grp->sharded) return grp->pending == 0;
+  for (uint32_t next : grp->lane_next)
+    if (next < grp->enqueued_total) return false;
+  return true;
+}
 
 static void group_worker(etxb_group* grp, uint32_t lane) {
   cudaSetDevice(grp->device);
   etxb_ctx* ctx = grp->lanes[lane];
   std::unique_lock<std::mutex> lock(grp->m);
   for (;;) {
-    grp->cv_work.wait(lock, [&] { return grp->quit || (grp->pending > 0); });
+    grp->cv_work.wait(lock, [&] { return grp->quit || group_has_work(grp, lane); });
     if (grp->quit) return;
-    uint32_t iteration = grp->first_iteration + (grp->taken++) * grp->stride;
-    grp->pending -= 1;
+    uint32_t ordinal = 0;
+    if (grp->sharded) {
+      ordinal = grp->lane_next[lane];
+      grp->lane_next[lane] += uint32_t(grp->lanes.size());
+      grp->taken = std::max(grp->taken, ordinal + 1u);
+    } else {
+      ordinal = grp->taken++;
+      grp->pending -= 1;
+    }
+    uint32_t iteration = grp->first_iteration + ordinal * grp->stride;
     grp->in_flight += 1;
     lock.unlock();
     int rc = etxb_set_next_iteration(ctx, iteration);
-    if (rc == ETXB_OK) rc = etxb_enqueue_iteration(ctx);  // returns when the iteration has finished (the bounce loops read queue sizes back)
+    if (rc == ETXB_OK) rc = run_iteration_blocking(ctx);  // returns when the iteration has finished (the bounce loops read queue sizes back)
     lock.lock();
     grp->in_flight -= 1;
     grp->last_iteration_seconds = ctx->last_iteration_time;
@@ -1516,8 +1811,9 @@ static void group_worker(etxb_group* grp, uint32_t lane) {
       grp->error = rc;
       grp->error_text = etxb_last_error(ctx);
       grp->pending = 0;
+      for (auto& next : grp->lane_next) next = 0xffffffffu;
     }
-    if ((grp->pending == 0) && (grp->in_flight == 0)) {
+    if (group_idle(grp)) {
       grp->busy_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - grp->busy_since).count();
       grp->cv_idle.notify_all();
     }
@@ -1539,6 +1835,9 @@ int etxb_group_create(etxb_group** out, const etxb_device_config* cfg, uint32_t 
     }
     grp->lanes.push_back(ctx);
   }
+  grp->lane_next.assign(lanes, 0u);
+  cudaSetDevice(grp->device);
+  cudaStreamCreateWithFlags(&grp->stream, cudaStreamNonBlocking);
   for (uint32_t l = 0; l < lanes; ++l) grp->workers.emplace_back(group_worker, grp, l);
   *out = grp;
   return ETXB_OK;
@@ -1555,6 +1854,12 @@ void etxb_group_destroy(etxb_group* grp) {
   for (auto& w : grp->workers) w.join();
   cudaSetDevice(grp->device);
   grp->combined.release();
+  grp->combined_light.release();
+  grp->reduced.release();
+  if (grp->reduce_comm != nullptr) {
+    if (NcclApi* n = nccl_api()) n->CommDestroy(grp->reduce_comm);
+  }
+  if (grp->stream) cudaStreamDestroy(grp->stream);
   for (auto* c : grp->lanes) etxb_destroy(c);
   delete grp;
 }
@@ -1566,7 +1871,7 @@ const char* etxb_group_last_error(const etxb_group* grp) { return grp ? grp->err
 int etxb_group_wait(etxb_group* grp) {
   if (!grp) return ETXB_ERR_INVALID_ARGUMENT;
   std::unique_lock<std::mutex> lock(grp->m);
-  grp->cv_idle.wait(lock, [&] { return (grp->pending == 0) && (grp->in_flight == 0); });
+  grp->cv_idle.wait(lock, [&] { return group_idle(grp); });
   return grp->error;
 }
 
@@ -1578,6 +1883,8 @@ int etxb_group_begin(etxb_group* grp, uint32_t first_iteration) {
   std::lock_guard<std::mutex> lock(grp->m);
   grp->first_iteration = first_iteration;
   grp->taken = 0;
+  grp->enqueued_total = 0;
+  for (uint32_t l = 0; l < grp->lane_next.size(); ++l) grp->lane_next[l] = l;
   grp->busy_seconds = 0.0;
   grp->error = ETXB_OK;
   grp->error_text.clear();
@@ -1597,8 +1904,12 @@ int etxb_group_enqueue(etxb_group* grp, uint32_t iterations) {
     std::lock_guard<std::mutex> lock(grp->m);
     if (grp->error != ETXB_OK) return grp->error;
     if (iterations == 0) return ETXB_OK;
-    if ((grp->pending == 0) && (grp->in_flight == 0)) grp->busy_since = std::chrono::steady_clock::now();
-    grp->pending += iterations;
+    if (group_idle(grp)) grp->busy_since = std::chrono::steady_clock::now();
+    if (grp->sharded) {
+      grp->enqueued_total += iterations;
+    } else {
+      grp->pending += iterations;
+    }
   }
   grp->cv_work.notify_all();
   return ETXB_OK;
@@ -1614,22 +1925,21 @@ int etxb_group_poll(etxb_group* grp, etxb_status* status) {
     status->overflow |= c->overflow_flag;
   }
   status->current_iteration = grp->first_iteration + grp->taken * grp->stride;
-  status->iteration_in_flight = ((grp->pending > 0) || (grp->in_flight > 0)) ? 1u : 0u;
+  status->iteration_in_flight = group_idle(grp) ? 0u : 1u;
   status->last_iteration_time = grp->last_iteration_seconds;
   status->total_time = grp->busy_seconds;
   if (status->iteration_in_flight) status->total_time += std::chrono::duration<double>(std::chrono::steady_clock::now() - grp->busy_since).count();
   return ETXB_OK;
 }
 
-int etxb_group_combine(etxb_group* grp, uint32_t layer, void** device_ptr, uint64_t* bytes, uint32_t* completed) {
-  if (!grp || (layer > ETXB_FILM_LIGHT)) return ETXB_ERR_INVALID_ARGUMENT;
+static int group_combine_into(etxb_group* grp, uint32_t layer, DevBuf<float4>& target, uint32_t* completed) {
   etxb_ctx* first = grp->lanes[0];
   if (!first->scene_ready) return fail(first, ETXB_ERR_NOT_READY, "no scene uploaded");
   size_t n = first->path_count;
   cudaSetDevice(grp->device);
-  if (grp->combined.count < n) {
-    grp->combined.release();
-    CUDA_OK(first, grp->combined.alloc(n));
+  if (target.count < n) {
+    target.release();
+    CUDA_OK(first, target.alloc(n));
   }
   FilmLanes f = {};
   f.lanes = uint32_t(grp->lanes.size());
@@ -1644,11 +1954,79 @@ int etxb_group_combine(etxb_group* grp, uint32_t layer, void** device_ptr, uint6
   }
   // lanes that are still rendering keep updating their films (a preview, like reading the reference's film while it runs); after
   // etxb_group_wait every lane has synchronised its stream and the result is exact
-  k_film_combine<<<blocks_for(f.pixels, 256), 256, 0, first->stream>>>(f, grp->combined.ptr);
-  CUDA_OK(first, cudaStreamSynchronize(first->stream));
-  if (device_ptr) *device_ptr = grp->combined.ptr;
-  if (bytes) *bytes = n * 16;
+  k_film_combine<<<blocks_for(f.pixels, 256), 256, 0, grp->stream>>>(f, target.ptr);
+  CUDA_OK(first, cudaStreamSynchronize(grp->stream));
   if (completed) *completed = total;
+  return ETXB_OK;
+}
+
+int etxb_group_combine(etxb_group* grp, uint32_t layer, void** device_ptr, uint64_t* bytes, uint32_t* completed) {
+  if (!grp || (layer > ETXB_FILM_LIGHT)) return ETXB_ERR_INVALID_ARGUMENT;
+  if (int rc = group_combine_into(grp, layer, grp->combined, completed)) return rc;
+  if (device_ptr) *device_ptr = grp->combined.ptr;
+  if (bytes) *bytes = uint64_t(grp->lanes[0]->path_count) * 16u;
+  return ETXB_OK;
+}
+
+// Pixel tiles over several processes, `lanes` iterations in flight on each: ids = (lanes + 1) NCCL unique ids of 128 bytes, the same on every
+// rank (lane l of every rank forms communicator l; the last one carries the frame reduce).  Collective.
+int etxb_group_comm_init(etxb_group* grp, uint32_t world, uint32_t rank, const void* ids, uint32_t id_count) {
+  if (!grp || !ids || (world == 0u) || (rank >= world) || (id_count != grp->lanes.size() + 1u)) return ETXB_ERR_INVALID_ARGUMENT;
+  if (int rc = etxb_group_wait(grp)) return rc;
+  NcclApi* n = nccl_api();
+  etxb_ctx* first = grp->lanes[0];
+  if (!n) return fail(first, ETXB_ERR_NOT_READY, "libnccl.so.2 could not be loaded");
+  const uint8_t* bytes = static_cast<const uint8_t*>(ids);
+  for (size_t l = 0; l < grp->lanes.size(); ++l) {
+    if (int rc = etxb_comm_init(grp->lanes[l], world, rank, bytes + l * sizeof(ncclUniqueId), sizeof(ncclUniqueId))) {
+      grp->error_text = etxb_last_error(grp->lanes[l]);
+      return rc;
+    }
+  }
+  cudaSetDevice(grp->device);
+  ncclUniqueId uid;
+  memcpy(&uid, bytes + grp->lanes.size() * sizeof(ncclUniqueId), sizeof(uid));
+  NCCL_OK(first, n->CommInitRank(&grp->reduce_comm, int(world), uid, int(rank)));
+  std::lock_guard<std::mutex> lock(grp->m);
+  grp->sharded = world > 1u;
+  grp->world = world;
+  grp->rank = rank;
+  for (uint32_t l = 0; l < grp->lane_next.size(); ++l) grp->lane_next[l] = l;
+  grp->enqueued_total = 0;
+  return ETXB_OK;
+}
+
+// Collective over the ranks of a sharded group: the lanes' films are combined locally (mean weighted by the iterations each lane finished —
+// the same weights on every rank, the lane -> iteration map is fixed), the camera tiles are summed on rank 0, Result = max(0, camera + light).
+int etxb_group_comm_reduce_film(etxb_group* grp, uint32_t layer, float* dst_rgba, uint64_t dst_bytes) {
+  if (!grp || (layer > ETXB_FILM_LIGHT)) return ETXB_ERR_INVALID_ARGUMENT;
+  if (!grp->sharded) return etxb_group_read_film(grp, layer, dst_rgba, dst_bytes);
+  NcclApi* n = nccl_api();
+  etxb_ctx* first = grp->lanes[0];
+  const size_t px = first->path_count;
+  cudaSetDevice(grp->device);
+  if (layer != ETXB_FILM_LIGHT) {
+    if (int rc = group_combine_into(grp, ETXB_FILM_CAMERA, grp->combined, nullptr)) return rc;
+    if (grp->reduced.count < px) CUDA_OK(first, grp->reduced.alloc(px));
+    NCCL_OK(first, n->Reduce(grp->combined.ptr, grp->reduced.ptr, px * 4u, ncclFloat, ncclSum, 0, grp->reduce_comm, grp->stream));
+  }
+  if (grp->rank != 0u) {
+    CUDA_OK(first, cudaStreamSynchronize(grp->stream));
+    return ETXB_OK;
+  }
+  if (!dst_rgba || (dst_bytes < px * 16u)) return fail(first, ETXB_ERR_INVALID_ARGUMENT, "film buffer too small");
+  const float4* src = grp->reduced.ptr;
+  if (layer != ETXB_FILM_CAMERA) {
+    if (int rc = group_combine_into(grp, ETXB_FILM_LIGHT, grp->combined_light, nullptr)) return rc;
+    src = grp->combined_light.ptr;
+  }
+  if (layer == ETXB_FILM_RESULT) {
+    FilmBuffers film = {grp->reduced.ptr, grp->combined_light.ptr, nullptr, first->width, first->height};
+    k_film_resolve<<<blocks_for(uint32_t(px), 256), 256, 0, grp->stream>>>(film, grp->combined.ptr);
+    src = grp->combined.ptr;
+  }
+  CUDA_OK(first, cudaMemcpyAsync(dst_rgba, src, px * 16u, cudaMemcpyDeviceToHost, grp->stream));
+  CUDA_OK(first, cudaStreamSynchronize(grp->stream));
   return ETXB_OK;
 }
 

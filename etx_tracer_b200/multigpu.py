@@ -145,6 +145,22 @@ class ShardedVCM:
         return result
 
 
+def distribute_comm_ids(dist, rank, count, make_ids, device="cuda"):
+    """The one thing the host does for the module's own multi-GPU path (etxb_comm_init / etxb_group_comm_init): rank 0 asks the module for
+    `count` NCCL unique ids (make_ids(count) -> uint8[count * 128]) and every rank receives the same bytes (one broadcast over whatever process
+    group the launcher set up)."""
+    import numpy as np
+    import torch
+    n = count * 128
+    buf = torch.zeros(n, dtype=torch.uint8, device=device)
+    if rank == 0:
+        ids = np.ascontiguousarray(make_ids(count), dtype=np.uint8)
+        assert ids.size == n
+        buf.copy_(torch.from_numpy(ids))
+    dist.broadcast(buf, src=0)
+    return buf.cpu().numpy()
+
+
 class InterleavedVCM:
     """Iteration-interleaved rendering: rank r owns iterations r, r + world, r + 2 world, ...
 

@@ -391,6 +391,23 @@ int etxb_group_read_film(etxb_group* group, uint32_t layer, float* dst_rgba, uin
 /* The same combined layer left on the device (float4[N]) + the number of iterations behind it: what a multi-GPU host reduces. */
 int etxb_group_combine(etxb_group* group, uint32_t layer, void** device_ptr, uint64_t* bytes, uint32_t* completed_iterations);
 
+/* ---- pixel-tile sharding over several GPUs (one process per GPU, NCCL over NVLink) ----------------------------------------
+ * The reference renders one frame with one thread pool (vcm_cpu.cxx:115-241).  Here rank r owns the 32x32 pixel tiles with tile % world == r
+ * (etxb_set_partition's rule) and runs the light and camera subpaths of its pixels; what is global is exchanged INSIDE etxb_enqueue_iteration:
+ * all-reduce of the per-iteration light image (light-tracing splats land on any pixel, vcm_cpu.cxx:147-154 -> film.cxx:332-343) and an
+ * all-gather of the photon records (merging queries every light path's vertices, vcm_cpu.cxx:219-221).  The host only distributes the NCCL id
+ * (any transport: MPI, a file, torch.distributed) — rank 0 calls etxb_comm_unique_id, every rank calls etxb_comm_init with those bytes. */
+#define ETXB_COMM_ID_BYTES 128
+int etxb_comm_unique_id(void* out_id, uint64_t bytes);
+int etxb_comm_init(etxb_ctx* ctx, uint32_t world, uint32_t rank, const void* id, uint64_t bytes); /* collective */
+int etxb_comm_world(const etxb_ctx* ctx, uint32_t* world, uint32_t* rank);
+/* Collective: sums the disjoint camera tiles on rank 0 (ncclReduce of the float4 film); dst_rgba is written on rank 0 only. */
+int etxb_comm_reduce_film(etxb_ctx* ctx, uint32_t layer, float* dst_rgba, uint64_t dst_bytes);
+/* The same with several iterations in flight per GPU: ids = (lanes + 1) x ETXB_COMM_ID_BYTES (one communicator per lane + one for the frame
+ * reduce); lane l renders the iteration ordinals l, l + lanes, ... on every rank. */
+int etxb_group_comm_init(etxb_group* group, uint32_t world, uint32_t rank, const void* ids, uint32_t id_count); /* collective */
+int etxb_group_comm_reduce_film(etxb_group* group, uint32_t layer, float* dst_rgba, uint64_t dst_bytes);        /* collective */
+
 #ifdef __cplusplus
 }
 #endif
