@@ -238,10 +238,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--lanes", type=int, default=4, help="iterations in flight per GPU (etxb_group); 1 = the plain one-context pump")
-    ap.add_argument("--parallelism", default="tile", choices=["tile", "iteration"],
-                    help="N > 1: 'tile' (default, the north star's mode) = every iteration split by pixel tile over the GPUs inside the module (strong "
-                         "scaling, NCCL all-reduce / all-gather per iteration); 'iteration' = every rank renders its own whole-frame iterations "
-                         "(weak scaling, no data-path collective)")
+    ap.add_argument("--parallelism", default="both", choices=["both", "tile", "iteration"],
+                    help="N > 1: how the job's K iterations are spread over the GPUs.  'tile' (the north star's mode) = every iteration split by pixel tile "
+                         "inside the module (NCCL all-reduce / all-gather per iteration); 'iteration' = the K iterations dealt to the ranks (one NCCL "
+                         "film reduce per frame); 'both' (default) measures the two on the same index set and reports the faster as `value`, both under `modes`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -272,34 +272,9 @@ def main():
 
     sd, desc = workload(args)
     n_pixels = sd.width * sd.height
-    tile_mode = world > 1 and args.parallelism == "tile"
-    interleaved = None
     from etx_tracer_b200.api import GPUVCMGroup, comm_unique_ids
     lanes = max(1, min(args.lanes, 8))
-    g = GPUVCMGroup(sd, lanes=lanes, flavor="fast", device=local_rank, profile=True)
-    if tile_mode:
-        # north-star mode: every iteration of the frame is split over the ranks by 32x32 pixel tile INSIDE the module (NCCL communicators created by
-        # etxb_group_comm_init: all-reduce of the light image + all-gather of the photon records per iteration, reduce of the film per frame);
-        # the host only hands out the NCCL ids.  Strong scaling: a step = one whole-frame iteration, whatever the number of GPUs.
-        from etx_tracer_b200.multigpu import distribute_comm_ids
-        ids = distribute_comm_ids(dist, rank, lanes + 1, comm_unique_ids, device=torch.device("cuda", local_rank))
-        g.comm_init(world, rank, ids)
-    elif world > 1:
-        # whole-frame iterations, rank r renders indices r, r + N, ... (weak scaling: a step is one iteration PER RANK, no data-path collective)
-        from etx_tracer_b200.multigpu import InterleavedVCM
-        interleaved = InterleavedVCM(g, dist, rank, world)
-    samples_per_step = n_pixels * (1 if (tile_mode or world == 1) else world)
-    g.options[:] = workload_vcm_options(args)
-
-    def begin():
-        if interleaved:
-            interleaved.begin()
-        else:
-            g.run(0)
-
-    def run_steps(n):
-        g.enqueue(n)
-        g.wait()
+    device = torch.device("cuda", local_rank)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -307,88 +282,105 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing ---------------------------------------------------------------------------------------------
-    begin()
-    run_steps(args.warmup)
-    sync_all()
-    st0 = g.status()
-    c0 = g.counters()
-    k0 = g.kernel_times()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    t_wall = time.time()
-    run_steps(args.steps)
-    sync_all()
-    t_wall = time.time() - t_wall
-    clk = clocks.stop() if rank == 0 else None
-    st1 = g.status()
-    c1 = g.counters()
-    k1 = g.kernel_times()
-    # one context: CUDA events on the module's stream around every iteration.  several iterations in flight: the streams overlap, so the
-    # module reports the span from the first enqueue (every lane idle and synchronised) to the last lane's end-of-iteration synchronise
-    mod_s = st1["total_time"] - st0["total_time"]
-    elapsed = mod_s  # tile mode: the collectives run inside the iterations, on the lanes' streams
-    if world > 1:
-        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+    def all_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
-    value = samples_per_step * args.steps / elapsed / 1e6
-    counters = {k: c1[k] - c0[k] for k in c1}
-    if tile_mode:  # every rank counted its own tiles
-        keys = sorted(counters)
-        t = torch.tensor([float(counters[k]) for k in keys], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        counters = {k: int(v) for k, v in zip(keys, t.tolist())}
-    ktimes = {k: (k1[k][0] - k0[k][0], k1[k][1] - k0[k][1]) for k in k1}
-    comm_ms = {k: round(v[0] / max(args.steps, 1), 3) for k, v in ktimes.items() if k.startswith("nccl_")}
+        return float(t.item())
 
-    # ---- end to end through the public API, host buffers inside the timed region ---------------------------------------------
-    # every step: options host -> module, one more iteration queued, the current film device -> pinned host (what a UI pumping the
-    # integrator does each frame; with iterations in flight the per-step film is the mean over the iterations finished so far); the
-    # region ends when every queued iteration has finished and the final film is on the host
-    pinned = torch.empty((sd.height, sd.width, 4), dtype=torch.float32).pin_memory()
-    host_film = pinned.numpy()
-    begin()
-    run_steps(args.warmup)
-    sync_all()
-    t0 = time.time()
-    film_reads = 0
-    for _ in range(args.steps):
-        if tile_mode:
-            g.set_options()
-            g.enqueue(1)
-            g.comm_reduce_film(S.FILM_RESULT, out=host_film)  # collective: ncclReduce of the camera tiles, Result layer to rank 0's host buffer
-        else:
-            g.set_options()
-            g.enqueue(1)
-            if interleaved:
-                combined = interleaved.reduce_film()
-                if rank == 0:
-                    pinned.view(-1, 4).copy_(combined)
+    def measure(mode):
+        """One way of running the SAME job — the K whole-frame iterations with indices W .. W+K-1 — on `world` GPUs:
+          single     one GPU, `lanes` iterations in flight
+          tile       (north star) every iteration split by 32x32 pixel tile over the ranks INSIDE the module: per iteration ncclAllReduce of the light
+                     image + all-gather of the photon records, per frame ncclReduce of the film (etxb_group_comm_init); `lanes` iterations in flight
+          iteration  the K iterations dealt to the ranks (index j on rank j % world), no collective inside an iteration, one count-weighted
+                     ncclReduce of the films per frame (etxb_group_comm_init_replicas)
+        Strong scaling in every mode: a step = one whole-frame iteration of the job, value = W*H*K / time (max over ranks)."""
+        from etx_tracer_b200.multigpu import distribute_comm_ids
+        g = GPUVCMGroup(sd, lanes=lanes, flavor="fast", device=local_rank, profile=True)
+        if mode == "tile":
+            g.comm_init(world, rank, distribute_comm_ids(dist, rank, lanes + 1, comm_unique_ids, device=device))
+        elif mode == "iteration":
+            g.comm_init_replicas(world, rank, distribute_comm_ids(dist, rank, 1, comm_unique_ids, device=device))
+        g.options[:] = workload_vcm_options(args)
+        multi = mode != "single"
+        warm = args.warmup * (world if mode == "iteration" else 1)  # every rank warms up on `warmup` iterations of its own
+
+        def film_to_host(out):
+            if multi:
+                g.comm_reduce_film(S.FILM_RESULT, out=out)  # collective: ncclReduce to rank 0, then device -> host there
             else:
-                g.film(S.FILM_RESULT, out=host_film)
+                g.film(S.FILM_RESULT, out=out)
+
+        # ---- device-resident timing: warm-up on indices 0.., then the timed index set W .. W+K-1 from a cleared film
+        g.run(0)
+        g.enqueue(warm)
+        g.wait()
+        sync_all()
+        g.run(args.warmup)
+        c0, k0 = g.counters(), g.kernel_times()
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        g.enqueue(args.steps)
+        g.wait()
+        sync_all()
+        clk = clocks.stop() if rank == 0 else None
+        st1, c1, k1 = g.status(), g.counters(), g.kernel_times()
+        # several iterations in flight: the streams overlap, so the module reports the span from the first enqueue (every lane idle and synchronised)
+        # to the last lane's end-of-iteration synchronise; max over ranks
+        elapsed = all_max(st1["total_time"])
+        counters = {k: c1[k] - c0[k] for k in c1}
+        if multi:  # every rank counted its own share
+            keys = sorted(counters)
+            t = torch.tensor([float(counters[k]) for k in keys], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            counters = {k: int(v) for k, v in zip(keys, t.tolist())}
+        ktimes = {k: (k1[k][0] - k0[k][0], k1[k][1] - k0[k][1]) for k in k1}
+        mine = max(1, sum(1 for j in range(args.steps) if (mode != "iteration") or (j % world == rank)))
+        comm_ms = {k: round(v[0] / mine, 3) for k, v in ktimes.items() if k.startswith("nccl_")}
+
+        # ---- end to end through the public API, host buffers inside the timed region: every step pushes the options host -> module, queues one
+        # more iteration of the job and brings the current frame (mean over the iterations finished so far) device -> pinned host; the region ends
+        # when every queued iteration has finished and the final frame is on the host
+        pinned = torch.empty((sd.height, sd.width, 4), dtype=torch.float32).pin_memory()
+        host_film = pinned.numpy()
+        g.run(0)
+        g.enqueue(warm)
+        g.wait()
+        sync_all()
+        g.run(args.warmup)
+        t0 = time.time()
+        film_reads = 0
+        for _ in range(args.steps):
+            g.set_options()
+            g.enqueue(1)
+            film_to_host(host_film)
+            film_reads += 1
+        g.wait()
+        film_to_host(host_film)
         film_reads += 1
-    g.wait()
-    if tile_mode:
-        g.comm_reduce_film(S.FILM_RESULT, out=host_film)
-        film_reads += 1
+        sync_all()
+        e2e_s = all_max(time.time() - t0)
+        finite = bool(np.isfinite(host_film).all()) if rank == 0 else True
+        light_vertices = st1["light_vertices"]
+        g.close()
+        return {"mode": mode, "value": n_pixels * args.steps / elapsed / 1e6, "elapsed": elapsed, "counters": counters, "clocks": clk,
+                "e2e": {"value": n_pixels * args.steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(g.options.nbytes) * lanes,
+                        "d2h_bytes_per_step": int(host_film.nbytes * film_reads / args.steps)},
+                "collective_ms_per_iteration": comm_ms or None, "film_finite": finite, "light_vertices": light_vertices}
+
+    if world == 1:
+        results = [measure("single")]
+    elif args.parallelism == "both":
+        results = [measure("tile"), measure("iteration")]
     else:
-        if interleaved:
-            combined = interleaved.reduce_film()
-            if rank == 0:
-                pinned.view(-1, 4).copy_(combined)
-        else:
-            g.film(S.FILM_RESULT, out=host_film)
-        film_reads += 1
-    sync_all()
-    e2e_s = time.time() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": samples_per_step * args.steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(g.options.nbytes) * lanes,
-           "d2h_bytes_per_step": int(host_film.nbytes * film_reads / args.steps)}
+        results = [measure(args.parallelism)]
+    best = max(results, key=lambda r: r["value"])
+    tile_mode = best["mode"] == "tile"
+    value, elapsed, counters, e2e, clk = best["value"], best["elapsed"], best["counters"], best["e2e"], best["clocks"]
+    st1 = {"light_vertices": best["light_vertices"]}
 
     if rank == 0:
         peaks = measured_peaks()
@@ -449,7 +441,7 @@ def main():
                    "tris_per_ray": cc["tris_tested"] / max(cc["rays_closest"] + cc["rays_shadow"], 1),
                    "bytes_per_iteration": int(it_bvh),
                    "step_algorithmic_GBps_without_bvh": total_bytes / elapsed / 1e9,
-                   "step_algorithmic_GBps_with_bvh": (total_bytes + it_bvh * args.steps * (world if not tile_mode else 1)) / elapsed / 1e9,
+                   "step_algorithmic_GBps_with_bvh": (total_bytes + it_bvh * args.steps) / elapsed / 1e9,
                    "trace_closest_GBps_without_bvh": trace_bytes / max(trace_ms * 1e-3, 1e-12) / 1e9,
                    "trace_closest_GBps_with_bvh": (trace_bytes + it_bvh_closest) / max(trace_ms * 1e-3, 1e-12) / 1e9}
             bvh["step_frac_without_bvh"] = bvh["step_algorithmic_GBps_without_bvh"] / peak
@@ -480,26 +472,31 @@ def main():
             from etx_tracer_b200 import scenes
             cpu, _ = cpu_baseline_run(lambda res: scene_factory(args, res), args.cpu_budget, os.cpu_count() or 1, workload_vcm_options(args))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if tile_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc,
-                           "parallelism": (f"pixel tiles (32x32, round-robin) over {world} GPUs inside the module, {lanes} iterations in flight per GPU; per iteration: "
-                                           f"ncclAllReduce of the light image + all-gather of the photon records; per frame: ncclReduce of the film" if tile_mode else
-                                           f"{lanes} iterations in flight per GPU" + (f"; iteration-interleaved x{world}: a step = one whole-frame iteration per rank "
-                                                                                      f"(indices rank + j*{world}), one film reduce" if world > 1 else "")),
-                           "collective_ms_per_iteration": (comm_ms if tile_mode else None),
+                           "parallelism": {"single": f"one GPU, {lanes} iterations in flight",
+                                           "tile": f"pixel tiles (32x32, round-robin) over {world} GPUs inside the module, {lanes} iterations in flight per GPU; per iteration "
+                                                   f"ncclAllReduce of the light image + all-gather of the photon records, per frame ncclReduce of the film",
+                                           "iteration": f"the job's iterations dealt to {world} GPUs (index j on rank j % {world}), {lanes} in flight per GPU; per frame one "
+                                                        f"count-weighted ncclReduce of the films"}[best["mode"]],
+                           "mode": best["mode"],
+                           "collective": None if world == 1 else "NCCL (communicators created inside the module: etxb_group_comm_init / etxb_group_comm_init_replicas)",
+                           "collective_ms_per_iteration": best["collective_ms_per_iteration"],
                            "timing": ("span from the first enqueue (all lanes idle, device synchronised) to the last lane's end-of-iteration stream synchronise, max over ranks"),
                            "l2": "inputs larger than L2 (path state + light-vertex pool + photon grid > 126 MB)",
                            "iterations": f"a fixed index set: {args.warmup} warm-up iterations (indices 0..{args.warmup - 1}), then the timed indices "
                                          f"{args.warmup}..{args.warmup + args.steps - 1} of the 1/(1 + i/256) merge-radius schedule (the most expensive end of a render)",
                            "light_vertices_per_iteration": st1["light_vertices"], "per_kernel_event_timing": True},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(counters["kernel_launches"]), "clocks": clk,
-                "counters": counters}
+                "counters": counters,
+                # every way of spreading the same K iterations that was measured in this run (N > 1, --parallelism both): `value` is the faster one
+                "modes": {r["mode"]: {"value": r["value"], "ms_per_step": r["elapsed"] / args.steps * 1e3, "e2e": r["e2e"]["value"],
+                                      "collective_ms_per_iteration": r["collective_ms_per_iteration"], "film_finite": r["film_finite"]} for r in results}}
         if json_fd is not None:
             sys.stdout.flush()
             os.write(json_fd, (json.dumps(line) + "\n").encode())
         else:
             print(json.dumps(line), flush=True)
-    g.close()
     if dist:
         dist.destroy_process_group()
 

@@ -232,6 +232,29 @@ void build_bvh(const float* positions, uint32_t position_stride_bytes, const uin
   b.build(0, tri_count, root_box, true);
 
   out.max_depth = b.max_depth;
+  // breadth-first node order: nodes[0 .. k) are then the top levels of the tree, which the traversal kernels copy into shared memory in one bulk
+  // transfer (dtrav.cuh).  Only indices move — boxes, child order and leaves stay, so every traversal visits the same candidates in the same order.
+  {
+    const size_t n = b.nodes.size();
+    std::vector<uint32_t> order_bfs;
+    order_bfs.reserve(n);
+    std::vector<uint32_t> new_index(n, 0u);
+    order_bfs.push_back(0u);
+    for (size_t head = 0; head < order_bfs.size(); ++head) {
+      const BvhNode& nd = b.nodes[order_bfs[head]];
+      new_index[order_bfs[head]] = uint32_t(head);
+      if (nd.child0 >= 0) order_bfs.push_back(uint32_t(nd.child0));
+      if ((nd.child1 >= 0) && (nd.child1 != nd.child0)) order_bfs.push_back(uint32_t(nd.child1));
+    }
+    std::vector<BvhNode> reordered(order_bfs.size());
+    for (size_t k = 0; k < order_bfs.size(); ++k) {
+      BvhNode nd = b.nodes[order_bfs[k]];
+      if (nd.child0 >= 0) nd.child0 = int32_t(new_index[uint32_t(nd.child0)]);
+      if (nd.child1 >= 0) nd.child1 = int32_t(new_index[uint32_t(nd.child1)]);
+      reordered[k] = nd;
+    }
+    b.nodes = std::move(reordered);
+  }
   out.nodes = std::move(b.nodes);
   out.tri_index = std::move(b.leaf_tris);
   out.tri_pos.resize(out.tri_index.size() * 3);

@@ -41,8 +41,9 @@ struct DeviceScene {
   const etxb_emitter* emitters;
   const DSpectrum* spectra;
   const etxb_distribution_entry* emitter_dist;  // E + 1 entries
-  const BvhNode* bvh_nodes;
+  const BvhNode* bvh_nodes;  // breadth-first order: the first nodes are the top levels (dtrav.cuh stages them in shared memory)
   const float4* bvh_tris;
+  uint32_t bvh_node_count;
   const float* xyz_table;           // 441 x 3
   const float* rgb_response_table;  // 391 x 3
   const uint8_t* bn_sobol;          // 256 x 256

@@ -601,7 +601,7 @@ DEV bool vcm_handle_boundary(const DeviceScene& sc, const Isect& isect, PathStat
 // vcm_connect_to_camera (vcm_shared.hxx:463-535)
 template <bool SP, bool PLAIN = false>
 DEV bool vcm_connect_to_camera(const DeviceScene& sc, const VcmParams& it, const Endpoint& ep, PathState<SP>& state, Spec<SP>& out_value, V2& uv, TraverseStats* stats,
-  uint32_t& shadow_rays) {
+  uint32_t& shadow_rays, V3* deferred_segment = nullptr) {
   if ((it.connect_to_camera() == false) || (state.total_path_depth + 2 > sc.max_path_length) || (state.total_path_depth + 2 < sc.min_path_length)) return false;
   const etxb_camera& camera = sc.camera;
   V3 sample_pos = ep.pos();
@@ -648,8 +648,14 @@ DEV bool vcm_connect_to_camera(const DeviceScene& sc, const VcmParams& it, const
   float cos_t = fabsf(dot(cs.direction, cam3(camera.direction)));
   V3 clip_pos = origin + cs.direction * fmaxf(0.0f, len - camera.clip_near / cos_t);
   shadow_rays += 1;
-  Spec<SP> tr = trace_transmittance<SP, PLAIN>(sc, state.wavelength, origin, clip_pos, state.medium_index, state.sampler, stats);
-  if (tr.is_zero()) return false;
+  Spec<SP> tr = Spec<SP>::make(1.0f);
+  if (deferred_segment != nullptr) {  // the caller queues the segment (ShadowBatch, atomic mode); out_value is the unoccluded contribution
+    deferred_segment[0] = origin;
+    deferred_segment[1] = clip_pos;
+  } else {
+    tr = trace_transmittance<SP, PLAIN>(sc, state.wavelength, origin, clip_pos, state.medium_index, state.sampler, stats);
+    if (tr.is_zero()) return false;
+  }
   uv = cs.uv;
   float camera_pdf = cs.pdf_dir_out * (ep.at_medium ? 1.0f : fabsf(dot(ep.isect->nrm, w_o))) / dist2;
   float vmW_cam = ep.at_medium ? 0.0f : it.vm_weight;
@@ -691,16 +697,26 @@ struct ShadowBatch {
   float4* p1;
   float4* value;
   uint32_t base, count;
+  // Product build, opaque scenes with stochastic BSDFs (no slot order to keep: those stages already run on derived sampler streams): segments
+  // from every producer of a bounce go to ONE list through an atomic cursor, each carrying the address its contribution is added to when the
+  // segment turns out unoccluded (k_shadow_resolve): a path's `gathered` sum, or a pixel of the light image (bit 31 set).
+  uint32_t* atomic_cursor = nullptr;
+  uint32_t capacity = 0;
+  uint32_t target = 0;
   template <bool SP>
   DEV void push(V3 a, V3 b, Spec<SP> v) {
-    uint32_t k = base + count;
+    push_rgb(a, b, v.as_v3());
+  }
+  DEV void push_rgb(V3 a, V3 b, V3 c) {
+    uint32_t k = (atomic_cursor != nullptr) ? atomicAdd(atomic_cursor, 1u) : (base + count);
     count += 1u;
-    V3 c = v.as_v3();
+    if ((atomic_cursor != nullptr) && (k >= capacity)) return;  // the host sized the list for every segment a bounce can produce; the resolver clamps
     p0[k] = make_float4(a.x, a.y, a.z, 0.0f);
-    p1[k] = make_float4(b.x, b.y, b.z, 0.0f);
+    p1[k] = make_float4(b.x, b.y, b.z, (atomic_cursor != nullptr) ? __uint_as_float(target) : 0.0f);
     value[k] = make_float4(c.x, c.y, c.z, 0.0f);
   }
 };
+constexpr uint32_t kShadowTargetPixel = 0x80000000u;
 
 // vcm_connect_to_light (vcm_shared.hxx:608-671)
 template <bool SP, bool PLAIN = false>

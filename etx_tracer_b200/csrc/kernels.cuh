@@ -14,6 +14,7 @@
 #include "dvcm.cuh"
 #include "dsss.cuh"
 #include "dclosure.cuh"
+#include "dtrav.cuh"
 
 // resident blocks per SM the bounce / connection kernels are compiled for (128 threads each: 4 blocks = 128 registers per thread).
 // Measured on the B200 (bench.py --lanes 1): 1|1 -> 4|4 gives C2 11.04 -> 11.36 and C3 5.55 -> 5.79 Msamples/s; 2 and 3 change nothing.
@@ -90,6 +91,8 @@ struct LaunchParams {
   uint32_t* shadow_count;        // [0] rays reserved this bounce, [1] work cursor of k_shadow_trace
   uint32_t shadow_capacity;
   uint32_t shadow_stage;         // 1: the scene qualifies (DeviceScene::deferred_shadow_rays) and the buffers exist
+  uint32_t shadow_atomic;        // 1 (product build, opaque scenes with stochastic BSDFs): the shadow segments of NEE, vertex connections and
+                                 //    light-to-camera connections go to the shadow list with their target address; k_shadow_resolve adds the unoccluded ones
   uint32_t closures;             // 1 (product build): connections and the generic gather evaluate vertex closures (dclosure.cuh); 0: A/B switch
   uint32_t merge_material_major; // 1: the gather queue is ordered by (material, Morton code) instead of the Morton code alone (ETXB_MERGE_MATERIAL_MAJOR=1)
   uint32_t connect_deferred;     // 1 (needs shadow_stage): the camera-vertex x light-vertex connections of such a scene run one per thread in
@@ -230,21 +233,32 @@ __global__ void __launch_bounds__(256) k_trace_closest(const __grid_constant__ L
 #endif
 }
 
-// Film::atomic_add_light_iteration (film.cxx:147-171) of one light-tracing contribution (vcm_cpu.cxx:147-154)
+// Film::atomic_add_light_iteration (film.cxx:147-171) of one light-tracing contribution (vcm_cpu.cxx:147-154), in two halves: value -> RGB and
+// pixel (false: below the driver's cut or off the film), then the three float atomics
 template <bool SP>
-DEV uint32_t splat_light(const LaunchParams& p, Spec<SP> value, V2 uv, float wavelength) {
-  V3 val = spec_to_rgb<SP>(p.scene, value, wavelength) / sampling_pdf<SP>(wavelength);
-  if (!(dot(val, val) > kEpsilon)) return 0u;
+DEV bool splat_prepare(const LaunchParams& p, Spec<SP> value, V2 uv, float wavelength, V3& rgb, uint32_t& pixel, uint32_t& counted) {
+  rgb = spec_to_rgb<SP>(p.scene, value, wavelength) / sampling_pdf<SP>(wavelength);
+  if (!(dot(rgb, rgb) > kEpsilon)) return false;
+  counted = 1u;
   V2 uv01 = uv * 0.5f + 0.5f;
   uint32_t x = static_cast<uint32_t>(uv01.x * float(p.film.width));
   uint32_t y = static_cast<uint32_t>(uv01.y * float(p.film.height));
-  if ((x < p.film.width) && (y < p.film.height)) {
-    float* dst = reinterpret_cast<float*>(p.film.light_iteration + (x + (p.film.height - 1u - y) * p.film.width));
-    atomicAdd(dst + 0, val.x);
-    atomicAdd(dst + 1, val.y);
-    atomicAdd(dst + 2, val.z);
-  }
-  return 1u;
+  if ((x >= p.film.width) || (y >= p.film.height)) return false;
+  pixel = x + (p.film.height - 1u - y) * p.film.width;
+  return true;
+}
+DEV void splat_add(const LaunchParams& p, uint32_t pixel, V3 rgb) {
+  float* dst = reinterpret_cast<float*>(p.film.light_iteration + pixel);
+  atomicAdd(dst + 0, rgb.x);
+  atomicAdd(dst + 1, rgb.y);
+  atomicAdd(dst + 2, rgb.z);
+}
+template <bool SP>
+DEV uint32_t splat_light(const LaunchParams& p, Spec<SP> value, V2 uv, float wavelength) {
+  V3 rgb;
+  uint32_t pixel = 0, counted = 0;
+  if (splat_prepare<SP>(p, value, uv, wavelength, rgb, pixel, counted)) splat_add(p, pixel, rgb);
+  return counted;
 }
 
 // store one light vertex in allocation order (k_lv_reorder makes the pool path-major)
@@ -364,9 +378,23 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_light_bounce(co
         state.sampler.push_fixed(rnd_connection.x, rnd_connection.y, rnd_support.y);
         Spec<SP> value;
         V2 uv;
-        bool ok = vcm_connect_to_camera<SP, PLAIN>(sc, p.vcm, ep, state, value, uv, stats, shadow_rays);
+        V3 segment[2];
+        const bool defer = PLAIN && (p.shadow_atomic != 0u);
+        bool ok = vcm_connect_to_camera<SP, PLAIN>(sc, p.vcm, ep, state, value, uv, stats, shadow_rays, defer ? segment : nullptr);
         state.sampler.pop_fixed();
-        if (ok && (value.maximum() > kEpsilon)) splats += splat_light<SP>(p, (ep_mode == kEpSubsurface) ? (w * value) : value, uv, state.wavelength);
+        if (ok && (value.maximum() > kEpsilon)) {
+          if (defer) {
+            // the segment goes to the bounce's shadow list with the pixel it lands on; k_shadow_resolve splats it if nothing is in between
+            V3 rgb;
+            uint32_t pixel = 0, counted = 0;
+            if (splat_prepare<SP>(p, value, uv, state.wavelength, rgb, pixel, counted)) {
+              ShadowBatch batch = {p.shadow_p0, p.shadow_p1, p.shadow_value, 0u, 0u, p.shadow_count, p.shadow_capacity, pixel | kShadowTargetPixel};
+              batch.push_rgb(segment[0], segment[1], rgb);
+            }
+          } else {
+            splats += splat_light<SP>(p, (ep_mode == kEpSubsurface) ? (w * value) : value, uv, state.wavelength);
+          }
+        }
       }
     }
     // ---- (C) ----
@@ -706,6 +734,13 @@ __global__ void __launch_bounds__(128, ETXB_BOUNCE_MIN_BLOCKS) k_camera_shade(co
         reserved = p.paths.lv_count[i] + 1u;
         batch.base = atomicAdd(p.shadow_count, reserved);
         if (batch.base + reserved <= p.shadow_capacity) deferred = &batch;  // otherwise this vertex traces inline (same result)
+      } else if (PLAIN && p.shadow_atomic && (ep_mode == kEpSurface)) {
+        // product build, opaque scene: the emitter-sample segment joins the bounce's shadow list; its contribution is added to this path's
+        // `gathered` by k_shadow_resolve
+        batch.atomic_cursor = p.shadow_count;
+        batch.capacity = p.shadow_capacity;
+        batch.target = i;
+        deferred = &batch;
       }
 #pragma unroll 1
       for (uint32_t k = 0; k < n; ++k) {
@@ -904,7 +939,12 @@ __global__ void __launch_bounds__(128, ETXB_CONNECT_MIN_BLOCKS) k_camera_connect
     const bool connected = p.closures ? vcm_connect_to_light_vertex_closure<SP>(sc, p.vcm, state, lv, isect, target_position, value)
                                       : vcm_connect_to_light_vertex<SP>(sc, p.vcm, state, lv, ep, target_position, value);
 #endif
-    if (connected) {
+    if (connected && PLAIN && p.shadow_atomic) {
+      shadow_rays += 1;
+      V3 p0 = shading_pos(sc, load_triangle(sc, isect.triangle_index), isect.barycentric, normalize(target_position - isect.pos));
+      ShadowBatch batch = {p.shadow_p0, p.shadow_p1, p.shadow_value, 0u, 0u, p.shadow_count, p.shadow_capacity, i};
+      batch.push<SP>(p0, target_position, value);
+    } else if (connected) {
       shadow_rays += 1;
       Spec<SP> tr = vcm_connection_transmittance<SP, PLAIN>(sc, ep, lv, target_position, state, stats);
       if (tr.is_zero() == false) {
@@ -1846,6 +1886,141 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_tiled
   counter_add(&p.counters->merge_queries, merge_queries);
   counter_add(&p.counters->merge_candidates, candidates);
   counter_add(&p.counters->merge_accepts, accepts);
+}
+
+// Closest hit for every queued path (Raytracing::trace, rt.cxx:428-466) on persistent warps with the top of the BVH in shared memory and lane
+// refill (dtrav.cuh).  Same per-ray walk, candidate order and sampler draws as k_trace_closest / the oracle.
+struct ClosestHitVisitor {
+  const DeviceScene& sc;
+  Smp* smp;
+  HitRec* best;
+  DEV int operator()(uint32_t triangle_index, float u, float v, float t) {
+    const etxb_material& mat = sc.materials[load_triangle_material(sc, triangle_index)];
+    if (mat.cls == ETXB_MAT_VOID) return kCandIgnore;
+    if (alpha_test_rejects(sc, mat, triangle_index, u, v, *smp)) return kCandIgnore;
+    *best = {u, v, t, triangle_index};
+    return kCandAccept;
+  }
+};
+__global__ void __launch_bounds__(256) k_trace_closest_persistent(const __grid_constant__ LaunchParams p, const uint32_t* queue, const uint32_t* queue_count, uint32_t* material_keys,
+                                                                  uint32_t key_limit, uint32_t* cursor) {
+  __shared__ __align__(128) BvhNode s_nodes[kNodeletNodes];
+  __shared__ __align__(8) uint64_t s_bar;
+  const uint32_t staged = nodelet_stage(s_nodes, &s_bar, p.scene.bvh_nodes, p.scene.bvh_node_count);
+  const StagedNodes nodes{s_nodes, p.scene.bvh_nodes, staged};
+  const uint32_t total = *queue_count;
+  // the host sorts `key_limit` (its upper bound of the queue size) slots by material: slots past the device-side count sort last
+  if (material_keys != nullptr) {
+    for (uint32_t q = total + blockIdx.x * blockDim.x + threadIdx.x; q < key_limit; q += gridDim.x * blockDim.x) material_keys[q] = 0x100u;
+  }
+  bool active = false, exhausted = false;
+  uint32_t q = 0, i = 0, n_nodes = 0, n_tris = 0, rays = 0;
+  RayWalk walk;
+  int32_t stack[kBvhStackSize];
+  Smp smp;
+  smp.seed = 0;
+  smp.fixed_u = smp.fixed_v = smp.fixed_w = 0.0f;
+  HitRec best = {0.0f, 0.0f, 0.0f, kInvalidIndex};
+  ClosestHitVisitor visit{p.scene, &smp, &best};
+  for (;;) {
+    uint32_t next = 0;
+    if (warp_refill(!active, cursor, total, next, exhausted)) {
+      q = next;
+      i = queue[q];
+      float4 o = p.paths.ray_o[i], d = p.paths.ray_d[i];
+      smp.seed = p.paths.misc[i].x;
+      best = {0.0f, 0.0f, 0.0f, kInvalidIndex};
+      walk.begin({o.x, o.y, o.z}, {d.x, d.y, d.z}, o.w, d.w);
+      active = true;
+      rays += 1u;
+    }
+    if (!__any_sync(0xffffffffu, active)) break;
+    while (active) {
+      if (walk_step(walk, stack, nodes, p.scene.bvh_tris, visit, n_nodes, n_tris)) {
+        p.paths.hit[i] = make_float4(best.u, best.v, best.t, __uint_as_float(best.tri));
+        p.paths.misc[i].x = smp.seed;
+        if (material_keys != nullptr) material_keys[q] = (best.tri == kInvalidIndex) ? 0xffu : umin(load_triangle_material(p.scene, best.tri), 0xfeu);
+        active = false;
+      } else if (!exhausted && (__popc(__activemask()) < kRefillLanes)) {
+        break;  // too few lanes left in this walk: go and fetch rays for the idle ones
+      }
+    }
+  }
+  counter_add(&p.counters->rays_closest, rays);
+#ifdef ETXB_COUNT_TRAVERSAL
+  counter_add(&p.counters->nodes, n_nodes);
+  counter_add(&p.counters->tris, n_tris);
+  counter_add(&p.counters->nodes_closest, n_nodes);
+  counter_add(&p.counters->tris_closest, n_tris);
+#endif
+}
+
+// The shadow segments of one bounce (ShadowBatch, atomic mode): any-hit on the same persistent, nodelet-staged, lane-refilled walk; a segment
+// that reaches its end adds its contribution to its target (a path's gathered sum, or a pixel of the light image).  Opaque scenes only: any
+// non-Void surface on the segment occludes (rt.cxx:468-579 without Boundary crossings).
+__global__ void __launch_bounds__(256) k_shadow_resolve(const __grid_constant__ LaunchParams p, uint32_t* cursor) {
+  __shared__ __align__(128) BvhNode s_nodes[kNodeletNodes];
+  __shared__ __align__(8) uint64_t s_bar;
+  const uint32_t staged = nodelet_stage(s_nodes, &s_bar, p.scene.bvh_nodes, p.scene.bvh_node_count);
+  const StagedNodes nodes{s_nodes, p.scene.bvh_nodes, staged};
+  const uint32_t total = umin(p.shadow_count[0], p.shadow_capacity);
+  bool active = false, exhausted = false;
+  uint32_t k = 0, n_nodes = 0, n_tris = 0, splats = 0;
+  RayWalk walk;
+  int32_t stack[kBvhStackSize];
+  OcclusionVisitor visit{p.scene, false};
+  auto contribute = [&](uint32_t slot, uint32_t target) {
+    float4 v = p.shadow_value[slot];
+    if (target & kShadowTargetPixel) {
+      splat_add(p, target & ~kShadowTargetPixel, V3{v.x, v.y, v.z});
+      splats += 1u;
+    } else {
+      float* dst = reinterpret_cast<float*>(p.paths.gathered + target);
+      atomicAdd(dst + 0, v.x);
+      if (p.scene.spectral == 0u) {
+        atomicAdd(dst + 1, v.y);
+        atomicAdd(dst + 2, v.z);
+      }
+    }
+  };
+  uint32_t target = 0;
+  for (;;) {
+    uint32_t next = 0;
+    if (warp_refill(!active, cursor, total, next, exhausted)) {
+      k = next;
+      float4 a = p.shadow_p0[k], b = p.shadow_p1[k];
+      target = __float_as_uint(b.w);
+      V3 direction = V3{b.x, b.y, b.z} - V3{a.x, a.y, a.z};
+      float t_max = dot(direction, direction);
+      if (t_max <= kRayEpsilon) {
+        contribute(k, target);  // a degenerate segment is unoccluded (rt.cxx:474-477)
+      } else {
+        t_max = sqrtf(t_max);
+        direction /= t_max;
+        t_max -= fmaxf(kRayEpsilon, t_max * kRayEpsilon);
+        walk.begin({a.x, a.y, a.z}, direction, kRayEpsilon, t_max);
+        visit.occluded = false;
+        active = true;
+      }
+    }
+    if (!__any_sync(0xffffffffu, active)) {
+      if (exhausted) break;
+      continue;
+    }
+    while (active) {
+      if (walk_step(walk, stack, nodes, p.scene.bvh_tris, visit, n_nodes, n_tris)) {
+        if (!visit.occluded) contribute(k, target);
+        active = false;
+      } else if (!exhausted && (__popc(__activemask()) < kRefillLanes)) {
+        break;
+      }
+    }
+  }
+  counter_add(&p.counters->splats, splats);
+#ifdef ETXB_COUNT_TRAVERSAL
+  counter_add(&p.counters->nodes, n_nodes);
+  counter_add(&p.counters->tris, n_tris);
+#endif
 }
 
 // The deferred shadow rays of one camera bounce (ShadowBatch, dvcm.cuh): a traversal-only kernel — persistent warps take 32 segments at a

@@ -100,6 +100,9 @@ struct etxb_ctx {
                                       // round 2: C3 generic gather 60.6 -> 46.1 ms per iteration; ETXB_MERGE_MATERIAL_MAJOR=0 switches it off)
   bool plain_kernels = true;          // bounce kernels specialised for scenes without media / Boundary surfaces / subsurface (ETXB_PLAIN_KERNELS=0: general ones)
   bool plain_scene = false;           // set at upload: the scene qualifies
+  bool opaque_scene = false;          // set at upload: no alpha test can reject a hit (every opacity 1, no alpha images), no Boundary surfaces / media
+  bool shadow_atomic = true;          // product build, opaque scenes with stochastic BSDFs: shadow segments resolved by k_shadow_resolve (ETXB_SHADOW_ATOMIC=0: inline)
+  bool persistent_trace = true;       // closest hits on the persistent, nodelet-staged kernel (ETXB_TRACE_PERSISTENT=0: thread-per-ray k_trace_closest)
   bool merge_closure = true;          // generic photon gather on vertex closures (dclosure.cuh; ETXB_MERGE_CLOSURE=0: the batched generic kernel of round 1)
   bool merge_batched = true;          // generic photon gather batches its BSDF evaluations across the queries of a warp (ETXB_MERGE_BATCHED=0: per query)
   bool sort_by_material = true;       // group path queues and the connection list by material where BSDFs are costly (ETXB_SORT_MATERIAL=0: A/B switch)
@@ -137,7 +140,7 @@ struct etxb_ctx {
   DevBuf<uint32_t> lv_count, lp_offset, queue_a, queue_b, queue_counts, sampler_end_light, sampler_end_camera, merge_key, conn_seed, conn_count;
   DevBuf<uint2> conn_list, shadow_span;
   DevBuf<float4> shadow_p0, shadow_p1, shadow_value;
-  DevBuf<uint32_t> shadow_result, shadow_count;
+  DevBuf<uint32_t> shadow_result, shadow_count, trace_cursor;
   // light vertices + grid
   uint32_t lv_capacity = 0, max_light_vertices_cfg = 0;
   DevBuf<LightVertexRec> lv_tmp, lv_final;
@@ -163,6 +166,9 @@ struct etxb_ctx {
 
   // pixel-tile sharding across processes (one per GPU): NCCL communicator over NVLink, created by etxb_comm_init
   ncclComm_t comm = nullptr;
+  cudaStream_t comm_stream = nullptr;  // highest priority: a collective's few CTAs start as soon as ANY slot frees up instead of queueing behind the
+                                       // tens of thousands of blocks of another lane's kernel (measured, 2 GPUs x 4 lanes: 43 ms per all-reduce waiting otherwise)
+  cudaEvent_t comm_ev_in = nullptr, comm_ev_out = nullptr;
   DevBuf<uint32_t> comm_counts;   // [world] stored light vertices per rank (all-gathered every iteration)
   DevBuf<float4> film_reduced;    // rank 0: sum of every rank's camera tiles (etxb_comm_reduce_film)
   double comm_ms = 0.0;           // device time of the collectives of the iterations since etxb_begin
@@ -346,6 +352,11 @@ LaunchParams make_params(etxb_ctx* ctx) {
   p.shadow_capacity = uint32_t(ctx->shadow_p0.count);
   p.shadow_stage = (ctx->dscene.deferred_shadow_rays && ctx->shadow_p0.count) ? 1u : 0u;
   p.connect_deferred = (p.shadow_stage && ctx->connect_deferred) ? 1u : 0u;
+#if defined(ETXB_PARITY) && ETXB_PARITY
+  p.shadow_atomic = 0;
+#else
+  p.shadow_atomic = (ctx->shadow_atomic && !p.shadow_stage && ctx->opaque_scene && ctx->plain_scene && ctx->plain_kernels && ctx->has_stochastic_merge && ctx->shadow_p0.count) ? 1u : 0u;
+#endif
   p.closures = ctx->merge_closure ? 1u : 0u;
   p.merge_material_major = (ctx->merge_material_major && ctx->has_stochastic_merge) ? 1u : 0u;
 #if defined(ETXB_PARITY) && ETXB_PARITY
@@ -411,6 +422,25 @@ int sort_queue_by_material(etxb_ctx* ctx, const uint32_t* queue, uint32_t active
   return ETXB_OK;
 }
 
+// closest hits of a queue: persistent, nodelet-staged, lane-refilled walk (dtrav.cuh) or the thread-per-ray kernel (A/B switch)
+int launch_trace_closest(etxb_ctx* ctx, const LaunchParams& p, const uint32_t* queue, const uint32_t* count, uint32_t* keys, uint32_t active) {
+  if (ctx->persistent_trace) {
+    CUDA_OK(ctx, cudaMemsetAsync(ctx->trace_cursor.ptr, 0, 4, ctx->stream));
+    const uint32_t blocks = std::min<uint32_t>(blocks_for(active, 256), 148u * 4u);
+    k_trace_closest_persistent<<<blocks, 256, 0, ctx->stream>>>(p, queue, count, keys, active, ctx->trace_cursor.ptr);
+  } else {
+    k_trace_closest<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, queue, count, keys, active);
+  }
+  return ETXB_OK;
+}
+// the bounce's shadow segments (ShadowBatch, atomic mode): traced and added to their targets
+int launch_shadow_resolve(etxb_ctx* ctx, const LaunchParams& p, uint32_t active) {
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->trace_cursor.ptr + 1, 0, 4, ctx->stream));
+  const uint32_t blocks = std::min<uint32_t>(blocks_for(std::min<uint64_t>(uint64_t(active) * 4ull, 0x7fffffffull), 256), 148u * 4u);
+  k_shadow_resolve<<<blocks, 256, 0, ctx->stream>>>(p, ctx->trace_cursor.ptr + 1);
+  return ETXB_OK;
+}
+
 template <bool SP>
 int run_light_pass(etxb_ctx* ctx) {
   LaunchParams p = make_params(ctx);
@@ -431,13 +461,14 @@ int run_light_pass(etxb_ctx* ctx) {
     const uint32_t* q = qin;
     {
       LaunchTimer t(ctx, K_TRACE_LIGHT);
-      k_trace_closest<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, qin, counts + cur, sorted ? ctx->queue_keys.ptr : nullptr, active);
+      if (int rc = launch_trace_closest(ctx, p, qin, counts + cur, sorted ? ctx->queue_keys.ptr : nullptr, active)) return rc;
     }
     if (sorted) {
       LaunchTimer t(ctx, K_QUEUE_SORT);
       if (int rc = sort_queue_by_material(ctx, qin, active, &q)) return rc;
     }
     CUDA_OK(ctx, cudaMemsetAsync(counts + (cur ^ 1u), 0, 4, ctx->stream));
+    if (p.shadow_atomic) CUDA_OK(ctx, cudaMemsetAsync(ctx->shadow_count.ptr, 0, 8, ctx->stream));
     {
       LaunchTimer t(ctx, K_LIGHT_BOUNCE);
       if (ctx->plain_scene && ctx->plain_kernels) {
@@ -445,6 +476,11 @@ int run_light_pass(etxb_ctx* ctx) {
       } else {
         k_light_bounce<SP, false><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, q, counts + cur, qout, counts + (cur ^ 1u));
       }
+    }
+    if (p.shadow_atomic) {
+      // the light-to-camera connections of this bounce: segments -> splats (light image)
+      LaunchTimer t(ctx, K_SHADOW_TRACE);
+      if (int rc = launch_shadow_resolve(ctx, p, active)) return rc;
     }
     cur ^= 1u;
     std::swap(qin, qout);
@@ -564,7 +600,7 @@ int run_camera_pass(etxb_ctx* ctx) {
     const uint32_t* q = qin;  // the queue every stage of this bounce reads
     {
       LaunchTimer t(ctx, K_TRACE_CAMERA);
-      k_trace_closest<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, qin, counts + cur, sorted ? ctx->queue_keys.ptr : nullptr, active);
+      if (int rc = launch_trace_closest(ctx, p, qin, counts + cur, sorted ? ctx->queue_keys.ptr : nullptr, active)) return rc;
     }
     if (sorted) {
       LaunchTimer t(ctx, K_QUEUE_SORT);
@@ -572,7 +608,7 @@ int run_camera_pass(etxb_ctx* ctx) {
     }
     CUDA_OK(ctx, cudaMemsetAsync(counts + (cur ^ 1u), 0, 4, ctx->stream));
     if (p.connect_stage) CUDA_OK(ctx, cudaMemsetAsync(ctx->conn_count.ptr, 0, 4, ctx->stream));
-    if (p.shadow_stage) CUDA_OK(ctx, cudaMemsetAsync(ctx->shadow_count.ptr, 0, 8, ctx->stream));
+    if (p.shadow_stage || p.shadow_atomic) CUDA_OK(ctx, cudaMemsetAsync(ctx->shadow_count.ptr, 0, 8, ctx->stream));
     {
       LaunchTimer t(ctx, K_CAMERA_SHADE);
       if (ctx->plain_scene && ctx->plain_kernels) {
@@ -625,6 +661,11 @@ int run_camera_pass(etxb_ctx* ctx) {
           }
         }
       }
+    }
+    if (p.shadow_atomic) {
+      // emitter-sample and vertex-connection segments of this bounce: traced, the unoccluded ones added to their paths' gathered sums
+      LaunchTimer t(ctx, K_SHADOW_TRACE);
+      if (int rc = launch_shadow_resolve(ctx, p, active)) return rc;
     }
 #if defined(ETXB_PARITY) && ETXB_PARITY
     if (merging) {
@@ -693,9 +734,18 @@ int comm_exchange(etxb_ctx* ctx, const void** records, uint64_t* count) {
   NcclApi* n = nccl_api();
   *records = nullptr;
   *count = 0;
+  // the collectives run on the context's high-priority stream, fenced against its work stream by events on both sides
+  cudaStream_t cs = ctx->comm_stream;
+  auto fence_out = [&]() -> cudaError_t {
+    cudaError_t e = cudaEventRecord(ctx->comm_ev_out, cs);
+    return (e == cudaSuccess) ? cudaStreamWaitEvent(ctx->stream, ctx->comm_ev_out, 0) : e;
+  };
   {
     LaunchTimer t(ctx, K_COMM_LIGHT_IMAGE);
-    NCCL_OK(ctx, n->AllReduce(ctx->film_light_iteration.ptr, ctx->film_light_iteration.ptr, size_t(ctx->path_count) * 4u, ncclFloat, ncclSum, ctx->comm, ctx->stream));
+    CUDA_OK(ctx, cudaEventRecord(ctx->comm_ev_in, ctx->stream));
+    CUDA_OK(ctx, cudaStreamWaitEvent(cs, ctx->comm_ev_in, 0));
+    NCCL_OK(ctx, n->AllReduce(ctx->film_light_iteration.ptr, ctx->film_light_iteration.ptr, size_t(ctx->path_count) * 4u, ncclFloat, ncclSum, ctx->comm, cs));
+    CUDA_OK(ctx, fence_out());
   }
   const bool merging = (ctx->options.options & ETXB_VCM_ENABLE_MERGING) && (ctx->options.options & ETXB_VCM_MERGE_VERTICES);
   if (!merging) return ETXB_OK;
@@ -704,10 +754,10 @@ int comm_exchange(etxb_ctx* ctx, const void** records, uint64_t* count) {
   {
     LaunchTimer t(ctx, K_COMM_PHOTONS);
     uint32_t mine = ctx->last_light_vertices;
-    CUDA_OK(ctx, cudaMemcpyAsync(ctx->comm_counts.ptr + rank, &mine, 4, cudaMemcpyHostToDevice, ctx->stream));
-    NCCL_OK(ctx, n->AllGather(ctx->comm_counts.ptr + rank, ctx->comm_counts.ptr, 1, ncclUint32, ctx->comm, ctx->stream));
-    CUDA_OK(ctx, cudaMemcpyAsync(counts.data(), ctx->comm_counts.ptr, size_t(world) * 4u, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->comm_counts.ptr + rank, &mine, 4, cudaMemcpyHostToDevice, cs));
+    NCCL_OK(ctx, n->AllGather(ctx->comm_counts.ptr + rank, ctx->comm_counts.ptr, 1, ncclUint32, ctx->comm, cs));
+    CUDA_OK(ctx, cudaMemcpyAsync(counts.data(), ctx->comm_counts.ptr, size_t(world) * 4u, cudaMemcpyDeviceToHost, cs));
+    CUDA_OK(ctx, cudaStreamSynchronize(cs));
     uint64_t total = 0;
     std::vector<uint64_t> offsets(world, 0u);
     for (uint32_t r = 0; r < world; ++r) {
@@ -719,13 +769,14 @@ int comm_exchange(etxb_ctx* ctx, const void** records, uint64_t* count) {
     NCCL_OK(ctx, n->GroupStart());
     for (uint32_t r = 0; r < world; ++r) {
       if (counts[r] == 0u) continue;
-      ncclResult_t res = n->Broadcast(ctx->lv_final.ptr, ctx->lv_tmp.ptr + offsets[r], size_t(counts[r]) * kRecordFloats, ncclFloat, int(r), ctx->comm, ctx->stream);
+      ncclResult_t res = n->Broadcast(ctx->lv_final.ptr, ctx->lv_tmp.ptr + offsets[r], size_t(counts[r]) * kRecordFloats, ncclFloat, int(r), ctx->comm, cs);
       if (res != ncclSuccess) {
         n->GroupEnd();
         return fail(ctx, ETXB_ERR_CUDA, "ncclBroadcast failed: %s", n->GetErrorString(res));
       }
     }
     NCCL_OK(ctx, n->GroupEnd());
+    CUDA_OK(ctx, fence_out());
     *records = ctx->lv_tmp.ptr;
     *count = total;
   }
@@ -786,6 +837,8 @@ int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
   if (const char* e = getenv("ETXB_SORT_MATERIAL")) ctx->sort_by_material = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_BATCHED")) ctx->merge_batched = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_CLOSURE")) ctx->merge_closure = (e[0] != '0');
+  if (const char* e = getenv("ETXB_SHADOW_ATOMIC")) ctx->shadow_atomic = (e[0] != '0');
+  if (const char* e = getenv("ETXB_TRACE_PERSISTENT")) ctx->persistent_trace = (e[0] != '0');
   if (const char* e = getenv("ETXB_PLAIN_KERNELS")) ctx->plain_kernels = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_MATERIAL_MAJOR")) ctx->merge_material_major = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_TILED")) ctx->merge_tiled = (e[0] != '0');
@@ -819,6 +872,9 @@ void etxb_destroy(etxb_ctx* ctx) {
   }
   ctx->comm_counts.release();
   ctx->film_reduced.release();
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  if (ctx->comm_ev_in) cudaEventDestroy(ctx->comm_ev_in);
+  if (ctx->comm_ev_out) cudaEventDestroy(ctx->comm_ev_out);
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_iter_start);
   cudaEventDestroy(ctx->ev_iter_stop);
@@ -862,6 +918,7 @@ void etxb_destroy(etxb_ctx* ctx) {
   ctx->shadow_value.release();
   ctx->shadow_result.release();
   ctx->shadow_count.release();
+  ctx->trace_cursor.release();
   ctx->bs_props.release();
   ctx->bs_weight_pdf.release();
   ctx->bs_wo_eta.release();
@@ -1009,6 +1066,15 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
       if ((im != ETXB_INVALID_INDEX) && (all_images[im].options & kImageHasAlpha)) deferred = false;
     }
     ctx->dscene.deferred_shadow_rays = deferred ? 1u : 0u;
+    {
+      bool opaque = !ctx->dscene.has_boundaries && !ctx->dscene.has_subsurface && (s.mediums.count == 0) && (cam.medium_index == ETXB_INVALID_INDEX);
+      for (uint64_t i = 0; opaque && (i < s.materials.count); ++i) {
+        if (mats[i].opacity != 1.0f) opaque = false;
+        uint32_t im = mats[i].scattering.image_index;
+        if ((im != ETXB_INVALID_INDEX) && (all_images[im].options & kImageHasAlpha)) opaque = false;
+      }
+      ctx->opaque_scene = opaque;
+    }
     ctx->plain_scene = !ctx->dscene.has_boundaries && !ctx->dscene.has_subsurface && (s.mediums.count == 0) && (cam.medium_index == ETXB_INVALID_INDEX);
   }
   // ---- images: pixels + flattened row/column CDFs (image.hxx:8-50) ---------------------------------------------------------------
@@ -1137,6 +1203,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   d.emitter_dist = ctx->emitter_dist.ptr;
   d.bvh_nodes = ctx->bvh_nodes.ptr;
   d.bvh_tris = ctx->bvh_tris.ptr;
+  d.bvh_node_count = uint32_t(bvh.nodes.size());
   d.emitter_count = uint32_t(s.emitter_instances.count);
   d.triangle_count = uint32_t(s.triangles.count);
   d.emitter_total_weight = s.emitters_distribution.total_weight;
@@ -1193,12 +1260,16 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
     ctx->queue_keys.release();
     ctx->queue_keys_sorted.release();
   }
-  if (ctx->dscene.deferred_shadow_rays) {
+  CUDA_OK(ctx, ctx->trace_cursor.alloc(4));
+  const bool atomic_candidate = ctx->shadow_atomic && ctx->opaque_scene && ctx->plain_scene && ctx->has_stochastic_merge;
+  if (ctx->dscene.deferred_shadow_rays || atomic_candidate) {
+    // atomic mode: a camera bounce queues its vertex connections (<= cap, the pair list's capacity) plus one emitter segment per path
+    const uint64_t shadow_cap = std::min<uint64_t>(cap + (atomic_candidate ? n : 0), 0x7fffffffull);
     CUDA_OK(ctx, ctx->shadow_span.alloc(n));
-    CUDA_OK(ctx, ctx->shadow_p0.alloc(cap));
-    CUDA_OK(ctx, ctx->shadow_p1.alloc(cap));
-    CUDA_OK(ctx, ctx->shadow_value.alloc(cap));
-    CUDA_OK(ctx, ctx->shadow_result.alloc(cap));
+    CUDA_OK(ctx, ctx->shadow_p0.alloc(shadow_cap));
+    CUDA_OK(ctx, ctx->shadow_p1.alloc(shadow_cap));
+    CUDA_OK(ctx, ctx->shadow_value.alloc(shadow_cap));
+    CUDA_OK(ctx, ctx->shadow_result.alloc(shadow_cap));
     CUDA_OK(ctx, ctx->shadow_count.alloc(2));
   } else {
     ctx->shadow_span.release();
@@ -1426,6 +1497,11 @@ int etxb_comm_init(etxb_ctx* ctx, uint32_t world, uint32_t rank, const void* id,
   ctx->rank = rank;
   ctx->world = world;
   CUDA_OK(ctx, ctx->comm_counts.alloc(world));
+  int prio_low = 0, prio_high = 0;
+  CUDA_OK(ctx, cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+  CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_high));
+  CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->comm_ev_in, cudaEventDisableTiming));
+  CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->comm_ev_out, cudaEventDisableTiming));
   return ETXB_OK;
 }
 
@@ -1728,6 +1804,7 @@ struct FilmLanes {
   const float4* light[kMaxLanes];
   float weight[kMaxLanes];
   uint32_t lanes, layer, pixels;
+  uint32_t raw;  // 1: no clamp, alpha = sum of the weights (a partial sum that another stage finishes)
 };
 __global__ void __launch_bounds__(256) k_film_combine(FilmLanes f, float4* out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1740,7 +1817,27 @@ __global__ void __launch_bounds__(256) k_film_combine(FilmLanes f, float4* out) 
     y += f.weight[l] * (c.y + g.y);
     z += f.weight[l] * (c.z + g.z);
   }
+  if (f.raw) {
+    float w = 0.0f;
+    for (uint32_t l = 0; l < f.lanes; ++l) w += f.weight[l];
+    out[i] = make_float4(x, y, z, w);
+    return;
+  }
   if (f.layer == ETXB_FILM_RESULT) {  // Film::layer(Result): max(0, camera + light) (film.cxx:381-418)
+    x = fmaxf(0.0f, x);
+    y = fmaxf(0.0f, y);
+    z = fmaxf(0.0f, z);
+  }
+  out[i] = make_float4(x, y, z, 1.0f);
+}
+// rank 0 of a replica run: the reduced sum of (iterations x mean film) over the ranks -> the mean over all iterations (.w carries the count)
+__global__ void __launch_bounds__(256) k_film_finish_mean(const float4* sum, float4* out, uint32_t pixels, uint32_t clamp) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels) return;
+  float4 v = sum[i];
+  float inv = (v.w > 0.0f) ? 1.0f / v.w : 0.0f;
+  float x = v.x * inv, y = v.y * inv, z = v.z * inv;
+  if (clamp) {
     x = fmaxf(0.0f, x);
     y = fmaxf(0.0f, y);
     z = fmaxf(0.0f, z);
@@ -1766,6 +1863,8 @@ struct etxb_group {
   // pixel-tile sharding over several processes (etxb_group_comm_init): every lane has its own communicator, and the k-th iteration of lane l is
   // the ordinal l + k * lanes on EVERY rank (the shared counter of the single-GPU mode would pair different iterations across ranks)
   bool sharded = false;
+  bool replicas = false;             // etxb_group_comm_init_replicas: whole-frame iterations dealt to the ranks (global index j -> rank j % world), one film reduce
+  uint32_t job_enqueued = 0;         // replicas: iterations enqueued for the whole job
   uint32_t world = 1, rank = 0;
   uint32_t enqueued_total = 0;
   std::vector<uint32_t> lane_next;
@@ -1799,6 +1898,7 @@ static void group_worker(etxb_group* grp, uint32_t lane) {
       ordinal = grp->taken++;
       grp->pending -= 1;
     }
+    if (grp->replicas) ordinal = ordinal * grp->world + grp->rank;  // this rank's k-th iteration is the job's (k * world + rank)-th
     uint32_t iteration = grp->first_iteration + ordinal * grp->stride;
     grp->in_flight += 1;
     lock.unlock();
@@ -1884,6 +1984,7 @@ int etxb_group_begin(etxb_group* grp, uint32_t first_iteration) {
   grp->first_iteration = first_iteration;
   grp->taken = 0;
   grp->enqueued_total = 0;
+  grp->job_enqueued = 0;
   for (uint32_t l = 0; l < grp->lane_next.size(); ++l) grp->lane_next[l] = l;
   grp->busy_seconds = 0.0;
   grp->error = ETXB_OK;
@@ -1907,6 +2008,12 @@ int etxb_group_enqueue(etxb_group* grp, uint32_t iterations) {
     if (group_idle(grp)) grp->busy_since = std::chrono::steady_clock::now();
     if (grp->sharded) {
       grp->enqueued_total += iterations;
+    } else if (grp->replicas) {
+      // `iterations` more of the JOB's iterations: this rank owns the global indices j with j % world == rank
+      uint32_t mine = 0;
+      for (uint32_t j = grp->job_enqueued; j < grp->job_enqueued + iterations; ++j) mine += ((j % grp->world) == grp->rank) ? 1u : 0u;
+      grp->job_enqueued += iterations;
+      grp->pending += mine;
     } else {
       grp->pending += iterations;
     }
@@ -1932,7 +2039,7 @@ int etxb_group_poll(etxb_group* grp, etxb_status* status) {
   return ETXB_OK;
 }
 
-static int group_combine_into(etxb_group* grp, uint32_t layer, DevBuf<float4>& target, uint32_t* completed) {
+static int group_combine_into(etxb_group* grp, uint32_t layer, DevBuf<float4>& target, uint32_t* completed, bool raw = false) {
   etxb_ctx* first = grp->lanes[0];
   if (!first->scene_ready) return fail(first, ETXB_ERR_NOT_READY, "no scene uploaded");
   size_t n = first->path_count;
@@ -1950,8 +2057,9 @@ static int group_combine_into(etxb_group* grp, uint32_t layer, DevBuf<float4>& t
   for (uint32_t l = 0; l < f.lanes; ++l) {
     f.camera[l] = grp->lanes[l]->film_camera.ptr;
     f.light[l] = grp->lanes[l]->film_light.ptr;
-    f.weight[l] = total ? float(double(grp->lanes[l]->completed) / double(total)) : 0.0f;
+    f.weight[l] = raw ? float(grp->lanes[l]->completed) : (total ? float(double(grp->lanes[l]->completed) / double(total)) : 0.0f);
   }
+  f.raw = raw ? 1u : 0u;
   // lanes that are still rendering keep updating their films (a preview, like reading the reference's film while it runs); after
   // etxb_group_wait every lane has synchronised its stream and the result is exact
   k_film_combine<<<blocks_for(f.pixels, 256), 256, 0, grp->stream>>>(f, target.ptr);
@@ -1996,15 +2104,51 @@ int etxb_group_comm_init(etxb_group* grp, uint32_t world, uint32_t rank, const v
   return ETXB_OK;
 }
 
+// The other way to split a K-iteration render over the ranks: whole-frame iterations, the job's j-th iteration on rank j % world (each rank's
+// lanes take that rank's share in order).  No collective inside an iteration; one ncclReduce of the (count-weighted) films per frame.  id = one
+// NCCL unique id.  Collective.
+int etxb_group_comm_init_replicas(etxb_group* grp, uint32_t world, uint32_t rank, const void* id, uint64_t bytes) {
+  if (!grp || !id || (bytes < sizeof(ncclUniqueId)) || (world == 0u) || (rank >= world)) return ETXB_ERR_INVALID_ARGUMENT;
+  if (int rc = etxb_group_wait(grp)) return rc;
+  NcclApi* n = nccl_api();
+  etxb_ctx* first = grp->lanes[0];
+  if (!n) return fail(first, ETXB_ERR_NOT_READY, "libnccl.so.2 could not be loaded");
+  cudaSetDevice(grp->device);
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  NCCL_OK(first, n->CommInitRank(&grp->reduce_comm, int(world), uid, int(rank)));
+  std::lock_guard<std::mutex> lock(grp->m);
+  grp->replicas = world > 1u;
+  grp->world = world;
+  grp->rank = rank;
+  grp->job_enqueued = 0;
+  return ETXB_OK;
+}
+
 // Collective over the ranks of a sharded group: the lanes' films are combined locally (mean weighted by the iterations each lane finished —
 // the same weights on every rank, the lane -> iteration map is fixed), the camera tiles are summed on rank 0, Result = max(0, camera + light).
 int etxb_group_comm_reduce_film(etxb_group* grp, uint32_t layer, float* dst_rgba, uint64_t dst_bytes) {
   if (!grp || (layer > ETXB_FILM_LIGHT)) return ETXB_ERR_INVALID_ARGUMENT;
-  if (!grp->sharded) return etxb_group_read_film(grp, layer, dst_rgba, dst_bytes);
+  if (!grp->sharded && !grp->replicas) return etxb_group_read_film(grp, layer, dst_rgba, dst_bytes);
   NcclApi* n = nccl_api();
   etxb_ctx* first = grp->lanes[0];
   const size_t px = first->path_count;
   cudaSetDevice(grp->device);
+  if (grp->replicas) {
+    // every rank: sum over its lanes of (iterations finished x mean film), .w = iterations; rank 0 divides the reduced sum by the reduced count
+    if (int rc = group_combine_into(grp, layer, grp->combined, nullptr, true)) return rc;
+    if (grp->reduced.count < px) CUDA_OK(first, grp->reduced.alloc(px));
+    NCCL_OK(first, n->Reduce(grp->combined.ptr, grp->reduced.ptr, px * 4u, ncclFloat, ncclSum, 0, grp->reduce_comm, grp->stream));
+    if (grp->rank != 0u) {
+      CUDA_OK(first, cudaStreamSynchronize(grp->stream));
+      return ETXB_OK;
+    }
+    if (!dst_rgba || (dst_bytes < px * 16u)) return fail(first, ETXB_ERR_INVALID_ARGUMENT, "film buffer too small");
+    k_film_finish_mean<<<blocks_for(uint32_t(px), 256), 256, 0, grp->stream>>>(grp->reduced.ptr, grp->combined.ptr, uint32_t(px), (layer == ETXB_FILM_RESULT) ? 1u : 0u);
+    CUDA_OK(first, cudaMemcpyAsync(dst_rgba, grp->combined.ptr, px * 16u, cudaMemcpyDeviceToHost, grp->stream));
+    CUDA_OK(first, cudaStreamSynchronize(grp->stream));
+    return ETXB_OK;
+  }
   if (layer != ETXB_FILM_LIGHT) {
     if (int rc = group_combine_into(grp, ETXB_FILM_CAMERA, grp->combined, nullptr)) return rc;
     if (grp->reduced.count < px) CUDA_OK(first, grp->reduced.alloc(px));

@@ -35,6 +35,11 @@ def _worker(rank, world, port, out_dir, lanes, flavor):
             g = api.GPUVCM(sd, flavor=flavor, device=rank)
             g.comm_init(world, rank, distribute_comm_ids(dist, rank, 1, lambda c: api.comm_unique_ids(c, flavor), device=torch.device("cuda", rank)))
             g.render(n)
+        elif lanes < 0:  # whole-frame iterations dealt to the ranks, one count-weighted film reduce
+            g = api.GPUVCMGroup(sd, lanes=-lanes, flavor=flavor, device=rank)
+            g.comm_init_replicas(world, rank, distribute_comm_ids(dist, rank, 1, lambda c: api.comm_unique_ids(c, flavor), device=torch.device("cuda", rank)))
+            g.render(n)
+            assert g.status()["completed_iterations"] == (3 if rank == 0 else 2)  # indices 0, 2, 4 | 1, 3
         else:
             g = api.GPUVCMGroup(sd, lanes=lanes, flavor=flavor, device=rank)
             g.comm_init(world, rank, distribute_comm_ids(dist, rank, lanes + 1, lambda c: api.comm_unique_ids(c, flavor), device=torch.device("cuda", rank)))
@@ -51,7 +56,7 @@ def _worker(rank, world, port, out_dir, lanes, flavor):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("lanes,flavor", [(0, "parity"), (0, "fast"), (2, "fast")])
+@pytest.mark.parametrize("lanes,flavor", [(0, "parity"), (0, "fast"), (2, "fast"), (-2, "fast")])
 def test_two_gpu_tiles_render_the_single_gpu_frame(tmp_path, lanes, flavor):
     import torch
     import torch.multiprocessing as mp
