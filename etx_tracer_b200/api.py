@@ -216,14 +216,18 @@ class GPUVCM:
         self._target_iterations = int(self.scene_data.scene["samples"][0])
 
     def update(self):
-        """One pump of the integrator: renders the next iteration; stops at scene.samples like the reference."""
+        """One pump of the integrator, non-blocking like CPUVCM::update (vcm_cpu.cxx:264-276): queues the next iteration once the previous one has
+        finished; stops at scene.samples like the reference."""
         if not self._running:
             return False
-        self._check(self.lib.etxb_enqueue_iteration(self.h))
         st = self.status()
+        if st["iteration_in_flight"]:
+            return True
         if st["completed_iterations"] >= self._target_iterations:
             self._running = False
-        return self._running
+            return False
+        self._check(self.lib.etxb_enqueue_iteration(self.h))
+        return True
 
     def render(self, iterations, first_iteration=0):
         self.run(first_iteration)

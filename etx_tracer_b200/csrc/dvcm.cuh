@@ -712,7 +712,10 @@ struct ShadowBatch {
     count += 1u;
     if ((atomic_cursor != nullptr) && (k >= capacity)) return;  // the host sized the list for every segment a bounce can produce; the resolver clamps
     p0[k] = make_float4(a.x, a.y, a.z, 0.0f);
-    p1[k] = make_float4(b.x, b.y, b.z, (atomic_cursor != nullptr) ? __uint_as_float(target) : 0.0f);
+    // the target travels as raw bits in p1.w.  It is stored through an integer lane: small integers are denormal bit patterns, and a float
+    // select on them is flushed to zero by the product build's -ftz (measured: every contribution landed on path 0 / pixel 0)
+    p1[k] = make_float4(b.x, b.y, b.z, 0.0f);
+    if (atomic_cursor != nullptr) reinterpret_cast<uint32_t*>(p1 + k)[3] = target;
     value[k] = make_float4(c.x, c.y, c.z, 0.0f);
   }
 };

@@ -1888,6 +1888,10 @@ __global__ void __launch_bounds__(kMergeWarpsPerBlock * 32) k_camera_merge_tiled
   counter_add(&p.counters->merge_accepts, accepts);
 }
 
+// One CTA of kTraversalBlock threads per SM: the staged nodelet then costs 32 KB of the SM's shared memory / L1 once (four 256-thread CTAs each
+// staging their own copy took 128 KB away from the L1 that caches the rest of the tree: ncu, L1 hit rate 64 % -> 46 %, and the kernel got slower).
+constexpr uint32_t kTraversalBlock = 1024u;
+
 // Closest hit for every queued path (Raytracing::trace, rt.cxx:428-466) on persistent warps with the top of the BVH in shared memory and lane
 // refill (dtrav.cuh).  Same per-ray walk, candidate order and sampler draws as k_trace_closest / the oracle.
 struct ClosestHitVisitor {
@@ -1902,7 +1906,7 @@ struct ClosestHitVisitor {
     return kCandAccept;
   }
 };
-__global__ void __launch_bounds__(256) k_trace_closest_persistent(const __grid_constant__ LaunchParams p, const uint32_t* queue, const uint32_t* queue_count, uint32_t* material_keys,
+__global__ void __launch_bounds__(kTraversalBlock) k_trace_closest_persistent(const __grid_constant__ LaunchParams p, const uint32_t* queue, const uint32_t* queue_count, uint32_t* material_keys,
                                                                   uint32_t key_limit, uint32_t* cursor) {
   __shared__ __align__(128) BvhNode s_nodes[kNodeletNodes];
   __shared__ __align__(8) uint64_t s_bar;
@@ -1958,7 +1962,7 @@ __global__ void __launch_bounds__(256) k_trace_closest_persistent(const __grid_c
 // The shadow segments of one bounce (ShadowBatch, atomic mode): any-hit on the same persistent, nodelet-staged, lane-refilled walk; a segment
 // that reaches its end adds its contribution to its target (a path's gathered sum, or a pixel of the light image).  Opaque scenes only: any
 // non-Void surface on the segment occludes (rt.cxx:468-579 without Boundary crossings).
-__global__ void __launch_bounds__(256) k_shadow_resolve(const __grid_constant__ LaunchParams p, uint32_t* cursor) {
+__global__ void __launch_bounds__(kTraversalBlock) k_shadow_resolve(const __grid_constant__ LaunchParams p, uint32_t* cursor) {
   __shared__ __align__(128) BvhNode s_nodes[kNodeletNodes];
   __shared__ __align__(8) uint64_t s_bar;
   const uint32_t staged = nodelet_stage(s_nodes, &s_bar, p.scene.bvh_nodes, p.scene.bvh_node_count);
@@ -1989,7 +1993,7 @@ __global__ void __launch_bounds__(256) k_shadow_resolve(const __grid_constant__ 
     if (warp_refill(!active, cursor, total, next, exhausted)) {
       k = next;
       float4 a = p.shadow_p0[k], b = p.shadow_p1[k];
-      target = __float_as_uint(b.w);
+      target = reinterpret_cast<const uint32_t*>(p.shadow_p1 + k)[3];  // raw bits (see ShadowBatch::push_rgb)
       V3 direction = V3{b.x, b.y, b.z} - V3{a.x, a.y, a.z};
       float t_max = dot(direction, direction);
       if (t_max <= kRayEpsilon) {

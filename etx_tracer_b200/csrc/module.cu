@@ -426,8 +426,8 @@ int sort_queue_by_material(etxb_ctx* ctx, const uint32_t* queue, uint32_t active
 int launch_trace_closest(etxb_ctx* ctx, const LaunchParams& p, const uint32_t* queue, const uint32_t* count, uint32_t* keys, uint32_t active) {
   if (ctx->persistent_trace) {
     CUDA_OK(ctx, cudaMemsetAsync(ctx->trace_cursor.ptr, 0, 4, ctx->stream));
-    const uint32_t blocks = std::min<uint32_t>(blocks_for(active, 256), 148u * 4u);
-    k_trace_closest_persistent<<<blocks, 256, 0, ctx->stream>>>(p, queue, count, keys, active, ctx->trace_cursor.ptr);
+    const uint32_t blocks = std::min<uint32_t>(blocks_for(active, kTraversalBlock), 148u);
+    k_trace_closest_persistent<<<blocks, kTraversalBlock, 0, ctx->stream>>>(p, queue, count, keys, active, ctx->trace_cursor.ptr);
   } else {
     k_trace_closest<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, queue, count, keys, active);
   }
@@ -436,8 +436,8 @@ int launch_trace_closest(etxb_ctx* ctx, const LaunchParams& p, const uint32_t* q
 // the bounce's shadow segments (ShadowBatch, atomic mode): traced and added to their targets
 int launch_shadow_resolve(etxb_ctx* ctx, const LaunchParams& p, uint32_t active) {
   CUDA_OK(ctx, cudaMemsetAsync(ctx->trace_cursor.ptr + 1, 0, 4, ctx->stream));
-  const uint32_t blocks = std::min<uint32_t>(blocks_for(std::min<uint64_t>(uint64_t(active) * 4ull, 0x7fffffffull), 256), 148u * 4u);
-  k_shadow_resolve<<<blocks, 256, 0, ctx->stream>>>(p, ctx->trace_cursor.ptr + 1);
+  const uint32_t blocks = std::min<uint32_t>(blocks_for(std::min<uint64_t>(uint64_t(active) * 4ull, 0x7fffffffull), kTraversalBlock), 148u);
+  k_shadow_resolve<<<blocks, kTraversalBlock, 0, ctx->stream>>>(p, ctx->trace_cursor.ptr + 1);
   return ETXB_OK;
 }
 

@@ -80,31 +80,41 @@ class GPUVCM {
     if (etxb_set_options(_ctx, &_options) != ETXB_OK) return;
     if (etxb_begin(_ctx, 0) != ETXB_OK) return;
     _status = {};
+    _seen_iterations = 0;
     _have_camera_image = _have_light_image = true;
     _state = State::Running;
   }
 
+  // Non-blocking, like CPUVCM::update (vcm_cpu.cxx:264-276): while the iteration queued earlier is still running this only refreshes the status;
+  // when it has completed, the next one is queued (etxb_enqueue_iteration returns at once: the module runs it on its own worker thread).
   void update() {
     if (_state.load() == State::Stopped) return;
-    if (etxb_enqueue_iteration(_ctx) != ETXB_OK) {
+    etxb_status st = {};
+    if (etxb_poll(_ctx, &st) != ETXB_OK) {
       _state = State::Stopped;
       return;
     }
-    etxb_status st = {};
-    etxb_poll(_ctx, &st);
     _status.last_iteration_time = st.last_iteration_time;
     _status.total_time = st.total_time;
     _status.completed_iterations = st.completed_iterations;
     _status.current_iteration = st.current_iteration;
-    _have_camera_image = _have_light_image = true;
+    if (st.iteration_in_flight) return;
+    if (st.completed_iterations > _seen_iterations) {
+      _seen_iterations = st.completed_iterations;
+      _have_camera_image = _have_light_image = true;
+    }
     // complete_camera_vertices (vcm_cpu.cxx:227-241)
-    if ((_state.load() == State::WaitingForCompletion) || (st.completed_iterations >= _samples)) _state = State::Stopped;
+    if ((_state.load() == State::WaitingForCompletion) || (st.completed_iterations >= _samples)) {
+      _state = State::Stopped;
+      return;
+    }
+    if (etxb_enqueue_iteration(_ctx) != ETXB_OK) _state = State::Stopped;
   }
 
   void stop(Stop st) {
     if (_state.load() == State::Stopped) return;
     _state = (st == Stop::Immediate) ? State::Stopped : State::WaitingForCompletion;
-    if (_state.load() == State::Stopped && _ctx) etxb_stop(_ctx, 0);
+    if (_state.load() == State::Stopped && _ctx) etxb_stop(_ctx, 0);  // drops what is queued; the iteration in flight completes (its film update is whole)
   }
 
   void update_options() {
@@ -133,7 +143,7 @@ class GPUVCM {
   etxb_vcm_options _options = {};
   std::atomic<State> _state{State::Stopped};
   Status _status;
-  uint32_t _samples = 0;
+  uint32_t _samples = 0, _seen_iterations = 0;
   bool _scene_committed = false;
   mutable bool _have_camera_image = false, _have_light_image = false;
 };

@@ -101,3 +101,105 @@ def test_reference_loader_hands_its_pods_to_the_host_adapter(tmp_path):
     out = subprocess.run([str(exe), os.path.join(ref, "bin"), os.path.join(ref, "bin", "assets", "cornellbox", "cornellbox.json")], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout[-500:], out.stderr[-500:])
     assert "hand-over ok" in out.stdout
+
+
+RENDER_SRC = r'''
+// The application's side of the boundary, in C++, on a real device: PODs in host memory -> GPUVCM::commit_scene -> run() -> update() pumped
+// like IntegratorThread does once per frame (non-blocking) until the integrator stops itself at scene.samples -> read_film.
+#include <chrono>
+#include <cstdio>
+#include <cstdint>
+#include <thread>
+#include <vector>
+#include "etx_tracer_b200/host/gpu_vcm.hpp"
+static std::vector<uint8_t> slurp(FILE* f, uint64_t n) { std::vector<uint8_t> v(n); if (n && fread(v.data(), 1, n, f) != n) v.clear(); return v; }
+int main(int argc, char** argv) {
+  FILE* f = fopen(argv[1], "rb");
+  if (!f) return 1;
+  uint64_t counts[10];
+  if (fread(counts, 8, 10, f) != 10) return 2;
+  etxb_scene scene; etxb_camera camera;
+  if (fread(&scene, sizeof(scene), 1, f) != 1 || fread(&camera, sizeof(camera), 1, f) != 1) return 3;
+  std::vector<std::vector<uint8_t>> arrays;
+  for (int k = 0; k < 10; ++k) arrays.push_back(slurp(f, counts[k]));
+  std::vector<uint8_t> xyz = slurp(f, 441 * 3 * 4), rgbr = slurp(f, 391 * 3 * 4), sobol = slurp(f, 256 * 256), scr = slurp(f, 128 * 128 * 8), rnk = slurp(f, 128 * 128 * 8);
+  fclose(f);
+  etxb_array_view* views[9] = {&scene.vertices, &scene.triangles, &scene.triangle_to_emitter, &scene.materials, &scene.emitter_profiles, &scene.emitter_instances,
+                               &scene.images, &scene.mediums, &scene.spectrums};
+  for (int k = 0; k < 9; ++k) views[k]->a = arrays[k].empty() ? nullptr : arrays[k].data();
+  scene.emitters_distribution.values.a = arrays[9].data();
+  etxb::GPUVCM vcm(0);
+  if (!vcm.enabled()) return 4;
+  if (vcm.upload_tables((const float*)xyz.data(), (const float*)rgbr.data(), sobol.data(), scr.data(), rnk.data()) != 0) return 5;
+  if (vcm.commit_scene(&scene, sizeof(scene), &camera, sizeof(camera), 6) != 0) { std::printf("%s\n", vcm.status_str()); return 6; }
+  vcm.run();
+  if (vcm.state() != etxb::GPUVCM::State::Running) return 7;
+  uint32_t pumps = 0, idle_returns = 0;
+  while (vcm.state() != etxb::GPUVCM::State::Stopped) {
+    auto t0 = std::chrono::steady_clock::now();
+    vcm.update();
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (ms < 2.0) idle_returns += 1;  // update() must not wait for an iteration
+    pumps += 1;
+    std::this_thread::sleep_for(std::chrono::microseconds(200));
+    if (pumps > 2000000) return 8;
+  }
+  if (vcm.status().completed_iterations != 6) return 9;
+  std::vector<float> film(size_t(camera.film_size[0]) * camera.film_size[1] * 4);
+  if (vcm.read_film(ETXB_FILM_RESULT, film.data(), film.size() * 4) != 0) return 10;
+  FILE* out = fopen(argv[2], "wb");
+  fwrite(film.data(), 4, film.size(), out);
+  fclose(out);
+  std::printf("pumps %u non-blocking %u iterations %u\n", pumps, idle_returns, vcm.status().completed_iterations);
+  return (idle_returns * 10 >= pumps * 9) ? 0 : 11;
+}
+'''
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_cpp_adapter_renders_on_the_device_with_a_non_blocking_update(tmp_path):
+    """The C++ adapter on a real GPU: the Integrator contract end to end (run / non-blocking update pumped until Stopped / film), same film as
+    the ctypes mirror renders through the same C ABI."""
+    import ctypes as C
+    import numpy as np
+    from etx_tracer_b200 import api, scenes, structs as S
+    sd = scenes.cornell_box(48, 40, samples=6, spectral=True, sphere=True)
+    sc = sd.scene
+    names = ["vertices", "triangles", "triangle_to_emitter", "materials", "emitter_profiles", "emitter_instances", "images", "mediums", "spectrums"]
+    sizes = [S.VERTEX.itemsize, S.TRIANGLE.itemsize, 4, S.MATERIAL.itemsize, S.EMITTER_PROFILE.itemsize, S.EMITTER.itemsize, S.IMAGE.itemsize, S.MEDIUM.itemsize,
+             S.SPECTRUM.itemsize]
+    blobs = []
+    for n, sz in zip(names, sizes):
+        cnt = int(sc[n]["count"][0])
+        blobs.append(bytes((C.c_char * (cnt * sz)).from_address(int(sc[n]["a"][0]))) if cnt else b"")
+    assert int(sc["images"]["count"][0]) == 0 and int(sc["mediums"]["count"][0]) == 0  # flat arrays only in this scene
+    ne = int(sc["emitter_instances"]["count"][0])
+    blobs.append(bytes((C.c_char * ((ne + 1) * S.DIST_ENTRY.itemsize)).from_address(int(sc["emitters_distribution"]["values"]["a"][0]))))
+    ct, bn = scenes.tables("color_tables"), scenes.tables("bluenoise")
+    spp = 8  # next_power(min(samples = 6, 256))
+    with open(tmp_path / "scene.bin", "wb") as f:
+        f.write(np.array([len(b) for b in blobs], dtype=np.uint64).tobytes())
+        f.write(sc.tobytes())
+        f.write(sd.camera.tobytes())
+        for b in blobs:
+            f.write(b)
+        f.write(np.ascontiguousarray(ct["xyz_441x3"], dtype=np.float32).tobytes())
+        f.write(np.ascontiguousarray(ct["rgb_response_391x3"], dtype=np.float32).tobytes())
+        for k in ("sobol", f"scrambling_{spp}", f"ranking_{spp}"):
+            f.write(np.ascontiguousarray(bn[k], dtype=np.uint8).tobytes())
+    lib = etx_build.lib_path("fast")
+    src = tmp_path / "r.cpp"
+    src.write_text(RENDER_SRC)
+    exe = tmp_path / "r"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", f"-I{ROOT}", str(src), lib, f"-Wl,-rpath,{os.path.dirname(lib)}", "-o", str(exe)])
+    out = subprocess.run([str(exe), str(tmp_path / "scene.bin"), str(tmp_path / "film.bin")], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout[-500:], out.stderr[-500:])
+    film = np.fromfile(tmp_path / "film.bin", dtype=np.float32).reshape(sd.height, sd.width, 4)
+    g = api.GPUVCM(sd, flavor="fast")
+    g.render(6)
+    ref = g.film(S.FILM_RESULT)
+    g.close()
+    assert np.array_equal(film[..., :3].view(np.uint32), ref[..., :3].view(np.uint32)), "C++ adapter and ctypes mirror must render the same film"

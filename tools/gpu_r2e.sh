@@ -1,0 +1,37 @@
+#!/bin/bash
+# Round 2, fifth GPU visit (2 GPUs): whole -m gpu suite incl. the 2-GPU and C++-adapter tests, A/B of the traversal kernels, N=2 in both modes.
+tag=${1:-r2e}
+mkdir -p gpurun_out
+( time timeout 1800 python -m pytest tests -m gpu -q -s ) > gpurun_out/${tag}_gpu_tests.log 2>&1
+tail -6 gpurun_out/${tag}_gpu_tests.log
+grep -h "statistical parity\|tier B" gpurun_out/${tag}_gpu_tests.log | cut -c1-330
+run() { # name, workload, steps, env...
+  local name=$1 wl=$2 steps=$3; shift 3
+  env "$@" timeout 400 python bench.py --workload $wl --steps $steps --warmup 3 --lanes 1 --no-cpu-baseline > gpurun_out/${tag}_${name}.json 2> gpurun_out/${tag}_${name}.err
+  python - <<P
+import json
+try:
+    d = json.load(open("gpurun_out/${tag}_${name}.json"))
+    print("${name}", round(d["value"], 3), "Msamples/s", {k: v for k, v in list(d["roofline"]["kernel_ms_per_iteration"].items())[:10]})
+except Exception as e:
+    print("${name} failed", e)
+P
+}
+run c3 C3 4 X=1
+run c3_threadtrace C3 4 ETXB_TRACE_PERSISTENT=0
+run c3_inline_shadow C3 4 ETXB_SHADOW_ATOMIC=0
+show() {
+  python - <<P
+import json
+try:
+    d = json.load(open("gpurun_out/${tag}_$1.json"))
+    print("$1", d["config"]["mode"], round(d["value"], 3), "Msamples/s e2e", round(d["e2e"]["value"], 3), "ms/step", round(d["ms_per_step"], 2), d["modes"])
+except Exception as e:
+    print("$1 failed", e)
+P
+}
+timeout 400 python bench.py --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_n1.json 2> gpurun_out/${tag}_n1.err; show n1
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_n2.json 2> gpurun_out/${tag}_n2.err; show n2
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 12 --warmup 3 --lanes 2 --parallelism tile --no-cpu-baseline > gpurun_out/${tag}_n2_tile_l2.json 2> gpurun_out/${tag}_n2_tile_l2.err; show n2_tile_l2
+tail -3 gpurun_out/${tag}_n2.err
+exit 0
