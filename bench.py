@@ -298,9 +298,12 @@ def main():
                      ncclReduce of the films per frame (etxb_group_comm_init_replicas)
         Strong scaling in every mode: a step = one whole-frame iteration of the job, value = W*H*K / time (max over ranks)."""
         from etx_tracer_b200.multigpu import distribute_comm_ids
-        g = GPUVCMGroup(sd, lanes=lanes, flavor="fast", device=local_rank, profile=True)
+        # tile mode: two iterations in flight per GPU (measured at N = 2: 30.7 Msamples/s with 2, 15.1 with 4 — every lane has two rendezvous with
+        # its peers per iteration, and four lanes' collectives wait on each other across the ranks)
+        mode_lanes = min(lanes, 2) if mode == "tile" else lanes
+        g = GPUVCMGroup(sd, lanes=mode_lanes, flavor="fast", device=local_rank, profile=True)
         if mode == "tile":
-            g.comm_init(world, rank, distribute_comm_ids(dist, rank, lanes + 1, comm_unique_ids, device=device))
+            g.comm_init(world, rank, distribute_comm_ids(dist, rank, mode_lanes + 1, comm_unique_ids, device=device))
         elif mode == "iteration":
             g.comm_init_replicas(world, rank, distribute_comm_ids(dist, rank, 1, comm_unique_ids, device=device))
         g.options[:] = workload_vcm_options(args)
@@ -367,7 +370,8 @@ def main():
         light_vertices = st1["light_vertices"]
         g.close()
         return {"mode": mode, "value": n_pixels * args.steps / elapsed / 1e6, "elapsed": elapsed, "counters": counters, "clocks": clk,
-                "e2e": {"value": n_pixels * args.steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(g.options.nbytes) * lanes,
+                "lanes": mode_lanes,
+                "e2e": {"value": n_pixels * args.steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(g.options.nbytes) * mode_lanes,
                         "d2h_bytes_per_step": int(host_film.nbytes * film_reads / args.steps)},
                 "collective_ms_per_iteration": comm_ms or None, "film_finite": finite, "light_vertices": light_vertices}
 
@@ -408,18 +412,6 @@ def main():
             # two gather kernels share the merge counters: split the bytes by their time
             tm, tg = ktimes["camera_merge"][0], ktimes["camera_merge_generic"][0]
             kbytes["camera_merge"], kbytes["camera_merge_generic"] = kbytes["camera_merge"] * tm / (tm + tg), kbytes["camera_merge_generic"] * tg / (tm + tg)
-        dominant = max(ktimes, key=lambda k: ktimes[k][0])
-        dom_ms, dom_launches = ktimes[dominant]
-        dom_bytes = kbytes.get(dominant, 0.0)
-        achieved = dom_bytes / max(dom_ms * 1e-3, 1e-12) / 1e9
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(prof):
-            try:
-                traffic = json.load(open(prof)).get(dominant)
-            except Exception:
-                traffic = None
-        step_ms = sum(v[0] for v in ktimes.values())
         # SURVEY 8(d) asks for the fractions with AND without the BVH term: one iteration (the first timed index) through the counting build
         bvh = None
         try:
@@ -444,18 +436,41 @@ def main():
                    "step_algorithmic_GBps_with_bvh": (total_bytes + it_bvh * args.steps) / elapsed / 1e9,
                    "trace_closest_GBps_without_bvh": trace_bytes / max(trace_ms * 1e-3, 1e-12) / 1e9,
                    "trace_closest_GBps_with_bvh": (trace_bytes + it_bvh_closest) / max(trace_ms * 1e-3, 1e-12) / 1e9}
+            # the traversal kernels' own algorithmic bytes include the nodes and triangles their rays touch (64 B / 48 B each); the ratio of the two
+            # closest-hit kernels' ray counts splits the closest-hit term, the rest (shadow segments) goes to the shadow kernel
+            rc_l, rc_c = kcounters["bounces_light"], kcounters["bounces_camera"]
+            share_l = rc_l / max(rc_l + rc_c, 1)
+            kbytes["trace_closest(light)"] += it_bvh_closest * kt_steps * share_l
+            kbytes["trace_closest(camera)"] += it_bvh_closest * kt_steps * (1.0 - share_l)
+            if ktimes.get("shadow_trace", (0, 0))[0] > 0:
+                kbytes["shadow_trace"] += max(it_bvh - it_bvh_closest, 0) * kt_steps
             bvh["step_frac_without_bvh"] = bvh["step_algorithmic_GBps_without_bvh"] / peak
             bvh["step_frac_with_bvh"] = bvh["step_algorithmic_GBps_with_bvh"] / peak
             bvh["trace_closest_frac_with_bvh"] = bvh["trace_closest_GBps_with_bvh"] / peak
         except Exception as e:  # the counting build is an extra; the headline does not depend on it
             bvh = {"unavailable": str(e)[:200]}
+        dominant = max(ktimes, key=lambda k: ktimes[k][0])
+        dom_ms, dom_launches = ktimes[dominant]
+        dom_bytes = kbytes.get(dominant, 0.0)
+        achieved = dom_bytes / max(dom_ms * 1e-3, 1e-12) / 1e9
+        # `traffic`: dram read + write of ONE head-of-pass launch of that kernel from the committed ncu --set full capture of this workload
+        traffic, traffic_source = None, None
+        try:
+            summary = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(args.workload, {})
+            rec = summary.get(dominant) or summary.get(dominant.split("(")[0])
+            if rec and (rec.get("dram_read_GB") is not None):
+                traffic = (rec["dram_read_GB"] + rec["dram_write_GB"]) * 1e9
+                traffic_source = f"profiles/{rec['file']} (head-of-pass launch, {rec['time_ms']:.3f} ms)"
+        except Exception:
+            traffic = None
+        step_ms = sum(v[0] for v in ktimes.values())
         # the ceilings that actually bind (L2 bandwidth, issue slots, lanes per instruction) come from the committed ncu summaries
         ncu = None
         try:
             ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(args.workload)
         except Exception:
             ncu = None
-        roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s",
                     "bytes_per_launch": dom_bytes / max(dom_launches, 1), "launches": dom_launches, "avg_launch_ms": dom_ms / max(dom_launches, 1),
                     "kernel_share_of_step": dom_ms / max(step_ms, 1e-9),
@@ -475,7 +490,7 @@ def main():
                 "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc,
                            "parallelism": {"single": f"one GPU, {lanes} iterations in flight",
-                                           "tile": f"pixel tiles (32x32, round-robin) over {world} GPUs inside the module, {lanes} iterations in flight per GPU; per iteration "
+                                           "tile": f"pixel tiles (32x32, round-robin) over {world} GPUs inside the module, {min(lanes, 2)} iterations in flight per GPU; per iteration "
                                                    f"ncclAllReduce of the light image + all-gather of the photon records, per frame ncclReduce of the film",
                                            "iteration": f"the job's iterations dealt to {world} GPUs (index j on rank j % {world}), {lanes} in flight per GPU; per frame one "
                                                         f"count-weighted ncclReduce of the films"}[best["mode"]],

@@ -89,6 +89,8 @@ def load_library(flavor="fast"):
     lib.etxb_stream.restype = vp
     lib.etxb_stream.argtypes = [vp]
     lib.etxb_debug_trace.argtypes = [vp, vp, vp, u32, vp, vp]
+    if hasattr(lib, "etxb_debug_select_tree"):
+        lib.etxb_debug_select_tree.argtypes = [vp, C.c_int]
     lib.etxb_debug_sampler.argtypes = [vp, vp, vp, u32, u32, vp, vp]
     lib.etxb_debug_math.argtypes = [vp, u32, vp, vp, u32, vp]
     _libs[flavor] = lib
@@ -298,6 +300,10 @@ class GPUVCM:
         return self.lib.etxb_stream(self.h)
 
     # -- unit entry points (parity tests) -----------------------------------------------------------------
+    def debug_select_tree(self, wide):
+        """etxb_debug_trace walks the BVH2 (False) or the product build's 4-wide quantised tree (True); returns whether that tree exists."""
+        return self.lib.etxb_debug_select_tree(self.h, 1 if wide else 0) == 1
+
     def debug_trace(self, rays, seeds):
         rays = np.ascontiguousarray(rays, dtype=np.float32)
         seeds = np.ascontiguousarray(seeds, dtype=np.uint32).copy()

@@ -37,6 +37,22 @@ struct alignas(16) F4 {
 constexpr int kBvhStackSize = 64;
 constexpr int kBvhMaxLeafTris = 4;
 
+// Wide, quantised form of the same tree for the product build's dedicated traversal kernels (dwide.cuh): up to four children per node — the
+// BVH2 node's grandchildren, largest box opened first — whose boxes are stored as 8-bit offsets from the node's own corner on a per-axis
+// power-of-two grid (conservative: the decoded box contains the exact one).  64 bytes cover four children instead of two: half the dependent
+// fetches per ray and half the bytes per box.  Leaves are the BVH2's leaves (same references into tri_pos).  Built by build_wide_bvh().
+struct alignas(16) WideNode {
+  float origin[3];     // min corner of the union of the children
+  uint8_t exp[3];      // per axis: grid step = 2^(exp - 127)
+  uint8_t count;       // children in use (1..4)
+  uint8_t qlo[4][3];   // child box, min corner, in grid steps from origin (rounded down)
+  uint8_t qhi[4][3];   // max corner (rounded up)
+  int32_t child[4];    // >= 0: wide node index; < 0: leaf, ~child = (first_slot << 2) | (count - 1)
+  uint32_t pad[2];
+};
+static_assert(sizeof(WideNode) == 64, "WideNode must be 64 bytes");
+constexpr int kWideStackSize = 96;
+
 BVH_FN uint32_t f2u(float f) {
   union { float f; uint32_t u; } c;
   c.f = f;

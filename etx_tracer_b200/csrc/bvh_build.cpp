@@ -232,23 +232,37 @@ void build_bvh(const float* positions, uint32_t position_stride_bytes, const uin
   b.build(0, tri_count, root_box, true);
 
   out.max_depth = b.max_depth;
-  // breadth-first node order: nodes[0 .. k) are then the top levels of the tree, which the traversal kernels copy into shared memory in one bulk
-  // transfer (dtrav.cuh).  Only indices move — boxes, child order and leaves stay, so every traversal visits the same candidates in the same order.
+  // node order: the top of the tree breadth-first (nodes[0 .. kTopNodes) are the levels every ray walks through: the traversal kernels copy
+  // them into shared memory in one bulk transfer, dtrav.cuh), everything below in the builder's depth-first order (a subtree stays contiguous,
+  // which is what the caches want once rays have spread out).  Only indices move — boxes, child order and leaves stay, so every traversal visits
+  // the same candidates in the same order.
   {
+    constexpr size_t kTopNodes = 512;
     const size_t n = b.nodes.size();
-    std::vector<uint32_t> order_bfs;
-    order_bfs.reserve(n);
-    std::vector<uint32_t> new_index(n, 0u);
-    order_bfs.push_back(0u);
-    for (size_t head = 0; head < order_bfs.size(); ++head) {
-      const BvhNode& nd = b.nodes[order_bfs[head]];
-      new_index[order_bfs[head]] = uint32_t(head);
-      if (nd.child0 >= 0) order_bfs.push_back(uint32_t(nd.child0));
-      if ((nd.child1 >= 0) && (nd.child1 != nd.child0)) order_bfs.push_back(uint32_t(nd.child1));
+    std::vector<uint32_t> order_new;
+    order_new.reserve(n);
+    std::vector<uint32_t> new_index(n, 0xffffffffu);
+    order_new.push_back(0u);
+    new_index[0] = 0u;
+    for (size_t head = 0; (head < order_new.size()) && (order_new.size() < kTopNodes); ++head) {
+      const BvhNode& nd = b.nodes[order_new[head]];
+      const int32_t kids[2] = {nd.child0, nd.child1};
+      for (int32_t c : kids) {
+        if ((c >= 0) && (new_index[uint32_t(c)] == 0xffffffffu) && (order_new.size() < kTopNodes)) {
+          new_index[uint32_t(c)] = uint32_t(order_new.size());
+          order_new.push_back(uint32_t(c));
+        }
+      }
     }
-    std::vector<BvhNode> reordered(order_bfs.size());
-    for (size_t k = 0; k < order_bfs.size(); ++k) {
-      BvhNode nd = b.nodes[order_bfs[k]];
+    for (size_t k = 0; k < n; ++k) {
+      if (new_index[k] == 0xffffffffu) {
+        new_index[k] = uint32_t(order_new.size());
+        order_new.push_back(uint32_t(k));
+      }
+    }
+    std::vector<BvhNode> reordered(n);
+    for (size_t k = 0; k < n; ++k) {
+      BvhNode nd = b.nodes[order_new[k]];
       if (nd.child0 >= 0) nd.child0 = int32_t(new_index[uint32_t(nd.child0)]);
       if (nd.child1 >= 0) nd.child1 = int32_t(new_index[uint32_t(nd.child1)]);
       reordered[k] = nd;
@@ -265,6 +279,134 @@ void build_bvh(const float* positions, uint32_t position_stride_bytes, const uin
       out.tri_pos[s * 3 + k] = F4{p[0], p[1], p[2], (k == 0) ? u2f(t) : 0.0f};
     }
   }
+}
+
+namespace {
+
+struct WideChild {
+  float lo[3], hi[3];
+  int32_t ref;  // BVH2 reference: >= 0 inner node, < 0 leaf
+};
+float box_area(const WideChild& c) {
+  float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
+  return dx * dy + dy * dz + dz * dx;
+}
+void children_of(const BvhNode& n, WideChild& a, WideChild& b) {
+  std::memcpy(a.lo, n.lo0, 12);
+  std::memcpy(a.hi, n.hi0, 12);
+  a.ref = n.child0;
+  std::memcpy(b.lo, n.lo1, 12);
+  std::memcpy(b.hi, n.hi1, 12);
+  b.ref = n.child1;
+}
+
+struct WideBuilder {
+  const Bvh& bvh;
+  std::vector<WideNode> nodes;
+  uint32_t max_stack = 0;
+
+  uint32_t build(int32_t bvh2_node, uint32_t stack_above) {
+    // the BVH2 node's children, the widest inner one opened until four are on the table
+    WideChild kids[4];
+    int count = 2;
+    children_of(bvh.nodes[size_t(bvh2_node)], kids[0], kids[1]);
+    if (kids[1].ref == kids[0].ref) count = 1;  // single-triangle root: both slots name the same leaf
+    while (count < 4) {
+      int best = -1;
+      float best_area = -1.0f;
+      for (int k = 0; k < count; ++k) {
+        if ((kids[k].ref >= 0) && (box_area(kids[k]) > best_area)) {
+          best_area = box_area(kids[k]);
+          best = k;
+        }
+      }
+      if (best < 0) break;
+      WideChild a, b;
+      children_of(bvh.nodes[size_t(kids[best].ref)], a, b);
+      kids[best] = a;
+      kids[count++] = b;
+    }
+    const uint32_t index = uint32_t(nodes.size());
+    nodes.emplace_back();
+    WideNode w = {};
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = kids[0].lo[a];
+      hi[a] = kids[0].hi[a];
+      for (int k = 1; k < count; ++k) {
+        lo[a] = std::min(lo[a], kids[k].lo[a]);
+        hi[a] = std::max(hi[a], kids[k].hi[a]);
+      }
+      w.origin[a] = lo[a];
+      // smallest power-of-two step with 255 steps covering the extent
+      float extent = std::max(hi[a] - lo[a], 1.0e-30f);
+      int e = 0;
+      (void)std::frexp(extent / 255.0f, &e);  // extent / 255 = m * 2^e, m in [0.5, 1)  =>  2^e >= extent / 255
+      e = std::max(-126, std::min(127, e));
+      w.exp[a] = uint8_t(e + 127);
+      const float step = std::ldexp(1.0f, e);
+      for (int k = 0; k < count; ++k) {
+        int ql = int(std::floor((kids[k].lo[a] - lo[a]) / step));
+        int qh = int(std::ceil((kids[k].hi[a] - lo[a]) / step));
+        ql = std::max(0, std::min(255, ql));
+        qh = std::max(0, std::min(255, qh));
+        // conservative in float arithmetic: the decoded corner (origin + q * step, as the device computes it) must not cut into the exact box
+        while ((ql > 0) && (lo[a] + float(ql) * step > kids[k].lo[a])) ql--;
+        while ((qh < 255) && (lo[a] + float(qh) * step < kids[k].hi[a])) qh++;
+        w.qlo[k][a] = uint8_t(ql);
+        w.qhi[k][a] = uint8_t(qh);
+      }
+    }
+    w.count = uint8_t(count);
+    max_stack = std::max(max_stack, stack_above + uint32_t(count - 1));
+    for (int k = 0; k < count; ++k) {
+      // when child k is being traversed, the other (count - 1 - k at most) siblings still wait on the stack: bound by count - 1
+      w.child[k] = (kids[k].ref >= 0) ? int32_t(build(kids[k].ref, stack_above + uint32_t(count - 1))) : kids[k].ref;
+    }
+    for (int k = count; k < 4; ++k) w.child[k] = int32_t(0x80000000u);
+    nodes[index] = w;
+    return index;
+  }
+};
+
+}  // namespace
+
+void build_wide_bvh(const Bvh& bvh, WideBvh& out) {
+  WideBuilder b{bvh};
+  b.nodes.reserve(bvh.nodes.size() / 2 + 1);
+  b.build(0, 0u);
+  // top levels breadth-first (staged in shared memory by the persistent kernels), the rest in the builder's depth-first order
+  constexpr size_t kTopNodes = 512;
+  const size_t n = b.nodes.size();
+  std::vector<uint32_t> order_new;
+  order_new.reserve(n);
+  std::vector<uint32_t> new_index(n, 0xffffffffu);
+  order_new.push_back(0u);
+  new_index[0] = 0u;
+  for (size_t head = 0; (head < order_new.size()) && (order_new.size() < kTopNodes); ++head) {
+    const WideNode& nd = b.nodes[order_new[head]];
+    for (int k = 0; k < nd.count; ++k) {
+      int32_t c = nd.child[k];
+      if ((c >= 0) && (new_index[uint32_t(c)] == 0xffffffffu) && (order_new.size() < kTopNodes)) {
+        new_index[uint32_t(c)] = uint32_t(order_new.size());
+        order_new.push_back(uint32_t(c));
+      }
+    }
+  }
+  for (size_t k = 0; k < n; ++k) {
+    if (new_index[k] == 0xffffffffu) {
+      new_index[k] = uint32_t(order_new.size());
+      order_new.push_back(uint32_t(k));
+    }
+  }
+  out.nodes.resize(n);
+  for (size_t k = 0; k < n; ++k) {
+    WideNode nd = b.nodes[order_new[k]];
+    for (int c = 0; c < nd.count; ++c)
+      if (nd.child[c] >= 0) nd.child[c] = int32_t(new_index[uint32_t(nd.child[c])]);
+    out.nodes[k] = nd;
+  }
+  out.max_stack = b.max_stack;
 }
 
 }  // namespace etxb

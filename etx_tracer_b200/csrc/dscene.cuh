@@ -41,9 +41,11 @@ struct DeviceScene {
   const etxb_emitter* emitters;
   const DSpectrum* spectra;
   const etxb_distribution_entry* emitter_dist;  // E + 1 entries
-  const BvhNode* bvh_nodes;  // breadth-first order: the first nodes are the top levels (dtrav.cuh stages them in shared memory)
+  const BvhNode* bvh_nodes;  // the first 512 nodes are the top levels, breadth-first (dtrav.cuh stages them in shared memory); below: depth-first
   const float4* bvh_tris;
   uint32_t bvh_node_count;
+  const WideNode* wide_nodes;  // product build, scenes with stochastic BSDFs: the 4-wide quantised form of the same tree (dwide.cuh); else null
+  uint32_t wide_node_count;
   const float* xyz_table;           // 441 x 3
   const float* rgb_response_table;  // 391 x 3
   const uint8_t* bn_sobol;          // 256 x 256

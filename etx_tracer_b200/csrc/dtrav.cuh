@@ -4,7 +4,7 @@
 // sources/etx/rt/rt.cxx:250-279, 428-466, 468-579).  What round 1 measured on the thread-per-ray kernel (profiles/r1b_c2_k_trace_closest.raw.csv,
 // profiles/r2a_c3_k_trace_closest.raw.csv): 6-10 of 32 lanes busy (a warp lives as long as its longest ray) and every node fetch a dependent
 // trip to L1 / L2.  Here:
-//   * the BVH nodes are in breadth-first order (bvh_build.cpp), so the first kNodeletNodes nodes ARE the top ~9 levels every ray walks through;
+//   * the first kNodeletNodes BVH nodes are the top ~9 levels in breadth-first order (bvh_build.cpp; the rest stays depth-first), the ones every ray walks through;
 //     each CTA copies them once into shared memory with one cp.async.bulk (TMA bulk copy, completion on an mbarrier) — 32 KB per CTA, the
 //     kernel is persistent, so the copy is amortised over thousands of rays;
 //   * rays come from a compacted list (queue of path ids / SoA shadow segments) through a shared cursor: a warp refills its idle lanes with

@@ -15,6 +15,7 @@
 #include "dsss.cuh"
 #include "dclosure.cuh"
 #include "dtrav.cuh"
+#include "dwide.cuh"
 
 // resident blocks per SM the bounce / connection kernels are compiled for (128 threads each: 4 blocks = 128 registers per thread).
 // Measured on the B200 (bench.py --lanes 1): 1|1 -> 4|4 gives C2 11.04 -> 11.36 and C3 5.55 -> 5.79 Msamples/s; 2 and 3 change nothing.
@@ -1959,19 +1960,60 @@ __global__ void __launch_bounds__(kTraversalBlock) k_trace_closest_persistent(co
 #endif
 }
 
+// Closest hit through the 4-wide quantised tree (dwide.cuh), one ray per thread: the product build's kernel for scenes with stochastic BSDFs.
+__global__ void __launch_bounds__(256) k_trace_closest_wide(const __grid_constant__ LaunchParams p, const uint32_t* queue, const uint32_t* queue_count, uint32_t* material_keys,
+                                                            uint32_t key_limit) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= *queue_count) {
+    if ((material_keys != nullptr) && (q < key_limit)) material_keys[q] = 0x100u;
+    return;
+  }
+  uint32_t i = queue[q];
+  float4 o = p.paths.ray_o[i], d = p.paths.ray_d[i];
+  Smp smp;
+  smp.seed = p.paths.misc[i].x;
+  smp.fixed_u = smp.fixed_v = smp.fixed_w = 0.0f;
+  HitRec best = {0.0f, 0.0f, 0.0f, kInvalidIndex};
+  ClosestHitVisitor visit{p.scene, &smp, &best};
+  const WideNodes nodes{nullptr, p.scene.wide_nodes, 0u};
+  WideWalk walk;
+  WideHit stack[kWideStackSize];
+  uint32_t n_nodes = 0, n_tris = 0;
+  wide_begin(walk, {o.x, o.y, o.z}, {d.x, d.y, d.z}, o.w, d.w);
+  while (!wide_step(walk, stack, nodes, p.scene.bvh_tris, visit, n_nodes, n_tris)) {
+  }
+  p.paths.hit[i] = make_float4(best.u, best.v, best.t, __uint_as_float(best.tri));
+  p.paths.misc[i].x = smp.seed;
+  if (material_keys != nullptr) material_keys[q] = (best.tri == kInvalidIndex) ? 0xffu : umin(load_triangle_material(p.scene, best.tri), 0xfeu);
+  counter_add(&p.counters->rays_closest, 1u);
+#ifdef ETXB_COUNT_TRAVERSAL
+  counter_add(&p.counters->nodes, n_nodes);
+  counter_add(&p.counters->tris, n_tris);
+  counter_add(&p.counters->nodes_closest, n_nodes);
+  counter_add(&p.counters->tris_closest, n_tris);
+#endif
+}
+
 // The shadow segments of one bounce (ShadowBatch, atomic mode): any-hit on the same persistent, nodelet-staged, lane-refilled walk; a segment
 // that reaches its end adds its contribution to its target (a path's gathered sum, or a pixel of the light image).  Opaque scenes only: any
 // non-Void surface on the segment occludes (rt.cxx:468-579 without Boundary crossings).
+template <bool WIDE>
 __global__ void __launch_bounds__(kTraversalBlock) k_shadow_resolve(const __grid_constant__ LaunchParams p, uint32_t* cursor) {
+  // 32 KB of shared memory: the top kNodeletNodes nodes of the tree this instantiation walks (both node types are 64 bytes)
   __shared__ __align__(128) BvhNode s_nodes[kNodeletNodes];
   __shared__ __align__(8) uint64_t s_bar;
-  const uint32_t staged = nodelet_stage(s_nodes, &s_bar, p.scene.bvh_nodes, p.scene.bvh_node_count);
+  static_assert(sizeof(WideNode) == sizeof(BvhNode), "one staging buffer serves both trees");
+  const uint32_t staged = WIDE ? nodelet_stage(s_nodes, &s_bar, reinterpret_cast<const BvhNode*>(p.scene.wide_nodes), p.scene.wide_node_count)
+                               : nodelet_stage(s_nodes, &s_bar, p.scene.bvh_nodes, p.scene.bvh_node_count);
   const StagedNodes nodes{s_nodes, p.scene.bvh_nodes, staged};
+  const WideNodes wide_nodes{reinterpret_cast<const WideNode*>(s_nodes), p.scene.wide_nodes, staged};
   const uint32_t total = umin(p.shadow_count[0], p.shadow_capacity);
   bool active = false, exhausted = false;
   uint32_t k = 0, n_nodes = 0, n_tris = 0, splats = 0;
   RayWalk walk;
-  int32_t stack[kBvhStackSize];
+  WideWalk wide_walk;
+  int32_t stack[WIDE ? 1 : kBvhStackSize];
+  WideHit wide_stack[WIDE ? kWideStackSize : 1];
   OcclusionVisitor visit{p.scene, false};
   auto contribute = [&](uint32_t slot, uint32_t target) {
     float4 v = p.shadow_value[slot];
@@ -2002,7 +2044,11 @@ __global__ void __launch_bounds__(kTraversalBlock) k_shadow_resolve(const __grid
         t_max = sqrtf(t_max);
         direction /= t_max;
         t_max -= fmaxf(kRayEpsilon, t_max * kRayEpsilon);
-        walk.begin({a.x, a.y, a.z}, direction, kRayEpsilon, t_max);
+        if constexpr (WIDE) {
+          wide_begin(wide_walk, {a.x, a.y, a.z}, direction, kRayEpsilon, t_max);
+        } else {
+          walk.begin({a.x, a.y, a.z}, direction, kRayEpsilon, t_max);
+        }
         visit.occluded = false;
         active = true;
       }
@@ -2012,7 +2058,13 @@ __global__ void __launch_bounds__(kTraversalBlock) k_shadow_resolve(const __grid
       continue;
     }
     while (active) {
-      if (walk_step(walk, stack, nodes, p.scene.bvh_tris, visit, n_nodes, n_tris)) {
+      bool done;
+      if constexpr (WIDE) {
+        done = wide_step(wide_walk, wide_stack, wide_nodes, p.scene.bvh_tris, visit, n_nodes, n_tris);
+      } else {
+        done = walk_step(walk, stack, nodes, p.scene.bvh_tris, visit, n_nodes, n_tris);
+      }
+      if (done) {
         if (!visit.occluded) contribute(k, target);
         active = false;
       } else if (!exhausted && (__popc(__activemask()) < kRefillLanes)) {
@@ -2160,6 +2212,31 @@ __global__ void k_debug_trace(const __grid_constant__ DeviceScene sc, const floa
   smp.seed = seeds[i];
   smp.fixed_u = smp.fixed_v = smp.fixed_w = 0.0f;
   HitRec h = trace_closest(sc, {r[0], r[1], r[2]}, {r[4], r[5], r[6]}, r[3], r[7], smp, nullptr);
+  seeds[i] = smp.seed;
+  hits_tri[i] = h.tri;
+  bool hit = h.tri != kInvalidIndex;
+  hits_uv_t[size_t(i) * 3 + 0] = hit ? h.u : 0.0f;
+  hits_uv_t[size_t(i) * 3 + 1] = hit ? h.v : 0.0f;
+  hits_uv_t[size_t(i) * 3 + 2] = hit ? h.t : 0.0f;
+}
+
+// the same query through the 4-wide quantised tree (product build, scenes that have one)
+__global__ void k_debug_trace_wide(const __grid_constant__ DeviceScene sc, const float* rays, uint32_t* seeds, uint32_t count, float* hits_uv_t, uint32_t* hits_tri) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float* r = rays + size_t(i) * 8;
+  Smp smp;
+  smp.seed = seeds[i];
+  smp.fixed_u = smp.fixed_v = smp.fixed_w = 0.0f;
+  HitRec h = {0.0f, 0.0f, 0.0f, kInvalidIndex};
+  ClosestHitVisitor visit{sc, &smp, &h};
+  const WideNodes nodes{nullptr, sc.wide_nodes, 0u};
+  WideWalk walk;
+  WideHit stack[kWideStackSize];
+  uint32_t n_nodes = 0, n_tris = 0;
+  wide_begin(walk, {r[0], r[1], r[2]}, {r[4], r[5], r[6]}, r[3], r[7]);
+  while (!wide_step(walk, stack, nodes, sc.bvh_tris, visit, n_nodes, n_tris)) {
+  }
   seeds[i] = smp.seed;
   hits_tri[i] = h.tri;
   bool hit = h.tri != kInvalidIndex;

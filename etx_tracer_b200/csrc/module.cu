@@ -102,7 +102,10 @@ struct etxb_ctx {
   bool plain_scene = false;           // set at upload: the scene qualifies
   bool opaque_scene = false;          // set at upload: no alpha test can reject a hit (every opacity 1, no alpha images), no Boundary surfaces / media
   bool shadow_atomic = true;          // product build, opaque scenes with stochastic BSDFs: shadow segments resolved by k_shadow_resolve (ETXB_SHADOW_ATOMIC=0: inline)
-  bool persistent_trace = true;       // closest hits on the persistent, nodelet-staged kernel (ETXB_TRACE_PERSISTENT=0: thread-per-ray k_trace_closest)
+  bool persistent_trace = false;      // closest hits on the persistent, nodelet-staged, lane-refilled kernel (ETXB_TRACE_PERSISTENT=1).  Measured on the B200 (C3,
+                                      // round 2): 27.1 ms per iteration against 22.9 ms for the thread-per-ray kernel — one ray per path leaves little to refill
+                                      // from, and the walk's dynamic stack costs the same either way — so the default stays thread-per-ray; the shadow segments
+                                      // (2-3x as many rays, from one list) always go through the persistent kernel
   bool merge_closure = true;          // generic photon gather on vertex closures (dclosure.cuh; ETXB_MERGE_CLOSURE=0: the batched generic kernel of round 1)
   bool merge_batched = true;          // generic photon gather batches its BSDF evaluations across the queries of a warp (ETXB_MERGE_BATCHED=0: per query)
   bool sort_by_material = true;       // group path queues and the connection list by material where BSDFs are costly (ETXB_SORT_MATERIAL=0: A/B switch)
@@ -122,6 +125,9 @@ struct etxb_ctx {
   std::vector<DevBuf<uint8_t>> image_pixels, image_dists;
   DevBuf<etxb_distribution_entry> emitter_dist;
   DevBuf<BvhNode> bvh_nodes;
+  DevBuf<WideNode> wide_nodes;
+  bool debug_trace_wide = false;      // etxb_debug_select_tree: etxb_debug_trace walks the 4-wide tree when the scene has one
+  bool wide_bvh = true;               // product build, scenes with stochastic BSDFs: closest hits and shadow segments walk the 4-wide quantised tree (ETXB_WIDE_BVH=0: BVH2)
   DevBuf<float4> bvh_tris;
   DevBuf<float> xyz_table, rgb_response_table;
   DevBuf<uint8_t> bn_sobol, bn_scrambling, bn_ranking;
@@ -428,6 +434,8 @@ int launch_trace_closest(etxb_ctx* ctx, const LaunchParams& p, const uint32_t* q
     CUDA_OK(ctx, cudaMemsetAsync(ctx->trace_cursor.ptr, 0, 4, ctx->stream));
     const uint32_t blocks = std::min<uint32_t>(blocks_for(active, kTraversalBlock), 148u);
     k_trace_closest_persistent<<<blocks, kTraversalBlock, 0, ctx->stream>>>(p, queue, count, keys, active, ctx->trace_cursor.ptr);
+  } else if (p.scene.wide_nodes != nullptr) {
+    k_trace_closest_wide<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, queue, count, keys, active);
   } else {
     k_trace_closest<<<blocks_for(active, 256), 256, 0, ctx->stream>>>(p, queue, count, keys, active);
   }
@@ -437,7 +445,11 @@ int launch_trace_closest(etxb_ctx* ctx, const LaunchParams& p, const uint32_t* q
 int launch_shadow_resolve(etxb_ctx* ctx, const LaunchParams& p, uint32_t active) {
   CUDA_OK(ctx, cudaMemsetAsync(ctx->trace_cursor.ptr + 1, 0, 4, ctx->stream));
   const uint32_t blocks = std::min<uint32_t>(blocks_for(std::min<uint64_t>(uint64_t(active) * 4ull, 0x7fffffffull), kTraversalBlock), 148u);
-  k_shadow_resolve<<<blocks, kTraversalBlock, 0, ctx->stream>>>(p, ctx->trace_cursor.ptr + 1);
+  if (p.scene.wide_nodes != nullptr) {
+    k_shadow_resolve<true><<<blocks, kTraversalBlock, 0, ctx->stream>>>(p, ctx->trace_cursor.ptr + 1);
+  } else {
+    k_shadow_resolve<false><<<blocks, kTraversalBlock, 0, ctx->stream>>>(p, ctx->trace_cursor.ptr + 1);
+  }
   return ETXB_OK;
 }
 
@@ -838,6 +850,7 @@ int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
   if (const char* e = getenv("ETXB_MERGE_BATCHED")) ctx->merge_batched = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_CLOSURE")) ctx->merge_closure = (e[0] != '0');
   if (const char* e = getenv("ETXB_SHADOW_ATOMIC")) ctx->shadow_atomic = (e[0] != '0');
+  if (const char* e = getenv("ETXB_WIDE_BVH")) ctx->wide_bvh = (e[0] != '0');
   if (const char* e = getenv("ETXB_TRACE_PERSISTENT")) ctx->persistent_trace = (e[0] != '0');
   if (const char* e = getenv("ETXB_PLAIN_KERNELS")) ctx->plain_kernels = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_MATERIAL_MAJOR")) ctx->merge_material_major = (e[0] != '0');
@@ -897,6 +910,7 @@ void etxb_destroy(etxb_ctx* ctx) {
   for (auto& b : ctx->image_dists) b.release();
   ctx->emitter_dist.release();
   ctx->bvh_nodes.release();
+  ctx->wide_nodes.release();
   ctx->xyz_table.release();
   ctx->rgb_response_table.release();
   ctx->bn_sobol.release();
@@ -1204,6 +1218,21 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   d.bvh_nodes = ctx->bvh_nodes.ptr;
   d.bvh_tris = ctx->bvh_tris.ptr;
   d.bvh_node_count = uint32_t(bvh.nodes.size());
+  d.wide_nodes = nullptr;
+  d.wide_node_count = 0;
+#if !(defined(ETXB_PARITY) && ETXB_PARITY)
+  if (ctx->wide_bvh && ctx->has_stochastic_merge) {
+    // the sampler streams of such a scene's stochastic stages are the product build's own already: its traversal kernels may meet candidates in
+    // another order, so they walk the 4-wide quantised form of the tree (dwide.cuh); Lambert / delta scenes keep the oracle's candidate order
+    WideBvh wide;
+    build_wide_bvh(bvh, wide);
+    if (wide.max_stack < uint32_t(kWideStackSize)) {
+      if (int rc = upload(ctx, ctx->wide_nodes, wide.nodes.data(), wide.nodes.size())) return rc;
+      d.wide_nodes = ctx->wide_nodes.ptr;
+      d.wide_node_count = uint32_t(wide.nodes.size());
+    }
+  }
+#endif
   d.emitter_count = uint32_t(s.emitter_instances.count);
   d.triangle_count = uint32_t(s.triangles.count);
   d.emitter_total_weight = s.emitters_distribution.total_weight;
@@ -1733,7 +1762,11 @@ int etxb_debug_trace(etxb_ctx* ctx, const float* rays, uint32_t* seeds, uint32_t
   CUDA_OK(ctx, d_tri.alloc(count));
   CUDA_OK(ctx, cudaMemcpy(d_rays.ptr, rays, d_rays.bytes(), cudaMemcpyHostToDevice));
   CUDA_OK(ctx, cudaMemcpy(d_seeds.ptr, seeds, d_seeds.bytes(), cudaMemcpyHostToDevice));
-  k_debug_trace<<<blocks_for(count, 128), 128, 0, ctx->stream>>>(ctx->dscene, d_rays.ptr, d_seeds.ptr, count, d_uvt.ptr, d_tri.ptr);
+  if (ctx->debug_trace_wide && (ctx->dscene.wide_nodes != nullptr)) {
+    k_debug_trace_wide<<<blocks_for(count, 128), 128, 0, ctx->stream>>>(ctx->dscene, d_rays.ptr, d_seeds.ptr, count, d_uvt.ptr, d_tri.ptr);
+  } else {
+    k_debug_trace<<<blocks_for(count, 128), 128, 0, ctx->stream>>>(ctx->dscene, d_rays.ptr, d_seeds.ptr, count, d_uvt.ptr, d_tri.ptr);
+  }
   ctx->kernel_launches += 1;
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   CUDA_OK(ctx, cudaMemcpy(seeds, d_seeds.ptr, d_seeds.bytes(), cudaMemcpyDeviceToHost));
@@ -1744,6 +1777,14 @@ int etxb_debug_trace(etxb_ctx* ctx, const float* rays, uint32_t* seeds, uint32_t
   d_seeds.release();
   d_tri.release();
   return ETXB_OK;
+}
+
+// Test hook: which tree etxb_debug_trace walks (0: the BVH2 shared with the oracle; 1: the 4-wide quantised tree of the product build).  Returns 1
+// when the requested tree exists for the uploaded scene.
+int etxb_debug_select_tree(etxb_ctx* ctx, int wide) {
+  if (!ctx) return ETXB_ERR_INVALID_ARGUMENT;
+  ctx->debug_trace_wide = wide != 0;
+  return (!wide || (ctx->dscene.wide_nodes != nullptr)) ? 1 : 0;
 }
 
 int etxb_debug_sampler(etxb_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t count, uint32_t draws, uint32_t* out_seed, float* out_values) {
@@ -1937,7 +1978,12 @@ int etxb_group_create(etxb_group** out, const etxb_device_config* cfg, uint32_t 
   }
   grp->lane_next.assign(lanes, 0u);
   cudaSetDevice(grp->device);
-  cudaStreamCreateWithFlags(&grp->stream, cudaStreamNonBlocking);
+  {
+    // the frame combine / reduce must not queue behind the lanes' kernels: highest priority
+    int prio_low = 0, prio_high = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high);
+    cudaStreamCreateWithPriority(&grp->stream, cudaStreamNonBlocking, prio_high);
+  }
   for (uint32_t l = 0; l < lanes; ++l) grp->workers.emplace_back(group_worker, grp, l);
   *out = grp;
   return ETXB_OK;

@@ -423,3 +423,55 @@ def test_camera_variants_are_bit_exact(api, oracle_mod, kind, spectral):
     img, ref = f.film(S.FILM_RESULT)[..., :3], o.film(S.FILM_RESULT)[..., :3]
     assert np.isfinite(img).all() and rel_l2(img, ref) < 0.05
     f.close()
+
+
+def test_device_closest_hits_against_float64_brute_force_on_the_million_triangle_room(api):
+    """The device ray casters against an independent answer: every ray against EVERY triangle of BASELINE config 3's geometry in float64 (no BVH,
+    no shared code) — the BVH2 walk the oracle shares, and the 4-wide quantised tree of the product build (dwide.cuh)."""
+    sd = scenes.procedural_room(32, 18, env_size=(64, 32))
+    import ctypes as C
+    sc = sd.scene
+    nv, nt = int(sc["vertices"]["count"][0]), int(sc["triangles"]["count"][0])
+    verts = np.frombuffer((C.c_char * (nv * S.VERTEX.itemsize)).from_address(int(sc["vertices"]["a"][0])), dtype=S.VERTEX)
+    tris = np.frombuffer((C.c_char * (nt * S.TRIANGLE.itemsize)).from_address(int(sc["triangles"]["a"][0])), dtype=S.TRIANGLE)
+    pos = verts["pos"].astype(np.float64)
+    a, b, c = pos[tris["i"][:, 0]], pos[tris["i"][:, 1]], pos[tris["i"][:, 2]]
+    rng = np.random.default_rng(7)
+    n = 256
+    lo, hi = pos.min(axis=0), pos.max(axis=0)
+    origin = lo + (hi - lo) * (0.3 + 0.4 * rng.random((n, 3)))
+    direction = rng.normal(size=(n, 3))
+    direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+    rays = np.zeros((n, 8), dtype=np.float32)
+    rays[:, 0:3], rays[:, 3], rays[:, 4:7], rays[:, 7] = origin, 1e-4, direction, 3.0e38
+    o64, d64 = rays[:, 0:3].astype(np.float64), rays[:, 4:7].astype(np.float64)
+    e1, e2 = b - a, c - a
+    best_t = np.full(n, np.inf)
+    best_tri = np.full(n, -1, dtype=np.int64)
+    for k in range(n):  # Moeller-Trumbore over all triangles, one ray at a time (vectorised over the million triangles)
+        pv = np.cross(d64[k], e2)
+        det = (e1 * pv).sum(axis=1)
+        ok = np.abs(det) > 0
+        inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+        tv = o64[k] - a
+        u = (tv * pv).sum(axis=1) * inv
+        qv = np.cross(tv, e1)
+        v = (qv * d64[k]).sum(axis=1) * inv
+        t = (qv * e2).sum(axis=1) * inv
+        hit = ok & (u >= 0) & (v >= 0) & (u + v <= 1) & (t > 1e-4)
+        if hit.any():
+            j = np.where(hit, t, np.inf).argmin()
+            best_t[k], best_tri[k] = t[j], j
+    seeds = np.arange(n, dtype=np.uint32) + 1
+    assert (best_tri >= 0).mean() > 0.9
+    for flavor, wide in (("parity", False), ("fast", False), ("fast", True)):
+        g = api.GPUVCM(sd, flavor=flavor)
+        assert g.debug_select_tree(wide) or not wide, "the room has stochastic BSDFs: the product build must have built the wide tree"
+        uvt, tri, _ = g.debug_trace(rays, seeds)
+        g.close()
+        found = tri != S.INVALID
+        assert np.array_equal(found, best_tri >= 0), (flavor, wide)
+        # the same triangle, or (edge / coplanar ties) another one at the same distance
+        same = tri[found].astype(np.int64) == best_tri[found]
+        np.testing.assert_allclose(uvt[found, 2], best_t[found], rtol=2e-4, atol=1e-5, err_msg=f"{flavor} wide={wide}")
+        assert same.mean() > 0.97, (flavor, wide, same.mean())

@@ -202,4 +202,6 @@ def test_cpp_adapter_renders_on_the_device_with_a_non_blocking_update(tmp_path):
     g.render(6)
     ref = g.film(S.FILM_RESULT)
     g.close()
-    assert np.array_equal(film[..., :3].view(np.uint32), ref[..., :3].view(np.uint32)), "C++ adapter and ctypes mirror must render the same film"
+    # same module, same iterations: the camera part is deterministic, the light image is a float-atomic sum (order differs from run to run)
+    err = float(np.sqrt(((film[..., :3].astype(np.float64) - ref[..., :3]) ** 2).sum()) / np.sqrt((ref[..., :3].astype(np.float64) ** 2).sum()))
+    assert err < 1e-5, f"C++ adapter and ctypes mirror must render the same film: relative L2 {err:.3e}"

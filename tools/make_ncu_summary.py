@@ -41,7 +41,12 @@ def summarise(path):
     idx = {h: i for i, h in enumerate(hdr)}
 
     def get(k):
-        return (r[idx[k]], units[idx[k]]) if k in idx else (None, None)
+        if k in idx:
+            return r[idx[k]], units[idx[k]]
+        for h, i in idx.items():  # section-prefixed duplicates ("SM_B.TriageCompute.l1tex__t_sectors.sum")
+            if h.endswith("." + k):
+                return r[i], units[i]
+        return None, None
     name = r[idx["Kernel Name"]]
     fn = re.sub(r"^void ", "", name).split("<")[0].split("(")[0]
     t = to_ms(*get("gpu__time_duration.sum"))
@@ -52,6 +57,12 @@ def summarise(path):
            "l1_hit_pct": num(get("l1tex__t_sector_hit_rate.pct")[0]), "l2_hit_pct": num(get("lts__t_sector_hit_rate.pct")[0])}
     rd, wr = to_bytes(*get("dram__bytes_read.sum")), to_bytes(*get("dram__bytes_write.sum"))
     l2, l1 = to_bytes(*get("lts__t_bytes.sum")), to_bytes(*get("l1tex__t_bytes.sum"))
+    if l2 is None and num(get("lts__t_sectors.sum")[0]) is not None:
+        l2 = num(get("lts__t_sectors.sum")[0]) * 32.0
+    if l1 is None and num(get("l1tex__t_sectors.sum")[0]) is not None:
+        l1 = num(get("l1tex__t_sectors.sum")[0]) * 32.0
+    out["l2_throughput_pct_of_peak"] = num(get("lts__throughput.avg.pct_of_peak_sustained_elapsed")[0])
+    out["l1_throughput_pct_of_peak"] = num(get("l1tex__throughput.avg.pct_of_peak_sustained_elapsed")[0])
     if t:
         sec = t * 1e-3
         out.update({"dram_read_GB": None if rd is None else rd / 1e9, "dram_write_GB": None if wr is None else wr / 1e9,
