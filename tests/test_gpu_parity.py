@@ -358,7 +358,9 @@ def test_reference_loaded_cornell_asset_is_bit_exact(api, oracle_mod):
     from etx_tracer_b200 import pod_io
     sd = pod_io.load(os.path.join(GOLDEN, "ref_cornell_40.npz"))
     assert sd.triangle_count == 138318 and (sd.width, sd.height) == (40, 40)
-    _compare_with_oracle(api, oracle_mod, sd, 2, fast_tolerance=0.3)
+    # bit-exact for the parity build; the product build of this asset is held to the converged statistical test
+    # (test_gpu_statistical.py::test_reference_cornell_asset_product_build), not to a 2-spp image distance
+    _compare_with_oracle(api, oracle_mod, sd, 2)
 
 
 @pytest.mark.parametrize("lanes", [2, 3])
@@ -463,7 +465,7 @@ def test_device_closest_hits_against_float64_brute_force_on_the_million_triangle
             j = np.where(hit, t, np.inf).argmin()
             best_t[k], best_tri[k] = t[j], j
     seeds = np.arange(n, dtype=np.uint32) + 1
-    assert (best_tri >= 0).mean() > 0.9
+    assert (best_tri >= 0).mean() > 0.5  # the room is open to the sky: a quarter of the random rays leave through the windows
     for flavor, wide in (("parity", False), ("fast", False), ("fast", True)):
         g = api.GPUVCM(sd, flavor=flavor)
         assert g.debug_select_tree(wide) or not wide, "the room has stochastic BSDFs: the product build must have built the wide tree"
