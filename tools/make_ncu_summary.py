@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NAMES = {  # kernel function -> bench.py's kernel key
-    "k_trace_closest_persistent": "trace_closest", "k_trace_closest": "trace_closest", "k_light_bounce": "light_bounce", "k_camera_shade": "camera_shade",
+    "k_trace_closest_persistent": "trace_closest(persistent)", "k_trace_closest_wide": "trace_closest", "k_trace_closest": "trace_closest(bvh2)", "k_light_bounce": "light_bounce", "k_camera_shade": "camera_shade",
     "k_camera_connect_deferred": "camera_connect", "k_camera_connect": "camera_connect", "k_shadow_resolve": "shadow_trace", "k_shadow_trace": "shadow_trace",
     "k_camera_merge_closure": "camera_merge_generic", "k_camera_merge_generic_batched": "camera_merge_generic", "k_camera_merge_coop": "camera_merge",
     "k_camera_continue": "camera_continue"}
