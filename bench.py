@@ -354,6 +354,8 @@ def main():
         g.wait()
         sync_all()
         g.run(args.warmup)
+        film_to_host(host_film)  # untimed: the first collective on a communicator sets up its NVLink channels (hundreds of ms with 8 ranks)
+        sync_all()
         t0 = time.time()
         film_reads = 0
         for _ in range(args.steps):

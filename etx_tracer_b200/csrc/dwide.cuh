@@ -47,16 +47,23 @@ DEV int wide_node_hits(const WideNodes& nodes, int32_t i, const RayWalk& r, Wide
   const uint32_t qw[6] = {b.x, b.y, b.z, b.w, c.x, c.y};  // 24 bytes: qlo then qhi
   const int32_t child[4] = {int32_t(c.z), int32_t(c.w), int32_t(d.x), int32_t(d.y)};
   auto q = [&](uint32_t byte) { return float((qw[byte >> 2] >> ((byte & 3u) * 8u)) & 0xffu); };
+  // plane distances straight from the quantised coordinates: t = (origin + q * step - ray_o) * inv_d = q * (step * inv_d) + (origin - ray_o) * inv_d —
+  // one multiply-add per plane, the two per-axis constants once per node (the compressed wide BVH's standard form)
+  const float ax = sx * r.ix, ay = sy * r.iy, az = sz * r.iz;
+  const float bx = (ox - r.ox) * r.ix, by = (oy - r.oy) * r.iy, bz = (oz - r.oz) * r.iz;
   // the four entry distances (kMaxFloat = missed / unused slot), then a 5-comparator sorting network: everything stays in registers
   float t[4];
   int32_t ref[4];
 #pragma unroll
   for (uint32_t k = 0; k < 4u; ++k) {
-    const float lo[3] = {ox + q(k * 3u + 0u) * sx, oy + q(k * 3u + 1u) * sy, oz + q(k * 3u + 2u) * sz};
-    const float hi[3] = {ox + q(12u + k * 3u + 0u) * sx, oy + q(12u + k * 3u + 1u) * sy, oz + q(12u + k * 3u + 2u) * sz};
-    float t_entry;
-    const bool hit = (k < count) && slab(lo, hi, r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, r.tmin, r.tmax, t_entry);
-    t[k] = hit ? t_entry : kMaxFloat;
+    const float tx0 = fmaf(q(k * 3u + 0u), ax, bx), tx1 = fmaf(q(12u + k * 3u + 0u), ax, bx);
+    const float ty0 = fmaf(q(k * 3u + 1u), ay, by), ty1 = fmaf(q(12u + k * 3u + 1u), ay, by);
+    const float tz0 = fmaf(q(k * 3u + 2u), az, bz), tz1 = fmaf(q(12u + k * 3u + 2u), az, bz);
+    const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), r.tmin));
+    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), r.tmax));
+    tf = tf * 1.0000004f;  // conservative far plane (2 ulp), like bvh.h slab()
+    const bool hit = (k < count) && (tn <= tf);
+    t[k] = hit ? tn : kMaxFloat;
     ref[k] = child[k];
   }
   auto cswap = [&](int i, int j) {
@@ -139,6 +146,12 @@ DEV bool wide_step(WideWalk& w, WideHit* stack, const WideNodes& nodes, const fl
 
 DEV void wide_begin(WideWalk& w, V3 o, V3 d, float t0, float t1) {
   w.ray.begin(o, d, t0, t1);
+  // the plane distances are formed as q * (step / d) + (origin - o) / d: a direction component of exactly zero would turn them into inf - inf;
+  // a huge finite reciprocal keeps the slab logic (the ray is inside the slab's extent or misses it) without NaNs.  The triangle test uses d itself.
+  auto safe_inv = [](float x) { return (fabsf(x) > 1.0e-20f) ? 1.0f / x : copysignf(1.0e20f, x); };
+  w.ray.ix = safe_inv(d.x);
+  w.ray.iy = safe_inv(d.y);
+  w.ray.iz = safe_inv(d.z);
   w.cur = 0;
   w.sp = 0;
 }
