@@ -301,11 +301,12 @@ def main():
         # tile mode: two iterations in flight per GPU (measured at N = 2: 30.7 Msamples/s with 2, 15.1 with 4 — every lane has two rendezvous with
         # its peers per iteration, and four lanes' collectives wait on each other across the ranks)
         mode_lanes = min(lanes, 2) if mode == "tile" else lanes
-        g = GPUVCMGroup(sd, lanes=mode_lanes, flavor="fast", device=local_rank, profile=True)
+        # iteration mode: one more lane, reserved for camera-split iterations (the remainder when K is not a multiple of the GPUs)
+        g = GPUVCMGroup(sd, lanes=mode_lanes + (1 if mode == "iteration" else 0), flavor="fast", device=local_rank, profile=True)
         if mode == "tile":
             g.comm_init(world, rank, distribute_comm_ids(dist, rank, mode_lanes + 1, comm_unique_ids, device=device))
         elif mode == "iteration":
-            g.comm_init_replicas(world, rank, distribute_comm_ids(dist, rank, 1, comm_unique_ids, device=device))
+            g.comm_init_replicas(world, rank, distribute_comm_ids(dist, rank, 1, comm_unique_ids, device=device), split_lane=True)
         g.options[:] = workload_vcm_options(args)
         multi = mode != "single"
         warm = args.warmup * (world if mode == "iteration" else 1)  # every rank warms up on `warmup` iterations of its own
@@ -344,9 +345,9 @@ def main():
         mine = max(1, sum(1 for j in range(args.steps) if (mode != "iteration") or (j % world == rank)))
         comm_ms = {k: round(v[0] / mine, 3) for k, v in ktimes.items() if k.startswith("nccl_")}
 
-        # ---- end to end through the public API, host buffers inside the timed region: every step pushes the options host -> module, queues one
-        # more iteration of the job and brings the current frame (mean over the iterations finished so far) device -> pinned host; the region ends
-        # when every queued iteration has finished and the final frame is on the host
+        # ---- end to end through the public API, host buffers inside the timed region: the K iterations are queued by the first step (the call a
+        # user makes), every step pushes the options host -> module and brings the current frame (mean over the iterations finished so far) device ->
+        # pinned host; the region ends when every queued iteration has finished and the final frame is on the host
         pinned = torch.empty((sd.height, sd.width, 4), dtype=torch.float32).pin_memory()
         host_film = pinned.numpy()
         g.run(0)
@@ -358,9 +359,10 @@ def main():
         sync_all()
         t0 = time.time()
         film_reads = 0
-        for _ in range(args.steps):
+        for step in range(args.steps):
             g.set_options()
-            g.enqueue(1)
+            if step == 0:
+                g.enqueue(args.steps)  # the call a user makes: render K iterations; the frame is then read once per step while they run
             film_to_host(host_film)
             film_reads += 1
         g.wait()
@@ -494,8 +496,8 @@ def main():
                            "parallelism": {"single": f"one GPU, {lanes} iterations in flight",
                                            "tile": f"pixel tiles (32x32, round-robin) over {world} GPUs inside the module, {min(lanes, 2)} iterations in flight per GPU; per iteration "
                                                    f"ncclAllReduce of the light image + all-gather of the photon records, per frame ncclReduce of the film",
-                                           "iteration": f"the job's iterations dealt to {world} GPUs (index j on rank j % {world}), {lanes} in flight per GPU; per frame one "
-                                                        f"count-weighted ncclReduce of the films"}[best["mode"]],
+                                           "iteration": f"the job's iterations dealt to {world} GPUs (index j on rank j % {world}; the K % {world} left over are split by camera tile, each "
+                                                        f"part tracing the whole light pass itself), {lanes} in flight per GPU; per frame one count-weighted ncclReduce of the films"}[best["mode"]],
                            "mode": best["mode"],
                            "collective": None if world == 1 else "NCCL (communicators created inside the module: etxb_group_comm_init / etxb_group_comm_init_replicas)",
                            "collective_ms_per_iteration": best["collective_ms_per_iteration"],

@@ -69,6 +69,7 @@ def load_library(flavor="fast"):
         lib.etxb_group_comm_init.argtypes = [vp, u32, u32, vp, u32]
         lib.etxb_group_comm_reduce_film.argtypes = [vp, u32, vp, u64]
         lib.etxb_group_comm_init_replicas.argtypes = [vp, u32, u32, vp, u64]
+        lib.etxb_group_reserve_split_lane.argtypes = [vp]
     lib.etxb_set_partition.argtypes = [vp, u32, u32]
     if hasattr(lib, "etxb_set_iteration_stride"):  # absent only from older builds loaded through the ETXB_LIB_* override
         lib.etxb_set_iteration_stride.argtypes = [vp, u32]
@@ -383,9 +384,12 @@ class GPUVCMGroup:
         self._check(self.lib.etxb_group_comm_init(self.h, world, rank, _p(comm_ids), comm_ids.nbytes // COMM_ID_BYTES))
         self.comm_rank, self.comm_world = rank, world
 
-    def comm_init_replicas(self, world, rank, comm_id):
+    def comm_init_replicas(self, world, rank, comm_id, split_lane=False):
         """Whole-frame iterations dealt to `world` processes (the job's j-th iteration on rank j % world); enqueue(n) then counts iterations of
-        the job.  Collective; comm_id = the 128 bytes rank 0 got from comm_unique_ids(1)."""
+        the job.  Collective; comm_id = the 128 bytes rank 0 got from comm_unique_ids(1).  split_lane: reserve the last lane for camera-split
+        iterations (the remainder of an enqueue that is not a multiple of `world`)."""
+        if split_lane:
+            self._check(self.lib.etxb_group_reserve_split_lane(self.h))
         comm_id = np.ascontiguousarray(comm_id, dtype=np.uint8)
         self._check(self.lib.etxb_group_comm_init_replicas(self.h, world, rank, _p(comm_id), comm_id.nbytes))
         self.comm_rank, self.comm_world = rank, world

@@ -77,6 +77,8 @@ struct LaunchParams {
   float4* camera_value;          // ETXB_BUF_CAMERA_GATHERED
   uint32_t path_count;           // N = W*H
   uint32_t rank, world;          // pixel-tile partition
+  uint32_t light_world;          // the light pass's partition: `world` (tiles over NCCL: every rank traces its own pixels' light paths) or 1 (a camera-split
+                                 //    iteration: every part traces ALL light paths itself — the same photon map everywhere, nothing to exchange)
   uint32_t camera_sample_index;  // Film sample_count of every pixel before this iteration
   uint2* conn_list;              // product build: (path id, light-vertex ordinal) of every pending vertex connection of this bounce
   uint32_t* conn_count;
@@ -138,12 +140,13 @@ DEV void queue_push(uint32_t* queue, uint32_t* queue_count, bool alive, uint32_t
   if (alive) queue[base + __popc(ballot & ((1u << lane) - 1u))] = id;
 }
 
-DEV bool pixel_owned(const LaunchParams& p, uint32_t index) {
-  if (p.world <= 1u) return true;
+DEV bool pixel_owned(const LaunchParams& p, uint32_t index, bool light_pass = false) {
+  const uint32_t world = light_pass ? p.light_world : p.world;
+  if (world <= 1u) return true;
   uint32_t x = index % p.film.width, y = index / p.film.width;
   uint32_t tiles_x = (p.film.width + 31u) / 32u;
   uint32_t tile = (y / 32u) * tiles_x + (x / 32u);
-  return (tile % p.world) == p.rank;
+  return (tile % world) == p.rank;
 }
 
 template <bool SP>
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(128) k_light_begin(const __grid_constant__ Lau
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool alive = false;
   if (i < p.path_count) {
-    bool owned = pixel_owned(p, i);
+    bool owned = pixel_owned(p, i, true);
     PathState<SP> s = generate_emitter_state<SP>(p.scene, p.vcm, i);
     p.paths.wavelength[i] = s.wavelength;
     p.paths.lv_count[i] = 0;

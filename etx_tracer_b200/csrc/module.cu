@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -163,6 +164,7 @@ struct etxb_ctx {
   uint32_t iteration_stride = 1;     // etxb_set_iteration_stride: this context renders iterations first, first + stride, ...
   uint32_t completed = 0;            // iterations finished since etxb_begin
   uint32_t rank = 0, world = 1;
+  bool light_full = false;           // camera-split iterations (etxb_group replicas): the partition applies to the camera pass only, the light pass traces every path
   uint32_t last_light_vertices = 0;
   uint32_t overflow_flag = 0;
   double last_iteration_time = 0.0, total_time = 0.0;
@@ -344,6 +346,7 @@ LaunchParams make_params(etxb_ctx* ctx) {
   p.path_count = ctx->path_count;
   p.rank = ctx->rank;
   p.world = ctx->world;
+  p.light_world = ctx->light_full ? 1u : ctx->world;
   p.camera_sample_index = ctx->completed;
   p.conn_list = ctx->conn_list.ptr;
   p.conn_count = ctx->conn_count.ptr;
@@ -1839,11 +1842,13 @@ int etxb_debug_math(etxb_ctx* ctx, uint32_t fn, const float* x, const float* y, 
 // flight that tail overlaps the full-width head of another iteration.  The film is the mean of the lanes' films weighted by the
 // iterations each lane finished — the same set of iterations, hence the same estimate, as one context running them in sequence.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t kMaxLanes = 8;
+constexpr uint32_t kMaxLanes = 9;  // 8 whole-iteration lanes + the camera-split lane of the replica mode
 struct FilmLanes {
   const float4* camera[kMaxLanes];
   const float4* light[kMaxLanes];
-  float weight[kMaxLanes];
+  float weight[kMaxLanes];        // camera layer
+  float weight_light[kMaxLanes];  // light layer (differs from `weight` only for a camera-split lane that is not part 0)
+  float weight_count[kMaxLanes];  // raw mode: what the lane adds to .w
   uint32_t lanes, layer, pixels;
   uint32_t raw;  // 1: no clamp, alpha = sum of the weights (a partial sum that another stage finishes)
 };
@@ -1854,13 +1859,13 @@ __global__ void __launch_bounds__(256) k_film_combine(FilmLanes f, float4* out) 
   for (uint32_t l = 0; l < f.lanes; ++l) {
     float4 c = (f.layer != ETXB_FILM_LIGHT) ? f.camera[l][i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     float4 g = (f.layer != ETXB_FILM_CAMERA) ? f.light[l][i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    x += f.weight[l] * (c.x + g.x);
-    y += f.weight[l] * (c.y + g.y);
-    z += f.weight[l] * (c.z + g.z);
+    x += f.weight[l] * c.x + f.weight_light[l] * g.x;
+    y += f.weight[l] * c.y + f.weight_light[l] * g.y;
+    z += f.weight[l] * c.z + f.weight_light[l] * g.z;
   }
   if (f.raw) {
     float w = 0.0f;
-    for (uint32_t l = 0; l < f.lanes; ++l) w += f.weight[l];
+    for (uint32_t l = 0; l < f.lanes; ++l) w += f.weight_count[l];
     out[i] = make_float4(x, y, z, w);
     return;
   }
@@ -1904,6 +1909,13 @@ struct etxb_group {
   // pixel-tile sharding over several processes (etxb_group_comm_init): every lane has its own communicator, and the k-th iteration of lane l is
   // the ordinal l + k * lanes on EVERY rank (the shared counter of the single-GPU mode would pair different iterations across ranks)
   bool sharded = false;
+  struct ReplicaItem {
+    uint32_t index;        // ordinal of the iteration within the job
+    uint32_t part, parts;  // parts == 1: the whole frame; else the camera pass of part `part` (tile % parts == part), light pass in full
+  };
+  std::deque<ReplicaItem> whole_queue, split_queue;
+  uint32_t split_lane = 0xffffffffu;  // replicas: the lane reserved for camera-split iterations (etxb_group_reserve_split_lane), or none
+  uint32_t split_part = 0, split_parts = 0;  // the (part, parts) that lane's film is made of; 0 parts = not used yet
   bool replicas = false;             // etxb_group_comm_init_replicas: whole-frame iterations dealt to the ranks (global index j -> rank j % world), one film reduce
   uint32_t job_enqueued = 0;         // replicas: iterations enqueued for the whole job
   uint32_t world = 1, rank = 0;
@@ -1914,9 +1926,43 @@ struct etxb_group {
   DevBuf<float4> combined_light, reduced;
 };
 
-static bool group_has_work(const etxb_group* grp, uint32_t lane) { return grp->sharded ? (grp->lane_next[lane] < grp->enqueued_total) : (grp->pending > 0); }
+// What one rank takes of `iterations` more iterations of a replica-mode job (ordinals base .. base + iterations - 1).  Whole frames are dealt
+// round-robin (ordinal j on rank j % world).  What is left when the count is not a multiple of the ranks would leave some ranks a whole iteration
+// behind the others (20 iterations on 8 ranks: 3, 3, 3, 3, 2, 2, 2, 2): with a split lane those R iterations are split instead, each over
+// P = world / R ranks by camera tile — every part traces the whole light pass itself (same photon map, no exchange) and the camera pass of its
+// tiles; the parts meet in the frame reduce.  A split lane's film is made of ONE (part, parts) geometry: a later round that would need another
+// one is dealt as whole frames.  Returns the parts of this round's split (0: none).
+static uint32_t replica_plan(uint32_t world, uint32_t rank, uint32_t base, uint32_t iterations, bool split_lane, uint32_t have_part, uint32_t have_parts,
+                             std::vector<etxb_group::ReplicaItem>& out) {
+  uint32_t whole = iterations, rest = 0, parts = 1;
+  if ((iterations >= world) && split_lane) {
+    rest = iterations % world;
+    parts = rest ? (world / rest) : 1u;
+    if ((parts >= 2u) && ((have_parts == 0u) || (have_parts == parts))) {
+      whole = iterations - rest;
+    } else {
+      rest = 0;
+    }
+  }
+  for (uint32_t j = base; j < base + whole; ++j)
+    if ((j % world) == rank) out.push_back({j, 0u, 1u});
+  for (uint32_t r = 0; r < rest; ++r) {
+    if ((rank / parts) != r) continue;
+    const uint32_t part = rank % parts;
+    if ((have_parts != 0u) && (have_part != part)) continue;  // cannot happen while `parts` stays the same: a rank's part is rank % parts
+    out.push_back({base + whole + r, part, parts});
+  }
+  return rest ? parts : 0u;
+}
+
+static bool group_has_work(const etxb_group* grp, uint32_t lane) {
+  if (grp->replicas) return (lane == grp->split_lane) ? !grp->split_queue.empty() : !grp->whole_queue.empty();
+  if (lane == grp->split_lane) return false;
+  return grp->sharded ? (grp->lane_next[lane] < grp->enqueued_total) : (grp->pending > 0);
+}
 static bool group_idle(const etxb_group* grp) {
   if (grp->in_flight > 0) return false;
+  if (grp->replicas) return grp->whole_queue.empty() && grp->split_queue.empty();
   if (!grp->sharded) return grp->pending == 0;
   for (uint32_t next : grp->lane_next)
     if (next < grp->enqueued_total) return false;
@@ -1931,7 +1977,14 @@ static void group_worker(etxb_group* grp, uint32_t lane) {
     grp->cv_work.wait(lock, [&] { return grp->quit || group_has_work(grp, lane); });
     if (grp->quit) return;
     uint32_t ordinal = 0;
-    if (grp->sharded) {
+    etxb_group::ReplicaItem item = {0u, 0u, 1u};
+    if (grp->replicas) {
+      auto& queue = (lane == grp->split_lane) ? grp->split_queue : grp->whole_queue;
+      item = queue.front();
+      queue.pop_front();
+      ordinal = item.index;
+      grp->taken = std::max(grp->taken, ordinal + 1u);
+    } else if (grp->sharded) {
       ordinal = grp->lane_next[lane];
       grp->lane_next[lane] += uint32_t(grp->lanes.size());
       grp->taken = std::max(grp->taken, ordinal + 1u);
@@ -1939,10 +1992,15 @@ static void group_worker(etxb_group* grp, uint32_t lane) {
       ordinal = grp->taken++;
       grp->pending -= 1;
     }
-    if (grp->replicas) ordinal = ordinal * grp->world + grp->rank;  // this rank's k-th iteration is the job's (k * world + rank)-th
     uint32_t iteration = grp->first_iteration + ordinal * grp->stride;
     grp->in_flight += 1;
     lock.unlock();
+    if (grp->replicas && (lane == grp->split_lane)) {
+      // this lane renders the camera pass of its part only; the light pass (and so the photon map) in full
+      ctx->rank = item.part;
+      ctx->world = item.parts;
+      ctx->light_full = true;
+    }
     int rc = etxb_set_next_iteration(ctx, iteration);
     if (rc == ETXB_OK) rc = run_iteration_blocking(ctx);  // returns when the iteration has finished (the bounce loops read queue sizes back)
     lock.lock();
@@ -1952,6 +2010,8 @@ static void group_worker(etxb_group* grp, uint32_t lane) {
       grp->error = rc;
       grp->error_text = etxb_last_error(ctx);
       grp->pending = 0;
+      grp->whole_queue.clear();
+      grp->split_queue.clear();
       for (auto& next : grp->lane_next) next = 0xffffffffu;
     }
     if (group_idle(grp)) {
@@ -2031,6 +2091,9 @@ int etxb_group_begin(etxb_group* grp, uint32_t first_iteration) {
   grp->taken = 0;
   grp->enqueued_total = 0;
   grp->job_enqueued = 0;
+  grp->whole_queue.clear();
+  grp->split_queue.clear();
+  grp->split_part = grp->split_parts = 0;
   for (uint32_t l = 0; l < grp->lane_next.size(); ++l) grp->lane_next[l] = l;
   grp->busy_seconds = 0.0;
   grp->error = ETXB_OK;
@@ -2055,11 +2118,22 @@ int etxb_group_enqueue(etxb_group* grp, uint32_t iterations) {
     if (grp->sharded) {
       grp->enqueued_total += iterations;
     } else if (grp->replicas) {
-      // `iterations` more of the JOB's iterations: this rank owns the global indices j with j % world == rank
-      uint32_t mine = 0;
-      for (uint32_t j = grp->job_enqueued; j < grp->job_enqueued + iterations; ++j) mine += ((j % grp->world) == grp->rank) ? 1u : 0u;
+      // `iterations` more of the JOB's iterations.  Whole frames are dealt round-robin (the job's j-th iteration on rank j % world).  What is left
+      // when the count is not a multiple of the ranks would leave some ranks a whole iteration behind the others (20 iterations on 8 ranks: 3, 3, 3, 3,
+      // 2, 2, 2, 2): those R iterations are split instead, each over P = world / R ranks by camera tile — every part traces the whole light pass itself
+      // (same photon map, no exchange) and the camera pass of its tiles; the parts meet in the frame reduce.
+      std::vector<etxb_group::ReplicaItem> items;
+      uint32_t parts_used = replica_plan(grp->world, grp->rank, grp->job_enqueued, iterations, grp->split_lane != 0xffffffffu, grp->split_part, grp->split_parts, items);
+      for (const auto& it : items) {
+        if (it.parts == 1u) {
+          grp->whole_queue.push_back(it);
+        } else {
+          grp->split_part = it.part;
+          grp->split_queue.push_back(it);
+        }
+      }
+      if (parts_used) grp->split_parts = parts_used;  // every rank records the split geometry, also those that got no part of this round
       grp->job_enqueued += iterations;
-      grp->pending += mine;
     } else {
       grp->pending += iterations;
     }
@@ -2072,8 +2146,10 @@ int etxb_group_poll(etxb_group* grp, etxb_status* status) {
   if (!grp || !status) return ETXB_ERR_INVALID_ARGUMENT;
   memset(status, 0, sizeof(*status));
   std::lock_guard<std::mutex> lock(grp->m);
-  for (auto* c : grp->lanes) {
-    status->completed_iterations += c->completed;
+  for (size_t l = 0; l < grp->lanes.size(); ++l) {
+    etxb_ctx* c = grp->lanes[l];
+    // a camera-split iteration is finished by several ranks: it counts where part 0 ran
+    if (!((l == grp->split_lane) && (grp->split_part != 0u))) status->completed_iterations += c->completed;
     status->light_vertices = std::max(status->light_vertices, c->last_light_vertices);
     status->overflow |= c->overflow_flag;
   }
@@ -2104,6 +2180,13 @@ static int group_combine_into(etxb_group* grp, uint32_t layer, DevBuf<float4>& t
     f.camera[l] = grp->lanes[l]->film_camera.ptr;
     f.light[l] = grp->lanes[l]->film_light.ptr;
     f.weight[l] = raw ? float(grp->lanes[l]->completed) : (total ? float(double(grp->lanes[l]->completed) / double(total)) : 0.0f);
+    f.weight_light[l] = f.weight[l];
+    f.weight_count[l] = f.weight[l];
+    if (raw && (l == grp->split_lane) && (grp->split_part != 0u)) {
+      // a camera-split lane that is not part 0: its camera tiles count, its (complete, redundant) light image and its iteration count do not
+      f.weight_light[l] = 0.0f;
+      f.weight_count[l] = 0.0f;
+    }
   }
   f.raw = raw ? 1u : 0u;
   // lanes that are still rendering keep updating their films (a preview, like reading the reference's film while it runs); after
@@ -2147,6 +2230,33 @@ int etxb_group_comm_init(etxb_group* grp, uint32_t world, uint32_t rank, const v
   grp->rank = rank;
   for (uint32_t l = 0; l < grp->lane_next.size(); ++l) grp->lane_next[l] = l;
   grp->enqueued_total = 0;
+  return ETXB_OK;
+}
+
+// Test hook (no device needed): what rank `rank` of `world` takes of an etxb_group_enqueue(iterations) in replica mode — triples (ordinal, part,
+// parts) into out; returns their number.
+int etxb_debug_replica_plan(uint32_t world, uint32_t rank, uint32_t base, uint32_t iterations, int split_lane, uint32_t* out_triples, uint32_t capacity) {
+  if ((world == 0u) || (rank >= world) || !out_triples) return ETXB_ERR_INVALID_ARGUMENT;
+  std::vector<etxb_group::ReplicaItem> items;
+  replica_plan(world, rank, base, iterations, split_lane != 0, 0u, 0u, items);
+  uint32_t n = 0;
+  for (const auto& it : items) {
+    if (n >= capacity) break;
+    out_triples[n * 3u + 0u] = it.index;
+    out_triples[n * 3u + 1u] = it.part;
+    out_triples[n * 3u + 2u] = it.parts;
+    n += 1u;
+  }
+  return int(n);
+}
+
+// Replica mode: reserves the group's LAST lane for camera-split iterations (see etxb_group_enqueue); it takes no whole-frame iterations.  Call
+// before etxb_group_comm_init_replicas; needs at least two lanes.
+int etxb_group_reserve_split_lane(etxb_group* grp) {
+  if (!grp || (grp->lanes.size() < 2u)) return ETXB_ERR_INVALID_ARGUMENT;
+  if (int rc = etxb_group_wait(grp)) return rc;
+  std::lock_guard<std::mutex> lock(grp->m);
+  grp->split_lane = uint32_t(grp->lanes.size()) - 1u;
   return ETXB_OK;
 }
 

@@ -411,6 +411,13 @@ int etxb_group_comm_init(etxb_group* group, uint32_t world, uint32_t rank, const
 /* Whole-frame iterations dealt to the ranks instead (the job's j-th iteration on rank j % world; etxb_group_enqueue then counts iterations of the
  * JOB): no collective inside an iteration, one count-weighted ncclReduce of the films per frame.  id = one ETXB_COMM_ID_BYTES id. */
 int etxb_group_comm_init_replicas(etxb_group* group, uint32_t world, uint32_t rank, const void* id, uint64_t bytes); /* collective */
+/* Optional, before etxb_group_comm_init_replicas: reserves the group's LAST lane for camera-split iterations.  When an etxb_group_enqueue(n >= world)
+ * is not a multiple of the ranks, its last n % world iterations are then split over world / (n % world) ranks each: every part traces the whole
+ * light pass itself (same photon map, no exchange) and the camera pass of its pixel tiles, and the parts meet in etxb_group_comm_reduce_film —
+ * instead of leaving some ranks one whole iteration behind the others. */
+int etxb_group_reserve_split_lane(etxb_group* group);
+/* Test hook (needs no device): the (ordinal, part, parts) triples rank `rank` of `world` takes of etxb_group_enqueue(iterations) in replica mode. */
+int etxb_debug_replica_plan(uint32_t world, uint32_t rank, uint32_t base, uint32_t iterations, int split_lane, uint32_t* out_triples, uint32_t capacity);
 int etxb_group_comm_reduce_film(etxb_group* group, uint32_t layer, float* dst_rgba, uint64_t dst_bytes);        /* collective, both modes */
 
 #ifdef __cplusplus

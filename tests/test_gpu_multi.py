@@ -36,10 +36,11 @@ def _worker(rank, world, port, out_dir, lanes, flavor):
             g.comm_init(world, rank, distribute_comm_ids(dist, rank, 1, lambda c: api.comm_unique_ids(c, flavor), device=torch.device("cuda", rank)))
             g.render(n)
         elif lanes < 0:  # whole-frame iterations dealt to the ranks, one count-weighted film reduce
-            g = api.GPUVCMGroup(sd, lanes=-lanes, flavor=flavor, device=rank)
-            g.comm_init_replicas(world, rank, distribute_comm_ids(dist, rank, 1, lambda c: api.comm_unique_ids(c, flavor), device=torch.device("cuda", rank)))
+            g = api.GPUVCMGroup(sd, lanes=-lanes + 1, flavor=flavor, device=rank)
+            g.comm_init_replicas(world, rank, distribute_comm_ids(dist, rank, 1, lambda c: api.comm_unique_ids(c, flavor), device=torch.device("cuda", rank)), split_lane=True)
             g.render(n)
-            assert g.status()["completed_iterations"] == (3 if rank == 0 else 2)  # indices 0, 2, 4 | 1, 3
+            # indices 0, 2 | 1, 3 whole; index 4 split by camera tile over both ranks (it counts where part 0 ran)
+            assert g.status()["completed_iterations"] == (3 if rank == 0 else 2)
         else:
             g = api.GPUVCMGroup(sd, lanes=lanes, flavor=flavor, device=rank)
             g.comm_init(world, rank, distribute_comm_ids(dist, rank, lanes + 1, lambda c: api.comm_unique_ids(c, flavor), device=torch.device("cuda", rank)))

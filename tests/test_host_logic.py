@@ -196,3 +196,41 @@ def test_cell_tiled_gather_visits_the_reference_candidate_multiset():
         assert sorted(tiled[qi]) == reference(qi), qi
     # the table is small enough that some query really sees a duplicate (otherwise the test would not cover that case)
     assert any(len(reference(qi)) != len(set(reference(qi))) for qi in range(len(queries)))
+
+
+def test_replica_mode_deals_every_iteration_exactly_once():
+    """etxb_group_enqueue in replica mode (module.cu replica_plan, through the device-free test hook): whole frames round-robin; with a split lane
+    the n % world left-over iterations are split over world / (n % world) ranks each by camera tile.  Whatever (world, n): every ordinal is
+    rendered exactly once — by one rank as a whole frame, or by `parts` ranks holding the parts 0 .. parts - 1 — and no rank carries more than
+    ceil(n / world) units of work."""
+    import ctypes as C
+    from etx_tracer_b200 import api
+    lib = api.load_library("fast")
+    lib.etxb_debug_replica_plan.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32]
+    buf = np.zeros(3 * 256, dtype=np.uint32)
+    for world in range(1, 9):
+        for n in range(1, 41):
+            for split in (0, 1):
+                whole, parts_seen, load = {}, {}, [0.0] * world
+                for rank in range(world):
+                    k = lib.etxb_debug_replica_plan(world, rank, 100, n, split, buf.ctypes.data_as(C.c_void_p), 256)
+                    assert k >= 0
+                    for i in range(k):
+                        j, part, parts = (int(v) for v in buf[i * 3:i * 3 + 3])
+                        assert 100 <= j < 100 + n
+                        if parts == 1:
+                            whole[j] = whole.get(j, 0) + 1
+                            load[rank] += 1.0
+                        else:
+                            assert split and n >= world and parts == world // (n % world) and parts >= 2
+                            parts_seen.setdefault(j, []).append(part)
+                            load[rank] += 1.0 / parts
+                for j in range(100, 100 + n):
+                    if j in whole:
+                        assert whole[j] == 1 and j not in parts_seen, (world, n, split, j)
+                    else:
+                        p = sorted(parts_seen[j])
+                        assert p == list(range(len(p))) and len(p) == world // (n % world), (world, n, split, j, p)
+                assert max(load) <= -(-n // world) + 1e-9
+                if split and n >= world and n % world and world // (n % world) >= 2:
+                    assert max(load) < -(-n // world)  # the point of the split: nobody a whole iteration behind
