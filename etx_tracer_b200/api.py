@@ -70,6 +70,14 @@ def load_library(flavor="fast"):
         lib.etxb_group_comm_reduce_film.argtypes = [vp, u32, vp, u64]
         lib.etxb_group_comm_init_replicas.argtypes = [vp, u32, u32, vp, u64]
         lib.etxb_group_reserve_split_lane.argtypes = [vp]
+    if hasattr(lib, "etxb_set_integrator"):
+        lib.etxb_set_integrator.argtypes = [vp, u32]
+        lib.etxb_pt_options_default.argtypes = [vp]
+        lib.etxb_pt_options_default.restype = None
+        lib.etxb_pt_options_set_key.argtypes = [vp, C.c_char_p, C.c_double]
+        lib.etxb_pt_set_options.argtypes = [vp, vp]
+        lib.etxb_pt_get_status.argtypes = [vp, vp]
+        lib.etxb_set_scene_settings.argtypes = [vp, C.c_float, C.c_float]
     lib.etxb_set_partition.argtypes = [vp, u32, u32]
     if hasattr(lib, "etxb_set_iteration_stride"):  # absent only from older builds loaded through the ETXB_LIB_* override
         lib.etxb_set_iteration_stride.argtypes = [vp, u32]
@@ -329,6 +337,58 @@ class GPUVCM:
         yy = np.ascontiguousarray(y, dtype=np.float32) if y is not None else None
         self._check(self.lib.etxb_debug_math(self.h, fn, _p(x), _p(yy) if yy is not None else None, x.shape[0], _p(out)))
         return out
+
+
+class GPUPathTracing(GPUVCM):
+    """`name()/run()/update()/stop()/status()/options` like the reference's CPUPathTracing (rt/integrators/path_tracing.cxx:122-170) on the same CUDA
+    context type: one path per active pixel and iteration, normal / albedo layers, adaptive sampling (Film::estimate_noise_levels)."""
+
+    def __init__(self, scene_data=None, flavor="fast", device=0, profile=False):
+        super().__init__(scene_data, flavor=flavor, device=device, profile=profile)
+        self.pt_options = S.default_pt_options()
+        self._check(self.lib.etxb_set_integrator(self.h, S.INTEGRATOR_PT))
+
+    @staticmethod
+    def name():
+        return "Path Tracing (B200)"
+
+    def set_option(self, key, value):
+        """The reference's option ids: "direct", "nee", "mis", "bn" (path_tracing.cxx:36-39)."""
+        rc = self.lib.etxb_pt_options_set_key(_p(self.pt_options), key.encode(), float(value))
+        if rc != 0:
+            raise EtxbError(rc, f"unknown option key {key}")
+
+    def set_scene_settings(self, noise_threshold, radiance_clamp=0.0):
+        """Scene::noise_threshold / radiance_clamp without a new upload."""
+        self._check(self.lib.etxb_set_scene_settings(self.h, C.c_float(noise_threshold), C.c_float(radiance_clamp)))
+
+    def run(self, first_iteration=0):
+        """CPUPathTracing::run -> CPUPathTracingImpl::start (path_tracing.cxx:35-48): options, film.clear(ClearCameraData), first task."""
+        self._check(self.lib.etxb_pt_set_options(self.h, _p(self.pt_options)))
+        self._check(self.lib.etxb_begin(self.h, first_iteration))
+        self._running = True
+        self._target_iterations = int(self.scene_data.scene["samples"][0])
+
+    def update(self):
+        """CPUPathTracingImpl::update (path_tracing.cxx:85-110), non-blocking: an iteration that processed no pixel (all converged) ends the run."""
+        if not self._running:
+            return False
+        st = self.status()
+        if st["iteration_in_flight"]:
+            return True
+        if st["completed_iterations"] and (self.pt_status()["pixels_processed"] == 0):
+            self._running = False
+            return False
+        if st["completed_iterations"] >= self._target_iterations:
+            self._running = False
+            return False
+        self._check(self.lib.etxb_enqueue_iteration(self.h))
+        return True
+
+    def pt_status(self):
+        st = np.zeros(1, dtype=S.PT_STATUS)
+        self._check(self.lib.etxb_pt_get_status(self.h, _p(st)))
+        return {k: st[k][0].item() for k in st.dtype.names}
 
 
 class GPUVCMGroup:

@@ -24,6 +24,7 @@
 
 #include "bvh_build.h"
 #include "kernels.cuh"
+#include "kernels_pt.cuh"
 
 using namespace etxb;
 
@@ -58,10 +59,15 @@ enum KernelId : uint32_t {
   K_FILM_COMMIT,
   K_COMM_LIGHT_IMAGE,
   K_COMM_PHOTONS,
+  K_PT_BEGIN,
+  K_PT_SHADE,
+  K_PT_ACCUMULATE,
+  K_FILM_NOISE,
   K_COUNT
 };
 const char* kKernelNames[K_COUNT] = {"light_begin", "trace_closest(light)", "light_bounce", "lv_scan", "lv_reorder", "grid_bbox", "grid_keys", "grid_sort", "grid_build",
-  "camera_begin", "trace_closest(camera)", "camera_shade", "camera_connect", "shadow_trace", "queue_sort", "camera_merge_sort", "camera_merge", "camera_merge_generic", "camera_continue", "film_commit_light", "nccl_allreduce_light_image", "nccl_allgather_photons"};
+  "camera_begin", "trace_closest(camera)", "camera_shade", "camera_connect", "shadow_trace", "queue_sort", "camera_merge_sort", "camera_merge", "camera_merge_generic", "camera_continue", "film_commit_light", "nccl_allreduce_light_image", "nccl_allgather_photons",
+  "pt_begin", "pt_shade", "pt_accumulate", "film_noise_levels"};
 
 template <class T>
 struct DevBuf {
@@ -158,6 +164,18 @@ struct etxb_ctx {
   DevBuf<DeviceCounters> counters;
   // film
   DevBuf<float4> film_camera, film_light, film_light_iteration, film_out;
+
+  // unidirectional path tracer: the same context renders with CPUPathTracing's algorithm once etxb_set_integrator selects it
+  uint32_t integrator = ETXB_INTEGRATOR_VCM;
+  etxb_pt_options pt_options = {1u, 1u, 1u, 1u};
+  DevBuf<float4> film_normals, film_albedo, film_adaptive;  // Film's Normals / Albedo / CameraAdaptive layers (allocated with the first PT run)
+  DevBuf<uint32_t> pt_info, pt_info_next, pt_stats;          // InternalData (sample count, converged, tmp); [converged this pass, error sum bits]
+  DevBuf<float> pt_error;
+  uint32_t pixel_sampler_image = 0xffffffffu;
+  float pixel_sampler_radius = 1.0f, noise_threshold = 0.0f, radiance_clamp = 0.0f;
+  uint32_t scene_samples = 0;
+  uint32_t pt_pixels_processed = 0, pt_active_pixels = 0;  // active pixels of the last iteration; Film::active_pixel_count
+  float pt_noise_level = 0.0f;                             // Film::noise_level
 
   etxb_vcm_options options = {};
   uint32_t iteration = 0;            // absolute iteration index (VCMIteration::iteration)
@@ -822,6 +840,122 @@ int finish_iteration(etxb_ctx* ctx) {
   return ETXB_OK;
 }
 
+// ---- unidirectional path tracer -----------------------------------------------------------------------------------------
+// The film layers and the per-pixel history only CPUPathTracing touches (film.cxx:14-40, 104-121), allocated with the first run.
+int pt_ensure_film(etxb_ctx* ctx) {
+  const size_t n = ctx->path_count;
+  if (ctx->film_normals.count == n) return ETXB_OK;
+  DevBuf<float4>* f4[] = {&ctx->film_normals, &ctx->film_albedo, &ctx->film_adaptive};
+  for (auto* b : f4) {
+    CUDA_OK(ctx, b->alloc(n));
+    CUDA_OK(ctx, cudaMemsetAsync(b->ptr, 0, n * 16, ctx->stream));
+  }
+  CUDA_OK(ctx, ctx->pt_info.alloc(n));
+  CUDA_OK(ctx, ctx->pt_info_next.alloc(n));
+  CUDA_OK(ctx, ctx->pt_error.alloc(n));
+  CUDA_OK(ctx, ctx->pt_stats.alloc(2));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->pt_info.ptr, 0, n * 4, ctx->stream));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->pt_error.ptr, 0, n * 4, ctx->stream));
+  return ETXB_OK;
+}
+
+PtFilm make_pt_film(etxb_ctx* ctx) { return {ctx->film_normals.ptr, ctx->film_albedo.ptr, ctx->film_adaptive.ptr, ctx->pt_info.ptr, ctx->pt_error.ptr, ctx->pt_info_next.ptr}; }
+
+// Film::estimate_noise_levels (film.cxx:233-330) after iteration `sample_index`
+constexpr uint32_t kFilmMinSamples = 32u;
+int pt_estimate_noise_levels(etxb_ctx* ctx, uint32_t sample_index) {
+  const float threshold = ctx->noise_threshold;
+  if ((threshold == 0.0f) || (sample_index < kFilmMinSamples) || ((sample_index % 2u) != 0u)) return ETXB_OK;
+  LaunchTimer t(ctx, K_FILM_NOISE);
+  const uint32_t n = ctx->path_count;
+  FilmBuffers film = {ctx->film_camera.ptr, ctx->film_light.ptr, ctx->film_light_iteration.ptr, ctx->width, ctx->height};
+  PtFilm pf = make_pt_film(ctx);
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->pt_stats.ptr, 0, 8, ctx->stream));
+  k_film_noise_level<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(film, pf, threshold, ctx->pt_stats.ptr);
+  k_film_noise_rows<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(film, ctx->pt_info.ptr, ctx->pt_info_next.ptr);
+  k_film_noise_columns<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(film, ctx->pt_info_next.ptr, ctx->pt_info.ptr);
+  ctx->kernel_launches += 2;
+  uint32_t stats[2] = {0u, 0u};
+  CUDA_OK(ctx, cudaMemcpyAsync(stats, ctx->pt_stats.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  float total = 0.0f;
+  memcpy(&total, &stats[1], 4);
+  ctx->pt_active_pixels = stats[0];
+  ctx->pt_noise_level = (stats[0] > 0u) ? (total / float(stats[0])) : total;
+  return ETXB_OK;
+}
+
+// One CPUPathTracingImpl task (path_tracing.cxx:50-83) followed by update()'s bookkeeping (:85-110): every active pixel's path, the film update,
+// the noise estimate.
+template <bool SP>
+int run_pt_iteration(etxb_ctx* ctx) {
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev_iter_start, ctx->stream));
+  if (int rc = pt_ensure_film(ctx)) return rc;
+  LaunchParams p = make_params(ctx);
+  p.connect_stage = 0;
+  p.shadow_stage = 0;  // the slot-ordered deferred shadow rays belong to the VCM camera step; the path tracer uses the atomic list or traces inline
+  PtParams pt = {};
+  pt.nee = ctx->pt_options.nee;
+  pt.direct = ctx->pt_options.direct;
+  pt.mis = ctx->pt_options.mis;
+  pt.blue_noise = (ctx->pt_options.blue_noise != 0u) && ctx->dscene.has_blue_noise;
+  pt.iteration = ctx->iteration;
+  pt.pixel_sampler_image = ctx->pixel_sampler_image;
+  pt.pixel_sampler_radius = ctx->pixel_sampler_radius;
+  pt.radiance_clamp = ctx->radiance_clamp;
+  PtFilm pf = make_pt_film(ctx);
+  const bool plain = ctx->plain_scene && ctx->plain_kernels;
+  if (!plain) p.shadow_atomic = 0;
+  uint32_t* counts = ctx->queue_counts.ptr;
+  CUDA_OK(ctx, cudaMemsetAsync(counts, 0, 8, ctx->stream));
+  uint32_t* qin = ctx->queue_a.ptr;
+  uint32_t* qout = ctx->queue_b.ptr;
+  {
+    LaunchTimer t(ctx, K_PT_BEGIN);
+    k_pt_begin<SP><<<blocks_for(ctx->path_count, 128), 128, 0, ctx->stream>>>(p, pt, pf, qin, counts + 0);
+  }
+  uint32_t active = 0;
+  if (int rc = read_u32(ctx, counts + 0, active)) return rc;
+  ctx->pt_pixels_processed = active;
+  uint32_t cur = 0, unsynced = 0;
+  while (active > 0) {
+    const bool sorted = sorts_queue(ctx, active);
+    const uint32_t* q = qin;
+    {
+      LaunchTimer t(ctx, K_TRACE_CAMERA);
+      if (int rc = launch_trace_closest(ctx, p, qin, counts + cur, sorted ? ctx->queue_keys.ptr : nullptr, active)) return rc;
+    }
+    if (sorted) {
+      LaunchTimer t(ctx, K_QUEUE_SORT);
+      if (int rc = sort_queue_by_material(ctx, qin, active, &q)) return rc;
+    }
+    CUDA_OK(ctx, cudaMemsetAsync(counts + (cur ^ 1u), 0, 4, ctx->stream));
+    if (p.shadow_atomic) CUDA_OK(ctx, cudaMemsetAsync(ctx->shadow_count.ptr, 0, 8, ctx->stream));
+    {
+      LaunchTimer t(ctx, K_PT_SHADE);
+      if (plain) {
+        k_pt_shade<SP, true><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, pt, q, counts + cur, qout, counts + (cur ^ 1u));
+      } else {
+        k_pt_shade<SP, false><<<blocks_for(active, 128), 128, 0, ctx->stream>>>(p, pt, q, counts + cur, qout, counts + (cur ^ 1u));
+      }
+    }
+    if (p.shadow_atomic) {
+      LaunchTimer t(ctx, K_SHADOW_TRACE);
+      if (int rc = launch_shadow_resolve(ctx, p, active)) return rc;
+    }
+    cur ^= 1u;
+    std::swap(qin, qout);
+    if (int rc = next_queue_size(ctx, counts + cur, active, unsynced)) return rc;
+  }
+  {
+    LaunchTimer t(ctx, K_PT_ACCUMULATE);
+    k_pt_accumulate<SP><<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(p, pt, pf);
+  }
+  if (int rc = pt_estimate_noise_levels(ctx, ctx->iteration)) return rc;
+  CUDA_OK(ctx, cudaGetLastError());
+  return finish_iteration(ctx);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -939,6 +1073,13 @@ void etxb_destroy(etxb_ctx* ctx) {
   ctx->bs_props.release();
   ctx->bs_weight_pdf.release();
   ctx->bs_wo_eta.release();
+  ctx->film_normals.release();
+  ctx->film_albedo.release();
+  ctx->film_adaptive.release();
+  ctx->pt_info.release();
+  ctx->pt_info_next.release();
+  ctx->pt_stats.release();
+  ctx->pt_error.release();
   ctx->cub_temp.release();
   ctx->counters.release();
   cudaStreamDestroy(ctx->stream);
@@ -1254,6 +1395,13 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
   d.default_conductor_k = s.default_conductor_k;
   d.camera = cam;
   ctx->spectral = d.spectral != 0;
+  if ((s.pixel_sampler_image != 0xffffffffu) && (s.pixel_sampler_image >= s.images.count)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "pixel sampler image out of range");
+  ctx->pixel_sampler_image = s.pixel_sampler_image;
+  ctx->pixel_sampler_radius = s.pixel_sampler_radius;
+  ctx->noise_threshold = s.noise_threshold;
+  ctx->radiance_clamp = s.radiance_clamp;
+  ctx->scene_samples = s.samples;
+  ctx->film_normals.release();  // sized by the film: re-allocated by the next path-tracer run
 
   // ---- film + queues (Film::allocate, film.cxx) ----------------------------------------------------------------------
   ctx->width = cam.film_size[0];
@@ -1401,6 +1549,16 @@ int etxb_begin(etxb_ctx* ctx, uint32_t first_iteration) {
   CUDA_OK(ctx, cudaMemsetAsync(ctx->film_light_iteration.ptr, 0, n * 16, ctx->stream));
   CUDA_OK(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(DeviceCounters), ctx->stream));
   CUDA_OK(ctx, cudaMemsetAsync(ctx->overflow.ptr, 0, 4, ctx->stream));
+  if (ctx->pt_info.count == n) {
+    // Film::clear(ClearCameraData) (film.cxx:345-368): the per-pixel history starts over
+    CUDA_OK(ctx, cudaMemsetAsync(ctx->pt_info.ptr, 0, n * 4, ctx->stream));
+    CUDA_OK(ctx, cudaMemsetAsync(ctx->pt_error.ptr, 0, n * 4, ctx->stream));
+    DevBuf<float4>* layers[] = {&ctx->film_normals, &ctx->film_albedo, &ctx->film_adaptive};
+    for (auto* b : layers) CUDA_OK(ctx, cudaMemsetAsync(b->ptr, 0, n * 16, ctx->stream));
+  }
+  ctx->pt_pixels_processed = 0;
+  ctx->pt_active_pixels = ctx->path_count;
+  ctx->pt_noise_level = 0.0f;
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->iteration = first_iteration;
   ctx->completed = 0;
@@ -1448,6 +1606,10 @@ int etxb_enqueue_camera_pass(etxb_ctx* ctx) {
 
 // one whole iteration on the calling thread; returns when it has finished (the bounce loops read queue sizes back)
 static int run_iteration_blocking(etxb_ctx* ctx) {
+  if (ctx->integrator == ETXB_INTEGRATOR_PT) {
+    cudaSetDevice(ctx->device);
+    return ctx->spectral ? run_pt_iteration<true>(ctx) : run_pt_iteration<false>(ctx);
+  }
   if (int rc = etxb_enqueue_light_pass(ctx)) return rc;
   const void* records = nullptr;
   uint64_t count = 0;
@@ -1503,6 +1665,59 @@ int etxb_enqueue_iteration(etxb_ctx* ctx) {
   if (!ctx->worker.joinable()) ctx->worker = std::thread(ctx_worker, ctx);
   ctx->worker_queued += 1;
   ctx->worker_cv.notify_one();
+  return ETXB_OK;
+}
+
+
+// ---- unidirectional path tracer (CPUPathTracing, rt/integrators/path_tracing.cxx) ---------------------------------------------------------
+void etxb_pt_options_default(etxb_pt_options* opt) {
+  if (!opt) return;
+  opt->nee = opt->direct = opt->mis = opt->blue_noise = 1u;  // PTOptions (path_tracing_shared.hxx:8-14)
+}
+
+// the reference's option ids (path_tracing.cxx:36-39, 112-119)
+int etxb_pt_options_set_key(etxb_pt_options* opt, const char* key, double value) {
+  if (!opt || !key) return ETXB_ERR_INVALID_ARGUMENT;
+  const uint32_t v = (value != 0.0) ? 1u : 0u;
+  if (!strcmp(key, "direct")) opt->direct = v;
+  else if (!strcmp(key, "nee")) opt->nee = v;
+  else if (!strcmp(key, "mis")) opt->mis = v;
+  else if (!strcmp(key, "bn")) opt->blue_noise = v;
+  else return ETXB_ERR_INVALID_ARGUMENT;
+  return ETXB_OK;
+}
+
+int etxb_pt_set_options(etxb_ctx* ctx, const etxb_pt_options* opt) {
+  if (!ctx || !opt) return ETXB_ERR_INVALID_ARGUMENT;
+  if (int rc = ctx_drain_impl(ctx)) return rc;
+  ctx->pt_options = *opt;
+  return ETXB_OK;
+}
+
+int etxb_set_integrator(etxb_ctx* ctx, uint32_t integrator) {
+  if (!ctx || (integrator > ETXB_INTEGRATOR_PT)) return ETXB_ERR_INVALID_ARGUMENT;
+  if (int rc = ctx_drain_impl(ctx)) return rc;
+  if ((integrator == ETXB_INTEGRATOR_PT) && (ctx->world > 1u)) return fail(ctx, ETXB_ERR_UNSUPPORTED, "the path tracer runs on one GPU per context");
+  ctx->integrator = integrator;
+  return ETXB_OK;
+}
+
+int etxb_pt_get_status(etxb_ctx* ctx, etxb_pt_status* out) {
+  if (!ctx || !out) return ETXB_ERR_INVALID_ARGUMENT;
+  memset(out, 0, sizeof(*out));
+  out->pixels_processed = ctx->pt_pixels_processed;
+  out->active_pixels = ctx->pt_active_pixels;
+  out->noise_level = ctx->pt_noise_level;
+  out->max_sample_count = ctx->scene_samples;
+  return ETXB_OK;
+}
+
+// Scene::noise_threshold / radiance_clamp / samples are scene settings the application edits between runs (ui.cxx) without a new upload
+int etxb_set_scene_settings(etxb_ctx* ctx, float noise_threshold, float radiance_clamp) {
+  if (!ctx || !(noise_threshold >= 0.0f) || !(radiance_clamp >= 0.0f)) return ETXB_ERR_INVALID_ARGUMENT;
+  if (int rc = ctx_drain_impl(ctx)) return rc;
+  ctx->noise_threshold = noise_threshold;
+  ctx->radiance_clamp = radiance_clamp;
   return ETXB_OK;
 }
 
@@ -1641,6 +1856,19 @@ int etxb_read_film(etxb_ctx* ctx, uint32_t layer, float* dst_rgba, uint64_t dst_
     case ETXB_FILM_LIGHT_ITERATION:
       src = ctx->film_light_iteration.ptr;
       break;
+    case ETXB_FILM_NORMALS:
+    case ETXB_FILM_ALBEDO:
+    case ETXB_FILM_CAMERA_ADAPTIVE: {
+      if (int rc = pt_ensure_film(ctx)) return rc;
+      if (layer == ETXB_FILM_NORMALS) {
+        k_film_layer_normals<<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(ctx->film_normals.ptr, ctx->film_out.ptr, ctx->path_count);
+        ctx->kernel_launches += 1;
+        src = ctx->film_out.ptr;
+      } else {
+        src = (layer == ETXB_FILM_ALBEDO) ? ctx->film_albedo.ptr : ctx->film_adaptive.ptr;
+      }
+      break;
+    }
     default:
       return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "unknown film layer %u", layer);
   }
@@ -1698,6 +1926,12 @@ int etxb_device_pointer(etxb_ctx* ctx, uint32_t buffer_id, void** out_ptr, uint6
     case ETXB_BUF_FILM_LIGHT: *out_ptr = ctx->film_light.ptr; *out_bytes = n * 16; break;
     case ETXB_BUF_PHOTON_RECORDS: *out_ptr = ctx->lv_final.ptr; *out_bytes = size_t(ctx->last_light_vertices) * sizeof(LightVertexRec); break;
     case ETXB_BUF_CAMERA_GATHERED: *out_ptr = ctx->camera_value.ptr; *out_bytes = n * 16; break;
+    case ETXB_BUF_PIXEL_INFO:
+      if (ctx->pt_info.count != n) return fail(ctx, ETXB_ERR_NOT_READY, "the path tracer has not run on this film");
+      *out_ptr = ctx->pt_info.ptr; *out_bytes = n * 4; break;
+    case ETXB_BUF_PIXEL_ERROR:
+      if (ctx->pt_error.count != n) return fail(ctx, ETXB_ERR_NOT_READY, "the path tracer has not run on this film");
+      *out_ptr = ctx->pt_error.ptr; *out_bytes = n * 4; break;
     default: return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "buffer %u has no direct device pointer", buffer_id);
   }
   return ETXB_OK;

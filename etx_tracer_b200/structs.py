@@ -125,10 +125,21 @@ VCM_CONNECT_ONLY = VCM_DIRECT_HIT | VCM_CONNECT_TO_LIGHT | VCM_CONNECT_TO_CAMERA
 VCM_FULL = VCM_CONNECT_ONLY | VCM_ENABLE_MERGING | VCM_MERGE_VERTICES
 
 # film layers / buffer ids (include/etx_b200.h)
-FILM_RESULT, FILM_CAMERA, FILM_LIGHT, FILM_LIGHT_ITERATION = range(4)
+FILM_RESULT, FILM_CAMERA, FILM_LIGHT, FILM_LIGHT_ITERATION, FILM_NORMALS, FILM_ALBEDO, FILM_CAMERA_ADAPTIVE = range(7)
 (BUF_LIGHT_PATH_COUNT, BUF_LIGHT_PATH_OFFSET, BUF_LIGHT_PATH_WAVELENGTH, BUF_LIGHT_SAMPLER, BUF_CAMERA_SAMPLER, BUF_LV_POS,
  BUF_LV_THROUGHPUT, BUF_LV_MIS, BUF_FILM_LIGHT_ITERATION, BUF_FILM_CAMERA, BUF_FILM_LIGHT, BUF_PHOTON_RECORDS,
- BUF_CAMERA_GATHERED) = range(13)
+ BUF_CAMERA_GATHERED, BUF_PIXEL_INFO, BUF_PIXEL_ERROR) = range(15)
+INTEGRATOR_VCM, INTEGRATOR_PT = 0, 1
+PIXEL_COUNT_MASK, PIXEL_CONVERGED, PIXEL_TMP = (1 << 30) - 1, 1 << 30, 1 << 31
+PT_OPTIONS = np.dtype([("nee", np.uint32), ("direct", np.uint32), ("mis", np.uint32), ("blue_noise", np.uint32)])
+PT_STATUS = np.dtype([("pixels_processed", np.uint32), ("active_pixels", np.uint32), ("noise_level", np.float32), ("max_sample_count", np.uint32)])
+
+
+def default_pt_options():
+    """PTOptions (path_tracing_shared.hxx:8-14): everything on."""
+    o = np.zeros(1, dtype=PT_OPTIONS)
+    o["nee"] = o["direct"] = o["mis"] = o["blue_noise"] = 1
+    return o
 
 
 def default_vcm_options():

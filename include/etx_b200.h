@@ -264,7 +264,11 @@ enum {
   ETXB_FILM_RESULT = 0,      /* max(0, camera + light) as float4 */
   ETXB_FILM_CAMERA = 1,      /* camera image (running mean over iterations) */
   ETXB_FILM_LIGHT = 2,       /* light image (running mean over iterations) */
-  ETXB_FILM_LIGHT_ITERATION = 3
+  ETXB_FILM_LIGHT_ITERATION = 3,
+  /* layers the path tracer fills (Film::Normals shown as n * 0.5 + 0.5, Film::Albedo, Film::CameraAdaptive; film.cxx:406-414) */
+  ETXB_FILM_NORMALS = 4,
+  ETXB_FILM_ALBEDO = 5,
+  ETXB_FILM_CAMERA_ADAPTIVE = 6
 };
 
 /* Named device buffers for etxb_read_buffer / etxb_device_pointer (parity tests + multi-GPU exchange). */
@@ -282,6 +286,8 @@ enum {
   ETXB_BUF_FILM_LIGHT = 10,        /* float4[N] */
   ETXB_BUF_PHOTON_RECORDS = 11,    /* packed photon records of this rank (all-gathered across ranks) */
   ETXB_BUF_CAMERA_GATHERED = 12,   /* float[3*N] last iteration's camera contribution per path */
+  ETXB_BUF_PIXEL_INFO = 13,        /* uint32[N]  Film's InternalData in film storage order (film.cxx:27-32): sample_count bits 0-29, converged bit 30, tmp bit 31 */
+  ETXB_BUF_PIXEL_ERROR = 14,       /* float[N]   InternalData::error_level */
   ETXB_BUF_COUNT
 };
 
@@ -330,6 +336,33 @@ int etxb_set_next_iteration(etxb_ctx* ctx, uint32_t iteration);
 
 /* CPUVCMImpl::start (vcm_cpu.cxx:81-93): clears film, sets iteration = first_iteration. */
 int etxb_begin(etxb_ctx* ctx, uint32_t first_iteration);
+
+/* ---- the unidirectional path tracer on the same context -----------------------------------------
+ * Replaces CPUPathTracing (rt/integrators/path_tracing.cxx:12-170) + run_path_iteration (rt/shared/path_tracing_shared.hxx:485-510)
+ * + Film::accumulate_camera_image with the normal / albedo layers and Film::estimate_noise_levels (render/host/film.cxx:173-330).
+ * etxb_set_integrator selects which algorithm etxb_begin / etxb_enqueue_iteration / etxb_poll / etxb_read_film drive: with
+ * ETXB_INTEGRATOR_PT one iteration = one path per active pixel (CPUPathTracingImpl::execute_range) followed by update()'s
+ * film.estimate_noise_levels(current_iteration, samples, noise_threshold); a pixel the estimate marks converged is skipped from
+ * then on (Film::active_pixel).  Progressive preview (pixel_size > 1, film.cxx:440-449) is not part of it: its pixel choice is rand(). */
+#define ETXB_INTEGRATOR_VCM 0u
+#define ETXB_INTEGRATOR_PT 1u
+/* PTOptions (path_tracing_shared.hxx:8-14); the reference's option ids are "nee", "direct", "mis", "bn" (path_tracing.cxx:36-39) */
+typedef struct etxb_pt_options {
+  uint32_t nee, direct, mis, blue_noise; /* all default 1 */
+} etxb_pt_options;
+typedef struct etxb_pt_status {
+  uint32_t pixels_processed; /* CPUPathTracingImpl::pixels_processed of the last finished iteration; 0 => the reference stops the run (:90-92) */
+  uint32_t active_pixels;    /* Film::active_pixel_count (film.cxx:430): pixel count after a clear, pixels converged in the last estimate after one */
+  float noise_level;         /* Film::noise_level (film.cxx:461) */
+  uint32_t max_sample_count; /* Scene::samples */
+} etxb_pt_status;
+void etxb_pt_options_default(etxb_pt_options* opt);
+int etxb_pt_options_set_key(etxb_pt_options* opt, const char* key, double value);
+int etxb_pt_set_options(etxb_ctx* ctx, const etxb_pt_options* opt);
+int etxb_set_integrator(etxb_ctx* ctx, uint32_t integrator);
+int etxb_pt_get_status(etxb_ctx* ctx, etxb_pt_status* out);
+/* Scene::noise_threshold / Scene::radiance_clamp (scene.hxx:45-46) changed without a new upload */
+int etxb_set_scene_settings(etxb_ctx* ctx, float noise_threshold, float radiance_clamp);
 
 /* One VCM iteration = start_next_iteration + gather_light_vertices + complete_light_vertices +
  * gather_camera_vertices + complete_camera_vertices (vcm_cpu.cxx:95-241).  Asynchronous: returns after

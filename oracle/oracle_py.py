@@ -35,6 +35,11 @@ def load(flavor="parity"):
     lib.oracle_run_iterations.restype = C.c_double
     lib.oracle_run_iterations.argtypes = [vp, u32, u32]
     lib.oracle_read_film.argtypes = [vp, u32, vp, u64]
+    if hasattr(lib, "oracle_set_integrator"):
+        lib.oracle_set_integrator.argtypes = [vp, u32]
+        lib.oracle_pt_set_options.argtypes = [vp, vp]
+        lib.oracle_pt_get_status.argtypes = [vp, vp]
+        lib.oracle_set_scene_settings.argtypes = [vp, f32, f32]
     lib.oracle_read_buffer.argtypes = [vp, u32, vp, u64, C.POINTER(u64)]
     lib.oracle_get_counters.argtypes = [vp, vp]
     lib.oracle_trace.argtypes = [vp, vp, vp, u32, vp, vp]
@@ -172,6 +177,21 @@ class Oracle:
 
     def set_options(self, opts):
         self.lib.oracle_set_options(self.h, _p(opts))
+
+    def set_integrator(self, integrator):
+        """0 = VCM (default), 1 = the reference's path tracer (run_path_iteration compiled in place + the restated CPUPathTracing driver)."""
+        self.lib.oracle_set_integrator(self.h, integrator)
+
+    def pt_set_options(self, opts):
+        self.lib.oracle_pt_set_options(self.h, _p(opts))
+
+    def pt_status(self):
+        st = np.zeros(1, dtype=self.S.PT_STATUS)
+        self.lib.oracle_pt_get_status(self.h, _p(st))
+        return {k: st[k][0].item() for k in st.dtype.names}
+
+    def set_scene_settings(self, noise_threshold, radiance_clamp=0.0):
+        self.lib.oracle_set_scene_settings(self.h, C.c_float(noise_threshold), C.c_float(radiance_clamp))
 
     def begin(self, first_iteration=0):
         self.lib.oracle_begin(self.h, first_iteration)

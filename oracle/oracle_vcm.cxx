@@ -12,7 +12,10 @@
 //   * VCMSpatialGrid::construct (sources/etx/rt/integrators/vcm_shared.cxx:49-152)  -> build_grid(), with the
 //     reference's `total = _cell_ends.back()` under-allocation fixed (sized by the full sum);
 //   * the Film subset the VCM integrator touches (sources/etx/render/host/film.cxx:147-230,332-343,381-418);
-//   * sample_blue_noise (sources/etx/rt/integrators/path_tracing.cxx:173-178).
+//   * sample_blue_noise (sources/etx/rt/integrators/path_tracing.cxx:173-178);
+//   * for the path tracer (run_path_iteration itself is the reference's rt/shared/path_tracing_shared.hxx, compiled in place):
+//     the CPUPathTracing driver (rt/integrators/path_tracing.cxx:50-110)            -> run_pt_iteration(), Film::sample (film.cxx:137-145),
+//     Film::accumulate_camera_image with the normal / albedo / adaptive layers (:173-230) and Film::estimate_noise_levels (:233-330).
 // Parity status: the reference ships no tests or golden vectors for this path; the pins are the
 // known-answer vectors in tests/golden/ generated from these compiled headers.
 #include <etx/core/core.hxx>
@@ -280,6 +283,31 @@ float2 sample_blue_noise(const uint2& pixel, const uint32_t total_samples, const
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Film: the one member make_ray_payload calls (path_tracing_shared.hxx:245).  film.cxx itself cannot be compiled here (denoiser, task scheduler):
+// the three members below restate film.cxx:104-121 (the dimensions only) and :137-145.
+// ---------------------------------------------------------------------------------------------------
+struct FilmImpl {
+  uint2 dimensions = {};
+};
+Film::Film(TaskScheduler&) {
+  _private = new (_private_storage) FilmImpl();
+}
+Film::~Film() {
+}
+void Film::allocate(const uint2& dim) {
+  _private->dimensions = dim;
+}
+float2 Film::sample(const Scene& scene, const PixelFilter& sampler, const uint2& pixel, const float2& rnd) const {
+  float2 jitter = rnd * 2.0f - 1.0f;
+  if (sampler.image_index != kInvalidIndex) {
+    jitter = scene.images[sampler.image_index].sample(rnd) * 2.0f - 1.0f;
+  }
+  float u = (float(pixel.x) + 0.5f + sampler.radius * jitter.x) / float(_private->dimensions.x) * 2.0f - 1.0f;
+  float v = (float(pixel.y) + 0.5f + sampler.radius * jitter.y) / float(_private->dimensions.y) * 2.0f - 1.0f;
+  return {u, v};
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Driver state
 // ---------------------------------------------------------------------------------------------------
 struct Oracle {
@@ -308,6 +336,17 @@ struct Oracle {
   std::vector<uint32_t> film_samples;
   std::vector<float4> film_out;
 
+  // path tracer: which integrator run_iterations drives, its options, the film members it alone touches (film.cxx:14-40)
+  uint32_t integrator = ETXB_INTEGRATOR_VCM;
+  PTOptions pt_options = {};
+  uint64_t film_storage[(sizeof(Film) + 7) / 8] = {};
+  Film* film = nullptr;
+  std::vector<float3> film_normals, film_albedo, film_adaptive;
+  std::vector<uint8_t> film_converged, film_tmp;
+  std::vector<float> film_error;
+  float noise_level = 0.0f;
+  uint32_t active_pixels = 0, pixels_processed = 0;
+
   // debug taps
   std::vector<uint32_t> light_sampler_end, camera_sampler_end;
   std::vector<float3> camera_value;
@@ -331,6 +370,15 @@ void film_clear(Oracle& o) {
   o.film_light_iteration.assign(n, float3{});
   o.film_samples.assign(n, 0u);
   o.film_out.assign(n, float4{});
+  o.film_normals.assign(n, float3{});
+  o.film_albedo.assign(n, float3{});
+  o.film_adaptive.assign(n, float3{});
+  o.film_converged.assign(n, 0u);
+  o.film_tmp.assign(n, 0u);
+  o.film_error.assign(n, 0.0f);
+  o.noise_level = 0.0f;
+  o.active_pixels = n;
+  o.pixels_processed = 0;
 }
 
 inline void atomic_add_f(float* ptr, float value) {
@@ -612,6 +660,134 @@ void run_iteration(Oracle& o, uint32_t threads) {
   it.iteration += 1;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Path tracer
+// ---------------------------------------------------------------------------------------------------
+// film.cxx:173-230 with pixel_size == 1: colour, normal, albedo running means; the every-other-sample mean; the sample counter
+void film_accumulate_pt(Oracle& o, const uint2& pixel, const float3& color, const float3& normal, const float3& albedo) {
+  if ((pixel.x >= o.width) || (pixel.y >= o.height))
+    return;
+  uint32_t i = pixel.x + (o.height - 1u - pixel.y) * o.width;
+  uint32_t sample_index = o.film_samples[i];
+  double ds = double(sample_index);
+  if (sample_index == 0) {
+    o.film_camera[i] = color;
+    o.film_normals[i] = normal;
+    o.film_albedo[i] = albedo;
+    o.film_adaptive[i] = color;
+  } else {
+    float t = float(ds / (ds + 1.0));
+    o.film_camera[i] = {lerp(color.x, o.film_camera[i].x, t), lerp(color.y, o.film_camera[i].y, t), lerp(color.z, o.film_camera[i].z, t)};
+    o.film_normals[i] = {lerp(normal.x, o.film_normals[i].x, t), lerp(normal.y, o.film_normals[i].y, t), lerp(normal.z, o.film_normals[i].z, t)};
+    o.film_albedo[i] = {lerp(albedo.x, o.film_albedo[i].x, t), lerp(albedo.y, o.film_albedo[i].y, t), lerp(albedo.z, o.film_albedo[i].z, t)};
+    if ((sample_index % 2) == 0) {
+      t = float(ds / (ds + 2.0));
+      o.film_adaptive[i] = {lerp(color.x, o.film_adaptive[i].x, t), lerp(color.y, o.film_adaptive[i].y, t), lerp(color.z, o.film_adaptive[i].z, t)};
+    }
+  }
+  o.film_samples[i] += 1u;
+}
+
+// film.cxx:233-330, single-threaded (the reference's three parallel passes only ever clear flags inside a pass, so their result does not depend on the thread order;
+// its float sum of error levels does, by rounding)
+void film_estimate_noise_levels(Oracle& o, uint32_t sample_index, float threshold) {
+  constexpr uint32_t kMinSamples = 32u;
+  if ((threshold == 0.0f) || (sample_index < kMinSamples) || (sample_index % 2) != 0)
+    return;
+  const uint32_t n = o.pixel_count();
+  uint32_t converged_now = 0;
+  float total_noise = 0.0f;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (o.film_converged[i])
+      continue;
+    const float3& v_i = o.film_camera[i];
+    const float3& v_a = o.film_adaptive[i];
+    float error_diff = dot(abs(v_i - v_a), 1.0f);
+    float error_norm = dot(abs(v_i), 1.0f);
+    float error_level = error_diff / (((error_norm < 1.0f) ? sqrtf(error_norm) : error_norm) + kEpsilon);
+    uint8_t converged = error_level < threshold ? 1u : 0u;
+    o.film_error[i] = error_level;
+    o.film_converged[i] = converged;
+    o.film_tmp[i] = converged;
+    converged_now += converged;
+    total_noise += error_level;
+  }
+  o.active_pixels = converged_now;
+  o.noise_level = (converged_now > 0) ? (total_noise / float(converged_now)) : total_noise;
+  constexpr uint32_t kBlockSize = 5u;
+  const uint32_t w = o.width, h = o.height;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (o.film_converged[i])
+      continue;
+    uint32_t x = i % w, y = i / w;
+    uint32_t begin_x = x >= kBlockSize ? x - kBlockSize : 0u;
+    uint32_t end_x = min(w, x + kBlockSize);
+    for (uint32_t p = begin_x; p < end_x; ++p)
+      o.film_tmp[p + y * w] = 0;
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    if (o.film_tmp[i])
+      continue;
+    uint32_t x = i % w, y = i / w;
+    uint32_t begin_y = y >= kBlockSize ? y - kBlockSize : 0u;
+    uint32_t end_y = min(h, y + kBlockSize);
+    for (uint32_t p = begin_y; p < end_y; ++p)
+      o.film_converged[x + p * w] = 0;
+  }
+}
+
+// CPUPathTracingImpl::execute_range over every pixel + update()'s bookkeeping (path_tracing.cxx:50-110)
+void run_pt_iteration(Oracle& o, uint32_t threads) {
+  auto t0 = std::chrono::steady_clock::now();
+  const Scene& scene = o.scene;
+  const Camera& camera = o.camera;
+  const uint32_t pixel_count = o.pixel_count();
+  const uint32_t iteration = o.iteration.iteration;
+  o.camera_sampler_end.assign(pixel_count, 0u);
+  o.camera_value.assign(pixel_count, float3{});
+  std::vector<uint64_t> bounces(std::max(1u, threads), 0), processed(std::max(1u, threads), 0);
+  parallel_ranges(pixel_count, threads, [&](uint32_t begin, uint32_t end, uint32_t, uint32_t tid) {
+    for (uint32_t i = begin; i < end; ++i) {
+      uint2 pixel = {i % o.width, i / o.width};  // Film::active_pixel with pixel_size == 1 (film.cxx:434-461)
+      uint32_t fi = pixel.x + (o.height - 1u - pixel.y) * o.width;
+      if (o.film_converged[fi])
+        continue;
+      processed[tid] += 1;
+      PTRayPayload payload = make_ray_payload(scene, camera, *o.film, pixel, i, iteration, scene.spectral(), o.pt_options.blue_noise);
+      // a call that gets past the length test (:486) traces a ray and handles one event: that is what the device counts as a bounce
+      bounces[tid] += (payload.path_length <= scene.max_path_length) ? 1 : 0;
+      while (run_path_iteration(scene, o.pt_options, o.rt, payload)) {
+        bounces[tid] += (payload.path_length <= scene.max_path_length) ? 1 : 0;
+      }
+      auto normal = payload.view_normal;
+      auto albedo = (payload.view_albedo / payload.spect.sampling_pdf()).to_rgb();
+      auto color = (payload.accumulated / payload.spect.sampling_pdf()).to_rgb();
+      if ((scene.radiance_clamp > 0.0f) && (payload.path_length > 1)) {
+        float lum = luminance(color);
+        if (lum > scene.radiance_clamp) {
+          color *= scene.radiance_clamp / lum;
+        }
+      }
+      film_accumulate_pt(o, pixel, color, normal, albedo);
+      o.camera_sampler_end[i] = payload.smp.seed;
+      o.camera_value[i] = color;
+    }
+    flush_thread_counters(o.counters);
+  });
+  o.pixels_processed = 0;
+  for (uint32_t t = 0; t < bounces.size(); ++t) {
+    o.stat_bounces_camera += bounces[t];
+    o.pixels_processed += uint32_t(processed[t]);
+  }
+  film_estimate_noise_levels(o, iteration, scene.noise_threshold);
+  auto t1 = std::chrono::steady_clock::now();
+  o.last_iteration_time = std::chrono::duration<double>(t1 - t0).count();
+  o.total_time += o.last_iteration_time;
+  o.completed += 1;
+  o.iteration.iteration += 1;
+}
+
 }  // namespace
 }  // namespace etx
 
@@ -643,6 +819,8 @@ void* oracle_create(const void* scene_blob, uint64_t scene_bytes, const void* ca
   o->options.initial_radius = 0.0f;
   o->options.kernel = VCMOptions::Epanechnikov;
   o->options.blue_noise = true;
+  o->film = new (o->film_storage) Film(*reinterpret_cast<TaskScheduler*>(o->film_storage));  // the scheduler reference is never used
+  o->film->allocate({o->width, o->height});
   film_clear(*o);
   return o;
 }
@@ -658,6 +836,32 @@ void oracle_set_options(void* h, const etxb_vcm_options* opt) {
   o->options.kernel = opt->kernel;
   o->options.initial_radius = opt->initial_radius;
   o->options.blue_noise = opt->blue_noise != 0;
+}
+
+void oracle_set_integrator(void* h, uint32_t integrator) {
+  static_cast<Oracle*>(h)->integrator = integrator;
+}
+
+void oracle_pt_set_options(void* h, const etxb_pt_options* opt) {
+  auto* o = static_cast<Oracle*>(h);
+  o->pt_options.nee = opt->nee != 0;
+  o->pt_options.direct = opt->direct != 0;
+  o->pt_options.mis = opt->mis != 0;
+  o->pt_options.blue_noise = opt->blue_noise != 0;
+}
+
+void oracle_pt_get_status(void* h, etxb_pt_status* out) {
+  auto* o = static_cast<Oracle*>(h);
+  out->pixels_processed = o->pixels_processed;
+  out->active_pixels = o->active_pixels;
+  out->noise_level = o->noise_level;
+  out->max_sample_count = o->scene.samples;
+}
+
+void oracle_set_scene_settings(void* h, float noise_threshold, float radiance_clamp) {
+  auto* o = static_cast<Oracle*>(h);
+  o->scene.noise_threshold = noise_threshold;
+  o->scene.radiance_clamp = radiance_clamp;
 }
 
 void oracle_begin(void* h, uint32_t first_iteration) {
@@ -676,8 +880,13 @@ void oracle_begin(void* h, uint32_t first_iteration) {
 
 double oracle_run_iterations(void* h, uint32_t count, uint32_t threads) {
   auto* o = static_cast<Oracle*>(h);
-  for (uint32_t i = 0; i < count; ++i)
-    run_iteration(*o, threads);
+  for (uint32_t i = 0; i < count; ++i) {
+    if (o->integrator == ETXB_INTEGRATOR_PT) {
+      run_pt_iteration(*o, threads);
+    } else {
+      run_iteration(*o, threads);
+    }
+  }
   return o->total_time;
 }
 
@@ -698,6 +907,15 @@ int oracle_read_film(void* h, uint32_t layer, float* dst, uint64_t dst_bytes) {
         break;
       case ETXB_FILM_LIGHT:
         v = o->film_light[i];
+        break;
+      case ETXB_FILM_NORMALS:
+        v = o->film_normals[i] * 0.5f + 0.5f;  // film.cxx:409
+        break;
+      case ETXB_FILM_ALBEDO:
+        v = o->film_albedo[i];
+        break;
+      case ETXB_FILM_CAMERA_ADAPTIVE:
+        v = o->film_adaptive[i];
         break;
       default:
         v = o->film_light_iteration[i];
@@ -769,6 +987,16 @@ int oracle_read_buffer(void* h, uint32_t id, void* dst, uint64_t dst_bytes, uint
     }
     case ETXB_BUF_CAMERA_GATHERED:
       put(o->camera_value.data(), o->camera_value.size() * 12);
+      break;
+    case ETXB_BUF_PIXEL_INFO: {
+      std::vector<uint32_t> v(n);
+      for (uint32_t i = 0; i < n; ++i)
+        v[i] = (o->film_samples[i] & 0x3fffffffu) | (o->film_converged[i] ? (1u << 30u) : 0u) | (o->film_tmp[i] ? (1u << 31u) : 0u);
+      put(v.data(), v.size() * 4);
+      break;
+    }
+    case ETXB_BUF_PIXEL_ERROR:
+      put(o->film_error.data(), o->film_error.size() * 4);
       break;
     default:
       return -1;

@@ -205,3 +205,91 @@ def test_cpp_adapter_renders_on_the_device_with_a_non_blocking_update(tmp_path):
     # same module, same iterations: the camera part is deterministic, the light image is a float-atomic sum (order differs from run to run)
     err = float(np.sqrt(((film[..., :3].astype(np.float64) - ref[..., :3]) ** 2).sum()) / np.sqrt((ref[..., :3].astype(np.float64) ** 2).sum()))
     assert err < 1e-5, f"C++ adapter and ctypes mirror must render the same film: relative L2 {err:.3e}"
+
+
+PT_SRC = r'''
+#include <cstdio>
+#include <cstring>
+#include "etx_tracer_b200/host/gpu_pt.hpp"
+int main() {
+  etxb::GPUPathTracing pt(0);
+  if (std::strcmp(pt.name(), "Path Tracing (B200)") != 0) return 1;
+  if (pt.set_option("nee", 0.0) != 0 || pt.options().nee != 0u || pt.options().mis != 1u) return 2;
+  if (pt.set_option("bn", 0.0) != 0 || pt.options().blue_noise != 0u) return 3;
+  if (pt.set_option("vcm-merging", 1.0) == 0) return 4;  // not one of CPUPathTracing's option ids
+  if (pt.state() != etxb::GPUPathTracing::State::Stopped) return 5;
+  if (!pt.enabled()) {
+    if (pt.can_run()) return 6;
+    pt.run();
+    pt.update();
+    if (pt.state() != etxb::GPUPathTracing::State::Stopped) return 7;
+    float px[4];
+    if (pt.read_film(ETXB_FILM_NORMALS, px, sizeof(px)) == 0) return 8;
+    if (pt.have_updated_light_image()) return 9;
+    std::puts("no-device contract ok");
+  } else {
+    std::puts("device present");
+  }
+  return 0;
+}
+'''
+
+
+def test_path_tracing_adapter_compiles_and_fails_closed_without_device(tmp_path):
+    lib = etx_build.lib_path("fast")
+    if not os.path.exists(lib):
+        etx_build.build(("fast",))
+    src = tmp_path / "p.cpp"
+    src.write_text(PT_SRC)
+    exe = tmp_path / "p"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", f"-I{ROOT}", str(src), lib, f"-Wl,-rpath,{os.path.dirname(lib)}", "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+
+
+@pytest.mark.gpu
+def test_cpp_path_tracing_adapter_renders_on_the_device(tmp_path):
+    """The same application-side program as above with the path-tracing adapter (host/gpu_pt.hpp): run() schedules iteration 0 itself, update() is
+    pumped without blocking until the integrator stops at scene.samples; the camera layer equals what the ctypes mirror renders, bit for bit (the
+    scene's shadow rays are traced inline, nothing in the pass is order dependent)."""
+    import ctypes as C
+    import numpy as np
+    from etx_tracer_b200 import api, scenes, structs as S
+    sd = scenes.cornell_box(48, 40, samples=6, spectral=True, sphere=True)
+    sc = sd.scene
+    names = ["vertices", "triangles", "triangle_to_emitter", "materials", "emitter_profiles", "emitter_instances", "images", "mediums", "spectrums"]
+    sizes = [S.VERTEX.itemsize, S.TRIANGLE.itemsize, 4, S.MATERIAL.itemsize, S.EMITTER_PROFILE.itemsize, S.EMITTER.itemsize, S.IMAGE.itemsize, S.MEDIUM.itemsize,
+             S.SPECTRUM.itemsize]
+    blobs = []
+    for n, sz in zip(names, sizes):
+        cnt = int(sc[n]["count"][0])
+        blobs.append(bytes((C.c_char * (cnt * sz)).from_address(int(sc[n]["a"][0]))) if cnt else b"")
+    ne = int(sc["emitter_instances"]["count"][0])
+    blobs.append(bytes((C.c_char * ((ne + 1) * S.DIST_ENTRY.itemsize)).from_address(int(sc["emitters_distribution"]["values"]["a"][0]))))
+    ct, bn = scenes.tables("color_tables"), scenes.tables("bluenoise")
+    with open(tmp_path / "scene.bin", "wb") as f:
+        f.write(np.array([len(b) for b in blobs], dtype=np.uint64).tobytes())
+        f.write(sc.tobytes())
+        f.write(sd.camera.tobytes())
+        for b in blobs:
+            f.write(b)
+        f.write(np.ascontiguousarray(ct["xyz_441x3"], dtype=np.float32).tobytes())
+        f.write(np.ascontiguousarray(ct["rgb_response_391x3"], dtype=np.float32).tobytes())
+        for k in ("sobol", "scrambling_8", "ranking_8"):
+            f.write(np.ascontiguousarray(bn[k], dtype=np.uint8).tobytes())
+    code = (RENDER_SRC.replace("gpu_vcm.hpp", "gpu_pt.hpp").replace("etxb::GPUVCM", "etxb::GPUPathTracing").replace("sizeof(camera), 6)", "sizeof(camera))")
+            .replace("ETXB_FILM_RESULT", "ETXB_FILM_CAMERA"))
+    assert "GPUPathTracing pt" not in code and "etxb::GPUPathTracing vcm(0)" in code
+    lib = etx_build.lib_path("fast")
+    src = tmp_path / "rp.cpp"
+    src.write_text(code)
+    exe = tmp_path / "rp"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", f"-I{ROOT}", str(src), lib, f"-Wl,-rpath,{os.path.dirname(lib)}", "-o", str(exe)])
+    out = subprocess.run([str(exe), str(tmp_path / "scene.bin"), str(tmp_path / "film.bin")], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout[-500:], out.stderr[-500:])
+    film = np.fromfile(tmp_path / "film.bin", dtype=np.float32).reshape(sd.height, sd.width, 4)
+    g = api.GPUPathTracing(sd, flavor="fast")
+    g.render(6)
+    ref = g.film(S.FILM_CAMERA)
+    g.close()
+    assert np.array_equal(film[..., :3].view(np.uint32), ref[..., :3].view(np.uint32))

@@ -7,6 +7,7 @@ oracle_c2_32.npz: same for config C2 (spectral, dielectric sphere)
 oracle_c3_24.npz, oracle_c4_24.npz, oracle_c5_24.npz, oracle_vmf_24.npz: the scenes of tests/golden_scenes.py (BASELINE configs 3-5 with their full geometry at a
                   small film, the vMF diffuse material box)
 Existing files are kept (zip metadata would change their bytes); delete one to regenerate it.
+oracle_pt_c2_32.npz: config C2 at 32x32, 3 iterations of the PATH TRACER oracle (camera image, normal / albedo layers, sampler end states)
 trace_c2.npz    : 4096 rays against the C2 scene -> (tri,u,v,t, sampler state)
 """
 import os, sys
@@ -78,8 +79,20 @@ def trace(sd):
     uvt, tri, seeds_out = o.trace(rays, seeds)
     np.savez_compressed(os.path.join(OUT, "trace_c2.npz"), rays=rays, seeds=seeds, uvt=uvt, tri=tri, seeds_out=seeds_out)
 
+def render_pt(name, sd, iters):
+    """the path tracer: run_path_iteration compiled from the reference + the restated CPUPathTracing driver"""
+    if os.path.exists(os.path.join(OUT, name)):
+        return
+    o = oracle_py.Oracle(sd)
+    o.set_integrator(S.INTEGRATOR_PT)
+    o.pt_set_options(S.default_pt_options())
+    o.begin(0); o.run(iters, threads=1)
+    np.savez_compressed(os.path.join(OUT, name), film_camera=o.film(S.FILM_CAMERA), film_normals=o.film(S.FILM_NORMALS), film_albedo=o.film(S.FILM_ALBEDO),
+                        camera_sampler=o.buffer(S.BUF_CAMERA_SAMPLER, np.uint32), iterations=np.array([iters]))
+
 if not os.path.exists(os.path.join(OUT, "kat.npz")):
     kat()
+render_pt("oracle_pt_c2_32.npz", scenes.cornell_box(32, 32, samples=256, spectral=True, sphere=True), 3)
 render("oracle_c1_32.npz", scenes.cornell_box(32, 32, samples=16, spectral=False), 3)
 render("oracle_c2_32.npz", scenes.cornell_box(32, 32, samples=256, spectral=True, sphere=True), 3)
 trace(scenes.cornell_box(32, 32, samples=256, spectral=True, sphere=True))
