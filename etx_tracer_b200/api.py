@@ -91,6 +91,12 @@ def load_library(flavor="fast"):
     lib.etxb_stop.argtypes = [vp, C.c_int]
     lib.etxb_read_film.argtypes = [vp, u32, vp, u64]
     lib.etxb_film_size.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+    if hasattr(lib, "etxb_save_film"):
+        lib.etxb_read_film_ldr.argtypes = [vp, u32, C.c_float, vp, u64]
+        lib.etxb_save_film.argtypes = [vp, u32, C.c_char_p, u32, C.c_float]
+        lib.etxb_write_exr.argtypes = [C.c_char_p, vp, u32, u32]
+        lib.etxb_write_png.argtypes = [C.c_char_p, vp, u32, u32]
+        lib.etxb_tonemap_rgba8.argtypes = [vp, u64, C.c_float, vp]
     lib.etxb_get_counters.argtypes = [vp, vp]
     lib.etxb_get_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(u32), u32]
     lib.etxb_read_buffer.argtypes = [vp, u32, vp, u64, C.POINTER(u64)]
@@ -108,6 +114,29 @@ def load_library(flavor="fast"):
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def write_exr(file_name, rgba, flavor="fast"):
+    """float4 image (H, W, 4) -> OpenEXR (32-bit float A, B, G, R channels, scan lines, no compression); host code of the module."""
+    rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+    rc = load_library(flavor).etxb_write_exr(os.fsencode(file_name), _p(rgba), rgba.shape[1], rgba.shape[0])
+    if rc != 0:
+        raise EtxbError(rc, f"could not write {file_name}")
+
+
+def write_png(file_name, rgba8, flavor="fast"):
+    rgba8 = np.ascontiguousarray(rgba8, dtype=np.uint8)
+    rc = load_library(flavor).etxb_write_png(os.fsencode(file_name), _p(rgba8), rgba8.shape[1], rgba8.shape[0])
+    if rc != 0:
+        raise EtxbError(rc, f"could not write {file_name}")
+
+
+def tonemap(rgba, exposure=1.0, flavor="fast"):
+    """The reference's LDR tone map on the host (app.cxx:268-282): 1 - exp(-exposure c), sRGB curve, 8 bits."""
+    rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+    out = np.zeros(rgba.shape[:-1] + (4,), dtype=np.uint8)
+    load_library(flavor).etxb_tonemap_rgba8(_p(rgba), rgba.size // 4, C.c_float(exposure), _p(out))
+    return out
 
 
 COMM_ID_BYTES = 128
@@ -278,6 +307,16 @@ class GPUVCM:
             out = np.zeros((self.height, self.width, 4), dtype=np.float32)
         self._check(self.lib.etxb_read_film(self.h, layer, _p(out), out.nbytes))
         return out
+
+    def film_ldr(self, layer=S.FILM_RESULT, exposure=1.0):
+        """The tone-mapped 8-bit frame of the reference's viewer / LDR export (app.cxx:268-282), tone-mapped on the device."""
+        out = np.zeros((self.height, self.width, 4), dtype=np.uint8)
+        self._check(self.lib.etxb_read_film_ldr(self.h, layer, C.c_float(exposure), _p(out), out.nbytes))
+        return out
+
+    def save_image(self, file_name, layer=S.FILM_RESULT, tonemapped=False, exposure=1.0):
+        """RTApplication::on_save_image_selected (app.cxx:261-295): the float layer as OpenEXR, or tone-mapped as PNG."""
+        self._check(self.lib.etxb_save_film(self.h, layer, os.fsencode(file_name), 1 if tonemapped else 0, C.c_float(exposure)))
 
     def counters(self):
         c = np.zeros(1, dtype=S.COUNTERS)

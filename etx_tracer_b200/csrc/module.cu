@@ -1832,11 +1832,9 @@ int etxb_film_size(const etxb_ctx* ctx, uint32_t* width, uint32_t* height) {
   return ETXB_OK;
 }
 
-int etxb_read_film(etxb_ctx* ctx, uint32_t layer, float* dst_rgba, uint64_t dst_bytes) {
-  if (!ctx || !dst_rgba) return ETXB_ERR_INVALID_ARGUMENT;
+// Film::layer (film.cxx:381-418): the device buffer that holds `layer` as float4 (computed into film_out where the layer is derived)
+static int film_layer_source(etxb_ctx* ctx, uint32_t layer, const float4** out_src) {
   if (!ctx->scene_ready) return fail(ctx, ETXB_ERR_NOT_READY, "no scene uploaded");
-  size_t n = ctx->path_count;
-  if (dst_bytes < n * 16) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "film buffer too small");
   cudaSetDevice(ctx->device);
   const float4* src = nullptr;
   switch (layer) {
@@ -1872,9 +1870,54 @@ int etxb_read_film(etxb_ctx* ctx, uint32_t layer, float* dst_rgba, uint64_t dst_
     default:
       return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "unknown film layer %u", layer);
   }
+  *out_src = src;
+  return ETXB_OK;
+}
+
+int etxb_read_film(etxb_ctx* ctx, uint32_t layer, float* dst_rgba, uint64_t dst_bytes) {
+  if (!ctx || !dst_rgba) return ETXB_ERR_INVALID_ARGUMENT;
+  size_t n = ctx->path_count;
+  if (ctx->scene_ready && (dst_bytes < n * 16)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "film buffer too small");
+  const float4* src = nullptr;
+  if (int rc = film_layer_source(ctx, layer, &src)) return rc;
   CUDA_OK(ctx, cudaMemcpyAsync(dst_rgba, src, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return ETXB_OK;
+}
+
+// The tone-mapped 8-bit frame the application shows and exports (app.cxx:268-282): computed on the device, 4 bytes per pixel cross the bus.
+int etxb_read_film_ldr(etxb_ctx* ctx, uint32_t layer, float exposure, uint8_t* dst_rgba8, uint64_t dst_bytes) {
+  if (!ctx || !dst_rgba8) return ETXB_ERR_INVALID_ARGUMENT;
+  size_t n = ctx->path_count;
+  if (ctx->scene_ready && (dst_bytes < n * 4)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "film buffer too small");
+  const float4* src = nullptr;
+  if (int rc = film_layer_source(ctx, layer, &src)) return rc;
+  // keys_out is free between iterations (the context is drained: the layer was just resolved on this stream) and holds at least one word per pixel
+  uint32_t* packed = ctx->keys_out.ptr;
+  k_film_tonemap<<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(src, packed, ctx->path_count, exposure);
+  ctx->kernel_launches += 1;
+  CUDA_OK(ctx, cudaMemcpyAsync(dst_rgba8, packed, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETXB_OK;
+}
+
+// RTApplication::on_save_image_selected (app.cxx:261-295): mode 0 = the float layer as OpenEXR, mode 1 = the tone-mapped layer as PNG
+int etxb_save_film(etxb_ctx* ctx, uint32_t layer, const char* file_name, uint32_t mode, float exposure) {
+  if (!ctx || !file_name || (mode > ETXB_SAVE_PNG_TONEMAPPED)) return ETXB_ERR_INVALID_ARGUMENT;
+  if (!ctx->scene_ready) return fail(ctx, ETXB_ERR_NOT_READY, "no scene uploaded");
+  if (int rc = ctx_drain_impl(ctx)) return rc;
+  const size_t n = ctx->path_count;
+  int rc = ETXB_OK;
+  if (mode == ETXB_SAVE_EXR) {
+    std::vector<float> pixels(n * 4u);
+    if ((rc = etxb_read_film(ctx, layer, pixels.data(), pixels.size() * 4u)) != ETXB_OK) return rc;
+    rc = etxb_write_exr(file_name, pixels.data(), ctx->width, ctx->height);
+  } else {
+    std::vector<uint8_t> pixels(n * 4u);
+    if ((rc = etxb_read_film_ldr(ctx, layer, exposure, pixels.data(), pixels.size())) != ETXB_OK) return rc;
+    rc = etxb_write_png(file_name, pixels.data(), ctx->width, ctx->height);
+  }
+  return (rc == ETXB_OK) ? ETXB_OK : fail(ctx, rc, "could not write %s", file_name);
 }
 
 int etxb_get_counters(etxb_ctx* ctx, etxb_counters* out) {

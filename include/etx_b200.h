@@ -337,6 +337,18 @@ int etxb_set_next_iteration(etxb_ctx* ctx, uint32_t iteration);
 /* CPUVCMImpl::start (vcm_cpu.cxx:81-93): clears film, sets iteration = first_iteration. */
 int etxb_begin(etxb_ctx* ctx, uint32_t first_iteration);
 
+/* ---- film export: RTApplication::on_save_image_selected (sources/raytracer/app.cxx:261-295) -------------------------
+ * The reference saves the selected Film layer either as float OpenEXR (tinyexr SaveEXR) or tone-mapped to 8-bit PNG (1 - exp(-exposure c),
+ * sRGB curve, stb_image_write).  etxb_read_film_ldr tone-maps on the device (4 bytes per pixel leave the GPU); the two writers and the host
+ * tone map are plain host code (usable on any float4 / RGBA8 buffer, e.g. a multi-GPU frame from etxb_group_comm_reduce_film). */
+#define ETXB_SAVE_EXR 0u
+#define ETXB_SAVE_PNG_TONEMAPPED 1u
+int etxb_read_film_ldr(etxb_ctx* ctx, uint32_t layer, float exposure, uint8_t* dst_rgba8, uint64_t dst_bytes);
+int etxb_save_film(etxb_ctx* ctx, uint32_t layer, const char* file_name, uint32_t mode, float exposure);
+int etxb_write_exr(const char* file_name, const float* rgba, uint32_t width, uint32_t height);
+int etxb_write_png(const char* file_name, const uint8_t* rgba8, uint32_t width, uint32_t height);
+int etxb_tonemap_rgba8(const float* rgba, uint64_t pixel_count, float exposure, uint8_t* out_rgba8);
+
 /* ---- the unidirectional path tracer on the same context -----------------------------------------
  * Replaces CPUPathTracing (rt/integrators/path_tracing.cxx:12-170) + run_path_iteration (rt/shared/path_tracing_shared.hxx:485-510)
  * + Film::accumulate_camera_image with the normal / albedo layers and Film::estimate_noise_levels (render/host/film.cxx:173-330).
