@@ -163,31 +163,34 @@ class SceneData:
         return len(self.materials) - 1
 
     # -- images / distant emitters ------------------------------------------------------------------
-    def add_image(self, pixels, repeat=True, build_table=False, uniform_table=False, offset=(0.0, 0.0), scale=(1.0, 1.0), has_alpha=None):
+    def add_image(self, pixels, repeat=True, build_table=False, uniform_table=False, offset=(0.0, 0.0), scale=(1.0, 1.0), has_alpha=None, repeat_v=None):
         """ImagePool::add_from_data + build_image_sampling_table (render/host/image_pool.cxx:226-259), RGBA32F."""
-        px = np.ascontiguousarray(pixels, dtype=f32)
+        u8 = np.asarray(pixels).dtype == np.uint8  # Image::Format::RGBA8 (8-bit files stay 8-bit, image_pool.cxx:188-205); float pixels: RGBA32F
+        store = np.ascontiguousarray(pixels, dtype=np.uint8) if u8 else None
+        px = (store.astype(f32) / f32(255.0)).astype(f32) if u8 else np.ascontiguousarray(pixels, dtype=f32)  # to_float4(ubyte4) (math.hxx:709-711)
         h, w = px.shape[:2]
         assert px.shape[2] == 4
         img = np.zeros(1, dtype=S.IMAGE)
-        opts = (6 if repeat else 0) | (1 if build_table else 0) | (32 if uniform_table else 0)
+        repeat_v = repeat if repeat_v is None else repeat_v  # Image::RepeatU / RepeatV are separate bits (an environment map wraps in u only)
+        opts = (2 if repeat else 0) | (4 if repeat_v else 0) | (1 if build_table else 0) | (32 if uniform_table else 0)
         if has_alpha is None:
             has_alpha = bool((px[..., 3] < 1.0).any())
         if has_alpha:
             opts |= 16
-        img["pixels"]["a"] = px.ctypes.data
+        img["pixels"]["a"] = store.ctypes.data if u8 else px.ctypes.data
         img["pixels"]["count"] = w * h
         img["fsize"][0] = (w, h)
         img["isize"][0] = (w, h)
         img["offset"][0] = offset
         img["scale"][0] = scale
         img["options"] = opts
-        img["format"] = 1
-        img["data_size"] = px.nbytes
-        keep = [px]
+        img["format"] = 2 if u8 else 1
+        img["data_size"] = store.nbytes if u8 else px.nbytes
+        keep = [px, store]
         if build_table:
             # Image::read at texel centres = mean of the 2x2 neighbourhood (image.hxx:173-186)
             xs1 = (np.arange(w) + 1) % w if repeat else np.minimum(np.arange(w) + 1, w - 1)
-            ys1 = (np.arange(h) + 1) % h if repeat else np.minimum(np.arange(h) + 1, h - 1)
+            ys1 = (np.arange(h) + 1) % h if repeat_v else np.minimum(np.arange(h) + 1, h - 1)
             rgb = px[..., :3]
             avg = (rgb * f32(0.25) + rgb[:, xs1] * f32(0.25) + rgb[ys1] * f32(0.25) + rgb[ys1][:, xs1] * f32(0.25)).astype(f32)
             lum = (avg[..., 0] * f32(0.212671) + avg[..., 1] * f32(0.715160) + avg[..., 2] * f32(0.072169)).astype(f32)
@@ -229,8 +232,61 @@ class SceneData:
         self._keep.append(keep)
         if not hasattr(self, "_images"):
             self._images = []
+        if not hasattr(self, "_image_px"):
+            self._image_px = {}
         self._images.append(img)
+        self._image_px[len(self._images) - 1] = px  # the pixels as Image::pixel() returns them (float4)
         return len(self._images) - 1
+
+    def image_evaluate(self, index, uv):
+        """Image::evaluate(uv, nullptr) (render/shared/image.hxx:51-88): bilinear gather with the image's repeat / clamp flags; uv = (N, 2) float32."""
+        rec, px = self._images[index], self._image_px[index]
+        w, h = int(rec["isize"][0][0]), int(rec["isize"][0][1])
+        fw, fh = f32(w), f32(h)
+        opts = int(rec["options"][0])
+
+        def coord(t, size, rep):
+            if rep:
+                x = np.fmod(t, size).astype(f32)
+                return np.where(x < 0, (x + size).astype(f32), x).astype(f32)
+            return np.clip(t, f32(0.0), np.nextafter(size, f32(0.0), dtype=f32)).astype(f32)
+        x0 = coord((uv[:, 0] * fw).astype(f32), fw, bool(opts & 2))
+        y0 = coord((uv[:, 1] * fh).astype(f32), fh, bool(opts & 4))
+        dx, dy = (x0 - np.floor(x0)).astype(f32), (y0 - np.floor(y0)).astype(f32)
+        r0 = np.clip(y0.astype(np.uint32), 0, h - 1)
+        r1 = np.clip(r0 + 1, 0, h - 1)
+        c0 = np.clip(x0.astype(np.uint32), 0, w - 1)
+        c1 = np.clip(c0 + 1, 0, w - 1)
+        one = f32(1.0)
+        p00 = ((px[r0, c0] * (one - dx)[:, None]).astype(f32) * (one - dy)[:, None]).astype(f32)
+        p01 = ((px[r0, c1] * dx[:, None]).astype(f32) * (one - dy)[:, None]).astype(f32)
+        p10 = ((px[r1, c0] * (one - dx)[:, None]).astype(f32) * dy[:, None]).astype(f32)
+        p11 = ((px[r1, c1] * dx[:, None]).astype(f32) * dy[:, None]).astype(f32)
+        return (((p00 + p01).astype(f32) + p10).astype(f32) + p11).astype(f32)
+
+    def _texture_emission(self, image_index, tex):
+        """The emission-image factor of an area emitter's weight (add_area_emitters_for_triangle, scene_representation.cxx:855-872): 1 + the image's
+        luminance x alpha averaged over a barycentric grid of the triangle (the inner loop of the reference steps by dv, kept)."""
+        rec = self._images[image_index]
+        fs = rec["fsize"][0]
+        mn, mx = tex.min(axis=0), tex.max(axis=0)
+        u_size = f32(4.0) * max(f32(1.0), f32(np.ceil(f32(f32(mx[0] - mn[0]) * fs[0]))))
+        v_size = f32(4.0) * max(f32(1.0), f32(np.ceil(f32(f32(mx[1] - mn[1]) * fs[1]))))
+        du, dv = f32(1.0) / u_size, f32(1.0) / v_size
+        steps, t = [], f32(0.0)
+        while t < f32(1.0):
+            steps.append(t)
+            t = f32(t + dv)
+        g = np.array(steps, dtype=f32)
+        v, u = np.repeat(g, len(g)), np.tile(g, len(g))
+        r1 = np.sqrt(u).astype(f32)
+        bc = np.stack([(f32(1.0) - r1).astype(f32), (r1 * (f32(1.0) - v).astype(f32)).astype(f32), (r1 * v).astype(f32)], 1)
+        uv = ((tex[0][None, :] * bc[:, 0:1]).astype(f32) + (tex[1][None, :] * bc[:, 1:2]).astype(f32)).astype(f32)
+        uv = (uv + (tex[2][None, :] * bc[:, 2:3]).astype(f32)).astype(f32)
+        val = self.image_evaluate(image_index, uv)
+        lum = ((val[:, 0] * f32(0.212671)).astype(f32) + (val[:, 1] * f32(0.715160)).astype(f32)).astype(f32) + (val[:, 2] * f32(0.072169)).astype(f32)
+        terms = (((lum.astype(f32) * du).astype(f32) * dv).astype(f32) * val[:, 3]).astype(f32)
+        return f32(np.cumsum(np.concatenate([[f32(1.0)], terms]).astype(f32), dtype=f32)[-1])
 
     def add_environment_emitter(self, image_index, rgb=(1.0, 1.0, 1.0)):
         """et::env with an image (scene_representation.cxx: environment profile + one instance)."""
@@ -384,7 +440,7 @@ class SceneData:
         self.add_mesh(np.array(pos), np.array(nrm), np.array(idx), material_index, uvs=np.array(uv))
 
     # -- finalisation ----------------------------------------------------------------------------
-    def set_camera(self, origin, target, up, width, height, fov_deg, clip_near=1.0 / 256.0, clip_far=1024.0, lens_radius=0.0, focal_distance=0.0):
+    def set_camera(self, origin, target, up, width, height, fov_deg, clip_near=1.0 / 256.0, clip_far=1024.0, lens_radius=0.0, focal_distance=0.0, f32_trig=False):
         """build_camera (scene_representation.cxx:579-598) with float32 arithmetic."""
         cam = self.camera
         cam[:] = 0
@@ -411,7 +467,11 @@ class SceneData:
         view[3][2] = np.dot(f, o)
         view[3][3] = 1.0
         fov = f32(fov_deg) * f32(math.pi) / f32(180.0)
-        w = f32(math.cos(0.5 * float(fov)) / math.sin(0.5 * float(fov)))
+        if f32_trig:  # perspective() divides cosf by sinf (vector_math.hxx:118): the scene-file loader follows it to the bit
+            half = f32(f32(0.5) * fov)
+            w = f32(np.cos(half, dtype=f32) / np.sin(half, dtype=f32))
+        else:        # the generators' cameras (and the golden renders made with them) use the double-precision quotient
+            w = f32(math.cos(0.5 * float(fov)) / math.sin(0.5 * float(fov)))
         aspect = f32(width) / f32(height)
         zn, zf = f32(clip_near), f32(clip_far)
         proj = np.zeros((4, 4), dtype=f32)
@@ -483,6 +543,22 @@ class SceneData:
             if m["thinfilm"]["ior"]["eta_index"][0] == S.INVALID:
                 m["thinfilm"]["ior"]["eta_index"] = one
 
+        self.finalize_arrays(samples, spectral, max_path_length, min_path_length, random_path_termination)
+        sc["black_spectrum"] = black
+        sc["white_spectrum"] = white
+        for fld in ("rayleigh_spectrum", "mie_spectrum", "ozone_spectrum"):
+            sc[fld] = S.INVALID
+        sc["subsurface_scatter_material"] = ss_scatter
+        sc["subsurface_exit_material"] = ss_exit
+        sc["default_dielectric_eta"] = def_diel
+        sc["default_conductor_eta"] = def_cond_eta
+        sc["default_conductor_k"] = def_cond_k
+        return self
+
+    def finalize_arrays(self, samples, spectral, max_path_length=1023, min_path_length=0, random_path_termination=6, distant_first=False):
+        """commit (scene_representation.cxx:420-455) + rebuild_area_emitters + build_emitters_distribution on validated materials: the flat arrays and
+        the Scene record (the default-spectrum / subsurface-material indices are the caller's)."""
+        sc = self.scene
         self.a_vertices = np.concatenate(self.vertices) if self.vertices else np.zeros(0, S.VERTEX)
         self.a_triangles = np.concatenate(self.triangles) if self.triangles else np.zeros(0, S.TRIANGLE)
         self.a_materials = np.concatenate(self.materials)
@@ -500,6 +576,18 @@ class SceneData:
         tri_to_emitter = np.full(nt, S.INVALID, dtype=np.uint32)
         profiles, instances, mat_to_profile = [], [], {}
         lum = {}
+
+        def add_distant():
+            for (p, e) in getattr(self, "_distant_emitters", []):
+                e = e.copy()
+                e["cls"] = p["cls"]
+                e["profile"] = len(profiles)
+                e["additional_weight"] = f32(math.pi) * radius * radius
+                e["spectrum_weight"] = luminance(self.a_spectra["integrated"][int(p["emission"]["spectrum_index"][0])])
+                profiles.append(p)
+                instances.append(e)
+        if distant_first:  # a scene FILE declares its et::env / et::dir emitters before commit() instances the area emitters (scene_representation.cxx:1308-1378, 956)
+            add_distant()
         for ti in range(nt):
             mi = int(self.a_triangles["material_index"][ti])
             m = self.a_materials[mi]
@@ -512,7 +600,10 @@ class SceneData:
             p0, p1, p2 = self.a_vertices["pos"][i0], self.a_vertices["pos"][i1], self.a_vertices["pos"][i2]
             cr = np.cross((p1 - p0).astype(f32), (p2 - p0).astype(f32)).astype(f32)
             area = f32(0.5) * f32(math.sqrt(float(np.dot(cr, cr))))
-            add_w = f32((2.0 if m["two_sided"] else 1.0)) * f32(area * f32(math.pi)) * f32(1.0)
+            tex_em = f32(1.0)
+            if int(m["emission"]["image_index"]) != S.INVALID:
+                tex_em = self._texture_emission(int(m["emission"]["image_index"]), self.a_vertices["tex"][[i0, i1, i2]])
+            add_w = f32((2.0 if m["two_sided"] else 1.0)) * f32(area * f32(math.pi)) * tex_em
             if mi not in mat_to_profile:
                 p = np.zeros(1, dtype=S.EMITTER_PROFILE)
                 p["emission"] = m["emission"]
@@ -529,14 +620,8 @@ class SceneData:
             e["spectrum_weight"] = lum[si]
             tri_to_emitter[ti] = len(instances)
             instances.append(e)
-        for (p, e) in getattr(self, "_distant_emitters", []):
-            e = e.copy()
-            e["cls"] = p["cls"]
-            e["profile"] = len(profiles)
-            e["additional_weight"] = f32(math.pi) * radius * radius
-            e["spectrum_weight"] = luminance(self.a_spectra["integrated"][int(p["emission"]["spectrum_index"][0])])
-            profiles.append(p)
-            instances.append(e)
+        if not distant_first:
+            add_distant()
         assert instances, "scene needs at least one emitter (the loader would synthesise an atmosphere otherwise)"
         self.a_profiles = np.concatenate(profiles)
         self.a_emitters = np.concatenate(instances)
@@ -590,15 +675,6 @@ class SceneData:
         sc["random_path_termination"] = random_path_termination
         sc["noise_threshold"] = 0.1
         sc["radiance_clamp"] = 0.0
-        sc["black_spectrum"] = black
-        sc["white_spectrum"] = white
-        for fld in ("rayleigh_spectrum", "mie_spectrum", "ozone_spectrum"):
-            sc[fld] = S.INVALID
-        sc["subsurface_scatter_material"] = ss_scatter
-        sc["subsurface_exit_material"] = ss_exit
-        sc["default_dielectric_eta"] = def_diel
-        sc["default_conductor_eta"] = def_cond_eta
-        sc["default_conductor_k"] = def_cond_k
         sc["flags"] = S.SCENE_COMMITTED | (S.SCENE_SPECTRAL if spectral else 0)
         return self
 

@@ -59,6 +59,15 @@ for (t, scale) in ((2700, 5.0), (5800, 1.0), (6500, 1.0), (12000, 0.1)):
     lib.oracle_spectrum_blackbody(t, scale, 1, P(s))
     spectra[f"nblackbody_{t}_{scale}.power"] = s["entries"]["power"][0].copy()
     spectra[f"nblackbody_{t}_{scale}.rgb"] = s["integrated"][0].copy()
+# the three atmosphere spectra every scene's spectrum pool starts with (scattering::init -> init_default_values, scene_representation.cxx:206-213):
+# entries 2, 3, 4 of the pool of any scene the reference's own loader has read
+rs = oracle_py.ReferenceScene("assets/cornellbox/cornellbox.json")
+pool = np.frombuffer((__import__("ctypes").c_char * (5 * S.SPECTRUM.itemsize)).from_address(int(rs.scene["spectrums"]["a"][0])), dtype=S.SPECTRUM)
+for idx, key in ((2, "rayleigh"), (3, "mie"), (4, "ozone")):
+    assert int(rs.scene[key + "_spectrum"][0]) == idx and int(pool[idx]["entry_count"]) == 441
+    spectra[f"atmosphere_{key}.power"] = pool[idx]["entries"]["power"].copy()
+    spectra[f"atmosphere_{key}.rgb"] = pool[idx]["integrated"].copy()
+rs.close()
 np.savez_compressed(os.path.join(OUT, "spectra.npz"), **spectra)
 for f in os.listdir(OUT):
     print(f, os.path.getsize(os.path.join(OUT, f)))
