@@ -406,3 +406,45 @@ def test_loaded_scene_renders_through_the_oracle(ref, oracle_mod, tmp_path):
     img = o.film(S.FILM_RESULT)[..., :3]
     assert np.isfinite(img).all() and img.mean() > 1e-3
     o.close()
+
+
+@pytest.mark.gpu
+def test_loaded_scene_files_render_bit_exact_on_the_device(oracle_mod, tmp_path):
+    """Scene FILE -> loader -> etxb_upload_scene: the parity build against the oracle on the loader's PODs, both integrators (the generated
+    directive-coverage scene: media, Boundary shell, thin film, subsurface glass, distant emitters with a disk, thin-lens camera inside a medium)."""
+    from conftest import bit_equal
+    sd = loader.load_scene(_write_scene(tmp_path))
+    o = oracle_mod.Oracle(sd)
+    o.begin(0)
+    o.run(2, threads=1)
+    g = api.GPUVCM(sd, flavor="parity")
+    g.render(2)
+    for bid, dt in ((S.BUF_LIGHT_SAMPLER, np.uint32), (S.BUF_LV_POS, np.float32), (S.BUF_CAMERA_SAMPLER, np.uint32), (S.BUF_CAMERA_GATHERED, np.float32)):
+        assert bit_equal(g.buffer(bid, dt), o.buffer(bid, dt)), f"buffer {bid}"
+    assert bit_equal(g.film(S.FILM_CAMERA)[..., :3], o.film(S.FILM_CAMERA)[..., :3])
+    g.close()
+    o.set_integrator(S.INTEGRATOR_PT)
+    o.pt_set_options(S.default_pt_options())
+    o.begin(0)
+    o.run(3, threads=1)
+    p = api.GPUPathTracing(sd, flavor="parity")
+    p.render(3)
+    assert bit_equal(p.buffer(S.BUF_CAMERA_SAMPLER, np.uint32), o.buffer(S.BUF_CAMERA_SAMPLER, np.uint32))
+    for layer in (S.FILM_CAMERA, S.FILM_NORMALS, S.FILM_ALBEDO):
+        assert bit_equal(p.film(layer)[..., :3], o.film(layer)[..., :3]), layer
+    p.close()
+    o.close()
+
+
+@pytest.mark.gpu
+def test_headless_render_command(tmp_path):
+    """python -m etx_tracer_b200.render: scene file in, OpenEXR / PNG out (loader + integrator pump + film export), both integrators."""
+    from etx_tracer_b200 import render
+    path = _write_scene(tmp_path)
+    out = str(tmp_path / "vcm.exr")
+    assert render.main([path, "-o", out, "--spp", "4", "--option", "vcm-merging=0"]) == 0
+    d = open(out, "rb").read()
+    assert d[:4] == b"\x76\x2f\x31\x01" and len(d) > 80 * 60 * 16
+    out = str(tmp_path / "pt.png")
+    assert render.main([path, "-o", out, "--integrator", "pt", "--spp", "6", "--layer", "camera", "--exposure", "2.0", "--option", "bn=0"]) == 0
+    assert open(out, "rb").read()[:8] == b"\x89PNG\r\n\x1a\n"
