@@ -177,6 +177,38 @@ def cpu_baseline_run(sd_factory, budget_s, threads, opts=None):
                       f"(reference headers compiled in place + our BVH instead of Embree)"}, flavor
 
 
+def path_tracer_line(sd, device, iterations=8, cpu_iterations=1):
+    """The second device integrator (CPUPathTracing's algorithm) on the same workload, one iteration in flight, next to the reference's CPU
+    path tracer (run_path_iteration compiled from the reference + the restated driver) on the host threads.  An extra key of the line, never its `value`."""
+    from etx_tracer_b200 import structs as S
+    from etx_tracer_b200.api import GPUPathTracing
+    g = GPUPathTracing(sd, flavor="fast", device=device, profile=True)
+    g.set_scene_settings(0.0, 0.0)  # no pixel converges: a sample = one pixel-iteration
+    g.render(2)
+    st = g.render(iterations, first_iteration=2)
+    n = sd.width * sd.height
+    out = {"metric": "Msamples/s (pixels*spp/s), unidirectional path tracer", "value": n * iterations / st["total_time"] / 1e6, "unit": UNIT, "iterations": iterations,
+           "ms_per_iteration": 1e3 * st["total_time"] / iterations, "in_flight": 1,
+           "kernel_ms_per_iteration": {k: round(v[0] / iterations, 3) for k, v in sorted(g.kernel_times().items(), key=lambda kv: -kv[1][0]) if v[1]},
+           "rays_per_iteration": int((g.counters()["rays_closest"] + g.counters()["rays_shadow"]) / iterations)}
+    g.close()
+    if cpu_iterations > 0:
+        from oracle import oracle_py
+        flavor = "native" if oracle_py.available("native") else "parity"
+        o = oracle_py.Oracle(sd, flavor)
+        o.set_integrator(S.INTEGRATOR_PT)
+        o.pt_set_options(S.default_pt_options())
+        o.set_scene_settings(0.0, 0.0)
+        o.begin(2)
+        threads = os.cpu_count() or 1
+        t = o.run(cpu_iterations, threads=threads)
+        o.close()
+        out["cpu_baseline"] = {"value": n * cpu_iterations / t / 1e6, "unit": UNIT, "cores": threads, "kind": "reference",
+                               "sample": f"{cpu_iterations} iteration(s) of the same scene and film ({t:.1f} s) by oracle/_ref/liboracle_{flavor}.so (run_path_iteration "
+                                         f"compiled from the reference, our BVH instead of Embree)"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -236,6 +268,7 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--res", type=int, default=0, help="override the film size (debug only; the default is the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-path-tracer", action="store_true", help="skip the extra `path_tracer` key (the second device integrator on the same workload, N = 1 only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--lanes", type=int, default=4, help="iterations in flight per GPU (etxb_group); 1 = the plain one-context pump")
     ap.add_argument("--parallelism", default="both", choices=["both", "tile", "iteration"],
@@ -490,6 +523,12 @@ def main():
         if not args.no_cpu_baseline:
             from etx_tracer_b200 import scenes
             cpu, _ = cpu_baseline_run(lambda res: scene_factory(args, res), args.cpu_budget, os.cpu_count() or 1, workload_vcm_options(args))
+        pt = None
+        if (world == 1) and not args.no_path_tracer:
+            try:
+                pt = path_tracer_line(sd, local_rank, cpu_iterations=0 if args.no_cpu_baseline else 1)
+            except Exception as e:  # an extra key must never cost the headline line
+                pt = {"error": f"{type(e).__name__}: {e}"[:300]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc,
@@ -507,7 +546,7 @@ def main():
                                          f"{args.warmup}..{args.warmup + args.steps - 1} of the 1/(1 + i/256) merge-radius schedule (the most expensive end of a render)",
                            "light_vertices_per_iteration": st1["light_vertices"], "per_kernel_event_timing": True},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(counters["kernel_launches"]), "clocks": clk,
-                "counters": counters,
+                "counters": counters, "path_tracer": pt,
                 # every way of spreading the same K iterations that was measured in this run (N > 1, --parallelism both): `value` is the faster one
                 "modes": {r["mode"]: {"value": r["value"], "ms_per_step": r["elapsed"] / args.steps * 1e3, "e2e": r["e2e"]["value"],
                                       "collective_ms_per_iteration": r["collective_ms_per_iteration"], "film_finite": r["film_finite"]} for r in results}}
