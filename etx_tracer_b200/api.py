@@ -467,6 +467,16 @@ class GPUVCMGroup:
         except Exception:
             pass
 
+    def set_integrator(self, integrator, pt_options=None):
+        """Every lane renders with the VCM (default) or the path-tracing algorithm.  With iterations in flight each lane keeps its own film and per-pixel
+        history, so the path tracer's adaptive sampling is switched off here (noise threshold 0: every pixel gets one sample per iteration, like the
+        reference with `noise_threshold 0`); the combined film is the mean over the iterations of all lanes."""
+        for g in self.lanes:
+            g._check(self.lib.etxb_set_integrator(g.h, integrator))
+            if integrator == S.INTEGRATOR_PT:
+                g._check(self.lib.etxb_pt_set_options(g.h, _p(pt_options if pt_options is not None else S.default_pt_options())))
+                g._check(self.lib.etxb_set_scene_settings(g.h, C.c_float(0.0), C.c_float(float(self.scene_data.scene["radiance_clamp"][0]))))
+
     def set_options(self):
         """Pushes self.options (the Integrator options) to every lane."""
         for g in self.lanes:

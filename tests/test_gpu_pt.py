@@ -254,3 +254,21 @@ def test_product_build_statistical_parity(api, oracle_mod, name):
     nrm_g, nrm_o = g.film(S.FILM_NORMALS)[..., :3], oa.film(S.FILM_NORMALS)[..., :3]
     assert rel_l2(nrm_g, nrm_o) < 2e-2  # the first-hit layers share the stream: same geometry up to a few flipped hits per thousand
     g.close()
+
+
+def test_iterations_in_flight_render_the_same_frame(api):
+    """etxb_group lanes with the path tracer (adaptive sampling off): the lanes render the iteration indices 0..n-1 between them, the combined film is the
+    mean over those iterations = the single-context frame up to float summation order."""
+    sd = scenes.cornell_box(64, 48, **C2)
+    n = 9
+    ref = api.GPUPathTracing(sd, flavor="fast")
+    ref.set_scene_settings(0.0, 0.0)
+    ref.render(n)
+    grp = api.GPUVCMGroup(sd, lanes=3, flavor="fast")
+    grp.set_integrator(S.INTEGRATOR_PT)
+    st = grp.render(n)
+    assert st["completed_iterations"] == n and st["iteration_in_flight"] == 0
+    a, b = grp.film(S.FILM_CAMERA)[..., :3], ref.film(S.FILM_CAMERA)[..., :3]
+    assert np.isfinite(a).all() and rel_l2(a, b) < 1e-5, rel_l2(a, b)
+    grp.close()
+    ref.close()

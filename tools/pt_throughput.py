@@ -22,6 +22,22 @@ out = {"metric": "Msamples/s path tracer", "workload": what, "film": [sd.width, 
        "kernel_ms_per_iteration": {k: round(v[0] / iters, 3) for k, v in sorted(g.kernel_times().items(), key=lambda kv: -kv[1][0]) if v[1]},
        "counters": {k: v for k, v in g.counters().items() if v}}
 g.close()
+try:  # several iterations in flight (etxb_group lanes, adaptive sampling off): the throughput form, like the VCM bench's `value`
+    from etx_tracer_b200.api import GPUVCMGroup
+    grp = GPUVCMGroup(sd, lanes=4, flavor="fast")
+    grp.set_integrator(S.INTEGRATOR_PT)
+    grp.render(4)
+    grp.run(4)
+    k = max(iters, 12)
+    grp.enqueue(k)
+    grp.wait()
+    st4 = grp.status()
+    img4 = grp.film(S.FILM_CAMERA)[..., :3]
+    out["in_flight_4"] = {"value": n * k / st4["total_time"] / 1e6, "ms_per_iteration": 1e3 * st4["total_time"] / k, "iterations": k, "mean": float(img4.mean()),
+                          "finite": bool(np.isfinite(img4).all())}
+    grp.close()
+except Exception as e:
+    out["in_flight_4"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 if cpu_iters > 0:
     from oracle import oracle_py
     if oracle_py.available("native"):
