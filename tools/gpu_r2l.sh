@@ -18,6 +18,14 @@ except Exception as e:
     print("bench failed", e)
 P
 tail -3 gpurun_out/${tag}_bench_c3.err
+for l in 6 8; do
+  timeout 300 python bench.py --steps 20 --warmup 5 --lanes $l --no-cpu-baseline --no-path-tracer > gpurun_out/${tag}_bench_c3_lanes$l.json 2> /dev/null
+  python -c "
+import json
+try:
+    d = json.load(open('gpurun_out/${tag}_bench_c3_lanes$l.json')); print('lanes $l', round(d['value'], 3), 'e2e', round(d['e2e']['value'], 3))
+except Exception as e: print('lanes $l failed', e)"
+done
 timeout 300 python tools/pt_throughput.py C3 8 0 > gpurun_out/${tag}_pt_c3.json 2> gpurun_out/${tag}_pt_c3.err; cut -c1-600 gpurun_out/${tag}_pt_c3.json
 timeout 300 ncu --metrics gpu__time_duration.sum,launch__grid_size,smsp__thread_inst_executed_per_inst_executed.ratio --clock-control none --csv --log-file gpurun_out/${tag}_pt_c3_launches.csv python tools/profile_run_pt.py C3 1 > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_pt_shade -s 1 -c 1 -o /tmp/ptshade python tools/profile_run_pt.py C3 1 > /dev/null 2>&1
