@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(128) k_pt_begin(const __grid_constant__ Launch
       // run_path_iteration's first test (:486): a path longer than the limit is not traced at all
       alive = s.path_length <= p.scene.max_path_length;
       if (!alive) p.sampler_end_camera[i] = s.smp.seed;
+    } else {
+      // a pixel that is skipped (converged, or another rank's tile) has no path in this iteration: its debug taps read zero, like the oracle's
+      p.sampler_end_camera[i] = 0u;
+      p.camera_value[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
   }
   queue_push(queue, queue_count, alive, i);
