@@ -2000,8 +2000,30 @@ __global__ void __launch_bounds__(256) k_trace_closest_wide(const __grid_constan
 // The shadow segments of one bounce (ShadowBatch, atomic mode): any-hit on the same persistent, nodelet-staged, lane-refilled walk; a segment
 // that reaches its end adds its contribution to its target (a path's gathered sum, or a pixel of the light image).  Opaque scenes only: any
 // non-Void surface on the segment occludes (rt.cxx:468-579 without Boundary crossings).
+// Experiment (ETXB_SHADOW_SORT=1, default off): order of the bounce's shadow list by the Morton code of the segments' origins, so that the rays a warp
+// of k_shadow_resolve walks together start in the same region of the tree.  keys[i] for the `upper` slots the host sorts (its upper bound of the
+// device-side count): 30-bit Morton code inside the scene's bounding cube, 0xffffffff past the count; vals[i] = i.
+__global__ void __launch_bounds__(256) k_shadow_keys(const __grid_constant__ LaunchParams p, uint32_t upper, uint32_t* keys, uint32_t* vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= upper) return;
+  const uint32_t count = umin(p.shadow_count[0], p.shadow_capacity);
+  uint32_t key = 0xffffffffu;
+  if (i < count) {
+    float4 a = p.shadow_p0[i];
+    const float r = p.scene.bounding_sphere_radius;
+    const V3 c = p.scene.bounding_sphere_center;
+    const float scale = 1024.0f / fmaxf(2.0f * r, 1e-20f);
+    uint32_t x = umin(uint32_t(fmaxf((a.x - (c.x - r)) * scale, 0.0f)), 1023u);
+    uint32_t y = umin(uint32_t(fmaxf((a.y - (c.y - r)) * scale, 0.0f)), 1023u);
+    uint32_t z = umin(uint32_t(fmaxf((a.z - (c.z - r)) * scale, 0.0f)), 1023u);
+    key = morton_part(x) | (morton_part(y) << 1) | (morton_part(z) << 2);
+  }
+  keys[i] = key;
+  vals[i] = i;
+}
+
 template <bool WIDE>
-__global__ void __launch_bounds__(kTraversalBlock) k_shadow_resolve(const __grid_constant__ LaunchParams p, uint32_t* cursor) {
+__global__ void __launch_bounds__(kTraversalBlock) k_shadow_resolve(const __grid_constant__ LaunchParams p, uint32_t* cursor, const uint32_t* order) {
   // 32 KB of shared memory: the top kNodeletNodes nodes of the tree this instantiation walks (both node types are 64 bytes)
   __shared__ __align__(128) BvhNode s_nodes[kNodeletNodes];
   __shared__ __align__(8) uint64_t s_bar;
@@ -2036,7 +2058,7 @@ __global__ void __launch_bounds__(kTraversalBlock) k_shadow_resolve(const __grid
   for (;;) {
     uint32_t next = 0;
     if (warp_refill(!active, cursor, total, next, exhausted)) {
-      k = next;
+      k = (order != nullptr) ? order[next] : next;
       float4 a = p.shadow_p0[k], b = p.shadow_p1[k];
       target = reinterpret_cast<const uint32_t*>(p.shadow_p1 + k)[3];  // raw bits (see ShadowBatch::push_rgb)
       V3 direction = V3{b.x, b.y, b.z} - V3{a.x, a.y, a.z};

@@ -109,6 +109,7 @@ struct etxb_ctx {
   bool plain_scene = false;           // set at upload: the scene qualifies
   bool opaque_scene = false;          // set at upload: no alpha test can reject a hit (every opacity 1, no alpha images), no Boundary surfaces / media
   bool shadow_atomic = true;          // product build, opaque scenes with stochastic BSDFs: shadow segments resolved by k_shadow_resolve (ETXB_SHADOW_ATOMIC=0: inline)
+  bool shadow_sort = false;           // experiment (ETXB_SHADOW_SORT=1): long shadow lists are walked in the Morton order of the segments' origins
   bool persistent_trace = false;      // closest hits on the persistent, nodelet-staged, lane-refilled kernel (ETXB_TRACE_PERSISTENT=1).  Measured on the B200 (C3,
                                       // round 2): 27.1 ms per iteration against 22.9 ms for the thread-per-ray kernel — one ray per path leaves little to refill
                                       // from, and the walk's dynamic stack costs the same either way — so the default stays thread-per-ray; the shadow segments
@@ -462,14 +463,25 @@ int launch_trace_closest(etxb_ctx* ctx, const LaunchParams& p, const uint32_t* q
   }
   return ETXB_OK;
 }
-// the bounce's shadow segments (ShadowBatch, atomic mode): traced and added to their targets
-int launch_shadow_resolve(etxb_ctx* ctx, const LaunchParams& p, uint32_t active) {
+// the bounce's shadow segments (ShadowBatch, atomic mode): traced and added to their targets.  seg_upper: the host's upper bound of the number of
+// segments (0: unknown) — with ETXB_SHADOW_SORT=1 a long list is walked in the Morton order of the segments' origins (experiment, default off)
+constexpr uint32_t kShadowSortMin = 1u << 16;
+int launch_shadow_resolve(etxb_ctx* ctx, const LaunchParams& p, uint32_t active, uint64_t seg_upper = 0) {
+  const uint32_t* order = nullptr;
+  if (ctx->shadow_sort && (seg_upper >= kShadowSortMin) && (seg_upper <= ctx->keys_in.count) && (seg_upper <= p.shadow_capacity)) {
+    const uint32_t upper = uint32_t(seg_upper);
+    k_shadow_keys<<<blocks_for(upper, 256), 256, 0, ctx->stream>>>(p, upper, ctx->keys_in.ptr, ctx->vals_in.ptr);
+    size_t temp_bytes = ctx->cub_temp.bytes();
+    CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->keys_in.ptr, ctx->keys_out.ptr, ctx->vals_in.ptr, ctx->vals_out.ptr, int(upper), 0, 30, ctx->stream));
+    order = ctx->vals_out.ptr;
+    ctx->kernel_launches += 1;
+  }
   CUDA_OK(ctx, cudaMemsetAsync(ctx->trace_cursor.ptr + 1, 0, 4, ctx->stream));
   const uint32_t blocks = std::min<uint32_t>(blocks_for(std::min<uint64_t>(uint64_t(active) * 4ull, 0x7fffffffull), kTraversalBlock), 148u);
   if (p.scene.wide_nodes != nullptr) {
-    k_shadow_resolve<true><<<blocks, kTraversalBlock, 0, ctx->stream>>>(p, ctx->trace_cursor.ptr + 1);
+    k_shadow_resolve<true><<<blocks, kTraversalBlock, 0, ctx->stream>>>(p, ctx->trace_cursor.ptr + 1, order);
   } else {
-    k_shadow_resolve<false><<<blocks, kTraversalBlock, 0, ctx->stream>>>(p, ctx->trace_cursor.ptr + 1);
+    k_shadow_resolve<false><<<blocks, kTraversalBlock, 0, ctx->stream>>>(p, ctx->trace_cursor.ptr + 1, order);
   }
   return ETXB_OK;
 }
@@ -513,7 +525,7 @@ int run_light_pass(etxb_ctx* ctx) {
     if (p.shadow_atomic) {
       // the light-to-camera connections of this bounce: segments -> splats (light image)
       LaunchTimer t(ctx, K_SHADOW_TRACE);
-      if (int rc = launch_shadow_resolve(ctx, p, active)) return rc;
+      if (int rc = launch_shadow_resolve(ctx, p, active, active)) return rc;
     }
     cur ^= 1u;
     std::swap(qin, qout);
@@ -662,6 +674,7 @@ int run_camera_pass(etxb_ctx* ctx) {
       uint32_t blocks = std::min<uint32_t>(148u * 8u, blocks_for(std::min<uint64_t>(uint64_t(active) * 32ull, 0x7fffffffull), 256));
       k_shadow_trace<<<blocks, 256, 0, ctx->stream>>>(p);
     }
+    uint64_t shadow_upper = 0;  // host-side upper bound of this bounce's shadow list (0 = not known: the tail keeps its counts on the device)
     if (p.connect_stage && (ctx->options.options & ETXB_VCM_CONNECT_VERTICES)) {
       if (active < kTailQueue) {
         // tail of the pass: the pair count stays on the device (k_camera_connect is grid-stride), no host round trip per bounce
@@ -676,6 +689,7 @@ int run_camera_pass(etxb_ctx* ctx) {
         uint32_t pending = 0;
         if (int rc = read_u32(ctx, ctx->conn_count.ptr, pending)) return rc;
         pending = std::min(pending, ctx->lv_capacity);
+        shadow_upper = uint64_t(pending) + active;  // one segment per vertex connection + one emitter segment per path
         if (pending) {
           const uint2* list = ctx->conn_list.ptr;
           if (p.conn_key && (pending >= kSortQueueMin)) {
@@ -698,7 +712,7 @@ int run_camera_pass(etxb_ctx* ctx) {
     if (p.shadow_atomic) {
       // emitter-sample and vertex-connection segments of this bounce: traced, the unoccluded ones added to their paths' gathered sums
       LaunchTimer t(ctx, K_SHADOW_TRACE);
-      if (int rc = launch_shadow_resolve(ctx, p, active)) return rc;
+      if (int rc = launch_shadow_resolve(ctx, p, active, shadow_upper)) return rc;
     }
 #if defined(ETXB_PARITY) && ETXB_PARITY
     if (merging) {
@@ -941,7 +955,7 @@ int run_pt_iteration(etxb_ctx* ctx) {
     }
     if (p.shadow_atomic) {
       LaunchTimer t(ctx, K_SHADOW_TRACE);
-      if (int rc = launch_shadow_resolve(ctx, p, active)) return rc;
+      if (int rc = launch_shadow_resolve(ctx, p, active, active)) return rc;
     }
     cur ^= 1u;
     std::swap(qin, qout);
@@ -992,6 +1006,7 @@ int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
   if (const char* e = getenv("ETXB_PLAIN_KERNELS")) ctx->plain_kernels = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_MATERIAL_MAJOR")) ctx->merge_material_major = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_TILED")) ctx->merge_tiled = (e[0] != '0');
+  if (const char* e = getenv("ETXB_SHADOW_SORT")) ctx->shadow_sort = (e[0] != '0');
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return ETXB_ERR_CUDA;
@@ -1459,7 +1474,7 @@ int etxb_upload_scene(etxb_ctx* ctx, const void* scene_blob, uint64_t scene_byte
     ctx->shadow_result.release();
   }
   // the sort buffers also hold the gather queue and the path queues (up to one entry per path), whatever the configured pool capacity
-  const uint64_t sort_cap = std::max<uint64_t>(cap, n);
+  const uint64_t sort_cap = std::max<uint64_t>(cap, n) + ((ctx->shadow_sort && atomic_candidate) ? n : 0);
   DevBuf<uint32_t>* per_vertex_u32[] = {&ctx->keys_in, &ctx->keys_out, &ctx->vals_in, &ctx->vals_out};
   for (auto* b : per_vertex_u32) CUDA_OK(ctx, b->alloc(sort_cap));
   DevBuf<float4>* per_vertex_f4[] = {&ctx->g_pos, &ctx->g_nrm, &ctx->g_win, &ctx->g_thr};
