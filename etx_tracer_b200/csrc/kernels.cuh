@@ -98,6 +98,8 @@ struct LaunchParams {
                                  //    light-to-camera connections go to the shadow list with their target address; k_shadow_resolve adds the unoccluded ones
   uint32_t closures;             // 1 (product build): connections and the generic gather evaluate vertex closures (dclosure.cuh); 0: A/B switch
   uint32_t merge_material_major; // 1: the gather queue is ordered by (material, Morton code) instead of the Morton code alone (ETXB_MERGE_MATERIAL_MAJOR=1)
+  uint32_t spatial_keys;         // 1 (experiment, ETXB_QUEUE_SORT_SPATIAL=1): the path-queue sort key is (hit material, Morton code of the hit point) instead of the
+                                 //    material alone — the next bounce's rays then start from neighbouring points in neighbouring queue slots
   uint32_t connect_deferred;     // 1 (needs shadow_stage): the camera-vertex x light-vertex connections of such a scene run one per thread in
                                  //    k_camera_connect_deferred — conn_list[slot] names the (path, light vertex) pair that fills shadow slot `slot`
 };
@@ -207,13 +209,36 @@ __global__ void __launch_bounds__(128) k_light_begin(const __grid_constant__ Lau
   queue_push(queue, queue_count, alive, i);
 }
 
+// Sort key of a queue slot after its closest-hit query: the hit material (0xff = miss; 0x100 = slot past the device-side count, sorts last); with
+// p.spatial_keys the material moves to bits 23-31 and bits 0-22 hold the top of the 30-bit Morton code of the hit point inside the scene's bounding cube
+constexpr uint32_t kQueueKeyPastCount = 0x100u;
+DEV uint32_t spread10(uint32_t v) {
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+DEV uint32_t queue_sort_key(const LaunchParams& p, uint32_t tri, float4 o, float4 d, float t) {
+  const uint32_t material = (tri == kInvalidIndex) ? 0xffu : umin(load_triangle_material(p.scene, tri), 0xfeu);
+  if (!p.spatial_keys) return material;
+  const float r = p.scene.bounding_sphere_radius, s = 1024.0f / fmaxf(2.0f * r, 1e-20f);
+  const float tt = (tri == kInvalidIndex) ? 0.0f : t;
+  const V3 c = p.scene.bounding_sphere_center;
+  uint32_t x = umin(uint32_t(fmaxf((o.x + d.x * tt - (c.x - r)) * s, 0.0f)), 1023u);
+  uint32_t y = umin(uint32_t(fmaxf((o.y + d.y * tt - (c.y - r)) * s, 0.0f)), 1023u);
+  uint32_t z = umin(uint32_t(fmaxf((o.z + d.z * tt - (c.z - r)) * s, 0.0f)), 1023u);
+  return (material << 23) | ((spread10(x) | (spread10(y) << 1) | (spread10(z) << 2)) >> 7);
+}
+DEV uint32_t queue_key_past_count(const LaunchParams& p) { return p.spatial_keys ? (kQueueKeyPastCount << 23) : kQueueKeyPastCount; }
+
 // closest-hit traversal for every queued path (Raytracing::trace, rt.cxx:428): SoA ray in, hit record out,
 // sampler advanced by one draw per candidate
 __global__ void __launch_bounds__(256) k_trace_closest(const __grid_constant__ LaunchParams p, const uint32_t* queue, const uint32_t* queue_count, uint32_t* material_keys, uint32_t key_limit) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= *queue_count) {
     // the host sorts `key_limit` (its upper bound of the queue size) slots by material: slots past the device-side count sort last
-    if ((material_keys != nullptr) && (q < key_limit)) material_keys[q] = 0x100u;
+    if ((material_keys != nullptr) && (q < key_limit)) material_keys[q] = queue_key_past_count(p);
     return;
   }
   uint32_t i = queue[q];
@@ -227,7 +252,7 @@ __global__ void __launch_bounds__(256) k_trace_closest(const __grid_constant__ L
   p.paths.hit[i] = make_float4(h.u, h.v, h.t, __uint_as_float(h.tri));
   p.paths.misc[i].x = smp.seed;
   // the bounce kernels' cost is the BSDF class of the surface that was hit: paths are grouped by material before they are shaded
-  if (material_keys != nullptr) material_keys[q] = (h.tri == kInvalidIndex) ? 0xffu : umin(load_triangle_material(p.scene, h.tri), 0xfeu);
+  if (material_keys != nullptr) material_keys[q] = queue_sort_key(p, h.tri, o, d, h.t);
   counter_add(&p.counters->rays_closest, 1u);
   counter_add(&p.counters->nodes, STATS_NODES);
   counter_add(&p.counters->tris, STATS_TRIS);
@@ -1919,7 +1944,7 @@ __global__ void __launch_bounds__(kTraversalBlock) k_trace_closest_persistent(co
   const uint32_t total = *queue_count;
   // the host sorts `key_limit` (its upper bound of the queue size) slots by material: slots past the device-side count sort last
   if (material_keys != nullptr) {
-    for (uint32_t q = total + blockIdx.x * blockDim.x + threadIdx.x; q < key_limit; q += gridDim.x * blockDim.x) material_keys[q] = 0x100u;
+    for (uint32_t q = total + blockIdx.x * blockDim.x + threadIdx.x; q < key_limit; q += gridDim.x * blockDim.x) material_keys[q] = queue_key_past_count(p);
   }
   bool active = false, exhausted = false;
   uint32_t q = 0, i = 0, n_nodes = 0, n_tris = 0, rays = 0;
@@ -1947,7 +1972,7 @@ __global__ void __launch_bounds__(kTraversalBlock) k_trace_closest_persistent(co
       if (walk_step(walk, stack, nodes, p.scene.bvh_tris, visit, n_nodes, n_tris)) {
         p.paths.hit[i] = make_float4(best.u, best.v, best.t, __uint_as_float(best.tri));
         p.paths.misc[i].x = smp.seed;
-        if (material_keys != nullptr) material_keys[q] = (best.tri == kInvalidIndex) ? 0xffu : umin(load_triangle_material(p.scene, best.tri), 0xfeu);
+        if (material_keys != nullptr) material_keys[q] = queue_sort_key(p, best.tri, p.paths.ray_o[i], p.paths.ray_d[i], best.t);
         active = false;
       } else if (!exhausted && (__popc(__activemask()) < kRefillLanes)) {
         break;  // too few lanes left in this walk: go and fetch rays for the idle ones
@@ -1968,7 +1993,7 @@ __global__ void __launch_bounds__(256) k_trace_closest_wide(const __grid_constan
                                                             uint32_t key_limit) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= *queue_count) {
-    if ((material_keys != nullptr) && (q < key_limit)) material_keys[q] = 0x100u;
+    if ((material_keys != nullptr) && (q < key_limit)) material_keys[q] = queue_key_past_count(p);
     return;
   }
   uint32_t i = queue[q];
@@ -1987,7 +2012,7 @@ __global__ void __launch_bounds__(256) k_trace_closest_wide(const __grid_constan
   }
   p.paths.hit[i] = make_float4(best.u, best.v, best.t, __uint_as_float(best.tri));
   p.paths.misc[i].x = smp.seed;
-  if (material_keys != nullptr) material_keys[q] = (best.tri == kInvalidIndex) ? 0xffu : umin(load_triangle_material(p.scene, best.tri), 0xfeu);
+  if (material_keys != nullptr) material_keys[q] = queue_sort_key(p, best.tri, o, d, best.t);
   counter_add(&p.counters->rays_closest, 1u);
 #ifdef ETXB_COUNT_TRAVERSAL
   counter_add(&p.counters->nodes, n_nodes);

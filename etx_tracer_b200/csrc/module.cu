@@ -109,6 +109,7 @@ struct etxb_ctx {
   bool plain_scene = false;           // set at upload: the scene qualifies
   bool opaque_scene = false;          // set at upload: no alpha test can reject a hit (every opacity 1, no alpha images), no Boundary surfaces / media
   bool shadow_atomic = true;          // product build, opaque scenes with stochastic BSDFs: shadow segments resolved by k_shadow_resolve (ETXB_SHADOW_ATOMIC=0: inline)
+  bool queue_sort_spatial = false;    // experiment (ETXB_QUEUE_SORT_SPATIAL=1): path queues sorted by (hit material, Morton code of the hit point)
   bool shadow_sort = false;           // experiment (ETXB_SHADOW_SORT=1): long shadow lists are walked in the Morton order of the segments' origins
   bool persistent_trace = false;      // closest hits on the persistent, nodelet-staged, lane-refilled kernel (ETXB_TRACE_PERSISTENT=1).  Measured on the B200 (C3,
                                       // round 2): 27.1 ms per iteration against 22.9 ms for the thread-per-ray kernel — one ray per path leaves little to refill
@@ -387,6 +388,7 @@ LaunchParams make_params(etxb_ctx* ctx) {
 #endif
   p.closures = ctx->merge_closure ? 1u : 0u;
   p.merge_material_major = (ctx->merge_material_major && ctx->has_stochastic_merge) ? 1u : 0u;
+  p.spatial_keys = ctx->queue_sort_spatial ? 1u : 0u;
 #if defined(ETXB_PARITY) && ETXB_PARITY
   p.connect_stage = 0;
 #else
@@ -444,8 +446,8 @@ constexpr uint32_t kSortQueueMin = 1024u;
 inline bool sorts_queue(const etxb_ctx* ctx, uint32_t active) { return ctx->sort_by_material && ctx->has_stochastic_merge && (active >= kSortQueueMin) && ctx->queue_sorted.count; }
 int sort_queue_by_material(etxb_ctx* ctx, const uint32_t* queue, uint32_t active, const uint32_t** sorted) {
   size_t temp_bytes = ctx->cub_temp.bytes();
-  CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->queue_keys.ptr, ctx->queue_keys_sorted.ptr, queue, ctx->queue_sorted.ptr, int(active), 0, 9,
-                 ctx->stream));
+  CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp.ptr, temp_bytes, ctx->queue_keys.ptr, ctx->queue_keys_sorted.ptr, queue, ctx->queue_sorted.ptr, int(active), 0,
+                 ctx->queue_sort_spatial ? 32 : 9, ctx->stream));
   *sorted = ctx->queue_sorted.ptr;
   return ETXB_OK;
 }
@@ -1007,6 +1009,7 @@ int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
   if (const char* e = getenv("ETXB_MERGE_MATERIAL_MAJOR")) ctx->merge_material_major = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_TILED")) ctx->merge_tiled = (e[0] != '0');
   if (const char* e = getenv("ETXB_SHADOW_SORT")) ctx->shadow_sort = (e[0] != '0');
+  if (const char* e = getenv("ETXB_QUEUE_SORT_SPATIAL")) ctx->queue_sort_spatial = (e[0] != '0');
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return ETXB_ERR_CUDA;
