@@ -171,6 +171,7 @@ struct etxb_ctx {
   uint32_t integrator = ETXB_INTEGRATOR_VCM;
   etxb_pt_options pt_options = {1u, 1u, 1u, 1u};
   DevBuf<float4> film_normals, film_albedo, film_adaptive;  // Film's Normals / Albedo / CameraAdaptive layers (allocated with the first PT run)
+  DevBuf<uint32_t> film_ldr;                                 // the tone-mapped RGBA8 frame of etxb_read_film_ldr
   DevBuf<uint32_t> pt_info, pt_info_next, pt_stats;          // InternalData (sample count, converged, tmp); [converged this pass, error sum bits]
   DevBuf<float> pt_error;
   uint32_t pixel_sampler_image = 0xffffffffu;
@@ -1091,6 +1092,7 @@ void etxb_destroy(etxb_ctx* ctx) {
   ctx->bs_props.release();
   ctx->bs_weight_pdf.release();
   ctx->bs_wo_eta.release();
+  ctx->film_ldr.release();
   ctx->film_normals.release();
   ctx->film_albedo.release();
   ctx->film_adaptive.release();
@@ -1910,8 +1912,9 @@ int etxb_read_film_ldr(etxb_ctx* ctx, uint32_t layer, float exposure, uint8_t* d
   if (ctx->scene_ready && (dst_bytes < n * 4)) return fail(ctx, ETXB_ERR_INVALID_ARGUMENT, "film buffer too small");
   const float4* src = nullptr;
   if (int rc = film_layer_source(ctx, layer, &src)) return rc;
-  // keys_out is free between iterations (the context is drained: the layer was just resolved on this stream) and holds at least one word per pixel
-  uint32_t* packed = ctx->keys_out.ptr;
+  // a buffer of its own: a preview may be taken while an iteration is in flight on this stream, whose scratch buffers must stay untouched
+  if (ctx->film_ldr.count != n) CUDA_OK(ctx, ctx->film_ldr.alloc(n));
+  uint32_t* packed = ctx->film_ldr.ptr;
   k_film_tonemap<<<blocks_for(ctx->path_count, 256), 256, 0, ctx->stream>>>(src, packed, ctx->path_count, exposure);
   ctx->kernel_launches += 1;
   CUDA_OK(ctx, cudaMemcpyAsync(dst_rgba8, packed, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
