@@ -74,12 +74,62 @@ def scene_factory(args, res):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons of this rank's GPU during the timed region (B200_PROFILING.md).  Read through NVML in-process (what nvidia-smi itself
+    reads): the library is initialised when the sampler is CONSTRUCTED — well before the timed region — and a sample is four cheap calls on one device.
+    The former `nvidia-smi -lms 100` child process is the fallback; on an 8-GPU box its start-up (NVML initialisation over every GPU) fell INSIDE the
+    0.3 s timed region and held the driver long enough to cost the N = 8 line ~15 % (value 150 against an end-to-end 174 Msamples/s in the same run)."""
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.handle, self.nvml, self.running = [], None, index, None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.handle = pynvml, handle
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        try:
+            reasons = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            try:
+                reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            except Exception:
+                reasons = 0
+        flags = []
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            flags.append("Active" if (reasons & bit) else "Not Active")
+        flags = [flags[0], flags[3], flags[2], flags[1]]  # the order of the nvidia-smi query below
+        def safe(fn, default):
+            try:
+                return fn()
+            except Exception:
+                return default
+        return [str(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), str(safe(lambda: n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM), 0)),
+                str(safe(lambda: n.nvmlDeviceGetPowerUsage(h) / 1000.0, 0.0))] + flags
+
+    def _poll(self):
+        while self.running:
+            try:
+                self.rows.append(self._sample_nvml())
+            except Exception:
+                pass
+            time.sleep(0.025)
 
     def start(self):
+        if self.nvml is not None:
+            self.running = True
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -92,10 +142,11 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        self.running = False
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        for r in list(self.rows):
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -104,7 +155,15 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        if (self.nvml is not None) and not sm:  # never leave the line without a clocks reading: one direct query after the region
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+                a, b = [float(x) for x in out.strip().split(",")[:2]]
+                sm, mx = [a], b
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml (in-process)" if self.nvml is not None else "nvidia-smi -lms 100"}
 
 
 def measured_peaks():
@@ -283,6 +342,7 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--res", type=int, default=0, help="override the film size (debug only; the default is the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split-leftover", action="store_true", help="iteration mode: split the K %% N left-over iterations by camera tile over N / (K %% N) ranks each (A/B switch)")
     ap.add_argument("--no-path-tracer", action="store_true", help="skip the extra `path_tracer` key (the second device integrator on the same workload, N = 1 only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--lanes", type=int, default=4, help="iterations in flight per GPU (etxb_group); 1 = the plain one-context pump")
@@ -349,12 +409,16 @@ def main():
         # tile mode: two iterations in flight per GPU (measured at N = 2: 30.7 Msamples/s with 2, 15.1 with 4 — every lane has two rendezvous with
         # its peers per iteration, and four lanes' collectives wait on each other across the ranks)
         mode_lanes = min(lanes, 2) if mode == "tile" else lanes
-        # iteration mode: one more lane, reserved for camera-split iterations (the remainder when K is not a multiple of the GPUs)
-        g = GPUVCMGroup(sd, lanes=mode_lanes + (1 if mode == "iteration" else 0), flavor="fast", device=local_rank, profile=True)
+        # iteration mode with --split-leftover: one more lane, reserved for camera-split iterations (the remainder when K is not a multiple of the GPUs).
+        # Measured at N = 8, K = 20 (profiles/r2g_n8.json against r2o_n8.json): 13.49 ms per step with the left-over 4 iterations dealt whole (3, 3, 3, 3, 2,
+        # 2, 2, 2), 13.79 with each of them split over two ranks — a camera-split half costs ~0.9 of an iteration (full light pass, the bounce tails do not
+        # shrink with the pixel count) — so the default deals whole iterations only.
+        split = (mode == "iteration") and args.split_leftover
+        g = GPUVCMGroup(sd, lanes=mode_lanes + (1 if split else 0), flavor="fast", device=local_rank, profile=True)
         if mode == "tile":
             g.comm_init(world, rank, distribute_comm_ids(dist, rank, mode_lanes + 1, comm_unique_ids, device=device))
         elif mode == "iteration":
-            g.comm_init_replicas(world, rank, distribute_comm_ids(dist, rank, 1, comm_unique_ids, device=device), split_lane=True)
+            g.comm_init_replicas(world, rank, distribute_comm_ids(dist, rank, 1, comm_unique_ids, device=device), split_lane=split)
         g.options[:] = workload_vcm_options(args)
         multi = mode != "single"
         warm = args.warmup * (world if mode == "iteration" else 1)  # every rank warms up on `warmup` iterations of its own
@@ -365,6 +429,7 @@ def main():
             else:
                 g.film(S.FILM_RESULT, out=out)
 
+        clocks = ClockSampler(local_rank) if rank == 0 else None  # NVML is initialised here, outside every timed region
         # ---- device-resident timing: warm-up on indices 0.., then the timed index set W .. W+K-1 from a cleared film
         g.run(0)
         g.enqueue(warm)
@@ -372,7 +437,6 @@ def main():
         sync_all()
         g.run(args.warmup)
         c0, k0 = g.counters(), g.kernel_times()
-        clocks = ClockSampler(local_rank)
         if rank == 0:
             clocks.start()
         g.enqueue(args.steps)
@@ -550,8 +614,9 @@ def main():
                            "parallelism": {"single": f"one GPU, {lanes} iterations in flight",
                                            "tile": f"pixel tiles (32x32, round-robin) over {world} GPUs inside the module, {min(lanes, 2)} iterations in flight per GPU; per iteration "
                                                    f"ncclAllReduce of the light image + all-gather of the photon records, per frame ncclReduce of the film",
-                                           "iteration": f"the job's iterations dealt to {world} GPUs (index j on rank j % {world}; the K % {world} left over are split by camera tile, each "
-                                                        f"part tracing the whole light pass itself), {lanes} in flight per GPU; per frame one count-weighted ncclReduce of the films"}[best["mode"]],
+                                           "iteration": f"the job's iterations dealt to {world} GPUs (index j on rank j % {world}"
+                                                        + ("; the K % N left over are split by camera tile, each part tracing the whole light pass itself" if args.split_leftover else "")
+                                                        + f"), {lanes} in flight per GPU; per frame one count-weighted ncclReduce of the films"}[best["mode"]],
                            "mode": best["mode"],
                            "collective": None if world == 1 else "NCCL (communicators created inside the module: etxb_group_comm_init / etxb_group_comm_init_replicas)",
                            "collective_ms_per_iteration": best["collective_ms_per_iteration"],
