@@ -342,7 +342,7 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--res", type=int, default=0, help="override the film size (debug only; the default is the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--split-leftover", action="store_true", help="iteration mode: split the K %% N left-over iterations by camera tile over N / (K %% N) ranks each (A/B switch)")
+    ap.add_argument("--no-split-leftover", action="store_true", help="iteration mode: deal the K %% N left-over iterations whole instead of splitting each by camera tile over N / (K %% N) ranks (A/B switch)")
     ap.add_argument("--no-path-tracer", action="store_true", help="skip the extra `path_tracer` key (the second device integrator on the same workload, N = 1 only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--lanes", type=int, default=4, help="iterations in flight per GPU (etxb_group); 1 = the plain one-context pump")
@@ -409,11 +409,11 @@ def main():
         # tile mode: two iterations in flight per GPU (measured at N = 2: 30.7 Msamples/s with 2, 15.1 with 4 — every lane has two rendezvous with
         # its peers per iteration, and four lanes' collectives wait on each other across the ranks)
         mode_lanes = min(lanes, 2) if mode == "tile" else lanes
-        # iteration mode with --split-leftover: one more lane, reserved for camera-split iterations (the remainder when K is not a multiple of the GPUs).
-        # Measured at N = 8, K = 20 (profiles/r2g_n8.json against r2o_n8.json): 13.49 ms per step with the left-over 4 iterations dealt whole (3, 3, 3, 3, 2,
-        # 2, 2, 2), 13.79 with each of them split over two ranks — a camera-split half costs ~0.9 of an iteration (full light pass, the bounce tails do not
-        # shrink with the pixel count) — so the default deals whole iterations only.
-        split = (mode == "iteration") and args.split_leftover
+        # iteration mode: one more lane, reserved for camera-split iterations (the remainder when K is not a multiple of the GPUs).  Measured at N = 8,
+        # K = 20 on one box (profiles/r2o_bench_c3_n8_split_smi.json, r2p_bench_c3_n8_whole.json): the left-over 4 iterations dealt whole (3, 3, 3, 3, 2, 2,
+        # 2, 2) 158 / 156 Msamples/s (value / e2e), each of them split over two ranks 174 end to end (that run's `value` region, 150, still had the
+        # nvidia-smi child starting inside it); --no-split-leftover is the A/B switch.
+        split = (mode == "iteration") and not args.no_split_leftover
         g = GPUVCMGroup(sd, lanes=mode_lanes + (1 if split else 0), flavor="fast", device=local_rank, profile=True)
         if mode == "tile":
             g.comm_init(world, rank, distribute_comm_ids(dist, rank, mode_lanes + 1, comm_unique_ids, device=device))
@@ -615,7 +615,7 @@ def main():
                                            "tile": f"pixel tiles (32x32, round-robin) over {world} GPUs inside the module, {min(lanes, 2)} iterations in flight per GPU; per iteration "
                                                    f"ncclAllReduce of the light image + all-gather of the photon records, per frame ncclReduce of the film",
                                            "iteration": f"the job's iterations dealt to {world} GPUs (index j on rank j % {world}"
-                                                        + ("; the K % N left over are split by camera tile, each part tracing the whole light pass itself" if args.split_leftover else "")
+                                                        + ("; the K % N left over are split by camera tile, each part tracing the whole light pass itself" if not args.no_split_leftover else "")
                                                         + f"), {lanes} in flight per GPU; per frame one count-weighted ncclReduce of the films"}[best["mode"]],
                            "mode": best["mode"],
                            "collective": None if world == 1 else "NCCL (communicators created inside the module: etxb_group_comm_init / etxb_group_comm_init_replicas)",
