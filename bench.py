@@ -75,9 +75,8 @@ def scene_factory(args, res):
 
 class ClockSampler:
     """SM clock + throttle reasons of this rank's GPU during the timed region (B200_PROFILING.md).  Read through NVML in-process (what nvidia-smi itself
-    reads): the library is initialised when the sampler is CONSTRUCTED — well before the timed region — and a sample is four cheap calls on one device.
-    The former `nvidia-smi -lms 100` child process is the fallback; on an 8-GPU box its start-up (NVML initialisation over every GPU) fell INSIDE the
-    0.3 s timed region and held the driver long enough to cost the N = 8 line ~15 % (value 150 against an end-to-end 174 Msamples/s in the same run)."""
+    reads): the library is initialised when the sampler is CONSTRUCTED — before the warm-up, outside every timed region — and a sample is four cheap calls
+    on one device; no child process starts inside a timed region that is only 0.3 s long at N = 8.  `nvidia-smi -lms 100` is the fallback."""
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index, self.handle, self.nvml, self.running = [], None, index, None, None, False
@@ -410,9 +409,10 @@ def main():
         # its peers per iteration, and four lanes' collectives wait on each other across the ranks)
         mode_lanes = min(lanes, 2) if mode == "tile" else lanes
         # iteration mode: one more lane, reserved for camera-split iterations (the remainder when K is not a multiple of the GPUs).  Measured at N = 8,
-        # K = 20 on one box (profiles/r2o_bench_c3_n8_split_smi.json, r2p_bench_c3_n8_whole.json): the left-over 4 iterations dealt whole (3, 3, 3, 3, 2, 2,
-        # 2, 2) 158 / 156 Msamples/s (value / e2e), each of them split over two ranks 174 end to end (that run's `value` region, 150, still had the
-        # nvidia-smi child starting inside it); --no-split-leftover is the A/B switch.
+        # K = 20 (profiles/r2o_*, r2p_*, r2q_*): the left-over 4 iterations dealt whole (3, 3, 3, 3, 2, 2, 2, 2) 158 / 156 Msamples/s (value / e2e); each of
+        # them split over two ranks 174 end to end, but 150 in the `value` region of those runs — the region in which the split lane rendered its FIRST
+        # iteration (it created its few thousand timing events there).  The events now exist from etxb_create, and the warm-up below exercises the split
+        # lane on the same left-over geometry.  --no-split-leftover is the A/B switch.
         split = (mode == "iteration") and not args.no_split_leftover
         g = GPUVCMGroup(sd, lanes=mode_lanes + (1 if split else 0), flavor="fast", device=local_rank, profile=True)
         if mode == "tile":
@@ -422,6 +422,8 @@ def main():
         g.options[:] = workload_vcm_options(args)
         multi = mode != "single"
         warm = args.warmup * (world if mode == "iteration" else 1)  # every rank warms up on `warmup` iterations of its own
+        if split:
+            warm += args.steps % world  # ... and the camera-split lane on the left-over geometry it will render in the timed region
 
         def film_to_host(out):
             if multi:

@@ -999,6 +999,16 @@ int etxb_create(etxb_ctx** out_ctx, const etxb_device_config* cfg) {
   ctx->device = device;
   ctx->max_light_vertices_cfg = cfg ? cfg->max_light_vertices : 0;
   ctx->profile = cfg ? (cfg->flags & 1u) != 0 : false;
+  if (ctx->profile) {
+    // the per-launch timing events of an iteration (two per launch, a few thousand per iteration) exist from the start: a lane that renders its first
+    // iteration inside a timed region (the camera-split lane of the replica mode) must not pay for creating them there
+    ctx->event_pool.reserve(8192);
+    for (uint32_t k = 0; k < 6144u; ++k) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess) break;
+      ctx->event_pool.push_back(e);
+    }
+  }
   if (const char* e = getenv("ETXB_CONNECT_DEFERRED")) ctx->connect_deferred = (e[0] != '0');
   if (const char* e = getenv("ETXB_SORT_MATERIAL")) ctx->sort_by_material = (e[0] != '0');
   if (const char* e = getenv("ETXB_MERGE_BATCHED")) ctx->merge_batched = (e[0] != '0');
