@@ -9,7 +9,7 @@ Everything is built on `scenes.SceneData` (the same record builders the syntheti
 result with the reference's own loader (compiled in place as test infrastructure) array by array on the shipped Cornell asset and on
 generated scene files.  Known differences, all stated there: tangent frames of meshes WITH texture coordinates come from per-triangle UV
 derivatives instead of MikkTSpace (only normal maps and anisotropic roughness see them); `et::atmosphere` (the procedural sun + sky images,
-host/scattering.cxx) and NanoVDB volumes are refused; image files: PNG (8-bit, non-interlaced) and OpenEXR (float, scan lines, none / ZIP).
+host/scattering.cxx) and NanoVDB volumes are refused; image files: PNG (8-bit, non-interlaced), OpenEXR (float, scan lines, none / ZIP), Radiance HDR and the reference's PFM variant.
 The .mtl reader follows the reference's patched tinyobjloader (thirdparty/tinyobjloader/tiny_obj_loader.hxx:1900-2190): names are lower-cased,
 `Kd / Ks / Kt / Ke` and every non-standard key land in the material's parameter list, the standard texture keys are consumed.
 """
@@ -234,6 +234,19 @@ def spd_from_samples(samples):
     return spd_from_power(power)
 
 
+def subsurface_remap(color, distances):
+    """subsurface::remap (render/shared/scene_bssrdf_subsurface.hxx:17-44) per channel, float32."""
+    a, b, c = f32(1.826052378200), f32(f32(4.985111943850) + f32(0.12735595943800)), f32(1.096861024240)
+    d, e, f = f32(0.496310210422), f32(f32(4.231902997010) + f32(0.00310603949088)), f32(2.406029994080)
+    color = np.maximum(f32(0.0), np.asarray(color, dtype=f32))
+    blend = np.power(color, f32(0.25)).astype(f32)
+    albedo = ((f32(1.0) - blend).astype(f32) * a * np.power(np.arctan((b * color).astype(f32)).astype(f32), c).astype(f32)).astype(f32)
+    albedo = (albedo + (blend * d * np.power(np.arctan((e * color).astype(f32)).astype(f32), f).astype(f32)).astype(f32)).astype(f32)
+    albedo = np.clip(albedo, f32(0.0), f32(1.0) - f32(1e-6)).astype(f32)
+    extinction = (f32(1.0) / np.maximum(np.asarray(distances, dtype=f32), f32(1.0 / 1024.0))).astype(f32)
+    return albedo, extinction, (extinction * albedo).astype(f32)
+
+
 # ---- image files ----------------------------------------------------------------------------------------------------------------------
 def _read_png(path):
     d = open(path, "rb").read()
@@ -348,6 +361,69 @@ def _read_exr(path):
     return out
 
 
+def _read_pfm(path):
+    """load_pfm (render/host/image_pool.cxx:463-541): the reference's own variant — `Pf` / `PF`, then width, height and scale each on a line of its own,
+    then float rows in file order; the scale (and with it the byte order) is ignored."""
+    d = open(path, "rb").read()
+    pos, lines = 0, []
+    for _ in range(4):
+        e = d.find(b"\n", pos)
+        if e < 0 or e - pos > 16:
+            raise LoaderError(f"{path}: not a PFM file the reference reads")
+        lines.append(d[pos:e].decode("ascii", "replace"))
+        pos = e + 1
+    fmt = lines[0][1:2]
+    w, h = int(lines[1].split()[0]), int(lines[2].split()[0])
+    float(lines[3].split()[0])
+    ch = {"f": 1, "F": 3}.get(fmt)
+    if ch is None:
+        raise LoaderError(f"{path}: PFM format P{fmt} is not read")
+    px = np.frombuffer(d, np.float32, w * h * ch, pos).reshape(h, w, ch)
+    out = np.ones((h, w, 4), dtype=f32)
+    out[..., :3] = px if ch == 3 else px[..., :1]
+    return out
+
+
+def _read_hdr(path):
+    """Radiance RGBE as stb_image's stbi_loadf reads it (flat or run-length encoded scan lines; value = mantissa * 2^(exponent - 136))."""
+    d = open(path, "rb").read()
+    if not (d.startswith(b"#?RADIANCE") or d.startswith(b"#?RGBE")):
+        raise LoaderError(f"{path}: not a Radiance HDR file")
+    pos = d.index(b"\n\n") + 2
+    e = d.index(b"\n", pos)
+    tok = d[pos:e].split()
+    if len(tok) != 4 or tok[0] != b"-Y" or tok[2] != b"+X":
+        raise LoaderError(f"{path}: unsupported HDR orientation {d[pos:e]!r}")
+    h, w = int(tok[1]), int(tok[3])
+    pos = e + 1
+    rgbe = np.zeros((h, w, 4), np.uint8)
+    rle = 8 <= w < 32768 and d[pos] == 2 and d[pos + 1] == 2 and (d[pos + 2] & 0x80) == 0  # decided once, at the first scan line, like stb_image
+    if not rle:
+        rgbe[:] = np.frombuffer(d, np.uint8, w * h * 4, pos).reshape(h, w, 4)
+    else:
+        for y in range(h):
+            if d[pos] != 2 or d[pos + 1] != 2 or ((d[pos + 2] << 8) | d[pos + 3]) != w:
+                raise LoaderError(f"{path}: corrupt HDR scan line")
+            pos += 4
+            for c in range(4):
+                x = 0
+                while x < w:
+                    n = d[pos]
+                    pos += 1
+                    if n > 128:
+                        n -= 128
+                        rgbe[y, x:x + n, c] = d[pos]
+                        pos += 1
+                    else:
+                        rgbe[y, x:x + n, c] = np.frombuffer(d, np.uint8, n, pos)
+                        pos += n
+                    x += n
+    scale = np.ldexp(f32(1.0), rgbe[..., 3].astype(np.int32) - 136).astype(f32)
+    out = np.ones((h, w, 4), dtype=f32)
+    out[..., :3] = np.where(rgbe[..., 3:4] != 0, (rgbe[..., :3].astype(f32) * scale[..., None]).astype(f32), f32(0.0))
+    return out
+
+
 def read_image(path):
     """-> float32 RGBA (linear values as stored for .exr, raw 0..1 for 8-bit files; the caller applies the sRGB curve)."""
     ext = os.path.splitext(path)[1].lower()
@@ -355,7 +431,11 @@ def read_image(path):
         return _read_png(path), True
     if ext == ".exr":
         return _read_exr(path), False
-    raise LoaderError(f"{path}: image files of type {ext} are not read (PNG and OpenEXR are)")
+    if ext == ".hdr":
+        return _read_hdr(path), False
+    if ext == ".pfm":
+        return _read_pfm(path), False
+    raise LoaderError(f"{path}: image files of type {ext} are not read (PNG, OpenEXR, Radiance HDR and PFM are)")
 
 
 # ---- the loader -----------------------------------------------------------------------------------------------------------------------------
@@ -665,8 +745,28 @@ class SceneLoader:
                     if tok == "scale" and i + 1 < len(p):
                         scale = _atof(p[i + 1])
                 spd_t = spd_scaled(base, f32(scale) / f32(base["entries"]["power"][0].max()))
-        if b.get("parametric") is not None:
-            raise LoaderError("et::medium `parametric` (subsurface::remap) is not read by this loader")
+        v = b.get("parametric")
+        if v is not None:
+            # colour + scattering distances -> absorption / scattering through subsurface::remap (scene_bssrdf_subsurface.hxx:17-44), :1254-1296
+            color, dist, scale = [1.0, 1.0, 1.0], [0.25, 0.25, 0.25], 1.0
+            p, i = v.split(), 0
+            while i < len(p):
+                if p[i] == "color" and i + 3 < len(p):
+                    color = [_atof(p[i + 1]), _atof(p[i + 2]), _atof(p[i + 3])]
+                    i += 3
+                if i < len(p) and p[i] == "distance" and i + 1 < len(p):
+                    dist = [_atof(p[i + 1])] * 3
+                    i += 1
+                if i < len(p) and p[i] == "distances" and i + 3 < len(p):
+                    dist = [_atof(p[i + 1]), _atof(p[i + 2]), _atof(p[i + 3])]
+                    i += 3
+                if i < len(p) and p[i] == "scale" and i + 1 < len(p):
+                    scale = _atof(p[i + 1])
+                    i += 1
+                i += 1
+            albedo, extinction, scattering = subsurface_remap(np.asarray(color, dtype=f32), (f32(scale) * np.asarray(dist, dtype=f32)).astype(f32))
+            s_t = [float(x) for x in scattering]
+            s_a = [float(x) for x in np.maximum(f32(0.0), (extinction - scattering).astype(f32))]
         explicit = b.get("enclosed") is None
         v = b.get("volume")
         if v is not None and v.strip():

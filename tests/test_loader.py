@@ -385,6 +385,62 @@ def test_textures_match_the_reference_loader(ref, tmp_path):
     rs.close()
 
 
+def _write_hdr(path, img, rle):
+    """float RGB -> Radiance RGBE (the classic float2rgbe), flat or with every scan line run-length framed (literal runs and one repeat run per plane)"""
+    h, w = img.shape[:2]
+    v = img[..., :3].max(axis=-1)
+    m, e = np.frexp(v)
+    scale = np.where(v < 1e-32, 0.0, m * 256.0 / np.maximum(v, 1e-38))
+    rgbe = np.zeros((h, w, 4), np.uint8)
+    rgbe[..., :3] = (img[..., :3] * scale[..., None]).astype(np.uint8)
+    rgbe[..., 3] = np.where(v < 1e-32, 0, e + 128).astype(np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n" + f"-Y {h} +X {w}\n".encode())
+        if not rle:
+            f.write(rgbe.tobytes())
+            return
+        for y in range(h):
+            f.write(bytes([2, 2, w >> 8, w & 255]))
+            for c in range(4):
+                row = rgbe[y, :, c]
+                if (row == row[0]).all():
+                    x = 0
+                    while x < w:
+                        n = min(127, w - x)
+                        f.write(bytes([128 + n, int(row[0])]))
+                        x += n
+                else:
+                    x = 0
+                    while x < w:
+                        n = min(128, w - x)
+                        f.write(bytes([n]) + row[x:x + n].tobytes())
+                        x += n
+
+
+@pytest.mark.parametrize("rle", [False, True])
+def test_hdr_pfm_images_and_parametric_media_match_the_reference_loader(ref, tmp_path, rle):
+    """A Radiance .hdr environment map (flat and run-length encoded scan lines, read there by stb_image), a .pfm texture in the reference's own header
+    variant, and an et::medium given as `parametric color … distances … scale …` (subsurface::remap)."""
+    rng = np.random.default_rng(11)
+    env = (rng.random((12, 24, 3)) * 3.0).astype(np.float32)
+    env[5, 5] = (30.0, 20.0, 10.0)
+    env[:, 20:] = 0.5  # constant columns: one repeat run per plane when run-length encoded
+    _write_hdr(str(tmp_path / "sky.hdr"), env, rle)
+    tex = rng.random((6, 10, 3)).astype(np.float32)
+    with open(tmp_path / "paint.pfm", "wb") as f:
+        f.write(b"PF\n10\n6\n-1.0\n" + tex.tobytes())
+    obj = OBJ.replace("vn 0 1 0\n", "vn 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\n").replace("f 1//1 4//1 3//1 2//1", "f 1/1/1 4/4/1 3/3/1 2/2/1")
+    mtl = MTL.replace("newmtl et::env\ncolor 0.1 0.2 0.4", "newmtl et::env\nimage sky.hdr\ncolor 0.1 0.2 0.4")
+    mtl = mtl.replace("newmtl Floor\n", "newmtl Floor\nmap_Kd paint.pfm\n")
+    mtl = mtl.replace("id sealed\nscattering 0.1 0.2 0.3", "id sealed\nparametric color 0.8 0.5 0.3 distances 0.4 0.2 0.1 scale 0.5")
+    path = _write_scene(tmp_path, obj=obj, mtl=mtl)
+    rs = ref(path)
+    sd = loader.load_scene(path)
+    problems = compare_scenes(rs, sd, uv_tangents_exact=False)
+    assert not problems, problems
+    rs.close()
+
+
 def test_loader_refuses_what_it_does_not_read(tmp_path):
     path = _write_scene(tmp_path, mtl=MTL + "\nnewmtl et::atmosphere\nquality 0.1\n")
     with pytest.raises(loader.LoaderError):
