@@ -141,3 +141,31 @@ def test_golden_render_matches_live_oracle(oracle_mod):
     o = _pt(oracle_mod, sd, int(ref["iterations"][0]), flavor="parity", threads=1)
     assert bit_equal(o.film(S.FILM_CAMERA), ref["film_camera"]) and bit_equal(o.buffer(S.BUF_CAMERA_SAMPLER, np.uint32), ref["camera_sampler"])
     assert bit_equal(o.film(S.FILM_NORMALS), ref["film_normals"]) and bit_equal(o.film(S.FILM_ALBEDO), ref["film_albedo"])
+
+
+def test_gather_form_of_the_dilation_passes_equals_the_reference_scatter_form():
+    """The device runs Film::estimate_noise_levels' two scatter passes (film.cxx:283-320) as GATHERS (kernels_pt.cuh: k_film_noise_rows / _columns: a pixel
+    loses `tmp` when a pixel x in [p - 4, p + 5] of its row has not converged; it loses `converged` when a pixel y in [p - 4, p + 5] of its column has no `tmp`).
+    A numpy model of the gathers against the scatter form of _numpy_noise_estimate, on random masks including the film borders."""
+    rng = np.random.default_rng(3)
+    for (h, w, density) in ((1, 1, 0.5), (7, 5, 0.3), (36, 40, 0.05), (36, 40, 0.6), (64, 3, 0.2)):
+        conv = rng.random((h, w)) > density
+        tmp = conv.copy()
+        # scatter form (the reference)
+        t_ref, c_ref = tmp.copy(), conv.copy()
+        for y, x in zip(*np.nonzero(~conv)):
+            t_ref[y, max(0, x - 5):min(w, x + 5)] = False
+        for y, x in zip(*np.nonzero(~t_ref)):
+            c_ref[max(0, y - 5):min(h, y + 5), x] = False
+        # gather form (the kernels)
+        t_dev = tmp.copy()
+        for y in range(h):
+            for x in range(w):
+                if tmp[y, x] and (~conv[y, max(0, x - 4):min(w - 1, x + 5) + 1]).any():
+                    t_dev[y, x] = False
+        c_dev = conv.copy()
+        for y in range(h):
+            for x in range(w):
+                if conv[y, x] and (~t_dev[max(0, y - 4):min(h - 1, y + 5) + 1, x]).any():
+                    c_dev[y, x] = False
+        assert np.array_equal(t_dev, t_ref) and np.array_equal(c_dev, c_ref), (h, w, density)
