@@ -39,6 +39,25 @@ def load_library(flavor="fast"):
     lib.etxb_upload_scene.argtypes = [vp, vp, u64, vp, u64]
     lib.etxb_upload_blue_noise.argtypes = [vp, vp, vp, vp]
     lib.etxb_upload_color_tables.argtypes = [vp, vp, vp]
+    if hasattr(lib, "etxb_scene_file_load"):
+        lib.etxb_scene_file_load.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp), C.c_char_p, u64]
+        lib.etxb_scene_file_free.argtypes = [vp]
+        lib.etxb_scene_file_free.restype = None
+        lib.etxb_scene_file_set_samples.argtypes = [vp, u32]
+        lib.etxb_scene_file_set_samples.restype = None
+        lib.etxb_scene_file_commit.argtypes = [vp, vp]
+        lib.etxb_scene_file_table.argtypes = [vp, C.c_char_p, C.POINTER(u64)]
+        lib.etxb_scene_file_table.restype = vp
+        lib.etxb_atmosphere_images.argtypes = [C.c_char_p, vp, C.c_float, vp, u32, u32, vp, vp]
+        for fn in (lib.etxb_scene_file_scene, lib.etxb_scene_file_camera):
+            fn.argtypes = [vp]
+            fn.restype = vp
+        for fn in (lib.etxb_scene_file_warning_count, lib.etxb_scene_file_material_count):
+            fn.argtypes = [vp]
+            fn.restype = u32
+        for fn in (lib.etxb_scene_file_warning, lib.etxb_scene_file_material_name):
+            fn.argtypes = [vp, u32]
+            fn.restype = C.c_char_p
     lib.etxb_options_default.argtypes = [vp]
     lib.etxb_options_default.restype = None
     lib.etxb_options_set_key.argtypes = [vp, C.c_char_p, C.c_double]
@@ -137,6 +156,60 @@ def tonemap(rgba, exposure=1.0, flavor="fast"):
     out = np.zeros(rgba.shape[:-1] + (4,), dtype=np.uint8)
     load_library(flavor).etxb_tonemap_rgba8(_p(rgba), rgba.size // 4, C.c_float(exposure), _p(out))
     return out
+
+
+class SceneFile:
+    """A scene file read by the module's C++ loader (csrc/scene_loader.cpp; replaces SceneRepresentation::load_from_file,
+    render/host/scene_representation.cxx:679-838).  Duck-types scenes.SceneData for GPUVCM / GPUPathTracing / GPUVCMGroup: `.scene`, `.camera`
+    (numpy views of the Scene / Camera PODs the loader object owns), width / height / triangle_count, `.warnings`, `.material_names`."""
+
+    def __init__(self, file_name, flavor="fast", data_folder=None):
+        self.lib = load_library(flavor)
+        self.h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        rc = self.lib.etxb_scene_file_load(os.fsencode(file_name), os.fsencode(data_folder) if data_folder else None, C.byref(self.h), err, len(err))
+        if rc != 0:
+            self.h = C.c_void_p()
+            raise EtxbError(rc, err.value.decode(errors="replace") or f"could not load {file_name}")
+        self.scene = np.frombuffer((C.c_char * S.SCENE.itemsize).from_address(self.lib.etxb_scene_file_scene(self.h)), dtype=S.SCENE)
+        self.camera = np.frombuffer((C.c_char * S.CAMERA.itemsize).from_address(self.lib.etxb_scene_file_camera(self.h)), dtype=S.CAMERA).copy()
+        self.warnings = [self.lib.etxb_scene_file_warning(self.h, i).decode(errors="replace") for i in range(self.lib.etxb_scene_file_warning_count(self.h))]
+        self.material_names = {self.lib.etxb_scene_file_material_name(self.h, i).decode(errors="replace"): i for i in range(self.lib.etxb_scene_file_material_count(self.h))}
+        self.name = os.path.basename(os.fsdecode(file_name))
+
+    @property
+    def width(self):
+        return int(self.camera["film_size"][0][0])
+
+    @property
+    def height(self):
+        return int(self.camera["film_size"][0][1])
+
+    @property
+    def triangle_count(self):
+        return int(self.scene["triangles"]["count"][0])
+
+    def table(self, name, dtype=np.uint8):
+        """a table of tables.bin by name ("bluenoise/sobol", "color_tables/xyz_441x3", ...), None when absent"""
+        n = C.c_uint64(0)
+        p = self.lib.etxb_scene_file_table(self.h, name.encode(), C.byref(n))
+        return np.frombuffer((C.c_char * n.value).from_address(p), dtype=dtype).copy() if p else None
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.scene = None
+            self.lib.etxb_scene_file_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def load_scene_file(file_name, flavor="fast"):
+    return SceneFile(file_name, flavor=flavor)
 
 
 COMM_ID_BYTES = 128

@@ -10,8 +10,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["module.cu", "bvh_build.cpp", "film_io.cpp"]
-HEADERS = ["bvh.h", "bvh_build.h", "dcore.cuh", "dscene.cuh", "dimage.cuh", "dbsdf.cuh", "dclosure.cuh", "dtrace.cuh", "dtrav.cuh", "dwide.cuh", "dmedium.cuh", "dsss.cuh", "dvcm.cuh", "dpt.cuh", "kernels.cuh", "kernels_pt.cuh", "portable_math.h",
+SOURCES = ["module.cu", "bvh_build.cpp", "film_io.cpp", "scene_loader.cpp"]
+HEADERS = ["bvh.h", "bvh_build.h", "dcore.cuh", "dscene.cuh", "dimage.cuh", "dbsdf.cuh", "dclosure.cuh", "dtrace.cuh", "dtrav.cuh", "dwide.cuh", "dmedium.cuh", "dsss.cuh", "dvcm.cuh", "dpt.cuh", "kernels.cuh", "kernels_pt.cuh", "portable_math.h", "scene_loader_formats.inl", "scene_loader_build.inl",
            os.path.join("..", "..", "include", "etx_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets"]
@@ -37,31 +37,66 @@ def lib_path(flavor="fast"):
     return FLAVORS[flavor][0]
 
 
-def _stale(out):
+# what each translation unit includes (the per-flavour objects are rebuilt when one of these is newer)
+UNIT_DEPS = {
+    "module.cu": [h for h in HEADERS if not h.endswith(".inl")],
+    "bvh_build.cpp": ["bvh.h", "bvh_build.h"],
+    "film_io.cpp": [os.path.join("..", "..", "include", "etx_b200.h")],
+    "scene_loader.cpp": ["scene_loader_formats.inl", "scene_loader_build.inl", os.path.join("..", "..", "include", "etx_b200.h")],
+}
+OBJ_ROOT = os.path.join(HERE, "build")  # git-ignored scratch: objects, one folder per flavour
+
+
+def _newer(deps, out):
     if not os.path.exists(out):
         return True
     t = os.path.getmtime(out)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _stale(out):
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return _newer(deps, out)
+
+
 def build(flavors=("fast", "parity", "count"), force=False, verbose=False, extra=()):
-    procs = []
+    """Every translation unit is compiled to an object per flavour (the CUDA unit takes minutes, the host units seconds), then linked; the shared
+    library is written beside its final name and renamed, so a half-written file is never what a loader (or a `gpurun` snapshot) sees."""
+    compile_flags = [f for f in COMMON if f != "-shared"]
+    jobs = []
     for fl in flavors:
         out, flags = FLAVORS[fl]
         if not force and not _stale(out):
             continue
-        cmd = ["nvcc"] + ARCH + COMMON + flags + list(extra) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-            print(" ".join(cmd), flush=True)
-        procs.append((fl, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for fl, cmd, p in procs:
-        out, _ = p.communicate()
+        odir = os.path.join(OBJ_ROOT, fl)
+        os.makedirs(odir, exist_ok=True)
+        objs = []
+        for src in SOURCES:
+            obj = os.path.join(odir, os.path.splitext(src)[0] + ".o")
+            objs.append(obj)
+            deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, d) for d in UNIT_DEPS[src]] + [os.path.abspath(__file__)]
+            if force or extra or _newer(deps, obj):
+                cmd = ["nvcc"] + ARCH + compile_flags + flags + list(extra) + ["-c", os.path.join(CSRC, src), "-o", obj]
+                if verbose:
+                    cmd.insert(1, "-Xptxas=-v")
+                    print(" ".join(cmd), flush=True)
+                jobs.append((fl, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for fl, cmd, p in jobs:
+        text, _ = p.communicate()
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed for flavor {fl}:\n{' '.join(cmd)}\n{out}")
+            raise RuntimeError(f"nvcc failed for flavor {fl}:\n{' '.join(cmd)}\n{text}")
         if verbose:
-            print(out)
+            print(text)
+    for fl in flavors:
+        out, flags = FLAVORS[fl]
+        if not force and not _stale(out):
+            continue
+        objs = [os.path.join(OBJ_ROOT, fl, os.path.splitext(src)[0] + ".o") for src in SOURCES]
+        cmd = ["nvcc"] + ARCH + ["-shared", "-Wno-deprecated-gpu-targets"] + objs + ["-o", out + ".tmp"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed for flavor {fl}:\n{' '.join(cmd)}\n{r.stdout}")
+        os.replace(out + ".tmp", out)
     return [FLAVORS[f][0] for f in flavors]
 
 

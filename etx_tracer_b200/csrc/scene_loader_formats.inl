@@ -1,0 +1,707 @@
+// scene_loader_formats.inl — the file formats the scene loader reads (included by scene_loader.cpp inside its anonymous namespace): DEFLATE, PNG, OpenEXR
+// (scan lines, none / ZIPS / ZIP), Radiance HDR, the reference's PFM variant, JSON, the patched tinyobjloader's .mtl / .obj dialect.
+
+// ---- DEFLATE (RFC 1951) + the zlib wrapper (RFC 1950) --------------------------------------------------------------------------------------------------
+struct BitReader {
+  const uint8_t* data;
+  size_t size, pos = 0;
+  uint32_t bit_buffer = 0, bit_count = 0;
+  uint32_t bits(uint32_t n) {
+    while (bit_count < n) {
+      if (pos >= size) fail("truncated deflate stream");
+      bit_buffer |= uint32_t(data[pos++]) << bit_count;
+      bit_count += 8;
+    }
+    uint32_t v = bit_buffer & ((n == 32u) ? 0xffffffffu : ((1u << n) - 1u));
+    bit_buffer = (n == 32u) ? 0u : (bit_buffer >> n);
+    bit_count -= n;
+    return v;
+  }
+};
+struct Huffman {
+  uint16_t count[16] = {}, symbol[320] = {};
+  void build(const uint8_t* lengths, int n) {
+    memset(count, 0, sizeof(count));
+    for (int i = 0; i < n; ++i) count[lengths[i]]++;
+    count[0] = 0;
+    uint16_t offs[16] = {};
+    for (int i = 1; i < 16; ++i) offs[i] = uint16_t(offs[i - 1] + count[i - 1]);
+    for (int i = 0; i < n; ++i)
+      if (lengths[i]) symbol[offs[lengths[i]]++] = uint16_t(i);
+  }
+  int decode(BitReader& br) const {
+    int code = 0, first = 0, index = 0;
+    for (int len = 1; len < 16; ++len) {
+      code |= int(br.bits(1));
+      int c = count[len];
+      if (code - c < first) return symbol[index + (code - first)];
+      index += c;
+      first += c;
+      first <<= 1;
+      code <<= 1;
+    }
+    fail("bad deflate code");
+  }
+};
+std::vector<uint8_t> inflate_raw(const uint8_t* data, size_t size) {
+  static const uint16_t len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+  static const uint16_t len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+  static const uint16_t dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+  static const uint16_t dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+  static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  BitReader br{data, size};
+  std::vector<uint8_t> out;
+  for (;;) {
+    uint32_t last = br.bits(1), type = br.bits(2);
+    if (type == 0u) {
+      br.bit_buffer = 0, br.bit_count = 0;
+      if (br.pos + 4 > size) fail("truncated stored block");
+      uint32_t len = data[br.pos] | (uint32_t(data[br.pos + 1]) << 8);
+      br.pos += 4;
+      if (br.pos + len > size) fail("truncated stored block");
+      out.insert(out.end(), data + br.pos, data + br.pos + len);
+      br.pos += len;
+    } else if (type == 1u || type == 2u) {
+      Huffman lit, dist;
+      uint8_t lengths[320] = {};
+      if (type == 1u) {
+        for (int i = 0; i < 144; ++i) lengths[i] = 8;
+        for (int i = 144; i < 256; ++i) lengths[i] = 9;
+        for (int i = 256; i < 280; ++i) lengths[i] = 7;
+        for (int i = 280; i < 288; ++i) lengths[i] = 8;
+        lit.build(lengths, 288);
+        for (int i = 0; i < 30; ++i) lengths[i] = 5;
+        dist.build(lengths, 30);
+      } else {
+        int nlen = int(br.bits(5)) + 257, ndist = int(br.bits(5)) + 1, ncode = int(br.bits(4)) + 4;
+        uint8_t cl[19] = {};
+        for (int i = 0; i < ncode; ++i) cl[order[i]] = uint8_t(br.bits(3));
+        Huffman code;
+        code.build(cl, 19);
+        int i = 0;
+        while (i < nlen + ndist) {
+          int sym = code.decode(br);
+          if (sym < 16) {
+            lengths[i++] = uint8_t(sym);
+          } else {
+            uint8_t prev = 0;
+            int rep = 0;
+            if (sym == 16) {
+              if (i == 0) fail("bad deflate lengths");
+              prev = lengths[i - 1];
+              rep = 3 + int(br.bits(2));
+            } else if (sym == 17) {
+              rep = 3 + int(br.bits(3));
+            } else {
+              rep = 11 + int(br.bits(7));
+            }
+            if (i + rep > nlen + ndist) fail("bad deflate lengths");
+            while (rep--) lengths[i++] = prev;
+          }
+        }
+        lit.build(lengths, nlen);
+        dist.build(lengths + nlen, ndist);
+      }
+      for (;;) {
+        int sym = lit.decode(br);
+        if (sym < 256) {
+          out.push_back(uint8_t(sym));
+        } else if (sym == 256) {
+          break;
+        } else {
+          sym -= 257;
+          if (sym >= 29) fail("bad deflate length symbol");
+          size_t len = len_base[sym] + br.bits(len_extra[sym]);
+          int ds = dist.decode(br);
+          if (ds >= 30) fail("bad deflate distance symbol");
+          size_t d = dist_base[ds] + br.bits(dist_extra[ds]);
+          if (d > out.size()) fail("bad deflate distance");
+          size_t from = out.size() - d;
+          for (size_t k = 0; k < len; ++k) out.push_back(out[from + k]);
+        }
+      }
+    } else {
+      fail("bad deflate block type");
+    }
+    if (last) break;
+  }
+  return out;
+}
+std::vector<uint8_t> inflate_zlib(const uint8_t* data, size_t size) {
+  if (size < 6) fail("truncated zlib stream");
+  return inflate_raw(data + 2, size - 2);
+}
+
+// ---- images -----------------------------------------------------------------------------------------------------------------------------------------------
+struct Pixels {
+  uint32_t w = 0, h = 0;
+  bool eight_bit = false;
+  std::vector<uint8_t> u8;  // RGBA8, rows in file order
+  std::vector<float> f32;   // RGBA32F
+};
+uint32_t be32(const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
+
+Pixels read_png(const std::string& path) {
+  std::string d = read_file(path);
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(d.data());
+  if (d.size() < 8 || memcmp(b, "\x89PNG\r\n\x1a\n", 8) != 0) fail(path + ": not a PNG file");
+  size_t pos = 8;
+  std::vector<uint8_t> idat, palette;
+  uint32_t w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
+  while (pos + 12 <= d.size()) {
+    uint32_t n = be32(b + pos);
+    const uint8_t* type = b + pos + 4;
+    const uint8_t* body = b + pos + 8;
+    if (pos + 12 + n > d.size()) break;
+    if (!memcmp(type, "IHDR", 4)) {
+      w = be32(body), h = be32(body + 4), depth = body[8], ctype = body[9], interlace = body[12];
+    } else if (!memcmp(type, "PLTE", 4)) {
+      palette.assign(body, body + n);
+    } else if (!memcmp(type, "IDAT", 4)) {
+      idat.insert(idat.end(), body, body + n);
+    }
+    pos += 12 + n;
+  }
+  if (depth != 8 || interlace != 0 || w == 0 || h == 0) fail(path + ": only 8-bit non-interlaced PNG files are read");
+  uint32_t ch = (ctype == 0) ? 1 : (ctype == 2) ? 3 : (ctype == 3) ? 1 : (ctype == 4) ? 2 : (ctype == 6) ? 4 : 0;
+  if (ch == 0) fail(path + ": unknown PNG colour type");
+  std::vector<uint8_t> raw = inflate_zlib(idat.data(), idat.size());
+  const size_t stride = size_t(w) * ch;
+  if (raw.size() < (stride + 1) * h) fail(path + ": truncated PNG data");
+  std::vector<uint8_t> img(stride * h);
+  std::vector<uint8_t> zero(stride, 0);
+  for (uint32_t y = 0; y < h; ++y) {
+    const uint8_t* line = raw.data() + size_t(y) * (stride + 1);
+    uint8_t ft = line[0];
+    const uint8_t* src = line + 1;
+    uint8_t* cur = img.data() + size_t(y) * stride;
+    const uint8_t* prev = y ? (cur - stride) : zero.data();
+    for (size_t x = 0; x < stride; ++x) {
+      int a = (x >= ch) ? cur[x - ch] : 0, bb = prev[x], c = (x >= ch) ? prev[x - ch] : 0, p = 0;
+      switch (ft) {
+        case 0: p = 0; break;
+        case 1: p = a; break;
+        case 2: p = bb; break;
+        case 3: p = (a + bb) >> 1; break;
+        default: {
+          int pa = abs(bb - c), pb = abs(a - c), pc = abs(a + bb - 2 * c);
+          p = (pa <= pb && pa <= pc) ? a : (pb <= pc ? bb : c);
+        }
+      }
+      cur[x] = uint8_t(src[x] + p);
+    }
+  }
+  Pixels out;
+  out.w = w, out.h = h, out.eight_bit = true;
+  out.u8.assign(size_t(w) * h * 4, 255);
+  for (size_t i = 0; i < size_t(w) * h; ++i) {
+    uint8_t* o = out.u8.data() + i * 4;
+    const uint8_t* s = img.data() + i * ch;
+    if (ctype == 3) {
+      if (size_t(s[0]) * 3 + 2 < palette.size()) memcpy(o, palette.data() + size_t(s[0]) * 3, 3);
+    } else if (ch == 1) {
+      o[0] = o[1] = o[2] = s[0];
+    } else if (ch == 2) {
+      // grey + alpha: the reference's switch over the channel count has no case for 2 (image_pool.cxx:353-381), the image stays zero-filled
+      o[0] = o[1] = o[2] = o[3] = 0;
+    } else {
+      memcpy(o, s, ch);
+    }
+  }
+  return out;
+}
+
+float half_to_float(uint16_t h) {
+  uint32_t sign = (h >> 15) & 1u, e = (h >> 10) & 31u, m = h & 1023u, bits;
+  if (e == 0) {
+    if (m == 0) {
+      bits = sign << 31;
+    } else {
+      e = 127 - 15 + 1;
+      while (!(m & 1024u)) {
+        m <<= 1;
+        e--;
+      }
+      bits = (sign << 31) | (e << 23) | ((m & 1023u) << 13);
+    }
+  } else if (e == 31) {
+    bits = (sign << 31) | 0x7f800000u | (m << 13);
+  } else {
+    bits = (sign << 31) | ((e + 127 - 15) << 23) | (m << 13);
+  }
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+}
+
+Pixels read_exr(const std::string& path) {
+  std::string d = read_file(path);
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(d.data());
+  auto le32 = [&](size_t at) {
+    uint32_t v;
+    if (at + 4 > d.size()) fail(path + ": truncated EXR file");
+    memcpy(&v, b + at, 4);
+    return v;
+  };
+  if (d.size() < 8 || le32(0) != 20000630u) fail(path + ": not an OpenEXR file");
+  size_t pos = 8;
+  std::map<std::string, std::string> attrs;
+  while (pos < d.size() && b[pos] != 0) {
+    size_t ne = d.find('\0', pos), te = d.find('\0', ne + 1);
+    if (ne == std::string::npos || te == std::string::npos) fail(path + ": bad EXR header");
+    uint32_t size = le32(te + 1);
+    attrs[d.substr(pos, ne - pos)] = d.substr(te + 5, size);
+    pos = te + 5 + size;
+  }
+  pos += 1;
+  if (!attrs.count("compression") || !attrs.count("dataWindow") || !attrs.count("channels")) fail(path + ": incomplete EXR header");
+  int comp = uint8_t(attrs["compression"][0]);
+  if (comp != 0 && comp != 2 && comp != 3) fail(path + ": this EXR compression is not read (none / ZIPS / ZIP are)");
+  int32_t win[4];
+  memcpy(win, attrs["dataWindow"].data(), 16);
+  const uint32_t w = uint32_t(win[2] - win[0] + 1), h = uint32_t(win[3] - win[1] + 1);
+  std::vector<std::string> names;
+  std::vector<int> types;
+  const std::string& chl = attrs["channels"];
+  for (size_t cp = 0; cp < chl.size() && chl[cp] != 0;) {
+    size_t e = chl.find('\0', cp);
+    names.push_back(chl.substr(cp, e - cp));
+    int32_t t;
+    memcpy(&t, chl.data() + e + 1, 4);
+    types.push_back(t);
+    cp = e + 17;
+  }
+  const uint32_t lines = (comp == 3) ? 16u : 1u, blocks = (h + lines - 1) / lines;
+  size_t bytes_per_pixel = 0;
+  for (int t : types) bytes_per_pixel += (t == 1) ? 2 : 4;
+  Pixels out;
+  out.w = w, out.h = h;
+  out.f32.assign(size_t(w) * h * 4, 0.0f);
+  for (size_t i = 0; i < size_t(w) * h; ++i) out.f32[i * 4 + 3] = 1.0f;
+  for (uint32_t k = 0; k < blocks; ++k) {
+    uint64_t off;
+    if (pos + size_t(k) * 8 + 8 > d.size()) fail(path + ": truncated EXR offset table");
+    memcpy(&off, b + pos + size_t(k) * 8, 8);
+    int32_t by = int32_t(le32(size_t(off)));
+    uint32_t size = le32(size_t(off) + 4);
+    const uint32_t nl = std::min<uint32_t>(lines, uint32_t(win[3] - by + 1));
+    const size_t want = size_t(nl) * w * bytes_per_pixel;
+    std::vector<uint8_t> raw;
+    if (size_t(off) + 8 + size > d.size()) fail(path + ": truncated EXR block");
+    if (comp != 0 && size < want) {
+      std::vector<uint8_t> z = inflate_zlib(b + off + 8, size);
+      for (size_t i = 1; i < z.size(); ++i) z[i] = uint8_t(z[i - 1] + z[i] - 128);  // predictor
+      raw.resize(z.size());
+      const size_t half = (z.size() + 1) / 2;
+      for (size_t i = 0; i < z.size(); ++i) raw[i] = (i & 1) ? z[half + i / 2] : z[i / 2];
+    } else {
+      raw.assign(b + off + 8, b + off + 8 + size);
+    }
+    if (raw.size() < want) fail(path + ": short EXR block");
+    size_t p = 0;
+    for (uint32_t ly = 0; ly < nl; ++ly) {
+      const uint32_t y = uint32_t(by - win[1]) + ly;
+      for (size_t ci = 0; ci < names.size(); ++ci) {
+        int slot = (names[ci] == "R") ? 0 : (names[ci] == "G") ? 1 : (names[ci] == "B") ? 2 : (names[ci] == "A") ? 3 : (names[ci] == "Y") ? 4 : -1;
+        for (uint32_t x = 0; x < w; ++x) {
+          float v;
+          if (types[ci] == 1) {
+            uint16_t hv;
+            memcpy(&hv, raw.data() + p, 2);
+            v = half_to_float(hv);
+            p += 2;
+          } else if (types[ci] == 2) {
+            memcpy(&v, raw.data() + p, 4);
+            p += 4;
+          } else {
+            uint32_t u;
+            memcpy(&u, raw.data() + p, 4);
+            v = float(u);
+            p += 4;
+          }
+          float* px = out.f32.data() + (size_t(y) * w + x) * 4;
+          if (slot >= 0 && slot < 4) px[slot] = v;
+          if (slot == 4) px[0] = px[1] = px[2] = v;
+        }
+      }
+    }
+  }
+  return out;
+}
+
+Pixels read_hdr(const std::string& path) {
+  std::string d = read_file(path);
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(d.data());
+  if (d.compare(0, 10, "#?RADIANCE") != 0 && d.compare(0, 6, "#?RGBE") != 0) fail(path + ": not a Radiance HDR file");
+  size_t pos = d.find("\n\n");
+  if (pos == std::string::npos) fail(path + ": bad HDR header");
+  pos += 2;
+  size_t e = d.find('\n', pos);
+  auto tok = split(d.substr(pos, e - pos));
+  if (tok.size() != 4 || tok[0] != "-Y" || tok[2] != "+X") fail(path + ": unsupported HDR orientation");
+  const uint32_t h = uint32_t(atoi(tok[1].c_str())), w = uint32_t(atoi(tok[3].c_str()));
+  pos = e + 1;
+  std::vector<uint8_t> rgbe(size_t(w) * h * 4);
+  const bool rle = (w >= 8 && w < 32768 && pos + 4 <= d.size() && b[pos] == 2 && b[pos + 1] == 2 && (b[pos + 2] & 0x80) == 0);  // decided at the first scan line, like stb_image
+  if (!rle) {
+    if (pos + rgbe.size() > d.size()) fail(path + ": truncated HDR data");
+    memcpy(rgbe.data(), b + pos, rgbe.size());
+  } else {
+    for (uint32_t y = 0; y < h; ++y) {
+      if (pos + 4 > d.size() || b[pos] != 2 || b[pos + 1] != 2 || ((uint32_t(b[pos + 2]) << 8) | b[pos + 3]) != w) fail(path + ": corrupt HDR scan line");
+      pos += 4;
+      for (uint32_t c = 0; c < 4; ++c) {
+        uint32_t x = 0;
+        while (x < w) {
+          if (pos >= d.size()) fail(path + ": truncated HDR data");
+          uint32_t n = b[pos++];
+          if (n > 128) {
+            n -= 128;
+            if (x + n > w || pos >= d.size()) fail(path + ": corrupt HDR run");
+            for (uint32_t k = 0; k < n; ++k) rgbe[(size_t(y) * w + x + k) * 4 + c] = b[pos];
+            pos += 1;
+          } else {
+            if (x + n > w || pos + n > d.size()) fail(path + ": corrupt HDR run");
+            for (uint32_t k = 0; k < n; ++k) rgbe[(size_t(y) * w + x + k) * 4 + c] = b[pos + k];
+            pos += n;
+          }
+          x += n;
+        }
+      }
+    }
+  }
+  Pixels out;
+  out.w = w, out.h = h;
+  out.f32.resize(size_t(w) * h * 4);
+  for (size_t i = 0; i < size_t(w) * h; ++i) {
+    const uint8_t* p = rgbe.data() + i * 4;
+    float* o = out.f32.data() + i * 4;
+    if (p[3] != 0) {
+      float f1 = ldexpf(1.0f, int(p[3]) - 136);
+      o[0] = p[0] * f1, o[1] = p[1] * f1, o[2] = p[2] * f1;
+    } else {
+      o[0] = o[1] = o[2] = 0.0f;
+    }
+    o[3] = 1.0f;
+  }
+  return out;
+}
+
+// load_pfm (render/host/image_pool.cxx:463-541): the reference's own header variant — width, height and scale each on a line of its own
+Pixels read_pfm(const std::string& path) {
+  std::string d = read_file(path);
+  size_t pos = 0;
+  std::string lines[4];
+  for (auto& line : lines) {
+    size_t e = d.find('\n', pos);
+    if (e == std::string::npos || e - pos > 16) fail(path + ": not a PFM file the reference reads");
+    line = d.substr(pos, e - pos);
+    pos = e + 1;
+  }
+  const char fmt = lines[0].size() > 1 ? lines[0][1] : 0;
+  const uint32_t w = uint32_t(atoi(lines[1].c_str())), h = uint32_t(atoi(lines[2].c_str()));
+  const uint32_t ch = (fmt == 'f') ? 1u : (fmt == 'F') ? 3u : 0u;
+  if (ch == 0 || w == 0 || h == 0 || pos + size_t(w) * h * ch * 4 > d.size()) fail(path + ": unsupported or truncated PFM file");
+  Pixels out;
+  out.w = w, out.h = h;
+  out.f32.resize(size_t(w) * h * 4);
+  for (size_t i = 0; i < size_t(w) * h; ++i) {
+    float v[3];
+    memcpy(v, d.data() + pos + i * ch * 4, ch * 4);
+    float* o = out.f32.data() + i * 4;
+    o[0] = v[0], o[1] = (ch == 3) ? v[1] : v[0], o[2] = (ch == 3) ? v[2] : v[0], o[3] = 1.0f;
+  }
+  return out;
+}
+
+Pixels read_image(const std::string& path) {
+  size_t dot_at = path.find_last_of('.');
+  std::string ext = dot_at == std::string::npos ? std::string("") : lower(path.substr(dot_at));
+  if (ext == ".png") return read_png(path);
+  if (ext == ".exr") return read_exr(path);
+  if (ext == ".hdr") return read_hdr(path);
+  if (ext == ".pfm") return read_pfm(path);
+  fail(path + ": image files of type `" + ext + "` are not read (PNG, OpenEXR, Radiance HDR and PFM are)");
+}
+
+// ---- JSON (what a scene description needs: objects, arrays, strings, numbers, booleans) ----------------------------------------------------------------------
+struct Json {
+  enum Kind { Null, Bool, Number, String, Array, Object } kind = Null;
+  bool b = false;
+  double number = 0.0;
+  std::string text;
+  std::vector<Json> items;
+  std::vector<std::pair<std::string, Json>> members;
+};
+struct JsonParser {
+  const std::string& s;
+  size_t pos = 0;
+  void ws() {
+    while (pos < s.size() && isspace(static_cast<unsigned char>(s[pos]))) ++pos;
+  }
+  std::string string() {
+    std::string out;
+    ++pos;
+    while (pos < s.size() && s[pos] != '"') {
+      if (s[pos] == '\\' && pos + 1 < s.size()) {
+        char c = s[pos + 1];
+        out.push_back(c == 'n' ? '\n' : c == 't' ? '\t' : c);
+        pos += 2;
+      } else {
+        out.push_back(s[pos++]);
+      }
+    }
+    ++pos;
+    return out;
+  }
+  Json value() {
+    ws();
+    Json j;
+    if (pos >= s.size()) fail("unexpected end of the scene description");
+    char c = s[pos];
+    if (c == '{') {
+      j.kind = Json::Object;
+      ++pos;
+      ws();
+      while (pos < s.size() && s[pos] != '}') {
+        ws();
+        if (s[pos] != '"') fail("bad scene description: a key was expected");
+        std::string key = string();
+        ws();
+        if (pos >= s.size() || s[pos] != ':') fail("bad scene description: `:` was expected");
+        ++pos;
+        j.members.push_back({key, value()});
+        ws();
+        if (pos < s.size() && s[pos] == ',') ++pos;
+        ws();
+      }
+      ++pos;
+    } else if (c == '[') {
+      j.kind = Json::Array;
+      ++pos;
+      ws();
+      while (pos < s.size() && s[pos] != ']') {
+        j.items.push_back(value());
+        ws();
+        if (pos < s.size() && s[pos] == ',') ++pos;
+        ws();
+      }
+      ++pos;
+    } else if (c == '"') {
+      j.kind = Json::String;
+      j.text = string();
+    } else if (!s.compare(pos, 4, "true")) {
+      j.kind = Json::Bool, j.b = true, pos += 4;
+    } else if (!s.compare(pos, 5, "false")) {
+      j.kind = Json::Bool, j.b = false, pos += 5;
+    } else if (!s.compare(pos, 4, "null")) {
+      pos += 4;
+    } else {
+      char* end = nullptr;
+      j.kind = Json::Number;
+      j.number = strtod(s.c_str() + pos, &end);
+      if (end == s.c_str() + pos) fail("bad scene description: a value was expected");
+      pos = size_t(end - s.c_str());
+    }
+    return j;
+  }
+};
+
+// ---- .mtl as the reference's patched tinyobjloader reads it (tiny_obj_loader.hxx:1900-2190) ------------------------------------------------------------------
+struct MtlBlock {
+  std::string name;
+  std::vector<std::pair<std::string, std::string>> params;  // in file order
+  std::map<std::string, std::string> textures;
+  bool get(const char* key, std::string& out) const {  // get_param (scene_representation.cxx:102-112): first match, case-insensitive
+    std::string k = lower(key);
+    for (const auto& p : params) {
+      if (lower(p.first) == k) {
+        out = p.second;
+        return true;
+      }
+    }
+    return false;
+  }
+  bool has(const char* key) const {
+    std::string unused;
+    return get(key, unused);
+  }
+};
+
+std::vector<MtlBlock> parse_mtl(const std::string& path) {
+  static const std::pair<const char*, const char*> textures[] = {{"map_ka", "ambient"}, {"map_kd", "diffuse"}, {"map_ks", "specular"}, {"map_kt", "transmittance"},
+    {"map_ns", "specular_highlight"}, {"map_bump", "bump"}, {"map_d", "alpha"}, {"disp", "displacement"}, {"refl", "reflection"}, {"map_pr", "roughness"}, {"map_pm", "metallic"},
+    {"map_ps", "sheen"}, {"map_ke", "emissive"}, {"norm", "normal"}};
+  static const std::pair<const char*, bool> scalars[] = {{"Ni", false}, {"illum", true}, {"d", false}, {"Tr", false}, {"Pm", false}, {"Ps", false}, {"Pc", false}, {"Pcr", true},
+    {"aniso", true}, {"anisor", true}};  // key, case-insensitive?
+  std::string data = read_file(path);
+  std::vector<MtlBlock> blocks;
+  size_t at = 0;
+  while (at <= data.size()) {
+    size_t e = data.find('\n', at);
+    if (e == std::string::npos) e = data.size();
+    std::string line = data.substr(at, e - at);
+    at = e + 1;
+    while (!line.empty() && (line.back() == '\r' || line.back() == ' ' || line.back() == '\t')) line.pop_back();
+    size_t lead = 0;
+    while (lead < line.size() && (line[lead] == ' ' || line[lead] == '\t')) ++lead;
+    line = line.substr(lead);
+    if (line.empty() || line[0] == '#') {
+      if (e == data.size()) break;
+      continue;
+    }
+    std::string low = lower(line);
+    auto separated = [&](size_t n) { return line.size() > n && (line[n] == ' ' || line[n] == '\t'); };
+    if (!low.compare(0, 6, "newmtl") && separated(6)) {
+      MtlBlock b;
+      b.name = lower(line.substr(7));
+      blocks.push_back(b);
+    } else if (!blocks.empty()) {
+      bool consumed = false;
+      for (const auto& t : textures) {
+        size_t n = strlen(t.first);
+        if (!low.compare(0, n, t.first) && separated(n)) {
+          auto tok = split(line.substr(n + 1));
+          blocks.back().textures[t.second] = tok.empty() ? std::string("") : tok.back();
+          consumed = true;
+          break;
+        }
+      }
+      for (const auto& sc : scalars) {
+        if (consumed) break;
+        size_t n = strlen(sc.first);
+        bool match = sc.second ? !low.compare(0, n, lower(sc.first)) : !line.compare(0, n, sc.first);
+        if (match && separated(n)) consumed = true;
+      }
+      if (!consumed) {
+        size_t sp = line.find(' ');
+        if (sp == std::string::npos) sp = line.find('\t');
+        if (sp == std::string::npos) {
+          blocks.back().params.push_back({line, ""});
+        } else {
+          blocks.back().params.push_back({line.substr(0, sp), line.substr(sp + 1)});
+        }
+      }
+    }
+    if (e == data.size()) break;
+  }
+  return blocks;
+}
+
+// ---- .obj: positions / normals / texture coordinates, triangulated faces with their material name and shape (o / g group) -------------------------------------
+struct ObjIndex {
+  int v = -1, t = -1, n = -1;
+};
+struct ObjData {
+  std::vector<float> pos, nrm, tex;
+  std::vector<ObjIndex> corners;  // 3 per face
+  std::vector<int> face_material;  // index into material_names, -1 = none
+  std::vector<uint32_t> face_shape;
+  std::vector<std::string> material_names;
+  std::string mtllib;
+};
+
+ObjData parse_obj(const std::string& path) {
+  std::string data = read_file(path);
+  ObjData o;
+  std::map<std::string, int> name_index;
+  int current = -1;
+  uint32_t shape = 0;
+  bool shape_has_faces = false;
+  const char* p = data.c_str();
+  const char* end = p + data.size();
+  std::vector<ObjIndex> poly;
+  while (p < end) {
+    const char* le = static_cast<const char*>(memchr(p, '\n', size_t(end - p)));
+    if (!le) le = end;
+    const char* q = p;
+    while (q < le && (*q == ' ' || *q == '\t')) ++q;
+    if (q < le && *q != '#') {
+      if (q[0] == 'v' && (q[1] == ' ' || q[1] == '\t')) {
+        char* e2 = nullptr;
+        for (int k = 0; k < 3; ++k) {
+          o.pos.push_back(strtof(k ? e2 : q + 1, &e2));
+        }
+      } else if (q[0] == 'v' && q[1] == 'n' && (q[2] == ' ' || q[2] == '\t')) {
+        char* e2 = nullptr;
+        for (int k = 0; k < 3; ++k) o.nrm.push_back(strtof(k ? e2 : q + 2, &e2));
+      } else if (q[0] == 'v' && q[1] == 't' && (q[2] == ' ' || q[2] == '\t')) {
+        char* e2 = nullptr;
+        float u = strtof(q + 2, &e2);
+        const char* after = e2;
+        float v = strtof(e2, &e2);
+        if (e2 == after) v = 0.0f;
+        o.tex.push_back(u), o.tex.push_back(v);
+      } else if (q[0] == 'f' && (q[1] == ' ' || q[1] == '\t')) {
+        poly.clear();
+        const char* c = q + 1;
+        while (c < le) {
+          while (c < le && (*c == ' ' || *c == '\t' || *c == '\r')) ++c;
+          if (c >= le) break;
+          ObjIndex idx;
+          char* e2 = nullptr;
+          long vi = strtol(c, &e2, 10);
+          if (e2 == c) break;
+          long ti = 0, ni = 0;
+          c = e2;
+          if (c < le && *c == '/') {
+            ++c;
+            if (c < le && *c != '/') {
+              ti = strtol(c, &e2, 10);
+              c = e2;
+            }
+            if (c < le && *c == '/') {
+              ++c;
+              ni = strtol(c, &e2, 10);
+              c = e2;
+            }
+          }
+          idx.v = int(vi > 0 ? vi - 1 : long(o.pos.size() / 3) + vi);
+          idx.t = ti ? int(ti > 0 ? ti - 1 : long(o.tex.size() / 2) + ti) : -1;
+          idx.n = ni ? int(ni > 0 ? ni - 1 : long(o.nrm.size() / 3) + ni) : -1;
+          poly.push_back(idx);
+        }
+        auto emit = [&](int a, int b2, int c2) {
+          o.corners.push_back(poly[size_t(a)]), o.corners.push_back(poly[size_t(b2)]), o.corners.push_back(poly[size_t(c2)]);
+          o.face_material.push_back(current);
+          o.face_shape.push_back(shape);
+        };
+        for (const auto& ix : poly)
+          if (ix.v < 0 || size_t(ix.v) * 3 + 2 >= o.pos.size()) fail(path + ": a face refers to a vertex that does not exist");
+        if (poly.size() == 4) {
+          // tinyobjloader splits a quad along its shorter diagonal (tiny_obj_loader.hxx:1464-1527)
+          F3 v0 = load3(&o.pos[size_t(poly[0].v) * 3]), v1 = load3(&o.pos[size_t(poly[1].v) * 3]), v2 = load3(&o.pos[size_t(poly[2].v) * 3]), v3 = load3(&o.pos[size_t(poly[3].v) * 3]);
+          F3 e02 = v2 - v0, e13 = v3 - v1;
+          float s02 = e02.x * e02.x + e02.y * e02.y + e02.z * e02.z, s13 = e13.x * e13.x + e13.y * e13.y + e13.z * e13.z;
+          if (s02 < s13) {
+            emit(0, 1, 2), emit(0, 2, 3);
+          } else {
+            emit(0, 1, 3), emit(1, 2, 3);
+          }
+        } else {
+          for (size_t j = 1; j + 1 < poly.size(); ++j) emit(0, int(j), int(j + 1));  // triangles; larger polygons as a fan (tinyobjloader clips ears)
+        }
+        shape_has_faces = shape_has_faces || (poly.size() >= 3);
+      } else if (!strncmp(q, "usemtl", 6) && (q[6] == ' ' || q[6] == '\t')) {
+        std::string name = lower(trim(std::string(q + 7, size_t(le - q - 7))));
+        auto it = name_index.find(name);
+        if (it == name_index.end()) {
+          current = int(o.material_names.size());
+          name_index[name] = current;
+          o.material_names.push_back(name);
+        } else {
+          current = it->second;
+        }
+      } else if ((q[0] == 'o' || q[0] == 'g') && (q + 1 == le || q[1] == ' ' || q[1] == '\t' || q[1] == '\r')) {
+        if (shape_has_faces) {
+          shape += 1;
+          shape_has_faces = false;
+        }
+      } else if (!strncmp(q, "mtllib", 6) && (q[6] == ' ' || q[6] == '\t')) {
+        o.mtllib = trim(std::string(q + 7, size_t(le - q - 7)));
+      }
+    }
+    p = le + 1;
+  }
+  return o;
+}

@@ -63,6 +63,16 @@ class GPUVCM {
     _samples = samples;
     return rc;
   }
+  // a scene file read by the module's loader (etxb_scene_file_load): tables + scene + camera in one call
+  int commit_scene_file(const etxb_scene_file* file) {
+    stop(Stop::Immediate);
+    _scene_committed = false;
+    if (!enabled()) return _create_result;
+    int rc = etxb_scene_file_commit(_ctx, file);
+    _scene_committed = (rc == ETXB_OK);
+    if (_scene_committed) _samples = etxb_scene_file_scene(file)->samples;
+    return rc;
+  }
   int upload_tables(const float* xyz_441x3, const float* rgb_response_391x3, const uint8_t* sobol, const uint8_t* scrambling, const uint8_t* ranking) {
     if (!enabled()) return _create_result;
     int rc = etxb_upload_color_tables(_ctx, xyz_441x3, rgb_response_391x3);

@@ -8,11 +8,13 @@ validate_normals / validate_tangents :304-418, commit :420-455) read into the Sc
 Everything is built on `scenes.SceneData` (the same record builders the synthetic generators use); `tests/test_loader.py` compares the
 result with the reference's own loader (compiled in place as test infrastructure) array by array on the shipped Cornell asset and on
 generated scene files.  Known differences, all stated there: tangent frames of meshes WITH texture coordinates come from per-triangle UV
-derivatives instead of MikkTSpace (only normal maps and anisotropic roughness see them); `et::atmosphere` (the procedural sun + sky images,
-host/scattering.cxx) and NanoVDB volumes are refused; image files: PNG (8-bit, non-interlaced), OpenEXR (float, scan lines, none / ZIP), Radiance HDR and the reference's PFM variant.
+derivatives instead of MikkTSpace (only normal maps and anisotropic roughness see them); NanoVDB volumes and glTF geometry are refused; the two images of
+an atmosphere block (`et::atmosphere`, and the default atmosphere of a file without distant emitters) come from the module's host code
+(etxb_atmosphere_images); this file is the Python twin of csrc/scene_loader.cpp, which is what the C ABI ships; image files: PNG (8-bit, non-interlaced), OpenEXR (float, scan lines, none / ZIP), Radiance HDR and the reference's PFM variant.
 The .mtl reader follows the reference's patched tinyobjloader (thirdparty/tinyobjloader/tiny_obj_loader.hxx:1900-2190): names are lower-cased,
 `Kd / Ks / Kt / Ke` and every non-standard key land in the material's parameter list, the standard texture keys are consumed.
 """
+import ctypes as C
 import json
 import math
 import os
@@ -299,8 +301,7 @@ def _read_png(path):
     if px.shape[2] == 1:
         rgba[..., :3] = px
     elif px.shape[2] == 2:
-        rgba[..., :3] = px[..., :1]
-        rgba[..., 3] = px[..., 1]
+        rgba[...] = 0  # grey + alpha: the reference's switch over the channel count has no case for 2 (image_pool.cxx:353-381), the image stays zero-filled
     else:
         rgba[..., :px.shape[2]] = px
     return rgba
@@ -821,6 +822,56 @@ class SceneLoader:
         p, _ = self.sd._distant_emitters[-1]
         self.sd.spectra[int(p["emission"]["spectrum_index"][0])] = spd
 
+    def parse_atmosphere(self, b):
+        """parse_atmosphere_light (:1376-1495): a sun (Directional, 128 x 128 limb-darkened extinction image) and a sky (Environment, single-scattering
+        image with its sampling table).  The two images come from the module's host code (etxb_atmosphere_images, csrc/scene_loader_atmosphere.inl:
+        render/host/scattering.cxx restated) — the C++ loader builds the same block from the same function."""
+        from . import api
+
+        def scalar(key, fallback):
+            v = b.get(key)
+            return _floats(v, 1)[0] if (v is not None and _floats(v, 1)) else fallback
+        quality, scale, sun_scale, sky_scale = scalar("quality", 1.0), scalar("scale", 1.0), scalar("sun_scale", 1.0), scalar("sky_scale", 1.0)
+        d = np.array([1.0, 1.0, 1.0], f32)
+        v = b.get("direction")
+        if v is not None and len(_floats(v, 3)) == 3:
+            d = np.array(_floats(v, 3), f32)
+        d = (d / np.sqrt((d * d).sum(dtype=f32), dtype=f32)).astype(f32)
+        ang_deg = scalar("angular_diameter", 0.5422)
+        ang = f32(ang_deg) * (f32(math.pi) / f32(180.0))
+        prm = np.array([scalar("altitude", 1000.0), scalar("anisotropy", 0.825), scalar("rayleigh", 1.0), scalar("mie", 1.0), scalar("ozone", 1.0)], f32)
+        radiance_scale = f32(scale) * (f32(2.0 * f32(math.pi)) * (f32(1.0) - f32(np.cos(f32(0.5) * ang, dtype=f32))))
+        sun_spectrum = spd_black_body(5900.0, radiance_scale)
+        sky_w, sky_h = max(64, int(f32(2048) * f32(quality))), max(64, int(f32(1024) * f32(quality)))
+        sun = np.zeros((128, 128, 4), f32)
+        sky = np.zeros((sky_h, sky_w, 4), f32)
+        lib = api.load_library("fast")
+        rc = lib.etxb_atmosphere_images(None, d.ctypes.data, C.c_float(float(ang)), prm.ctypes.data, sky_w, sky_h,
+                                        sun.ctypes.data if ang > 0 else None, sky.ctypes.data)
+        if rc != 0:
+            raise LoaderError(f"etxb_atmosphere_images failed ({rc})")
+        self.sd.add_directional_emitter(d, [1.0, 1.0, 1.0], 0.0)
+        p, _ = self.sd._distant_emitters[-1]
+        self.sd.spectra[int(p["emission"]["spectrum_index"][0])] = spd_scaled(sun_spectrum, sun_scale)
+        p["direction"][0] = d
+        p["angular_size"] = ang
+        p["equivalent_disk_size"] = f32(2.0) * f32(math.tan(float(ang) / 2.0))
+        p["angular_size_cosine"] = f32(math.cos(float(ang) / 2.0))
+        if ang > 0:
+            p["emission"]["image_index"] = self.sd.add_image(sun, repeat=False, build_table=False)
+        image = self.sd.add_image(sky, repeat=False, build_table=True)
+        self.sd.add_environment_emitter(image)
+        p, _ = self.sd._distant_emitters[-1]
+        self.sd.spectra[int(p["emission"]["spectrum_index"][0])] = spd_scaled(sun_spectrum, sky_scale)
+        p["direction"][0] = d
+
+    def add_default_atmosphere(self):
+        """load_from_file :805-820: what a scene file that declares no distant emitter gets."""
+        b = MtlBlock("et::atmosphere")
+        b.params = [("direction", "0.0 2.0 1.0"), ("quality", "0.125"), ("angular_diameter", "0.5422"), ("anisotropy", "0.825"), ("altitude", "1000.0"), ("scale", "1.0"),
+                    ("sky_scale", "1.0"), ("sun_scale", "1.0"), ("rayleigh", "1.0"), ("mie", "1.0"), ("ozone", "1.0")]
+        self.parse_atmosphere(b)
+
     def parse_spectrum(self, b):
         name = b.get("id")
         if name is None:
@@ -1060,7 +1111,7 @@ class SceneLoader:
             elif b.name == "et::env":
                 self.parse_env(b)
             elif b.name == "et::atmosphere":
-                raise LoaderError("et::atmosphere (procedural sun + sky images, host/scattering.cxx) is not generated by this loader: use et::env / et::dir")
+                self.parse_atmosphere(b)
             elif b.name == "et::spectrum":
                 self.parse_spectrum(b)
             else:
@@ -1190,7 +1241,11 @@ def load_scene(file_name, data_folder=None):
     cam = dict(cls=0, viewport=(0, 0), origin=(5.0, 5.0, 5.0), target=(float(dflt),) * 3, up=(0.0, 1.0, 0.0), fov=26.99, focal=None, lens_radius=0.0, focal_distance=0.0,
                clip_near=None, clip_far=None)
     if file_name.lower().endswith(".json"):
-        js = json.load(open(file_name))
+        try:
+            with open(file_name) as f:
+                js = json.load(f)
+        except (OSError, ValueError) as e:
+            raise LoaderError(f"{file_name}: {e}")
         for key in sorted(js):
             val = js[key]
             if key == "samples":
@@ -1230,8 +1285,8 @@ def load_scene(file_name, data_folder=None):
         raise LoaderError(f"{geometry}: only Wavefront .obj geometry is read by this loader (glTF is not)")
     ld.load_obj(geometry, materials)
     sd = ld.sd
-    if not sd._distant_emitters and not any(int(m["emission"]["spectrum_index"][0]) != S.INVALID for m in sd.materials):
-        raise LoaderError("the scene has no emitter: the reference would synthesise an atmosphere (et::atmosphere), which this loader does not generate")
+    if not getattr(sd, "_distant_emitters", None):
+        ld.add_default_atmosphere()
     # camera (:789-804)
     if ld.cameras:
         sel = next((c for c in ld.cameras if c["active"]), ld.cameras[0])

@@ -1,7 +1,7 @@
 """Headless render of a reference scene file on the GPU:  python -m etx_tracer_b200.render scene.json [-o out.exr]
 
 What the reference application does between File > Open and File > Save (sources/raytracer/app.cxx: load_scene_file :318-352, the integrator
-selected by options.json "integrator" :88-99, on_save_image_selected :261-295) without its window: the scene loader (loader.py), one of the two
+selected by options.json "integrator" :88-99, on_save_image_selected :261-295) without its window: the scene loader (the module's C++ one by default; host/render_main.cpp is this program in C++), one of the two
 device integrators — "vcm" (CPUVCM's algorithm, the default) or "pt" (CPUPathTracing's) — pumped like IntegratorThread pumps Integrator::update,
 and the film export (OpenEXR float layer, or the tone-mapped PNG).  There is no CPU fallback: without a CUDA device this fails.
 """
@@ -10,7 +10,7 @@ import sys
 import time
 
 from . import loader, structs as S
-from .api import GPUPathTracing, GPUVCM
+from .api import GPUPathTracing, GPUVCM, SceneFile
 
 LAYERS = {"result": S.FILM_RESULT, "camera": S.FILM_CAMERA, "light": S.FILM_LIGHT, "normals": S.FILM_NORMALS, "albedo": S.FILM_ALBEDO}
 
@@ -24,12 +24,13 @@ def main(argv=None):
     ap.add_argument("--layer", choices=sorted(LAYERS), default="result")
     ap.add_argument("--exposure", type=float, default=1.0, help="tone map exposure of a .png output")
     ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE", help="integrator option in the reference's ids, e.g. vcm-merging=0 or nee=0")
+    ap.add_argument("--loader", choices=("cpp", "python"), default="cpp", help="the module's C++ scene loader (etxb_scene_file_load) or its Python twin (loader.py)")
     ap.add_argument("--noise-threshold", type=float, default=None, help="pt: Scene::noise_threshold of the adaptive sampling (default: the scene's)")
     args = ap.parse_args(argv)
 
     t0 = time.time()
-    sd = loader.load_scene(args.scene)
-    for w in sd.loader_warnings:
+    sd = SceneFile(args.scene) if args.loader == "cpp" else loader.load_scene(args.scene)
+    for w in (sd.warnings if args.loader == "cpp" else sd.loader_warnings):
         print("warning:", w, file=sys.stderr)
     print(f"loaded {sd.triangle_count} triangles, {sd.width}x{sd.height}, in {time.time() - t0:.2f} s", file=sys.stderr)
     if args.spp > 0:

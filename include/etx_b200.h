@@ -349,6 +349,36 @@ int etxb_write_exr(const char* file_name, const float* rgba, uint32_t width, uin
 int etxb_write_png(const char* file_name, const uint8_t* rgba8, uint32_t width, uint32_t height);
 int etxb_tonemap_rgba8(const float* rgba, uint64_t pixel_count, float exposure, uint8_t* out_rgba8);
 
+/* ---- scene files: SceneRepresentation::load_from_file (render/host/scene_representation.cxx:679-838) ------------------
+ * Reads the reference's `.json` + `.obj` + `.mtl` scene dialect (et::camera / et::medium / et::dir / et::env / et::spectrum blocks, the material
+ * directives of parse_material :1682-2079, PNG / EXR / HDR / PFM textures) into the Scene / Camera PODs etxb_create takes: host C++, no CUDA, no
+ * third-party reader.  The object owns every array the PODs point into; keep it alive until etxb_create has returned (the module copies).
+ * A file without an et::dir / et::env block gets the reference's default atmosphere (sun + sky images, generated here on the host threads).
+ * Failure: ETXB_ERR_UNSUPPORTED with the reason in `err` (missing file, NanoVDB volume, glTF).
+ * `data_folder` = where tables.bin lives; NULL = the `data/` folder beside the shared library. */
+typedef struct etxb_scene_file etxb_scene_file;
+int etxb_scene_file_load(const char* file_name, const char* data_folder, etxb_scene_file** out, char* err, uint64_t err_bytes);
+const etxb_scene* etxb_scene_file_scene(const etxb_scene_file* sf);
+const etxb_camera* etxb_scene_file_camera(const etxb_scene_file* sf);
+uint32_t etxb_scene_file_warning_count(const etxb_scene_file* sf);
+const char* etxb_scene_file_warning(const etxb_scene_file* sf, uint32_t index);
+uint32_t etxb_scene_file_material_count(const etxb_scene_file* sf);
+const char* etxb_scene_file_material_name(const etxb_scene_file* sf, uint32_t index);
+void etxb_scene_file_free(etxb_scene_file* sf);
+/* Scene::samples (the iteration count the integrators stop at, and what selects the blue-noise variant) — the application's "samples" setting */
+void etxb_scene_file_set_samples(etxb_scene_file* sf, uint32_t samples);
+/* One call from file to device: etxb_upload_color_tables + etxb_upload_blue_noise (the variant BNSampler picks for scene.samples,
+ * thirdparty/bluenoise/bluenoise.cxx:73-95) + etxb_upload_scene, all from tables.bin and the loaded PODs. */
+int etxb_scene_file_commit(etxb_ctx* ctx, const etxb_scene_file* sf);
+/* The procedural sun disk (128 x 128) and sky dome (sky_width x sky_height) images of an atmosphere block — what the loader generates for a
+ * `newmtl et::atmosphere` block and for every scene file that declares no distant emitter (scene_representation.cxx:805-820, :1376-1495;
+ * render/host/scattering.cxx) — for callers that assemble the emitters themselves.  parameters = altitude, anisotropy, rayleigh, mie, ozone
+ * (scattering::Parameters); direction normalised; angular_size in radians; either output may be NULL. */
+int etxb_atmosphere_images(const char* data_folder, const float direction[3], float angular_size, const float parameters[5], uint32_t sky_width, uint32_t sky_height,
+                           float* sun_rgba_128x128, float* sky_rgba);
+/* A table of tables.bin by name ("color_tables/xyz_441x3", "bluenoise/sobol", "spectra/gold.eta_power", ...); NULL when absent. */
+const void* etxb_scene_file_table(const etxb_scene_file* sf, const char* name, uint64_t* bytes);
+
 /* ---- the unidirectional path tracer on the same context -----------------------------------------
  * Replaces CPUPathTracing (rt/integrators/path_tracing.cxx:12-170) + run_path_iteration (rt/shared/path_tracing_shared.hxx:485-510)
  * + Film::accumulate_camera_image with the normal / albedo layers and Film::estimate_noise_levels (render/host/film.cxx:173-330).

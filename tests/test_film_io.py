@@ -112,6 +112,7 @@ def test_tonemap_and_png_writer(tmp_path):
     ref = _reference_readers()
     if ref is not None:  # stb_image, the reader the reference's texture pool uses
         w, h, n = C.c_int(), C.c_int(), C.c_int()
+        ref.stbi_set_flip_vertically_on_load(0)  # a process-wide switch the reference's texture pool leaves on (image_pool.cxx:344)
         p = ref.stbi_load(f.encode(), C.byref(w), C.byref(h), C.byref(n), 4)
         assert bool(p) and (w.value, h.value, n.value) == (img.shape[1], img.shape[0], 4)
         assert np.array_equal(np.ctypeslib.as_array(p, ldr.shape), ldr)

@@ -293,3 +293,79 @@ def test_cpp_path_tracing_adapter_renders_on_the_device(tmp_path):
     ref = g.film(S.FILM_CAMERA)
     g.close()
     assert np.array_equal(film[..., :3].view(np.uint32), ref[..., :3].view(np.uint32))
+
+
+def _build_native_renderer(tmp_path):
+    lib = etx_build.lib_path("fast")
+    if not os.path.exists(lib):
+        etx_build.build(("fast",))
+    exe = tmp_path / "etx_render"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-Wall", "-Werror", f"-I{ROOT}", os.path.join(ROOT, "etx_tracer_b200", "host", "render_main.cpp"), lib,
+                           f"-Wl,-rpath,{os.path.dirname(lib)}", "-o", str(exe)])
+    return str(exe)
+
+
+def _tiny_scene(tmp_path):
+    (tmp_path / "s.obj").write_text("mtllib s.mtl\nv -1 0 -1\nv 1 0 -1\nv 1 0 1\nv -1 0 1\nv -0.3 1.9 -0.3\nv 0.3 1.9 -0.3\nv 0.3 1.9 0.3\nv -0.3 1.9 0.3\n"
+                                    "usemtl floor\nf 1 4 3 2\nusemtl lamp\nf 5 6 7 8\n")
+    (tmp_path / "s.mtl").write_text("newmtl floor\nKd 0.6 0.5 0.4\n\nnewmtl lamp\nKd 0 0 0\nKe 9 9 9\n\nnewmtl et::camera\nviewport 40 30\norigin 0 1 3.5\ntarget 0 0.8 0\nfov 45\n")
+    (tmp_path / "s.json").write_text('{"geometry": "s.obj", "materials": "s.mtl", "samples": 4, "max-path-length": 6}')
+    return str(tmp_path / "s.json")
+
+
+def test_native_renderer_loads_the_scene_and_fails_closed_without_device(tmp_path):
+    """host/render_main.cpp (scene file -> C++ loader -> integrator adapter -> film export) compiles warning-free against the C ABI; on a box without a
+    GPU it gets as far as the loaded scene and stops with exit code 4, a scene it cannot read is exit code 3."""
+    exe = _build_native_renderer(tmp_path)
+    out = subprocess.run([exe, _tiny_scene(tmp_path), "-o", str(tmp_path / "o.exr"), "--option", "vcm-merging=0"], capture_output=True, text=True)
+    assert out.returncode in (0, 4), (out.returncode, out.stdout[-300:], out.stderr[-300:])
+    if out.returncode == 4:
+        assert "no CUDA device" in out.stderr and not os.path.exists(tmp_path / "o.exr")
+    out = subprocess.run([exe, str(tmp_path / "absent.json")], capture_output=True, text=True)
+    assert out.returncode == 3 and "absent.json" in out.stderr
+    assert subprocess.run([exe], capture_output=True).returncode == 2
+
+
+def test_scene_file_tables_are_the_shipped_tables(tmp_path):
+    """tables.bin (what the C++ side reads) holds the same colour, blue-noise and spectrum tables as the npz files the Python side reads."""
+    import numpy as np
+    from etx_tracer_b200 import api, scenes
+    sf = api.SceneFile(_tiny_scene(tmp_path))
+    for stem in ("color_tables", "bluenoise", "spectra"):
+        z = scenes.tables(stem)
+        for key in z:
+            if key.startswith("blackbody_") or key.startswith("nblackbody_"):
+                continue
+            t = sf.table(f"{stem}/{key}", z[key].dtype)
+            assert t is not None and np.array_equal(t, np.asarray(z[key]).reshape(-1)), f"{stem}/{key}: run tools/make_tables_bin.py"
+    assert sf.table("bluenoise/none") is None
+    assert (sf.width, sf.height, sf.triangle_count) == (40, 30, 4) and int(sf.scene["samples"][0]) == 4
+    sf.lib.etxb_scene_file_set_samples(sf.h, 9)
+    assert int(sf.scene["samples"][0]) == 9
+    sf.close()
+
+
+@pytest.mark.gpu
+def test_native_renderer_renders_what_the_python_front_end_renders(tmp_path):
+    """The C++ program and `python -m etx_tracer_b200.render` on the same scene file: same film (the light image is a float-atomic sum, so equal to
+    rounding), both integrators, EXR and tone-mapped PNG."""
+    import numpy as np
+    from etx_tracer_b200 import loader, render
+    exe = _build_native_renderer(tmp_path)
+    scene = _tiny_scene(tmp_path)
+    a, b = str(tmp_path / "native.exr"), str(tmp_path / "python.exr")
+    out = subprocess.run([exe, scene, "-o", a, "--spp", "5", "--option", "vcm-merging=0"], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout[-500:], out.stderr[-500:])
+    assert "5 of 5 iterations" in out.stdout
+    assert render.main([scene, "-o", b, "--spp", "5", "--option", "vcm-merging=0"]) == 0
+    fa, fb = loader.read_image(a)[0].astype(np.float64), loader.read_image(b)[0].astype(np.float64)
+    assert fa.shape == fb.shape == (30, 40, 4) and fb[..., :3].mean() > 1e-3
+    err = float(np.sqrt(((fa - fb)[..., :3] ** 2).sum()) / np.sqrt((fb[..., :3] ** 2).sum()))
+    assert err < 1e-5, f"relative L2 {err:.3e}"
+    a, b = str(tmp_path / "native.png"), str(tmp_path / "python.png")
+    out = subprocess.run([exe, scene, "-o", a, "--integrator", "pt", "--spp", "6", "--png-exposure", "2.0", "--option", "bn=0"], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout[-500:], out.stderr[-500:])
+    assert render.main([scene, "-o", b, "--integrator", "pt", "--spp", "6", "--exposure", "2.0", "--option", "bn=0"]) == 0
+    pa, pb = loader.read_image(a)[0].astype(np.int32), loader.read_image(b)[0].astype(np.int32)
+    assert pa.shape == pb.shape == (30, 40, 4) and pb[..., :3].max() > 30
+    assert np.abs(pa - pb).max() <= 1
