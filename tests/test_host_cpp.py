@@ -343,29 +343,3 @@ def test_scene_file_tables_are_the_shipped_tables(tmp_path):
     sf.lib.etxb_scene_file_set_samples(sf.h, 9)
     assert int(sf.scene["samples"][0]) == 9
     sf.close()
-
-
-@pytest.mark.gpu
-def test_native_renderer_renders_what_the_python_front_end_renders(tmp_path):
-    """The C++ program and `python -m etx_tracer_b200.render` on the same scene file: same film (the light image is a float-atomic sum, so equal to
-    rounding), both integrators, EXR and tone-mapped PNG."""
-    import numpy as np
-    from etx_tracer_b200 import loader, render
-    exe = _build_native_renderer(tmp_path)
-    scene = _tiny_scene(tmp_path)
-    a, b = str(tmp_path / "native.exr"), str(tmp_path / "python.exr")
-    out = subprocess.run([exe, scene, "-o", a, "--spp", "5", "--option", "vcm-merging=0"], capture_output=True, text=True)
-    assert out.returncode == 0, (out.returncode, out.stdout[-500:], out.stderr[-500:])
-    assert "5 of 5 iterations" in out.stdout
-    assert render.main([scene, "-o", b, "--spp", "5", "--option", "vcm-merging=0"]) == 0
-    fa, fb = loader.read_image(a)[0].astype(np.float64), loader.read_image(b)[0].astype(np.float64)
-    assert fa.shape == fb.shape == (30, 40, 4) and fb[..., :3].mean() > 1e-3
-    err = float(np.sqrt(((fa - fb)[..., :3] ** 2).sum()) / np.sqrt((fb[..., :3] ** 2).sum()))
-    assert err < 1e-5, f"relative L2 {err:.3e}"
-    a, b = str(tmp_path / "native.png"), str(tmp_path / "python.png")
-    out = subprocess.run([exe, scene, "-o", a, "--integrator", "pt", "--spp", "6", "--png-exposure", "2.0", "--option", "bn=0"], capture_output=True, text=True)
-    assert out.returncode == 0, (out.returncode, out.stdout[-500:], out.stderr[-500:])
-    assert render.main([scene, "-o", b, "--integrator", "pt", "--spp", "6", "--exposure", "2.0", "--option", "bn=0"]) == 0
-    pa, pb = loader.read_image(a)[0].astype(np.int32), loader.read_image(b)[0].astype(np.int32)
-    assert pa.shape == pb.shape == (30, 40, 4) and pb[..., :3].max() > 30
-    assert np.abs(pa - pb).max() <= 1
