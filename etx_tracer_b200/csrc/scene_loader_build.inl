@@ -962,29 +962,13 @@ struct etxb_scene_file_impl {
         store3(v[tri.i[k]].nrm, normalize(load3(tri.geo_n) * area));  // every vertex belongs to one triangle: the first contribution is an assignment
       }
     }
-    // build_tangents (:337-398): without texture coordinates nothing; with them per-triangle UV-derivative tangents (NOT MikkTSpace)
+    // build_tangents (:337-398): without texture coordinates nothing; with them the tangent-space generator (scene_loader_tangents.inl)
     float lo[2] = {3.402823466e+38f, 3.402823466e+38f}, hi[2] = {-3.402823466e+38f, -3.402823466e+38f};
     for (const etxb_vertex& x : v) {
       lo[0] = fminf(lo[0], x.tex[0]), lo[1] = fminf(lo[1], x.tex[1]);
       hi[0] = fmaxf(hi[0], x.tex[0]), hi[1] = fmaxf(hi[1], x.tex[1]);
     }
-    if (!v.empty() && ((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) > kEps)) {
-      for (const etxb_triangle& tri : triangles) {
-        etxb_vertex &a = v[tri.i[0]], &b = v[tri.i[1]], &c = v[tri.i[2]];
-        F3 e1 = load3(b.pos) - load3(a.pos), e2 = load3(c.pos) - load3(a.pos);
-        float du1 = b.tex[0] - a.tex[0], dv1 = b.tex[1] - a.tex[1], du2 = c.tex[0] - a.tex[0], dv2 = c.tex[1] - a.tex[1];
-        float det = du1 * dv2 - du2 * dv1;
-        F3 tan = (e1 * dv2 - e2 * dv1) / det;
-        if (!valid_vector(tan)) continue;
-        tan = normalize(tan);
-        float sign = det < 0.0f ? -1.0f : 1.0f;
-        for (uint32_t k = 0; k < 3; ++k) {
-          etxb_vertex& x = v[tri.i[k]];
-          store3(x.tan, tan);
-          store3(x.btn, normalize(cross(tan, load3(x.nrm)) * sign));
-        }
-      }
-    }
+    if (!v.empty() && ((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) > kEps)) tangents::generate(v, triangles);
     // validate_tangents (:400-418): orthonormal_basis (math.hxx:737-746) where no frame exists, then orthogonalize (scene.hxx:133-139) everywhere
     for (size_t i = 0; i < v.size(); ++i) {
       etxb_vertex& x = v[i];

@@ -3,11 +3,11 @@ etx_tracer_b200/loader.py) against the reference's OWN loader (scene_representat
 friends compiled in place into oracle/_ref/libreference_loader.so — test infrastructure): the same scene FILES read by both, the Scene / Camera
 PODs compared array by array.  CPU only; skipped where the reference tree is absent.
 
-Byte-identical: triangles (indices, material, geometric normal), vertex positions / normals / texture coordinates, tangent frames of meshes without
-texture coordinates, every Material record, emitter profiles / instances / the emitter distribution, media, images (pixels, options, sampling
-tables), the scene scalars, the camera (up to the sign of a zero in `position`).  Stated differences: tangent frames of meshes WITH texture
-coordinates (per-triangle UV derivatives here, MikkTSpace there), black-body spectra to 1e-6 relative (glibc expf against numpy's float32 exp),
-padding bytes the reference leaves uninitialised."""
+Byte-identical: triangles (indices, material, geometric normal), vertex positions / normals / texture coordinates, tangent frames (C++ loader: all,
+incl. the 414 954 vertices of the Cornell asset; Python twin: of meshes without texture coordinates), every Material record, emitter profiles / instances / the emitter distribution, media, images (pixels, options, sampling
+tables), the scene scalars, the camera (up to the sign of a zero in `position`).  Stated differences, Python twin only: tangent frames of meshes WITH
+texture coordinates (per-triangle UV derivatives there, the tangent-space generator in the reference and in the C++ loader), black-body spectra to 1e-6
+relative (glibc expf against numpy's float32 exp); both: padding bytes the reference leaves uninitialised."""
 import ctypes as C
 import json
 import os
@@ -35,7 +35,14 @@ LOADERS = {"cpp": (_load_cpp, api.EtxbError), "python": (loader.load_scene, load
 @pytest.fixture(params=["cpp", "python"])
 def load(request):
     """the loader under test: the C ABI's etxb_scene_file_load (host C++ of the module) and the Python twin, held to the same comparisons"""
-    return LOADERS[request.param][0]
+    fn = LOADERS[request.param][0]
+
+    def run(path):
+        return fn(path)
+    # meshes with texture coordinates: the C++ loader restates the tangent-space generator the reference calls (bit-identical frames), the Python
+    # twin keeps per-triangle UV derivatives (a stated difference)
+    run.exact_tangents = request.param == "cpp"
+    return run
 
 
 def _view(av, dt):
@@ -144,7 +151,7 @@ def test_shipped_cornell_asset_matches_the_reference_loader(ref, load):
     rs = ref("assets/cornellbox/cornellbox.json")
     sd = load(os.path.join(os.environ.get("ETX_REFERENCE", "/root/reference"), "bin", "assets", "cornellbox", "cornellbox.json"))
     assert sd.triangle_count == 138318 and (sd.width, sd.height) == (640, 640)
-    problems = compare_scenes(rs, sd, uv_tangents_exact=False)  # the asset has texture coordinates: MikkTSpace frames in the reference
+    problems = compare_scenes(rs, sd, uv_tangents_exact=load.exact_tangents)  # the asset has texture coordinates: MikkTSpace frames in the reference
     assert not problems, problems
     rs.close()
 
@@ -153,7 +160,7 @@ def test_saved_scene_variant_matches_the_reference_loader(ref, load):
     """cornellbox.etx.json + cornellbox.etx.materials: what the application writes back (RGB emitter colours, et::camera block, medium ids)."""
     rs = ref("assets/cornellbox/cornellbox.etx.json")
     sd = load(os.path.join(os.environ.get("ETX_REFERENCE", "/root/reference"), "bin", "assets", "cornellbox", "cornellbox.etx.json"))
-    problems = compare_scenes(rs, sd, uv_tangents_exact=False)
+    problems = compare_scenes(rs, sd, uv_tangents_exact=load.exact_tangents)
     assert not problems, problems
     rs.close()
 
@@ -402,7 +409,7 @@ def test_textures_match_the_reference_loader(ref, tmp_path, load):
     rs = ref(path)
     sd = load(path)
     assert int(sd.scene["images"]["count"][0]) == int(rs.scene["images"]["count"][0]) == 5  # sky, albedo, normal map, glow, pixel filter
-    problems = compare_scenes(rs, sd, uv_tangents_exact=False)
+    problems = compare_scenes(rs, sd, uv_tangents_exact=load.exact_tangents)
     assert not problems, problems
     rs.close()
 
@@ -458,7 +465,7 @@ def test_hdr_pfm_images_and_parametric_media_match_the_reference_loader(ref, tmp
     path = _write_scene(tmp_path, obj=obj, mtl=mtl)
     rs = ref(path)
     sd = load(path)
-    problems = compare_scenes(rs, sd, uv_tangents_exact=False)
+    problems = compare_scenes(rs, sd, uv_tangents_exact=load.exact_tangents)
     assert not problems, problems
     rs.close()
 
@@ -492,7 +499,7 @@ def test_cpp_loader_matches_the_python_loader(tmp_path):
     mtl = mtl.replace("collimated 0.4 twosided", "collimated 0.4 twosided image albedo.png")
     path = _write_scene(tmp_path, obj=obj, mtl=mtl)
     a, b = loader.load_scene(path), _load_cpp(path)
-    problems = compare_scenes(a, b, uv_tangents_exact=True)
+    problems = compare_scenes(a, b, uv_tangents_exact=False)  # the mesh has texture coordinates: the twin's frames are UV-derivative ones
     assert not problems, problems
     assert sorted(b.material_names) == sorted(a.material_names)
     b.close()
@@ -662,7 +669,7 @@ def test_compressed_png_files_decode_like_the_reference(ref, tmp_path, load, cas
     rs = ref(path)
     sd = load(path)
     assert int(sd.scene["images"]["count"][0]) == int(rs.scene["images"]["count"][0]) == 3  # the placeholder environment, the texture, the pixel filter
-    problems = compare_scenes(rs, sd, uv_tangents_exact=False)
+    problems = compare_scenes(rs, sd, uv_tangents_exact=load.exact_tangents)
     assert not problems, problems
     rs.close()
 
@@ -741,3 +748,59 @@ def test_a_scene_without_distant_emitters_gets_the_default_atmosphere(tmp_path, 
     (tmp_path / "s.mtl").write_text(ATMOSPHERE_MTL + "\nnewmtl et::dir\ncolor 2 2 2\ndirection 0 1 0\n")
     sd2 = load(str(tmp_path / "s.json"))
     assert [int(c) for c in _view(sd2.scene["emitter_profiles"], S.EMITTER_PROFILE)["cls"]] == [S.EMITTER_DIRECTIONAL, S.EMITTER_AREA]
+
+
+def _tangent_stress_obj():
+    """A smooth UV sphere whose right half mirrors its texture coordinates (orientation flip along a seam), a fin that makes one edge non-manifold, a
+    triangle without texture area (it groups with whatever claims it first) and a flat-shaded strip (split normals along shared positions)."""
+    rng = np.random.default_rng(21)
+    nu, nv = 20, 10
+    lines = ["mtllib room.mtl"]
+    for j in range(nv + 1):
+        for i in range(nu + 1):
+            phi, theta = 2 * np.pi * i / nu, np.pi * j / nv
+            p = np.array([np.sin(theta) * np.cos(phi), np.cos(theta), np.sin(theta) * np.sin(phi)])
+            lines.append("v %.6f %.6f %.6f" % tuple(0.7 * p + [0.0, 1.0, 0.0]))
+            lines.append("vn %.6f %.6f %.6f" % tuple(p))
+            u = i / nu
+            lines.append("vt %.6f %.6f" % ((1.0 - u) if i > nu // 2 else u, 1.0 - j / nv + 0.01 * rng.random()))
+    lines.append("usemtl Floor")
+    for j in range(nv):
+        for i in range(nu):
+            a, b, c, d = (j * (nu + 1) + i + 1, j * (nu + 1) + i + 2, (j + 1) * (nu + 1) + i + 2, (j + 1) * (nu + 1) + i + 1)
+            if j > 0:
+                lines.append(f"f {a}/{a}/{a} {b}/{b}/{b} {c}/{c}/{c}")
+            if j < nv - 1:
+                lines.append(f"f {a}/{a}/{a} {c}/{c}/{c} {d}/{d}/{d}")
+    n = (nu + 1) * (nv + 1)
+    # the fin: a third triangle on the edge between the sphere's vertices (5, 2) and (5, 3)
+    a, b = 5 * (nu + 1) + 3, 5 * (nu + 1) + 4
+    lines += ["v 0.2 1.1 1.4", "vn 0 0 1", "vt 0.3 0.9", f"f {a}/{a}/{a} {b}/{b}/{b} {n + 1}/{n + 1}/{n + 1}"]
+    # no texture area
+    lines += ["v 2 0 0", "v 2 1 0", "v 2 0 1", "vt 0.5 0.5", f"f {n + 2}/{n + 2}/{n + 1} {n + 3}/{n + 2}/{n + 1} {n + 4}/{n + 2}/{n + 1}"]
+    # flat strip without normals (validate_normals gives every corner its triangle's normal), texture coordinates shared along the strip
+    base_v, base_t = n + 5, n + 3
+    for k in range(6):
+        lines += ["v %.3f %.3f -2" % (0.4 * k, 0.3 * (k % 2)), "v %.3f %.3f -1.5" % (0.4 * k, 0.3 * (k % 2)), "vt %.3f 0" % (k / 5), "vt %.3f 1" % (k / 5)]
+    for k in range(5):
+        v0, t0 = base_v + 2 * k, base_t + 2 * k
+        lines += [f"f {v0}/{t0} {v0 + 2}/{t0 + 2} {v0 + 3}/{t0 + 3}", f"f {v0}/{t0} {v0 + 3}/{t0 + 3} {v0 + 1}/{t0 + 1}"]
+    return "\n".join(lines) + "\n"
+
+
+def test_tangent_frames_match_the_reference_generator(ref, tmp_path):
+    """csrc/scene_loader_tangents.inl against the generator the reference calls (thirdparty/mikktspace through build_tangents): mirrored mapping, a
+    non-manifold edge, a triangle without texture area, hard edges.  Bit-identical frames; the generator's unsorted final edge run (see the header of
+    the .inl) may cost a handful of corners at the end of the mesh, never more."""
+    path = _write_scene(tmp_path, obj=_tangent_stress_obj())
+    rs = ref(path)
+    sd = _load_cpp(path)
+    va, vb = _view(rs.scene["vertices"], S.VERTEX), _view(sd.scene["vertices"], S.VERTEX)
+    assert va.shape == vb.shape and len(va) > 1000
+    assert not compare_scenes(rs, sd, uv_tangents_exact=False)
+    same = (va["tan"].view(np.uint32) == vb["tan"].view(np.uint32)).all(axis=1) & (va["btn"].view(np.uint32) == vb["btn"].view(np.uint32)).all(axis=1)
+    assert (~same).sum() <= 6, f"{int((~same).sum())} of {len(same)} corners differ"
+    flips = np.einsum("ij,ij->i", np.cross(vb["nrm"], vb["tan"]), vb["btn"])
+    assert (flips > 0.5).any() and (flips < -0.5).any(), "both orientations occur in the mirrored mapping"
+    rs.close()
+    sd.close()
