@@ -200,10 +200,18 @@ struct etxb_scene_file_impl {
     if (hit != image_cache.end()) return hit->second;
     auto rec = std::make_unique<ImageRecord>();
     options |= IMG_PERFORM_LOADING;
+    std::string problem;
+    bool loaded = false;
     try {
       rec->px = read_image(path);
+      loaded = true;
     } catch (const LoadError& e) {
-      if (file_exists(path)) warn(e.text + "; using the 1x1 white placeholder");
+      problem = e.text;
+    } catch (const std::exception& e) {  // a container refusing a size a corrupt header asked for
+      problem = path + ": " + e.what();
+    }
+    if (!loaded) {
+      if (file_exists(path)) warn(problem + "; using the 1x1 white placeholder");
       rec->px = Pixels();
       rec->px.w = rec->px.h = 1;
       rec->px.f32 = {1.0f, 1.0f, 1.0f, 1.0f};

@@ -153,7 +153,7 @@ Pixels read_png(const std::string& path) {
     const uint8_t* type = b + pos + 4;
     const uint8_t* body = b + pos + 8;
     if (pos + 12 + n > d.size()) break;
-    if (!memcmp(type, "IHDR", 4)) {
+    if (!memcmp(type, "IHDR", 4) && n >= 13) {
       w = be32(body), h = be32(body + 4), depth = body[8], ctype = body[9], interlace = body[12];
     } else if (!memcmp(type, "PLTE", 4)) {
       palette.assign(body, body + n);
@@ -255,6 +255,7 @@ Pixels read_exr(const std::string& path) {
   }
   pos += 1;
   if (!attrs.count("compression") || !attrs.count("dataWindow") || !attrs.count("channels")) fail(path + ": incomplete EXR header");
+  if (attrs["compression"].empty() || attrs["dataWindow"].size() < 16) fail(path + ": incomplete EXR header");
   int comp = uint8_t(attrs["compression"][0]);
   if (comp != 0 && comp != 2 && comp != 3) fail(path + ": this EXR compression is not read (none / ZIPS / ZIP are)");
   int32_t win[4];
@@ -265,6 +266,7 @@ Pixels read_exr(const std::string& path) {
   const std::string& chl = attrs["channels"];
   for (size_t cp = 0; cp < chl.size() && chl[cp] != 0;) {
     size_t e = chl.find('\0', cp);
+    if (e == std::string::npos || e + 17 > chl.size()) fail(path + ": bad EXR channel list");
     names.push_back(chl.substr(cp, e - cp));
     int32_t t;
     memcpy(&t, chl.data() + e + 1, 4);
@@ -274,6 +276,8 @@ Pixels read_exr(const std::string& path) {
   const uint32_t lines = (comp == 3) ? 16u : 1u, blocks = (h + lines - 1) / lines;
   size_t bytes_per_pixel = 0;
   for (int t : types) bytes_per_pixel += (t == 1) ? 2 : 4;
+  // a header is only believed as far as the file can back it: a deflate stream expands at most ~1032 : 1
+  if (win[2] < win[0] || win[3] < win[1] || bytes_per_pixel == 0 || uint64_t(w) * h * bytes_per_pixel > uint64_t(d.size()) * 1032u) fail(path + ": EXR header does not match the file size");
   Pixels out;
   out.w = w, out.h = h;
   out.f32.assign(size_t(w) * h * 4, 0.0f);
@@ -282,12 +286,14 @@ Pixels read_exr(const std::string& path) {
     uint64_t off;
     if (pos + size_t(k) * 8 + 8 > d.size()) fail(path + ": truncated EXR offset table");
     memcpy(&off, b + pos + size_t(k) * 8, 8);
+    if (off > d.size() || d.size() - off < 8) fail(path + ": bad EXR block offset");
     int32_t by = int32_t(le32(size_t(off)));
     uint32_t size = le32(size_t(off) + 4);
+    if (by < win[1] || by > win[3]) fail(path + ": EXR block outside the data window");
     const uint32_t nl = std::min<uint32_t>(lines, uint32_t(win[3] - by + 1));
     const size_t want = size_t(nl) * w * bytes_per_pixel;
     std::vector<uint8_t> raw;
-    if (size_t(off) + 8 + size > d.size()) fail(path + ": truncated EXR block");
+    if (size > d.size() - size_t(off) - 8) fail(path + ": truncated EXR block");
     if (comp != 0 && size < want) {
       std::vector<uint8_t> z = inflate_zlib(b + off + 8, size);
       for (size_t i = 1; i < z.size(); ++i) z[i] = uint8_t(z[i - 1] + z[i] - 128);  // predictor
@@ -341,6 +347,7 @@ Pixels read_hdr(const std::string& path) {
   if (tok.size() != 4 || tok[0] != "-Y" || tok[2] != "+X") fail(path + ": unsupported HDR orientation");
   const uint32_t h = uint32_t(atoi(tok[1].c_str())), w = uint32_t(atoi(tok[3].c_str()));
   pos = e + 1;
+  if (e == std::string::npos || w == 0 || h == 0 || uint64_t(w) * h > uint64_t(d.size()) * 64u) fail(path + ": HDR header does not match the file size");  // a run covers <= 127 texels of a plane in 2 bytes
   std::vector<uint8_t> rgbe(size_t(w) * h * 4);
   const bool rle = (w >= 8 && w < 32768 && pos + 4 <= d.size() && b[pos] == 2 && b[pos + 1] == 2 && (b[pos + 2] & 0x80) == 0);  // decided at the first scan line, like stb_image
   if (!rle) {
@@ -401,7 +408,7 @@ Pixels read_pfm(const std::string& path) {
   const char fmt = lines[0].size() > 1 ? lines[0][1] : 0;
   const uint32_t w = uint32_t(atoi(lines[1].c_str())), h = uint32_t(atoi(lines[2].c_str()));
   const uint32_t ch = (fmt == 'f') ? 1u : (fmt == 'F') ? 3u : 0u;
-  if (ch == 0 || w == 0 || h == 0 || pos + size_t(w) * h * ch * 4 > d.size()) fail(path + ": unsupported or truncated PFM file");
+  if (ch == 0 || w == 0 || h == 0 || uint64_t(w) * h > d.size() || pos + size_t(w) * h * ch * 4 > d.size()) fail(path + ": unsupported or truncated PFM file");
   Pixels out;
   out.w = w, out.h = h;
   out.f32.resize(size_t(w) * h * 4);
