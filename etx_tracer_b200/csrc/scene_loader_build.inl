@@ -118,6 +118,7 @@ struct etxb_scene_file_impl {
   std::vector<std::unique_ptr<ImageRecord>> images;
   std::vector<etxb_image> image_pods;
   std::vector<etxb_medium> mediums;
+  std::list<std::vector<float>> densities;  // the dense grids of heterogeneous media (addresses stay put)
   std::vector<etxb_emitter_profile> profiles;   // distant ones first (declared in the material file), area ones appended by commit
   std::vector<etxb_emitter> emitters;
   std::vector<etxb_distribution_entry> emitter_dist;
@@ -464,8 +465,24 @@ struct etxb_scene_file_impl {
       s_a = spd_rgb_reflectance(t(), {fmaxf(0.0f, ext.x - sca.x), fmaxf(0.0f, ext.y - sca.y), fmaxf(0.0f, ext.z - sca.z)});
     }
     const bool explicit_connections = !b.has("enclosed");
-    if (b.get("volume", v) && !trim(v).empty()) fail("heterogeneous media from NanoVDB files are not read by this loader");
-    medium_names[name] = add_medium(s_a, s_t, g, explicit_connections);
+    const uint32_t index = add_medium(s_a, s_t, g, explicit_connections);
+    medium_names[name] = index;
+    if (b.get("volume", v) && !trim(v).empty()) {  // MediumPool::add (medium_pool.cxx:41-59): a dense grid scaled to a maximum of 1
+      const std::string file = join(base_dir, trim(v));
+      const size_t dot = file.find_last_of('.');
+      if (dot == std::string::npos || lower(file.substr(dot)) != ".nvdb") fail(file + ": only NanoVDB (.nvdb) volume files are read");
+      DensityGrid grid = read_nvdb_density(file, warnings);
+      float max_density = 0.0f;
+      for (float f : grid.values) max_density = fmaxf(max_density, f);
+      if (max_density > 0.0f) {
+        for (float& f : grid.values) f /= max_density;
+        densities.push_back(std::move(grid.values));
+        etxb_medium& m = mediums[index];
+        m.cls = 1u;
+        m.density = {densities.back().data(), densities.back().size()};
+        memcpy(m.dimensions, grid.dim, sizeof(m.dimensions));
+      }
+    }
   }
 
   void add_distant(uint32_t cls, const Spd& spd, uint32_t image, F3 direction, float angular_size) {

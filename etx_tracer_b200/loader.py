@@ -8,7 +8,7 @@ validate_normals / validate_tangents :304-418, commit :420-455) read into the Sc
 Everything is built on `scenes.SceneData` (the same record builders the synthetic generators use); `tests/test_loader.py` compares the
 result with the reference's own loader (compiled in place as test infrastructure) array by array on the shipped Cornell asset and on
 generated scene files.  Known differences, all stated there: tangent frames of meshes WITH texture coordinates come from per-triangle UV
-derivatives instead of MikkTSpace (only normal maps and anisotropic roughness see them); NanoVDB volumes and glTF geometry are refused; the two images of
+derivatives instead of MikkTSpace (only normal maps and anisotropic roughness see them); NanoVDB volumes (the C++ loader reads them) and glTF geometry are refused here; the two images of
 an atmosphere block (`et::atmosphere`, and the default atmosphere of a file without distant emitters) come from the module's host code
 (etxb_atmosphere_images); this file is the Python twin of csrc/scene_loader.cpp, which is what the C ABI ships; image files: PNG (8-bit, non-interlaced), OpenEXR (float, scan lines, none / ZIP), Radiance HDR and the reference's PFM variant.
 The .mtl reader follows the reference's patched tinyobjloader (thirdparty/tinyobjloader/tiny_obj_loader.hxx:1900-2190): names are lower-cased,

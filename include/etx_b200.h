@@ -354,7 +354,8 @@ int etxb_tonemap_rgba8(const float* rgba, uint64_t pixel_count, float exposure, 
  * directives of parse_material :1682-2079, PNG / EXR / HDR / PFM textures) into the Scene / Camera PODs etxb_create takes: host C++, no CUDA, no
  * third-party reader.  The object owns every array the PODs point into; keep it alive until etxb_create has returned (the module copies).
  * A file without an et::dir / et::env block gets the reference's default atmosphere (sun + sky images, generated here on the host threads).
- * Failure: ETXB_ERR_UNSUPPORTED with the reason in `err` (missing file, NanoVDB volume, glTF).
+ * `et::medium ... volume file.nvdb` becomes a heterogeneous medium with a dense grid (own NanoVDB 32.x reader, codecs none / ZIP; medium_pool.cxx:102-159).
+ * Failure: ETXB_ERR_UNSUPPORTED with the reason in `err` (missing or corrupt file, BLOSC-compressed volume, glTF).
  * `data_folder` = where tables.bin lives; NULL = the `data/` folder beside the shared library. */
 typedef struct etxb_scene_file etxb_scene_file;
 int etxb_scene_file_load(const char* file_name, const char* data_folder, etxb_scene_file** out, char* err, uint64_t err_bytes);

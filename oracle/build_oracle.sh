@@ -53,4 +53,6 @@ build_loader() {
   rm -f $objs
 }
 if build_loader; then :; else echo "reference loader did not build; tests that use it will skip" >&2; fi
-echo "built: $(ls $OUT/*.so)"
+# nvdb_make : writes NanoVDB test files with the reference's own NanoVDB headers (oracle/nvdb_make.cxx)
+if g++ -std=c++17 -O1 -w -I"$REF/thirdparty/nanovdb" "$HERE/nvdb_make.cxx" -o "$OUT/nvdb_make" -pthread; then :; else echo "nvdb_make did not build; the .nvdb tests will skip" >&2; fi
+echo "built: $(ls $OUT/*.so) $(ls $OUT/nvdb_make 2>/dev/null)"

@@ -62,3 +62,37 @@ def test_default_atmosphere_scene_renders_bit_exact_on_the_device(oracle_mod, tm
         assert bit_equal(p.film(layer)[..., :3], o.film(layer)[..., :3]), layer
     p.close()
     o.close()
+
+
+def test_nanovdb_medium_scene_renders_bit_exact_on_the_device(oracle_mod, tmp_path):
+    """`et::medium … volume cloud.nvdb` read by the module's NanoVDB reader into the dense grid of a heterogeneous medium: the parity build against the
+    oracle on the loader's PODs (delta tracking through the grid), both integrators."""
+    import os
+    from conftest import bit_equal
+    from etx_tracer_b200 import api, structs as S
+    from test_loader import MTL, NVDB_MAKE, _write_scene
+    if not os.path.exists(NVDB_MAKE):
+        pytest.skip("oracle/_ref/nvdb_make not built")
+    subprocess.check_call([NVDB_MAKE, "blobs", str(tmp_path / "cloud.nvdb")])
+    sd = api.SceneFile(_write_scene(tmp_path, mtl=MTL.replace("scattering 0.4", "scattering 0.4\nvolume cloud.nvdb")), flavor="parity")
+    assert 1 in [int(m["cls"]) for m in np.frombuffer((__import__("ctypes").c_char * (int(sd.scene["mediums"]["count"][0]) * S.MEDIUM.itemsize)).from_address(
+        int(sd.scene["mediums"]["a"][0])), dtype=S.MEDIUM)]
+    o = oracle_mod.Oracle(sd)
+    o.begin(0)
+    o.run(2, threads=1)
+    g = api.GPUVCM(sd, flavor="parity")
+    g.render(2)
+    for bid, dt in ((S.BUF_LIGHT_SAMPLER, np.uint32), (S.BUF_LV_POS, np.float32), (S.BUF_CAMERA_SAMPLER, np.uint32), (S.BUF_CAMERA_GATHERED, np.float32)):
+        assert bit_equal(g.buffer(bid, dt), o.buffer(bid, dt)), f"buffer {bid}"
+    assert bit_equal(g.film(S.FILM_CAMERA)[..., :3], o.film(S.FILM_CAMERA)[..., :3])
+    g.close()
+    o.set_integrator(S.INTEGRATOR_PT)
+    o.pt_set_options(S.default_pt_options())
+    o.begin(0)
+    o.run(2, threads=1)
+    p = api.GPUPathTracing(sd, flavor="parity")
+    p.render(2)
+    assert bit_equal(p.buffer(S.BUF_CAMERA_SAMPLER, np.uint32), o.buffer(S.BUF_CAMERA_SAMPLER, np.uint32))
+    assert bit_equal(p.film(S.FILM_CAMERA)[..., :3], o.film(S.FILM_CAMERA)[..., :3])
+    p.close()
+    o.close()
