@@ -135,7 +135,7 @@ DensityGrid read_nvdb_density(const std::string& path, std::vector<std::string>&
   g.at(tree.root + nvdb::kRootDataBytes, size_t(tree.tiles) * nvdb::kRootTileBytes);
   if (hi[0] <= lo[0] || hi[1] <= lo[1] || hi[2] <= lo[2]) return out;  // an empty tree has an inverted box
   const uint64_t dx = uint64_t(int64_t(hi[0]) - lo[0]), dy = uint64_t(int64_t(hi[1]) - lo[1]), dz = uint64_t(int64_t(hi[2]) - lo[2]);
-  if (dx > 4096 || dy > 4096 || dz > 4096 || dx * dy * dz > (1ull << 31)) fail(path + ": the volume's index box is too large for a dense grid");
+  if (dx > 4096 || dy > 4096 || dz > 4096 || dx * dy * dz > (1ull << 30)) fail(path + ": the volume's index box is too large for a dense grid");
   out.dim[0] = uint32_t(dx), out.dim[1] = uint32_t(dy), out.dim[2] = uint32_t(dz);
   out.values.assign(size_t(dx * dy * dz), 0.0f);
   float min_val = 3.402823466e+38f, max_val = -3.402823466e+38f;
