@@ -7,6 +7,7 @@
 //
 //   g++ -std=c++17 -O2 -pthread -I<repo> etx_tracer_b200/host/render_main.cpp <repo>/etx_tracer_b200/libetx_b200.so -Wl,-rpath,<repo>/etx_tracer_b200 -o etx_render
 //   etx_render scene.json -o out.exr [--integrator vcm|pt] [--spp N] [--option key=value]... [--png-exposure E] [--layer N]
+//   etx_render --options bin/options.json -o out.exr        the application's own options file names the scene and the integrator
 //
 // Exit codes: 0 rendered and saved; 2 usage; 3 the scene could not be loaded; 4 no CUDA device (the module has no CPU path); 5 device error; 6 save failed.
 #include <chrono>
@@ -24,7 +25,8 @@
 namespace {
 
 struct Arguments {
-  std::string scene, output = "out.exr", integrator = "vcm";
+  std::string scene, output = "out.exr", integrator = "vcm", options_file;
+  bool integrator_given = false;
   std::vector<std::pair<std::string, double>> options;
   uint32_t spp = 0, layer = ETXB_FILM_RESULT;
   float exposure = 1.0f;
@@ -44,6 +46,7 @@ Arguments parse(int argc, char** argv) {
       const char* v = next();
       if (!v || (strcmp(v, "vcm") != 0 && strcmp(v, "pt") != 0)) return a;
       a.integrator = v;
+      a.integrator_given = true;
     } else if (s == "--spp") {
       const char* v = next();
       if (!v) return a;
@@ -56,6 +59,10 @@ Arguments parse(int argc, char** argv) {
       const char* v = next();
       if (!v) return a;
       a.exposure = float(atof(v));
+    } else if (s == "--options") {  // the application's options.json: "scene" and "integrator" (raytracer/app.cxx:88-105)
+      const char* v = next();
+      if (!v) return a;
+      a.options_file = v;
     } else if (s == "--option") {
       const char* v = next();
       const char* eq = v ? strchr(v, '=') : nullptr;
@@ -65,6 +72,27 @@ Arguments parse(int argc, char** argv) {
       return a;
     } else {
       a.scene = s;
+    }
+  }
+  if (!a.options_file.empty()) {
+    char value[2048] = {};
+    if (a.scene.empty() && etxb_options_file_string(a.options_file.c_str(), "scene", value, sizeof(value)) > 0) {
+      // the application stores the path relative to its working directory, which is the folder of options.json
+      std::string folder = a.options_file.substr(0, a.options_file.find_last_of('/') == std::string::npos ? 0 : a.options_file.find_last_of('/') + 1);
+      a.scene = (value[0] == '/') ? std::string(value) : (folder + value);
+    }
+    if (!a.integrator_given && etxb_options_file_string(a.options_file.c_str(), "integrator", value, sizeof(value)) > 0) {
+      // "VCM (CPU)" / "VCM (B200)" -> vcm, "Path Tracing (CPU)" / "Path Tracing (B200)" -> pt; the bidirectional integrator has no device twin:
+      // VCM with merging off is the reference's own equivalent (vcm_shared.hxx:33)
+      const std::string name = value;
+      if (name.compare(0, 12, "Path Tracing") == 0) {
+        a.integrator = "pt";
+      } else if (name.compare(0, 13, "Bidirectional") == 0) {
+        a.integrator = "vcm";
+        a.options.insert(a.options.begin(), {"vcm-merging", 0.0});
+      } else {
+        a.integrator = "vcm";
+      }
     }
   }
   a.ok = !a.scene.empty();
@@ -120,7 +148,7 @@ int pump(Integrator& integrator, const Arguments& args, etxb_scene_file* file, u
 int main(int argc, char** argv) {
   Arguments args = parse(argc, argv);
   if (!args.ok) {
-    std::fprintf(stderr, "usage: %s scene.json [-o out.exr|out.png] [--integrator vcm|pt] [--spp N] [--option key=value] [--png-exposure E] [--layer N]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s scene.json [-o out.exr|out.png] [--integrator vcm|pt] [--spp N] [--option key=value] [--options options.json] [--png-exposure E] [--layer N]\n", argv[0]);
     return 2;
   }
   char error[1024] = {};

@@ -371,6 +371,9 @@ void etxb_scene_file_set_samples(etxb_scene_file* sf, uint32_t samples);
 /* One call from file to device: etxb_upload_color_tables + etxb_upload_blue_noise (the variant BNSampler picks for scene.samples,
  * thirdparty/bluenoise/bluenoise.cxx:73-95) + etxb_upload_scene, all from tables.bin and the loaded PODs. */
 int etxb_scene_file_commit(etxb_ctx* ctx, const etxb_scene_file* sf);
+/* A string value of the application's options file (util/options.cxx; ids "integrator" and "scene" are what RTApplication::init reads,
+ * raytracer/app.cxx:88-105): copies it to `out` (NUL-terminated, truncated to out_bytes) and returns its length; 0 = id absent; < 0 = error. */
+int etxb_options_file_string(const char* file_name, const char* id, char* out, uint64_t out_bytes);
 /* The procedural sun disk (128 x 128) and sky dome (sky_width x sky_height) images of an atmosphere block — what the loader generates for a
  * `newmtl et::atmosphere` block and for every scene file that declares no distant emitter (scene_representation.cxx:805-820, :1376-1495;
  * render/host/scattering.cxx) — for callers that assemble the emitters themselves.  parameters = altitude, anisotropy, rayleigh, mie, ozone

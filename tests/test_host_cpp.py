@@ -343,3 +343,30 @@ def test_scene_file_tables_are_the_shipped_tables(tmp_path):
     sf.lib.etxb_scene_file_set_samples(sf.h, 9)
     assert int(sf.scene["samples"][0]) == 9
     sf.close()
+
+
+def test_native_renderer_reads_the_applications_options_file(tmp_path):
+    """`etx_render --options options.json`: the scene and the integrator come from the application's own options file (util/options.cxx format; the ids
+    RTApplication::init reads, raytracer/app.cxx:88-105); "Bidirectional (CPU)" maps to VCM with merging off (vcm_shared.hxx:33)."""
+    import ctypes as C
+    import json
+    from etx_tracer_b200 import api
+    exe = _build_native_renderer(tmp_path)
+    scene = _tiny_scene(tmp_path)
+    values = [{"class": 5, "description": "Integrator", "id": "integrator", "meta": 0, "value": "Bidirectional (CPU)"},
+              {"class": 5, "description": "Scene", "id": "scene", "meta": 0, "value": "./" + os.path.basename(scene)},
+              {"class": 1, "description": "Samples", "id": "spp", "meta": 0, "value": 4}]
+    (tmp_path / "options.json").write_text(json.dumps({"values": values}, indent=2))
+    lib = api.load_library("fast")
+    buf = C.create_string_buffer(256)
+    assert lib.etxb_options_file_string(str(tmp_path / "options.json").encode(), b"integrator", buf, len(buf)) == len("Bidirectional (CPU)") and buf.value == b"Bidirectional (CPU)"
+    assert lib.etxb_options_file_string(str(tmp_path / "options.json").encode(), b"recent-0", buf, len(buf)) == 0
+    assert lib.etxb_options_file_string(str(tmp_path / "options.json").encode(), b"spp", buf, len(buf)) == 0  # not a string option
+    assert lib.etxb_options_file_string(str(tmp_path / "absent.json").encode(), b"scene", buf, len(buf)) < 0
+    out = subprocess.run([exe, "--options", str(tmp_path / "options.json"), "-o", str(tmp_path / "o.exr")], capture_output=True, text=True)
+    assert out.returncode in (0, 4), (out.returncode, out.stdout[-300:], out.stderr[-300:])  # 4: the scene was found and loaded, no device here
+    if out.returncode == 4:
+        assert "VCM (B200)" in out.stderr
+    values[1]["value"] = "./missing.json"
+    (tmp_path / "options.json").write_text(json.dumps({"values": values}))
+    assert subprocess.run([exe, "--options", str(tmp_path / "options.json")], capture_output=True).returncode == 3
