@@ -125,7 +125,6 @@ struct etxb_scene_file_impl {
   std::vector<std::string> warnings;
   std::map<std::string, uint32_t> named_spectra, medium_names, material_index, image_cache;
   std::vector<CameraBlock> cameras;
-  std::vector<uint32_t> face_shape;  // per kept triangle (before degenerate removal), for the medium bounds
   std::string base_dir;
   uint32_t black = 0, white = 0, rayleigh = 0, mie = 0, ozone = 0, def_diel = 0, def_cond_eta = 0, def_cond_k = 0, ss_scatter = 0, ss_exit = 0;
 
@@ -911,7 +910,6 @@ struct etxb_scene_file_impl {
       if (material_index.count(o.material_names[i])) mat_of_name[i] = int(material_index[o.material_names[i]]);
     // load_from_obj skips a face whose material is unknown WITHOUT advancing its index cursor (:1005-1008, 1029): inside that shape the j-th face
     // that is kept reads the corners of the shape's j-th face.  Kept as the reference does it.
-    std::vector<uint32_t> shape_begin_cursor;
     std::vector<etxb_vertex>& v = vertices;
     std::vector<etxb_triangle> tris;
     std::vector<uint32_t> shapes;
