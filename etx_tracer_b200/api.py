@@ -50,6 +50,8 @@ def load_library(flavor="fast"):
         lib.etxb_scene_file_table.restype = vp
         lib.etxb_atmosphere_images.argtypes = [C.c_char_p, vp, C.c_float, vp, u32, u32, vp, vp]
         lib.etxb_options_file_string.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, u64]
+        lib.etxb_mesh_tangents.argtypes = [vp, u64, vp, u64]
+        lib.etxb_nvdb_density.argtypes = [C.c_char_p, vp, vp, u64, C.c_char_p, u64]
         for fn in (lib.etxb_scene_file_scene, lib.etxb_scene_file_camera):
             fn.argtypes = [vp]
             fn.restype = vp

@@ -7,10 +7,10 @@ validate_normals / validate_tangents :304-418, commit :420-455) read into the Sc
 
 Everything is built on `scenes.SceneData` (the same record builders the synthetic generators use); `tests/test_loader.py` compares the
 result with the reference's own loader (compiled in place as test infrastructure) array by array on the shipped Cornell asset and on
-generated scene files.  Known differences, all stated there: tangent frames of meshes WITH texture coordinates come from per-triangle UV
-derivatives instead of MikkTSpace (only normal maps and anisotropic roughness see them); NanoVDB volumes (the C++ loader reads them) and glTF geometry are refused here; the two images of
-an atmosphere block (`et::atmosphere`, and the default atmosphere of a file without distant emitters) come from the module's host code
-(etxb_atmosphere_images); this file is the Python twin of csrc/scene_loader.cpp, which is what the C ABI ships; image files: PNG (8-bit, non-interlaced), OpenEXR (float, scan lines, none / ZIP), Radiance HDR and the reference's PFM variant.
+generated scene files.  This file is the Python twin of csrc/scene_loader.cpp (what the C ABI ships) and shares three pieces of host code with it through
+the C ABI: the tangent-space generator of meshes with texture coordinates (etxb_mesh_tangents), the NanoVDB reader (etxb_nvdb_density) and the two images of an
+atmosphere block (etxb_atmosphere_images).  Remaining difference to the reference: black-body spectra to 1e-6 (numpy's float32 exp against glibc expf).
+glTF geometry is refused.  Image files: PNG (8-bit, non-interlaced), OpenEXR (float, scan lines, none / ZIP), Radiance HDR and the reference's PFM variant.
 The .mtl reader follows the reference's patched tinyobjloader (thirdparty/tinyobjloader/tiny_obj_loader.hxx:1900-2190): names are lower-cased,
 `Kd / Ks / Kt / Ke` and every non-standard key land in the material's parameter list, the standard texture keys are consumed.
 """
@@ -770,10 +770,29 @@ class SceneLoader:
             s_a = [float(x) for x in np.maximum(f32(0.0), (extinction - scattering).astype(f32))]
         explicit = b.get("enclosed") is None
         v = b.get("volume")
-        if v is not None and v.strip():
-            raise LoaderError("heterogeneous media from NanoVDB files are not read by this loader")
         m = self.sd.add_medium(absorption=s_a, scattering=s_t, g=g, explicit_connections=explicit)
         rec = self.sd._mediums[m]
+        if v is not None and v.strip():
+            # MediumPool::add (medium_pool.cxx:41-59) on the dense grid of the module's NanoVDB reader (etxb_nvdb_density, csrc/scene_loader_nvdb.inl)
+            from . import api
+            file = os.path.join(self.base_dir, v.strip())
+            if not file.lower().endswith(".nvdb"):
+                raise LoaderError(f"{file}: only NanoVDB (.nvdb) volume files are read")
+            lib, dims, err = api.load_library("fast"), np.zeros(3, np.uint32), C.create_string_buffer(512)
+            if lib.etxb_nvdb_density(os.fsencode(file), dims.ctypes.data, None, 0, err, len(err)) != 0:
+                raise LoaderError(err.value.decode(errors="replace"))
+            if int(dims.prod()) > 0:
+                grid = np.zeros(int(dims.prod()), f32)
+                if lib.etxb_nvdb_density(os.fsencode(file), dims.ctypes.data, grid.ctypes.data, grid.size, err, len(err)) != 0:
+                    raise LoaderError(err.value.decode(errors="replace"))
+                top = f32(grid.max())
+                if top > 0:
+                    grid = (grid / top).astype(f32)
+                    rec["cls"] = 1
+                    rec["density"]["a"] = grid.ctypes.data
+                    rec["density"]["count"] = grid.size
+                    rec["dimensions"][0] = dims
+                    self.sd._keep.append(grid)
         if spd_t is not None:
             self.sd.spectra[int(rec["scattering_index"][0])] = spd_t
         # max_sigma = the two spectra's maximum powers added up (scene_data.hxx:137-143)
@@ -1190,25 +1209,16 @@ class SceneLoader:
             # every vertex belongs to exactly one triangle (load_from_obj unrolls the faces): the first contribution is an assignment (:318-320)
             contrib = (np.repeat(tri["geo_n"], 3, axis=0) * np.repeat(area, 3)[:, None]).astype(f32)
             v["nrm"][idx[fix]] = _normalize(contrib[fix])
-        # build_tangents (:337-398): without texture coordinates nothing; with them per-triangle UV-derivative tangents (NOT MikkTSpace)
+        # build_tangents (:337-398): without texture coordinates nothing; with them the tangent-space generator the reference calls, which the module's
+        # host code restates (etxb_mesh_tangents, csrc/scene_loader_tangents.inl) — the C++ loader runs the same function
         span = v["tex"].max(axis=0) - v["tex"].min(axis=0) if v.shape[0] else np.zeros(2, f32)
         if float(span[0] * span[0] + span[1] * span[1]) > 1e-6:
-            uv = v["tex"][idx].reshape(nt, 3, 2)
-            e1, e2 = p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]
-            du1, dv1, du2, dv2 = uv[:, 1, 0] - uv[:, 0, 0], uv[:, 1, 1] - uv[:, 0, 1], uv[:, 2, 0] - uv[:, 0, 0], uv[:, 2, 1] - uv[:, 0, 1]
-            det = du1 * dv2 - du2 * dv1
-            with np.errstate(invalid="ignore", divide="ignore"):
-                t = ((e1 * dv2[:, None] - e2 * dv1[:, None]) / det[:, None]).astype(f32)
-            sign = np.where(det < 0, f32(-1.0), f32(1.0))
-            tv = np.repeat(t, 3, axis=0)
-            good = _valid(tv)
-            tan = np.zeros((v.shape[0], 3), f32)
-            tan[idx[good]] = _normalize(tv[good])
-            has = _valid(tan)
-            v["tan"][has] = tan[has]
-            sg = np.ones(v.shape[0], f32)
-            sg[idx] = np.repeat(sign, 3)
-            v["btn"][has] = _normalize((_cross(tan[has], v["nrm"][has]) * sg[has][:, None]).astype(f32))
+            from . import api
+            v = np.ascontiguousarray(v)
+            tri = np.ascontiguousarray(tri)
+            rc = api.load_library("fast").etxb_mesh_tangents(v.ctypes.data, v.shape[0], tri.ctypes.data, tri.shape[0])
+            if rc != 0:
+                raise LoaderError(f"etxb_mesh_tangents failed ({rc})")
         # validate_tangents (:400-418)
         need = (np.ones(v.shape[0], bool) if force_tangents else ~(_valid(v["tan"]) & _valid(v["btn"]))) & (referenced | force_tangents)
         if need.any():

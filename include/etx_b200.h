@@ -374,6 +374,12 @@ int etxb_scene_file_commit(etxb_ctx* ctx, const etxb_scene_file* sf);
 /* A string value of the application's options file (util/options.cxx; ids "integrator" and "scene" are what RTApplication::init reads,
  * raytracer/app.cxx:88-105): copies it to `out` (NUL-terminated, truncated to out_bytes) and returns its length; 0 = id absent; < 0 = error. */
 int etxb_options_file_string(const char* file_name, const char* id, char* out, uint64_t out_bytes);
+/* Two parts of the loader on their own.  etxb_mesh_tangents: the tangent-space generator the reference calls for meshes with texture coordinates
+ * (build_tangents, scene_representation.cxx:337-398) over etx::Vertex / etx::Triangle arrays, writing tan / btn of the vertices whose tangent is not valid
+ * yet.  etxb_nvdb_density: the dense grid MediumPool::load_nvdb (medium_pool.cxx:102-159) builds from the first float grid of a NanoVDB file — call with
+ * values = NULL for the dimensions (x, y, z; all 0 = the medium stays homogeneous), then with a buffer of x*y*z floats (x fastest; not yet normalised). */
+int etxb_mesh_tangents(etxb_vertex* vertices, uint64_t vertex_count, const etxb_triangle* triangles, uint64_t triangle_count);
+int etxb_nvdb_density(const char* file_name, uint32_t dimensions[3], float* values, uint64_t value_capacity, char* err, uint64_t err_bytes);
 /* The procedural sun disk (128 x 128) and sky dome (sky_width x sky_height) images of an atmosphere block — what the loader generates for a
  * `newmtl et::atmosphere` block and for every scene file that declares no distant emitter (scene_representation.cxx:805-820, :1376-1495;
  * render/host/scattering.cxx) — for callers that assemble the emitters themselves.  parameters = altitude, anisotropy, rayleigh, mie, ozone

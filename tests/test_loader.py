@@ -3,11 +3,10 @@ etx_tracer_b200/loader.py) against the reference's OWN loader (scene_representat
 friends compiled in place into oracle/_ref/libreference_loader.so — test infrastructure): the same scene FILES read by both, the Scene / Camera
 PODs compared array by array.  CPU only; skipped where the reference tree is absent.
 
-Byte-identical: triangles (indices, material, geometric normal), vertex positions / normals / texture coordinates, tangent frames (C++ loader: all,
-incl. the 414 954 vertices of the Cornell asset; Python twin: of meshes without texture coordinates), every Material record, emitter profiles / instances / the emitter distribution, media, images (pixels, options, sampling
-tables), the scene scalars, the camera (up to the sign of a zero in `position`).  Stated differences, Python twin only: tangent frames of meshes WITH
-texture coordinates (per-triangle UV derivatives there, the tangent-space generator in the reference and in the C++ loader), black-body spectra to 1e-6
-relative (glibc expf against numpy's float32 exp); both: padding bytes the reference leaves uninitialised."""
+Byte-identical: triangles (indices, material, geometric normal), vertex positions / normals / texture coordinates, tangent frames (incl. the 414 954
+vertices of the Cornell asset), every Material record, emitter profiles / instances / the emitter distribution, media, images (pixels, options, sampling
+tables), the scene scalars, the camera (up to the sign of a zero in `position`).  Stated differences: the Python twin's black-body spectra to 1e-6
+relative (glibc expf against numpy's float32 exp); padding bytes the reference leaves uninitialised."""
 import ctypes as C
 import json
 import os
@@ -39,9 +38,8 @@ def load(request):
 
     def run(path):
         return fn(path)
-    # meshes with texture coordinates: the C++ loader restates the tangent-space generator the reference calls (bit-identical frames), the Python
-    # twin keeps per-triangle UV derivatives (a stated difference)
-    run.exact_tangents = request.param == "cpp"
+    # meshes with texture coordinates: both loaders run the module's restatement of the tangent-space generator the reference calls (bit-identical frames)
+    run.exact_tangents = True
     return run
 
 
@@ -496,7 +494,7 @@ def test_cpp_loader_matches_the_python_loader(tmp_path):
     mtl = mtl.replace("collimated 0.4 twosided", "collimated 0.4 twosided image albedo.png")
     path = _write_scene(tmp_path, obj=obj, mtl=mtl)
     a, b = loader.load_scene(path), _load_cpp(path)
-    problems = compare_scenes(a, b, uv_tangents_exact=False)  # the mesh has texture coordinates: the twin's frames are UV-derivative ones
+    problems = compare_scenes(a, b, uv_tangents_exact=True)
     assert not problems, problems
     assert sorted(b.material_names) == sorted(a.material_names)
     b.close()
@@ -871,7 +869,7 @@ def _medium_density(scene):
 
 
 @pytest.mark.parametrize("kind", ["sphere", "blobs", "empty", "vec3"])
-def test_nanovdb_volume_matches_the_reference_loader(ref, tmp_path, kind):
+def test_nanovdb_volume_matches_the_reference_loader(ref, tmp_path, kind, load):
     """`et::medium … volume cloud.nvdb`: a file written with the reference's NanoVDB headers (oracle/nvdb_make.cxx, test infrastructure) read by the module's
     own NanoVDB reader and by the reference (nanovdb::io::readGrid + an accessor sweep, medium_pool.cxx:102-159): same class, dimensions and dense
     grid — a fog sphere; two blobs across node boundaries plus a far block (negative coordinates, a sparse tree); an all-negative grid and a Vec3f grid
@@ -882,7 +880,7 @@ def test_nanovdb_volume_matches_the_reference_loader(ref, tmp_path, kind):
     subprocess.check_call([NVDB_MAKE, kind, str(tmp_path / "cloud.nvdb")])
     path = _write_scene(tmp_path, mtl=MTL.replace("scattering 0.4", "scattering 0.4\nvolume cloud.nvdb"))
     rs = ref(path)
-    sd = _load_cpp(path)
+    sd = load(path)
     problems = compare_scenes(rs, sd)
     assert not problems, problems
     ma, mb = _view(rs.scene["mediums"], S.MEDIUM), _view(sd.scene["mediums"], S.MEDIUM)
@@ -894,7 +892,6 @@ def test_nanovdb_volume_matches_the_reference_loader(ref, tmp_path, kind):
         k = heterogeneous.index(1)
         assert tuple(int(x) for x in mb[k]["dimensions"]) == tuple(int(x) for x in ma[k]["dimensions"]) and float(_medium_density(sd.scene)[k].max()) == 1.0
     rs.close()
-    sd.close()
 
 
 def test_zip_compressed_nanovdb_file_and_refusals(tmp_path):
