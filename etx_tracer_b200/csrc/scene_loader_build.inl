@@ -179,19 +179,12 @@ struct etxb_scene_file_impl {
   }
 
   // get_file (:114-154): relative to the material file's folder, else as given
+  // get_file (:114-121): "<folder of the material file>/<name>" for any non-empty name — the file is not looked for here; one that cannot be read
+  // becomes the 1 x 1 white placeholder in add_image_file, like in the reference's texture pool
   bool find_file(const std::string& name, std::string& out) {
     if (name.empty()) return false;
-    std::string a = join(base_dir, name);
-    if (file_exists(a)) {
-      out = a;
-      return true;
-    }
-    if (file_exists(name)) {
-      out = name;
-      return true;
-    }
-    warn("file " + name + " not found");
-    return false;
+    out = base_dir.empty() ? name : (base_dir + "/" + name);
+    return true;
   }
 
   // ImagePool::add_from_file + load_image (image_pool.cxx:51-66, 162-215)
@@ -211,7 +204,7 @@ struct etxb_scene_file_impl {
       problem = path + ": " + e.what();
     }
     if (!loaded) {
-      if (file_exists(path)) warn(problem + "; using the 1x1 white placeholder");
+      warn(problem + "; using the 1x1 white placeholder");
       rec->px = Pixels();
       rec->px.w = rec->px.h = 1;
       rec->px.f32 = {1.0f, 1.0f, 1.0f, 1.0f};
@@ -261,13 +254,13 @@ struct etxb_scene_file_impl {
 
   // ---- spectra directives -----------------------------------------------------------------------------------------------------------------------------
   uint32_t reflectance_spectrum(const std::string& text) {  // load_reflectance_spectrum (:1613-1633)
-    auto p = split(text);
+    auto p = split_params(text);
     if (p.size() == 1 && named_spectra.count(p[0])) return named_spectra[p[0]];
     if (p.size() == 3) return add_spectrum(spd_rgb_reflectance(t(), gamma_to_linear({c_atof(p[0]), c_atof(p[1]), c_atof(p[2])})));
     return 0;
   }
   Spd illuminant_spectrum(const std::string& text) {  // load_illuminant_spectrum (:1635-1680)
-    auto p = split(text);
+    auto p = split_params(text);
     if (p.size() == 1) {
       auto fl = leading_floats(p[0], 1);
       if (!fl.empty()) return spd_rgb_luminance(t(), {fl[0], fl[0], fl[0]});
@@ -419,7 +412,7 @@ struct etxb_scene_file_impl {
       if (b.get(key, v)) {
         s_t = spectra[!strcmp(key, "rayleigh") ? rayleigh : mie];
         float scale = 1.0f;
-        auto p = split(v);
+        auto p = split_params(v);
         for (size_t i = 0; i < p.size(); ++i)
           if (p[i] == "scale" && i + 1 < p.size()) scale = c_atof(p[i + 1]);
         spd_scale(s_t, scale / spd_max_power(s_t));
@@ -428,7 +421,7 @@ struct etxb_scene_file_impl {
     if (b.get("parametric", v)) {  // colour + distances -> absorption / scattering through subsurface::remap (scene_bssrdf_subsurface.hxx:17-44), :1254-1296
       F3 color = {1.0f, 1.0f, 1.0f}, dist = {0.25f, 0.25f, 0.25f};
       float scale = 1.0f;
-      auto p = split(v);
+      auto p = split_params(v);
       for (size_t i = 0; i < p.size(); ++i) {
         if (p[i] == "color" && i + 3 < p.size()) {
           color = {c_atof(p[i + 1]), c_atof(p[i + 2]), c_atof(p[i + 3])};
@@ -626,18 +619,18 @@ struct etxb_scene_file_impl {
     bool initialized = false;
     Spd spd = {};
     if (b.get("rgb", v)) {
-      auto p = split(v);
+      auto p = split_params(v);
       if (p.size() < 3) return;
       F3 value = gamma_to_linear({c_atof(p[0]), c_atof(p[1]), c_atof(p[2])});
       spd = illuminant ? spd_rgb_luminance(t(), value) : spd_rgb_reflectance(t(), value);
       initialized = true;
     } else if (b.get("blackbody", v)) {
-      auto p = split(v);
+      auto p = split_params(v);
       if (p.empty()) return;
       spd = spd_black_body(t(), c_atof(p[0]), scale);
       initialized = true;
     } else if (b.get("nblackbody", v)) {
-      auto p = split(v);
+      auto p = split_params(v);
       if (p.empty()) return;
       float s2 = 1.0f;
       for (size_t i = 0; i < p.size(); ++i)
@@ -648,7 +641,7 @@ struct etxb_scene_file_impl {
     const bool have_samples = b.get("samples", v);
     if (!have_samples && !initialized) return;
     if (!initialized) {
-      auto p = split(v);
+      auto p = split_params(v);
       if (p.size() % 2) return;
       std::vector<std::pair<float, float>> samples;
       for (size_t i = 0; i + 1 < p.size(); i += 2) samples.push_back({c_atof(p[i]), c_atof(p[i + 1])});
@@ -686,12 +679,10 @@ struct etxb_scene_file_impl {
     if (b.get("Kd", v)) materials[mi].scattering.spectrum_index = reflectance_spectrum(v);
     if (b.get("Ks", v)) materials[mi].reflectance.spectrum_index = reflectance_spectrum(v);
     if (b.get("Kt", v)) materials[mi].scattering.spectrum_index = reflectance_spectrum(v);
-    if (b.get("two_sided", v)) {
-      auto tk = split(v);
-      std::string tok = tk.empty() ? std::string("") : tk[0];
+    if (b.get("two_sided", v)) {  // an integer, else the whole value against "true" / "on" (:1714-1722)
       char* end = nullptr;
-      long val = strtol(tok.c_str(), &end, 10);
-      materials[mi].two_sided = (end != tok.c_str()) ? (val != 0 ? 1u : 0u) : ((tok == "true" || tok == "on") ? 1u : 0u);
+      long val = strtol(v.c_str(), &end, 10);
+      materials[mi].two_sided = (end != v.c_str()) ? (val != 0 ? 1u : 0u) : ((v == "true" || v == "on") ? 1u : 0u);
     }
     if (b.get("opacity", v)) {
       auto fl = leading_floats(v, 1);
@@ -716,6 +707,25 @@ struct etxb_scene_file_impl {
       if (!fl.empty())
         for (float& x : materials[mi].transmission.value) x = fl[0];
     }
+    // map_Ml / map_Tm: metalness / transmission maps with an optional `channel N` (:1772-1800).  (`map_Pr`, the roughness map of the same block, is
+    // dead code in the reference: the .mtl reader consumes that key as a standard texture before parse_material looks for it.)
+    auto channel_map = [&](const char* key, uint32_t& image_index, uint32_t& channel) {
+      if (!b.get(key, v)) return;
+      auto p = split_params(v);
+      int ch = 0;
+      for (size_t i = 0; i < p.size(); ++i) {
+        if (p[i] == "channel" && i + 1 < p.size()) {
+          ch = std::max(0, atoi(p[i + 1].c_str()));
+          ++i;
+        }
+      }
+      if (find_file(p[0], f)) {
+        image_index = add_image_file(f, IMG_REPEAT_U | IMG_REPEAT_V);
+        channel = uint32_t(ch);
+      }
+    };
+    channel_map("map_Ml", materials[mi].metalness.image_index, materials[mi].metalness.channel);
+    channel_map("map_Tm", materials[mi].transmission.image_index, materials[mi].transmission.channel);
     auto texture = [&](const char* slot) -> std::string {
       auto it = b.textures.find(slot);
       return it == b.textures.end() ? std::string("") : it->second;
@@ -724,7 +734,7 @@ struct etxb_scene_file_impl {
     if (find_file(texture("specular"), f)) materials[mi].reflectance.image_index = add_image_file(f, IMG_REPEAT_U | IMG_REPEAT_V);
     if (find_file(texture("transmittance"), f)) materials[mi].scattering.image_index = add_image_file(f, IMG_REPEAT_U | IMG_REPEAT_V);
     if (b.get("material", v)) {
-      auto p = split(v);
+      auto p = split_params(v);
       for (size_t i = 0; i < p.size(); ++i)
         if (p[i] == "class" && i + 1 < p.size()) materials[mi].cls = material_class(p[++i]);
     }
@@ -757,7 +767,7 @@ struct etxb_scene_file_impl {
       materials[mi].ext_medium = medium_names.count(trim(v)) ? medium_names[trim(v)] : kInvalid;
     }
     if (b.get("normalmap", v)) {
-      auto p = split(v);
+      auto p = split_params(v);
       for (size_t i = 0; i < p.size(); ++i) {
         if (p[i] == "image" && i + 1 < p.size()) {
           if (find_file(p[i + 1], f)) materials[mi].normal_image_index = add_image_file(f, IMG_REPEAT_U | IMG_REPEAT_V | IMG_SKIP_SRGB);
@@ -770,7 +780,7 @@ struct etxb_scene_file_impl {
       }
     }
     if (b.get("thinfilm", v)) {
-      auto p = split(v);
+      auto p = split_params(v);
       for (size_t i = 0; i < p.size(); ++i) {
         if (p[i] == "image" && i + 1 < p.size()) {
           if (find_file(p[i + 1], f)) materials[mi].thinfilm.thickness_image = add_image_file(f, IMG_REPEAT_U | IMG_REPEAT_V);
@@ -798,7 +808,7 @@ struct etxb_scene_file_impl {
       materials[mi].subsurface.cls = 1u;
       float scale = 1.0f;
       F3 dist = {1.0f, 0.2f, 0.04f};
-      auto p = split(v);
+      auto p = split_params(v);
       for (size_t i = 0; i < p.size(); ++i) {
         if (p[i] == "path" && i + 1 < p.size()) materials[mi].subsurface.path = (p[i + 1] == "refracted" || p[i + 1] == "refraction" || p[i + 1] == "refract") ? 1u : 0u;
         if (p[i] == "distances" && i + 3 < p.size()) {
@@ -830,7 +840,7 @@ struct etxb_scene_file_impl {
     }
     if (b.get("emitter", v)) {
       is_emitter = true;
-      auto p = split(v);
+      auto p = split_params(v);
       for (size_t i = 0; i < p.size(); ++i) {
         if (p[i] == "image" && i + 1 < p.size() && find_file(p[i + 1], f)) {
           materials[mi].emission.image_index = add_image_file(f, IMG_REPEAT_U | IMG_REPEAT_V | IMG_BUILD_TABLE);

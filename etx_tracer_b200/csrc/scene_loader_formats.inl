@@ -668,11 +668,12 @@ ObjData parse_obj(const std::string& path) {
           idx.n = ni ? int(ni > 0 ? ni - 1 : long(o.nrm.size() / 3) + ni) : -1;
           poly.push_back(idx);
         }
-        auto emit = [&](int a, int b2, int c2) {
-          o.corners.push_back(poly[size_t(a)]), o.corners.push_back(poly[size_t(b2)]), o.corners.push_back(poly[size_t(c2)]);
+        auto emit_corners = [&](const ObjIndex& a, const ObjIndex& b2, const ObjIndex& c2) {
+          o.corners.push_back(a), o.corners.push_back(b2), o.corners.push_back(c2);
           o.face_material.push_back(current);
           o.face_shape.push_back(shape);
         };
+        auto emit = [&](int a, int b2, int c2) { emit_corners(poly[size_t(a)], poly[size_t(b2)], poly[size_t(c2)]); };
         for (const auto& ix : poly)
           if (ix.v < 0 || size_t(ix.v) * 3 + 2 >= o.pos.size()) fail(path + ": a face refers to a vertex that does not exist");
         if (poly.size() == 4) {
@@ -685,8 +686,68 @@ ObjData parse_obj(const std::string& path) {
           } else {
             emit(0, 1, 3), emit(1, 2, 3);
           }
-        } else {
-          for (size_t j = 1; j + 1 < poly.size(); ++j) emit(0, int(j), int(j + 1));  // triangles; larger polygons as a fan (tinyobjloader clips ears)
+        } else if (poly.size() == 3) {
+          emit(0, 1, 2);
+        } else if (poly.size() > 4) {
+          // tinyobjloader clips ears in the plane of the polygon's two dominant axes (tiny_obj_loader.hxx:1537-1800), in float
+          size_t axes[2] = {1, 2};
+          const size_t n = poly.size();
+          for (size_t k = 0; k < n; ++k) {
+            const float* a = &o.pos[size_t(poly[k % n].v) * 3];
+            const float* b2 = &o.pos[size_t(poly[(k + 1) % n].v) * 3];
+            const float* c2 = &o.pos[size_t(poly[(k + 2) % n].v) * 3];
+            const float e0x = b2[0] - a[0], e0y = b2[1] - a[1], e0z = b2[2] - a[2], e1x = c2[0] - b2[0], e1y = c2[1] - b2[1], e1z = c2[2] - b2[2];
+            const float cx = std::fabs(e0y * e1z - e0z * e1y), cy = std::fabs(e0z * e1x - e0x * e1z), cz = std::fabs(e0x * e1y - e0y * e1x);
+            if (cx > FLT_EPSILON || cy > FLT_EPSILON || cz > FLT_EPSILON) {  // the first real corner decides
+              if (!(cx > cy && cx > cz)) {
+                axes[0] = 0;
+                if (cz > cx && cz > cy) axes[1] = 1;
+              }
+              break;
+            }
+          }
+          std::vector<ObjIndex> rest = poly;
+          size_t guess = 0, budget = n, previous = n;
+          while (rest.size() > 3 && budget > 0) {
+            const size_t m = rest.size();
+            if (guess >= m) guess -= m;
+            if (previous != m) {
+              previous = m;
+              budget = m;
+            } else {
+              budget--;
+            }
+            ObjIndex ind[3];
+            float vx[3], vy[3];
+            for (size_t k = 0; k < 3; ++k) {
+              ind[k] = rest[(guess + k) % m];
+              vx[k] = o.pos[size_t(ind[k].v) * 3 + axes[0]];
+              vy[k] = o.pos[size_t(ind[k].v) * 3 + axes[1]];
+            }
+            const float e0x = vx[1] - vx[0], e0y = vy[1] - vy[0], e1x = vx[2] - vx[1], e1y = vy[2] - vy[1];
+            const float turn = e0x * e1y - e0y * e1x, area = (vx[0] * vy[1] - vy[0] * vx[1]) * 0.5f;
+            if (turn * area < 0.0f) {  // "an internal angle"
+              guess += 1;
+              continue;
+            }
+            bool overlap = false;
+            for (size_t other = 3; other < m && !overlap; ++other) {
+              const ObjIndex& t = rest[(guess + other) % m];
+              const float tx = o.pos[size_t(t.v) * 3 + axes[0]], ty = o.pos[size_t(t.v) * 3 + axes[1]];
+              bool inside = false;  // the crossing-number test over the candidate ear
+              for (int i = 0, j = 2; i < 3; j = i++) {
+                if (((vy[i] > ty) != (vy[j] > ty)) && (tx < (vx[j] - vx[i]) * (ty - vy[i]) / (vy[j] - vy[i]) + vx[i])) inside = !inside;
+              }
+              overlap = inside;
+            }
+            if (overlap) {
+              guess += 1;
+              continue;
+            }
+            emit_corners(ind[0], ind[1], ind[2]);
+            rest.erase(rest.begin() + long((guess + 1) % m));
+          }
+          if (rest.size() == 3) emit_corners(rest[0], rest[1], rest[2]);
         }
         shape_has_faces = shape_has_faces || (poly.size() >= 3);
       } else if (!strncmp(q, "usemtl", 6) && (q[6] == ' ' || q[6] == '\t')) {

@@ -9,7 +9,7 @@ Everything is built on `scenes.SceneData` (the same record builders the syntheti
 result with the reference's own loader (compiled in place as test infrastructure) array by array on the shipped Cornell asset and on
 generated scene files.  This file is the Python twin of csrc/scene_loader.cpp (what the C ABI ships) and shares three pieces of host code with it through
 the C ABI: the tangent-space generator of meshes with texture coordinates (etxb_mesh_tangents), the NanoVDB reader (etxb_nvdb_density) and the two images of an
-atmosphere block (etxb_atmosphere_images).  Remaining difference to the reference: black-body spectra to 1e-6 (numpy's float32 exp against glibc expf).
+atmosphere block (etxb_atmosphere_images).  Remaining difference to the reference: spectra in the last bits (numpy's float32 arithmetic against the C++ builders; 2e-6 in the tests).
 glTF geometry is refused.  Image files: PNG (8-bit, non-interlaced), OpenEXR (float, scan lines, none / ZIP), Radiance HDR and the reference's PFM variant.
 The .mtl reader follows the reference's patched tinyobjloader (thirdparty/tinyobjloader/tiny_obj_loader.hxx:1900-2190): names are lower-cased,
 `Kd / Ks / Kt / Ke` and every non-standard key land in the material's parameter list, the standard texture keys are consumed.
@@ -159,12 +159,28 @@ def spd_from_power(power441, integrated=None):
     return scenes._spd(power, integrated)
 
 
+_libm = None
+
+
+def _expf(x):
+    """the C library's expf, element by element: numpy's float32 exp differs from it in the last bit for some arguments, and the reference's black-body
+    spectra (hence emitter weights and max_sigma of media built from them) are made with expf"""
+    global _libm
+    if _libm is None:
+        import ctypes.util
+        _libm = C.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        _libm.expf.restype = C.c_float
+        _libm.expf.argtypes = [C.c_float]
+    x = np.asarray(x, dtype=f32)
+    return np.array([_libm.expf(float(v)) for v in x.reshape(-1)], dtype=f32).reshape(x.shape)
+
+
 def black_body_radiation(wavelength_nm, t_kelvins):
     """spectrum::black_body_radiation (render/shared/spectrum.hxx:171-189) in its float32 steps."""
     wl = (np.asarray(wavelength_nm, dtype=f32) * f32(1.0 / 1000.0)).astype(f32)
     wl5 = (wl * (wl * wl).astype(f32)).astype(f32) * (wl * wl).astype(f32)
     with np.errstate(over="ignore"):
-        e0 = np.exp((f32(1.4387752e+4) / (wl * f32(t_kelvins)).astype(f32)).astype(f32)).astype(f32)
+        e0 = _expf((f32(1.4387752e+4) / (wl * f32(t_kelvins)).astype(f32)).astype(f32))
         d = (wl5.astype(f32) * (e0 - f32(1.0)).astype(f32)).astype(f32)
     return np.where(np.isinf(d), f32(0.0), (f32(3.7417712e+5) / d).astype(f32)).astype(f32)
 
@@ -244,7 +260,7 @@ def subsurface_remap(color, distances):
     blend = np.power(color, f32(0.25)).astype(f32)
     albedo = ((f32(1.0) - blend).astype(f32) * a * np.power(np.arctan((b * color).astype(f32)).astype(f32), c).astype(f32)).astype(f32)
     albedo = (albedo + (blend * d * np.power(np.arctan((e * color).astype(f32)).astype(f32), f).astype(f32)).astype(f32)).astype(f32)
-    albedo = np.clip(albedo, f32(0.0), f32(1.0) - f32(1e-6)).astype(f32)
+    albedo = np.clip(albedo, f32(0.0), f32(1.0) - f32(1.192092896e-07)).astype(f32)  # kEpsilon (math.hxx:107)
     extinction = (f32(1.0) / np.maximum(np.asarray(distances, dtype=f32), f32(1.0 / 1024.0))).astype(f32)
     return albedo, extinction, (extinction * albedo).astype(f32)
 
@@ -468,12 +484,71 @@ def _valid(v):
     return np.isfinite(v).all(axis=1) & (_dot(v, v) > 0)
 
 
+def _clip_ears(q):
+    """tinyobjloader's triangulation of a polygon with more than four corners (tiny_obj_loader.hxx:1537-1800): ears clipped in the plane of the two
+    dominant axes, float32 arithmetic.  `q` = corner positions; returns index triples into the polygon."""
+    n, axes, eps = len(q), [1, 2], np.finfo(f32).eps
+    for k in range(n):
+        a, b, c = q[k % n], q[(k + 1) % n], q[(k + 2) % n]
+        e0, e1 = (b - a).astype(f32), (c - b).astype(f32)
+        cx = abs(f32(f32(e0[1] * e1[2]) - f32(e0[2] * e1[1])))
+        cy = abs(f32(f32(e0[2] * e1[0]) - f32(e0[0] * e1[2])))
+        cz = abs(f32(f32(e0[0] * e1[1]) - f32(e0[1] * e1[0])))
+        if cx > eps or cy > eps or cz > eps:
+            if not (cx > cy and cx > cz):
+                axes[0] = 0
+                if cz > cx and cz > cy:
+                    axes[1] = 1
+            break
+    rest, out, guess, budget, previous = list(range(n)), [], 0, n, n
+    while len(rest) > 3 and budget > 0:
+        m = len(rest)
+        if guess >= m:
+            guess -= m
+        if previous != m:
+            previous, budget = m, m
+        else:
+            budget -= 1
+        ind = [rest[(guess + k) % m] for k in range(3)]
+        vx = [f32(q[i][axes[0]]) for i in ind]
+        vy = [f32(q[i][axes[1]]) for i in ind]
+        e0x, e0y, e1x, e1y = f32(vx[1] - vx[0]), f32(vy[1] - vy[0]), f32(vx[2] - vx[1]), f32(vy[2] - vy[1])
+        turn = f32(f32(e0x * e1y) - f32(e0y * e1x))
+        area = f32(f32(f32(vx[0] * vy[1]) - f32(vy[0] * vx[1])) * f32(0.5))
+        if f32(turn * area) < 0:
+            guess += 1
+            continue
+        overlap = False
+        for other in range(3, m):
+            t = q[rest[(guess + other) % m]]
+            tx, ty = f32(t[axes[0]]), f32(t[axes[1]])
+            inside, j = False, 2
+            for i in range(3):
+                if (vy[i] > ty) != (vy[j] > ty):
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        x = f32(f32(f32(f32(vx[j] - vx[i]) * f32(ty - vy[i])) / f32(vy[j] - vy[i])) + vx[i])
+                    if tx < x:
+                        inside = not inside
+                j = i
+            if inside:
+                overlap = True
+                break
+        if overlap:
+            guess += 1
+            continue
+        out.append(tuple(ind))
+        del rest[(guess + 1) % m]
+    if len(rest) == 3:
+        out.append(tuple(rest))
+    return tuple(out)
+
+
 class _ObjData:
     pass
 
 
 def parse_obj(path):
-    """Positions / normals / texcoords, triangulated faces (fan), the material name and the shape (o / g group) of every face, and the mtllib."""
+    """Positions / normals / texcoords, triangulated faces (quads along the shorter diagonal, larger polygons by ear clipping, like tinyobjloader), the material name and the shape (o / g group) of every face, and the mtllib."""
     pos, nrm, tex = [], [], []
     faces, face_mtl, face_shape = [], [], []
     mtllib, cur_mtl, shape, shape_has_faces = None, None, 0, False
@@ -506,8 +581,12 @@ def parse_obj(path):
                     s02 = f32(f32(f32(e02[0] * e02[0]) + f32(e02[1] * e02[1])) + f32(e02[2] * e02[2]))
                     s13 = f32(f32(f32(e13[0] * e13[0]) + f32(e13[1] * e13[1])) + f32(e13[2] * e13[2]))
                     tris = ((0, 1, 2), (0, 2, 3)) if s02 < s13 else ((0, 1, 3), (1, 2, 3))
+                elif len(idx) == 3:
+                    tris = ((0, 1, 2),)
+                elif len(idx) > 4:
+                    tris = _clip_ears([np.asarray(pos[i[0]], dtype=f32) for i in idx])
                 else:
-                    tris = tuple((0, j, j + 1) for j in range(1, len(idx) - 1))  # triangles; larger polygons as a fan (tinyobjloader clips ears)
+                    tris = ()
                 for (a, b, c) in tris:
                     faces.append((idx[a], idx[b], idx[c]))
                     face_mtl.append(cur_mtl)
@@ -573,14 +652,11 @@ class SceneLoader:
         return i
 
     def find_file(self, name):
-        """get_file (:114-154): relative to the material file's folder, else as given."""
+        """get_file (:114-121): "<folder of the material file>/<name>" for any non-empty name — the file is not looked for here; one that cannot be read
+        becomes the 1 x 1 white placeholder in add_image_file, like in the reference's texture pool."""
         if not name:
             return None
-        for cand in (os.path.join(self.base_dir, name), name):
-            if os.path.isfile(cand):
-                return cand
-        self.warn(f"file {name} not found")
-        return None
+        return (self.base_dir + "/" + name) if self.base_dir else name
 
     def add_image_file(self, path, options, offset=(0.0, 0.0), scale=(1.0, 1.0)):
         """ImagePool::add_from_file + load_image (image_pool.cxx:51-66, 162-215): 8-bit files stay RGBA8 with the sRGB curve removed and re-quantised
@@ -592,8 +668,7 @@ class SceneLoader:
         try:
             px, eight_bit = read_image(path)
         except (LoaderError, OSError, ValueError, KeyError) as e:
-            if os.path.exists(path):
-                self.warn(f"{path}: {e}; using the 1x1 white placeholder")
+            self.warn(f"{path}: {e}; using the 1x1 white placeholder")
             px, eight_bit = np.ones((1, 1, 4), dtype=f32), False
             options |= IMG_SKIP_SRGB | IMG_REPEAT_U | IMG_REPEAT_V
         if eight_bit:
@@ -614,7 +689,7 @@ class SceneLoader:
     # -- spectra directives ---------------------------------------------------------------------------
     def reflectance_spectrum(self, text):
         """load_reflectance_spectrum (:1613-1633)."""
-        p = text.split()
+        p = _split_params(text)
         if len(p) == 1 and p[0] in self.named_spectra:
             return self.named_spectra[p[0]]
         if len(p) == 3:
@@ -623,7 +698,7 @@ class SceneLoader:
 
     def illuminant_spectrum(self, text):
         """load_illuminant_spectrum (:1635-1680)."""
-        p = text.split()
+        p = _split_params(text)
         if len(p) == 1:
             fl = _floats(p[0], 1)
             if fl:
@@ -741,7 +816,7 @@ class SceneLoader:
             v = b.get(key)
             if v is not None:
                 base = self.sd.spectra[self.defaults[key + "_spectrum"]]
-                scale, p = 1.0, v.split()
+                scale, p = 1.0, _split_params(v)
                 for i, tok in enumerate(p):
                     if tok == "scale" and i + 1 < len(p):
                         scale = _atof(p[i + 1])
@@ -750,7 +825,7 @@ class SceneLoader:
         if v is not None:
             # colour + scattering distances -> absorption / scattering through subsurface::remap (scene_bssrdf_subsurface.hxx:17-44), :1254-1296
             color, dist, scale = [1.0, 1.0, 1.0], [0.25, 0.25, 0.25], 1.0
-            p, i = v.split(), 0
+            p, i = _split_params(v), 0
             while i < len(p):
                 if p[i] == "color" and i + 3 < len(p):
                     color = [_atof(p[i + 1]), _atof(p[i + 2]), _atof(p[i + 3])]
@@ -901,18 +976,18 @@ class SceneLoader:
         illuminant = b.get("illuminant") is not None
         spd = None
         if b.get("rgb") is not None:
-            p = b.get("rgb").split()
+            p = _split_params(b.get("rgb"))
             if len(p) < 3:
                 return
             value = gamma_to_linear([_atof(p[0]), _atof(p[1]), _atof(p[2])])
             spd = scenes.spd_rgb_luminance(value) if illuminant else scenes.spd_rgb_reflectance(value)
         elif b.get("blackbody") is not None:
-            p = b.get("blackbody").split()
+            p = _split_params(b.get("blackbody"))
             if not p:
                 return
             spd = spd_black_body(_atof(p[0]), scale)
         elif b.get("nblackbody") is not None:
-            p = b.get("nblackbody").split()
+            p = _split_params(b.get("nblackbody"))
             if not p:
                 return
             sc2 = 1.0
@@ -924,7 +999,7 @@ class SceneLoader:
         if spd is None and smp is None:
             return
         if spd is None:
-            p = smp.split()
+            p = _split_params(smp)
             if len(p) % 2:
                 return
             spd = spd_from_samples([(_atof(p[i]), _atof(p[i + 1])) for i in range(0, len(p), 2)])
@@ -933,7 +1008,7 @@ class SceneLoader:
                 xyz = integrate_to_xyz(spd["entries"]["power"][0])
                 rgbv = _xyz_to_rgb(xyz)
                 lum = f32(xyz[1]) if nrm.strip() == "luminance" else f32(max(f32(0.0), rgbv.max()))  # :1597-1600
-                if lum > f32(1e-6):
+                if lum > f32(1.192092896e-07):
                     spd = spd_scaled(spd, f32(1.0) / lum)
         self.add_named_spectrum(name, spd_scaled(spd, scale))
 
@@ -958,11 +1033,8 @@ class SceneLoader:
                 m[fld]["spectrum_index"] = self.reflectance_spectrum(v)
         v = b.get("two_sided")
         if v is not None:
-            tok = v.split()[0] if v.split() else ""
-            try:
-                m["two_sided"] = 1 if int(tok) != 0 else 0
-            except ValueError:
-                m["two_sided"] = 1 if tok in ("true", "on") else 0
+            lead = _leading_int(v)  # an integer, else the whole value against "true" / "on" (:1714-1722)
+            m["two_sided"] = (1 if lead != 0 else 0) if lead is not None else (1 if v in ("true", "on") else 0)
         v = b.get("opacity")
         if v is not None and _floats(v, 1):
             m["opacity"] = min(max(f32(_floats(v, 1)[0]), f32(0.0)), f32(1.0))
@@ -977,13 +1049,30 @@ class SceneLoader:
             v = b.get(key)
             if v is not None and _floats(v, 1):
                 m[key]["value"][0][:] = f32(_floats(v, 1)[0])
+        # map_Ml / map_Tm: metalness / transmission maps with an optional `channel N` (:1772-1800); `map_Pr` never reaches parse_material (the .mtl reader
+        # consumes it as a standard texture key)
+        for key, fld in (("map_Ml", "metalness"), ("map_Tm", "transmission")):
+            v = b.get(key)
+            if v is None:
+                continue
+            p, ch, i = _split_params(v), 0, 0
+            while i < len(p):
+                if p[i] == "channel" and i + 1 < len(p):
+                    lead = _leading_int(p[i + 1])
+                    ch = max(0, lead if lead is not None else 0)
+                    i += 1
+                i += 1
+            f = self.find_file(p[0])
+            if f:
+                m[fld]["image_index"] = self.add_image_file(f, IMG_REPEAT)
+                m[fld]["channel"] = ch
         for slot, fld in (("diffuse", "scattering"), ("specular", "reflectance"), ("transmittance", "scattering")):
             f = self.find_file(b.textures.get(slot))
             if f:
                 m[fld]["image_index"] = self.add_image_file(f, IMG_REPEAT)
         v = b.get("material")
         if v is not None:
-            p = v.split()
+            p = _split_params(v)
             for i, tok in enumerate(p):
                 if tok == "class" and i + 1 < len(p):
                     m["cls"] = MATERIAL_CLASSES.get(p[i + 1].lower(), S.MAT_DIFFUSE)
@@ -1012,7 +1101,7 @@ class SceneLoader:
                 m[key] = self.medium_names.get(v.strip(), S.INVALID)
         v = b.get("normalmap")
         if v is not None:
-            p, i = v.split(), 0
+            p, i = _split_params(v), 0
             while i < len(p):
                 if p[i] == "image" and i + 1 < len(p):
                     f = self.find_file(p[i + 1])
@@ -1025,7 +1114,7 @@ class SceneLoader:
                 i += 1
         v = b.get("thinfilm")
         if v is not None:
-            p, i = v.split(), 0
+            p, i = _split_params(v), 0
             while i < len(p):
                 if p[i] == "image" and i + 1 < len(p):
                     f = self.find_file(p[i + 1])
@@ -1049,7 +1138,7 @@ class SceneLoader:
         if v is not None:
             m["subsurface"]["cls"] = 1
             scale, dist = 1.0, [1.0, 0.2, 0.04]
-            p, i = v.split(), 0
+            p, i = _split_params(v), 0
             while i < len(p):
                 if p[i] == "path" and i + 1 < len(p):
                     m["subsurface"]["path"] = 1 if p[i + 1] in ("refracted", "refraction", "refract") else 0
@@ -1077,7 +1166,7 @@ class SceneLoader:
         v = b.get("emitter")
         if v is not None:
             is_emitter = True
-            p, i = v.split(), 0
+            p, i = _split_params(v), 0
             while i < len(p):
                 if p[i] == "image" and i + 1 < len(p) and self.find_file(p[i + 1]):
                     m["emission"]["image_index"] = self.add_image_file(self.find_file(p[i + 1]), IMG_REPEAT | IMG_BUILD_TABLE)
@@ -1212,7 +1301,7 @@ class SceneLoader:
         # build_tangents (:337-398): without texture coordinates nothing; with them the tangent-space generator the reference calls, which the module's
         # host code restates (etxb_mesh_tangents, csrc/scene_loader_tangents.inl) — the C++ loader runs the same function
         span = v["tex"].max(axis=0) - v["tex"].min(axis=0) if v.shape[0] else np.zeros(2, f32)
-        if float(span[0] * span[0] + span[1] * span[1]) > 1e-6:
+        if float(span[0] * span[0] + span[1] * span[1]) > 1.192092896e-07:
             from . import api
             v = np.ascontiguousarray(v)
             tri = np.ascontiguousarray(tri)
@@ -1232,6 +1321,18 @@ class SceneLoader:
             bt = (bt * np.where(_dot(b0, bt) > 0, f32(1.0), f32(-1.0))[:, None]).astype(f32)
         v["nrm"], v["tan"], v["btn"] = n, t, bt
         self.sd.vertices, self.sd.triangles = [v], [tri]
+
+
+def _leading_int(text):
+    """what sscanf("%d") / atoi read at the start of a string; None when there is no integer"""
+    import re
+    m = re.match(r"\s*([+-]?\d+)", text)
+    return int(m.group(1)) if m else None
+
+
+def _split_params(text):
+    """split_params (scene_representation.cxx:463-478): cut at every single space, empty pieces kept."""
+    return text.split(" ")
 
 
 def focal_length_to_fov(focal_len):

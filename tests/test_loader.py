@@ -937,3 +937,182 @@ def test_zip_compressed_nanovdb_file_and_refusals(tmp_path):
     path = _write_scene(tmp_path, mtl=MTL.replace("scattering 0.4", "scattering 0.4\nvolume cloud.vdb"))
     with pytest.raises(api.EtxbError, match="nvdb"):
         _load_cpp(path)
+
+
+FUZZ_OBJ = """mtllib room.mtl
+v -1 0 -1
+v 1 0 -1
+v 1 0 1
+v -1 0 1
+v -0.3 1.9 -0.3
+v 0.3 1.9 -0.3
+v 0.3 1.9 0.3
+v -0.3 1.9 0.3
+v -1 2 -1
+v 1 2 -1
+v 1 2 1
+vt 0 0
+vt 1 0
+vt 1 1
+vt 0 1
+o floor
+usemtl m0
+f 1/1 4/4 3/3 2/2
+o lamp
+usemtl m1
+f 5 6 7 8
+o top
+usemtl m2
+f 9/1 10/2 11/3
+usemtl m3
+f 1 2 10 9
+"""
+
+
+def _random_material_file(rng):
+    """A random walk through the material dialect: mostly well-formed values, now and then a doubled space (the reference's tokenizer keeps the empty piece),
+    a missing number, an unknown name, a missing texture file.  Cases whose meaning in the reference is undefined behaviour or a NaN camera are left out."""
+    def num():
+        return rng.choice(["0", "1", "0.5", "0.25", "2.5", "1e-3", "10", "0.8", "0.05", "3", "1.5", "0.33", "7e-2"]) if rng.random() < 0.95 else rng.choice(["-1", "abc", ""])
+
+    def rgb():
+        return (" " if rng.random() < 0.9 else "  ").join(num() for _ in range(rng.choice([3, 3, 3, 3, 3, 1, 2, 4])))
+    classes = ["diffuse", "translucent", "plastic", "conductor", "dielectric", "thinfilm", "mirror", "boundary", "velvet", "principled", "void", "bogus"]
+    iors = ["gold", "silver", "water", "glass", "copper", "1.33", "1.5 0.2", "0.2 3.9", "unobtainium", "diamond", "plastic", "chrome"]
+
+    def material(name, others):
+        o = []
+        if rng.random() < 0.7: o.append("Kd " + rgb())
+        if rng.random() < 0.4: o.append("Ks " + rgb())
+        if rng.random() < 0.2: o.append("Kt " + rgb())
+        if rng.random() < 0.3: o.append("Ke " + rng.choice([rgb(), "blackbody 3000", "nblackbody 5000 scale 2", "sunlike", "5", "warm"]))
+        if rng.random() < 0.6: o.append("material class " + rng.choice(classes))
+        if rng.random() < 0.4: o.append("Pr " + rng.choice([num(), num() + " " + num()]))
+        if rng.random() < 0.3: o.append("int_ior " + rng.choice(iors))
+        if rng.random() < 0.2: o.append("ext_ior " + rng.choice(iors))
+        if rng.random() < 0.2: o.append("two_sided " + rng.choice(["1", "0", "true", "on", "off", "yes", "true 1"]))
+        if rng.random() < 0.2: o.append("opacity " + num())
+        if rng.random() < 0.2: o.append("metalness " + num())
+        if rng.random() < 0.2: o.append("transmission " + num())
+        if rng.random() < 0.2: o.append("diffuse " + rng.choice(["0", "1", "2", "x"]))
+        if rng.random() < 0.25: o.append("thinfilm " + rng.choice(["range 100 500 ior 1.3", "ior water range 50 60", "range 10", "ior 1.4"]))
+        if rng.random() < 0.25: o.append("subsurface " + rng.choice(["path refracted distances 1 0.5 0.2 scale 0.1", "class approximate scale 2", "distances 0.1 0.2 0.3", "path diffuse"]))
+        if rng.random() < 0.3: o.append("emitter " + rng.choice(["color 3 2 1 scale 2", "blackbody 4500 scale 0.5 twosided", "nblackbody 6500 collimated 0.5", "scale 3", "collimated 2 color 1 1", "twosided"]))
+        if rng.random() < 0.25 and others: o.append("base " + rng.choice(others))
+        if rng.random() < 0.2: o.append("int_medium " + rng.choice(["fog", "haze", "none"]))
+        if rng.random() < 0.1: o.append("ext_medium " + rng.choice(["fog", "haze"]))
+        if rng.random() < 0.15: o.append("normalmap scale " + num())
+        if rng.random() < 0.2: o.append("map_Ml tex.png" + rng.choice(["", " channel 2", " channel -3", "  channel 1"]))
+        if rng.random() < 0.2: o.append("map_Tm " + rng.choice(["tex.png channel 1", "missing.png", "tex.png"]))
+        if rng.random() < 0.2: o.append("map_Kd tex.png")
+        if rng.random() < 0.1: o.append("map_Pr tex.png channel 1")
+        rng.shuffle(o)
+        return "\n".join(["newmtl " + name] + o) + "\n"
+    parts = ["newmtl et::spectrum\nid warm\n" + rng.choice(["blackbody 2800", "rgb 1 0.6 0.3\nilluminant", "samples 400 0.2 500 0.5 700 1.0\nnormalize " + rng.choice(["luminance", "max"]),
+                                                           "nblackbody 4000 scale 3", "rgb 0.5 0.5", "samples 400 1 500"]) + "\n" + (("scale " + num() + "\n") if rng.random() < 0.5 else ""),
+             "newmtl et::medium\nid fog\n" + rng.choice(["absorption 0.1 0.2 0.3\nscattering 0.5", "scattering 0.2 0.3 0.4\ng 0.5", "rayleigh scale 0.01", "mie scale 2\nanisotropy 0.7",
+                                                        "parametric color 0.9 0.5 0.3 distance 0.5", "absorbtion 0.3", "parametric distances 1 2 3 scale 0.2"]) + "\n" + ("enclosed\n" if rng.random() < 0.3 else "")]
+    if rng.random() < 0.9:
+        parts.append("newmtl et::dir\ncolor " + rng.choice([rgb(), "warm", "blackbody 5500 scale 2", "7"]) + "\ndirection " + rgb() + "\n" + (("angular_diameter " + num() + "\n") if rng.random() < 0.5 else ""))
+    else:
+        parts.append("newmtl et::env\ncolor " + rgb() + "\n" + (("rotation " + num() + "\n") if rng.random() < 0.5 else "") + (("scale " + num() + "\n") if rng.random() < 0.5 else ""))
+    if rng.random() < 0.5:
+        parts.append("newmtl et::env\ncolor " + rng.choice([rgb(), "warm"]) + "\n")
+    if rng.random() < 0.7:
+        keys = ["target 0 1 0", "up 0 1 0", "fov " + num(), "focal-length 35", "lens-radius 0.01", "focal-distance 3", "clip-near 0.1", "clip-far 100", "class eq", "ext_medium fog", "active 1"]
+        parts.append("newmtl et::camera\n" + "\n".join(rng.sample(keys, rng.randrange(1, 8))) + "\nviewport 40 30\norigin 0.5 1 4\n")
+    names = []
+    for k in range(4):
+        if rng.random() < 0.1:
+            continue
+        parts.append(material("m%d" % k, names))
+        names.append("m%d" % k)
+    return "\n".join(parts)
+
+
+def test_random_material_files_match_the_reference_loader(ref, tmp_path):
+    """Differential test of the material dialect: 60 random material files (seeded) read by the C++ loader and by the reference's loader, PODs compared like
+    everywhere else in this file.  This is the test that found: kEpsilon is FLT_EPSILON, the reference's tokenizer keeps the empty piece between two spaces,
+    `two_sided` compares its whole value, texture paths are not checked for existence (a missing file is the white placeholder), `map_Ml` / `map_Tm`."""
+    import random
+    rng = random.Random(2024)
+    tex = np.random.default_rng(3).integers(0, 256, (4, 6, 4), dtype=np.uint8)
+    tex[..., 3] = 255
+    for it in range(60):
+        d = tmp_path / f"s{it}"
+        d.mkdir()
+        (d / "room.obj").write_text(FUZZ_OBJ)
+        (d / "tex.png").write_bytes(_png_bytes(tex, 6, [0, 1], 6))
+        (d / "room.mtl").write_text(_random_material_file(rng))
+        js = {"geometry": "room.obj", "materials": "room.mtl", "samples": rng.choice([1, 16, 300]), "spectral": rng.random() < 0.5}
+        if rng.random() < 0.3:
+            js["camera"] = {"fov": 40, "viewport": [32, 24], "origin": [0, 1, 3], "target": [0, 1, 0]}
+        if rng.random() < 0.3:
+            js["max-path-length"] = rng.choice([0, 1, 7])
+        (d / "room.json").write_text(json.dumps(js))
+        rs = ref(str(d / "room.json"))
+        sd = _load_cpp(str(d / "room.json"))
+        problems = compare_scenes(rs, sd)
+        assert not problems, (it, problems, (d / "room.mtl").read_text())
+        rs.close()
+        sd.close()
+
+
+def _random_obj_file(rng):
+    """Random geometry in the .obj dialect: polygons with 3-6 corners (quads split along the shorter diagonal, larger ones by ear clipping), the four index
+    styles, negative indices, doubled spaces, `o` / `g` / `s` lines, material switches incl. an undeclared one (the index-cursor quirk), a degenerate face."""
+    def f():
+        return "%.3f" % rng.uniform(-2, 2)
+    lines = ["mtllib room.mtl"]
+    nv, nn, nt = rng.randrange(6, 30), rng.choice([0, 0, rng.randrange(1, 10)]), rng.choice([0, rng.randrange(1, 10)])
+    lines += ["v %s %s %s" % (f(), f(), f()) + (" 1.0" if rng.random() < 0.1 else "") for _ in range(nv)]
+    lines += ["vn %s %s %s" % (f(), f(), f()) for _ in range(nn)]
+    lines += ["vt %s %s" % (f(), f()) + (" 0" if rng.random() < 0.2 else "") for _ in range(nt)]
+    for face in range(rng.randrange(3, 25)):
+        r = rng.random()
+        if r < 0.25:
+            lines.append("usemtl " + rng.choice(["a", "b", "lamp", "A", "nope", "b"]))
+        elif r < 0.35:
+            lines.append(rng.choice(["o", "g"]) + " part%d" % face)
+        elif r < 0.4:
+            lines.append("s " + rng.choice(["1", "off", "0"]))
+        elif r < 0.43:
+            lines.append("# comment")
+        corners = rng.sample(range(1, nv + 1), rng.choice([3, 3, 3, 4, 4, 5, 6]))
+        style, negative, tokens = rng.choice(["v", "v/t", "v//n", "v/t/n"]), rng.random() < 0.15, []
+        for i in corners:
+            vi = (i - nv - 1) if negative else i
+            t, n = (rng.randrange(1, nt + 1) if nt else None), (rng.randrange(1, nn + 1) if nn else None)
+            if style == "v" or (style == "v/t" and t is None) or (style == "v//n" and n is None) or (style == "v/t/n" and (t is None or n is None)):
+                tokens.append(str(vi))
+            elif style == "v/t":
+                tokens.append(f"{vi}/{t}")
+            elif style == "v//n":
+                tokens.append(f"{vi}//{n}")
+            else:
+                tokens.append(f"{vi}/{t}/{n}")
+        lines.append("f " + (" " if rng.random() < 0.9 else "  ").join(tokens))
+    if rng.random() < 0.2:
+        lines.append("f 1 1 2")
+    return "\n".join(lines) + "\n"
+
+
+def test_random_obj_files_match_the_reference_loader(ref, tmp_path):
+    """Differential test of the geometry side: 60 random .obj files (seeded) through the C++ loader and the reference's (tinyobjloader + load_from_obj +
+    validate_normals + the tangent-space generator + commit).  It found the ear clipping of polygons with more than four corners."""
+    import random
+    rng = random.Random(77)
+    mtl = ("newmtl et::dir\ncolor 2 2 2\ndirection 0.2 1 0.3\n\nnewmtl a\nKd 0.5 0.5 0.5\n\nnewmtl b\nKd 0.2 0.6 0.2\nmaterial class plastic\n\nnewmtl lamp\nKe 5 5 5\n\n"
+           "newmtl et::camera\nviewport 32 24\norigin 0.3 1 6\ntarget 0 0.5 0\n")
+    for it in range(60):
+        d = tmp_path / f"o{it}"
+        d.mkdir()
+        (d / "room.obj").write_text(_random_obj_file(rng))
+        (d / "room.mtl").write_text(mtl)
+        (d / "room.json").write_text(json.dumps({"geometry": "room.obj", "materials": "room.mtl", "samples": 4, "force-tangents": rng.random() < 0.2}))
+        rs = ref(str(d / "room.json"))
+        sd = _load_cpp(str(d / "room.json"))
+        problems = compare_scenes(rs, sd)
+        assert not problems, (it, problems, (d / "room.obj").read_text())
+        rs.close()
+        sd.close()
