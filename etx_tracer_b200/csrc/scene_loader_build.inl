@@ -1267,18 +1267,20 @@ struct etxb_scene_file_impl {
       JsonParser parser{text};
       Json js = parser.value();
       if (js.kind != Json::Object) fail(file_name + ": a JSON object was expected");
-      auto number = [](const Json& j) { return j.kind == Json::Number ? j.number : (j.kind == Json::Bool ? (j.b ? 1.0 : 0.0) : 0.0); };
+      // json_get_int / _float / _bool / _string (core/json.hxx:41-72) look at the value's type: a number where a bool is expected (or the other way round) is ignored
+      auto number = [](const Json& j) { return j.number; };
+      auto is_number = [](const Json& j) { return j.kind == Json::Number; };
       for (const auto& kv : js.members) {
         const std::string& key = kv.first;
         const Json& val = kv.second;
-        if (key == "samples") samples = uint32_t(std::max<int64_t>(1, int64_t(number(val))));
-        else if (key == "random-termination-start") rr_start = uint32_t(std::max<int64_t>(1, int64_t(number(val))));
-        else if (key == "max-path-length") max_len = uint32_t(std::max<int64_t>(1, int64_t(number(val))));
-        else if (key == "min-path-length") min_len = uint32_t(std::max<int64_t>(1, int64_t(number(val))));  // the reference clamps this one to 1 as well (:716)
+        if (key == "samples" && is_number(val)) samples = uint32_t(std::max<int64_t>(1, int64_t(number(val))));
+        else if (key == "random-termination-start" && is_number(val)) rr_start = uint32_t(std::max<int64_t>(1, int64_t(number(val))));
+        else if (key == "max-path-length" && is_number(val)) max_len = uint32_t(std::max<int64_t>(1, int64_t(number(val))));
+        else if (key == "min-path-length" && is_number(val)) min_len = uint32_t(std::max<int64_t>(1, int64_t(number(val))));  // the reference clamps this one to 1 as well (:716)
         else if (key == "geometry" && val.kind == Json::String) geometry = join(base, val.text);
         else if (key == "materials" && val.kind == Json::String) materials_file = join(base, val.text);
-        else if (key == "spectral") spectral = number(val) != 0.0;
-        else if (key == "force-tangents") force_tangents = number(val) != 0.0;
+        else if (key == "spectral" && val.kind == Json::Bool) spectral = val.b;
+        else if (key == "force-tangents" && val.kind == Json::Bool) force_tangents = val.b;
         else if (key == "camera" && val.kind == Json::Object) {
           for (const auto& ck : val.members) {
             const Json& cv = ck.second;
@@ -1286,12 +1288,12 @@ struct etxb_scene_file_impl {
               if (cv.kind == Json::Array && cv.items.size() >= 3) out = {float(cv.items[0].number), float(cv.items[1].number), float(cv.items[2].number)};
             };
             if (ck.first == "class") cam.cls = (cv.text == "eq") ? 1u : 0u;
-            else if (ck.first == "fov") cam.fov = float(number(cv));
-            else if (ck.first == "focal-length") focal = float(number(cv)), has_focal = true;
-            else if (ck.first == "lens-radius") cam.lens_radius = float(number(cv));
-            else if (ck.first == "focal-distance") cam.focal_distance = float(number(cv));
-            else if (ck.first == "clip-near") cam.clip_near = float(number(cv)), cam.has_near = true;
-            else if (ck.first == "clip-far") cam.clip_far = float(number(cv)), cam.has_far = true;
+            else if (ck.first == "fov" && is_number(cv)) cam.fov = float(number(cv));
+            else if (ck.first == "focal-length" && is_number(cv)) focal = float(number(cv)), has_focal = true;
+            else if (ck.first == "lens-radius" && is_number(cv)) cam.lens_radius = float(number(cv));
+            else if (ck.first == "focal-distance" && is_number(cv)) cam.focal_distance = float(number(cv));
+            else if (ck.first == "clip-near" && is_number(cv)) cam.clip_near = float(number(cv)), cam.has_near = true;
+            else if (ck.first == "clip-far" && is_number(cv)) cam.clip_far = float(number(cv)), cam.has_far = true;
             else if (ck.first == "origin") vec(cam.origin);
             else if (ck.first == "target") vec(cam.target);
             else if (ck.first == "up") vec(cam.up);

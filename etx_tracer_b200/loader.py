@@ -1359,36 +1359,40 @@ def load_scene(file_name, data_folder=None):
             raise LoaderError(f"{file_name}: {e}")
         for key in sorted(js):
             val = js[key]
-            if key == "samples":
+            # json_get_int / _float / _bool / _string (core/json.hxx:41-72) look at the value's type: a number where a bool is expected (or the other way
+            # round) is ignored
+            number = isinstance(val, (int, float)) and not isinstance(val, bool)
+            if key == "samples" and number:
                 samples = max(1, int(val))
-            elif key == "random-termination-start":
+            elif key == "random-termination-start" and number:
                 rr_start = max(1, int(val))
-            elif key == "max-path-length":
+            elif key == "max-path-length" and number:
                 max_len = max(1, int(val))
-            elif key == "min-path-length":
+            elif key == "min-path-length" and number:
                 min_len = max(1, int(val))  # the reference clamps this one to 1 as well (:716)
-            elif key == "geometry":
+            elif key == "geometry" and isinstance(val, str):
                 geometry = os.path.join(base, val)
-            elif key == "materials":
+            elif key == "materials" and isinstance(val, str):
                 materials = os.path.join(base, val)
-            elif key == "spectral":
-                spectral = bool(val)
-            elif key == "force-tangents":
-                force_tangents = bool(val)
+            elif key == "spectral" and isinstance(val, bool):
+                spectral = val
+            elif key == "force-tangents" and isinstance(val, bool):
+                force_tangents = val
             elif key == "camera" and isinstance(val, dict):
                 for ck in sorted(val):
                     cv = val[ck]
+                    cnum = isinstance(cv, (int, float)) and not isinstance(cv, bool)
                     if ck == "class":
                         cam["cls"] = 1 if cv == "eq" else 0
-                    elif ck == "fov":
+                    elif ck == "fov" and cnum:
                         cam["fov"] = float(cv)
-                    elif ck == "focal-length":
+                    elif ck == "focal-length" and cnum:
                         cam["focal"] = float(cv)
-                    elif ck in ("lens-radius", "focal-distance", "clip-near", "clip-far"):
+                    elif ck in ("lens-radius", "focal-distance", "clip-near", "clip-far") and cnum:
                         cam[ck.replace("-", "_")] = float(cv)
-                    elif ck in ("origin", "target", "up"):
+                    elif ck in ("origin", "target", "up") and isinstance(cv, list) and len(cv) >= 3:
                         cam[ck] = tuple(float(x) for x in cv[:3])
-                    elif ck == "viewport":
+                    elif ck == "viewport" and isinstance(cv, list) and len(cv) >= 2:
                         cam["viewport"] = (int(cv[0]), int(cv[1]))
     if cam["viewport"][0] * cam["viewport"][1] == 0:
         cam["viewport"] = (1280, 720)

@@ -1033,7 +1033,8 @@ def _random_material_file(rng):
 def test_random_material_files_match_the_reference_loader(ref, tmp_path):
     """Differential test of the material dialect: 60 random material files (seeded) read by the C++ loader and by the reference's loader, PODs compared like
     everywhere else in this file.  This is the test that found: kEpsilon is FLT_EPSILON, the reference's tokenizer keeps the empty piece between two spaces,
-    `two_sided` compares its whole value, texture paths are not checked for existence (a missing file is the white placeholder), `map_Ml` / `map_Tm`."""
+    `two_sided` compares its whole value, texture paths are not checked for existence (a missing file is the white placeholder), `map_Ml` / `map_Tm`, and that
+    the scene description's values are type-checked (`"spectral": 1` is ignored)."""
     import random
     rng = random.Random(2024)
     tex = np.random.default_rng(3).integers(0, 256, (4, 6, 4), dtype=np.uint8)
@@ -1044,11 +1045,15 @@ def test_random_material_files_match_the_reference_loader(ref, tmp_path):
         (d / "room.obj").write_text(FUZZ_OBJ)
         (d / "tex.png").write_bytes(_png_bytes(tex, 6, [0, 1], 6))
         (d / "room.mtl").write_text(_random_material_file(rng))
-        js = {"geometry": "room.obj", "materials": "room.mtl", "samples": rng.choice([1, 16, 300]), "spectral": rng.random() < 0.5}
-        if rng.random() < 0.3:
-            js["camera"] = {"fov": 40, "viewport": [32, 24], "origin": [0, 1, 3], "target": [0, 1, 0]}
-        if rng.random() < 0.3:
-            js["max-path-length"] = rng.choice([0, 1, 7])
+        js = {"geometry": "room.obj", "materials": "room.mtl", "samples": rng.choice([1, 16, 300, 0]), "spectral": rng.choice([True, False, 1, 0])}  # 1 / 0 are not booleans: ignored
+        if rng.random() < 0.5:
+            options = (("class", rng.choice(["perspective", "eq"])), ("fov", rng.choice([40, 65.5, 120])), ("focal-length", rng.choice([24, 50.0])), ("lens-radius", 0.02),
+                       ("focal-distance", 2.5), ("clip-near", 0.05), ("clip-far", 200.0), ("origin", [0.2, 1, 3]), ("target", [0, 1, 0]), ("up", [0, 1, 0.1]),
+                       ("viewport", rng.choice([[32, 24], [17, 9]])))
+            js["camera"] = {k: v for k, v in options if rng.random() < 0.5}
+        for key, choices in (("max-path-length", [0, 1, 7, 100000]), ("min-path-length", [0, 1, 3]), ("random-termination-start", [0, 1, 9]), ("force-tangents", [True, False])):
+            if rng.random() < 0.3:
+                js[key] = rng.choice(choices)
         (d / "room.json").write_text(json.dumps(js))
         rs = ref(str(d / "room.json"))
         sd = _load_cpp(str(d / "room.json"))
