@@ -51,6 +51,7 @@ def load_library(flavor="fast"):
         lib.etxb_atmosphere_images.argtypes = [C.c_char_p, vp, C.c_float, vp, u32, u32, vp, vp]
         lib.etxb_options_file_string.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, u64]
         lib.etxb_mesh_tangents.argtypes = [vp, u64, vp, u64]
+        lib.etxb_image_file_read.argtypes = [C.c_char_p, vp, vp, vp, vp, u64, C.c_char_p, u64]
         lib.etxb_nvdb_density.argtypes = [C.c_char_p, vp, vp, u64, C.c_char_p, u64]
         for fn in (lib.etxb_scene_file_scene, lib.etxb_scene_file_camera):
             fn.argtypes = [vp]
@@ -136,6 +137,19 @@ def load_library(flavor="fast"):
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def read_image(file_name, flavor="fast"):
+    """The module's image readers (PNG in every form, OpenEXR, Radiance HDR, PFM): (H, W, 4) uint8 or float32, rows in file order."""
+    lib = load_library(flavor)
+    w, h, eight = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    err = C.create_string_buffer(512)
+    if lib.etxb_image_file_read(os.fsencode(file_name), C.byref(w), C.byref(h), C.byref(eight), None, 0, err, len(err)) != 0:
+        raise EtxbError(-4, err.value.decode(errors="replace"))
+    out = np.zeros((h.value, w.value, 4), dtype=np.uint8 if eight.value else np.float32)
+    if lib.etxb_image_file_read(os.fsencode(file_name), C.byref(w), C.byref(h), C.byref(eight), _p(out), out.nbytes, err, len(err)) != 0:
+        raise EtxbError(-4, err.value.decode(errors="replace"))
+    return out
 
 
 def write_exr(file_name, rgba, flavor="fast"):

@@ -141,71 +141,140 @@ struct Pixels {
 };
 uint32_t be32(const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
 
+// Every PNG form the reference's reader (stb_image) decodes: bit depths 1 / 2 / 4 / 8 / 16, the five colour types, Adam7 interlacing, tRNS colour keys
+// and palette alpha — reduced to 8 bits the way stb_image does it (16-bit samples keep their high byte, low-depth grey is scaled to 0..255), then
+// widened to RGBA8 the way the reference's texture pool does it (image_pool.cxx:353-381: 4 channels kept, 3 get alpha 255, 1 is replicated, 2 — grey with
+// alpha, which includes grey with a colour key — has no case there and stays zero-filled).
 Pixels read_png(const std::string& path) {
   std::string d = read_file(path);
   const uint8_t* b = reinterpret_cast<const uint8_t*>(d.data());
   if (d.size() < 8 || memcmp(b, "\x89PNG\r\n\x1a\n", 8) != 0) fail(path + ": not a PNG file");
   size_t pos = 8;
-  std::vector<uint8_t> idat, palette;
+  std::vector<uint8_t> idat, palette, trns;
   uint32_t w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
   while (pos + 12 <= d.size()) {
     uint32_t n = be32(b + pos);
     const uint8_t* type = b + pos + 4;
     const uint8_t* body = b + pos + 8;
-    if (pos + 12 + n > d.size()) break;
+    if (n > d.size() || pos + 12 + n > d.size()) break;
     if (!memcmp(type, "IHDR", 4) && n >= 13) {
       w = be32(body), h = be32(body + 4), depth = body[8], ctype = body[9], interlace = body[12];
     } else if (!memcmp(type, "PLTE", 4)) {
       palette.assign(body, body + n);
+    } else if (!memcmp(type, "tRNS", 4)) {
+      trns.assign(body, body + n);
     } else if (!memcmp(type, "IDAT", 4)) {
       idat.insert(idat.end(), body, body + n);
     }
     pos += 12 + n;
   }
-  if (depth != 8 || interlace != 0 || w == 0 || h == 0) fail(path + ": only 8-bit non-interlaced PNG files are read");
-  uint32_t ch = (ctype == 0) ? 1 : (ctype == 2) ? 3 : (ctype == 3) ? 1 : (ctype == 4) ? 2 : (ctype == 6) ? 4 : 0;
-  if (ch == 0) fail(path + ": unknown PNG colour type");
+  const uint32_t ch = (ctype == 0) ? 1 : (ctype == 2) ? 3 : (ctype == 3) ? 1 : (ctype == 4) ? 2 : (ctype == 6) ? 4 : 0;
+  const bool depth_ok = (depth == 8) || (depth == 16 && ctype != 3) || ((depth == 1 || depth == 2 || depth == 4) && (ctype == 0 || ctype == 3));
+  if (ch == 0 || !depth_ok || interlace > 1 || w == 0 || h == 0 || w > (1u << 24) || h > (1u << 24)) fail(path + ": unsupported PNG header");
   std::vector<uint8_t> raw = inflate_zlib(idat.data(), idat.size());
-  const size_t stride = size_t(w) * ch;
-  if (raw.size() < (stride + 1) * h) fail(path + ": truncated PNG data");
-  std::vector<uint8_t> img(stride * h);
-  std::vector<uint8_t> zero(stride, 0);
-  for (uint32_t y = 0; y < h; ++y) {
-    const uint8_t* line = raw.data() + size_t(y) * (stride + 1);
-    uint8_t ft = line[0];
-    const uint8_t* src = line + 1;
-    uint8_t* cur = img.data() + size_t(y) * stride;
-    const uint8_t* prev = y ? (cur - stride) : zero.data();
-    for (size_t x = 0; x < stride; ++x) {
-      int a = (x >= ch) ? cur[x - ch] : 0, bb = prev[x], c = (x >= ch) ? prev[x - ch] : 0, p = 0;
-      switch (ft) {
-        case 0: p = 0; break;
-        case 1: p = a; break;
-        case 2: p = bb; break;
-        case 3: p = (a + bb) >> 1; break;
-        default: {
-          int pa = abs(bb - c), pb = abs(a - c), pc = abs(a + bb - 2 * c);
-          p = (pa <= pb && pa <= pc) ? a : (pb <= pc ? bb : c);
+  if (uint64_t(w) * h * ch * (depth == 16 ? 2 : 1) > uint64_t(raw.size()) * 8u + 64u) fail(path + ": truncated PNG data");
+  // samples of the whole image, 16 bits wide (low depths unscaled for now)
+  std::vector<uint16_t> img(size_t(w) * h * ch, 0);
+  static const uint32_t x0[7] = {0, 4, 0, 2, 0, 1, 0}, y0[7] = {0, 0, 4, 0, 2, 0, 1}, dx[7] = {8, 8, 4, 4, 2, 2, 1}, dy[7] = {8, 8, 8, 4, 4, 2, 2};
+  const uint32_t passes = interlace ? 7u : 1u;
+  const size_t bpp = std::max<size_t>(1, size_t(ch) * depth / 8);  // the filters' pixel distance in bytes
+  size_t at = 0;
+  std::vector<uint8_t> cur, prev;
+  for (uint32_t pass = 0; pass < passes; ++pass) {
+    const uint32_t ox = interlace ? x0[pass] : 0u, oy = interlace ? y0[pass] : 0u, sx = interlace ? dx[pass] : 1u, sy = interlace ? dy[pass] : 1u;
+    const uint32_t pw = (w > ox) ? (w - ox + sx - 1) / sx : 0u, ph = (h > oy) ? (h - oy + sy - 1) / sy : 0u;
+    if (pw == 0 || ph == 0) continue;
+    const size_t stride = (size_t(pw) * ch * depth + 7) / 8;
+    prev.assign(stride, 0);
+    cur.assign(stride, 0);
+    for (uint32_t y = 0; y < ph; ++y) {
+      if (at + 1 + stride > raw.size()) fail(path + ": truncated PNG data");
+      const uint8_t ft = raw[at];
+      const uint8_t* src = raw.data() + at + 1;
+      at += 1 + stride;
+      if (ft > 4) fail(path + ": bad PNG filter");
+      for (size_t x = 0; x < stride; ++x) {
+        const int a = (x >= bpp) ? cur[x - bpp] : 0, up = prev[x], c = (x >= bpp) ? prev[x - bpp] : 0;
+        int p = 0;
+        switch (ft) {
+          case 1: p = a; break;
+          case 2: p = up; break;
+          case 3: p = (a + up) >> 1; break;
+          case 4: {
+            const int pa = abs(up - c), pb = abs(a - c), pc = abs(a + up - 2 * c);
+            p = (pa <= pb && pa <= pc) ? a : (pb <= pc ? up : c);
+            break;
+          }
+          default: break;
+        }
+        cur[x] = uint8_t(src[x] + p);
+      }
+      const uint32_t iy = oy + y * sy;
+      for (uint32_t x = 0; x < pw; ++x) {
+        uint16_t* o = img.data() + (size_t(iy) * w + (ox + size_t(x) * sx)) * ch;
+        for (uint32_t k = 0; k < ch; ++k) {
+          const size_t sample = size_t(x) * ch + k;
+          if (depth == 16) {
+            o[k] = uint16_t((uint16_t(cur[sample * 2]) << 8) | cur[sample * 2 + 1]);
+          } else if (depth == 8) {
+            o[k] = cur[sample];
+          } else {
+            const size_t bit = sample * depth;
+            o[k] = uint16_t((cur[bit >> 3] >> (8 - depth - (bit & 7))) & ((1u << depth) - 1u));
+          }
         }
       }
-      cur[x] = uint8_t(src[x] + p);
+      prev.swap(cur);
+    }
+  }
+  // 8-bit samples, palette and colour key
+  static const uint32_t depth_scale[9] = {0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01};
+  uint32_t out_n = ch;
+  std::vector<uint8_t> px;
+  const size_t count = size_t(w) * h;
+  if (ctype == 3) {
+    out_n = trns.empty() ? 3u : 4u;
+    px.assign(count * out_n, 0);
+    for (size_t i = 0; i < count; ++i) {
+      const size_t idx = img[i];
+      uint8_t rgba[4] = {0, 0, 0, 255};
+      if (idx * 3 + 2 < palette.size()) memcpy(rgba, palette.data() + idx * 3, 3);
+      if (idx < trns.size()) rgba[3] = trns[idx];
+      memcpy(px.data() + i * out_n, rgba, out_n);
+    }
+  } else {
+    const bool keyed = !trns.empty() && (ctype == 0 || ctype == 2) && trns.size() >= size_t(ch) * 2;
+    out_n = ch + (keyed ? 1u : 0u);
+    px.assign(count * out_n, 0);
+    uint16_t key[3] = {0, 0, 0};
+    for (uint32_t k = 0; keyed && k < ch; ++k) {
+      const uint16_t v = uint16_t((uint16_t(trns[k * 2]) << 8) | trns[k * 2 + 1]);
+      key[k] = (depth == 16) ? v : uint16_t((v & 255u) * depth_scale[depth]);
+    }
+    for (size_t i = 0; i < count; ++i) {
+      bool match = keyed;
+      for (uint32_t k = 0; k < ch; ++k) {
+        const uint16_t v = (depth == 16) ? img[i * ch + k] : uint16_t(img[i * ch + k] * depth_scale[depth]);
+        if (keyed && v != key[k]) match = false;
+        px[i * out_n + k] = (depth == 16) ? uint8_t(v >> 8) : uint8_t(v);
+      }
+      if (keyed) px[i * out_n + ch] = match ? 0 : 255;
     }
   }
   Pixels out;
   out.w = w, out.h = h, out.eight_bit = true;
-  out.u8.assign(size_t(w) * h * 4, 255);
-  for (size_t i = 0; i < size_t(w) * h; ++i) {
+  out.u8.assign(count * 4, 255);
+  for (size_t i = 0; i < count; ++i) {
     uint8_t* o = out.u8.data() + i * 4;
-    const uint8_t* s = img.data() + i * ch;
-    if (ctype == 3) {
-      if (size_t(s[0]) * 3 + 2 < palette.size()) memcpy(o, palette.data() + size_t(s[0]) * 3, 3);
-    } else if (ch == 1) {
-      o[0] = o[1] = o[2] = s[0];
-    } else if (ch == 2) {
-      // grey + alpha: the reference's switch over the channel count has no case for 2 (image_pool.cxx:353-381), the image stays zero-filled
-      o[0] = o[1] = o[2] = o[3] = 0;
+    const uint8_t* sp = px.data() + i * out_n;
+    if (out_n == 4) {
+      memcpy(o, sp, 4);
+    } else if (out_n == 3) {
+      memcpy(o, sp, 3);
+    } else if (out_n == 1) {
+      o[0] = o[1] = o[2] = sp[0];
     } else {
-      memcpy(o, s, ch);
+      o[0] = o[1] = o[2] = o[3] = 0;  // two channels: no case in the reference's switch over the channel count
     }
   }
   return out;

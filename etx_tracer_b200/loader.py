@@ -278,6 +278,8 @@ def _read_png(path):
             hdr = struct.unpack(">IIBBBBB", body)
         elif typ == b"PLTE":
             pal = np.frombuffer(body, np.uint8).reshape(-1, 3)
+        elif typ == b"tRNS":
+            raise LoaderError(f"{path}: a PNG with a tRNS chunk is left to the module's reader")
         elif typ == b"IDAT":
             idat += body
         pos += 12 + n
@@ -445,7 +447,15 @@ def read_image(path):
     """-> float32 RGBA (linear values as stored for .exr, raw 0..1 for 8-bit files; the caller applies the sRGB curve)."""
     ext = os.path.splitext(path)[1].lower()
     if ext == ".png":
-        return _read_png(path), True
+        try:
+            return _read_png(path), True
+        except LoaderError:
+            # bit depths other than 8, Adam7, colour keys: the module's reader covers every PNG form the reference's does (etxb_image_file_read)
+            from . import api
+            try:
+                return api.read_image(path), True
+            except api.EtxbError as e:
+                raise LoaderError(str(e))
     if ext == ".exr":
         return _read_exr(path), False
     if ext == ".hdr":

@@ -1121,3 +1121,115 @@ def test_random_obj_files_match_the_reference_loader(ref, tmp_path):
         assert not problems, (it, problems, (d / "room.obj").read_text())
         rs.close()
         sd.close()
+
+
+def _png_any(samples, ctype, depth, interlace=False, trns=None, palette=None, level=6):
+    """A PNG of any form: `samples` (h, w, channels) integers below 2**depth; bit depths 1 / 2 / 4 / 8 / 16; Adam7 interlacing; a tRNS chunk; a palette.
+    Row filters cycle through the five types."""
+    import struct
+    import zlib
+    h, w, ch = samples.shape
+
+    def pack_rows(block):
+        out = bytearray()
+        ph, pw = block.shape[:2]
+        prev = np.zeros(0, np.int32)
+        bpp = max(1, ch * depth // 8)
+        for y in range(ph):
+            row = block[y].reshape(-1).astype(np.uint32)
+            if depth == 16:
+                data = np.stack([row >> 8, row & 255], axis=1).reshape(-1).astype(np.int32)
+            elif depth == 8:
+                data = row.astype(np.int32)
+            else:
+                bits = np.zeros(((len(row) * depth + 7) // 8) * 8, np.uint8)
+                for k in range(depth):
+                    bits[np.arange(len(row)) * depth + k] = (row >> (depth - 1 - k)) & 1
+                data = np.packbits(bits).astype(np.int32)
+            if len(prev) != len(data):
+                prev = np.zeros(len(data), np.int32)
+            ft = y % 5
+            a = np.concatenate([np.zeros(bpp, np.int32), data[:-bpp]]) if len(data) > bpp else np.zeros(len(data), np.int32)
+            c = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]]) if len(data) > bpp else np.zeros(len(data), np.int32)
+            if ft == 0:
+                pred = np.zeros_like(data)
+            elif ft == 1:
+                pred = a
+            elif ft == 2:
+                pred = prev
+            elif ft == 3:
+                pred = (a + prev) >> 1
+            else:
+                pa, pb, pc = np.abs(prev - c), np.abs(a - c), np.abs(a + prev - 2 * c)
+                pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, prev, c))
+            out += bytes([ft]) + ((data - pred) & 255).astype(np.uint8).tobytes()
+            prev = data
+        return bytes(out)
+    if interlace:
+        raw = b""
+        for ox, oy, sx, sy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+            block = samples[oy::sy, ox::sx]
+            if block.shape[0] and block.shape[1]:
+                raw += pack_rows(block)
+    else:
+        raw = pack_rows(samples)
+
+    def chunk(typ, body):
+        return struct.pack(">I", len(body)) + typ + body + struct.pack(">I", zlib.crc32(typ + body) & 0xffffffff)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 1 if interlace else 0))
+    if palette is not None:
+        out += chunk(b"PLTE", np.asarray(palette, np.uint8).tobytes())
+    if trns is not None:
+        out += chunk(b"tRNS", bytes(trns))
+    return out + chunk(b"IDAT", zlib.compress(raw, level)) + chunk(b"IEND", b"")
+
+
+PNG_FORMS = ["rgb16", "rgba16_interlaced", "gray1", "gray2_interlaced", "gray4", "gray16", "palette2", "palette4_trns_interlaced", "palette8_trns", "rgb8_key", "rgb16_key", "gray8_key",
+             "rgba8_interlaced", "gray_alpha16"]
+
+
+@pytest.mark.parametrize("form", PNG_FORMS)
+def test_every_png_form_decodes_like_the_reference(ref, tmp_path, form, load):
+    """Bit depths 1 / 2 / 4 / 16, Adam7 interlacing, colour keys and palette alpha: whatever stb_image decodes, reduced to 8 bits its way (16-bit samples keep the
+    high byte, low-depth grey is scaled) — and grey + alpha forms (incl. grey with a colour key) zero-filled like in the reference's texture pool."""
+    import struct
+    rng = np.random.default_rng(PNG_FORMS.index(form))
+    h, w = 11, 13  # odd sizes: partial bytes at low depths, short Adam7 passes
+    kw = {}
+    if form.startswith("rgb16"):
+        s, ct, dp = rng.integers(0, 65536, (h, w, 3)), 2, 16
+        if form.endswith("key"):
+            s[3, 4] = (1000, 2000, 3000)
+            kw["trns"] = struct.pack(">HHH", 1000, 2000, 3000)
+    elif form.startswith("rgba16"):
+        s, ct, dp = rng.integers(0, 65536, (h, w, 4)), 6, 16
+    elif form.startswith("rgba8"):
+        s, ct, dp = rng.integers(0, 256, (h, w, 4)), 6, 8
+    elif form == "gray_alpha16":
+        s, ct, dp = rng.integers(0, 65536, (h, w, 2)), 4, 16
+    elif form.startswith("gray") and not form.startswith("gray_"):
+        dp = int("".join(c for c in form.split("_")[0] if c.isdigit()))
+        s, ct = rng.integers(0, 2 ** dp, (h, w, 1)), 0
+        if form.endswith("key"):
+            kw["trns"] = struct.pack(">H", int(s[2, 2, 0]))
+    elif form.startswith("palette"):
+        dp = int("".join(c for c in form.split("_")[0] if c.isdigit()))
+        n = min(2 ** dp, 200)
+        s, ct = rng.integers(0, n, (h, w, 1)), 3
+        kw["palette"] = rng.integers(0, 256, (n, 3))
+        if "trns" in form:
+            kw["trns"] = bytes(rng.integers(0, 256, n // 2).tolist())
+    else:
+        s, ct, dp = rng.integers(0, 256, (h, w, 3)), 2, 8
+        s[5, 6] = (9, 8, 7)
+        kw["trns"] = struct.pack(">HHH", 9, 8, 7)
+    (tmp_path / "albedo.png").write_bytes(_png_any(s, ct, dp, interlace="interlaced" in form, **kw))
+    obj = OBJ.replace("vn 0 1 0\n", "vn 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\n").replace("f 1//1 4//1 3//1 2//1", "f 1/1/1 4/4/1 3/3/1 2/2/1")
+    path = _write_scene(tmp_path, obj=obj, mtl=MTL.replace("newmtl Floor\n", "newmtl Floor\nmap_Kd albedo.png\n"))
+    rs = ref(path)
+    sd = load(path)
+    ia = _view(rs.scene["images"], S.IMAGE)
+    assert tuple(ia[1]["isize"]) == (w, h) and int(ia[1]["format"]) == 2, "the reference decoded the file (not its 1 x 1 placeholder)"
+    problems = compare_scenes(rs, sd)
+    assert not problems, problems
+    rs.close()
