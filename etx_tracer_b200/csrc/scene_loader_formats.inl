@@ -490,14 +490,27 @@ Pixels read_pfm(const std::string& path) {
   return out;
 }
 
+#include "scene_loader_jpeg.inl"
+
+// ImagePool::load_data (image_pool.cxx:271-383): the extension (compared as written) picks OpenEXR / Radiance HDR / PFM; every other file goes to
+// stb_image there, which looks at the content
 Pixels read_image(const std::string& path) {
   size_t dot_at = path.find_last_of('.');
-  std::string ext = dot_at == std::string::npos ? std::string("") : lower(path.substr(dot_at));
-  if (ext == ".png") return read_png(path);
+  std::string ext = dot_at == std::string::npos ? std::string("") : path.substr(dot_at);
   if (ext == ".exr") return read_exr(path);
   if (ext == ".hdr") return read_hdr(path);
   if (ext == ".pfm") return read_pfm(path);
-  fail(path + ": image files of type `" + ext + "` are not read (PNG, OpenEXR, Radiance HDR and PFM are)");
+  uint8_t head[8] = {};
+  if (FILE* f = fopen(path.c_str(), "rb")) {
+    size_t got = fread(head, 1, sizeof(head), f);
+    (void)got;
+    fclose(f);
+  } else {
+    fail("cannot open " + path);
+  }
+  if (memcmp(head, "\x89PNG\r\n\x1a\n", 8) == 0) return read_png(path);
+  if (head[0] == 0xff && head[1] == 0xd8) return read_jpeg(path);
+  fail(path + ": this image format is not read (PNG, JPEG, OpenEXR, Radiance HDR and PFM are)");
 }
 
 // ---- JSON (what a scene description needs: objects, arrays, strings, numbers, booleans) ----------------------------------------------------------------------

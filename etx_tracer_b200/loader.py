@@ -462,7 +462,12 @@ def read_image(path):
         return _read_hdr(path), False
     if ext == ".pfm":
         return _read_pfm(path), False
-    raise LoaderError(f"{path}: image files of type {ext} are not read (PNG, OpenEXR, Radiance HDR and PFM are)")
+    # every other file goes to stb_image in the reference, which looks at the content: JPEG (and PNG under another name) through the module's readers
+    from . import api
+    try:
+        return api.read_image(path), True
+    except api.EtxbError as e:
+        raise LoaderError(str(e))
 
 
 # ---- the loader -----------------------------------------------------------------------------------------------------------------------------

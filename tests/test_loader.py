@@ -1233,3 +1233,38 @@ def test_every_png_form_decodes_like_the_reference(ref, tmp_path, form, load):
     problems = compare_scenes(rs, sd)
     assert not problems, problems
     rs.close()
+
+
+JPEG_FORMS = ["baseline_444", "baseline_420_odd", "progressive_422", "progressive_420_q20", "grey", "grey_progressive", "restart_optimized", "adobe_rgb", "tiny"]
+
+
+@pytest.mark.parametrize("form", JPEG_FORMS)
+def test_jpeg_textures_decode_like_the_reference(ref, tmp_path, form, load):
+    """.jpg textures: the reference decodes them with stb_image; the module's JPEG reader (csrc/scene_loader_jpeg.inl) restates that decoder's inverse DCT,
+    chroma upsampling and colour conversion, so the RGBA8 texels are the same bytes — baseline and progressive, 4:4:4 / 4:2:2 / 4:2:0, grey, restart intervals
+    with optimised Huffman tables, an RGB (Adobe transform 0) file, odd sizes.  140 further files were compared while developing."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(JPEG_FORMS.index(form))
+    h, w = (9, 11) if form == "tiny" else ((33, 47) if "odd" in form else (40, 56))
+    y, x = np.mgrid[0:h, 0:w]
+    a = (np.stack([(x * 5 + y * 3) % 256, (x * 2 + y * 7) % 256, (x * y) % 256], -1) + rng.integers(0, 60, (h, w, 3))).clip(0, 255).astype(np.uint8)
+    file = tmp_path / "albedo.jpg"
+    if form.startswith("grey"):
+        Image.fromarray(a[..., 0]).save(file, "JPEG", quality=80, progressive="progressive" in form)
+    elif form == "restart_optimized":
+        cv2 = pytest.importorskip("cv2")
+        cv2.imwrite(str(file), a, [cv2.IMWRITE_JPEG_QUALITY, 80, cv2.IMWRITE_JPEG_RST_INTERVAL, 3, cv2.IMWRITE_JPEG_OPTIMIZE, 1])
+    elif form == "adobe_rgb":
+        Image.fromarray(a).save(file, "JPEG", quality=85, keep_rgb=True)
+    else:
+        sub = {"444": 0, "422": 1, "420": 2}[[t for t in form.split("_") if t in ("444", "422", "420")][0]] if form != "tiny" else 2
+        Image.fromarray(a).save(file, "JPEG", quality=20 if "q20" in form else 88, subsampling=sub, progressive="progressive" in form)
+    obj = OBJ.replace("vn 0 1 0\n", "vn 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\n").replace("f 1//1 4//1 3//1 2//1", "f 1/1/1 4/4/1 3/3/1 2/2/1")
+    path = _write_scene(tmp_path, obj=obj, mtl=MTL.replace("newmtl Floor\n", "newmtl Floor\nmap_Kd albedo.jpg\n"))
+    rs = ref(path)
+    sd = load(path)
+    ia = _view(rs.scene["images"], S.IMAGE)
+    assert tuple(ia[1]["isize"]) == (w, h) and int(ia[1]["format"]) == 2, "the reference decoded the file (not its 1 x 1 placeholder)"
+    problems = compare_scenes(rs, sd)
+    assert not problems, problems
+    rs.close()
