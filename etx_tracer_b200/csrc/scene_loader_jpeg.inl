@@ -230,10 +230,12 @@ struct Decoder {
   }
 
   // one 1-D pass of the inverse DCT in 12-bit fixed point (the classic factorisation with four rotations); outputs scaled by 4096
-  static inline int fx(double v) { return int(v * 4096 + 0.5); }
-  static void idct_1d(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7, int& x0, int& x1, int& x2, int& x3, int& t0, int& t1, int& t2, int& t3) {
-    int p2 = s2, p3 = s6;
-    int p1 = (p2 + p3) * fx(0.5411961f);
+  // (64-bit intermediates: identical to 32-bit arithmetic on every decodable file, and defined on corrupt ones)
+  using Wide = int64_t;
+  static inline Wide fx(double v) { return Wide(v * 4096 + 0.5); }
+  static void idct_1d(Wide s0, Wide s1, Wide s2, Wide s3, Wide s4, Wide s5, Wide s6, Wide s7, Wide& x0, Wide& x1, Wide& x2, Wide& x3, Wide& t0, Wide& t1, Wide& t2, Wide& t3) {
+    Wide p2 = s2, p3 = s6;
+    Wide p1 = (p2 + p3) * fx(0.5411961f);
     t2 = p1 + p3 * fx(-1.847759065f);
     t3 = p1 + p2 * fx(0.765366865f);
     p2 = s0, p3 = s4;
@@ -242,24 +244,24 @@ struct Decoder {
     x0 = t0 + t3, x3 = t0 - t3, x1 = t1 + t2, x2 = t1 - t2;
     t0 = s7, t1 = s5, t2 = s3, t3 = s1;
     p3 = t0 + t2;
-    int p4 = t1 + t3;
+    Wide p4 = t1 + t3;
     p1 = t0 + t3, p2 = t1 + t2;
-    int p5 = (p3 + p4) * fx(1.175875602f);
+    Wide p5 = (p3 + p4) * fx(1.175875602f);
     t0 = t0 * fx(0.298631336f), t1 = t1 * fx(2.053119869f), t2 = t2 * fx(3.072711026f), t3 = t3 * fx(1.501321110f);
     p1 = p5 + p1 * fx(-0.899976223f), p2 = p5 + p2 * fx(-2.562915447f);
     p3 = p3 * fx(-1.961570560f), p4 = p4 * fx(-0.390180644f);
     t3 += p1 + p4, t2 += p2 + p3, t1 += p2 + p4, t0 += p1 + p3;
   }
-  static uint8_t clamp8(int v) { return uint8_t(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+  static uint8_t clamp8(Wide v) { return uint8_t(v < 0 ? 0 : (v > 255 ? 255 : v)); }
   static void idct(uint8_t* out, int stride, const int16_t* d) {
-    int val[64];
+    Wide val[64];
     for (int i = 0; i < 8; ++i) {  // columns; two extra bits are kept
       if (d[i + 8] == 0 && d[i + 16] == 0 && d[i + 24] == 0 && d[i + 32] == 0 && d[i + 40] == 0 && d[i + 48] == 0 && d[i + 56] == 0) {
-        const int dc_term = d[i] * 4;
+        const Wide dc_term = Wide(d[i]) * 4;
         for (int r = 0; r < 8; ++r) val[i + r * 8] = dc_term;
         continue;
       }
-      int x0, x1, x2, x3, t0, t1, t2, t3;
+      Wide x0, x1, x2, x3, t0, t1, t2, t3;
       idct_1d(d[i], d[i + 8], d[i + 16], d[i + 24], d[i + 32], d[i + 40], d[i + 48], d[i + 56], x0, x1, x2, x3, t0, t1, t2, t3);
       x0 += 512, x1 += 512, x2 += 512, x3 += 512;
       val[i] = (x0 + t3) >> 10, val[i + 56] = (x0 - t3) >> 10;
@@ -268,11 +270,11 @@ struct Decoder {
       val[i + 24] = (x3 + t0) >> 10, val[i + 32] = (x3 - t0) >> 10;
     }
     for (int i = 0; i < 8; ++i) {  // rows; 17 bits to drop, + 128 for the level shift
-      const int* v = val + i * 8;
+      const Wide* v = val + i * 8;
       uint8_t* o = out + size_t(i) * stride;
-      int x0, x1, x2, x3, t0, t1, t2, t3;
+      Wide x0, x1, x2, x3, t0, t1, t2, t3;
       idct_1d(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], x0, x1, x2, x3, t0, t1, t2, t3);
-      const int bias = 65536 + (128 << 17);
+      const Wide bias = 65536 + (128 << 17);
       x0 += bias, x1 += bias, x2 += bias, x3 += bias;
       o[0] = clamp8((x0 + t3) >> 17), o[7] = clamp8((x0 - t3) >> 17);
       o[1] = clamp8((x1 + t2) >> 17), o[6] = clamp8((x1 - t2) >> 17);
