@@ -492,6 +492,125 @@ Pixels read_pfm(const std::string& path) {
 
 #include "scene_loader_jpeg.inl"
 
+// Truevision TGA the way stb_image reads it (stb_image.hxx:5654-5990; it is the last format tried there, recognised by a consistent header): true colour
+// 15 / 16 / 24 / 32 bits, grey 8 / 16 bits, colour-mapped with 8- or 16-bit indices, raw or run-length encoded, either row order.  15 / 16-bit colour is
+// x555 with channels scaled by 255 / 31 (the top bit is not an alpha), 16-bit grey is grey + alpha (which the reference's pool then zero-fills).
+bool looks_like_tga(const uint8_t* h, size_t n) {
+  if (n < 18 || h[1] > 1) return false;
+  const int type = h[2], bpp = h[16];
+  if (h[1] == 1) {
+    if (type != 1 && type != 9) return false;
+    const int pal_bits = h[7];
+    if (pal_bits != 8 && pal_bits != 15 && pal_bits != 16 && pal_bits != 24 && pal_bits != 32) return false;
+  } else if (type != 2 && type != 3 && type != 10 && type != 11) {
+    return false;
+  }
+  if ((h[12] | (h[13] << 8)) < 1 || (h[14] | (h[15] << 8)) < 1) return false;
+  if (h[1] == 1 && bpp != 8 && bpp != 16) return false;
+  return bpp == 8 || bpp == 15 || bpp == 16 || bpp == 24 || bpp == 32;
+}
+
+Pixels read_tga(const std::string& path) {
+  const std::string d = read_file(path);
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(d.data());
+  if (!looks_like_tga(b, d.size())) fail(path + ": not a TGA file");
+  size_t pos = 18;
+  auto get8 = [&]() -> int { return pos < d.size() ? b[pos++] : 0; };
+  auto get16 = [&]() -> int {
+    int lo = get8();
+    return lo | (get8() << 8);
+  };
+  const int id_length = b[0], indexed = b[1], pal_start = b[3] | (b[4] << 8), pal_len = b[5] | (b[6] << 8), pal_bits = b[7];
+  const int w = b[12] | (b[13] << 8), h = b[14] | (b[15] << 8), bpp = b[16];
+  int type = b[2];
+  const bool rle = type >= 8;
+  if (rle) type -= 8;
+  const bool bottom_up = ((b[17] >> 5) & 1) == 0;
+  bool rgb16 = false;
+  auto channels_of = [&](int bits, bool grey) -> int {
+    switch (bits) {
+      case 8: return 1;
+      case 16:
+        if (grey) return 2;
+        [[fallthrough]];
+      case 15: rgb16 = true; return 3;
+      case 24: return 3;
+      case 32: return 4;
+      default: return 0;
+    }
+  };
+  const int comp = indexed ? channels_of(pal_bits, false) : channels_of(bpp, type == 3);
+  if (comp == 0) fail(path + ": unsupported TGA pixel format");
+  if (uint64_t(w) * h > uint64_t(d.size()) * 130u) fail(path + ": TGA header does not match the file size");  // a run packet covers <= 128 pixels
+  auto read_rgb16 = [&](uint8_t* out) {
+    const int px = get16();
+    out[0] = uint8_t((((px >> 10) & 31) * 255) / 31), out[1] = uint8_t((((px >> 5) & 31) * 255) / 31), out[2] = uint8_t(((px & 31) * 255) / 31);
+  };
+  pos += size_t(id_length);
+  std::vector<uint8_t> palette;
+  if (indexed) {
+    if (pal_len == 0) fail(path + ": TGA colour map without entries");
+    pos += size_t(pal_start);
+    palette.assign(size_t(pal_len) * comp, 0);
+    for (int i = 0; i < pal_len; ++i) {
+      if (rgb16) {
+        read_rgb16(&palette[size_t(i) * comp]);
+      } else {
+        for (int j = 0; j < comp; ++j) palette[size_t(i) * comp + j] = uint8_t(get8());
+      }
+    }
+  }
+  std::vector<uint8_t> px(size_t(w) * h * comp, 0);
+  uint8_t raw[4] = {0, 0, 0, 0};
+  int run = 0;
+  bool repeating = false;
+  for (size_t i = 0; i < size_t(w) * h; ++i) {
+    bool read = true;
+    if (rle) {
+      if (run == 0) {
+        const int cmd = get8();
+        run = 1 + (cmd & 127);
+        repeating = (cmd >> 7) != 0;
+      } else if (repeating) {
+        read = false;
+      }
+    }
+    if (read) {
+      if (indexed) {
+        int index = (bpp == 8) ? get8() : get16();
+        if (index >= pal_len) index = 0;
+        memcpy(raw, &palette[size_t(index) * comp], size_t(comp));
+      } else if (rgb16) {
+        read_rgb16(raw);
+      } else {
+        for (int j = 0; j < comp; ++j) raw[j] = uint8_t(get8());
+      }
+    }
+    memcpy(&px[i * comp], raw, size_t(comp));
+    --run;
+  }
+  Pixels out;
+  out.w = uint32_t(w), out.h = uint32_t(h), out.eight_bit = true;
+  out.u8.assign(size_t(w) * h * 4, 255);
+  for (int y = 0; y < h; ++y) {
+    const uint8_t* row = &px[size_t(bottom_up ? h - 1 - y : y) * w * comp];
+    uint8_t* o = &out.u8[size_t(y) * w * 4];
+    for (int x = 0; x < w; ++x, o += 4, row += comp) {
+      if (comp == 1) {
+        o[0] = o[1] = o[2] = row[0];
+      } else if (comp == 2) {
+        o[0] = o[1] = o[2] = o[3] = 0;  // grey + alpha: no case in the reference's switch over the channel count (image_pool.cxx:353-381)
+      } else if (rgb16) {
+        o[0] = row[0], o[1] = row[1], o[2] = row[2];
+      } else {
+        o[0] = row[2], o[1] = row[1], o[2] = row[0];  // stored blue first
+        if (comp == 4) o[3] = row[3];
+      }
+    }
+  }
+  return out;
+}
+
 // ImagePool::load_data (image_pool.cxx:271-383): the extension (compared as written) picks OpenEXR / Radiance HDR / PFM; every other file goes to
 // stb_image there, which looks at the content
 Pixels read_image(const std::string& path) {
@@ -510,7 +629,16 @@ Pixels read_image(const std::string& path) {
   }
   if (memcmp(head, "\x89PNG\r\n\x1a\n", 8) == 0) return read_png(path);
   if (head[0] == 0xff && head[1] == 0xd8) return read_jpeg(path);
-  fail(path + ": this image format is not read (PNG, JPEG, OpenEXR, Radiance HDR and PFM are)");
+  if (memcmp(head, "BM", 2) != 0 && memcmp(head, "GIF8", 4) != 0 && memcmp(head, "8BPS", 4) != 0 && memcmp(head, "#?RADIANCE", 8) != 0) {
+    uint8_t header[18] = {};
+    size_t got = 0;
+    if (FILE* f = fopen(path.c_str(), "rb")) {
+      got = fread(header, 1, sizeof(header), f);
+      fclose(f);
+    }
+    if (looks_like_tga(header, got)) return read_tga(path);
+  }
+  fail(path + ": this image format is not read (PNG, JPEG, TGA, OpenEXR, Radiance HDR and PFM are)");
 }
 
 // ---- JSON (what a scene description needs: objects, arrays, strings, numbers, booleans) ----------------------------------------------------------------------

@@ -1268,3 +1268,39 @@ def test_jpeg_textures_decode_like_the_reference(ref, tmp_path, form, load):
     problems = compare_scenes(rs, sd)
     assert not problems, problems
     rs.close()
+
+
+TGA_FORMS = ["rgb", "rgba_rle", "grey_top_down", "palette_rle", "rgb16", "grey16"]
+
+
+@pytest.mark.parametrize("form", TGA_FORMS)
+def test_tga_textures_decode_like_the_reference(ref, tmp_path, form, load):
+    """.tga textures the way stb_image reads them: true colour (blue first) and grey, raw and run-length encoded, bottom-up and top-down, colour-mapped, x555
+    16-bit colour scaled by 255 / 31, and 16-bit grey + alpha (zero-filled by the reference's texture pool like every two-channel image)."""
+    import struct
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(TGA_FORMS.index(form))
+    h, w = 7, 9
+    a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    a[:, 3:6] = a[:, 3:4]
+    file = str(tmp_path / "albedo.tga")
+    if form == "rgb":
+        Image.fromarray(a[..., :3]).save(file)
+    elif form == "rgba_rle":
+        Image.fromarray(a).save(file, compression="tga_rle")
+    elif form == "grey_top_down":
+        Image.fromarray(a[..., 0]).save(file, orientation=1)
+    elif form == "palette_rle":
+        Image.fromarray(a[..., :3]).quantize(16).save(file, compression="tga_rle")
+    else:
+        body = rng.integers(0, 65536, h * w, dtype=np.uint16).tobytes()
+        open(file, "wb").write(struct.pack("<BBBHHBHHHHBB", 0, 0, 2 if form == "rgb16" else 3, 0, 0, 0, 0, 0, w, h, 16, 0) + body)
+    obj = OBJ.replace("vn 0 1 0\n", "vn 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\n").replace("f 1//1 4//1 3//1 2//1", "f 1/1/1 4/4/1 3/3/1 2/2/1")
+    path = _write_scene(tmp_path, obj=obj, mtl=MTL.replace("newmtl Floor\n", "newmtl Floor\nmap_Kd albedo.tga\n"))
+    rs = ref(path)
+    sd = load(path)
+    ia = _view(rs.scene["images"], S.IMAGE)
+    assert tuple(ia[1]["isize"]) == (w, h) and int(ia[1]["format"]) == 2, "the reference decoded the file (not its 1 x 1 placeholder)"
+    problems = compare_scenes(rs, sd)
+    assert not problems, problems
+    rs.close()
