@@ -745,6 +745,40 @@ struct MtlBlock {
   }
 };
 
+// ParseTextureNameAndOption (tiny_obj_loader.hxx:1242-1321): the `-option args` of a texture statement are skipped by their argument COUNT (whatever the
+// words are), the first word that is not an option starts the file name, which runs to the end of the line — spaces included
+bool texture_name(const std::string& text, std::string& name) {
+  static const struct {
+    const char* key;
+    int args;
+  } options[] = {{"-blendu", 1}, {"-blendv", 1}, {"-clamp", 1}, {"-boost", 1}, {"-bm", 1}, {"-o", 3}, {"-s", 3}, {"-t", 3}, {"-type", 1}, {"-texres", 1}, {"-imfchan", 1}, {"-mm", 2},
+                 {"-colorspace", 1}};
+  size_t at = 0;
+  const auto blank = [&](size_t i) { return i >= text.size() || text[i] == ' ' || text[i] == '\t'; };
+  while (at < text.size()) {
+    while (at < text.size() && (text[at] == ' ' || text[at] == '\t')) ++at;
+    if (at >= text.size()) break;
+    bool option = false;
+    for (const auto& o : options) {
+      const size_t n = strlen(o.key);
+      if (lower(text.substr(at, n)) == o.key && at + n < text.size() && blank(at + n)) {
+        at += n;
+        for (int a = 0; a < o.args; ++a) {
+          while (at < text.size() && (text[at] == ' ' || text[at] == '\t')) ++at;
+          while (at < text.size() && text[at] != ' ' && text[at] != '\t' && text[at] != '\r') ++at;
+        }
+        option = true;
+        break;
+      }
+    }
+    if (!option) {
+      name = text.substr(at);
+      return true;
+    }
+  }
+  return false;
+}
+
 std::vector<MtlBlock> parse_mtl(const std::string& path) {
   static const std::pair<const char*, const char*> textures[] = {{"map_ka", "ambient"}, {"map_kd", "diffuse"}, {"map_ks", "specular"}, {"map_kt", "transmittance"},
     {"map_ns", "specular_highlight"}, {"map_bump", "bump"}, {"map_d", "alpha"}, {"disp", "displacement"}, {"refl", "reflection"}, {"map_pr", "roughness"}, {"map_pm", "metallic"},
@@ -778,8 +812,8 @@ std::vector<MtlBlock> parse_mtl(const std::string& path) {
       for (const auto& t : textures) {
         size_t n = strlen(t.first);
         if (!low.compare(0, n, t.first) && separated(n)) {
-          auto tok = split(line.substr(n + 1));
-          blocks.back().textures[t.second] = tok.empty() ? std::string("") : tok.back();
+          std::string name;
+          if (texture_name(line.substr(n + 1), name)) blocks.back().textures[t.second] = name;  // without a name the earlier value stays
           consumed = true;
           break;
         }

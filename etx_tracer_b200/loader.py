@@ -60,6 +60,33 @@ class MtlBlock:
         return None
 
 
+_TEXTURE_OPTIONS = {"-blendu": 1, "-blendv": 1, "-clamp": 1, "-boost": 1, "-bm": 1, "-o": 3, "-s": 3, "-t": 3, "-type": 1, "-texres": 1, "-imfchan": 1, "-mm": 2, "-colorspace": 1}
+
+
+def _texture_name(text):
+    """ParseTextureNameAndOption (tiny_obj_loader.hxx:1242-1321): `-option args` are skipped by their argument COUNT, the first word that is not an option
+    starts the file name, which runs to the end of the line — spaces included."""
+    at, n = 0, len(text)
+    while at < n:
+        while at < n and text[at] in " \t":
+            at += 1
+        if at >= n:
+            break
+        for key, args in _TEXTURE_OPTIONS.items():
+            k = len(key)
+            if text[at:at + k].lower() == key and at + k < n and text[at + k] in " \t":
+                at += k
+                for _ in range(args):
+                    while at < n and text[at] in " \t":
+                        at += 1
+                    while at < n and text[at] not in " \t\r":
+                        at += 1
+                break
+        else:
+            return text[at:]
+    return None
+
+
 def parse_mtl(path):
     blocks, cur = [], None
     with open(path, "r", errors="replace") as f:
@@ -78,7 +105,9 @@ def parse_mtl(path):
             consumed = False
             for key, slot in _TINYOBJ_TEXTURES.items():
                 if low.startswith(key) and len(line) > len(key) and line[len(key)] in " \t":
-                    cur.textures[slot] = line[len(key) + 1:].split()[-1] if line[len(key) + 1:].split() else ""
+                    name = _texture_name(line[len(key) + 1:])
+                    if name is not None:  # without a name the earlier value stays
+                        cur.textures[slot] = name
                     consumed = True
                     break
             if consumed:

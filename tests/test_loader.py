@@ -1004,7 +1004,11 @@ def _random_material_file(rng):
         if rng.random() < 0.15: o.append("normalmap scale " + num())
         if rng.random() < 0.2: o.append("map_Ml tex.png" + rng.choice(["", " channel 2", " channel -3", "  channel 1"]))
         if rng.random() < 0.2: o.append("map_Tm " + rng.choice(["tex.png channel 1", "missing.png", "tex.png"]))
-        if rng.random() < 0.2: o.append("map_Kd tex.png")
+        if rng.random() < 0.4:
+            o.append(rng.choice(["map_Kd", "map_Ks", "map_Ke", "map_Kt", "map_kd", "MAP_KD", "map_Ka", "map_Bump", "bump", "map_d", "disp", "norm", "refl -type sphere"]) + " " +
+                     rng.choice(["tex.png", "-s 1 1 1 tex.png", "-bm 0.5 tex.png", "-clamp on tex.png", "-o 0.1 0.2 tex.png -mm 0 1", "tex.png tex.png", "my tex.png", "-blendu off -blendv on tex.png",
+                                 "  tex.png", "-imfchan r tex.png", "-texres 512 tex.png", "-boost 2 tex.png", "-colorspace linear tex.png"]))
+        if rng.random() < 0.3: o.append(rng.choice(["Ns 10", "Ni 1.45", "d 0.5", "Tr 0.2", "illum 2", "Ka 0.1 0.1 0.1", "Tf 1 1 1", "Pm 0.5", "Ps 0.1", "Pc 0.2", "Pcr 0.3", "aniso 0.1", "anisor 0.2", "Ke", "Kd", "d"]))
         if rng.random() < 0.1: o.append("map_Pr tex.png channel 1")
         rng.shuffle(o)
         return "\n".join(["newmtl " + name] + o) + "\n"
