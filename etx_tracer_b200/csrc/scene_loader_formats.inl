@@ -326,7 +326,7 @@ Pixels read_exr(const std::string& path) {
   if (!attrs.count("compression") || !attrs.count("dataWindow") || !attrs.count("channels")) fail(path + ": incomplete EXR header");
   if (attrs["compression"].empty() || attrs["dataWindow"].size() < 16) fail(path + ": incomplete EXR header");
   int comp = uint8_t(attrs["compression"][0]);
-  if (comp != 0 && comp != 2 && comp != 3) fail(path + ": this EXR compression is not read (none / ZIPS / ZIP are)");
+  if (comp != 0 && comp != 1 && comp != 2 && comp != 3) fail(path + ": this EXR compression is not read (none / RLE / ZIPS / ZIP are)");
   int32_t win[4];
   memcpy(win, attrs["dataWindow"].data(), 16);
   const uint32_t w = uint32_t(win[2] - win[0] + 1), h = uint32_t(win[3] - win[1] + 1);
@@ -364,7 +364,24 @@ Pixels read_exr(const std::string& path) {
     std::vector<uint8_t> raw;
     if (size > d.size() - size_t(off) - 8) fail(path + ": truncated EXR block");
     if (comp != 0 && size < want) {
-      std::vector<uint8_t> z = inflate_zlib(b + off + 8, size);
+      std::vector<uint8_t> z;
+      if (comp == 1) {  // run lengths: a negative count copies that many bytes, any other repeats the next byte count + 1 times
+        const uint8_t* in = b + off + 8;
+        for (size_t i = 0; i < size;) {
+          const int count = int8_t(in[i++]);
+          if (count < 0) {
+            if (i + size_t(-count) > size) fail(path + ": corrupt EXR run");
+            z.insert(z.end(), in + i, in + i + size_t(-count));
+            i += size_t(-count);
+          } else {
+            if (i >= size) fail(path + ": corrupt EXR run");
+            z.insert(z.end(), size_t(count) + 1, in[i++]);
+          }
+          if (z.size() > want) fail(path + ": corrupt EXR run");
+        }
+      } else {
+        z = inflate_zlib(b + off + 8, size);
+      }
       for (size_t i = 1; i < z.size(); ++i) z[i] = uint8_t(z[i - 1] + z[i] - 128);  // predictor
       raw.resize(z.size());
       const size_t half = (z.size() + 1) / 2;

@@ -368,7 +368,7 @@ def _read_exr(path):
     pos += 1
     comp = attrs["compression"][0]
     if comp not in (0, 2, 3):
-        raise LoaderError(f"{path}: EXR compression {comp} is not read (none / ZIPS / ZIP are)")
+        raise LoaderError(f"{path}: EXR compression {comp} is not read here (none / ZIPS / ZIP are)")
     x0, y0, x1, y1 = struct.unpack("<iiii", attrs["dataWindow"])
     w, h = x1 - x0 + 1, y1 - y0 + 1
     names, types, cp, ch = [], [], 0, attrs["channels"]
@@ -486,7 +486,14 @@ def read_image(path):
             except api.EtxbError as e:
                 raise LoaderError(str(e))
     if ext == ".exr":
-        return _read_exr(path), False
+        try:
+            return _read_exr(path), False
+        except LoaderError:
+            from . import api  # run-length encoded blocks: the module's reader
+            try:
+                return api.read_image(path), False
+            except api.EtxbError as e:
+                raise LoaderError(str(e))
     if ext == ".hdr":
         return _read_hdr(path), False
     if ext == ".pfm":

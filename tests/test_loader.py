@@ -608,7 +608,24 @@ def _exr_bytes(img, comp, types):
     header = struct.pack("<II", 20000630, 2) + attr("channels", "chlist", chan) + attr("compression", "compression", bytes([comp])) + attr("dataWindow", "box2i", box) + \
         attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", b"\0") + attr("pixelAspectRatio", "float", struct.pack("<f", 1.0)) + \
         attr("screenWindowCenter", "v2f", struct.pack("<ff", 0.0, 0.0)) + attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + b"\0"
-    lines = {0: 1, 2: 1, 3: 16}[comp]
+    lines = {0: 1, 1: 1, 2: 1, 3: 16}[comp]
+
+    def run_lengths(data):
+        out, i, n = bytearray(), 0, len(data)
+        while i < n:
+            j = i
+            while j + 1 < n and data[j + 1] == data[i] and j - i < 126:
+                j += 1
+            if j - i >= 2:
+                out += bytes([j - i, data[i]])
+                i = j + 1
+            else:
+                k = i
+                while k < n and k - i < 127 and not (k + 2 < n and data[k] == data[k + 1] == data[k + 2]):
+                    k += 1
+                out += bytes([(256 - (k - i)) & 255]) + bytes(data[i:k])
+                i = k
+        return bytes(out)
     blocks = []
     for y0 in range(0, h, lines):
         body = b""
@@ -621,7 +638,7 @@ def _exr_bytes(img, comp, types):
             re = np.concatenate([b[0::2], b[1::2]]).astype(np.int32)
             d = re.copy()
             d[1:] = (re[1:] - re[:-1] + 128 + 256) & 255
-            packed = zlib.compress(d.astype(np.uint8).tobytes(), 6)
+            packed = run_lengths(d.astype(np.uint8).tobytes()) if comp == 1 else zlib.compress(d.astype(np.uint8).tobytes(), 6)
             if len(packed) < len(body):
                 body = packed
         blocks.append(struct.pack("<iI", y0, len(body)) + body)
@@ -669,7 +686,7 @@ def test_compressed_png_files_decode_like_the_reference(ref, tmp_path, load, cas
     rs.close()
 
 
-@pytest.mark.parametrize("comp,half", [(2, False), (3, False), (3, True), (0, True)])
+@pytest.mark.parametrize("comp,half", [(2, False), (3, False), (3, True), (0, True), (1, True), (1, False)])
 def test_compressed_exr_files_decode_like_the_reference(ref, tmp_path, load, comp, half):
     """OpenEXR scan-line files with ZIPS / ZIP blocks (the predictor + byte interleave around a zlib stream) and half-float channels, through the
     module's own reader, the Python twin and the reference (tinyexr): the same float pixels and the same importance-sampling table."""
