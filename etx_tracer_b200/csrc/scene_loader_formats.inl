@@ -628,6 +628,164 @@ Pixels read_tga(const std::string& path) {
   return out;
 }
 
+// Windows BMP the way stb_image reads it (stb_image.hxx:5324-5650): header sizes 12 / 40 / 56 / 108 / 124; 1 / 4 / 8 bits with a palette, 16 / 32 bits through
+// channel masks (x555 and 8888 by default, BI_BITFIELDS otherwise; a channel of n bits is widened to 8 by bit replication), 24 bits; bottom-up or top-down rows;
+// run-length and embedded JPEG / PNG variants are rejected there too.  A 32-bit file whose alpha bytes are all zero is opaque.
+Pixels read_bmp(const std::string& path) {
+  const std::string d = read_file(path);
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(d.data());
+  size_t pos = 0;
+  auto get8 = [&]() -> uint32_t { return pos < d.size() ? b[pos++] : 0u; };
+  auto get16 = [&]() -> uint32_t {
+    uint32_t lo = get8();
+    return lo | (get8() << 8);
+  };
+  auto get32 = [&]() -> uint32_t {
+    uint32_t lo = get16();
+    return lo | (get16() << 16);
+  };
+  if (get8() != 'B' || get8() != 'M') fail(path + ": not a BMP file");
+  get32(), get16(), get16();
+  const int64_t offset = int32_t(get32());
+  const uint32_t hsz = get32();
+  if (offset < 0 || (hsz != 12 && hsz != 40 && hsz != 56 && hsz != 108 && hsz != 124)) fail(path + ": unsupported BMP header");
+  int64_t width, height;
+  if (hsz == 12) {
+    width = get16(), height = get16();
+  } else {
+    width = int32_t(get32()), height = int32_t(get32());
+  }
+  if (get16() != 1) fail(path + ": bad BMP");
+  const uint32_t bpp = get16();
+  uint32_t mr = 0, mg = 0, mb = 0, ma = 0, all_a = 255, extra = 14;
+  auto default_masks = [&]() {
+    if (bpp == 16) {
+      mr = 31u << 10, mg = 31u << 5, mb = 31u;
+    } else if (bpp == 32) {
+      mr = 0xffu << 16, mg = 0xffu << 8, mb = 0xffu, ma = 0xffu << 24;
+      all_a = 0;
+    } else {
+      mr = mg = mb = ma = 0;
+    }
+  };
+  if (hsz != 12) {
+    const uint32_t compress = get32();
+    if (compress == 1 || compress == 2 || compress >= 4) fail(path + ": this BMP compression is not read");
+    if (compress == 3 && bpp != 16 && bpp != 32) fail(path + ": bad BMP");
+    get32(), get32(), get32(), get32(), get32();
+    if (hsz == 40 || hsz == 56) {
+      if (hsz == 56) get32(), get32(), get32(), get32();
+      if (bpp == 16 || bpp == 32) {
+        if (compress == 0) {
+          default_masks();
+        } else {
+          mr = get32(), mg = get32(), mb = get32();
+          extra += 12;
+          if (mr == mg && mg == mb) fail(path + ": bad BMP masks");
+        }
+      }
+    } else {
+      mr = get32(), mg = get32(), mb = get32(), ma = get32();
+      if (compress != 3) default_masks();
+      for (int i = 0; i < 13; ++i) get32();
+      if (hsz == 124) get32(), get32(), get32(), get32();
+    }
+  }
+  const bool bottom_up = height > 0;
+  if (height < 0) height = -height;
+  if (width <= 0 || height <= 0 || width > (1 << 24) || height > (1 << 24) || uint64_t(width) * uint64_t(height) > uint64_t(d.size()) * 8u) fail(path + ": BMP header does not match the file size");
+  int64_t psize = 0;
+  if (hsz == 12) {
+    if (bpp < 24) psize = (offset - int64_t(extra) - 24) / 3;
+  } else if (bpp < 16) {
+    psize = (offset - int64_t(extra) - int64_t(hsz)) >> 2;
+  }
+  if (psize == 0 && uint64_t(offset) != pos) fail(path + ": bad BMP data offset");
+  const uint32_t channels = (bpp == 24 && ma == 0xff000000u) ? 3u : (ma ? 4u : 3u);
+  const size_t w = size_t(width), h = size_t(height);
+  std::vector<uint8_t> px(w * h * channels, 0);
+  size_t z = 0;
+  if (bpp < 16) {
+    if (psize <= 0 || psize > 256) fail(path + ": bad BMP palette");
+    uint8_t pal[256][3] = {};
+    for (int64_t i = 0; i < psize; ++i) {
+      pal[i][2] = uint8_t(get8()), pal[i][1] = uint8_t(get8()), pal[i][0] = uint8_t(get8());
+      if (hsz != 12) get8();
+    }
+    pos = std::min<size_t>(d.size(), pos + size_t(std::max<int64_t>(0, offset - int64_t(extra) - int64_t(hsz) - psize * (hsz == 12 ? 3 : 4))));
+    if (bpp != 1 && bpp != 4 && bpp != 8) fail(path + ": bad BMP bit depth");
+    const size_t row_bytes = (bpp == 1) ? (w + 7) >> 3 : ((bpp == 4) ? (w + 1) >> 1 : w), pad = (0 - row_bytes) & 3;
+    for (size_t j = 0; j < h; ++j) {
+      const size_t row_start = pos;
+      for (size_t i = 0; i < w; ++i) {
+        const size_t bit = i * bpp;
+        const uint32_t byte = (row_start + (bit >> 3) < d.size()) ? b[row_start + (bit >> 3)] : 0u;
+        uint32_t v = (byte >> (8 - bpp - (bit & 7))) & ((1u << bpp) - 1u);
+        px[z++] = pal[v][0], px[z++] = pal[v][1], px[z++] = pal[v][2];
+        if (channels == 4) px[z++] = 255;
+      }
+      pos = row_start + row_bytes + pad;
+    }
+  } else {
+    pos = std::min<size_t>(d.size(), pos + size_t(std::max<int64_t>(0, offset - int64_t(extra) - int64_t(hsz))));
+    const size_t row_bytes = (bpp == 24) ? 3 * w : ((bpp == 16) ? 2 * w : 0), pad = (0 - row_bytes) & 3;
+    int easy = 0;
+    if (bpp == 24) easy = 1;
+    if (bpp == 32 && mb == 0xffu && mg == 0xff00u && mr == 0x00ff0000u && ma == 0xff000000u) easy = 2;
+    auto high_bit = [](uint32_t v) {
+      int n = -1;
+      while (v) ++n, v >>= 1;
+      return n;
+    };
+    auto bit_count = [](uint32_t v) {
+      int n = 0;
+      while (v) n += int(v & 1u), v >>= 1;
+      return n;
+    };
+    int rs = 0, gs = 0, bs = 0, as = 0, rc = 0, gc = 0, bc = 0, ac = 0;
+    if (!easy) {
+      if (!mr || !mg || !mb) fail(path + ": bad BMP masks");
+      rs = high_bit(mr) - 7, rc = bit_count(mr), gs = high_bit(mg) - 7, gc = bit_count(mg), bs = high_bit(mb) - 7, bc = bit_count(mb), as = high_bit(ma) - 7, ac = bit_count(ma);
+      if (rc > 8 || gc > 8 || bc > 8 || ac > 8) fail(path + ": bad BMP masks");
+    }
+    auto widen = [](uint32_t v, int shift, int bits) -> uint32_t {  // a channel of `bits` bits to 8 bits by replication
+      static const uint32_t mul[9] = {0, 0xff, 0x55, 0x49, 0x11, 0x21, 0x41, 0x81, 0x01}, down[9] = {0, 0, 0, 1, 0, 2, 4, 6, 0};
+      v = (shift < 0) ? (v << -shift) : (v >> shift);
+      v >>= (8 - bits);
+      return (v * mul[bits]) >> down[bits];
+    };
+    for (size_t j = 0; j < h; ++j) {
+      for (size_t i = 0; i < w; ++i) {
+        uint32_t a;
+        if (easy) {
+          px[z + 2] = uint8_t(get8()), px[z + 1] = uint8_t(get8()), px[z + 0] = uint8_t(get8());
+          z += 3;
+          a = (easy == 2) ? get8() : 255u;
+        } else {
+          const uint32_t v = (bpp == 16) ? get16() : get32();
+          px[z++] = uint8_t(widen(v & mr, rs, rc)), px[z++] = uint8_t(widen(v & mg, gs, gc)), px[z++] = uint8_t(widen(v & mb, bs, bc));
+          a = ma ? widen(v & ma, as, ac) : 255u;
+        }
+        all_a |= a;
+        if (channels == 4) px[z++] = uint8_t(a);
+      }
+      pos = std::min(d.size(), pos + pad);
+    }
+  }
+  Pixels out;
+  out.w = uint32_t(w), out.h = uint32_t(h), out.eight_bit = true;
+  out.u8.assign(w * h * 4, 255);
+  for (size_t y = 0; y < h; ++y) {
+    const uint8_t* row = &px[(bottom_up ? h - 1 - y : y) * w * channels];
+    uint8_t* o = &out.u8[y * w * 4];
+    for (size_t x = 0; x < w; ++x, o += 4, row += channels) {
+      o[0] = row[0], o[1] = row[1], o[2] = row[2];
+      if (channels == 4) o[3] = (all_a == 0) ? 255 : row[3];
+    }
+  }
+  return out;
+}
+
 // ImagePool::load_data (image_pool.cxx:271-383): the extension (compared as written) picks OpenEXR / Radiance HDR / PFM; every other file goes to
 // stb_image there, which looks at the content
 Pixels read_image(const std::string& path) {
@@ -646,7 +804,8 @@ Pixels read_image(const std::string& path) {
   }
   if (memcmp(head, "\x89PNG\r\n\x1a\n", 8) == 0) return read_png(path);
   if (head[0] == 0xff && head[1] == 0xd8) return read_jpeg(path);
-  if (memcmp(head, "BM", 2) != 0 && memcmp(head, "GIF8", 4) != 0 && memcmp(head, "8BPS", 4) != 0 && memcmp(head, "#?RADIANCE", 8) != 0) {
+  if (memcmp(head, "BM", 2) == 0) return read_bmp(path);
+  if (memcmp(head, "GIF8", 4) != 0 && memcmp(head, "8BPS", 4) != 0 && memcmp(head, "#?RADIANCE", 8) != 0) {
     uint8_t header[18] = {};
     size_t got = 0;
     if (FILE* f = fopen(path.c_str(), "rb")) {
@@ -655,7 +814,7 @@ Pixels read_image(const std::string& path) {
     }
     if (looks_like_tga(header, got)) return read_tga(path);
   }
-  fail(path + ": this image format is not read (PNG, JPEG, TGA, OpenEXR, Radiance HDR and PFM are)");
+  fail(path + ": this image format is not read (PNG, JPEG, TGA, BMP, OpenEXR, Radiance HDR and PFM are)");
 }
 
 // ---- JSON (what a scene description needs: objects, arrays, strings, numbers, booleans) ----------------------------------------------------------------------

@@ -351,7 +351,7 @@ int etxb_tonemap_rgba8(const float* rgba, uint64_t pixel_count, float exposure, 
 
 /* ---- scene files: SceneRepresentation::load_from_file (render/host/scene_representation.cxx:679-838) ------------------
  * Reads the reference's `.json` + `.obj` + `.mtl` scene dialect (et::camera / et::medium / et::dir / et::env / et::spectrum blocks, the material
- * directives of parse_material :1682-2079, PNG / JPEG / TGA / EXR / HDR / PFM textures) into the Scene / Camera PODs etxb_create takes: host C++, no CUDA, no
+ * directives of parse_material :1682-2079, PNG / JPEG / TGA / BMP / EXR / HDR / PFM textures) into the Scene / Camera PODs etxb_create takes: host C++, no CUDA, no
  * third-party reader.  The object owns every array the PODs point into; keep it alive until etxb_create has returned (the module copies).
  * A file without an et::dir / et::env block gets the reference's default atmosphere (sun + sky images, generated here on the host threads).
  * `et::medium ... volume file.nvdb` becomes a heterogeneous medium with a dense grid (own NanoVDB 32.x reader, codecs none / ZIP; medium_pool.cxx:102-159).
@@ -375,7 +375,7 @@ int etxb_scene_file_commit(etxb_ctx* ctx, const etxb_scene_file* sf);
  * raytracer/app.cxx:88-105): copies it to `out` (NUL-terminated, truncated to out_bytes) and returns its length; 0 = id absent; < 0 = error. */
 int etxb_options_file_string(const char* file_name, const char* id, char* out, uint64_t out_bytes);
 /* The loader's image readers on their own — every PNG form stb_image decodes (bit depths 1-16, palette, colour keys, Adam7), baseline / progressive JPEG
- * (same bytes as stb_image's decoder), TGA, OpenEXR scan lines (none /
+ * (same bytes as stb_image's decoder), TGA, BMP, OpenEXR scan lines (none /
  * ZIPS / ZIP; half and float), Radiance HDR, the reference's PFM variant — as ImagePool::load_data uses them (image_pool.cxx:271-383): rows in file order,
  * RGBA8 (*eight_bit = 1; the file's values, no sRGB step) or RGBA32F.  pixels = NULL queries the size. */
 int etxb_image_file_read(const char* file_name, uint32_t* width, uint32_t* height, uint32_t* eight_bit, void* pixels, uint64_t capacity, char* err, uint64_t err_bytes);

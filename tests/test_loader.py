@@ -1325,3 +1325,47 @@ def test_tga_textures_decode_like_the_reference(ref, tmp_path, form, load):
     problems = compare_scenes(rs, sd)
     assert not problems, problems
     rs.close()
+
+
+BMP_FORMS = ["rgb24", "rgba32", "palette8", "one_bit", "x555", "rgb565_top_down", "rgb32_zero_alpha"]
+
+
+@pytest.mark.parametrize("form", BMP_FORMS)
+def test_bmp_textures_decode_like_the_reference(ref, tmp_path, form, load):
+    """.bmp textures the way stb_image reads them: 24 / 32 bits, palettes of 8 and 1 bit, 16 bits through the default x555 masks and through BI_BITFIELDS 565
+    (channels widened by bit replication), top-down rows, and a 32-bit file whose alpha bytes are all zero (opaque)."""
+    import struct
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(BMP_FORMS.index(form))
+    h, w = 7, 9
+    a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    file = str(tmp_path / "albedo.bmp")
+
+    def write(bpp, rows, compress=0, masks=b"", top_down=False):
+        body = b"".join(r + b"\0" * ((-len(r)) & 3) for r in rows)
+        off = 14 + 40 + len(masks)
+        open(file, "wb").write(b"BM" + struct.pack("<IHHI", off + len(body), 0, 0, off) + struct.pack("<IiiHHIIiiII", 40, w, -h if top_down else h, 1, bpp, compress, len(body), 2835, 2835, 0, 0) +
+                               masks + body)
+    if form == "rgb24":
+        Image.fromarray(a[..., :3]).save(file)
+    elif form == "rgba32":
+        Image.fromarray(a).save(file)
+    elif form == "palette8":
+        Image.fromarray(a[..., :3]).quantize(16).save(file)
+    elif form == "one_bit":
+        Image.fromarray(a[..., 0] > 127).convert("1").save(file)
+    elif form == "x555":
+        write(16, [rng.integers(0, 65536, w, dtype=np.uint16).tobytes() for _ in range(h)])
+    elif form == "rgb565_top_down":
+        write(16, [rng.integers(0, 65536, w, dtype=np.uint16).tobytes() for _ in range(h)], compress=3, masks=struct.pack("<III", 0xF800, 0x07E0, 0x001F), top_down=True)
+    else:
+        write(32, [(rng.integers(0, 2 ** 32, w, dtype=np.uint32) & 0x00ffffff).astype(np.uint32).tobytes() for _ in range(h)])
+    obj = OBJ.replace("vn 0 1 0\n", "vn 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\n").replace("f 1//1 4//1 3//1 2//1", "f 1/1/1 4/4/1 3/3/1 2/2/1")
+    path = _write_scene(tmp_path, obj=obj, mtl=MTL.replace("newmtl Floor\n", "newmtl Floor\nmap_Kd albedo.bmp\n"))
+    rs = ref(path)
+    sd = load(path)
+    ia = _view(rs.scene["images"], S.IMAGE)
+    assert tuple(ia[1]["isize"]) == (w, h) and int(ia[1]["format"]) == 2, "the reference decoded the file (not its 1 x 1 placeholder)"
+    problems = compare_scenes(rs, sd)
+    assert not problems, problems
+    rs.close()
