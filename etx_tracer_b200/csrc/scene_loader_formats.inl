@@ -303,6 +303,201 @@ float half_to_float(uint16_t h) {
   return f;
 }
 
+// One PIZ-compressed block of an OpenEXR file (ImfPizCompressor, as tinyexr's DecompressPiz :9508-9620 reads it): a bitmap of the 16-bit values that
+// occur -> a lookup table; the table indices, wavelet-transformed per channel plane (14- or 16-bit lifting, ImfWav), Huffman-coded with run lengths
+// (ImfHuf: 6-bit packed code lengths, canonical codes, the last symbol = "repeat the previous word n times").  Output: the block's scan lines, every
+// channel's row in turn, native 16-bit words.
+namespace piz {
+
+inline void lift14(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
+  const int hi = int16_t(h), ai = int16_t(l) + (hi & 1) + (hi >> 1);
+  a = uint16_t(int16_t(ai)), b = uint16_t(int16_t(ai - hi));
+}
+inline void lift16(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
+  const int m = l, d = h, bb = (m - (d >> 1)) & 0xffff, aa = (d + bb - 0x8000) & 0xffff;
+  b = uint16_t(bb), a = uint16_t(aa);
+}
+
+void wavelet_decode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t max_value) {
+  const bool narrow = max_value < (1 << 14);
+  const int n = std::min(nx, ny);
+  int p = 1;
+  while (p <= n) p <<= 1;
+  p >>= 1;
+  int p2 = p;
+  p >>= 1;
+  auto lift = [&](uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) { narrow ? lift14(l, h, a, b) : lift16(l, h, a, b); };
+  while (p >= 1) {
+    uint16_t* py = in;
+    uint16_t* const ey = in + ptrdiff_t(oy) * (ny - p2);
+    const int oy1 = oy * p, oy2 = oy * p2, ox1 = ox * p, ox2 = ox * p2;
+    uint16_t i00, i01, i10, i11;
+    for (; py <= ey; py += oy2) {
+      uint16_t* px = py;
+      uint16_t* const ex = py + ptrdiff_t(ox) * (nx - p2);
+      for (; px <= ex; px += ox2) {
+        uint16_t *p01 = px + ox1, *p10 = px + oy1, *p11 = p10 + ox1;
+        lift(*px, *p10, i00, i10);
+        lift(*p01, *p11, i01, i11);
+        lift(i00, i01, *px, *p01);
+        lift(i10, i11, *p10, *p11);
+      }
+      if (nx & p) {
+        uint16_t* p10 = px + oy1;
+        lift(*px, *p10, i00, *p10);
+        *px = i00;
+      }
+    }
+    if (ny & p) {
+      uint16_t* px = py;
+      uint16_t* const ex = py + ptrdiff_t(ox) * (nx - p2);
+      for (; px <= ex; px += ox2) {
+        uint16_t* p01 = px + ox1;
+        lift(*px, *p01, i00, *p01);
+        *px = i00;
+      }
+    }
+    p2 = p;
+    p >>= 1;
+  }
+}
+
+struct Bits {
+  const uint8_t* in;
+  size_t size, pos = 0;
+  uint64_t c = 0;
+  int lc = 0;
+  uint32_t get(int n) {
+    while (lc < n) {
+      c = (c << 8) | (pos < size ? in[pos] : 0u);
+      ++pos;
+      lc += 8;
+    }
+    lc -= n;
+    return uint32_t((c >> lc) & ((1ull << n) - 1ull));
+  }
+};
+
+bool huffman_decode(const uint8_t* in, size_t size, std::vector<uint16_t>& out, size_t expected) {
+  constexpr int kSymbols = (1 << 16) + 1;
+  if (size < 20) return false;
+  auto u32 = [&](size_t at) { return uint32_t(in[at]) | (uint32_t(in[at + 1]) << 8) | (uint32_t(in[at + 2]) << 16) | (uint32_t(in[at + 3]) << 24); };
+  const int im = int(u32(0)), iM = int(u32(4));
+  const uint64_t n_bits = u32(12);
+  if (im < 0 || im >= kSymbols || iM < 0 || iM >= kSymbols || im > iM) return false;
+  std::vector<uint8_t> length(kSymbols, 0);
+  Bits table{in + 20, size - 20};
+  for (int i = im; i <= iM; ++i) {  // packed code lengths: 0..58, 59..62 = 2..5 zeros, 63 = 6 + (8 bits) zeros
+    if (table.pos > table.size) return false;
+    const uint32_t l = table.get(6);
+    if (l == 63u || l >= 59u) {
+      int zeros = (l == 63u) ? int(table.get(8)) + 6 : int(l) - 59 + 2;
+      if (i + zeros > iM + 1) return false;
+      i += zeros - 1;
+    } else {
+      length[i] = uint8_t(l);
+    }
+  }
+  const size_t data_at = 20 + table.pos;
+  if (data_at > size || n_bits > 8ull * (size - data_at)) return false;
+  // canonical codes: counted per length, the longest lengths take the smallest code values, symbols of one length in increasing order
+  uint64_t count[59] = {}, base[59] = {};
+  for (int i = 0; i < kSymbols; ++i) count[length[i]] += 1;
+  {
+    uint64_t c = 0;
+    for (int l = 58; l > 0; --l) {
+      const uint64_t next = (c + count[l]) >> 1;
+      base[l] = c;
+      c = next;
+    }
+  }
+  std::vector<uint32_t> start(60, 0), order;
+  for (int l = 1; l <= 58; ++l) start[l + 1] = start[l] + uint32_t(count[l]);
+  order.assign(start[59], 0);
+  {
+    std::vector<uint32_t> fill(start.begin(), start.end());
+    for (int i = 0; i < kSymbols; ++i)
+      if (length[i]) order[fill[length[i]]++] = uint32_t(i);
+  }
+  out.clear();
+  out.reserve(expected);
+  Bits data{in + data_at, size - data_at};
+  uint64_t used = 0;
+  while (used < n_bits) {
+    uint64_t code = 0;
+    int l = 0;
+    uint32_t symbol = 0;
+    bool found = false;
+    while (l < 58 && used < n_bits) {
+      code = (code << 1) | data.get(1);
+      ++l, ++used;
+      if (count[l] && code >= base[l] && code < base[l] + count[l]) {
+        symbol = order[start[l] + uint32_t(code - base[l])];
+        found = true;
+        break;
+      }
+    }
+    if (!found) return used >= n_bits && out.size() == expected;  // trailing pad bits
+    if (int(symbol) == iM) {
+      if (used + 8 > n_bits || out.empty()) return false;
+      const uint32_t repeat = data.get(8);
+      used += 8;
+      if (out.size() + repeat > expected) return false;
+      out.insert(out.end(), repeat, out.back());
+    } else {
+      if (out.size() >= expected) return false;
+      out.push_back(uint16_t(symbol));
+    }
+  }
+  return out.size() == expected;
+}
+
+// `words_per_pixel[c]` = 1 for a half channel, 2 for float / uint
+bool decode_block(const uint8_t* in, size_t size, const std::vector<int>& words_per_pixel, int width, int lines, std::vector<uint8_t>& raw) {
+  size_t total_words = 0;
+  for (int wpp : words_per_pixel) total_words += size_t(width) * lines * wpp;
+  if (size < 4) return false;
+  const uint32_t min_nz = in[0] | (in[1] << 8), max_nz = in[2] | (in[3] << 8);
+  size_t at = 4;
+  std::vector<uint8_t> bitmap(8192, 0);
+  if (max_nz >= 8192) return false;
+  if (min_nz <= max_nz) {
+    if (at + (max_nz - min_nz + 1) > size) return false;
+    memcpy(bitmap.data() + min_nz, in + at, max_nz - min_nz + 1);
+    at += max_nz - min_nz + 1;
+  }
+  std::vector<uint16_t> lut(65536, 0);
+  int k = 0;
+  for (int i = 0; i < 65536; ++i)
+    if (i == 0 || (bitmap[i >> 3] & (1 << (i & 7)))) lut[k++] = uint16_t(i);
+  const uint16_t max_value = uint16_t(k - 1);
+  if (at + 4 > size) return false;
+  const uint32_t length = uint32_t(in[at]) | (uint32_t(in[at + 1]) << 8) | (uint32_t(in[at + 2]) << 16) | (uint32_t(in[at + 3]) << 24);
+  at += 4;
+  if (at + length > size) return false;
+  std::vector<uint16_t> words;
+  if (!huffman_decode(in + at, length, words, total_words)) return false;
+  size_t plane = 0;
+  std::vector<size_t> begin;
+  for (int wpp : words_per_pixel) {
+    begin.push_back(plane);
+    for (int j = 0; j < wpp; ++j) wavelet_decode(words.data() + plane + j, width, wpp, lines, width * wpp, max_value);
+    plane += size_t(width) * lines * wpp;
+  }
+  for (uint16_t& w : words) w = lut[w];
+  raw.resize(total_words * 2);
+  size_t o = 0;
+  for (int y = 0; y < lines; ++y)
+    for (size_t c = 0; c < words_per_pixel.size(); ++c) {
+      const size_t n = size_t(width) * words_per_pixel[c];
+      memcpy(raw.data() + o, words.data() + begin[c] + size_t(y) * n, n * 2);
+      o += n * 2;
+    }
+  return true;
+}
+
+}  // namespace piz
+
 Pixels read_exr(const std::string& path) {
   std::string d = read_file(path);
   const uint8_t* b = reinterpret_cast<const uint8_t*>(d.data());
@@ -326,7 +521,7 @@ Pixels read_exr(const std::string& path) {
   if (!attrs.count("compression") || !attrs.count("dataWindow") || !attrs.count("channels")) fail(path + ": incomplete EXR header");
   if (attrs["compression"].empty() || attrs["dataWindow"].size() < 16) fail(path + ": incomplete EXR header");
   int comp = uint8_t(attrs["compression"][0]);
-  if (comp != 0 && comp != 1 && comp != 2 && comp != 3) fail(path + ": this EXR compression is not read (none / RLE / ZIPS / ZIP are)");
+  if (comp < 0 || comp > 4) fail(path + ": this EXR compression is not read (none / RLE / ZIPS / ZIP / PIZ are)");
   int32_t win[4];
   memcpy(win, attrs["dataWindow"].data(), 16);
   const uint32_t w = uint32_t(win[2] - win[0] + 1), h = uint32_t(win[3] - win[1] + 1);
@@ -342,7 +537,7 @@ Pixels read_exr(const std::string& path) {
     types.push_back(t);
     cp = e + 17;
   }
-  const uint32_t lines = (comp == 3) ? 16u : 1u, blocks = (h + lines - 1) / lines;
+  const uint32_t lines = (comp == 3) ? 16u : ((comp == 4) ? 32u : 1u), blocks = (h + lines - 1) / lines;
   size_t bytes_per_pixel = 0;
   for (int t : types) bytes_per_pixel += (t == 1) ? 2 : 4;
   // a header is only believed as far as the file can back it: a deflate stream expands at most ~1032 : 1
@@ -363,7 +558,11 @@ Pixels read_exr(const std::string& path) {
     const size_t want = size_t(nl) * w * bytes_per_pixel;
     std::vector<uint8_t> raw;
     if (size > d.size() - size_t(off) - 8) fail(path + ": truncated EXR block");
-    if (comp != 0 && size < want) {
+    if (comp == 4 && size < want) {
+      std::vector<int> words_per_pixel;
+      for (int t : types) words_per_pixel.push_back(t == 1 ? 1 : 2);
+      if (!piz::decode_block(b + off + 8, size, words_per_pixel, int(w), int(nl), raw)) fail(path + ": corrupt PIZ block in the EXR file");
+    } else if (comp != 0 && size < want) {
       std::vector<uint8_t> z;
       if (comp == 1) {  // run lengths: a negative count copies that many bytes, any other repeats the next byte count + 1 times
         const uint8_t* in = b + off + 8;

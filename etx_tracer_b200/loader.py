@@ -489,7 +489,7 @@ def read_image(path):
         try:
             return _read_exr(path), False
         except LoaderError:
-            from . import api  # run-length encoded blocks: the module's reader
+            from . import api  # run-length encoded and PIZ blocks: the module's reader
             try:
                 return api.read_image(path), False
             except api.EtxbError as e:

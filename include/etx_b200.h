@@ -376,7 +376,7 @@ int etxb_scene_file_commit(etxb_ctx* ctx, const etxb_scene_file* sf);
 int etxb_options_file_string(const char* file_name, const char* id, char* out, uint64_t out_bytes);
 /* The loader's image readers on their own — every PNG form stb_image decodes (bit depths 1-16, palette, colour keys, Adam7), baseline / progressive JPEG
  * (same bytes as stb_image's decoder), TGA, BMP, OpenEXR scan lines (none /
- * ZIPS / ZIP; half and float), Radiance HDR, the reference's PFM variant — as ImagePool::load_data uses them (image_pool.cxx:271-383): rows in file order,
+ * RLE / ZIPS / ZIP / PIZ; half and float), Radiance HDR, the reference's PFM variant — as ImagePool::load_data uses them (image_pool.cxx:271-383): rows in file order,
  * RGBA8 (*eight_bit = 1; the file's values, no sRGB step) or RGBA32F.  pixels = NULL queries the size. */
 int etxb_image_file_read(const char* file_name, uint32_t* width, uint32_t* height, uint32_t* eight_bit, void* pixels, uint64_t capacity, char* err, uint64_t err_bytes);
 /* Two parts of the loader on their own.  etxb_mesh_tangents: the tangent-space generator the reference calls for meshes with texture coordinates
