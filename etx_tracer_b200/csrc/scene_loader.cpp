@@ -8,12 +8,20 @@
 // MediumPool / SceneLoaderContext::add_medium (scene_data.hxx:125-147) — for the `.json` + `.obj` + `.mtl` dialect.  The .mtl reader follows the
 // reference's patched tinyobjloader (thirdparty/tinyobjloader/tiny_obj_loader.hxx:1900-2190, quads :1464-1527).
 //
-// tests/test_loader.py loads the same files with the reference's OWN loader (compiled in place, test infrastructure) and compares array by array.
-// Tangent frames of meshes with texture coordinates: scene_loader_tangents.inl (the tangent-space generator the reference calls, restated; identical
-// but for the few corners its unsorted final edge run touches).  NanoVDB volumes: scene_loader_nvdb.inl.  Refused with a message: glTF (DESIGN.md 10 says why).  The atmosphere (`et::atmosphere`, and the default one of a file without distant emitters; render/host/scattering.cxx) is
-// generated by scene_loader_atmosphere.inl.  The data tables the reference derives at start-up (CIE / RGB-response tables,
-// the IOR database resampled to the 1 nm grid, the three atmosphere spectra) ship as etx_tracer_b200/data/tables.bin (tools/make_data.py).
-// etx_tracer_b200/loader.py is the same loader in Python (the executable specification this file was checked against).
+// tests/test_loader.py loads the same files with the reference's OWN loader (compiled in place, test infrastructure) and compares array by array —
+// hand-written scenes, the shipped Cornell asset, and seeded random material / geometry files.
+// Parts (each .inl is included below, inside this file's anonymous namespace):
+//   scene_loader_formats.inl     DEFLATE, PNG (every form stb_image decodes), TGA, BMP, OpenEXR scan lines (none / RLE / ZIPS / ZIP / PIZ), Radiance HDR,
+//                                the reference's PFM variant, JSON, the .mtl / .obj dialect of the patched tinyobjloader (ear-clipped polygons)
+//   scene_loader_jpeg.inl        baseline / progressive JPEG with stb_image's IDCT, upsampling and colour conversion (same bytes)
+//   scene_loader_tangents.inl    the tangent-space generator the reference calls for meshes with texture coordinates (identical frames)
+//   scene_loader_nvdb.inl        NanoVDB 32.x float grids -> the dense grid of a heterogeneous medium
+//   scene_loader_atmosphere.inl  `et::atmosphere`, and the default sun + sky of a file without distant emitters (render/host/scattering.cxx)
+//   scene_loader_build.inl       the directives -> Scene / Camera PODs
+// Refused with a message: glTF (DESIGN.md 10 says why), BLOSC-compressed volumes.  Textures in a format that is not read (GIF, PSD, CMYK JPEG, lossy EXR
+// codecs) become the 1 x 1 white placeholder the reference uses for files it cannot read.  The data tables the reference derives at start-up (CIE /
+// RGB-response tables, the IOR database on the 1 nm grid, the atmosphere spectra, blue-noise tiles) ship as etx_tracer_b200/data/tables.bin
+// (tools/make_tables_bin.py).  etx_tracer_b200/loader.py is the same loader in Python, sharing the readers above through the C ABI.
 #include <algorithm>
 #include <atomic>
 #include <cfloat>
